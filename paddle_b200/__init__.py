@@ -1,0 +1,33 @@
+"""paddle_b200 — a Blackwell(B200)-native deep-learning framework with the PaddlePaddle API surface.
+
+``import paddle_b200 as paddle`` gives the reference's public namespace (python/paddle/__init__.py): Tensor, ops,
+nn, optimizer, amp, io, jit, distributed (+fleet), vision, ... backed by PyTorch tensors/autograd for the plumbing
+and hand-written sm_100a CUDA kernels (``paddle_b200/csrc``) for the hot paths.
+"""
+from __future__ import annotations
+
+__version__ = "0.1.0"
+
+import torch as _torch
+
+from .framework import dtype as _dtype_mod
+from .framework.dtype import (bfloat16, bool, complex64, complex128, dtype, finfo, float8_e4m3fn, float8_e5m2,  # noqa: A004,F401
+                              float16, float32, float64, get_default_dtype, iinfo, int8, int16, int32, int64,
+                              set_default_dtype, uint8)
+from .framework.flags import get_flags, set_flags  # noqa: F401
+from .framework.place import (CPUPlace, CUDAPinnedPlace, CUDAPlace, Place, get_device, is_compiled_with_cinn,  # noqa: F401
+                              is_compiled_with_cuda, is_compiled_with_custom_device, is_compiled_with_distribute,
+                              is_compiled_with_rocm, is_compiled_with_xpu, set_device)
+from .framework.random import get_cuda_rng_state, get_rng_state, seed, set_cuda_rng_state, set_rng_state  # noqa: F401
+from .tensor import Parameter, Tensor, is_tensor, to_tensor  # noqa: F401
+from . import ops as _ops
+from .ops import *  # noqa: F401,F403
+from .ops import linalg as _linalg_ops  # noqa: F401
+from . import autograd  # noqa: F401
+from .autograd import PyLayer, enable_grad, grad, is_grad_enabled, no_grad, set_grad_enabled  # noqa: F401
+
+half = float16
+float = float32  # noqa: A001
+double = float64
+int = int32  # noqa: A001
+long = int64

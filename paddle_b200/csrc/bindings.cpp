@@ -1,0 +1,401 @@
+// pybind11 bindings: at::Tensor <-> plain-C launch API (include/b200_ops.h). The only TU that includes torch headers.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <atomic>
+#include <optional>
+
+#include "include/b200_ops.h"
+#include "runtime/runtime.h"
+
+namespace {
+
+std::atomic<int64_t> g_launches{0};
+
+using torch::Tensor;
+using OptT = std::optional<Tensor>;
+
+int dt_code(const Tensor& t) {
+  switch (t.scalar_type()) {
+    case at::kFloat: return 0;
+    case at::kHalf: return 1;
+    case at::kBFloat16: return 2;
+    default: TORCH_CHECK(false, "paddle_b200: unsupported dtype ", t.scalar_type());
+  }
+}
+int dt_code(at::ScalarType st) {
+  switch (st) {
+    case at::kFloat: return 0;
+    case at::kHalf: return 1;
+    case at::kBFloat16: return 2;
+    default: TORCH_CHECK(false, "paddle_b200: unsupported dtype ", st);
+  }
+}
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+void check_err() {
+  const char* e = b200::take_last_error();
+  TORCH_CHECK(e[0] == 0, "paddle_b200 kernel error: ", e);
+}
+const void* optp(const OptT& t) { return t.has_value() && t->defined() ? t->data_ptr() : nullptr; }
+void check_cuda_contig(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+}
+
+// ------------------------------------------------------------------------------------------------ norm
+std::vector<Tensor> rms_norm_fwd(const Tensor& x, const OptT& residual, const OptT& w, const OptT& b, double eps) {
+  check_cuda_contig(x, "x");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int cols = (int)x.size(-1);
+  const int64_t rows = x.numel() / cols;
+  Tensor y = torch::empty_like(x);
+  Tensor rstd = torch::empty({rows}, x.options().dtype(at::kFloat));
+  Tensor res_out;
+  if (residual.has_value() && residual->defined()) res_out = torch::empty_like(x);
+  b200::rms_norm_fwd(x.data_ptr(), optp(residual), optp(w), optp(b), y.data_ptr(), res_out.defined() ? res_out.data_ptr() : nullptr,
+                     rstd.data_ptr<float>(), rows, cols, (float)eps, dt_code(x), cur_stream());
+  g_launches += 1;
+  check_err();
+  return {y, rstd, res_out.defined() ? res_out : Tensor()};
+}
+
+std::vector<Tensor> rms_norm_bwd(const Tensor& dy, const Tensor& x, const OptT& w, const Tensor& rstd) {
+  check_cuda_contig(dy, "dy");
+  check_cuda_contig(x, "x");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int cols = (int)x.size(-1);
+  const int64_t rows = x.numel() / cols;
+  Tensor dx = torch::empty_like(x);
+  const bool has_w = w.has_value() && w->defined();
+  const int np = b200::norm_bwd_num_partials(rows);
+  Tensor dwp, dw;
+  if (has_w) dwp = torch::empty({np, cols}, x.options().dtype(at::kFloat));
+  b200::rms_norm_bwd(dy.data_ptr(), x.data_ptr(), optp(w), rstd.data_ptr<float>(), dx.data_ptr(),
+                     has_w ? dwp.data_ptr<float>() : nullptr, nullptr, rows, cols, dt_code(x), np, cur_stream());
+  g_launches += 1;
+  if (has_w) {
+    dw = torch::empty_like(*w);
+    b200::reduce_partials(dwp.data_ptr<float>(), dw.data_ptr(), np, cols, dt_code(*w), cur_stream());
+    g_launches += 1;
+  }
+  check_err();
+  return {dx, dw};
+}
+
+std::vector<Tensor> layer_norm_fwd(const Tensor& x, const OptT& w, const OptT& b, double eps) {
+  check_cuda_contig(x, "x");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int cols = (int)x.size(-1);
+  const int64_t rows = x.numel() / cols;
+  Tensor y = torch::empty_like(x);
+  Tensor mean = torch::empty({rows}, x.options().dtype(at::kFloat));
+  Tensor rstd = torch::empty({rows}, x.options().dtype(at::kFloat));
+  b200::layer_norm_fwd(x.data_ptr(), optp(w), optp(b), y.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(), rows, cols,
+                       (float)eps, dt_code(x), cur_stream());
+  g_launches += 1;
+  check_err();
+  return {y, mean, rstd};
+}
+
+std::vector<Tensor> layer_norm_bwd(const Tensor& dy, const Tensor& x, const OptT& w, const Tensor& mean, const Tensor& rstd, bool need_db) {
+  check_cuda_contig(dy, "dy");
+  check_cuda_contig(x, "x");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int cols = (int)x.size(-1);
+  const int64_t rows = x.numel() / cols;
+  Tensor dx = torch::empty_like(x);
+  const int np = b200::norm_bwd_num_partials(rows);
+  Tensor dwp = torch::empty({np, cols}, x.options().dtype(at::kFloat));
+  Tensor dbp = torch::empty({np, cols}, x.options().dtype(at::kFloat));
+  b200::layer_norm_bwd(dy.data_ptr(), x.data_ptr(), optp(w), mean.data_ptr<float>(), rstd.data_ptr<float>(), dx.data_ptr(),
+                       dwp.data_ptr<float>(), dbp.data_ptr<float>(), rows, cols, dt_code(x), np, cur_stream());
+  auto pdt = (w.has_value() && w->defined()) ? w->scalar_type() : x.scalar_type();
+  Tensor dw = torch::empty({cols}, x.options().dtype(pdt));
+  Tensor db = torch::empty({cols}, x.options().dtype(pdt));
+  b200::reduce_partials(dwp.data_ptr<float>(), dw.data_ptr(), np, cols, dt_code(pdt), cur_stream());
+  b200::reduce_partials(dbp.data_ptr<float>(), db.data_ptr(), np, cols, dt_code(pdt), cur_stream());
+  g_launches += 3;
+  check_err();
+  return {dx, dw, db};
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise
+Tensor swiglu_fwd(const Tensor& gate, const OptT& up) {
+  check_cuda_contig(gate, "gate");
+  c10::cuda::CUDAGuard guard(gate.device());
+  const bool packed = !(up.has_value() && up->defined());
+  const int cols = packed ? (int)gate.size(-1) / 2 : (int)gate.size(-1);
+  const int64_t rows = gate.numel() / gate.size(-1);
+  auto sizes = gate.sizes().vec();
+  sizes.back() = cols;
+  Tensor out = torch::empty(sizes, gate.options());
+  b200::swiglu_fwd(gate.data_ptr(), optp(up), out.data_ptr(), rows, cols, dt_code(gate), cur_stream());
+  g_launches += 1;
+  check_err();
+  return out;
+}
+
+std::vector<Tensor> swiglu_bwd(const Tensor& dout, const Tensor& gate, const OptT& up) {
+  check_cuda_contig(dout, "dout");
+  c10::cuda::CUDAGuard guard(gate.device());
+  const bool packed = !(up.has_value() && up->defined());
+  const int cols = packed ? (int)gate.size(-1) / 2 : (int)gate.size(-1);
+  const int64_t rows = gate.numel() / gate.size(-1);
+  Tensor dgate = torch::empty_like(gate);
+  Tensor dup;
+  if (!packed) dup = torch::empty_like(*up);
+  b200::swiglu_bwd(dout.data_ptr(), gate.data_ptr(), optp(up), dgate.data_ptr(), packed ? nullptr : dup.data_ptr(), rows, cols,
+                   dt_code(gate), cur_stream());
+  g_launches += 1;
+  check_err();
+  return {dgate, dup};
+}
+
+Tensor rope(const Tensor& x, const Tensor& cos_t, const Tensor& sin_t, const OptT& pos_ids, int64_t seq, bool neox, bool backward) {
+  check_cuda_contig(x, "x");
+  TORCH_CHECK(x.dim() >= 3, "rope expects [..., seq, heads, dim]");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int dim = (int)x.size(-1), heads = (int)x.size(-2);
+  const int64_t tokens = x.numel() / ((int64_t)dim * heads);
+  Tensor y = torch::empty_like(x);
+  const int64_t* pid = nullptr;
+  Tensor pos;
+  if (pos_ids.has_value() && pos_ids->defined()) {
+    pos = pos_ids->to(at::kLong).contiguous();
+    pid = pos.data_ptr<int64_t>();
+  }
+  b200::rope_apply(x.data_ptr(), y.data_ptr(), cos_t.data_ptr<float>(), sin_t.data_ptr<float>(), pid, tokens, (int)seq, heads, dim,
+                   neox ? 1 : 0, backward ? 1 : 0, dt_code(x), cur_stream());
+  g_launches += 1;
+  check_err();
+  return y;
+}
+
+// ------------------------------------------------------------------------------------------------ loss
+std::vector<Tensor> softmax_ce_fwd(const Tensor& logits, const Tensor& labels, int64_t ignore_index) {
+  check_cuda_contig(logits, "logits");
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int vocab = (int)logits.size(-1);
+  const int64_t rows = logits.numel() / vocab;
+  Tensor lab = labels.to(at::kLong).contiguous();
+  Tensor loss = torch::empty({rows}, logits.options().dtype(at::kFloat));
+  Tensor lse = torch::empty({rows}, logits.options().dtype(at::kFloat));
+  b200::softmax_ce_fwd(logits.data_ptr(), lab.data_ptr<int64_t>(), loss.data_ptr<float>(), lse.data_ptr<float>(), rows, vocab,
+                       ignore_index, dt_code(logits), cur_stream());
+  g_launches += 1;
+  check_err();
+  return {loss, lse};
+}
+
+Tensor softmax_ce_bwd(const Tensor& logits, const Tensor& labels, const Tensor& lse, const Tensor& dloss, int64_t ignore_index, bool inplace) {
+  check_cuda_contig(logits, "logits");
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int vocab = (int)logits.size(-1);
+  const int64_t rows = logits.numel() / vocab;
+  Tensor lab = labels.to(at::kLong).contiguous();
+  Tensor dl = dloss.to(at::kFloat).contiguous();
+  Tensor out = inplace ? logits : torch::empty_like(logits);
+  b200::softmax_ce_bwd(logits.data_ptr(), lab.data_ptr<int64_t>(), lse.data_ptr<float>(), dl.data_ptr<float>(), out.data_ptr(), rows,
+                       vocab, ignore_index, dt_code(logits), cur_stream());
+  g_launches += 1;
+  check_err();
+  return out;
+}
+
+Tensor vp_ce_max(const Tensor& logits) {
+  check_cuda_contig(logits, "logits");
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int vocab = (int)logits.size(-1);
+  const int64_t rows = logits.numel() / vocab;
+  Tensor mx = torch::empty({rows}, logits.options().dtype(at::kFloat));
+  b200::vocab_parallel_ce_stats(logits.data_ptr(), nullptr, mx.data_ptr<float>(), rows, vocab, dt_code(logits), cur_stream());
+  g_launches += 1;
+  check_err();
+  return mx;
+}
+
+std::vector<Tensor> vp_ce_sumexp(const Tensor& logits, const Tensor& labels, const Tensor& row_max, int64_t vocab_start) {
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int vocab = (int)logits.size(-1);
+  const int64_t rows = logits.numel() / vocab;
+  Tensor lab = labels.to(at::kLong).contiguous();
+  Tensor se = torch::empty({rows}, logits.options().dtype(at::kFloat));
+  Tensor tl = torch::empty({rows}, logits.options().dtype(at::kFloat));
+  b200::vocab_parallel_ce_sumexp(logits.data_ptr(), lab.data_ptr<int64_t>(), row_max.data_ptr<float>(), se.data_ptr<float>(),
+                                 tl.data_ptr<float>(), rows, vocab, vocab_start, dt_code(logits), cur_stream());
+  g_launches += 1;
+  check_err();
+  return {se, tl};
+}
+
+Tensor vp_ce_bwd(const Tensor& logits, const Tensor& labels, const Tensor& row_max, const Tensor& sumexp, const Tensor& dloss,
+                 int64_t vocab_start, int64_t ignore_index, bool inplace) {
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int vocab = (int)logits.size(-1);
+  const int64_t rows = logits.numel() / vocab;
+  Tensor lab = labels.to(at::kLong).contiguous();
+  Tensor dl = dloss.to(at::kFloat).contiguous();
+  Tensor out = inplace ? logits : torch::empty_like(logits);
+  b200::vocab_parallel_ce_bwd(logits.data_ptr(), lab.data_ptr<int64_t>(), row_max.data_ptr<float>(), sumexp.data_ptr<float>(),
+                              dl.data_ptr<float>(), out.data_ptr(), rows, vocab, vocab_start, ignore_index, dt_code(logits), cur_stream());
+  g_launches += 1;
+  check_err();
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------ optimizer
+void adamw_step(Tensor p, const Tensor& g, const OptT& master, Tensor m, Tensor v, double lr, double beta1, double beta2, double eps,
+                double weight_decay, int64_t step, const OptT& grad_sq_norm, double max_norm, const OptT& found_inf, const OptT& inv_scale) {
+  check_cuda_contig(p, "param");
+  check_cuda_contig(g, "grad");
+  c10::cuda::CUDAGuard guard(p.device());
+  b200::AdamWArgs a;
+  a.lr = (float)lr; a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps; a.weight_decay = (float)weight_decay;
+  a.bias_c1 = (float)(1.0 - std::pow(beta1, (double)step));
+  a.bias_c2 = (float)(1.0 - std::pow(beta2, (double)step));
+  a.grad_sq_norm = (const float*)optp(grad_sq_norm);
+  a.max_norm = (float)max_norm;
+  a.found_inf = (const float*)optp(found_inf);
+  a.inv_scale = (const float*)optp(inv_scale);
+  float* mp = master.has_value() && master->defined() ? master->data_ptr<float>() : nullptr;
+  b200::adamw_step(p.data_ptr(), g.data_ptr(), mp, m.data_ptr(), v.data_ptr(), p.numel(), dt_code(p), dt_code(g), dt_code(m), a, cur_stream());
+  g_launches += 1;
+  check_err();
+}
+
+void grad_sq_norm(const Tensor& g, Tensor out, const OptT& found_inf) {
+  check_cuda_contig(g, "grad");
+  c10::cuda::CUDAGuard guard(g.device());
+  float* fi = found_inf.has_value() && found_inf->defined() ? found_inf->data_ptr<float>() : nullptr;
+  b200::grad_sq_norm(g.data_ptr(), g.numel(), dt_code(g), out.data_ptr<float>(), fi, cur_stream());
+  g_launches += 1;
+  check_err();
+}
+
+void scale_inplace(Tensor g, const OptT& scale_dev, double scale_host) {
+  check_cuda_contig(g, "tensor");
+  c10::cuda::CUDAGuard guard(g.device());
+  b200::scale_inplace(g.data_ptr(), g.numel(), dt_code(g), (const float*)optp(scale_dev), (float)scale_host, cur_stream());
+  g_launches += 1;
+  check_err();
+}
+
+void sgd_step(Tensor p, const Tensor& g, const OptT& master, const OptT& mom, double lr, double momentum, double wd, bool nesterov) {
+  check_cuda_contig(p, "param");
+  c10::cuda::CUDAGuard guard(p.device());
+  float* mp = master.has_value() && master->defined() ? master->data_ptr<float>() : nullptr;
+  void* mo = mom.has_value() && mom->defined() ? mom->data_ptr() : nullptr;
+  b200::sgd_momentum_step(p.data_ptr(), g.data_ptr(), mp, mo, p.numel(), dt_code(p), dt_code(g), (float)lr, (float)momentum, (float)wd,
+                          nesterov ? 1 : 0, cur_stream());
+  g_launches += 1;
+  check_err();
+}
+
+void lamb_step(Tensor p, const Tensor& g, const OptT& master, Tensor m, Tensor v, double lr, double beta1, double beta2, double eps,
+               double wd, int64_t step) {
+  check_cuda_contig(p, "param");
+  c10::cuda::CUDAGuard guard(p.device());
+  Tensor upd = torch::empty({p.numel()}, p.options().dtype(at::kFloat));
+  Tensor sq = torch::zeros({2}, p.options().dtype(at::kFloat));
+  const float* mp = master.has_value() && master->defined() ? master->data_ptr<float>() : nullptr;
+  b200::lamb_stage1(p.data_ptr(), g.data_ptr(), mp, m.data_ptr(), v.data_ptr(), upd.data_ptr<float>(), p.numel(), dt_code(p), dt_code(g),
+                    (float)beta1, (float)beta2, (float)eps, (float)wd, (float)(1.0 - std::pow(beta1, (double)step)),
+                    (float)(1.0 - std::pow(beta2, (double)step)), sq.data_ptr<float>(), sq.data_ptr<float>() + 1, cur_stream());
+  b200::lamb_stage2(p.data_ptr(), const_cast<float*>(mp), upd.data_ptr<float>(), p.numel(), dt_code(p), (float)lr, sq.data_ptr<float>(),
+                    sq.data_ptr<float>() + 1, cur_stream());
+  g_launches += 2;
+  check_err();
+}
+
+// ------------------------------------------------------------------------------------------------ gemm
+// a: [.., M, K] (or [.., K, M] when a_is_km); b: [.., N, K] when b_is_nk else [.., K, N]. Last-dim stride must be 1.
+bool gemm_supported(const Tensor& a, const Tensor& b, bool a_is_km, bool b_is_nk) {
+  if (!a.is_cuda() || a.scalar_type() != b.scalar_type()) return false;
+  if (a.scalar_type() != at::kBFloat16 && a.scalar_type() != at::kHalf) return false;
+  if (a.dim() < 2 || b.dim() < 2 || a.dim() > 3 || b.dim() != a.dim()) return false;
+  if (a.stride(-1) != 1 || b.stride(-1) != 1) return false;
+  const int64_t m = a_is_km ? a.size(-1) : a.size(-2), k = a_is_km ? a.size(-2) : a.size(-1);
+  const int64_t n = b_is_nk ? b.size(-2) : b.size(-1), kb = b_is_nk ? b.size(-1) : b.size(-2);
+  if (k != kb) return false;
+  if (a.dim() == 3 && (a.size(0) != b.size(0) || a.stride(0) % 8 || b.stride(0) % 8)) return false;
+  if ((reinterpret_cast<uintptr_t>(a.data_ptr()) & 15) || (reinterpret_cast<uintptr_t>(b.data_ptr()) & 15)) return false;
+  return b200::gemm_tcgen05_supported((int)m, (int)n, (int)k, a.stride(-2), b.stride(-2), n, a_is_km, b_is_nk) != 0;
+}
+
+Tensor gemm(const Tensor& a, const Tensor& b, const OptT& bias, bool a_is_km, bool b_is_nk, int64_t epilogue, const OptT& out,
+            const std::optional<at::ScalarType>& out_dtype) {
+  TORCH_CHECK(gemm_supported(a, b, a_is_km, b_is_nk), "paddle_b200.gemm: unsupported operands for the tcgen05 path");
+  c10::cuda::CUDAGuard guard(a.device());
+  b200::GemmArgs g;
+  g.m = (int)(a_is_km ? a.size(-1) : a.size(-2));
+  g.k = (int)(a_is_km ? a.size(-2) : a.size(-1));
+  g.n = (int)(b_is_nk ? b.size(-2) : b.size(-1));
+  g.batch = a.dim() == 3 ? (int)a.size(0) : 1;
+  Tensor d;
+  if (out.has_value() && out->defined()) {
+    d = *out;
+    TORCH_CHECK(d.stride(-1) == 1, "gemm: out must have unit inner stride");
+  } else {
+    auto od = out_dtype.has_value() ? *out_dtype : a.scalar_type();
+    d = g.batch > 1 ? torch::empty({g.batch, g.m, g.n}, a.options().dtype(od)) : torch::empty({g.m, g.n}, a.options().dtype(od));
+  }
+  g.a = a.data_ptr(); g.b = b.data_ptr(); g.d = d.data_ptr();
+  g.bias = optp(bias);
+  g.lda = a.stride(-2); g.ldb = b.stride(-2); g.ldd = d.stride(-2);
+  g.a_is_km = a_is_km; g.b_is_nk = b_is_nk;
+  g.epilogue = (int)epilogue;
+  g.dtype = dt_code(a);
+  g.out_dtype = dt_code(d);
+  g.stride_a = a.dim() == 3 ? a.stride(0) : 0;
+  g.stride_b = b.dim() == 3 ? b.stride(0) : 0;
+  g.stride_d = d.dim() == 3 ? d.stride(0) : 0;
+  if (g.bias) TORCH_CHECK(bias->scalar_type() == a.scalar_type() || bias->scalar_type() == at::kFloat, "gemm: bias dtype");
+  if (g.bias && bias->scalar_type() == at::kFloat && a.scalar_type() != at::kFloat) {
+    // epilogue reads bias in the input dtype
+    Tensor bb = bias->to(a.scalar_type());
+    g.bias = bb.data_ptr();
+    int rc = b200::gemm_tcgen05(g, cur_stream());
+    g_launches += 1;
+    check_err();
+    TORCH_CHECK(rc == 0, "paddle_b200.gemm launch failed rc=", rc);
+    return d;
+  }
+  int rc = b200::gemm_tcgen05(g, cur_stream());
+  g_launches += 1;
+  check_err();
+  TORCH_CHECK(rc == 0, "paddle_b200.gemm launch failed rc=", rc);
+  return d;
+}
+
+int64_t launch_count() { return g_launches.load(); }
+void reset_launch_count() { g_launches.store(0); }
+void add_launches(int64_t n) { g_launches += n; }
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("rms_norm_fwd", &rms_norm_fwd);
+  m.def("rms_norm_bwd", &rms_norm_bwd);
+  m.def("layer_norm_fwd", &layer_norm_fwd);
+  m.def("layer_norm_bwd", &layer_norm_bwd);
+  m.def("swiglu_fwd", &swiglu_fwd);
+  m.def("swiglu_bwd", &swiglu_bwd);
+  m.def("rope", &rope);
+  m.def("softmax_ce_fwd", &softmax_ce_fwd);
+  m.def("softmax_ce_bwd", &softmax_ce_bwd);
+  m.def("vp_ce_max", &vp_ce_max);
+  m.def("vp_ce_sumexp", &vp_ce_sumexp);
+  m.def("vp_ce_bwd", &vp_ce_bwd);
+  m.def("adamw_step", &adamw_step);
+  m.def("grad_sq_norm", &grad_sq_norm);
+  m.def("scale_inplace", &scale_inplace);
+  m.def("sgd_step", &sgd_step);
+  m.def("lamb_step", &lamb_step);
+  m.def("gemm_supported", &gemm_supported);
+  m.def("gemm", &gemm);
+  m.def("launch_count", &launch_count);
+  m.def("reset_launch_count", &reset_launch_count);
+  m.def("add_launches", &add_launches);
+  b200::runtime::bind(m);
+}

@@ -1,0 +1,96 @@
+// Host launch API of the sm_100a kernels. Plain C types only: bindings.cpp adapts at::Tensor to these.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+// last error raised by a launcher on this thread ("" if none); cleared by take_last_error()
+const char* take_last_error();
+
+// ---- norm.cu --------------------------------------------------------------------------------------------------
+// y = x * rsqrt(mean(x^2) + eps) * w (+ b) ; optional fused residual: h = x + residual (h written to res_out)
+void rms_norm_fwd(const void* x, const void* residual, const void* w, const void* b, void* y, void* res_out,
+                  float* rstd, int64_t rows, int cols, float eps, int dtype, cudaStream_t s);
+void rms_norm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, float* dw_partial,
+                  float* db_partial, int64_t rows, int cols, int dtype, int n_partial, cudaStream_t s);
+void layer_norm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t rows,
+                    int cols, float eps, int dtype, cudaStream_t s);
+void layer_norm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
+                    float* dw_partial, float* db_partial, int64_t rows, int cols, int dtype, int n_partial,
+                    cudaStream_t s);
+// out[c] = sum_p partial[p, c]  (fp32 in, `dtype` out)
+void reduce_partials(const float* partial, void* out, int n_partial, int cols, int dtype, cudaStream_t s);
+int norm_bwd_num_partials(int64_t rows);
+
+// ---- elementwise.cu -------------------------------------------------------------------------------------------
+// out = silu(gate) * up. If up == nullptr, x is [rows, 2*cols] packed (gate | up).
+void swiglu_fwd(const void* gate, const void* up, void* out, int64_t rows, int cols, int dtype, cudaStream_t s);
+void swiglu_bwd(const void* dout, const void* gate, const void* up, void* dgate, void* dup, int64_t rows, int cols,
+                int dtype, cudaStream_t s);
+// rotary embedding on [tokens, heads, dim]; cos/sin are fp32 [positions, dim/2]; pos_ids may be null (pos = token % seq)
+void rope_apply(const void* x, void* y, const float* cos_t, const float* sin_t, const int64_t* pos_ids, int64_t tokens,
+                int seq, int heads, int dim, int neox, int backward, int dtype, cudaStream_t s);
+// y = a + b (residual add), vectorised
+void add_fwd(const void* a, const void* b, void* y, int64_t n, int dtype, cudaStream_t s);
+
+// ---- loss.cu --------------------------------------------------------------------------------------------------
+// per-row softmax cross-entropy with integer labels. loss/lse fp32 [rows].
+void softmax_ce_fwd(const void* logits, const int64_t* labels, float* loss, float* lse, int64_t rows, int vocab,
+                    int64_t ignore_index, int dtype, cudaStream_t s);
+// dlogits = (softmax - onehot) * dloss[row]; may alias logits (in-place).
+void softmax_ce_bwd(const void* logits, const int64_t* labels, const float* lse, const float* dloss, void* dlogits,
+                    int64_t rows, int vocab, int64_t ignore_index, int dtype, cudaStream_t s);
+// vocab-parallel pieces (c_softmax_with_cross_entropy): local max / local sumexp+target logit
+void vocab_parallel_ce_stats(const void* logits, const int64_t* labels, float* row_max, int64_t rows, int vocab,
+                             int dtype, cudaStream_t s);
+void vocab_parallel_ce_sumexp(const void* logits, const int64_t* labels, const float* row_max, float* sumexp,
+                              float* target_logit, int64_t rows, int vocab, int64_t vocab_start, int dtype,
+                              cudaStream_t s);
+void vocab_parallel_ce_bwd(const void* logits, const int64_t* labels, const float* row_max, const float* sumexp,
+                           const float* dloss, void* dlogits, int64_t rows, int vocab, int64_t vocab_start,
+                           int64_t ignore_index, int dtype, cudaStream_t s);
+
+// ---- optim.cu -------------------------------------------------------------------------------------------------
+struct AdamWArgs {
+  float lr, beta1, beta2, eps, weight_decay;
+  float bias_c1, bias_c2;      // 1 - beta^t
+  const float* grad_sq_norm;   // device: global sum of squares (nullptr = no clipping)
+  float max_norm;              // clip threshold (<=0: none)
+  const float* found_inf;      // device flag (nullptr = none): skip update if != 0
+  const float* inv_scale;      // device: 1/loss_scale (nullptr = 1)
+};
+// p (param dtype), g (grad dtype), master fp32 (may be null), m/v in `state_dtype` (fp32 or bf16)
+void adamw_step(void* p, const void* g, float* master, void* m, void* v, int64_t n, int p_dtype, int g_dtype,
+                int state_dtype, const AdamWArgs& a, cudaStream_t s);
+// accumulates sum(g^2) into *out (fp32, must be zeroed by caller) and sets *found_inf if any non-finite
+void grad_sq_norm(const void* g, int64_t n, int dtype, float* out, float* found_inf, cudaStream_t s);
+// g *= *scale_dev (unscale / clip by precomputed coefficient)
+void scale_inplace(void* g, int64_t n, int dtype, const float* scale_dev, float scale_host, cudaStream_t s);
+void sgd_momentum_step(void* p, const void* g, float* master, void* mom, int64_t n, int p_dtype, int g_dtype, float lr,
+                       float momentum, float weight_decay, int nesterov, cudaStream_t s);
+void lamb_stage1(const void* p, const void* g, const float* master, void* m, void* v, float* update, int64_t n,
+                 int p_dtype, int g_dtype, float beta1, float beta2, float eps, float weight_decay, float bias_c1,
+                 float bias_c2, float* p_sq, float* u_sq, cudaStream_t s);
+void lamb_stage2(void* p, float* master, const float* update, int64_t n, int p_dtype, float lr, const float* p_sq,
+                 const float* u_sq, cudaStream_t s);
+
+// ---- gemm_sm100.cu --------------------------------------------------------------------------------------------
+// D[M,N] = A[M,K] * B + bias, all row-major in memory.  b_is_nk: B stored [N,K] (K contiguous) else [K,N].
+// a_is_km: A stored [K,M] (M contiguous) else [M,K].  epilogue: 0 none, 1 bias, 2 bias+gelu, 3 bias+relu, 4 accumulate (D += )
+struct GemmArgs {
+  const void* a; const void* b; void* d; const void* bias;
+  int m, n, k;
+  int64_t lda, ldb, ldd;
+  int a_is_km, b_is_nk;
+  int epilogue;
+  int dtype;       // kF16 / kBF16 inputs
+  int out_dtype;   // kF16 / kBF16 / kF32
+  int batch;       // >1: strided batched
+  int64_t stride_a, stride_b, stride_d;
+};
+// returns 0 on success, nonzero if the shape is unsupported by the tcgen05 path (caller falls back)
+int gemm_tcgen05(const GemmArgs& g, cudaStream_t s);
+int gemm_tcgen05_supported(int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd, int a_is_km, int b_is_nk);
+
+}  // namespace b200

@@ -1,0 +1,11 @@
+#include "runtime.h"
+
+namespace b200 {
+namespace runtime {
+void bind(pybind11::module_& m) {
+  bind_symm(m);
+  bind_loader(m);
+  bind_graph(m);
+}
+}  // namespace runtime
+}  // namespace b200

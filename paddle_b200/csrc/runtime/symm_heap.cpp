@@ -1,0 +1,126 @@
+// Symmetric peer heap: one cudaMalloc'ed slab per rank, IPC-mapped into every peer of the node so kernels can issue
+// ld/st.global straight to peer HBM over NVLink/NVSwitch.  The reference has no direct equivalent (NCCL rings via
+// ProcessGroupNCCL, paddle/fluid/distributed/collective/process_group_nccl.cc); closest is
+// paddle/phi/core/memory/allocation/cuda_ipc_allocator.cc.
+//
+// Layout of the slab: [0, signal_bytes) = signal pad (uint32 flags, zero-initialised) | bump-allocated data region.
+// Allocation is collective and deterministic (same sequence of alloc() calls on every rank => same offsets), which is
+// what makes the heap "symmetric": peer address = peer_base + my_offset.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "runtime.h"
+
+namespace b200 {
+namespace runtime {
+
+namespace {
+void ck(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string("symm_heap: ") + what + ": " + cudaGetErrorString(e));
+}
+}  // namespace
+
+class SymmHeap {
+ public:
+  SymmHeap(int64_t bytes, int64_t signal_bytes, int device) : bytes_(bytes), signal_bytes_(signal_bytes), device_(device) {
+    c10::cuda::CUDAGuard g(device_);
+    ck(cudaMalloc(&base_, bytes_), "cudaMalloc");
+    ck(cudaMemset(base_, 0, bytes_), "cudaMemset");
+    ck(cudaDeviceSynchronize(), "sync");
+    cursor_ = (signal_bytes_ + 1023) / 1024 * 1024;
+  }
+  ~SymmHeap() {
+    for (size_t i = 0; i < peers_.size(); ++i)
+      if (peers_[i] && (int)i != rank_) cudaIpcCloseMemHandle(peers_[i]);
+    if (peer_table_dev_) cudaFree(peer_table_dev_);
+    if (base_) cudaFree(base_);
+  }
+
+  pybind11::bytes ipc_handle() {
+    cudaIpcMemHandle_t h;
+    ck(cudaIpcGetMemHandle(&h, base_), "cudaIpcGetMemHandle");
+    return pybind11::bytes(reinterpret_cast<const char*>(&h), sizeof(h));
+  }
+
+  // handles[r] = ipc handle bytes of rank r (this rank's own entry is ignored)
+  void open_peers(const std::vector<std::string>& handles, int rank) {
+    c10::cuda::CUDAGuard g(device_);
+    rank_ = rank;
+    world_ = (int)handles.size();
+    peers_.assign(world_, nullptr);
+    for (int r = 0; r < world_; ++r) {
+      if (r == rank) { peers_[r] = base_; continue; }
+      if (handles[r].size() != sizeof(cudaIpcMemHandle_t)) throw std::runtime_error("symm_heap: bad ipc handle size");
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handles[r].data(), sizeof(h));
+      ck(cudaIpcOpenMemHandle(&peers_[r], h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    }
+    std::vector<uint64_t> tab(world_);
+    for (int r = 0; r < world_; ++r) tab[r] = reinterpret_cast<uint64_t>(peers_[r]);
+    ck(cudaMalloc(&peer_table_dev_, sizeof(uint64_t) * world_), "cudaMalloc table");
+    ck(cudaMemcpy(peer_table_dev_, tab.data(), sizeof(uint64_t) * world_, cudaMemcpyHostToDevice), "memcpy table");
+  }
+
+  // Single-process mode (world 1, or tests): the "peer" table just points at ourselves.
+  void open_self() { open_peers(std::vector<std::string>(1), 0); }
+
+  int64_t alloc(int64_t nbytes, int64_t align) {
+    if (align < 256) align = 256;
+    int64_t off = (cursor_ + align - 1) / align * align;
+    if (off + nbytes > bytes_) throw std::runtime_error("symm_heap: out of symmetric memory (" + std::to_string(off + nbytes) + " > " + std::to_string(bytes_) + ")");
+    cursor_ = off + nbytes;
+    return off;
+  }
+  void reset_cursor(int64_t to) { cursor_ = to; }
+  int64_t cursor() const { return cursor_; }
+
+  torch::Tensor tensor(int64_t offset, std::vector<int64_t> sizes, at::ScalarType dtype, int peer) {
+    void* b = peer < 0 ? base_ : peers_.at(peer);
+    auto opts = torch::TensorOptions().dtype(dtype).device(torch::kCUDA, device_);
+    return torch::from_blob(static_cast<char*>(b) + offset, sizes, opts);
+  }
+  int64_t base_ptr() const { return reinterpret_cast<int64_t>(base_); }
+  int64_t peer_ptr(int r) const { return reinterpret_cast<int64_t>(peers_.at(r)); }
+  int64_t peer_table_ptr() const { return reinterpret_cast<int64_t>(peer_table_dev_); }
+  int64_t size() const { return bytes_; }
+  int64_t signal_bytes() const { return signal_bytes_; }
+  int rank() const { return rank_; }
+  int world() const { return world_; }
+
+ private:
+  int64_t bytes_, signal_bytes_;
+  int device_;
+  void* base_ = nullptr;
+  int64_t cursor_ = 0;
+  int rank_ = 0, world_ = 1;
+  std::vector<void*> peers_;
+  void* peer_table_dev_ = nullptr;
+};
+
+void bind_symm(pybind11::module_& m) {
+  pybind11::class_<SymmHeap, std::shared_ptr<SymmHeap>>(m, "SymmHeap")
+      .def(pybind11::init<int64_t, int64_t, int>())
+      .def("ipc_handle", &SymmHeap::ipc_handle)
+      .def("open_peers", &SymmHeap::open_peers)
+      .def("open_self", &SymmHeap::open_self)
+      .def("alloc", &SymmHeap::alloc)
+      .def("reset_cursor", &SymmHeap::reset_cursor)
+      .def("cursor", &SymmHeap::cursor)
+      .def("tensor", &SymmHeap::tensor)
+      .def("base_ptr", &SymmHeap::base_ptr)
+      .def("peer_ptr", &SymmHeap::peer_ptr)
+      .def("peer_table_ptr", &SymmHeap::peer_table_ptr)
+      .def("size", &SymmHeap::size)
+      .def("signal_bytes", &SymmHeap::signal_bytes)
+      .def("rank", &SymmHeap::rank)
+      .def("world", &SymmHeap::world);
+}
+
+}  // namespace runtime
+}  // namespace b200

@@ -1,0 +1,50 @@
+"""Global flags. Parity: paddle/common/flags.cc, python/paddle/base/framework.py:set_flags."""
+from __future__ import annotations
+
+import os
+
+_FLAGS = {
+    "FLAGS_check_nan_inf": False,
+    "FLAGS_cudnn_deterministic": False,
+    "FLAGS_use_fused_kernels": True,       # route nn/functional hot ops to the sm_100a kernels
+    "FLAGS_b200_sync_debug": False,        # serialise side streams (race triage)
+    "FLAGS_b200_p2p_collectives": True,    # fused compute+collective kernels over peer memory
+    "FLAGS_b200_gemm_backend": "tcgen05",  # "tcgen05" | "cublas"
+    "FLAGS_embedding_deterministic": 0,
+    "FLAGS_eager_delete_tensor_gb": 0.0,
+    "FLAGS_fraction_of_gpu_memory_to_use": 0.92,
+    "FLAGS_allocator_strategy": "auto_growth",
+    "FLAGS_enable_async_trace": False,
+    "FLAGS_sync_nccl_allreduce": False,
+    "FLAGS_max_inplace_grad_add": 0,
+}
+
+
+def _coerce(old, v):
+    if isinstance(old, bool):
+        return v if isinstance(v, bool) else str(v).lower() in ("1", "true", "yes", "on")
+    if isinstance(old, int):
+        return int(v)
+    if isinstance(old, float):
+        return float(v)
+    return v
+
+
+for _k in list(_FLAGS):
+    if _k in os.environ:
+        _FLAGS[_k] = _coerce(_FLAGS[_k], os.environ[_k])
+
+
+def set_flags(flags: dict):
+    for k, v in flags.items():
+        _FLAGS[k] = _coerce(_FLAGS[k], v) if k in _FLAGS else v
+
+
+def get_flags(names):
+    if isinstance(names, str):
+        names = [names]
+    return {n: _FLAGS[n] for n in names}
+
+
+def flag(name, default=None):
+    return _FLAGS.get(name, default)

@@ -1,0 +1,64 @@
+"""Rotary position embedding. Parity: python/paddle/incubate/nn/functional/fused_rotary_position_embedding.py."""
+from __future__ import annotations
+
+import torch
+
+from . import ext, raw, use_fused, wrap
+
+_table_cache = {}
+
+
+def rope_tables(seq_len, dim, base=10000.0, device="cpu"):
+    """fp32 cos/sin tables [seq_len, dim/2]."""
+    key = (int(seq_len), int(dim), float(base), str(device))
+    t = _table_cache.get(key)
+    if t is None:
+        inv = 1.0 / (base ** (torch.arange(0, dim, 2, dtype=torch.float32, device=device) / dim))
+        ang = torch.outer(torch.arange(seq_len, dtype=torch.float32, device=device), inv)
+        t = (ang.cos().contiguous(), ang.sin().contiguous())
+        if len(_table_cache) > 64:
+            _table_cache.clear()
+        _table_cache[key] = t
+    return t
+
+
+class _Rope(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cos_t, sin_t, pos_ids, seq, neox):
+        ctx.save_for_backward(cos_t, sin_t, pos_ids)
+        ctx.seq, ctx.neox = seq, neox
+        return ext().rope(x.contiguous(), cos_t, sin_t, pos_ids, seq, neox, False)
+
+    @staticmethod
+    def backward(ctx, dy):
+        cos_t, sin_t, pos_ids = ctx.saved_tensors
+        return ext().rope(dy.contiguous(), cos_t, sin_t, pos_ids, ctx.seq, ctx.neox, True), None, None, None, None, None
+
+
+def rope_ref(x, cos_t, sin_t, pos_ids, neox):
+    # x: [B, S, H, D]; tables [P, D/2]
+    b, s, h, d = x.shape
+    if pos_ids is None:
+        cos, sin = cos_t[:s], sin_t[:s]
+        cos, sin = cos[None, :, None, :], sin[None, :, None, :]
+    else:
+        cos, sin = cos_t[pos_ids][:, :, None, :], sin_t[pos_ids][:, :, None, :]
+    xf = x.float()
+    if neox:
+        a, bb = xf[..., : d // 2], xf[..., d // 2:]
+        out = torch.cat([a * cos - bb * sin, bb * cos + a * sin], -1)
+    else:
+        a, bb = xf[..., 0::2], xf[..., 1::2]
+        out = torch.stack([a * cos - bb * sin, bb * cos + a * sin], -1).flatten(-2)
+    return out.to(x.dtype)
+
+
+def apply_rope(x, cos_t, sin_t, position_ids=None, neox=True):
+    """x: [B, S, H, D]; cos/sin fp32 [P, D/2]."""
+    x = raw(x)
+    cos_t, sin_t, position_ids = raw(cos_t), raw(sin_t), raw(position_ids)
+    d = x.shape[-1]
+    if use_fused(x) and x.dtype in (torch.float32, torch.float16, torch.bfloat16) and (d // 2) % (16 // x.element_size()) == 0:
+        pid = position_ids.reshape(-1).contiguous() if position_ids is not None else None
+        return wrap(_Rope.apply(x, cos_t.float().contiguous(), sin_t.float().contiguous(), pid, int(x.shape[1]), bool(neox)))
+    return wrap(rope_ref(x, cos_t.float(), sin_t.float(), position_ids, neox))

@@ -1,0 +1,223 @@
+"""Numerics of every sm_100a kernel vs a plain PyTorch fp32 reference (run on the B200 box: pytest -m gpu)."""
+import pytest
+import torch
+
+import paddle_b200 as paddle
+from paddle_b200 import kernels
+from paddle_b200.kernels import activation as KA
+from paddle_b200.kernels import gemm as KG
+from paddle_b200.kernels import loss as KL
+from paddle_b200.kernels import norm as KN
+from paddle_b200.kernels import rope as KR
+
+pytestmark = pytest.mark.gpu
+
+
+def _ext():
+    from paddle_b200._build import ext
+
+    return ext()
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp(min=1e-12)).item()
+
+
+@pytest.mark.parametrize("a_km,b_nk", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("m,n,k", [(256, 512, 256), (384, 320, 192), (128, 64, 64), (1000, 776, 520), (4096, 5120, 1024)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_gemm_layouts(a_km, b_nk, m, n, k, dtype):
+    torch.manual_seed(0)
+    dev = "cuda"
+    A = torch.randn(m, k, device=dev, dtype=dtype)
+    B = torch.randn(k, n, device=dev, dtype=dtype)
+    a_in = A.t().contiguous() if a_km else A
+    b_in = B.t().contiguous() if b_nk else B
+    if not _ext().gemm_supported(a_in, b_in, a_km, b_nk):
+        pytest.skip("shape not supported by tcgen05 path")
+    out = _ext().gemm(a_in, b_in, None, a_km, b_nk, 0, None, None)
+    ref = A.float() @ B.float()
+    assert out.shape == (m, n)
+    assert rel_err(out, ref) < 5e-3, rel_err(out, ref)
+
+
+def test_gemm_bias_act_accumulate_fp32out():
+    torch.manual_seed(1)
+    m, n, k = 512, 768, 384
+    A = torch.randn(m, k, device="cuda", dtype=torch.bfloat16)
+    B = torch.randn(k, n, device="cuda", dtype=torch.bfloat16)
+    bias = torch.randn(n, device="cuda", dtype=torch.bfloat16)
+    ref = A.float() @ B.float() + bias.float()
+    out = _ext().gemm(A, B, bias, False, False, 1, None, None)
+    assert rel_err(out, ref) < 5e-3
+    out = _ext().gemm(A, B, bias, False, False, 2, None, None)
+    assert rel_err(out, torch.nn.functional.gelu(ref)) < 5e-3
+    out = _ext().gemm(A, B, bias, False, False, 3, None, None)
+    assert rel_err(out, torch.relu(ref)) < 5e-3
+    acc = torch.ones(m, n, device="cuda", dtype=torch.float32)
+    _ext().gemm(A, B, None, False, False, 4, acc, None)
+    assert rel_err(acc, A.float() @ B.float() + 1) < 1e-3
+    o32 = _ext().gemm(A, B, None, False, False, 0, None, torch.float32)
+    assert o32.dtype == torch.float32 and rel_err(o32, A.float() @ B.float()) < 1e-3
+
+
+def test_gemm_batched():
+    torch.manual_seed(2)
+    b, m, n, k = 6, 256, 192, 128
+    A = torch.randn(b, m, k, device="cuda", dtype=torch.bfloat16)
+    B = torch.randn(b, n, k, device="cuda", dtype=torch.bfloat16)
+    out = _ext().gemm(A, B, None, False, True, 0, None, None)
+    ref = torch.einsum("bmk,bnk->bmn", A.float(), B.float())
+    assert rel_err(out, ref) < 5e-3
+
+
+def test_linear_autograd_matches_fp32():
+    torch.manual_seed(3)
+    x = torch.randn(4, 128, 512, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    w = torch.randn(512, 1024, device="cuda", dtype=torch.bfloat16, requires_grad=True) * 0.05
+    w = w.detach().requires_grad_(True)
+    b = torch.randn(1024, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    y = KG.linear(x, w, b)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xf, wf, bf = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True), b.detach().float().requires_grad_(True)
+    yr = xf @ wf + bf
+    yr.backward(dy.float())
+    assert rel_err(y, yr) < 5e-3
+    assert rel_err(x.grad, xf.grad) < 5e-3
+    assert rel_err(w.grad, wf.grad) < 5e-3
+    assert rel_err(b.grad, bf.grad) < 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("cols", [512, 5120, 4096, 8192])
+def test_rms_norm(dtype, cols):
+    torch.manual_seed(0)
+    x = torch.randn(300, cols, device="cuda", dtype=dtype, requires_grad=True)
+    w = (torch.rand(cols, device="cuda", dtype=dtype) + 0.5).requires_grad_(True)
+    y = KN.rms_norm(x, w, 1e-6)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xf, wf = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    yr = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6) * wf
+    yr.backward(dy.float())
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-4
+    assert rel_err(y, yr) < tol
+    assert rel_err(x.grad, xf.grad) < tol
+    assert rel_err(w.grad, wf.grad) < tol * 2
+
+
+def test_rms_norm_residual():
+    x = torch.randn(64, 1024, device="cuda", dtype=torch.bfloat16)
+    r = torch.randn_like(x)
+    w = torch.rand(1024, device="cuda", dtype=torch.bfloat16)
+    y, h = KN.rms_norm(x, w, 1e-6, residual=r)
+    hf = (x.float() + r.float())
+    assert rel_err(h, hf) < 1e-2
+    hh = h.float()
+    assert rel_err(y, hh * torch.rsqrt(hh.pow(2).mean(-1, keepdim=True) + 1e-6) * w.float()) < 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_layer_norm(dtype):
+    torch.manual_seed(0)
+    cols = 1024
+    x = torch.randn(200, cols, device="cuda", dtype=dtype, requires_grad=True)
+    w = (torch.rand(cols, device="cuda", dtype=dtype) + 0.5).requires_grad_(True)
+    b = torch.randn(cols, device="cuda", dtype=dtype).requires_grad_(True)
+    y = KN.layer_norm(x, [cols], w, b, 1e-5)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xf, wf, bf = (t.detach().float().requires_grad_(True) for t in (x, w, b))
+    yr = torch.nn.functional.layer_norm(xf, (cols,), wf, bf, 1e-5)
+    yr.backward(dy.float())
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-4
+    assert rel_err(y, yr) < tol and rel_err(x.grad, xf.grad) < tol
+    assert rel_err(w.grad, wf.grad) < 2 * tol and rel_err(b.grad, bf.grad) < 2 * tol
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_swiglu(packed):
+    g = torch.randn(128, 2048, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    u = torch.randn(128, 2048, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    if packed:
+        xin = torch.cat([g.detach(), u.detach()], -1).requires_grad_(True)
+        y = KA.swiglu(xin)
+    else:
+        y = KA.swiglu(g, u)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    gf, uf = g.detach().float().requires_grad_(True), u.detach().float().requires_grad_(True)
+    yr = torch.nn.functional.silu(gf) * uf
+    yr.backward(dy.float())
+    assert rel_err(y, yr) < 1e-2
+    if packed:
+        assert rel_err(xin.grad, torch.cat([gf.grad, uf.grad], -1)) < 1e-2
+    else:
+        assert rel_err(g.grad, gf.grad) < 1e-2 and rel_err(u.grad, uf.grad) < 1e-2
+
+
+@pytest.mark.parametrize("neox", [True, False])
+def test_rope(neox):
+    x = torch.randn(2, 64, 8, 128, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    cos, sin = KR.rope_tables(64, 128, device="cuda")
+    y = KR.apply_rope(x, cos, sin, None, neox)
+    ref = KR.rope_ref(x.detach().float(), cos, sin, None, neox)
+    assert rel_err(y, ref) < 1e-2
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xf = x.detach().float().requires_grad_(True)
+    KR.rope_ref(xf, cos, sin, None, neox).backward(dy.float())
+    assert rel_err(x.grad, xf.grad) < 1e-2
+
+
+@pytest.mark.parametrize("vocab", [32000, 1000, 50257])
+def test_softmax_ce(vocab):
+    torch.manual_seed(0)
+    n = 257
+    lg = (torch.randn(n, vocab, device="cuda") * 3).to(torch.bfloat16).requires_grad_(True)
+    lab = torch.randint(0, vocab, (n,), device="cuda")
+    lab[5] = -100
+    loss = KL.softmax_cross_entropy(lg, lab, -100)
+    w = torch.rand(n, device="cuda")
+    (loss * w).sum().backward()
+    lf = lg.detach().float().requires_grad_(True)
+    lr = torch.nn.functional.cross_entropy(lf, lab, ignore_index=-100, reduction="none")
+    (lr * w).sum().backward()
+    assert rel_err(loss, lr) < 1e-3
+    assert rel_err(lg.grad, lf.grad) < 2e-2
+
+
+@pytest.mark.parametrize("state_dtype", [torch.float32, torch.bfloat16])
+def test_adamw_kernel(state_dtype):
+    torch.manual_seed(0)
+    n = 100003
+    p32 = torch.randn(n, device="cuda")
+    g = torch.randn(n, device="cuda").to(torch.bfloat16)
+    p = p32.to(torch.bfloat16)
+    master = p.float().clone()
+    m = torch.zeros(n, device="cuda", dtype=state_dtype)
+    v = torch.zeros(n, device="cuda", dtype=state_dtype)
+    ref_p = torch.nn.Parameter(master.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+    for step in range(1, 4):
+        ref_p.grad = g.float()
+        opt.step()
+        _ext().adamw_step(p, g, master, m, v, 1e-2, 0.9, 0.95, 1e-8, 0.1, step, None, 0.0, None, None)
+    tol = 1e-5 if state_dtype == torch.float32 else 2e-2
+    assert rel_err(master, ref_p.detach()) < tol
+    assert rel_err(p, ref_p.detach()) < 1e-2
+
+
+def test_grad_norm_and_clip():
+    g = torch.randn(1 << 20, device="cuda").to(torch.bfloat16)
+    out = torch.zeros(1, device="cuda")
+    fi = torch.zeros(1, device="cuda")
+    _ext().grad_sq_norm(g, out, fi)
+    assert abs(out.item() - g.float().pow(2).sum().item()) / g.float().pow(2).sum().item() < 1e-4
+    assert fi.item() == 0
+    g[123] = float("inf")
+    out.zero_()
+    _ext().grad_sq_norm(g, out, fi)
+    assert fi.item() == 1
