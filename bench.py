@@ -1,0 +1,252 @@
+#!/usr/bin/env python
+"""Headline benchmark: Llama-2-13B training throughput (tokens/s, whole job) on N B200s of one node.
+
+Metric / config come from BASELINE.json: Llama-2 13B, fleet hybrid parallel (dp x mp x pp as N allows), bf16,
+synthetic tokens, random-init weights.  Parallel layout per N: 1 -> single GPU; 2 -> mp2; 4 -> mp2 x pp2;
+8 -> dp2 x mp2 x pp2.  Weak scaling: 4 sequences of 4096 tokens per GPU per step.
+
+  python bench.py --gpus 1 --steps 5 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 ...
+  python bench.py --impl reference ...   -> {"impl": "reference", "unavailable": ...}
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--model", default="llama2-13b")
+    ap.add_argument("--seq", type=int, default=4096)
+    ap.add_argument("--seqs-per-gpu", type=int, default=4)
+    ap.add_argument("--micro-batch", type=int, default=1)
+    ap.add_argument("--layers", type=int, default=0, help="debug only: override layer count (result is then marked invalid)")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def layout_for(n):
+    return {1: (1, 1, 1), 2: (1, 2, 1), 4: (1, 2, 2), 8: (2, 2, 2)}.get(n, (n, 1, 1))  # (dp, mp, pp)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        print(json.dumps({"impl": "reference", "unavailable": "PaddlePaddle cannot be built offline: third_party/ submodules are empty "
+                                                              "and build dependency 'opteinsum' is not in /opt/wheelhouse (see DESIGN.md)"}))
+        return 0
+
+    import torch
+
+    import paddle_b200 as paddle
+    from paddle_b200 import kernels
+    from paddle_b200.distributed import env, fleet
+    from paddle_b200.models import llama as L
+
+    n = args.gpus
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if n > 1 and world != n:
+        print(json.dumps({"error": f"--gpus {n} needs torchrun with {n} ranks (WORLD_SIZE={world})"}))
+        return 1
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    paddle.set_device(f"gpu:{local_rank}")
+    dp, mp, pp = layout_for(n)
+    if n > 1:
+        strategy = fleet.DistributedStrategy()
+        strategy.hybrid_configs = {"dp_degree": dp, "mp_degree": mp, "pp_degree": pp}
+        fleet.init(is_collective=True, strategy=strategy)
+    rank = env.get_rank()
+
+    cfg = L.llama2_13b() if args.model == "llama2-13b" else L.llama2_7b()
+    if args.layers:
+        cfg.num_hidden_layers = args.layers
+    cfg.max_position_embeddings = args.seq
+    cfg.tensor_parallel_degree = mp
+    cfg.sequence_parallel = mp > 1
+    # single GPU: 13B params + AdamW state fill HBM -> full activation recompute; model-parallel runs keep activations
+    cfg.recompute = (n == 1)
+    paddle.seed(1234 + rank)
+    paddle.set_default_dtype("bfloat16")
+
+    seqs_per_replica = args.seqs_per_gpu * mp * pp
+    global_batch = seqs_per_replica * dp
+    accumulate = seqs_per_replica // args.micro_batch
+
+    if pp > 1:
+        from paddle_b200.distributed.fleet.pipeline import PipelineLayer
+
+        strategy.pipeline_configs = {"accumulate_steps": accumulate, "micro_batch_size": args.micro_batch}
+        model = PipelineLayer(layers=L.pipeline_layer_descs(cfg), num_stages=pp, loss_fn=L.LlamaPretrainingCriterion(cfg),
+                              seg_method="layer:LlamaDecoderLayer")
+    else:
+        model = L.LlamaForCausalLM(cfg)
+    n_params_local = sum(p.numel() for p in model.parameters())
+    decay_fn = lambda name: not any(k in name for k in ("norm", "bias"))  # noqa: E731
+    opt = paddle.optimizer.AdamW(learning_rate=1e-5, beta1=0.9, beta2=0.95, epsilon=1e-8, parameters=model.parameters(), weight_decay=0.1,
+                                 grad_clip=paddle.nn.ClipGradByGlobalNorm(1.0), multi_precision=True, moment_dtype="bfloat16",
+                                 apply_decay_param_fun=decay_fn)
+    if n > 1:
+        model = fleet.distributed_model(model)
+        opt = fleet.distributed_optimizer(opt)
+    else:
+        opt.enable_flat_arena()
+
+    vocab, seq = cfg.vocab_size, args.seq
+    steps_total = args.warmup + args.steps
+    # synthetic token stream in pinned host memory (one fresh batch per step: e2e copies it H2D every step)
+    host = torch.randint(0, vocab, (steps_total * 2 + 2, seqs_per_replica, seq + 1), dtype=torch.int64).pin_memory()
+    h2d_bytes = seqs_per_replica * (seq + 1) * 8
+    dev_batches = [host[i].cuda(non_blocking=True) for i in range(2)]
+
+    def train_step(tokens, read_loss):
+        """One optimizer step over `accumulate` micro-batches; public-API calls only."""
+        if pp > 1:
+            loss = model.train_batch([tokens[:, :-1], tokens[:, 1:]], opt)
+        else:
+            loss_acc = None
+            for mb in range(accumulate):
+                sl = slice(mb * args.micro_batch, (mb + 1) * args.micro_batch)
+                loss = model(tokens[sl, :-1], tokens[sl, 1:]) / accumulate
+                loss.backward()
+                loss_acc = loss.detach() if loss_acc is None else loss_acc + loss.detach()
+            opt.step()
+            opt.clear_grad()
+            loss = loss_acc
+        return float(loss.item()) if read_loss else loss
+
+    def barrier():
+        if n > 1:
+            paddle.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e, offset):
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        kernels.reset_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        last = None
+        for i in range(nsteps):
+            if e2e:
+                tok = host[offset + i].cuda(non_blocking=True)       # H2D of this step's inputs from pinned memory
+                last = train_step(tok.as_subclass(paddle.Tensor), read_loss=True)  # D2H read of the loss
+            else:
+                last = train_step(dev_batches[i % 2].as_subclass(paddle.Tensor), read_loss=False)
+        ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([ms], device="cuda")
+        if n > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        clocks = sampler.stop()
+        return float(t.item()), wall, kernels.launch_count(), clocks, last
+
+    # warm-up (also materialises optimizer state and tensor maps)
+    for i in range(args.warmup):
+        train_step(dev_batches[i % 2].as_subclass(paddle.Tensor), read_loss=False)
+    ms, wall, launches, clocks, last = timed(args.steps, e2e=False, offset=0)
+    tokens_per_step = global_batch * seq
+    value = tokens_per_step * args.steps / (ms / 1e3)
+    out = {
+        "metric": "tokens/sec (whole job, device-timed, max over ranks) Llama-2-13B fleet hybrid parallel training step",
+        "value": round(value, 1), "unit": "tokens/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms / args.steps, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic tokens (pinned host), random-init weights",
+        "config": {"model": "Llama-2-13B" if args.model == "llama2-13b" and not args.layers else f"{args.model} layers={cfg.num_hidden_layers}",
+                   "hidden": cfg.hidden_size, "layers": cfg.num_hidden_layers, "heads": cfg.num_attention_heads, "ffn": cfg.intermediate_size,
+                   "vocab": vocab, "global_batch": global_batch, "seq_len": seq, "micro_batch": args.micro_batch, "accumulate_steps": accumulate,
+                   "parallelism": f"dp{dp}xmp{mp}xpp{pp}", "sequence_parallel": bool(cfg.sequence_parallel), "recompute": "full" if cfg.recompute else "none",
+                   "optimizer": "AdamW fp32 master weights, bf16 moments, global-norm clip 1.0 (fused, device-side)",
+                   "l2": "working set (weights+optimizer state >= 26 GB per GPU) >> 126 MB L2; no explicit flush needed",
+                   "params_per_gpu": n_params_local},
+        "gpu_launches": int(launches), "clocks": clocks, "wall_s": round(wall, 3),
+    }
+    if args.layers:
+        out["invalid"] = "debug run with reduced layer count"
+    if not args.no_e2e:
+        ms2, wall2, _, _, last = timed(args.steps, e2e=True, offset=2)
+        out["e2e"] = {"value": round(tokens_per_step * args.steps / (ms2 / 1e3), 1), "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes,
+                      "d2h_bytes_per_step": 4, "ms_per_step": round(ms2 / args.steps, 2), "last_loss": last}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    flops_per_token = 6 * 13.0e9 + 12 * cfg.num_hidden_layers * cfg.hidden_size * seq  # fwd+bwd model FLOPs
+    out["model_tflops_per_gpu"] = round(value * flops_per_token / n / 1e12, 1)
+    if peaks.get("bf16_tflops_sustained"):
+        out["mfu_of_measured_sustained_peak"] = round(out["model_tflops_per_gpu"] / peaks["bf16_tflops_sustained"], 3)
+    if rank == 0:
+        print(json.dumps(out))
+    if n > 1:
+        env.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -31,3 +31,55 @@ float = float32  # noqa: A001
 double = float64
 int = int32  # noqa: A001
 long = int64
+
+from . import nn, optimizer, amp, io, regularizer  # noqa: E402,F401
+from .nn.layer import ParamAttr  # noqa: E402,F401
+from .framework.io import async_save, clear_async_save_task_queue, load, save  # noqa: E402,F401
+from . import distributed  # noqa: E402,F401
+from . import kernels  # noqa: E402,F401
+
+
+def __getattr__(name):
+    """Lazy sub-packages (keeps `import paddle_b200` fast)."""
+    import importlib
+
+    lazy = {"vision", "metric", "hapi", "distribution", "sparse", "incubate", "jit", "static", "inference", "profiler", "quantization",
+            "device", "text", "audio", "geometric", "models", "parallel", "utils", "fft", "signal", "linalg", "hub", "onnx", "callbacks",
+            "sysconfig", "version", "base", "tensor_ns", "decomposition", "cost_model", "reader", "dataset"}
+    if name in lazy:
+        return importlib.import_module("." + name, __name__)
+    if name == "DataParallel":
+        from .distributed.data_parallel import DataParallel
+
+        return DataParallel
+    if name in ("Model", "summary", "flops"):
+        from . import hapi
+
+        return getattr(hapi, name)
+    if name == "batch":
+        from .reader import batch
+
+        return batch
+    if name in ("disable_static", "enable_static", "in_dynamic_mode"):
+        from . import static
+
+        return getattr(static, name)
+    if name in ("set_grad_enabled",):
+        from .autograd import set_grad_enabled
+
+        return set_grad_enabled
+    if name in ("get_cuda_rng_state",):
+        from .framework import random
+
+        return getattr(random, name)
+    raise AttributeError(f"module 'paddle_b200' has no attribute '{name}'")
+
+
+def install_as_paddle():
+    """Register this package under the name ``paddle`` so reference user code runs unchanged."""
+    import sys
+
+    sys.modules.setdefault("paddle", sys.modules[__name__])
+    for k, v in list(sys.modules.items()):
+        if k.startswith(__name__ + "."):
+            sys.modules.setdefault("paddle" + k[len(__name__):], v)

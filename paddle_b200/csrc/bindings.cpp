@@ -166,10 +166,29 @@ Tensor rope(const Tensor& x, const Tensor& cos_t, const Tensor& sin_t, const Opt
     pid = pos.data_ptr<int64_t>();
   }
   b200::rope_apply(x.data_ptr(), y.data_ptr(), cos_t.data_ptr<float>(), sin_t.data_ptr<float>(), pid, tokens, (int)seq, heads, dim,
-                   neox ? 1 : 0, backward ? 1 : 0, dt_code(x), cur_stream());
+                   neox ? 1 : 0, backward ? 1 : 0, dt_code(x), 0, cur_stream());
   g_launches += 1;
   check_err();
   return y;
+}
+
+// In-place rotary on the first `rope_heads` heads of a packed [tokens, total_heads, dim] tensor (fused QKV: q and k heads
+// rotate, v heads are left untouched) -> no split/concat copies around the attention.
+void rope_packed_(Tensor x, const Tensor& cos_t, const Tensor& sin_t, const OptT& pos_ids, int64_t seq, int64_t rope_heads,
+                  int64_t total_heads, int64_t dim, bool neox, bool backward) {
+  check_cuda_contig(x, "x");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int64_t tokens = x.numel() / (total_heads * dim);
+  const int64_t* pid = nullptr;
+  Tensor pos;
+  if (pos_ids.has_value() && pos_ids->defined()) {
+    pos = pos_ids->to(at::kLong).contiguous();
+    pid = pos.data_ptr<int64_t>();
+  }
+  b200::rope_apply(x.data_ptr(), x.data_ptr(), cos_t.data_ptr<float>(), sin_t.data_ptr<float>(), pid, tokens, (int)seq, (int)rope_heads,
+                   (int)dim, neox ? 1 : 0, backward ? 1 : 0, dt_code(x), total_heads * dim, cur_stream());
+  g_launches += 1;
+  check_err();
 }
 
 // ------------------------------------------------------------------------------------------------ loss
@@ -382,6 +401,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("swiglu_fwd", &swiglu_fwd);
   m.def("swiglu_bwd", &swiglu_bwd);
   m.def("rope", &rope);
+  m.def("rope_packed_", &rope_packed_);
   m.def("softmax_ce_fwd", &softmax_ce_fwd);
   m.def("softmax_ce_bwd", &softmax_ce_bwd);
   m.def("vp_ce_max", &vp_ce_max);

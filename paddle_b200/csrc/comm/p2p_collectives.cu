@@ -1,0 +1,255 @@
+// Collectives over NVLink/NVSwitch peer memory: the kernels issue ld/st.global directly on IPC-mapped peer pointers
+// (symmetric heap, csrc/runtime/symm_heap.cpp).  No NCCL on these paths.
+//
+// Parity (role): ProcessGroupNCCL::AllReduce/ReduceScatter/AllGather (paddle/fluid/distributed/collective/
+// process_group_nccl.cc) as used by DataParallel's EagerReducer, GroupSharded stage2/3 and the mp layers.
+//
+// Protocol: every rank owns a signal pad (first bytes of its heap slab): pad[slot][src_rank] (uint32).
+//   start barrier  : rank r stores `epoch` into pad[0][r] of every peer (st.release.sys); all CTAs spin on their local
+//                    pad[0][*] >= epoch (ld.acquire.sys)  -> peers' input data is visible.
+//   end barrier    : the last CTA of the grid stores `epoch` into pad[1][r] of every peer and waits for pad[1][*]
+//                    -> when the kernel retires, every peer has finished reading/writing this rank's buffer.
+// Reductions accumulate in fp32 in a fixed rank order (deterministic).
+#include <cstdio>
+
+#include "../include/b200_common.cuh"
+#include "../include/b200_comm.h"
+
+namespace b200 {
+namespace comm {
+
+constexpr int kMaxRanks = 8;
+constexpr int kThreads = 512;
+
+struct Peers {
+  char* base[kMaxRanks];
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t gtimer() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// pad layout: uint32 pad[kSlots][kMaxRanks] at heap base
+__device__ __forceinline__ uint32_t* pad_ptr(char* base, int slot, int src) {
+  return reinterpret_cast<uint32_t*>(base) + slot * kMaxRanks + src;
+}
+
+// All threads of the CTA return once every peer has published `epoch` in local pad[slot].
+__device__ __forceinline__ void wait_all(const Peers& P, int rank, int world, int slot, uint32_t epoch) {
+  if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
+    const uint32_t* f = pad_ptr(P.base[rank], slot, threadIdx.x);
+    const uint64_t t0 = gtimer();
+    // epochs are monotonically increasing; signed distance handles wrap-around
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+      if (gtimer() - t0 > 10000000000ull) {  // 10 s: peer died or protocol bug -> fail loudly, do not hang the GPU
+        printf("b200 p2p: barrier timeout rank %d waiting for %d slot %d epoch %u (have %u)\n", rank, (int)threadIdx.x, slot, epoch, ld_acquire_sys(f));
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void signal_all(const Peers& P, int rank, int world, int slot, uint32_t epoch) {
+  if ((int)threadIdx.x < world && (int)threadIdx.x != rank) st_release_sys(pad_ptr(P.base[threadIdx.x], slot, rank), epoch);
+}
+
+// Grid-wide completion: returns true in the last CTA to arrive.
+__device__ __forceinline__ bool last_cta(uint32_t* counter) {
+  __shared__ bool is_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(counter, 1u);
+    is_last = (prev == gridDim.x - 1);
+    if (is_last) *counter = 0;  // reset for the next launch (stream-ordered)
+  }
+  __syncthreads();
+  return is_last;
+}
+
+// ---------------------------------------------------------------------------------------------- two-shot all-reduce
+// buffer of n elements at `off` in every rank's heap. Rank r owns elements [r*chunk, (r+1)*chunk): it reads that range
+// from every peer, sums, and writes the result back into every peer's buffer.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) allreduce_kernel(Peers P, int64_t off, int64_t n, int rank, int world,
+                                                             uint32_t epoch, uint32_t* counter) {
+  constexpr int N = Vec16<T>::N;
+  if (blockIdx.x == 0) signal_all(P, rank, world, 0, epoch);
+  wait_all(P, rank, world, 0, epoch);
+  const int64_t nvec = n / N;
+  const int64_t per = (nvec + world - 1) / world;
+  const int64_t v0 = per * rank, v1 = min(nvec, v0 + per);
+  for (int64_t v = v0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < v1; v += (int64_t)gridDim.x * blockDim.x) {
+    float acc[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) acc[j] = 0.f;
+    Vec16<T> in[kMaxRanks];
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r)
+      if (r < world) in[r] = ld16(reinterpret_cast<const T*>(P.base[r] + off) + v * N);   // all peer loads in flight
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r)
+      if (r < world) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) acc[j] += to_f(in[r].v[j]);
+      }
+    Vec16<T> o;
+#pragma unroll
+    for (int j = 0; j < N; ++j) o.v[j] = from_f<T>(acc[j]);
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r)
+      if (r < world) st16(reinterpret_cast<T*>(P.base[r] + off) + v * N, o);
+  }
+  // scalar tail (n % N) handled by the last rank
+  if (rank == world - 1 && blockIdx.x == 0) {
+    for (int64_t i = nvec * N + threadIdx.x; i < n; i += blockDim.x) {
+      float a = 0.f;
+      for (int r = 0; r < world; ++r) a += to_f(reinterpret_cast<const T*>(P.base[r] + off)[i]);
+      for (int r = 0; r < world; ++r) reinterpret_cast<T*>(P.base[r] + off)[i] = from_f<T>(a);
+    }
+  }
+  if (last_cta(counter)) {
+    signal_all(P, rank, world, 1, epoch);
+    wait_all(P, rank, world, 1, epoch);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- reduce-scatter
+// input: n elements at `off` in every heap; rank r's output = sum over peers of elements [r*n/world, (r+1)*n/world)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) reduce_scatter_kernel(Peers P, int64_t off, T* __restrict__ out, int64_t n, int rank,
+                                                                  int world, uint32_t epoch, uint32_t* counter) {
+  constexpr int N = Vec16<T>::N;
+  if (blockIdx.x == 0) signal_all(P, rank, world, 0, epoch);
+  wait_all(P, rank, world, 0, epoch);
+  const int64_t chunk = n / world;          // caller guarantees divisibility and chunk % N == 0
+  const int64_t nvec = chunk / N;
+  const int64_t base = chunk * rank;
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    float acc[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) acc[j] = 0.f;
+    Vec16<T> in[kMaxRanks];
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r)
+      if (r < world) in[r] = ld16(reinterpret_cast<const T*>(P.base[r] + off) + base + v * N);
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r)
+      if (r < world) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) acc[j] += to_f(in[r].v[j]);
+      }
+    Vec16<T> o;
+#pragma unroll
+    for (int j = 0; j < N; ++j) o.v[j] = from_f<T>(acc[j]);
+    st16_stream(out + v * N, o);
+  }
+  if (last_cta(counter)) {
+    signal_all(P, rank, world, 1, epoch);
+    wait_all(P, rank, world, 1, epoch);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- all-gather (pull)
+// every rank has its shard at [rank*chunk, (rank+1)*chunk) of the buffer at `off`; pull the other shards from their owners.
+__global__ void __launch_bounds__(kThreads) allgather_kernel(Peers P, int64_t off, int64_t chunk_bytes, int rank, int world,
+                                                             uint32_t epoch, uint32_t* counter) {
+  if (blockIdx.x == 0) signal_all(P, rank, world, 0, epoch);
+  wait_all(P, rank, world, 0, epoch);
+  const int64_t nvec = chunk_bytes / 16;
+  for (int pr = 1; pr < world; ++pr) {
+    const int src = (rank + pr) % world;  // stagger peers so the switch sees a permutation, not a hotspot
+    const uint4* s = reinterpret_cast<const uint4*>(P.base[src] + off + chunk_bytes * src);
+    uint4* d = reinterpret_cast<uint4*>(P.base[rank] + off + chunk_bytes * src);
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) d[v] = s[v];
+  }
+  if (last_cta(counter)) {
+    signal_all(P, rank, world, 1, epoch);
+    wait_all(P, rank, world, 1, epoch);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- all-to-all (push)
+// send buffer at off_send: world chunks of chunk_bytes (chunk d goes to rank d); recv buffer at off_recv: chunk s comes from rank s.
+__global__ void __launch_bounds__(kThreads) alltoall_kernel(Peers P, int64_t off_send, int64_t off_recv, int64_t chunk_bytes, int rank,
+                                                            int world, uint32_t epoch, uint32_t* counter) {
+  if (blockIdx.x == 0) signal_all(P, rank, world, 0, epoch);
+  wait_all(P, rank, world, 0, epoch);  // receivers' previous consumers are done (stream order on each rank + end barrier)
+  const int64_t nvec = chunk_bytes / 16;
+  for (int pr = 0; pr < world; ++pr) {
+    const int dst = (rank + pr) % world;
+    const uint4* s = reinterpret_cast<const uint4*>(P.base[rank] + off_send + chunk_bytes * dst);
+    uint4* d = reinterpret_cast<uint4*>(P.base[dst] + off_recv + chunk_bytes * rank);
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) d[v] = s[v];
+  }
+  if (last_cta(counter)) {
+    signal_all(P, rank, world, 1, epoch);
+    wait_all(P, rank, world, 1, epoch);
+  }
+}
+
+static Peers make_peers(const int64_t* bases, int world) {
+  Peers P;
+  for (int r = 0; r < kMaxRanks; ++r) P.base[r] = r < world ? reinterpret_cast<char*>(bases[r]) : nullptr;
+  return P;
+}
+
+static int comm_grid(int64_t work_vecs) {
+  // NVLink saturates with a fraction of the SMs; keep the rest free for overlapped compute
+  int64_t blocks = (work_vecs + kThreads - 1) / kThreads;
+  const int cap = 64;
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+void p2p_allreduce(const int64_t* bases, int64_t off, int64_t n, int dtype, int rank, int world, uint32_t epoch, uint32_t* counter,
+                   cudaStream_t s) {
+  if (world > kMaxRanks) { set_last_error(__FILE__, __LINE__, "p2p collectives support up to 8 ranks (one NVSwitch domain)"); return; }
+  Peers P = make_peers(bases, world);
+  B200_DISPATCH_DTYPE(dtype, T, {
+    constexpr int N = Vec16<T>::N;
+    allreduce_kernel<T><<<comm_grid(n / N / world + 1), kThreads, 0, s>>>(P, off, n, rank, world, epoch, counter);
+  });
+  B200_CUDA_CHECK(cudaGetLastError());
+}
+
+void p2p_reduce_scatter(const int64_t* bases, int64_t off, void* out, int64_t n, int dtype, int rank, int world, uint32_t epoch,
+                        uint32_t* counter, cudaStream_t s) {
+  if (world > kMaxRanks) { set_last_error(__FILE__, __LINE__, "p2p collectives support up to 8 ranks"); return; }
+  Peers P = make_peers(bases, world);
+  B200_DISPATCH_DTYPE(dtype, T, {
+    constexpr int N = Vec16<T>::N;
+    if (n % world || (n / world) % N) { set_last_error(__FILE__, __LINE__, "p2p_reduce_scatter: n/world must be a multiple of the 16B vector"); return; }
+    reduce_scatter_kernel<T><<<comm_grid(n / world / N), kThreads, 0, s>>>(P, off, (T*)out, n, rank, world, epoch, counter);
+  });
+  B200_CUDA_CHECK(cudaGetLastError());
+}
+
+void p2p_allgather(const int64_t* bases, int64_t off, int64_t chunk_bytes, int rank, int world, uint32_t epoch, uint32_t* counter,
+                   cudaStream_t s) {
+  if (world > kMaxRanks || chunk_bytes % 16) { set_last_error(__FILE__, __LINE__, "p2p_allgather: bad world/chunk"); return; }
+  Peers P = make_peers(bases, world);
+  allgather_kernel<<<comm_grid(chunk_bytes / 16), kThreads, 0, s>>>(P, off, chunk_bytes, rank, world, epoch, counter);
+  B200_CUDA_CHECK(cudaGetLastError());
+}
+
+void p2p_alltoall(const int64_t* bases, int64_t off_send, int64_t off_recv, int64_t chunk_bytes, int rank, int world, uint32_t epoch,
+                  uint32_t* counter, cudaStream_t s) {
+  if (world > kMaxRanks || chunk_bytes % 16) { set_last_error(__FILE__, __LINE__, "p2p_alltoall: bad world/chunk"); return; }
+  Peers P = make_peers(bases, world);
+  alltoall_kernel<<<comm_grid(chunk_bytes / 16), kThreads, 0, s>>>(P, off_send, off_recv, chunk_bytes, rank, world, epoch, counter);
+  B200_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace comm
+}  // namespace b200

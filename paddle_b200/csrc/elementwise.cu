@@ -13,18 +13,36 @@ template <typename T>
 __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const T* __restrict__ gate, const T* __restrict__ up,
                                                           T* __restrict__ out, int64_t rows, int cols, int64_t ld) {
   constexpr int N = Vec16<T>::N;
+  constexpr int U = 4;  // independent 16B loads in flight per thread and tensor
   const int vec_per_row = cols / N;
   const int64_t total = rows * vec_per_row;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / vec_per_row;
-    const int c = (int)(i - r * vec_per_row) * N;
-    Vec16<T> g = ld16_stream(gate + r * ld + c), u = ld16_stream(up + r * ld + c), o;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+    Vec16<T> g[U], u[U];
+    int64_t oidx[U];
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      const float x = to_f(g.v[j]);
-      o.v[j] = from_f<T>(x * sigmoidf_fast(x) * to_f(u.v[j]));
+    for (int k = 0; k < U; ++k) {
+      const int64_t i = i0 + k * stride;
+      if (i < total) {
+        const int64_t r = i / vec_per_row;
+        const int c = (int)(i - r * vec_per_row) * N;
+        g[k] = ld16_stream(gate + r * ld + c);
+        u[k] = ld16_stream(up + r * ld + c);
+        oidx[k] = r * cols + c;
+      }
     }
-    st16_stream(out + r * cols + c, o);
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      if (i0 + k * stride < total) {
+        Vec16<T> o;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const float x = to_f(g[k].v[j]);
+          o.v[j] = from_f<T>(x * sigmoidf_fast(x) * to_f(u[k].v[j]));
+        }
+        st16_stream(out + oidx[k], o);
+      }
+    }
   }
 }
 
@@ -33,22 +51,40 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const T* __restrict__ d
                                                           const T* __restrict__ up, T* __restrict__ dgate,
                                                           T* __restrict__ dup, int64_t rows, int cols, int64_t ld) {
   constexpr int N = Vec16<T>::N;
+  constexpr int U = 2;
   const int vec_per_row = cols / N;
   const int64_t total = rows * vec_per_row;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / vec_per_row;
-    const int c = (int)(i - r * vec_per_row) * N;
-    Vec16<T> g = ld16_stream(gate + r * ld + c), u = ld16_stream(up + r * ld + c), d = ld16_stream(dout + r * cols + c);
-    Vec16<T> og, ou;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+    Vec16<T> g[U], u[U], d[U];
+    int64_t gi[U];
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      const float x = to_f(g.v[j]), y = to_f(u.v[j]), dy = to_f(d.v[j]);
-      const float sg = sigmoidf_fast(x);
-      og.v[j] = from_f<T>(dy * y * sg * (1.f + x * (1.f - sg)));
-      ou.v[j] = from_f<T>(dy * x * sg);
+    for (int k = 0; k < U; ++k) {
+      const int64_t i = i0 + k * stride;
+      if (i < total) {
+        const int64_t r = i / vec_per_row;
+        const int c = (int)(i - r * vec_per_row) * N;
+        gi[k] = r * ld + c;
+        g[k] = ld16_stream(gate + gi[k]);
+        u[k] = ld16_stream(up + gi[k]);
+        d[k] = ld16_stream(dout + r * cols + c);
+      }
     }
-    st16_stream(dgate + r * ld + c, og);
-    st16_stream(dup + r * ld + c, ou);
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      if (i0 + k * stride < total) {
+        Vec16<T> og, ou;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const float x = to_f(g[k].v[j]), y = to_f(u[k].v[j]), dy = to_f(d[k].v[j]);
+          const float sg = sigmoidf_fast(x);
+          og.v[j] = from_f<T>(dy * y * sg * (1.f + x * (1.f - sg)));
+          ou.v[j] = from_f<T>(dy * x * sg);
+        }
+        st16_stream(dgate + gi[k], og);
+        st16_stream(dup + gi[k], ou);
+      }
+    }
   }
 }
 
@@ -66,7 +102,7 @@ void swiglu_fwd(const void* gate, const void* up, void* out, int64_t rows, int c
     const T* g = (const T*)gate;
     const T* u = up ? (const T*)up : g + cols;
     const int64_t ld = up ? cols : 2 * (int64_t)cols;
-    swiglu_fwd_kernel<T><<<ew_grid(rows * (cols / N), 256), 256, 0, s>>>(g, u, (T*)out, rows, cols, ld);
+    swiglu_fwd_kernel<T><<<ew_grid((rows * (cols / N) + 3) / 4, 256), 256, 0, s>>>(g, u, (T*)out, rows, cols, ld);
   });
   B200_CUDA_CHECK(cudaGetLastError());
 }
@@ -82,7 +118,7 @@ void swiglu_bwd(const void* dout, const void* gate, const void* up, void* dgate,
     T* dg = (T*)dgate;
     T* du = up ? (T*)dup : dg + cols;
     const int64_t ld = up ? cols : 2 * (int64_t)cols;
-    swiglu_bwd_kernel<T><<<ew_grid(rows * (cols / N), 256), 256, 0, s>>>((const T*)dout, g, u, dg, du, rows, cols, ld);
+    swiglu_bwd_kernel<T><<<ew_grid((rows * (cols / N) + 1) / 2, 256), 256, 0, s>>>((const T*)dout, g, u, dg, du, rows, cols, ld);
   });
   B200_CUDA_CHECK(cudaGetLastError());
 }
@@ -94,7 +130,7 @@ template <typename T, bool kNeox>
 __global__ void __launch_bounds__(256) rope_kernel(const T* __restrict__ x, T* __restrict__ y,
                                                     const float* __restrict__ cos_t, const float* __restrict__ sin_t,
                                                     const int64_t* __restrict__ pos_ids, int64_t tokens, int seq,
-                                                    int heads, int dim, float sign) {
+                                                    int heads, int dim, float sign, int64_t row_stride) {
   constexpr int N = Vec16<T>::N;
   const int half = dim / 2;
   const int vec_per_head = kNeox ? half / N : dim / N;
@@ -104,8 +140,9 @@ __global__ void __launch_bounds__(256) rope_kernel(const T* __restrict__ x, T* _
     const int64_t th = i / vec_per_head;
     const int64_t tok = th / heads;
     const int64_t pos = pos_ids ? pos_ids[tok] : (tok % seq);
-    const T* xp = x + th * dim;
-    T* yp = y + th * dim;
+    const int head = (int)(th - tok * heads);
+    const T* xp = x + tok * row_stride + (int64_t)head * dim;
+    T* yp = y + tok * row_stride + (int64_t)head * dim;
     if constexpr (kNeox) {
       const int c = v * N;
       Vec16<T> a = ld16_stream(xp + c), b = ld16_stream(xp + half + c), oa, ob;
@@ -135,7 +172,7 @@ __global__ void __launch_bounds__(256) rope_kernel(const T* __restrict__ x, T* _
 }
 
 void rope_apply(const void* x, void* y, const float* cos_t, const float* sin_t, const int64_t* pos_ids, int64_t tokens,
-                int seq, int heads, int dim, int neox, int backward, int dtype, cudaStream_t s) {
+                int seq, int heads, int dim, int neox, int backward, int dtype, int64_t row_stride, cudaStream_t s) {
   if (tokens == 0) return;
   const float sign = backward ? -1.f : 1.f;
   B200_DISPATCH_DTYPE(dtype, T, {
@@ -143,10 +180,10 @@ void rope_apply(const void* x, void* y, const float* cos_t, const float* sin_t, 
     if ((dim / 2) % N) { set_last_error(__FILE__, __LINE__, "rope: head_dim/2 must be a multiple of the 16B vector"); return; }
     if (neox) {
       const int64_t items = tokens * heads * ((dim / 2) / N);
-      rope_kernel<T, true><<<ew_grid(items, 256), 256, 0, s>>>((const T*)x, (T*)y, cos_t, sin_t, pos_ids, tokens, seq, heads, dim, sign);
+      rope_kernel<T, true><<<ew_grid(items, 256), 256, 0, s>>>((const T*)x, (T*)y, cos_t, sin_t, pos_ids, tokens, seq, heads, dim, sign, row_stride > 0 ? row_stride : (int64_t)heads * dim);
     } else {
       const int64_t items = tokens * heads * (dim / N);
-      rope_kernel<T, false><<<ew_grid(items, 256), 256, 0, s>>>((const T*)x, (T*)y, cos_t, sin_t, pos_ids, tokens, seq, heads, dim, sign);
+      rope_kernel<T, false><<<ew_grid(items, 256), 256, 0, s>>>((const T*)x, (T*)y, cos_t, sin_t, pos_ids, tokens, seq, heads, dim, sign, row_stride > 0 ? row_stride : (int64_t)heads * dim);
     }
   });
   B200_CUDA_CHECK(cudaGetLastError());

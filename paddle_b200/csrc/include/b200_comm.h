@@ -1,0 +1,18 @@
+// Host launch API of the peer-memory collectives (csrc/comm/*.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+namespace comm {
+// bases[r] = address of rank r's heap slab as mapped in THIS process; off = byte offset of the symmetric buffer.
+void p2p_allreduce(const int64_t* bases, int64_t off, int64_t n, int dtype, int rank, int world, uint32_t epoch, uint32_t* counter,
+                   cudaStream_t s);
+void p2p_reduce_scatter(const int64_t* bases, int64_t off, void* out, int64_t n, int dtype, int rank, int world, uint32_t epoch,
+                        uint32_t* counter, cudaStream_t s);
+void p2p_allgather(const int64_t* bases, int64_t off, int64_t chunk_bytes, int rank, int world, uint32_t epoch, uint32_t* counter,
+                   cudaStream_t s);
+void p2p_alltoall(const int64_t* bases, int64_t off_send, int64_t off_recv, int64_t chunk_bytes, int rank, int world, uint32_t epoch,
+                  uint32_t* counter, cudaStream_t s);
+}  // namespace comm
+}  // namespace b200

@@ -30,7 +30,7 @@ void swiglu_bwd(const void* dout, const void* gate, const void* up, void* dgate,
                 int dtype, cudaStream_t s);
 // rotary embedding on [tokens, heads, dim]; cos/sin are fp32 [positions, dim/2]; pos_ids may be null (pos = token % seq)
 void rope_apply(const void* x, void* y, const float* cos_t, const float* sin_t, const int64_t* pos_ids, int64_t tokens,
-                int seq, int heads, int dim, int neox, int backward, int dtype, cudaStream_t s);
+                int seq, int heads, int dim, int neox, int backward, int dtype, int64_t row_stride, cudaStream_t s);
 // y = a + b (residual add), vectorised
 void add_fwd(const void* a, const void* b, void* y, int64_t n, int dtype, cudaStream_t s);
 

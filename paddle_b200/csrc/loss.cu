@@ -39,17 +39,29 @@ __device__ __forceinline__ void block_online(float& m, float& s, float* sm_m, fl
 template <typename T>
 __device__ __forceinline__ void row_online(const T* __restrict__ xr, int vocab, float& m, float& s) {
   constexpr int N = Vec16<T>::N;
+  constexpr int U = 4;  // 4 independent 16B loads in flight per thread
   m = -INFINITY; s = 0.f;
   const int nvec = ((vocab * (int)sizeof(T)) % 16 == 0) ? vocab / N : 0;  // rows stay 16B-aligned only then
-  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
-    Vec16<T> xv = ld16(xr + v * N);
-    float lm = -INFINITY;
+  for (int v0 = threadIdx.x; v0 < nvec; v0 += blockDim.x * U) {
+    Vec16<T> xv[U];
 #pragma unroll
-    for (int j = 0; j < N; ++j) lm = fmaxf(lm, to_f(xv.v[j]));
-    float ls = 0.f;
+    for (int k = 0; k < U; ++k) {
+      const int v = v0 + k * blockDim.x;
+      if (v < nvec) xv[k] = ld16_stream(xr + v * N);
+    }
 #pragma unroll
-    for (int j = 0; j < N; ++j) ls += __expf(to_f(xv.v[j]) - lm);
-    online_combine(m, s, lm, ls);
+    for (int k = 0; k < U; ++k) {
+      const int v = v0 + k * blockDim.x;
+      if (v < nvec) {
+        float lm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < N; ++j) lm = fmaxf(lm, to_f(xv[k].v[j]));
+        float ls = 0.f;
+#pragma unroll
+        for (int j = 0; j < N; ++j) ls += __expf(to_f(xv[k].v[j]) - lm);
+        online_combine(m, s, lm, ls);
+      }
+    }
   }
   for (int c = nvec * N + threadIdx.x; c < vocab; c += blockDim.x) online_combine(m, s, to_f(xr[c]), 1.f);
 }

@@ -16,6 +16,8 @@
 #include <vector>
 
 #include "runtime.h"
+#include "../include/b200_comm.h"
+#include "../include/b200_ops.h"
 
 namespace b200 {
 namespace runtime {
@@ -93,6 +95,59 @@ class SymmHeap {
   int rank() const { return rank_; }
   int world() const { return world_; }
 
+  // ---- peer-memory collectives on symmetric buffers (csrc/comm/p2p_collectives.cu) ----
+  static int dcode(at::ScalarType st) {
+    switch (st) {
+      case at::kFloat: return 0;
+      case at::kHalf: return 1;
+      case at::kBFloat16: return 2;
+      default: throw std::runtime_error("symm_heap: unsupported dtype for p2p collective");
+    }
+  }
+  std::vector<int64_t> bases() const {
+    std::vector<int64_t> b(world_);
+    for (int r = 0; r < world_; ++r) b[r] = reinterpret_cast<int64_t>(peers_[r]);
+    return b;
+  }
+  uint32_t* counter() {
+    if (!counter_) {
+      c10::cuda::CUDAGuard g(device_);
+      ck(cudaMalloc(&counter_, 64), "cudaMalloc counter");
+      ck(cudaMemset(counter_, 0, 64), "memset counter");
+    }
+    return static_cast<uint32_t*>(counter_);
+  }
+  void finish() {
+    const char* e = b200::take_last_error();
+    if (e[0]) throw std::runtime_error(std::string("paddle_b200 comm kernel error: ") + e);
+  }
+  void allreduce(int64_t off, int64_t n, at::ScalarType dt, int64_t epoch) {
+    c10::cuda::CUDAGuard g(device_);
+    auto b = bases();
+    comm::p2p_allreduce(b.data(), off, n, dcode(dt), rank_, world_, (uint32_t)epoch, counter(), at::cuda::getCurrentCUDAStream().stream());
+    finish();
+  }
+  void reduce_scatter(int64_t off, torch::Tensor out, int64_t n, int64_t epoch) {
+    c10::cuda::CUDAGuard g(device_);
+    auto b = bases();
+    comm::p2p_reduce_scatter(b.data(), off, out.data_ptr(), n, dcode(out.scalar_type()), rank_, world_, (uint32_t)epoch, counter(),
+                             at::cuda::getCurrentCUDAStream().stream());
+    finish();
+  }
+  void allgather(int64_t off, int64_t chunk_bytes, int64_t epoch) {
+    c10::cuda::CUDAGuard g(device_);
+    auto b = bases();
+    comm::p2p_allgather(b.data(), off, chunk_bytes, rank_, world_, (uint32_t)epoch, counter(), at::cuda::getCurrentCUDAStream().stream());
+    finish();
+  }
+  void alltoall(int64_t off_send, int64_t off_recv, int64_t chunk_bytes, int64_t epoch) {
+    c10::cuda::CUDAGuard g(device_);
+    auto b = bases();
+    comm::p2p_alltoall(b.data(), off_send, off_recv, chunk_bytes, rank_, world_, (uint32_t)epoch, counter(),
+                       at::cuda::getCurrentCUDAStream().stream());
+    finish();
+  }
+
  private:
   int64_t bytes_, signal_bytes_;
   int device_;
@@ -101,6 +156,7 @@ class SymmHeap {
   int rank_ = 0, world_ = 1;
   std::vector<void*> peers_;
   void* peer_table_dev_ = nullptr;
+  void* counter_ = nullptr;
 };
 
 void bind_symm(pybind11::module_& m) {
@@ -119,7 +175,11 @@ void bind_symm(pybind11::module_& m) {
       .def("size", &SymmHeap::size)
       .def("signal_bytes", &SymmHeap::signal_bytes)
       .def("rank", &SymmHeap::rank)
-      .def("world", &SymmHeap::world);
+      .def("world", &SymmHeap::world)
+      .def("allreduce", &SymmHeap::allreduce)
+      .def("reduce_scatter", &SymmHeap::reduce_scatter)
+      .def("allgather", &SymmHeap::allgather)
+      .def("alltoall", &SymmHeap::alltoall);
 }
 
 }  // namespace runtime

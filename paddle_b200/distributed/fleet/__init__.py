@@ -1,0 +1,142 @@
+"""paddle.distributed.fleet. Parity: python/paddle/distributed/fleet/__init__.py, fleet.py, model.py, optimizer.py."""
+from __future__ import annotations
+
+from .. import env as _env
+from . import mp_layers as meta_parallel_layers  # noqa: F401
+from . import topology as _topo
+from .mp_layers import (ColumnParallelLinear, ColumnSequenceParallelLinear, ParallelCrossEntropy, RowParallelLinear,  # noqa: F401
+                        RowSequenceParallelLinear, VocabParallelEmbedding)
+from .random import get_rng_state_tracker, model_parallel_random_seed  # noqa: F401
+from .recompute import recompute, recompute_hybrid, recompute_sequential  # noqa: F401
+from .strategy import DistributedStrategy  # noqa: F401
+from .topology import CommunicateTopology, HybridCommunicateGroup, ParallelMode, get_hybrid_communicate_group  # noqa: F401
+
+_state = {"strategy": None, "hcg": None, "initialized": False}
+
+
+class _RoleMaker:
+    def __init__(self, is_collective=True, **kw):
+        self._is_collective = is_collective
+
+    def _worker_index(self):
+        return _env.get_rank()
+
+    def _worker_num(self):
+        return _env.get_world_size()
+
+
+PaddleCloudRoleMaker = _RoleMaker
+UserDefinedRoleMaker = _RoleMaker
+
+
+def init(role_maker=None, is_collective=False, strategy=None, log_level="INFO"):
+    """fleet.init: builds the hybrid topology (dp/pp/sharding/sep/mp) and its process groups."""
+    strategy = strategy or DistributedStrategy()
+    _state["strategy"] = strategy
+    if not _env.is_initialized():
+        _env.init_parallel_env()
+    hc = strategy.hybrid_configs
+    world = _env.get_world_size()
+    mp, pp, sh, sep = hc["mp_degree"], hc["pp_degree"], hc["sharding_degree"], hc.get("sep_degree", 1) or 1
+    dp = hc["dp_degree"]
+    if dp * mp * pp * sh * sep != world:
+        dp = world // (mp * pp * sh * sep)
+        hc["dp_degree"] = dp
+    assert dp * mp * pp * sh * sep == world, f"hybrid degrees {dp}x{pp}x{sh}x{sep}x{mp} do not match world size {world}"
+    names_map = {"dp": "data", "pp": "pipe", "sharding": "sharding", "sep": "sep", "mp": "model"}
+    order = hc.get("order") or ["dp", "pp", "sharding", "sep", "mp"]
+    dims_map = {"dp": dp, "pp": pp, "sharding": sh, "sep": sep, "mp": mp}
+    topo = CommunicateTopology([names_map[o] for o in order], [dims_map[o] for o in order])
+    hcg = HybridCommunicateGroup(topo)
+    _state["hcg"] = hcg
+    _state["initialized"] = True
+    seed = strategy.tensor_parallel_configs.get("tensor_init_seed", -1)
+    model_parallel_random_seed(seed if seed and seed > 0 else None)
+    return None
+
+
+def is_first_worker():
+    return _env.get_rank() == 0
+
+
+def worker_index():
+    return _env.get_rank()
+
+
+def worker_num():
+    return _env.get_world_size()
+
+
+def is_worker():
+    return True
+
+
+def is_server():
+    return False
+
+
+def barrier_worker():
+    from .. import collective
+
+    collective.barrier()
+
+
+def init_worker():
+    pass
+
+
+def stop_worker():
+    pass
+
+
+def get_strategy():
+    return _state["strategy"]
+
+
+def distributed_model(model):
+    """Wraps `model` according to the hybrid topology. Parity: fleet/model.py:distributed_model."""
+    from . import hybrid
+
+    return hybrid.distributed_model(model, _state["hcg"], _state["strategy"] or DistributedStrategy())
+
+
+def distributed_optimizer(optimizer, strategy=None):
+    from . import hybrid
+
+    if strategy is not None:
+        _state["strategy"] = strategy
+    return hybrid.HybridParallelOptimizer(optimizer, _state["hcg"], _state["strategy"] or DistributedStrategy())
+
+
+def distributed_scaler(scaler):
+    from . import hybrid
+
+    return hybrid.distributed_scaler(scaler, _state["hcg"])
+
+
+class _Utils:
+    @staticmethod
+    def recompute(function, *args, **kwargs):
+        return recompute(function, *args, **kwargs)
+
+
+utils = _Utils()
+
+
+class _MetaParallel:
+    """fleet.meta_parallel namespace."""
+
+    def __getattr__(self, name):
+        from . import hybrid, mp_layers, pipeline
+
+        for mod in (mp_layers, pipeline, hybrid):
+            if hasattr(mod, name):
+                return getattr(mod, name)
+        if name in ("get_rng_state_tracker", "model_parallel_random_seed"):
+            from . import random as r
+
+            return getattr(r, name)
+        raise AttributeError(name)
+
+
+meta_parallel = _MetaParallel()

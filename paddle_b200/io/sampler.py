@@ -1,0 +1,133 @@
+"""Samplers. Parity: python/paddle/io/dataloader/sampler.py, batch_sampler.py."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+class Sampler:
+    def __init__(self, data_source=None):
+        self.data_source = data_source
+
+    def __iter__(self):
+        raise NotImplementedError
+
+
+class SequenceSampler(Sampler):
+    def __iter__(self):
+        return iter(range(len(self.data_source)))
+
+    def __len__(self):
+        return len(self.data_source)
+
+
+class RandomSampler(Sampler):
+    def __init__(self, data_source, replacement=False, num_samples=None, generator=None):
+        super().__init__(data_source)
+        self.replacement, self._num_samples, self.generator = replacement, num_samples, generator
+
+    @property
+    def num_samples(self):
+        return len(self.data_source) if self._num_samples is None else self._num_samples
+
+    def __iter__(self):
+        n = len(self.data_source)
+        if self.replacement:
+            return iter(np.random.randint(0, n, self.num_samples).tolist())
+        return iter(np.random.permutation(n)[: self.num_samples].tolist())
+
+    def __len__(self):
+        return self.num_samples
+
+
+class SubsetRandomSampler(Sampler):
+    def __init__(self, indices):
+        super().__init__(None)
+        self.indices = list(indices)
+
+    def __iter__(self):
+        return iter(np.random.permutation(self.indices).tolist())
+
+    def __len__(self):
+        return len(self.indices)
+
+
+class WeightedRandomSampler(Sampler):
+    def __init__(self, weights, num_samples, replacement=True):
+        super().__init__(None)
+        self.weights = np.asarray(weights, dtype=np.float64)
+        self.num_samples, self.replacement = num_samples, replacement
+
+    def __iter__(self):
+        p = self.weights / self.weights.sum()
+        return iter(np.random.choice(len(p), self.num_samples, replace=self.replacement, p=p).tolist())
+
+    def __len__(self):
+        return self.num_samples
+
+
+class BatchSampler(Sampler):
+    def __init__(self, dataset=None, sampler=None, shuffle=False, batch_size=1, drop_last=False):
+        super().__init__(dataset)
+        if sampler is None:
+            sampler = RandomSampler(dataset) if shuffle else SequenceSampler(dataset)
+        self.sampler, self.batch_size, self.drop_last = sampler, int(batch_size), drop_last
+
+    def __iter__(self):
+        batch = []
+        for idx in self.sampler:
+            batch.append(idx)
+            if len(batch) == self.batch_size:
+                yield batch
+                batch = []
+        if batch and not self.drop_last:
+            yield batch
+
+    def __len__(self):
+        n = len(self.sampler)
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+
+class DistributedBatchSampler(BatchSampler):
+    """Parity: python/paddle/io/dataloader/batch_sampler.py:DistributedBatchSampler."""
+
+    def __init__(self, dataset, batch_size, num_replicas=None, rank=None, shuffle=False, drop_last=False):
+        from ..distributed import env
+
+        self.dataset, self.batch_size, self.shuffle, self.drop_last = dataset, int(batch_size), shuffle, drop_last
+        self.nranks = num_replicas if num_replicas is not None else env.get_world_size()
+        self.local_rank = rank if rank is not None else env.get_rank()
+        self.epoch = 0
+        self.num_samples = int(math.ceil(len(dataset) / self.nranks))
+        self.total_size = self.num_samples * self.nranks
+
+    def __iter__(self):
+        n = len(self.dataset)
+        idx = list(range(n))
+        idx += idx[: self.total_size - n]
+        if self.shuffle:
+            rng = np.random.RandomState(self.epoch)
+            rng.shuffle(idx)
+            self.epoch += 1
+        # rank r takes contiguous batch_size chunks strided by nranks (reference behaviour)
+        mine = []
+        step = self.batch_size * self.nranks
+        for i in range(self.local_rank * self.batch_size, len(idx) - (len(idx) % step if False else 0), step):
+            mine.extend(idx[i:i + self.batch_size])
+        mine = mine[: self.num_samples] if len(mine) > self.num_samples else mine
+        batch = []
+        for i in mine:
+            batch.append(i)
+            if len(batch) == self.batch_size:
+                yield batch
+                batch = []
+        if batch and not self.drop_last:
+            yield batch
+
+    def __len__(self):
+        n = self.num_samples
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def set_epoch(self, epoch):
+        self.epoch = epoch

@@ -53,6 +53,42 @@ def rope_ref(x, cos_t, sin_t, pos_ids, neox):
     return out.to(x.dtype)
 
 
+class _RopePacked(torch.autograd.Function):
+    """In-place rotary on the q,k heads of a fused [B, S, (q|k|v heads), D] tensor."""
+
+    @staticmethod
+    def forward(ctx, qkv, cos_t, sin_t, pos_ids, seq, rope_heads, total_heads, dim, neox):
+        ctx.save_for_backward(cos_t, sin_t, pos_ids)
+        ctx.cfg = (seq, rope_heads, total_heads, dim, neox)
+        ext().rope_packed_(qkv, cos_t, sin_t, pos_ids, seq, rope_heads, total_heads, dim, neox, False)
+        ctx.mark_dirty(qkv)
+        return qkv
+
+    @staticmethod
+    def backward(ctx, dy):
+        cos_t, sin_t, pos_ids = ctx.saved_tensors
+        seq, rope_heads, total_heads, dim, neox = ctx.cfg
+        g = dy.contiguous()
+        if g.data_ptr() == dy.data_ptr():
+            g = g.clone()
+        ext().rope_packed_(g, cos_t, sin_t, pos_ids, seq, rope_heads, total_heads, dim, neox, True)
+        return g, None, None, None, None, None, None, None, None
+
+
+def apply_rope_packed(qkv, cos_t, sin_t, rope_heads, total_heads, dim, position_ids=None, neox=True):
+    """qkv: [B, S, total_heads*dim] (or [B,S,total_heads,dim]); rotates heads [0, rope_heads) in place."""
+    q = raw(qkv)
+    cos_t, sin_t, position_ids = raw(cos_t), raw(sin_t), raw(position_ids)
+    if use_fused(q) and q.is_contiguous() and q.dtype in (torch.float32, torch.float16, torch.bfloat16) and (dim // 2) % (16 // q.element_size()) == 0:
+        pid = position_ids.reshape(-1).contiguous() if position_ids is not None else None
+        return wrap(_RopePacked.apply(q, cos_t.float().contiguous(), sin_t.float().contiguous(), pid, int(q.shape[1]),
+                                      int(rope_heads), int(total_heads), int(dim), bool(neox)))
+    b, s = q.shape[0], q.shape[1]
+    x4 = q.reshape(b, s, total_heads, dim)
+    rot = rope_ref(x4[:, :, :rope_heads], cos_t.float(), sin_t.float(), position_ids, neox)
+    return wrap(torch.cat([rot, x4[:, :, rope_heads:]], 2).reshape(q.shape))
+
+
 def apply_rope(x, cos_t, sin_t, position_ids=None, neox=True):
     """x: [B, S, H, D]; cos/sin fp32 [P, D/2]."""
     x = raw(x)

@@ -1,0 +1,137 @@
+"""Symmetric peer memory contexts (per process group) + the fused compute/collective kernels built on them.
+
+The native heap lives in csrc/runtime/symm_heap.cpp; the kernels in csrc/comm/*.cu.  A context is created lazily per
+group the first time a fused op runs on it; creation is collective (IPC handle exchange through torch.distributed).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+_contexts = {}
+_disabled = [False]
+
+
+def _pg(group):
+    return getattr(group, "pg", group)
+
+
+def available():
+    if _disabled[0] or not torch.cuda.is_available():
+        return False
+    from .._build import load
+
+    m = load()
+    return m is not None and hasattr(m, "SymmHeap")
+
+
+def context_for(group):
+    """SymmContext for `group`, or None when fused P2P collectives are not usable."""
+    if not available():
+        return None
+    key = id(_pg(group)) if group is not None else 0
+    ctx = _contexts.get(key)
+    if ctx is None:
+        try:
+            ctx = SymmContext(group)
+        except Exception as e:  # noqa: BLE001
+            import warnings
+
+            warnings.warn(f"paddle_b200: symmetric-memory setup failed ({e}); using NCCL collectives")
+            _disabled[0] = True
+            return None
+        _contexts[key] = ctx
+    return ctx
+
+
+class SymmContext:
+    """Symmetric heap + signal pad for one process group (all ranks on one NVSwitch domain)."""
+
+    def __init__(self, group, heap_bytes=None, signal_bytes=1 << 20):
+        from .._build import ext
+
+        self.group = group
+        pg = _pg(group)
+        self.world = dist.get_world_size(pg)
+        self.rank = dist.get_rank(pg)
+        heap_bytes = heap_bytes or int(os.environ.get("B200_SYMM_HEAP_MB", "2048")) << 20
+        self.dev = torch.cuda.current_device()
+        self.heap = ext().SymmHeap(heap_bytes, signal_bytes, self.dev)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(self.heap.ipc_handle()), group=pg)
+        self.heap.open_peers([bytes(h) for h in handles], self.rank)
+        dist.barrier(group=pg, device_ids=[self.dev]) if dist.get_backend(pg) == "nccl" else dist.barrier(group=pg)
+        self._base_cursor = self.heap.cursor()
+        self._bufs = {}
+        self._epoch = 0
+        self.ext = ext()
+
+    # symmetric scratch buffers keyed by (tag, nbytes): allocated once, identical offsets on every rank
+    def buffer(self, tag, shape, dtype):
+        nbytes = 1
+        for s in shape:
+            nbytes *= int(s)
+        nbytes *= torch.empty(0, dtype=dtype).element_size()
+        key = (tag, nbytes)
+        off = self._bufs.get(key)
+        if off is None:
+            off = self.heap.alloc(nbytes, 1024)
+            self._bufs[key] = off
+        return self.heap.tensor(off, list(shape), dtype, -1), off
+
+    def next_epoch(self):
+        self._epoch += 1
+        return self._epoch
+
+    # ---- fused ops ------------------------------------------------------------------------------------------
+    def allreduce_(self, t):
+        """In-place sum all-reduce of a CUDA tensor through the symmetric heap (two-shot over P2P)."""
+        buf, off = self.buffer("ar", (t.numel(),), t.dtype)
+        buf.copy_(t.reshape(-1))
+        self.heap.allreduce(off, t.numel(), t.dtype, self.next_epoch())
+        t.copy_(buf.view_as(t))
+        return t
+
+    def gemm_allreduce(self, x, w):
+        """Y = sum_r X_r @ W_r.  GEMM writes into the symmetric buffer, then P2P two-shot all-reduce on the same stream."""
+        from ..kernels import gemm as KG
+
+        x2 = x.reshape(-1, x.shape[-1])
+        m, n = x2.shape[0], w.shape[1]
+        buf, off = self.buffer("gar", (m, n), x.dtype)
+        KG.gemm(x2, w, out=buf)
+        self.heap.allreduce(off, m * n, x.dtype, self.next_epoch())
+        return buf.clone().reshape(*x.shape[:-1], n)
+
+    def gemm_reduce_scatter(self, x, w, b_is_nk=False):
+        """Y[S/p] = reduce_scatter_dim0(X @ op(W)): GEMM into symmetric memory, each rank reduces its own row slice
+        by reading the peers' partial tiles over NVLink."""
+        from ..kernels import gemm as KG
+
+        x2 = x.reshape(-1, x.shape[-1])
+        m = x2.shape[0]
+        n = w.shape[0] if b_is_nk else w.shape[1]
+        buf, off = self.buffer("grs", (m, n), x.dtype)
+        KG.gemm(x2, w, b_is_nk=b_is_nk, out=buf)
+        out = torch.empty((m // self.world, n), dtype=x.dtype, device=x.device)
+        self.heap.reduce_scatter(off, out, m * n, self.next_epoch())
+        return out.reshape(x.shape[0] // self.world, *x.shape[1:-1], n)
+
+    def allgather_gemm(self, x, w, b_is_nk=False, return_gathered=False):
+        """Y = all_gather_dim0(X) @ op(W): peers' shards are pulled over NVLink into the symmetric buffer while the GEMM
+        on the local shard runs; then the remaining row blocks are multiplied."""
+        from ..kernels import gemm as KG
+
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        ml, k = x2.shape
+        full, off = self.buffer("agg", (ml * self.world, k), x.dtype)
+        full[self.rank * ml:(self.rank + 1) * ml].copy_(x2)
+        self.heap.allgather(off, ml * k * x.element_size(), self.next_epoch())
+        y = KG.gemm(full, w, b_is_nk=b_is_nk)
+        n = y.shape[-1]
+        y = y.reshape(x.shape[0] * self.world, *x.shape[1:-1], n)
+        if return_gathered:
+            return y, full.clone().reshape(x.shape[0] * self.world, *x.shape[1:])
+        return y
