@@ -86,12 +86,29 @@ class SymmContext:
         return self._epoch
 
     # ---- fused ops ------------------------------------------------------------------------------------------
+    def max_message_bytes(self):
+        return 1 << 62  # large messages are streamed through the staging window in chunks
+
+    def owns(self, t):
+        base = self.heap.base_ptr()
+        return base <= t.data_ptr() and t.data_ptr() + t.numel() * t.element_size() <= base + self.heap.size()
+
     def allreduce_(self, t):
-        """In-place sum all-reduce of a CUDA tensor through the symmetric heap (two-shot over P2P)."""
-        buf, off = self.buffer("ar", (t.numel(),), t.dtype)
-        buf.copy_(t.reshape(-1))
-        self.heap.allreduce(off, t.numel(), t.dtype, self.next_epoch())
-        t.copy_(buf.view_as(t))
+        """In-place sum all-reduce of a contiguous CUDA tensor (two-shot over peer memory).
+        Tensors that already live in the symmetric heap (flat gradient arenas placed there) are reduced in place with no
+        staging copy; others stream through a staging window."""
+        flat = t.reshape(-1)
+        if self.owns(flat):
+            self.heap.allreduce(flat.data_ptr() - self.heap.base_ptr(), flat.numel(), flat.dtype, self.next_epoch())
+            return t
+        window = int(os.environ.get("B200_SYMM_WINDOW_MB", "256")) << 20
+        per = max(1, window // flat.element_size())
+        buf, off = self.buffer("ar", (min(per, flat.numel()),), flat.dtype) if flat.numel() <= per else self.buffer("ar", (per,), flat.dtype)
+        for lo in range(0, flat.numel(), per):
+            hi = min(flat.numel(), lo + per)
+            buf[: hi - lo].copy_(flat[lo:hi])
+            self.heap.allreduce(off, hi - lo, flat.dtype, self.next_epoch())
+            flat[lo:hi].copy_(buf[: hi - lo])
         return t
 
     def gemm_allreduce(self, x, w):

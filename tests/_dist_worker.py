@@ -1,0 +1,301 @@
+"""Worker body for the multi-process tests. Each case compares the parallel result with a single-process reference
+computed locally with identical seeds (the reference's hybrid_parallel_* test pattern)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+import paddle_b200 as paddle
+import paddle_b200.distributed as dist
+from paddle_b200 import nn
+from paddle_b200.distributed import fleet
+
+GPU = torch.cuda.is_available() and os.environ.get("B200_TEST_GPU", "0") == "1"
+
+
+def setup(dp=1, mp=1, pp=1, sharding=1):
+    if GPU:
+        paddle.set_device(f"gpu:{os.environ['LOCAL_RANK']}")
+    s = fleet.DistributedStrategy()
+    s.hybrid_configs = {"dp_degree": dp, "mp_degree": mp, "pp_degree": pp, "sharding_degree": sharding}
+    fleet.init(is_collective=True, strategy=s)
+    return s, fleet.get_hybrid_communicate_group()
+
+
+def close(a, b, tol=1e-4):
+    a, b = torch.as_tensor(np.asarray(a, dtype=np.float64)), torch.as_tensor(np.asarray(b, dtype=np.float64))
+    err = (a - b).abs().max().item() / max(1e-8, b.abs().max().item())
+    assert err < tol, f"mismatch {err}"
+
+
+def case_collectives():
+    dist.init_parallel_env()
+    r, w = dist.get_rank(), dist.get_world_size()
+    t = paddle.to_tensor([float(r + 1)] * 4)
+    dist.all_reduce(t)
+    close(t.numpy(), [sum(range(1, w + 1))] * 4)
+    outs = []
+    dist.all_gather(outs, paddle.to_tensor([float(r)]))
+    close([o.item() for o in outs], list(range(w)))
+    b = paddle.to_tensor([float(r)])
+    dist.broadcast(b, 1)
+    close(b.numpy(), [1.0])
+    objs = []
+    dist.all_gather_object(objs, {"r": r})
+    assert [o["r"] for o in objs] == list(range(w))
+    ins = [paddle.to_tensor([float(r * 10 + j)]) for j in range(w)]
+    res = []
+    dist.alltoall(res, ins)
+    close([x.item() for x in res], [j * 10 + r for j in range(w)])
+    g = dist.new_group(list(range(w)))
+    x = paddle.to_tensor([1.0])
+    dist.all_reduce(x, group=g)
+    close(x.numpy(), [float(w)])
+    if r == 0:
+        dist.send(paddle.to_tensor([42.0]), dst=1)
+    elif r == 1:
+        y = paddle.zeros([1])
+        dist.recv(y, src=0)
+        close(y.numpy(), [42.0])
+    dist.barrier()
+
+
+def _mlp_ref(seed, din, dh, dout):
+    paddle.seed(seed)
+    return nn.Linear(din, dh), nn.Linear(dh, dout)
+
+
+def case_mp_layers():
+    """Column+Row parallel MLP == dense MLP (loss and grads). Parity: test/collective/fleet/hybrid_parallel_mp_layers.py."""
+    _, hcg = setup(mp=2)
+    r = hcg.get_model_parallel_rank()
+    paddle.seed(7)
+    w1 = paddle.randn([16, 32]) * 0.1
+    w2 = paddle.randn([32, 8]) * 0.1
+    x = paddle.randn([4, 16])
+    col = fleet.ColumnParallelLinear(16, 32, has_bias=False, gather_output=False)
+    row = fleet.RowParallelLinear(32, 8, has_bias=False, input_is_parallel=True)
+    col.weight.set_value(w1[:, r * 16:(r + 1) * 16])
+    row.weight.set_value(w2[r * 16:(r + 1) * 16])
+    y = row(paddle.nn.functional.relu(col(x)))
+    loss = (y * y).sum()
+    loss.backward()
+    w1r, w2r = paddle.to_tensor(w1, stop_gradient=False), paddle.to_tensor(w2, stop_gradient=False)
+    yr = paddle.nn.functional.relu(x @ w1r) @ w2r
+    lr = (yr * yr).sum()
+    lr.backward()
+    close(loss.item(), lr.item())
+    close(col.weight.grad.numpy(), w1r.grad[:, r * 16:(r + 1) * 16].numpy())
+    close(row.weight.grad.numpy(), w2r.grad[r * 16:(r + 1) * 16].numpy())
+    # vocab parallel embedding + parallel cross entropy
+    emb = fleet.VocabParallelEmbedding(20, 6)
+    full = paddle.randn([20, 6])
+    emb.weight.set_value(full[r * 10:(r + 1) * 10])
+    ids = paddle.to_tensor([[1, 15, 7], [19, 0, 11]])
+    close(emb(ids).numpy(), full[ids].numpy())
+    logits = paddle.randn([5, 12])
+    lab = paddle.to_tensor([0, 3, 11, 6, 7])
+    pce = fleet.ParallelCrossEntropy()
+    lp = pce(logits[:, r * 6:(r + 1) * 6], lab)
+    ref = paddle.nn.functional.cross_entropy(logits, lab, reduction="none")
+    close(lp.numpy().reshape(-1), ref.numpy().reshape(-1))
+
+
+def case_sequence_parallel():
+    _, hcg = setup(mp=2)
+    r = hcg.get_model_parallel_rank()
+    paddle.seed(3)
+    w1 = paddle.randn([8, 16]) * 0.2
+    w2 = paddle.randn([16, 8]) * 0.2
+    x = paddle.randn([6, 2, 8])  # [S, B, H]
+    col = fleet.ColumnSequenceParallelLinear(8, 16, has_bias=False)
+    row = fleet.RowSequenceParallelLinear(16, 8, has_bias=False)
+    col.weight.set_value(w1[:, r * 8:(r + 1) * 8])
+    row.weight.set_value(w2[r * 8:(r + 1) * 8])
+    xl = paddle.to_tensor(x[r * 3:(r + 1) * 3], stop_gradient=False)
+    y = row(paddle.tanh(col(xl)))
+    (y * y).sum().backward()
+    xr = paddle.to_tensor(x, stop_gradient=False)
+    w1r, w2r = paddle.to_tensor(w1, stop_gradient=False), paddle.to_tensor(w2, stop_gradient=False)
+    yr = paddle.tanh(xr @ w1r) @ w2r
+    (yr * yr).sum().backward()
+    close(y.numpy(), yr[r * 3:(r + 1) * 3].numpy())
+    close(xl.grad.numpy(), xr.grad[r * 3:(r + 1) * 3].numpy())
+    close(col.weight.grad.numpy(), w1r.grad[:, r * 8:(r + 1) * 8].numpy())
+    close(row.weight.grad.numpy(), w2r.grad[r * 8:(r + 1) * 8].numpy())
+
+
+def _tiny_llama(cfg_kw):
+    from paddle_b200.models import llama as L
+
+    return L, L.llama_tiny(dtype="float32", **cfg_kw)
+
+
+def _train_ref(L, cfg, ids, steps, lr=1e-2):
+    paddle.seed(11)
+    m = L.LlamaForCausalLM(cfg)
+    opt = paddle.optimizer.AdamW(lr, parameters=m.parameters(), weight_decay=0.0)
+    losses = []
+    for _ in range(steps):
+        loss = m(ids[:, :-1], ids[:, 1:])
+        loss.backward()
+        opt.step()
+        opt.clear_grad()
+        losses.append(loss.item())
+    return m, losses
+
+
+def case_dp():
+    """DataParallel: 2 ranks x half batch == 1 rank x full batch. Parity: test/collective parallel_dygraph_*."""
+    dist.init_parallel_env()
+    r, w = dist.get_rank(), dist.get_world_size()
+    paddle.seed(5)
+    net = nn.Sequential(nn.Linear(8, 16), nn.Tanh(), nn.Linear(16, 4))
+    ref = nn.Sequential(nn.Linear(8, 16), nn.Tanh(), nn.Linear(16, 4))
+    ref.set_state_dict(net.state_dict())
+    x = paddle.randn([8, 8])
+    y = paddle.randn([8, 4])
+    dp = paddle.DataParallel(net, comm_buffer_size=1)
+    opt = paddle.optimizer.SGD(0.1, parameters=dp.parameters())
+    ropt = paddle.optimizer.SGD(0.1, parameters=ref.parameters())
+    for _ in range(3):
+        sl = slice(r * 4, (r + 1) * 4)
+        loss = ((dp(x[sl]) - y[sl]) ** 2).mean()
+        loss.backward()
+        opt.step()
+        opt.clear_grad()
+        lr_ = ((ref(x) - y) ** 2).mean()
+        lr_.backward()
+        ropt.step()
+        ropt.clear_grad()
+    for (k, a), (_, b) in zip(net.state_dict().items(), ref.state_dict().items()):
+        close(a.numpy(), b.numpy(), 1e-4)
+
+
+def case_pp():
+    """PipelineParallel 1F1B (pp=2, 4 micro-batches) == single-process training. Parity: hybrid_parallel_pp_*.py."""
+    s, hcg = setup(pp=2)
+    L, cfg = _tiny_llama({})
+    ids = paddle.to_tensor(np.random.RandomState(0).randint(0, cfg.vocab_size, (4, 33)))
+    s.pipeline_configs = {"accumulate_steps": 4, "micro_batch_size": 1}
+    paddle.seed(11)
+    from paddle_b200.distributed.fleet.pipeline import PipelineLayer
+
+    # build the reference first with the same seed stream, then load its weights into this stage's layers
+    ref, ref_losses = _train_ref(L, cfg, ids, 0)
+    ref_sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    pl = PipelineLayer(L.pipeline_layer_descs(cfg), num_stages=2, loss_fn=L.LlamaPretrainingCriterion(cfg), seg_method="layer:LlamaDecoderLayer")
+    # map pipeline names -> reference names
+    mapping = {}
+    for name, _ in pl.named_parameters():
+        idx, rest = name.split(".", 1)
+        i = int(idx)
+        if i == 0:
+            mapping[name] = "llama.embedding." + rest
+        elif i == cfg.num_hidden_layers + 1:
+            mapping[name] = "lm_head." + rest
+        else:
+            mapping[name] = f"llama.layers.{i - 1}." + rest
+    pl.set_state_dict({k: ref_sd[v] for k, v in mapping.items()})
+    model = fleet.distributed_model(pl)
+    opt = fleet.distributed_optimizer(paddle.optimizer.AdamW(1e-2, parameters=pl.parameters(), weight_decay=0.0))
+    ropt = paddle.optimizer.AdamW(1e-2, parameters=ref.parameters(), weight_decay=0.0)
+    for _ in range(3):
+        loss = model.train_batch([ids[:, :-1], ids[:, 1:]], opt)
+        rl = ref(ids[:, :-1], ids[:, 1:])
+        rl.backward()
+        ropt.step()
+        ropt.clear_grad()
+        close(loss.item(), rl.item(), 2e-4)
+    sd = ref.state_dict()
+    for name, p in pl.named_parameters():
+        close(p.numpy(), sd[mapping[name]].numpy(), 2e-3)
+
+
+def case_hybrid_mp_pp():
+    """mp2 x pp2 (4 ranks) with sequence parallel: loss decreases and matches across ranks."""
+    s, hcg = setup(mp=2, pp=2)
+    L, cfg = _tiny_llama({"sequence_parallel": True})
+    from paddle_b200.distributed.fleet.pipeline import PipelineLayer
+
+    s.pipeline_configs = {"accumulate_steps": 2, "micro_batch_size": 1}
+    pl = PipelineLayer(L.pipeline_layer_descs(cfg), num_stages=2, loss_fn=L.LlamaPretrainingCriterion(cfg), seg_method="layer:LlamaDecoderLayer")
+    model = fleet.distributed_model(pl)
+    opt = fleet.distributed_optimizer(paddle.optimizer.AdamW(5e-3, parameters=pl.parameters(), weight_decay=0.0,
+                                                             grad_clip=paddle.nn.ClipGradByGlobalNorm(1.0)))
+    ids = paddle.to_tensor(np.random.RandomState(0).randint(0, cfg.vocab_size, (2, 33)))
+    losses = [model.train_batch([ids[:, :-1], ids[:, 1:]], opt).item() for _ in range(6)]
+    assert losses[-1] < losses[0] - 0.2, losses
+    t = paddle.to_tensor([losses[-1]])
+    lst = []
+    dist.all_gather(lst, t)
+    close([x.item() for x in lst], [losses[-1]] * len(lst), 1e-5)
+
+
+def case_sharding():
+    """group_sharded_parallel os_g and p_g_os == plain training. Parity: dygraph_group_sharded_stage2/3.py."""
+    dist.init_parallel_env()
+    r, w = dist.get_rank(), dist.get_world_size()
+    from paddle_b200.distributed.sharding import group_sharded_parallel
+
+    for level in ("os_g", "p_g_os"):
+        paddle.seed(21)
+        net = nn.Sequential(nn.Linear(8, 32), nn.GELU(), nn.Linear(32, 4))
+        ref = nn.Sequential(nn.Linear(8, 32), nn.GELU(), nn.Linear(32, 4))
+        ref.set_state_dict(net.state_dict())
+        x, y = paddle.randn([8, 8]), paddle.randn([8, 4])
+        opt = paddle.optimizer.AdamW(1e-2, parameters=net.parameters(), weight_decay=0.0)
+        ropt = paddle.optimizer.AdamW(1e-2, parameters=ref.parameters(), weight_decay=0.0)
+        model, opt, _ = group_sharded_parallel(net, opt, level)
+        for _ in range(3):
+            sl = slice(r * 4, (r + 1) * 4)
+            loss = ((model(x[sl]) - y[sl]) ** 2).mean()
+            loss.backward()
+            opt.step()
+            opt.clear_grad()
+            rl = ((ref(x) - y) ** 2).mean()
+            rl.backward()
+            ropt.step()
+            ropt.clear_grad()
+        sd = model.state_dict()
+        for (k, a), (_, b) in zip(sd.items(), ref.state_dict().items()):
+            close(a.numpy(), b.numpy(), 1e-3)
+
+
+def case_p2p_kernels():
+    """Peer-memory collectives vs NCCL (GPU only)."""
+    assert GPU
+    dist.init_parallel_env()
+    r, w = dist.get_rank(), dist.get_world_size()
+    from paddle_b200.parallel import symm
+
+    sc = symm.context_for(None)
+    assert sc is not None, "symmetric heap unavailable"
+    torch.manual_seed(r)
+    for n in (1 << 10, (1 << 20) + 8, 3 << 20):
+        for dt in (torch.bfloat16, torch.float32):
+            t = torch.randn(n, device="cuda").to(dt)
+            ref = t.clone()
+            torch.distributed.all_reduce(ref)
+            sc.allreduce_(t)
+            torch.cuda.synchronize()
+            assert (t.float() - ref.float()).abs().max().item() <= 2e-2 * max(1.0, ref.float().abs().max().item()), (n, dt)
+    # fused row-parallel linear etc.
+    from paddle_b200.parallel import fused_mp
+
+    x = (torch.randn(256, 512, device="cuda") * 0.1).to(torch.bfloat16)
+    wgt = (torch.randn(512, 384, device="cuda") * 0.1).to(torch.bfloat16)
+    y = fused_mp.row_parallel_linear(x, wgt, None if False else dist.collective._global_group())
+    ref = (x.float() @ wgt.float())
+    torch.distributed.all_reduce(ref)
+    assert ((y.float() - ref).norm() / ref.norm()).item() < 2e-2
+    dist.barrier()
+
+
+if __name__ == "__main__":
+    case = sys.argv[1]
+    globals()["case_" + case]()
+    if dist.is_initialized():
+        dist.barrier()
+    print(f"rank {os.environ.get('RANK')} case {case} OK")
