@@ -11,6 +11,7 @@
 // Warp roles (256 threads): w0 TMA producer | w1 MMA issuer | w2 TMEM allocator | w4..w7 epilogue (TMEM lane quadrants).
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 #include <string>
@@ -380,7 +381,7 @@ struct MapKeyHash {
 };
 
 // 3-D map {inner (contiguous), rows, batch}; element = 2 bytes.
-static bool make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t ld,
+bool make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t ld,
                      uint64_t bstride, uint32_t box_inner, uint32_t box_rows, int dtype) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
@@ -479,6 +480,9 @@ int gemm_tcgen05(const GemmArgs& g, cudaStream_t s) {
   if (!gemm_tcgen05_supported(g.m, g.n, g.k, g.lda, g.ldb, g.ldd, g.a_is_km, g.b_is_nk)) return 1;
   if ((reinterpret_cast<uintptr_t>(g.a) & 15) || (reinterpret_cast<uintptr_t>(g.b) & 15)) return 1;
   if (g.dtype != kBF16 && g.dtype != kF16) return 1;
+  // large problems: CTA-pair kernel (cta_group::2, 256x256 cluster tile); B200_GEMM_2CTA=0 forces the 1-CTA kernel
+  static const int use_2cta = [] { const char* e = getenv("B200_GEMM_2CTA"); return e ? atoi(e) : 1; }();
+  if (use_2cta && g.m >= 256 && g.n >= 256) return gemm_tcgen05_2cta(g, s);
   // tile-N choice: widest tile that keeps the last wave reasonably full
   const int sms = sm_count();
   auto waves_eff = [&](int bn) {

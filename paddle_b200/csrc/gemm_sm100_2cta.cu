@@ -1,0 +1,409 @@
+// 2-CTA (cta_group::2) variant of the persistent tcgen05 GEMM: a cluster of two CTAs (one TPC) computes one 256x256
+// output tile.  Each CTA stages its own 128 rows of A and its own 128-column half of B, the leader CTA issues
+// tcgen05.mma.cta_group::2 (UMMA M=256, N=256) which reads both CTAs' shared memory, and every CTA drains its own
+// 128x256 accumulator half from its TMEM.  Versus the 1-CTA kernel this halves the B traffic through each SM's
+// shared memory (96 -> 64 B/clk/SM at full MMA rate), which is what limits the long-K shapes.
+//
+// Barrier protocol (per pipeline stage s; leader = cluster rank 0):
+//   full[s]   (leader only)  : 1 arrival (leader producer, expect_tx = bytes of BOTH CTAs) + complete_tx from the TMA
+//                              loads of both CTAs (cp.async.bulk.tensor.cta_group::2 signals the leader's barrier)
+//   empty[s]  (both CTAs)    : tcgen05.commit.cta_group::2 ... multicast -> each producer waits on its own copy
+//   tfull[a]  (both CTAs)    : multicast commit after the last k-block -> each CTA's epilogue waits on its own copy
+//   tempty[a] (leader only)  : 8 arrivals = 4 epilogue warps x 2 CTAs (the peer arrives remotely through mapa)
+#include <cuda.h>
+#include <cstdio>
+
+#include "include/b200_common.cuh"
+#include "include/b200_ops.h"
+
+namespace b200 {
+namespace gemm {
+bool make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t ld, uint64_t bstride,
+              uint32_t box_inner, uint32_t box_rows, int dtype);
+}
+namespace gemm2 {
+
+constexpr int BLOCK_M = 128;      // per CTA (cluster tile M = 256)
+constexpr int BLOCK_N = 256;      // cluster tile N; each CTA stages BLOCK_N/2 columns of B
+constexpr int HALF_N = BLOCK_N / 2;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int kStages = 6;
+constexpr int kThreads = 256;
+constexpr int kAccStages = 2;
+constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
+constexpr uint32_t B_STAGE_BYTES = HALF_N * BLOCK_K * 2;    // 16 KB
+constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr uint32_t TMEM_COLS = kAccStages * BLOCK_N;        // 512
+constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + 1024 + 256;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;              // clears the CTA-rank bit of a shared::cluster address
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// arrive on the barrier at the same smem offset in cluster CTA `rank`
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  uint64_t t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins == 1024) t0 = globaltimer_ns();
+    if (spins > 1024 && (spins & 1023) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+      printf("b200 gemm2: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit -> arrive on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)0x3)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+struct Params {
+  int m, n, k, batch;
+  void* d;
+  const void* bias;
+  int64_t ldd, stride_d;
+  int in_dtype, out_dtype;
+  int has_bias, act, accumulate;
+  uint32_t idesc;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+template <typename TO>
+__device__ __forceinline__ void store_row_chunk(TO* __restrict__ dst, const float (&v)[32], int valid, bool accumulate) {
+  if (valid >= 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    constexpr int N = Vec16<TO>::N;
+#pragma unroll
+    for (int q = 0; q < 32 / N; ++q) {
+      Vec16<TO> o;
+      if (accumulate) {
+        Vec16<TO> old = ld16(dst + q * N);
+#pragma unroll
+        for (int j = 0; j < N; ++j) o.v[j] = from_f<TO>(v[q * N + j] + to_f(old.v[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) o.v[j] = from_f<TO>(v[q * N + j]);
+      }
+      st16(dst + q * N, o);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < valid) dst[j] = from_f<TO>(accumulate ? v[j] + to_f(dst[j]) : v[j]);
+  }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + kStages * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + kAccStages + s); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * STAGE_BYTES + 8 * (2 * kStages + 2 * kAccStages));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_m = (p.m + 2 * BLOCK_M - 1) / (2 * BLOCK_M), num_n = (p.n + BLOCK_N - 1) / BLOCK_N;
+  const int tiles_per_batch = num_m * num_n;
+  const int num_tiles = tiles_per_batch * p.batch;
+  const int num_kb = (p.k + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  cluster_sync();  // barriers of both CTAs are initialised before any remote arrive / TMA completion can target them
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto tile_coords = [&](int tile, int& bz, int& mb, int& nb) {
+    bz = tile / tiles_per_batch;
+    const int t = tile - bz * tiles_per_batch;
+    constexpr int GROUP_M = 4;  // 4 x 256 rows
+    const int in_group = GROUP_M * num_n;
+    const int g = t / in_group;
+    const int first_m = g * GROUP_M;
+    const int gsz = min(num_m - first_m, GROUP_M);
+    const int r = t - g * in_group;
+    mb = first_m + r % gsz;
+    nb = r / gsz;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer (both CTAs: own A rows, own half of B) =================
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint64_t hint = 0x1000000000000000ull;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int bz, mb, nb;
+        tile_coords(tile, bz, mb, nb);
+        const int m0 = mb * 2 * BLOCK_M + (int)cta_rank * BLOCK_M;
+        const int n0 = nb * BLOCK_N + (int)cta_rank * HALF_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+          const int k0 = kb * BLOCK_K;
+          if constexpr (!A_MN) {
+            tma_load_3d_2sm(sa, &map_a, full_bar(stage), k0, m0, bz, hint);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_3d_2sm(sa + i * 8192, &map_a, full_bar(stage), m0 + i * 64, k0, bz, hint);
+          }
+          if constexpr (!B_MN) {
+            tma_load_3d_2sm(sb, &map_b, full_bar(stage), k0, n0, bz, hint);
+          } else {
+#pragma unroll
+            for (int i = 0; i < HALF_N / 64; ++i) tma_load_3d_2sm(sb + i * 8192, &map_b, full_bar(stage), n0 + i * 64, k0, bz, hint);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      // ================= MMA issuer (leader CTA only) =================
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(tempty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+            umma_f16_2sm(tmem_d, adesc, bdesc, p.idesc, (kb | k) != 0);
+          }
+          umma_commit_2sm(empty_bar(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(tfull_bar(as));
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue (both CTAs: own 128 rows x 256 columns) =================
+    const int ew = warp - 4;
+    int local = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+      int bz, mb, nb;
+      tile_coords(tile, bz, mb, nb);
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int row = mb * 2 * BLOCK_M + (int)cta_rank * BLOCK_M + ew * 32 + lane;
+      const bool row_ok = row < p.m;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int col0 = nb * BLOCK_N + c * 32;
+        if (col0 >= p.n) break;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N + c * 32, r);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const int valid = min(32, p.n - col0);
+        if (p.has_bias) {
+          if (p.in_dtype == kBF16) {
+            const __nv_bfloat16* b = (const __nv_bfloat16*)p.bias + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < valid) v[j] += __bfloat162float(b[j]);
+          } else {
+            const __half* b = (const __half*)p.bias + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < valid) v[j] += __half2float(b[j]);
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (row_ok) {
+          const int64_t off = (int64_t)bz * p.stride_d + (int64_t)row * p.ldd + col0;
+          if (p.out_dtype == kBF16) store_row_chunk((__nv_bfloat16*)p.d + off, v, valid, p.accumulate);
+          else if (p.out_dtype == kF16) store_row_chunk((__half*)p.d + off, v, valid, p.accumulate);
+          else store_row_chunk((float*)p.d + off, v, valid, p.accumulate);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_bar(as), 0);  // leader's barrier counts both CTAs' epilogue warps
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync();  // peer smem / TMEM stay valid until every MMA and remote arrive has retired
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+static uint32_t make_idesc(int in_dtype, bool a_mn, bool b_mn) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  const uint32_t f = in_dtype == kBF16 ? 1u : 0u;
+  d |= f << 7;
+  d |= f << 10;
+  d |= (a_mn ? 1u : 0u) << 15;
+  d |= (b_mn ? 1u : 0u) << 16;
+  d |= (uint32_t)(BLOCK_N >> 3) << 17;
+  d |= (uint32_t)((2 * BLOCK_M) >> 4) << 24;   // UMMA M = 256 across the CTA pair
+  return d;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch(const GemmArgs& g, cudaStream_t s) {
+  CUtensorMap ma, mb;
+  const uint64_t batch = g.batch > 1 ? g.batch : 1;
+  bool ok;
+  if (!A_MN) ok = gemm::make_map(&ma, g.a, g.k, g.m, batch, g.lda, g.stride_a, BLOCK_K, BLOCK_M, g.dtype);
+  else       ok = gemm::make_map(&ma, g.a, g.m, g.k, batch, g.lda, g.stride_a, 64, BLOCK_K, g.dtype);
+  if (!ok) return 2;
+  if (!B_MN) ok = gemm::make_map(&mb, g.b, g.k, g.n, batch, g.ldb, g.stride_b, BLOCK_K, HALF_N, g.dtype);
+  else       ok = gemm::make_map(&mb, g.b, g.n, g.k, batch, g.ldb, g.stride_b, 64, BLOCK_K, g.dtype);
+  if (!ok) return 2;
+  Params p;
+  p.m = g.m; p.n = g.n; p.k = g.k; p.batch = (int)batch;
+  p.d = g.d; p.bias = g.bias; p.ldd = g.ldd; p.stride_d = g.stride_d;
+  p.in_dtype = g.dtype; p.out_dtype = g.out_dtype;
+  p.has_bias = (g.epilogue >= 1 && g.epilogue <= 3 && g.bias) ? 1 : 0;
+  p.act = g.epilogue == 2 ? 1 : (g.epilogue == 3 ? 2 : 0);
+  p.accumulate = g.epilogue == 4 ? 1 : 0;
+  p.idesc = make_idesc(g.dtype, A_MN, B_MN);
+  static bool attr_set = false;
+  auto kern = gemm2_kernel<A_MN, B_MN>;
+  if (!attr_set) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_tiles = ((g.m + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((g.n + BLOCK_N - 1) / BLOCK_N) * (int)batch;
+  const int max_clusters = sm_count() / 2;
+  const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+  kern<<<clusters * 2, kThreads, SMEM_BYTES, s>>>(ma, mb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return 3; }
+  return 0;
+}
+
+}  // namespace gemm2
+
+int gemm_tcgen05_2cta(const GemmArgs& g, cudaStream_t s) {
+  if (g.a_is_km) return g.b_is_nk ? gemm2::launch<true, false>(g, s) : gemm2::launch<true, true>(g, s);
+  return g.b_is_nk ? gemm2::launch<false, false>(g, s) : gemm2::launch<false, true>(g, s);
+}
+
+}  // namespace b200

@@ -91,6 +91,8 @@ struct GemmArgs {
 };
 // returns 0 on success, nonzero if the shape is unsupported by the tcgen05 path (caller falls back)
 int gemm_tcgen05(const GemmArgs& g, cudaStream_t s);
+// CTA-pair variant (cta_group::2, UMMA M=256): gemm_sm100_2cta.cu
+int gemm_tcgen05_2cta(const GemmArgs& g, cudaStream_t s);
 int gemm_tcgen05_supported(int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd, int a_is_km, int b_is_nk);
 
 }  // namespace b200
