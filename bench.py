@@ -143,6 +143,7 @@ def main():
     else:
         model = L.LlamaForCausalLM(cfg)
     n_params_local = sum(p.numel() for p in model.parameters())
+    assert all(p.dtype == torch.bfloat16 for p in model.parameters()), "model parameters must be bf16"
     decay_fn = lambda name: not any(k in name for k in ("norm", "bias"))  # noqa: E731
     opt = paddle.optimizer.AdamW(learning_rate=1e-5, beta1=0.9, beta2=0.95, epsilon=1e-8, parameters=model.parameters(), weight_decay=0.1,
                                  grad_clip=paddle.nn.ClipGradByGlobalNorm(1.0), multi_precision=True, moment_dtype="bfloat16",

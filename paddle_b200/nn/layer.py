@@ -93,7 +93,8 @@ class Layer:
         d["_sub_layers"] = OrderedDict()
         d["_forward_pre_hooks"] = OrderedDict()
         d["_forward_post_hooks"] = OrderedDict()
-        d["_dtype"] = _dt.convert_dtype(dtype) if dtype is not None else _dt.default_dtype()
+        # like the reference's built-in layers (LayerHelper.get_default_dtype) parameters follow paddle.set_default_dtype
+        d["_dtype"] = _dt.default_dtype() if dtype in (None, "float32") else _dt.convert_dtype(dtype)
         base = name_scope or _camel_to_snake(self.__class__.__name__)
         d["_full_name"] = unique_name.generate(base)
         d["_helper_w"] = 0
