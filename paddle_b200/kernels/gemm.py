@@ -64,8 +64,11 @@ class _Linear(torch.autograd.Function):
         ctx.save_for_backward(x2, w)
         ctx.x_shape = x.shape
         ctx.has_b = b is not None
-        y = ext().gemm(x2, w, b, False, False, 1 if b is not None else 0, None, None)
-        return y.reshape(*x.shape[:-1], w.shape[1])
+        # allocate the result in its final shape: a view created inside a custom Function could not be modified in
+        # place afterwards (the packed rotary embedding rotates q/k inside the fused QKV output)
+        out = torch.empty((*x.shape[:-1], w.shape[1]), dtype=x.dtype, device=x.device)
+        ext().gemm(x2, w, b, False, False, 1 if b is not None else 0, out.view(-1, w.shape[1]), None)
+        return out
 
     @staticmethod
     def backward(ctx, dy):
