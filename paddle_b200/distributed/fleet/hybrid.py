@@ -245,7 +245,7 @@ class HybridParallelOptimizer:
         self._need_hybrid_clip = hcg is not None and (hcg.get_model_parallel_world_size() > 1 or hcg.get_pipe_parallel_world_size() > 1 or self._sharding_enable)
         clip = optimizer._grad_clip
         self._params = optimizer._parameter_list
-        self._use_arena = bool(self._params) and all(p.is_cuda for p in self._params) and hasattr(optimizer, "_arena_step")
+        self._use_arena = bool(self._params) and hasattr(optimizer, "_arena_step") and optimizer._arena_ok_static()
         if self._use_arena:
             from ...parallel.arena import ParamArena
 
@@ -260,6 +260,9 @@ class HybridParallelOptimizer:
             for key, slab in arena.slabs.items():
                 d, is_dist, is_sp = key[2]
                 slab.decay, slab.is_distributed, slab.sequence_parallel = bool(d), bool(is_dist), bool(is_sp)
+                if is_sp:
+                    for p in slab.params:
+                        p.__dict__["_sp_reduce_in_optimizer"] = True
             optimizer.enable_flat_arena(arena)
             if isinstance(clip, ClipGradByGlobalNorm) and self._need_hybrid_clip:
                 optimizer._aux["norm_allreduce"] = self._arena_norm_allreduce
@@ -269,8 +272,6 @@ class HybridParallelOptimizer:
 
     # arena path: sq holds sum over ALL local slabs; replicated slabs must be counted once across mp -> recompute split
     def _arena_norm_allreduce(self, sq):
-        from ..._build import ext
-
         hcg = self._hcg
         mp = hcg.get_model_parallel_world_size()
         if mp > 1:
@@ -278,7 +279,12 @@ class HybridParallelOptimizer:
             rep = torch.zeros(1, dtype=torch.float32, device=sq.device)
             for s in self._inner_opt._arena.all_slabs():
                 if not s.is_distributed:
-                    ext().grad_sq_norm(s.grad, rep, None)
+                    if s.grad.is_cuda:
+                        from ..._build import ext
+
+                        ext().grad_sq_norm(s.grad, rep, None)
+                    else:
+                        rep.add_(s.grad.float().pow(2).sum())
             sq.sub_(rep * (1.0 - 1.0 / mp))
             dist.all_reduce(sq, group=_pg(hcg.get_model_parallel_group()))
         if hcg.get_pipe_parallel_world_size() > 1:

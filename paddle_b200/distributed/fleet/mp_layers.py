@@ -231,7 +231,9 @@ def register_sequence_parallel_allreduce_hooks(model, accumulation_steps=1, fuse
         return
     for p in model.parameters():
         if is_sequence_parallel_parameter(p):
-            def hook(g, _grp=group):
+            def hook(g, _grp=group, _p=p):
+                if _p.__dict__.get("_sp_reduce_in_optimizer", False):
+                    return g  # the hybrid optimizer reduces the whole sequence-parallel gradient slab in one collective
                 g = g.contiguous()
                 dist.all_reduce(g, group=_pg(_grp))
                 return g

@@ -231,11 +231,14 @@ class LlamaPretrainingCriterion(nn.Layer):
     def __init__(self, config=None, ignore_index=-100):
         super().__init__()
         self.ignore_index = ignore_index
+        self.vocab_size = config.vocab_size if config is not None else None
 
     def forward(self, logits, labels):
         lg, lab = _raw(logits), _raw(labels).reshape(-1)
         v = lg.shape[-1]
         mp = _mp_degree()
+        if self.vocab_size is not None and v == self.vocab_size:
+            mp = 1  # logits carry the full vocabulary (dense model, or gathered): plain fused CE
         if mp > 1:
             hcg = topo.get_hybrid_communicate_group()
             grp = hcg.get_model_parallel_group()

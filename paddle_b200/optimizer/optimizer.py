@@ -228,6 +228,50 @@ class Optimizer:
         return self._arena
 
 
+class _NativeOps:
+    """csrc/optim.cu launchers."""
+
+    def __init__(self):
+        from .._build import ext
+
+        self._e = ext()
+
+    def grad_sq_norm(self, g, out, found_inf):
+        self._e.grad_sq_norm(g, out, found_inf)
+
+    def adamw_step(self, *a):
+        self._e.adamw_step(*a)
+
+
+class _TorchOps:
+    """Reference implementation of the same slab ops in plain PyTorch (CPU tests / fallback)."""
+
+    def grad_sq_norm(self, g, out, found_inf):
+        s = g.float().pow(2).sum()
+        out.add_(s)
+        if found_inf is not None and not bool(torch.isfinite(s)):
+            found_inf.fill_(1.0)
+
+    def adamw_step(self, p, g, master, m, v, lr, b1, b2, eps, wd, step, sq, max_norm, found_inf, inv_scale):
+        if found_inf is not None and float(found_inf) != 0.0:
+            return
+        gs = float(inv_scale) if inv_scale is not None else 1.0
+        if sq is not None and max_norm > 0:
+            norm = float(sq.sqrt()) * gs
+            if norm > max_norm:
+                gs *= max_norm / (norm + 1e-6)
+        gf = g.float() * gs
+        pf = master if master is not None else p.float()
+        mf, vf = m.float(), v.float()
+        mf.mul_(b1).add_(gf, alpha=1 - b1)
+        vf.mul_(b2).addcmul_(gf, gf, value=1 - b2)
+        c1, c2 = 1 - b1 ** step, 1 - b2 ** step
+        pf.mul_(1 - lr * wd).addcdiv_(mf, (vf / c2).sqrt_().add_(eps), value=-lr / c1)
+        m.copy_(mf)
+        v.copy_(vf)
+        p.copy_(pf)
+
+
 class SGD(Optimizer):
     def __init__(self, learning_rate=0.001, parameters=None, weight_decay=None, grad_clip=None, multi_precision=False, name=None):
         super().__init__(learning_rate, parameters, weight_decay, grad_clip, name, multi_precision)
@@ -341,6 +385,13 @@ class Adam(Optimizer):
         self._write_back(p, pr, pf, cp)
 
     # ---- flat-arena fast path: one fused kernel per slab, clip/loss-scale read on device ---------------------
+    def _arena_ok_static(self):
+        from ..nn.clip import ClipGradByGlobalNorm
+
+        if self._amsgrad or not (self._decoupled or not self._weight_decay):
+            return False
+        return self._grad_clip is None or isinstance(self._grad_clip, ClipGradByGlobalNorm)
+
     def _arena_ok(self):
         from ..nn.clip import ClipGradByGlobalNorm
 
@@ -348,12 +399,11 @@ class Adam(Optimizer):
             return False
         if self._grad_clip is not None and not isinstance(self._grad_clip, ClipGradByGlobalNorm):
             return False
-        return all(s.data.is_cuda for s in self._arena.all_slabs())
+        return True
 
     def _arena_step(self):
-        from .._build import ext
-
-        E = ext()
+        cuda = all(s.data.is_cuda for s in self._arena.all_slabs())
+        E = _NativeOps() if cuda else _TorchOps()   # same slab algorithm; CPU path = plain torch (used by the gloo tests)
         b1, b2 = self._betas()
         lr = self.get_lr()
         slabs = self._arena.all_slabs()

@@ -233,6 +233,77 @@ def case_hybrid_mp_pp():
     close([x.item() for x in lst], [losses[-1]] * len(lst), 1e-5)
 
 
+def case_mp_sp_parity():
+    """mp2 + sequence parallel Llama (flat-arena AdamW + hybrid global-norm clip) == dense single-process training."""
+    _, hcg = setup(mp=2)
+    r = hcg.get_model_parallel_rank()
+    from paddle_b200.models import llama as L
+
+    cfg_d = L.llama_tiny(dtype="float32")
+    ids = paddle.to_tensor(np.random.RandomState(0).randint(0, cfg_d.vocab_size, (2, 33)))
+    # dense reference is built with the mp topology hidden, so it uses plain Linear layers
+    from paddle_b200.distributed.fleet import topology as topo
+
+    saved = topo.get_hybrid_communicate_group()
+    topo._set_hcg(None)
+    paddle.seed(11)
+    ref = L.LlamaForCausalLM(cfg_d)
+    topo._set_hcg(saved)
+    for p_ in ref.parameters():  # the lm head draws from the per-rank mp RNG tracker: make the reference identical everywhere
+        dist.broadcast(p_, 0)
+    cfg = L.llama_tiny(dtype="float32", sequence_parallel=True)
+    par = L.LlamaForCausalLM(cfg)
+    sd = ref.state_dict()
+    h, f = cfg.hidden_size, cfg.intermediate_size
+
+    def shard_cols(w, parts):  # w [in, sum(parts)] -> this rank's slice of every part, concatenated
+        outs, off = [], 0
+        for n in parts:
+            seg = w[:, off:off + n]
+            outs.append(seg[:, r * (n // 2):(r + 1) * (n // 2)])
+            off += n
+        return paddle.concat(outs, axis=1)
+
+    new = {}
+    for k, v in par.state_dict().items():
+        d = sd[k]
+        if k.endswith("qkv_proj.weight"):
+            new[k] = shard_cols(d, [h, h, h])
+        elif k.endswith("gate_up_proj.weight"):
+            new[k] = shard_cols(d, [f, f])
+        elif k.endswith("o_proj.weight") or k.endswith("down_proj.weight"):
+            n = d.shape[0]
+            new[k] = d[r * (n // 2):(r + 1) * (n // 2)]
+        elif k.endswith("embed_tokens.weight"):
+            n = d.shape[0]
+            new[k] = d[r * (n // 2):(r + 1) * (n // 2)]
+        elif k == "lm_head.weight":
+            n = d.shape[1]
+            new[k] = d[:, r * (n // 2):(r + 1) * (n // 2)]
+        else:
+            new[k] = d
+    par.set_state_dict(new)
+    model = fleet.distributed_model(par)
+    mk = lambda ps: paddle.optimizer.AdamW(1e-2, parameters=ps, weight_decay=0.01, grad_clip=paddle.nn.ClipGradByGlobalNorm(0.5))  # noqa: E731
+    opt = fleet.distributed_optimizer(mk(par.parameters()))
+    ropt = mk(ref.parameters())
+    for _ in range(3):
+        loss = model(ids[:, :-1], ids[:, 1:])
+        loss.backward()
+        opt.step()
+        opt.clear_grad()
+        rl = ref(ids[:, :-1], ids[:, 1:])
+        rl.backward()
+        ropt.step()
+        ropt.clear_grad()
+        print('STEP', _, loss.item(), rl.item(), flush=True)
+        close(loss.item(), rl.item(), 5e-4)
+    close(par.state_dict()["llama.layers.0.input_layernorm.weight"].numpy(), ref.state_dict()["llama.layers.0.input_layernorm.weight"].numpy(), 2e-3)
+    n = ref.state_dict()["llama.layers.1.mlp.down_proj.weight"].shape[0]
+    close(par.state_dict()["llama.layers.1.mlp.down_proj.weight"].numpy(),
+          ref.state_dict()["llama.layers.1.mlp.down_proj.weight"][r * (n // 2):(r + 1) * (n // 2)].numpy(), 5e-3)
+
+
 def case_sharding():
     """group_sharded_parallel os_g and p_g_os == plain training. Parity: dygraph_group_sharded_stage2/3.py."""
     dist.init_parallel_env()

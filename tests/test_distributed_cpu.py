@@ -6,6 +6,6 @@ from dist_utils import run_dist
 
 
 @pytest.mark.parametrize("case,world", [("collectives", 2), ("mp_layers", 2), ("sequence_parallel", 2), ("dp", 2), ("pp", 2),
-                                        ("sharding", 2), ("hybrid_mp_pp", 4)])
+                                        ("sharding", 2), ("mp_sp_parity", 2), ("hybrid_mp_pp", 4)])
 def test_dist_case(case, world):
     run_dist(case, world)

@@ -1,0 +1,27 @@
+"""Multi-GPU tests (NCCL + peer-memory kernels). Need >= 2 visible GPUs; skipped otherwise."""
+import pytest
+import torch
+
+from dist_utils import run_dist
+
+pytestmark = pytest.mark.gpu
+
+
+def _need(n):
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+
+
+def test_p2p_collectives_and_fused_linear():
+    _need(2)
+    run_dist("p2p_kernels", 2, extra_env={"B200_TEST_GPU": "1"})
+
+
+def test_mp_sp_parity_gpu():
+    _need(2)
+    run_dist("mp_sp_parity", 2, extra_env={"B200_TEST_GPU": "1"})
+
+
+def test_pp_gpu():
+    _need(2)
+    run_dist("pp", 2, extra_env={"B200_TEST_GPU": "1"})
