@@ -1,0 +1,231 @@
+"""paddle.jit. Parity: python/paddle/jit/api.py (to_static, save, load, not_to_static, enable_to_static, ignore_module),
+translated_layer.py (TranslatedLayer).
+
+B200 design ("CUDA streams and graphs instead of a tracing compiler"): ``to_static`` does not trace into an IR.  A
+static function keeps running the eager kernels, but once its inputs have a stable signature (shapes/dtypes) the whole
+call is captured into a CUDA graph and replayed with one launch; a guard cache keyed by the signature holds one graph
+per shape.  ``jit.save`` writes the parameters (.pdiparams, same pickle format as paddle.save) plus a .pdmodel file that
+pickles the Layer's class path + constructor spec + InputSpec, so ``jit.load`` rebuilds a ``TranslatedLayer``.
+"""
+from __future__ import annotations
+
+import functools
+import importlib
+import os
+import pickle
+
+import torch
+
+from ..framework.io import load as _load
+from ..framework.io import save as _save
+from ..nn.layer import Layer
+from ..static.input import InputSpec
+from ..tensor import Tensor
+
+_enabled = [True]
+_ignored_modules = []
+
+
+def enable_to_static(enable_to_static_bool):
+    _enabled[0] = bool(enable_to_static_bool)
+
+
+def ignore_module(modules):
+    _ignored_modules.extend(modules if isinstance(modules, (list, tuple)) else [modules])
+
+
+def not_to_static(func=None):
+    if func is None:
+        return not_to_static
+    func._not_to_static = True
+    return func
+
+
+def _sig(args, kwargs):
+    out = []
+    for a in list(args) + [kwargs[k] for k in sorted(kwargs)]:
+        if isinstance(a, torch.Tensor):
+            out.append((tuple(a.shape), a.dtype, a.device.type, a.requires_grad))
+        elif isinstance(a, (int, float, bool, str, type(None))):
+            out.append(a)
+        else:
+            out.append(id(a))
+    return tuple(out)
+
+
+class StaticFunction:
+    """Callable produced by to_static. Eager warm-up, then CUDA-graph replay for inference-mode CUDA calls."""
+
+    def __init__(self, fn, layer=None, input_spec=None, build_strategy=None, backend=None, full_graph=False):
+        self._fn, self._layer, self._input_spec = fn, layer, input_spec
+        self._graphs = {}
+        self._warm = {}
+        self._capture_after = 2
+        functools.update_wrapper(self, fn)
+
+    @property
+    def dygraph_function(self):
+        return self._fn
+
+    def concrete_program_specify_input_spec(self, *a, **k):
+        return None
+
+    def rollback(self):
+        return self._fn
+
+    def _can_graph(self, args, kwargs):
+        if torch.is_grad_enabled() and any(isinstance(a, torch.Tensor) and a.requires_grad for a in args):
+            return False
+        if self._layer is not None and self._layer.training and torch.is_grad_enabled():
+            return False
+        ts = [a for a in list(args) + list(kwargs.values()) if isinstance(a, torch.Tensor)]
+        return bool(ts) and all(t.is_cuda for t in ts)
+
+    def __call__(self, *args, **kwargs):
+        if not _enabled[0] or getattr(self._fn, "_not_to_static", False):
+            return self._fn(*args, **kwargs)
+        if not self._can_graph(args, kwargs) or torch.is_grad_enabled():
+            return self._fn(*args, **kwargs)
+        key = _sig(args, kwargs)
+        entry = self._graphs.get(key)
+        if entry is None:
+            n = self._warm.get(key, 0) + 1
+            self._warm[key] = n
+            if n <= self._capture_after:
+                return self._fn(*args, **kwargs)
+            entry = self._capture(args, kwargs)
+            self._graphs[key] = entry
+            if entry is None:
+                return self._fn(*args, **kwargs)
+        if entry is None:
+            return self._fn(*args, **kwargs)
+        graph, static_in, static_out = entry
+        for s, a in zip(static_in, [a for a in list(args) + [kwargs[k] for k in sorted(kwargs)] if isinstance(a, torch.Tensor)]):
+            s.copy_(a)
+        graph.replay()
+        return _clone_tree(static_out)
+
+    def _capture(self, args, kwargs):
+        try:
+            static_args = [a.clone() if isinstance(a, torch.Tensor) else a for a in args]
+            static_kwargs = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in kwargs.items()}
+            static_in = [a for a in static_args + [static_kwargs[k] for k in sorted(static_kwargs)] if isinstance(a, torch.Tensor)]
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._fn(*static_args, **static_kwargs)
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._fn(*static_args, **static_kwargs)
+            return g, static_in, out
+        except Exception:  # capture-unsafe function (host sync, dynamic shapes...): stay eager for this signature
+            torch.cuda.synchronize()
+            return None
+
+
+def _clone_tree(o):
+    if isinstance(o, torch.Tensor):
+        return o.clone()
+    if isinstance(o, (list, tuple)):
+        return type(o)(_clone_tree(i) for i in o)
+    if isinstance(o, dict):
+        return {k: _clone_tree(v) for k, v in o.items()}
+    return o
+
+
+def to_static(function=None, input_spec=None, build_strategy=None, backend=None, **kwargs):
+    def decorate(fn):
+        if isinstance(fn, Layer):
+            layer = fn
+            sf = StaticFunction(layer.forward, layer, input_spec, build_strategy, backend)
+            layer.forward = sf
+            layer._input_spec = input_spec
+            return layer
+        return StaticFunction(fn, None, input_spec, build_strategy, backend)
+
+    if function is not None:
+        return decorate(function)
+    return decorate
+
+
+def _layer_spec(layer):
+    cls = type(layer)
+    spec = {"module": cls.__module__, "qualname": cls.__qualname__, "init_args": getattr(layer, "_init_args", None)}
+    return spec
+
+
+def save(layer, path, input_spec=None, **configs):
+    """jit.save(layer, path): path.pdmodel (structure spec) + path.pdiparams (weights)."""
+    if not isinstance(layer, Layer):
+        raise TypeError("jit.save expects a Layer (functions are captured at call time by to_static)")
+    d = os.path.dirname(path)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    _save(layer.state_dict(), path + ".pdiparams")
+    spec = _layer_spec(layer)
+    spec["input_spec"] = [(list(s.shape), str(s.dtype), s.name) if isinstance(s, InputSpec) else None for s in (input_spec or getattr(layer, "_input_spec", None) or [])]
+    try:
+        fwd = layer.forward
+        if isinstance(fwd, StaticFunction):
+            layer.__dict__.pop("forward", None)
+        blob = pickle.dumps(layer)
+        if isinstance(fwd, StaticFunction):
+            layer.forward = fwd
+        spec["pickled_layer"] = blob
+    except Exception:
+        spec["pickled_layer"] = None
+    with open(path + ".pdmodel", "wb") as f:
+        pickle.dump(spec, f)
+
+
+class TranslatedLayer(Layer):
+    """Layer rebuilt by jit.load. Parity: python/paddle/jit/translated_layer.py."""
+
+    def __init__(self, inner, spec):
+        super().__init__()
+        self._inner = inner
+        self._spec = spec
+        self._static = StaticFunction(inner.forward, inner)
+
+    def forward(self, *args, **kwargs):
+        return self._static(*args, **kwargs)
+
+    def program(self, method_name="forward"):
+        return self._spec
+
+
+def load(path, **configs):
+    with open(path + ".pdmodel", "rb") as f:
+        spec = pickle.load(f)
+    layer = None
+    if spec.get("pickled_layer"):
+        layer = pickle.loads(spec["pickled_layer"])
+    else:
+        mod = importlib.import_module(spec["module"])
+        cls = mod
+        for part in spec["qualname"].split("."):
+            cls = getattr(cls, part)
+        args = spec.get("init_args") or ((), {})
+        layer = cls(*args[0], **args[1])
+    layer.set_state_dict(_load(path + ".pdiparams"))
+    layer.eval()
+    return TranslatedLayer(layer, spec)
+
+
+def set_code_level(level=100, also_to_stdout=False):
+    pass
+
+
+def set_verbosity(level=0, also_to_stdout=False):
+    pass
+
+
+def marker_unified(*a, **k):
+    def deco(fn):
+        return fn
+
+    return deco
+
+
+__all__ = ["to_static", "save", "load", "TranslatedLayer", "not_to_static", "enable_to_static", "ignore_module", "set_code_level", "set_verbosity"]

@@ -191,6 +191,13 @@ class Optimizer:
             self._update_param(g, p, _raw(p), gr, lr, wd, kind)
 
     def minimize(self, loss, startup_program=None, parameters=None, no_grad_set=None):
+        from .. import static
+
+        prog = static._recording[0]
+        if prog is not None and (id(loss) in prog._vids):
+            # static graph: defer backward+update to Executor.run (python/paddle/optimizer/optimizer.py:minimize appends ops)
+            static._minimize_node(self, loss, prog)
+            return None, None
         loss.backward()
         self.step()
         return None, None

@@ -1,0 +1,624 @@
+"""paddle.static. Parity: python/paddle/static/__init__.py, python/paddle/base/{framework,executor}.py.
+
+Design: a ``Program`` is a recorded op tape, not a protobuf ProgramDesc.  Under ``program_guard`` every tensor op that
+touches a program Variable is executed once on placeholder data (shape inference by example) and recorded as a node
+``(callable, argument refs) -> outputs``.  ``Executor.run(program, feed, fetch_list)`` binds the feed tensors to the
+placeholders and replays the tape through the native scheduler (csrc/runtime/graph_exec.cpp GraphExecutor: topological
+order from data dependencies); ``optimizer.minimize(loss)`` inside the guard appends a backward+update node, so training
+programs work.  Parameters created by ``static.nn`` / ``create_parameter`` live in the global scope across runs.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+import pickle
+
+import numpy as np
+import torch
+from torch.overrides import TorchFunctionMode
+
+from ..framework import dtype as _dt
+from ..framework.io import load as _pload
+from ..framework.io import save as _psave
+from ..framework.place import CPUPlace, CUDAPlace  # noqa: F401
+from ..nn.layer import ParamAttr  # noqa: F401
+from ..tensor import Parameter, Tensor, to_tensor
+from .input import InputSpec  # noqa: F401
+
+_static_mode = [False]
+
+
+def enable_static():
+    _static_mode[0] = True
+
+
+def disable_static(place=None):
+    _static_mode[0] = False
+
+
+def in_dynamic_mode():
+    return not _static_mode[0]
+
+
+def in_static_mode():
+    return _static_mode[0]
+
+
+class Variable(Tensor):
+    """A program variable: a Tensor carrying its symbolic declaration (name, shape with -1)."""
+
+    @property
+    def desc_shape(self):
+        return self.__dict__.get("_pd_desc_shape", list(self.size()))
+
+
+class _Node:
+    __slots__ = ("fn", "args", "kwargs", "outs", "kind")
+
+    def __init__(self, fn, args, kwargs, outs, kind="op"):
+        self.fn, self.args, self.kwargs, self.outs, self.kind = fn, args, kwargs, outs, kind
+
+
+class _Ref:
+    __slots__ = ("vid",)
+
+    def __init__(self, vid):
+        self.vid = vid
+
+
+class Program:
+    def __init__(self):
+        self.nodes = []
+        self.placeholders = {}       # name -> vid
+        self._vids = {}              # id(tensor) -> vid  (only valid while recording)
+        self._keep = []              # keep recorded example tensors alive so ids stay unique
+        self._next = 0
+        self.random_seed = 0
+        self._fetch_alias = {}       # id(example tensor) -> vid (for fetch_list lookups after recording)
+        self._name2vid = {}
+
+    # ---- recording -----------------------------------------------------------------------------------------
+    def _new_vid(self, t, name=None):
+        vid = self._next
+        self._next += 1
+        self._vids[id(t)] = vid
+        self._fetch_alias[id(t)] = vid
+        self._keep.append(t)
+        if name:
+            self._name2vid[name] = vid
+        return vid
+
+    def _encode(self, x):
+        if isinstance(x, torch.Tensor):
+            vid = self._vids.get(id(x))
+            return _Ref(vid) if vid is not None else x   # unknown tensors are constants / parameters (by reference)
+        if isinstance(x, (list, tuple)):
+            return type(x)(self._encode(i) for i in x)
+        if isinstance(x, dict):
+            return {k: self._encode(v) for k, v in x.items()}
+        return x
+
+    def _touches_program(self, x):
+        if isinstance(x, torch.Tensor):
+            return id(x) in self._vids
+        if isinstance(x, (list, tuple)):
+            return any(self._touches_program(i) for i in x)
+        if isinstance(x, dict):
+            return any(self._touches_program(v) for v in x.values())
+        return False
+
+    def _record(self, fn, args, kwargs, out):
+        outs = []
+
+        def reg(o):
+            if isinstance(o, torch.Tensor):
+                if id(o) not in self._vids:
+                    self._new_vid(o)
+                outs.append(self._vids[id(o)])
+            elif isinstance(o, (list, tuple)):
+                for i in o:
+                    reg(i)
+
+        enc_a, enc_k = self._encode(args), self._encode(kwargs)
+        reg(out)
+        self.nodes.append(_Node(fn, enc_a, enc_k, outs))
+
+    # ---- api ------------------------------------------------------------------------------------------------------
+    def global_block(self):
+        return self
+
+    def clone(self, for_test=False):
+        p = Program()
+        p.nodes = [n for n in self.nodes if not (for_test and n.kind == "train")]
+        p.placeholders = dict(self.placeholders)
+        p._fetch_alias, p._name2vid, p._next, p._keep = dict(self._fetch_alias), dict(self._name2vid), self._next, list(self._keep)
+        return p
+
+    def all_parameters(self):
+        seen, out = set(), []
+
+        def walk(x):
+            if isinstance(x, Parameter) and id(x) not in seen:
+                seen.add(id(x))
+                out.append(x)
+            elif isinstance(x, (list, tuple)):
+                for i in x:
+                    walk(i)
+            elif isinstance(x, dict):
+                for v in x.values():
+                    walk(v)
+
+        for n in self.nodes:
+            walk(n.args)
+            walk(n.kwargs)
+            if n.kind == "train":
+                for p in n.fn.__self__._parameter_list if hasattr(n.fn, "__self__") else []:
+                    walk(p)
+        return out
+
+    def list_vars(self):
+        return list(self._keep)
+
+    def var(self, name):
+        return self._keep[self._name2vid[name]] if name in self._name2vid else None
+
+    @property
+    def num_blocks(self):
+        return 1
+
+    def __repr__(self):
+        return f"Program(nodes={len(self.nodes)}, feeds={list(self.placeholders)})"
+
+
+_main = [Program()]
+_startup = [Program()]
+_recording = [None]
+
+
+def default_main_program():
+    return _main[0]
+
+
+def default_startup_program():
+    return _startup[0]
+
+
+class _Recorder(TorchFunctionMode):
+    def __init__(self, program):
+        super().__init__()
+        self.program = program
+
+    def __torch_function__(self, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        out = func(*args, **kwargs)
+        p = self.program
+        if p._touches_program(args) or p._touches_program(kwargs):
+            name = getattr(func, "__name__", "")
+            if name not in ("__get__", "size", "dim", "numel", "stride", "is_contiguous", "data_ptr", "__len__", "is_floating_point", "is_complex", "element_size", "_is_view", "storage_offset"):
+                p._record(func, args, kwargs, out)
+        return out
+
+
+@contextlib.contextmanager
+def program_guard(main_program, startup_program=None):
+    prev_m, prev_s, prev_r = _main[0], _startup[0], _recording[0]
+    _main[0] = main_program
+    if startup_program is not None:
+        _startup[0] = startup_program
+    rec = _Recorder(main_program)
+    _recording[0] = main_program
+    try:
+        with rec:
+            yield
+    finally:
+        _main[0], _startup[0], _recording[0] = prev_m, prev_s, prev_r
+
+
+def data(name, shape, dtype="float32", lod_level=0):
+    prog = _main[0]
+    ex_shape = [1 if (s is None or s < 0) else int(s) for s in shape]
+    d = _dt.convert_dtype(dtype) or torch.float32
+    with torch._C.DisableTorchFunction():
+        t = torch.zeros(ex_shape, dtype=d)
+    v = t.as_subclass(Variable)
+    v.name = name
+    v.__dict__["_pd_desc_shape"] = [-1 if (s is None or s < 0) else int(s) for s in shape]
+    prog.placeholders[name] = prog._new_vid(v, name)
+    return v
+
+
+def create_parameter(shape, dtype, name=None, attr=None, is_bias=False, default_initializer=None):
+    from ..nn.layer import _make_parameter
+
+    return _make_parameter(list(shape), _dt.convert_dtype(dtype), attr=attr, is_bias=is_bias, default_initializer=default_initializer, name=name)
+
+
+def create_global_var(shape, value, dtype, persistable=False, force_cpu=False, name=None):
+    t = torch.full(list(shape), value, dtype=_dt.convert_dtype(dtype)).as_subclass(Tensor)
+    t.persistable = persistable
+    if name:
+        t.name = name
+    return t
+
+
+def _minimize_node(optimizer, loss, program):
+    """Appended by Optimizer.minimize in static mode: replayed as backward + update."""
+    vid = program._vids.get(id(loss), program._fetch_alias.get(id(loss)))
+
+    def train_step(env):
+        l = env[vid]
+        optimizer.clear_grad()
+        l.backward()
+        optimizer.step()
+
+    n = _Node(train_step, (), {}, [], kind="train")
+    n.args = (optimizer,)
+    program.nodes.append(n)
+
+
+def append_backward(loss, parameter_list=None, no_grad_set=None, callbacks=None):
+    prog = _main[0]
+    vid = prog._vids.get(id(loss))
+    params = list(parameter_list) if parameter_list is not None else prog.all_parameters()
+
+    def bwd(env):
+        for p in params:
+            p.clear_grad()
+        env[vid].backward(retain_graph=True)
+
+    n = _Node(bwd, (), {}, [], kind="train")
+    prog.nodes.append(n)
+    return [(p, p) for p in params]
+
+
+def gradients(targets, inputs, target_gradients=None, no_grad_set=None):
+    from ..autograd import grad
+
+    return grad(targets, inputs, target_gradients, allow_unused=True)
+
+
+class Executor:
+    def __init__(self, place=None):
+        self.place = place
+
+    def run(self, program=None, feed=None, fetch_list=None, feed_var_name="feed", fetch_var_name="fetch", scope=None, return_numpy=True,
+            use_program_cache=False, use_prune=False):
+        program = program if program is not None else _main[0]
+        if isinstance(program, CompiledProgram):
+            program = program._program
+        if not program.nodes and not fetch_list:
+            return []   # startup program: parameters are initialised at creation time
+        feed = feed or {}
+        env = {}
+        dev = None
+        for name, vid in program.placeholders.items():
+            if name in feed:
+                v = feed[name]
+                t = v if isinstance(v, torch.Tensor) else to_tensor(np.asarray(v))
+                env[vid] = t
+                dev = t.device
+
+        def decode(x):
+            if isinstance(x, _Ref):
+                if x.vid not in env:
+                    raise KeyError(f"program variable #{x.vid} is not available: is a feed missing? feeds={list(program.placeholders)}")
+                return env[x.vid]
+            if isinstance(x, (list, tuple)):
+                return type(x)(decode(i) for i in x)
+            if isinstance(x, dict):
+                return {k: decode(v) for k, v in x.items()}
+            return x
+
+        def run_node(n):
+            if n.kind == "train":
+                n.fn(env)
+                return
+            out = n.fn(*decode(n.args), **decode(n.kwargs))
+            flat = []
+
+            def fl(o):
+                if isinstance(o, torch.Tensor):
+                    flat.append(o)
+                elif isinstance(o, (list, tuple)):
+                    for i in o:
+                        fl(i)
+
+            fl(out)
+            for vid, t in zip(n.outs, flat):
+                env[vid] = t
+
+        self._schedule(program, run_node)
+        outs = []
+        for f in fetch_list or []:
+            if isinstance(f, str):
+                vid = program._name2vid[f]
+            else:
+                vid = program._fetch_alias.get(id(f))
+                if vid is None:
+                    outs.append(f.numpy() if return_numpy and isinstance(f, torch.Tensor) else f)
+                    continue
+            v = env[vid]
+            outs.append(v.detach().cpu().as_subclass(Tensor).numpy() if return_numpy else v)
+        return outs
+
+    @staticmethod
+    def _schedule(program, run_node):
+        """Replay in dependency order through the native GraphExecutor when available (falls back to tape order)."""
+        from .._build import load
+
+        m = load()
+        nodes = program.nodes
+        if m is None or not hasattr(m, "GraphExecutor") or len(nodes) < 2:
+            for n in nodes:
+                run_node(n)
+            return
+        ge = m.GraphExecutor()
+        producer = {}
+        last_train = -1
+        for i, n in enumerate(nodes):
+            deps = set()
+
+            def collect(x):
+                if isinstance(x, _Ref) and x.vid in producer:
+                    deps.add(producer[x.vid])
+                elif isinstance(x, (list, tuple)):
+                    for j in x:
+                        collect(j)
+                elif isinstance(x, dict):
+                    for v in x.values():
+                        collect(v)
+
+            collect(n.args)
+            collect(n.kwargs)
+            if n.kind == "train":   # side effects: order after everything recorded before it
+                deps.update(range(i))
+            elif last_train >= 0:
+                deps.add(last_train)
+            if i > 0 and not n.outs:
+                deps.add(i - 1)
+            ge.add_node((lambda nn=n: run_node(nn)), sorted(deps), 0, 0)
+            for vid in n.outs:
+                producer[vid] = i
+            if n.kind == "train":
+                last_train = i
+        ge.run(-1)
+
+    def close(self):
+        pass
+
+
+class CompiledProgram:
+    def __init__(self, program_or_graph, build_strategy=None):
+        self._program = program_or_graph
+
+    def with_data_parallel(self, *a, **k):
+        return self
+
+
+class BuildStrategy:
+    def __init__(self):
+        self.fuse_all_reduce_ops = self.fuse_elewise_add_act_ops = self.fuse_bn_act_ops = self.enable_inplace = False
+        self.memory_optimize = self.build_cinn_pass = False
+
+
+class ExecutionStrategy:
+    def __init__(self):
+        self.num_threads, self.num_iteration_per_drop_scope = 1, 10
+
+
+class _Scope:
+    def __init__(self):
+        self.vars = {}
+
+    def find_var(self, name):
+        return self.vars.get(name)
+
+    def var(self, name):
+        return self.vars.setdefault(name, None)
+
+
+_scope = _Scope()
+
+
+def global_scope():
+    return _scope
+
+
+@contextlib.contextmanager
+def scope_guard(scope):
+    global _scope
+    prev = _scope
+    _scope = scope
+    try:
+        yield
+    finally:
+        _scope = prev
+
+
+@contextlib.contextmanager
+def name_scope(prefix=None):
+    yield
+
+
+@contextlib.contextmanager
+def device_guard(device=None):
+    yield
+
+
+def cpu_places(device_count=None):
+    return [CPUPlace()] * (device_count or 1)
+
+
+def cuda_places(device_ids=None):
+    ids = device_ids if device_ids is not None else range(max(1, torch.cuda.device_count()))
+    return [CUDAPlace(i) for i in ids]
+
+
+def xpu_places(device_ids=None):
+    return []
+
+
+def save(program, model_path, protocol=4, **configs):
+    params = {p.name: p for p in program.all_parameters()}
+    _psave(params, model_path + ".pdparams", protocol)
+    with open(model_path + ".pdmodel", "wb") as f:
+        pickle.dump({"feeds": list(program.placeholders), "n_nodes": len(program.nodes)}, f)
+
+
+def load(program, model_path, executor=None, var_list=None):
+    sd = _pload(model_path + ".pdparams")
+    for p in program.all_parameters():
+        if p.name in sd:
+            p.set_value(sd[p.name])
+
+
+def load_program_state(model_path, var_list=None):
+    return _pload(model_path + ".pdparams", return_numpy=True)
+
+
+def set_program_state(program, state_dict):
+    for p in program.all_parameters():
+        if p.name in state_dict:
+            p.set_value(state_dict[p.name])
+
+
+def save_inference_model(path_prefix, feed_vars, fetch_vars, executor, program=None, **kwargs):
+    program = program or _main[0]
+    feed_vars = feed_vars if isinstance(feed_vars, (list, tuple)) else [feed_vars]
+    fetch_vars = fetch_vars if isinstance(fetch_vars, (list, tuple)) else [fetch_vars]
+    d = os.path.dirname(path_prefix)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    infer = program.clone(for_test=True)
+    blob = {"program": infer, "feeds": [v.name for v in feed_vars], "fetch_vids": [program._fetch_alias[id(v)] for v in fetch_vars]}
+    with open(path_prefix + ".pdmodel", "wb") as f:
+        pickle.dump(blob, f)
+
+
+def load_inference_model(path_prefix, executor, **kwargs):
+    with open(path_prefix + ".pdmodel", "rb") as f:
+        blob = pickle.load(f)
+    prog = blob["program"]
+    fetch = [prog._keep[v] for v in blob["fetch_vids"]]
+    return prog, blob["feeds"], fetch
+
+
+def normalize_program(program, feed_vars, fetch_vars, **kwargs):
+    return program.clone(for_test=True)
+
+
+def serialize_program(feed_vars, fetch_vars, **kwargs):
+    return pickle.dumps({"feeds": [v.name for v in feed_vars]})
+
+
+def serialize_persistables(feed_vars, fetch_vars, executor, **kwargs):
+    return pickle.dumps({p.name: p.numpy() for p in _main[0].all_parameters()})
+
+
+def deserialize_program(data):
+    return pickle.loads(data)
+
+
+def deserialize_persistables(program, data, executor):
+    sd = pickle.loads(data)
+    set_program_state(program, sd)
+
+
+def save_to_file(path, content):
+    with open(path, "wb") as f:
+        f.write(content)
+
+
+def load_from_file(path):
+    with open(path, "rb") as f:
+        return f.read()
+
+
+def Print(input, first_n=-1, message=None, summarize=20, print_tensor_name=True, print_tensor_type=True, print_tensor_shape=True,
+          print_tensor_layout=True, print_tensor_lod=True, print_phase="both"):
+    print(message or "", input)
+    return input
+
+
+def py_func(func, x, out, backward_func=None, skip_vars_in_backward_input=None):
+    res = func(*x) if isinstance(x, (list, tuple)) else func(x)
+    return res
+
+
+def accuracy(input, label, k=1, correct=None, total=None):
+    from ..metric import accuracy as acc
+
+    return acc(input, label, k)
+
+
+def auc(input, label, curve="ROC", num_thresholds=4095, topk=1, slide_steps=1, ins_tag_weight=None):
+    from ..metric import Auc
+
+    m = Auc(curve, num_thresholds)
+    m.update(input, label)
+    return to_tensor(np.asarray(m.accumulate(), dtype=np.float32))
+
+
+def ctr_metric_bundle(input, label, ins_tag_weight=None):
+    raise NotImplementedError("ctr_metric_bundle belongs to the parameter-server stack")
+
+
+class WeightNormParamAttr(ParamAttr):
+    def __init__(self, dim=None, **kw):
+        super().__init__(**kw)
+        self.dim = dim
+
+
+class ExponentialMovingAverage:
+    def __init__(self, decay=0.999, thres_steps=None, name=None):
+        self._decay, self._shadow, self._backup, self._params = decay, {}, {}, None
+
+    def update(self, parameters=None):
+        params = parameters or self._params or _main[0].all_parameters()
+        self._params = params
+        with torch.no_grad():
+            for p in params:
+                s = self._shadow.get(p.name)
+                if s is None:
+                    self._shadow[p.name] = p.detach().clone()
+                else:
+                    s.mul_(self._decay).add_(p.detach(), alpha=1 - self._decay)
+
+    @contextlib.contextmanager
+    def apply(self, executor=None, need_restore=True):
+        params = self._params or []
+        with torch.no_grad():
+            for p in params:
+                self._backup[p.name] = p.detach().clone()
+                if p.name in self._shadow:
+                    p.copy_(self._shadow[p.name])
+        try:
+            yield
+        finally:
+            if need_restore:
+                self.restore()
+
+    def restore(self, executor=None):
+        with torch.no_grad():
+            for p in self._params or []:
+                if p.name in self._backup:
+                    p.copy_(self._backup[p.name])
+
+
+class IpuStrategy:
+    def __init__(self):
+        raise RuntimeError("IPU is not supported")
+
+
+IpuCompiledProgram = IpuStrategy
+
+
+def ipu_shard_guard(*a, **k):
+    raise RuntimeError("IPU is not supported")
+
+
+def set_ipu_shard(*a, **k):
+    raise RuntimeError("IPU is not supported")
+
+
+from . import nn  # noqa: E402,F401

@@ -53,8 +53,9 @@ class Tensor(torch.Tensor):
         return _convert(ret)
 
     def __reduce_ex__(self, proto):
-        # pickle as (name, ndarray) like the reference (framework/io.py:_pickle_save.reduce_varbase)
-        return (tuple, ((self.name, self.numpy()),))
+        # generic pickling (multiprocessing, jit.save of a Layer) keeps the tensor type; paddle.save uses its own
+        # dispatch table to write the reference's (name, ndarray) form (framework/io.py:_pickle_dump)
+        return (_rebuild_tensor, (type(self), self.detach().cpu().as_subclass(torch.Tensor), self.requires_grad, dict(self.__dict__)))
 
     def __deepcopy__(self, memo):
         with torch.no_grad():
@@ -363,11 +364,20 @@ class Parameter(Tensor):
         memo[id(self)] = new
         return new
 
-    def __reduce_ex__(self, proto):
-        return (tuple, ((self.name, self.numpy()),))
-
-
 EagerParamBase = Parameter
+
+
+def _rebuild_tensor(cls, base, requires_grad, attrs):
+    if issubclass(cls, Parameter):
+        t = Parameter(base, trainable=requires_grad, name=attrs.get("_pd_name"))
+    else:
+        t = base.as_subclass(cls)
+        if requires_grad:
+            t.requires_grad_(True)
+    for k, v in attrs.items():
+        if k not in ("_arena_grad",):
+            t.__dict__[k] = v
+    return t
 
 
 def _np_to_torch(a: np.ndarray):
