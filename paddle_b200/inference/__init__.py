@@ -1,0 +1,273 @@
+"""paddle.inference. Parity: python/paddle/inference/wrapper.py, paddle/fluid/inference/api/analysis_predictor.cc
+(Config, create_predictor, Predictor, Tensor handles, PrecisionType, PlaceType, get_version...).
+
+The predictor loads ``jit.save`` artifacts (prefix.pdmodel + prefix.pdiparams) and serves them with CUDA-graph replay
+per input signature (jit.StaticFunction) - the sm_100a answer to the reference's IR-pass + TensorRT pipeline."""
+from __future__ import annotations
+
+import enum
+import os
+
+import numpy as np
+import torch
+
+from ..tensor import to_tensor
+
+
+class PrecisionType(enum.Enum):
+    Float32 = 0
+    Half = 1
+    Int8 = 2
+    Bfloat16 = 3
+
+
+class PlaceType(enum.Enum):
+    UNK = -1
+    CPU = 0
+    GPU = 1
+    XPU = 2
+    CUSTOM = 3
+
+
+class DataType(enum.Enum):
+    FLOAT32 = 0
+    INT64 = 1
+    INT32 = 2
+    UINT8 = 3
+    INT8 = 4
+    FLOAT16 = 5
+    BOOL = 6
+    FLOAT64 = 7
+    BFLOAT16 = 8
+
+
+class Config:
+    def __init__(self, model_dir_or_prog=None, params_file=None):
+        self._prefix = None
+        if model_dir_or_prog is not None:
+            self.set_model(model_dir_or_prog, params_file)
+        self._use_gpu, self._gpu_id, self._precision = False, 0, PrecisionType.Float32
+        self._memory_optim, self._ir_optim, self._glog, self._threads = False, True, True, 1
+
+    def set_model(self, prog_file, params_file=None):
+        p = prog_file
+        for suf in (".pdmodel", ".json"):
+            if p.endswith(suf):
+                p = p[: -len(suf)]
+        self._prefix = p
+
+    def set_prog_file(self, f):
+        self.set_model(f)
+
+    def set_params_file(self, f):
+        pass
+
+    def prog_file(self):
+        return self._prefix + ".pdmodel"
+
+    def params_file(self):
+        return self._prefix + ".pdiparams"
+
+    def model_dir(self):
+        return os.path.dirname(self._prefix or "")
+
+    def enable_use_gpu(self, memory_pool_init_size_mb=100, device_id=0, precision_mode=PrecisionType.Float32):
+        self._use_gpu, self._gpu_id, self._precision = True, device_id, precision_mode
+
+    def disable_gpu(self):
+        self._use_gpu = False
+
+    def use_gpu(self):
+        return self._use_gpu
+
+    def gpu_device_id(self):
+        return self._gpu_id
+
+    def enable_memory_optim(self, x=True):
+        self._memory_optim = x
+
+    def switch_ir_optim(self, x=True):
+        self._ir_optim = x
+
+    def ir_optim(self):
+        return self._ir_optim
+
+    def switch_use_feed_fetch_ops(self, x=False):
+        pass
+
+    def switch_specify_input_names(self, x=True):
+        pass
+
+    def set_cpu_math_library_num_threads(self, n):
+        self._threads = n
+        torch.set_num_threads(max(1, int(n)))
+
+    def cpu_math_library_num_threads(self):
+        return self._threads
+
+    def enable_mkldnn(self):
+        pass
+
+    def disable_glog_info(self):
+        self._glog = False
+
+    def enable_tensorrt_engine(self, *a, **k):
+        """TensorRT subgraphs are replaced by the native CUDA-graph path; accepted for config compatibility."""
+        self._trt = True
+
+    def tensorrt_engine_enabled(self):
+        return getattr(self, "_trt", False)
+
+    def set_trt_dynamic_shape_info(self, *a, **k):
+        pass
+
+    def enable_cuda_graph(self):
+        self._cuda_graph = True
+
+    def summary(self):
+        return f"Config(prefix={self._prefix}, gpu={self._use_gpu}, precision={self._precision.name})"
+
+
+class _Handle:
+    """Input/output tensor handle (paddle_infer.Tensor)."""
+
+    def __init__(self, name):
+        self.name_, self._t = name, None
+
+    def name(self):
+        return self.name_
+
+    def reshape(self, shape):
+        self._shape = list(shape)
+
+    def copy_from_cpu(self, arr):
+        self._t = to_tensor(np.ascontiguousarray(arr))
+
+    def share_external_data(self, t):
+        self._t = t
+
+    def copy_to_cpu(self):
+        return self._t.numpy()
+
+    def shape(self):
+        return list(self._t.shape) if self._t is not None else getattr(self, "_shape", [])
+
+    def type(self):
+        return None if self._t is None else self._t.dtype
+
+    def lod(self):
+        return []
+
+    def set_lod(self, lod):
+        pass
+
+
+class Predictor:
+    def __init__(self, config):
+        from .. import jit
+
+        self._config = config
+        self._layer = jit.load(config._prefix)
+        spec = self._layer._spec.get("input_spec") or []
+        names = [s[2] if s and s[2] else f"x{i}" for i, s in enumerate(spec)] or ["x0"]
+        self._inputs = {n: _Handle(n) for n in names}
+        self._outputs = {}
+        if config._use_gpu and torch.cuda.is_available():
+            self._layer.to(torch.device("cuda", config._gpu_id))
+            if config._precision in (PrecisionType.Half, PrecisionType.Bfloat16):
+                self._layer._inner._cast_floating(torch.float16 if config._precision == PrecisionType.Half else torch.bfloat16)
+        self._dev = torch.device("cuda", config._gpu_id) if (config._use_gpu and torch.cuda.is_available()) else torch.device("cpu")
+
+    def get_input_names(self):
+        return list(self._inputs)
+
+    def get_input_handle(self, name):
+        if name not in self._inputs:
+            self._inputs[name] = _Handle(name)
+        return self._inputs[name]
+
+    def get_output_names(self):
+        return list(self._outputs) or ["out0"]
+
+    def get_output_handle(self, name):
+        if name not in self._outputs:
+            self._outputs[name] = _Handle(name)
+        return self._outputs[name]
+
+    @torch.no_grad()
+    def run(self, inputs=None):
+        if inputs is not None:
+            args = [i if isinstance(i, torch.Tensor) else to_tensor(np.asarray(i)) for i in inputs]
+        else:
+            args = [h._t for h in self._inputs.values() if h._t is not None]
+        p0 = next(iter(self._layer._inner.parameters()), None)
+        args = [a.to(self._dev) for a in args]
+        if p0 is not None and p0.dtype in (torch.float16, torch.bfloat16):
+            args = [a.to(p0.dtype) if a.is_floating_point() else a for a in args]
+        out = self._layer(*args)
+        outs = list(out) if isinstance(out, (list, tuple)) else [out]
+        for i, o in enumerate(outs):
+            self.get_output_handle(f"out{i}")._t = o
+        return outs if inputs is not None else True
+
+    def clone(self):
+        return Predictor(self._config)
+
+    def clear_intermediate_tensor(self):
+        pass
+
+    def try_shrink_memory(self):
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+
+
+def create_predictor(config):
+    return Predictor(config)
+
+
+class PredictorPool:
+    def __init__(self, config, size=1):
+        self._preds = [Predictor(config) for _ in range(size)]
+
+    def retrive(self, idx):
+        return self._preds[idx]
+
+    retrieve = retrive
+
+
+def get_version():
+    from .. import __version__
+
+    return f"paddle_b200 {__version__} (sm_100a)"
+
+
+def get_trt_compile_version():
+    return (0, 0, 0)
+
+
+def get_trt_runtime_version():
+    return (0, 0, 0)
+
+
+def get_num_bytes_of_data_type(dtype):
+    return {DataType.FLOAT32: 4, DataType.INT64: 8, DataType.INT32: 4, DataType.UINT8: 1, DataType.INT8: 1, DataType.FLOAT16: 2,
+            DataType.BOOL: 1, DataType.FLOAT64: 8, DataType.BFLOAT16: 2}[dtype]
+
+
+def convert_to_mixed_precision(model_file, params_file, mixed_model_file, mixed_params_file, mixed_precision, backend=None, keep_io_types=True, black_list=None, **kw):
+    from .. import jit
+    from ..framework.io import load, save
+
+    prefix = model_file[: -len(".pdmodel")] if model_file.endswith(".pdmodel") else model_file
+    sd = load(prefix + ".pdiparams")
+    d = torch.float16 if mixed_precision == PrecisionType.Half else torch.bfloat16
+    sd = {k: (v.astype(d) if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in sd.items()}
+    out = mixed_model_file[: -len(".pdmodel")] if mixed_model_file.endswith(".pdmodel") else mixed_model_file
+    save(sd, out + ".pdiparams")
+    import shutil
+
+    shutil.copy(prefix + ".pdmodel", out + ".pdmodel")
+
+
+Tensor = _Handle
+XpuConfig = InternalUtils = None
