@@ -81,6 +81,8 @@ def apply_rope_packed(qkv, cos_t, sin_t, rope_heads, total_heads, dim, position_
     cos_t, sin_t, position_ids = raw(cos_t), raw(sin_t), raw(position_ids)
     if use_fused(q) and q.is_contiguous() and q.dtype in (torch.float32, torch.float16, torch.bfloat16) and (dim // 2) % (16 // q.element_size()) == 0:
         pid = position_ids.reshape(-1).contiguous() if position_ids is not None else None
+        if q._is_view() and q.requires_grad:
+            q = q.clone()  # autograd forbids in-place updates of views produced inside custom Functions (e.g. fused all-gather GEMM)
         return wrap(_RopePacked.apply(q, cos_t.float().contiguous(), sin_t.float().contiguous(), pid, int(q.shape[1]),
                                       int(rope_heads), int(total_heads), int(dim), bool(neox)))
     b, s = q.shape[0], q.shape[1]
