@@ -1,0 +1,28 @@
+"""paddle.base.core stand-ins used by user code (eager.Tensor, is_compiled_with_*, VarDesc types)."""
+import torch
+
+from ..framework.place import CPUPlace, CUDAPinnedPlace, CUDAPlace, Place, is_compiled_with_cuda, is_compiled_with_rocm, is_compiled_with_xpu  # noqa: F401
+from ..tensor import Tensor
+
+
+class eager:
+    Tensor = Tensor
+
+
+class VarDesc:
+    class VarType:
+        BOOL, INT8, UINT8, INT16, INT32, INT64, FP16, BF16, FP32, FP64 = (torch.bool, torch.int8, torch.uint8, torch.int16, torch.int32, torch.int64,
+                                                                        torch.float16, torch.bfloat16, torch.float32, torch.float64)
+        LOD_TENSOR, SELECTED_ROWS, VOCAB = 7, 8, 99
+
+
+def get_cuda_device_count():
+    return torch.cuda.device_count()
+
+
+def is_bfloat16_supported(place=None):
+    return True
+
+
+def is_float16_supported(place=None):
+    return True

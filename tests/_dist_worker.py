@@ -357,11 +357,138 @@ def case_p2p_kernels():
 
     x = (torch.randn(256, 512, device="cuda") * 0.1).to(torch.bfloat16)
     wgt = (torch.randn(512, 384, device="cuda") * 0.1).to(torch.bfloat16)
-    y = fused_mp.row_parallel_linear(x, wgt, None if False else dist.collective._global_group())
+    grp = dist.collective._global_group()
+    y = fused_mp.row_parallel_linear(x, wgt, grp)
     ref = (x.float() @ wgt.float())
     torch.distributed.all_reduce(ref)
     assert ((y.float() - ref).norm() / ref.norm()).item() < 2e-2
+    # GEMM -> reduce-scatter (sequence dim) and all-gather -> GEMM, forward and backward, vs NCCL + fp32 matmul
+    torch.manual_seed(100 + r)
+    xs = (torch.randn(128 * w, 2, 512, device="cuda") * 0.1).to(torch.bfloat16).requires_grad_(True)      # [S, B, K_local]
+    wr = (torch.randn(512, 384, device="cuda") * 0.1).to(torch.bfloat16).requires_grad_(True)
+    yrs = fused_mp.linear_reduce_scatter(xs, wr, grp)
+    full = xs.detach().float() @ wr.detach().float()
+    torch.distributed.all_reduce(full)
+    ref_rs = full.chunk(w, 0)[r]
+    assert yrs.shape == ref_rs.shape, (yrs.shape, ref_rs.shape)
+    e = ((yrs.float() - ref_rs).norm() / ref_rs.norm()).item()
+    assert e < 2e-2, f"gemm_reduce_scatter fwd {e}"
+    gy = (torch.randn_like(yrs) * 0.1)
+    yrs.backward(gy)
+    gl = [torch.empty_like(gy) for _ in range(w)]
+    torch.distributed.all_gather(gl, gy.contiguous())
+    gfull = torch.cat(gl, 0).float()
+    ref_dx = gfull @ wr.detach().float().t()
+    ref_dw = xs.detach().float().reshape(-1, 512).t() @ gfull.reshape(-1, 384)
+    e = ((xs.grad.float() - ref_dx).norm() / ref_dx.norm()).item()
+    assert e < 2e-2, f"gemm_reduce_scatter dx {e}"
+    e = ((wr.grad.float() - ref_dw).norm() / ref_dw.norm()).item()
+    assert e < 2e-2, f"gemm_reduce_scatter dw {e}"
+    xa = (torch.randn(128, 2, 512, device="cuda") * 0.1).to(torch.bfloat16).requires_grad_(True)          # [S/p, B, K]
+    wc = (torch.randn(512, 256, device="cuda") * 0.1).to(torch.bfloat16).requires_grad_(True)
+    yag = fused_mp.allgather_linear(xa, wc, grp)
+    xl = [torch.empty_like(xa) for _ in range(w)]
+    torch.distributed.all_gather(xl, xa.detach().contiguous())
+    xfull = torch.cat(xl, 0).float()
+    ref_ag = xfull @ wc.detach().float()
+    e = ((yag.float() - ref_ag).norm() / ref_ag.norm()).item()
+    assert e < 2e-2, f"allgather_gemm fwd {e}"
+    g2 = torch.randn_like(yag) * 0.1
+    yag.backward(g2)
+    dxf = g2.float() @ wc.detach().float().t()
+    torch.distributed.all_reduce(dxf)
+    e = ((xa.grad.float() - dxf.chunk(w, 0)[r]).norm() / dxf.chunk(w, 0)[r].norm()).item()
+    assert e < 2e-2, f"allgather_gemm dx {e}"
+    ref_dw2 = xfull.reshape(-1, 512).t() @ g2.float().reshape(-1, 256)
+    e = ((wc.grad.float() - ref_dw2).norm() / ref_dw2.norm()).item()
+    assert e < 2e-2, f"allgather_gemm dw {e}"
+    # vocab-parallel fused cross entropy kernels vs dense fp32
+    from paddle_b200.kernels import loss as KL
+
+    torch.manual_seed(7)
+    logits = (torch.randn(300, 1024, device="cuda") * 2).to(torch.bfloat16)
+    labels = torch.randint(0, 1024, (300,), device="cuda")
+    labels[3] = -100
+    v = 1024 // w
+    loc = logits[:, r * v:(r + 1) * v].contiguous().requires_grad_(True)
+    lv = KL.vocab_parallel_cross_entropy(loc, labels, r * v, None, -100)
+    lref_in = logits.float().requires_grad_(True)
+    lref = torch.nn.functional.cross_entropy(lref_in, labels, ignore_index=-100, reduction="none")
+    e = ((lv.float() - lref).norm() / lref.norm()).item()
+    assert e < 1e-2, f"vocab parallel CE fwd {e}"
+    lv.sum().backward()
+    lref.sum().backward()
+    gref = lref_in.grad[:, r * v:(r + 1) * v]
+    e = ((loc.grad.float() - gref).norm() / gref.norm()).item()
+    assert e < 3e-2, f"vocab parallel CE bwd {e}"
     dist.barrier()
+
+
+def case_mp_sp_bf16():
+    """bf16 GPU run of the mp2+SP tiny Llama through the fused peer-memory paths: loss tracks the dense bf16 model."""
+    assert GPU
+    _, hcg = setup(mp=2)
+    r = hcg.get_model_parallel_rank()
+    from paddle_b200.distributed.fleet import topology as topo
+    from paddle_b200.models import llama as L
+
+    paddle.set_default_dtype("bfloat16")
+    kw = dict(hidden_size=256, intermediate_size=512, num_attention_heads=4, num_key_value_heads=4, vocab_size=1024, max_position_embeddings=128)
+    cfg_d = L.llama_tiny(**kw)
+    ids = paddle.to_tensor(np.random.RandomState(0).randint(0, cfg_d.vocab_size, (2, 129)))
+    saved = topo.get_hybrid_communicate_group()
+    topo._set_hcg(None)
+    paddle.seed(11)
+    ref = L.LlamaForCausalLM(cfg_d)
+    topo._set_hcg(saved)
+    for p_ in ref.parameters():
+        dist.broadcast(p_, 0)
+    cfg = L.llama_tiny(sequence_parallel=True, **kw)
+    par = L.LlamaForCausalLM(cfg)
+    sd = ref.state_dict()
+    h, f = cfg.hidden_size, cfg.intermediate_size
+
+    def shard_cols(wt, parts):
+        outs, off = [], 0
+        for n in parts:
+            seg = wt[:, off:off + n]
+            outs.append(seg[:, r * (n // 2):(r + 1) * (n // 2)])
+            off += n
+        return paddle.concat(outs, axis=1)
+
+    new = {}
+    for k, v in par.state_dict().items():
+        d = sd[k]
+        if k.endswith("qkv_proj.weight"):
+            new[k] = shard_cols(d, [h, h, h])
+        elif k.endswith("gate_up_proj.weight"):
+            new[k] = shard_cols(d, [f, f])
+        elif k.endswith("o_proj.weight") or k.endswith("down_proj.weight") or k.endswith("embed_tokens.weight"):
+            n = d.shape[0]
+            new[k] = d[r * (n // 2):(r + 1) * (n // 2)]
+        elif k == "lm_head.weight":
+            n = d.shape[1]
+            new[k] = d[:, r * (n // 2):(r + 1) * (n // 2)]
+        else:
+            new[k] = d
+    par.set_state_dict(new)
+    model = fleet.distributed_model(par)
+    mk = lambda ps: paddle.optimizer.AdamW(1e-3, parameters=ps, weight_decay=0.01, multi_precision=True, grad_clip=paddle.nn.ClipGradByGlobalNorm(1.0))  # noqa: E731
+    opt = fleet.distributed_optimizer(mk(par.parameters()))
+    ropt = mk(ref.parameters())
+    for it in range(4):
+        loss = model(ids[:, :-1], ids[:, 1:])
+        loss.backward()
+        opt.step()
+        opt.clear_grad()
+        rl = ref(ids[:, :-1], ids[:, 1:])
+        rl.backward()
+        ropt.step()
+        ropt.clear_grad()
+        print("STEP", it, loss.item(), rl.item(), flush=True)
+        assert np.isfinite(loss.item()), "loss is not finite"
+        close(loss.item(), rl.item(), 3e-2)
+    paddle.set_default_dtype("float32")
 
 
 if __name__ == "__main__":

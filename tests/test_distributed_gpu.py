@@ -22,6 +22,11 @@ def test_mp_sp_parity_gpu():
     run_dist("mp_sp_parity", 2, extra_env={"B200_TEST_GPU": "1"})
 
 
+def test_mp_sp_bf16_fused_paths():
+    _need(2)
+    run_dist("mp_sp_bf16", 2, extra_env={"B200_TEST_GPU": "1"})
+
+
 def test_pp_gpu():
     _need(2)
     run_dist("pp", 2, extra_env={"B200_TEST_GPU": "1"})
