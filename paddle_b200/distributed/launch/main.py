@@ -1,0 +1,96 @@
+from __future__ import annotations
+
+import argparse
+import os
+import signal
+import socket
+import subprocess
+import sys
+import time
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def parse(argv=None):
+    ap = argparse.ArgumentParser("paddle_b200.distributed.launch")
+    ap.add_argument("--master", default=None, help="ip:port of the rendezvous endpoint (default 127.0.0.1:<free port>)")
+    ap.add_argument("--nnodes", default="1")
+    ap.add_argument("--rank", type=int, default=0, help="node rank")
+    ap.add_argument("--nproc_per_node", type=int, default=None)
+    ap.add_argument("--devices", "--gpus", dest="devices", default=None, help="comma separated device ids")
+    ap.add_argument("--log_dir", default="log")
+    ap.add_argument("--job_id", default="default")
+    ap.add_argument("--run_mode", default="collective")
+    ap.add_argument("--max_restart", type=int, default=0)
+    ap.add_argument("--elastic_timeout", type=int, default=30)
+    ap.add_argument("training_script")
+    ap.add_argument("training_script_args", nargs=argparse.REMAINDER)
+    return ap.parse_args(argv)
+
+
+def launch(args):
+    import torch
+
+    devices = [d for d in args.devices.split(",")] if args.devices else [str(i) for i in range(max(1, torch.cuda.device_count()))]
+    nproc = args.nproc_per_node or len(devices)
+    nnodes = int(str(args.nnodes).split(":")[0])
+    if args.master:
+        addr, port = args.master.split(":")
+    else:
+        addr, port = "127.0.0.1", str(_free_port())
+    os.makedirs(args.log_dir, exist_ok=True)
+    world = nproc * nnodes
+    restarts = 0
+    while True:
+        procs = []
+        for lr in range(nproc):
+            rank = args.rank * nproc + lr
+            env = dict(os.environ)
+            env.update({"RANK": str(rank), "WORLD_SIZE": str(world), "LOCAL_RANK": str(lr), "MASTER_ADDR": addr, "MASTER_PORT": port,
+                        "PADDLE_TRAINER_ID": str(rank), "PADDLE_TRAINERS_NUM": str(world), "PADDLE_RANK_IN_NODE": str(lr),
+                        "PADDLE_LOCAL_SIZE": str(nproc), "PADDLE_JOB_ID": args.job_id, "FLAGS_selected_gpus": devices[lr % len(devices)]})
+            log = open(os.path.join(args.log_dir, f"workerlog.{rank}"), "w")
+            p = subprocess.Popen([sys.executable, "-u", args.training_script, *args.training_script_args], env=env,
+                                 stdout=log if lr != 0 else None, stderr=subprocess.STDOUT if lr != 0 else None)
+            procs.append((p, log))
+        failed = None
+        while True:   # watcher: first failure tears the pod down
+            alive = False
+            for p, _ in procs:
+                rc = p.poll()
+                if rc is None:
+                    alive = True
+                elif rc != 0 and failed is None:
+                    failed = rc
+            if failed is not None or not alive:
+                break
+            time.sleep(0.5)
+        if failed is not None:
+            for p, _ in procs:
+                if p.poll() is None:
+                    p.send_signal(signal.SIGTERM)
+            for p, _ in procs:
+                try:
+                    p.wait(timeout=10)
+                except subprocess.TimeoutExpired:
+                    p.kill()
+        for _, log in procs:
+            log.close()
+        if failed is None:
+            return 0
+        restarts += 1
+        if restarts > args.max_restart:
+            print(f"[launch] worker failed with exit code {failed}; see {args.log_dir}/workerlog.*", file=sys.stderr)
+            return failed
+        print(f"[launch] restart {restarts}/{args.max_restart} after failure (exit code {failed})", file=sys.stderr)
+        port = str(_free_port()) if not args.master else port
+
+
+def main(argv=None):
+    sys.exit(launch(parse(argv)))

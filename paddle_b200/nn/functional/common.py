@@ -17,6 +17,9 @@ def linear(x, weight, bias=None, name=None):
     """
     from ...kernels import gemm as K
 
+    if getattr(type(weight), "_is_dist", False) or getattr(type(x), "_is_dist", False):   # DistTensor: sharding propagation rules
+        y = torch.matmul(x, weight)
+        return y if bias is None else y + bias
     return K.linear(T(x), weight, bias)
 
 

@@ -19,7 +19,7 @@ def _pg(group):
 
 
 def available():
-    if _disabled[0] or not torch.cuda.is_available():
+    if _disabled[0] or not torch.cuda.is_available() or os.environ.get("B200_DISABLE_SYMM", "0") == "1":
         return False
     from .._build import load
 

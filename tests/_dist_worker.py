@@ -334,6 +334,114 @@ def case_sharding():
             close(a.numpy(), b.numpy(), 1e-3)
 
 
+def case_auto_parallel():
+    """DistTensor: shard/reshard round trips, matmul/elementwise/reduce propagation and dp+mp training parity.
+    Parity: test/auto_parallel/{test_shard_tensor_api,reshard_*,semi_auto_parallel_simple_net}.py."""
+    dist.init_parallel_env()
+    r, w = dist.get_rank(), dist.get_world_size()
+    import paddle_b200.distributed as D
+    from paddle_b200.distributed.auto_parallel import Partial, ProcessMesh, Replicate, Shard
+
+    mesh = ProcessMesh(list(range(w)), dim_names=["x"])
+    paddle.seed(5)
+    g = paddle.randn([4 * w, 6 * w])
+    a = D.shard_tensor(g, mesh, [Shard(0)])
+    assert a.shape == [4 * w, 6 * w] and a._local_shape == [4, 6 * w]
+    close(a._local_value().numpy(), g[r * 4:(r + 1) * 4].numpy())
+    b = D.reshard(a, mesh, [Shard(1)])
+    close(b._local_value().numpy(), g[:, r * 6:(r + 1) * 6].numpy())
+    c = D.reshard(b, mesh, [Replicate()])
+    close(c._local_value().numpy(), g.numpy())
+    p = D.reshard(c, mesh, [Partial()])
+    close(D.reshard(p, mesh, [Shard(0)])._local_value().numpy(), g[r * 4:(r + 1) * 4].numpy())
+    close(D.unshard_dtensor(a).numpy(), g.numpy())
+    # elementwise with a replicated bias that must be sliced, and reductions
+    bias = paddle.randn([6 * w])
+    e = b + bias
+    close(D.unshard_dtensor(e).numpy(), (g + bias).numpy())
+    close(float(D.unshard_dtensor(a.sum())), float(g.sum()), 1e-3)
+    close(D.unshard_dtensor(b.mean(0)).numpy(), g.mean(0).numpy(), 1e-5)
+    close(D.unshard_dtensor(paddle.transpose(a, [1, 0])).numpy(), g.t().numpy())
+
+    # tensor-parallel MLP through propagation rules: col-parallel then row-parallel, fwd + grads vs dense
+    paddle.seed(9)
+    w1, w2, x = paddle.randn([8, 16]) * 0.3, paddle.randn([16, 8]) * 0.3, paddle.randn([4, 8])
+    rw1, rw2 = paddle.to_tensor(w1.numpy(), stop_gradient=False), paddle.to_tensor(w2.numpy(), stop_gradient=False)
+    ref = paddle.matmul(paddle.nn.functional.gelu(paddle.matmul(x, rw1)), rw2)
+    ref.sum().backward()
+    d1 = D.shard_tensor(w1, mesh, [Shard(1)], stop_gradient=False)
+    d2 = D.shard_tensor(w2, mesh, [Shard(0)], stop_gradient=False)
+    h = paddle.nn.functional.gelu(paddle.matmul(D.shard_tensor(x, mesh, [Replicate()]), d1))
+    assert h.placements == [Shard(1)], h.placements
+    out = paddle.matmul(h, d2)
+    assert out.placements == [Partial()], out.placements
+    full = D.reshard(out, mesh, [Replicate()])
+    close(full._local_value().numpy(), ref.numpy(), 1e-4)
+    full.sum().backward()
+    close(d1.grad._local_value().numpy(), rw1.grad[:, r * (16 // w):(r + 1) * (16 // w)].numpy(), 1e-4)
+    close(d2.grad._local_value().numpy(), rw2.grad[r * (16 // w):(r + 1) * (16 // w)].numpy(), 1e-4)
+
+    # data parallel: batch sharded, params replicated, shard_optimizer (ZeRO-1 ownership) == single-process training
+    paddle.seed(13)
+    net = nn.Sequential(nn.Linear(8, 16), nn.Tanh(), nn.Linear(16, 2))
+    refn = nn.Sequential(nn.Linear(8, 16), nn.Tanh(), nn.Linear(16, 2))
+    refn.set_state_dict(net.state_dict())
+    D.shard_layer(net, mesh)
+    opt = D.shard_optimizer(paddle.optimizer.AdamW(1e-2, parameters=net.parameters()), D.ShardingStage1("x", mesh))
+    ropt = paddle.optimizer.AdamW(1e-2, parameters=refn.parameters())
+    X, Y = paddle.randn([4 * w, 8]), paddle.randn([4 * w, 2])
+    for _ in range(3):
+        xs, ys = D.shard_tensor(X, mesh, [Shard(0)]), D.shard_tensor(Y, mesh, [Shard(0)])
+        loss = paddle.nn.functional.mse_loss(net(xs), ys)
+        loss.backward()
+        opt.step()
+        opt.clear_grad()
+        rl = paddle.nn.functional.mse_loss(refn(X), Y)
+        rl.backward()
+        ropt.step()
+        ropt.clear_grad()
+        close(float(D.unshard_dtensor(loss)), float(rl), 1e-4)
+    for (k, pa), (_, pb) in zip(net.state_dict().items(), refn.state_dict().items()):
+        close(D.unshard_dtensor(pa).numpy(), pb.numpy(), 1e-4)
+
+    # intermediate API: parallelize() with a col/row plan == dense
+    paddle.seed(17)
+    mesh2 = ProcessMesh(np.arange(w).reshape(1, w), dim_names=["dp", "mp"])
+
+    class MLP(nn.Layer):
+        def __init__(self):
+            super().__init__()
+            self.up, self.down = nn.Linear(8, 16), nn.Linear(16, 8)
+
+        def forward(self, t):
+            return self.down(paddle.nn.functional.relu(self.up(t)))
+
+    m, mr = MLP(), MLP()
+    mr.set_state_dict(m.state_dict())
+    xin = paddle.randn([4, 8])
+    m = D.parallelize(m, mesh=mesh2, config={"mp_config": {"parallelize_plan": {"up": D.ColWiseParallel(), "down": D.RowWiseParallel()}}})
+    close(m(xin).numpy(), mr(xin).numpy(), 1e-4)
+
+
+def case_dist_checkpoint():
+    """Sharded save on one layout, load on another. Parity: test/auto_parallel/semi_auto_parallel_checkpoint_*.py."""
+    dist.init_parallel_env()
+    r, w = dist.get_rank(), dist.get_world_size()
+    import paddle_b200.distributed as D
+    from paddle_b200.distributed.auto_parallel import ProcessMesh, Replicate, Shard
+
+    mesh = ProcessMesh(list(range(w)), dim_names=["x"])
+    paddle.seed(3)
+    g1, g2 = paddle.randn([4 * w, 6 * w]), paddle.randn([5])
+    path = os.environ.get("B200_TEST_TMP", "/tmp") + "/dist_ckpt_case"
+    sd = {"a": D.shard_tensor(g1, mesh, [Shard(0)]), "b": D.shard_tensor(g2, mesh, [Replicate()])}
+    D.save_state_dict(sd, path)
+    tgt = {"a": D.shard_tensor(paddle.zeros([4 * w, 6 * w]), mesh, [Shard(1)]), "b": D.shard_tensor(paddle.zeros([5]), mesh, [Replicate()])}
+    D.load_state_dict(tgt, path)
+    close(tgt["a"]._local_value().numpy(), g1[:, r * 6:(r + 1) * 6].numpy())
+    close(tgt["b"]._local_value().numpy(), g2.numpy())
+
+
 def case_p2p_kernels():
     """Peer-memory collectives vs NCCL (GPU only)."""
     assert GPU
@@ -370,7 +478,7 @@ def case_p2p_kernels():
     full = xs.detach().float() @ wr.detach().float()
     torch.distributed.all_reduce(full)
     ref_rs = full.chunk(w, 0)[r]
-    assert yrs.shape == ref_rs.shape, (yrs.shape, ref_rs.shape)
+    assert list(yrs.shape) == list(ref_rs.shape), (yrs.shape, ref_rs.shape)
     e = ((yrs.float() - ref_rs).norm() / ref_rs.norm()).item()
     assert e < 2e-2, f"gemm_reduce_scatter fwd {e}"
     gy = (torch.randn_like(yrs) * 0.1)
