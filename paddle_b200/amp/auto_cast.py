@@ -16,7 +16,29 @@ WHITE_LIST = {"conv2d", "einsum", "matmul", "matmul_v2", "max_pool2d_with_index"
 BLACK_LIST = {"exp", "square", "log", "mean", "sum", "cos_sim", "softmax", "softmax_with_cross_entropy", "sigmoid_cross_entropy_with_logits",
               "c_softmax_with_cross_entropy", "cross_entropy", "cross_entropy2", "reduce_sum", "layer_norm", "batch_norm", "rms_norm"}
 
-_state = {"enabled": False, "level": "O0", "dtype": torch.float32}
+_state = {"enabled": False, "level": "O0", "dtype": torch.float32, "black": frozenset(), "white": frozenset()}
+
+
+def fp32_guard(op, *tensors):
+    """For white-list ops that the user moved to `custom_black_list`: returns (context, tensors cast to fp32) so the op runs
+    outside autocast; a no-op context and the tensors unchanged otherwise."""
+    if _state["enabled"] and op in _state["black"]:
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        return torch.autocast(device_type=dev, enabled=False), tuple(t.float() if isinstance(t, torch.Tensor) and t.is_floating_point() else t for t in tensors)
+    return contextlib.nullcontext(), tensors
+
+
+def black_dtype(op, x, dtype=None):
+    """Compute dtype for a black-list op under O1: fp32 for low-precision inputs unless the user white-listed the op."""
+    if dtype is None and _state["enabled"] and _state["level"] == "O1" and op in BLACK_LIST and op not in _state["white"] \
+            and x.dtype in (torch.float16, torch.bfloat16):
+        return torch.float32
+    return dtype
+
+
+def low_precision_forced(op):
+    """True for black-list ops the user moved to `custom_white_list` (they then run in the autocast dtype)."""
+    return _state["enabled"] and op in _state["white"]
 
 
 def white_list():
@@ -46,7 +68,8 @@ def auto_cast(enable=True, custom_white_list=None, custom_black_list=None, level
     d = _dt.convert_dtype(dtype)
     prev = dict(_state)
     active = enable and level != "O0"
-    _state.update(enabled=active, level=level if active else "O0", dtype=d if active else torch.float32)
+    _state.update(enabled=active, level=level if active else "O0", dtype=d if active else torch.float32,
+                  black=frozenset(custom_black_list or ()) if active else frozenset(), white=frozenset(custom_white_list or ()) if active else frozenset())
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     try:
         if active and level in ("O1", "OD"):

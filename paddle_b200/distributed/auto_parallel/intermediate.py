@@ -173,9 +173,7 @@ def parallelize(model, optimizer=None, mesh=None, config=None):
             model, optimizer, _ = group_sharded_parallel(model, optimizer, lvl, group=g)
         else:
             model = _DPModel(model, g)
-    if optimizer is not None and mp.get("parallelize_plan") and hasattr(optimizer, "_parameter_list") and not isinstance(optimizer._parameter_list[0], dict):
+    if optimizer is not None and mp.get("parallelize_plan") and len(getattr(optimizer, "_param_groups", ())) == 1:
         # sublayers were replaced: re-point the optimizer at the live parameters
-        live = list(model.parameters())
-        if len(live) == len(optimizer._parameter_list):
-            optimizer._parameter_list = live
+        optimizer._param_groups[0]["params"] = list(model.parameters())
     return (model, optimizer) if optimizer is not None else model

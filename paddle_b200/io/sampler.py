@@ -111,11 +111,17 @@ class DistributedBatchSampler(BatchSampler):
             rng.shuffle(idx)
             self.epoch += 1
         # rank r takes contiguous batch_size chunks strided by nranks (reference behaviour)
+        # whole rounds of `nranks` batches first; the tail round (total_size % step samples) is split evenly so every rank
+        # sees exactly num_samples indices
         mine = []
         step = self.batch_size * self.nranks
-        for i in range(self.local_rank * self.batch_size, len(idx) - (len(idx) % step if False else 0), step):
+        tail = self.total_size % step
+        for i in range(self.local_rank * self.batch_size, len(idx) - tail, step):
             mine.extend(idx[i:i + self.batch_size])
-        mine = mine[: self.num_samples] if len(mine) > self.num_samples else mine
+        if tail:
+            per = tail // self.nranks
+            rest = idx[len(idx) - tail:]
+            mine.extend(rest[self.local_rank * per:(self.local_rank + 1) * per])
         batch = []
         for i in mine:
             batch.append(i)

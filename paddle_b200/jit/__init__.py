@@ -175,8 +175,52 @@ def save(layer, path, input_spec=None, **configs):
         spec["pickled_layer"] = blob
     except Exception:
         spec["pickled_layer"] = None
+    if spec["pickled_layer"] is None and spec["input_spec"] and all(s is not None for s in spec["input_spec"]):
+        # classes that cannot be re-imported (defined in a function / __main__): store the traced forward as a static Program
+        try:
+            spec["program"] = pickle.dumps(_trace_program(layer, spec["input_spec"]))
+        except Exception:
+            spec["program"] = None
     with open(path + ".pdmodel", "wb") as f:
         pickle.dump(spec, f)
+
+
+def _trace_program(layer, input_spec):
+    from .. import static
+
+    prog = static.Program()
+    fwd = layer.__dict__.get("forward")
+    if isinstance(fwd, StaticFunction):
+        layer.__dict__.pop("forward", None)
+    try:
+        with static.program_guard(prog), torch.no_grad():
+            ins = [static.data(name or f"x{i}", shape, dtype.replace("paddle.", "").replace("torch.", "")) for i, (shape, dtype, name) in enumerate(input_spec)]
+            out = layer(*ins)
+    finally:
+        if isinstance(fwd, StaticFunction):
+            layer.forward = fwd
+    outs = list(out) if isinstance(out, (list, tuple)) else [out]
+    infer = prog.clone(for_test=True)
+    return {"program": infer, "feeds": [v.name for v in ins], "fetch_vids": [prog._fetch_alias[id(o)] for o in outs], "single": not isinstance(out, (list, tuple))}
+
+
+class _ProgramLayer(Layer):
+    """Runs a traced Program (jit.load of a model whose Python class is not importable)."""
+
+    def __init__(self, blob):
+        super().__init__()
+        from .. import static
+
+        self._blob = blob
+        self._exe = static.Executor()
+        prog = blob["program"]
+        prog._fetch_alias = {id(t): vid for vid, t in enumerate(prog._keep)}
+        self._fetch = [prog._keep[v] for v in blob["fetch_vids"]]
+
+    def forward(self, *args):
+        outs = self._exe.run(self._blob["program"], feed=dict(zip(self._blob["feeds"], args)), fetch_list=self._fetch, return_numpy=False)
+        outs = [o.as_subclass(Tensor) if isinstance(o, torch.Tensor) else o for o in outs]
+        return outs[0] if self._blob["single"] else outs
 
 
 class TranslatedLayer(Layer):
@@ -201,6 +245,10 @@ def load(path, **configs):
     layer = None
     if spec.get("pickled_layer"):
         layer = pickle.loads(spec["pickled_layer"])
+    elif spec.get("program"):
+        layer = _ProgramLayer(pickle.loads(spec["program"]))
+        layer.eval()
+        return layer
     else:
         mod = importlib.import_module(spec["module"])
         cls = mod

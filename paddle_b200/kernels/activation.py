@@ -2,6 +2,8 @@
 from __future__ import annotations
 
 import torch
+
+from ..framework.recording import recordable
 import torch.nn.functional as F
 
 from . import ext, raw, use_fused, wrap
@@ -22,6 +24,7 @@ class _SwiGLU(torch.autograd.Function):
         return dg, (du if u is not None else None)
 
 
+@recordable
 def swiglu(x, y=None):
     x, y = raw(x), raw(y)
     cols = x.shape[-1] if y is not None else x.shape[-1] // 2

@@ -7,6 +7,8 @@ from __future__ import annotations
 import math
 
 import torch
+
+from ..framework.recording import recordable
 import torch.nn.functional as F
 
 from . import raw, use_fused, wrap
@@ -26,6 +28,7 @@ def attention_ref(q, k, v, mask=None, dropout_p=0.0, causal=False, scale=None):
     return out.transpose(1, 2)
 
 
+@recordable
 def attention(q, k, v, mask=None, dropout_p=0.0, causal=False, scale=None):
     q, k, v, mask = raw(q), raw(k), raw(v), raw(mask)
     if causal and mask is not None:

@@ -8,6 +8,8 @@ from __future__ import annotations
 
 import torch
 
+from ..framework.recording import recordable
+
 from . import ext, raw, use_fused, wrap
 from ..framework.flags import flag
 
@@ -86,6 +88,7 @@ class _Linear(torch.autograd.Function):
         return dx, dw, db
 
 
+@recordable
 def linear(x, weight, bias=None):
     x, weight, bias = raw(x), raw(weight), raw(bias)
     if x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and weight.dim() == 2 and weight.dtype == x.dtype \
@@ -95,12 +98,17 @@ def linear(x, weight, bias=None):
         m = x.numel() // x.shape[-1]
         if m % 8 == 0:  # dW needs the token count 16B-aligned for the MN-major map
             return wrap(_Linear.apply(x, weight, bias))
-    y = torch.matmul(x, weight)
-    if bias is not None:
-        y = y + bias
-    return wrap(y)
+    from ..amp.auto_cast import fp32_guard
+
+    ctx, (x, weight, bias) = fp32_guard("linear", x, weight, bias)
+    with ctx:
+        if weight.dim() == 2:
+            return wrap(torch.nn.functional.linear(x, weight.t(), bias))   # one addmm; a single autocast unit like the reference's linear op
+        y = torch.matmul(x, weight)
+        return wrap(y if bias is None else y + bias)
 
 
+@recordable
 def matmul(x, y, transpose_x=False, transpose_y=False):
     """paddle.matmul fast path for 2-D / batched 3-D half-precision operands (no autograd wrapper: used by inference)."""
     x, y = raw(x), raw(y)

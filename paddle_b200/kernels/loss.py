@@ -2,6 +2,8 @@
 from __future__ import annotations
 
 import torch
+
+from ..framework.recording import recordable
 import torch.nn.functional as F
 
 from . import ext, raw, use_fused, wrap
@@ -23,6 +25,7 @@ class _SoftmaxCE(torch.autograd.Function):
         return ext().softmax_ce_bwd(lg, labels, lse, dloss.contiguous(), ctx.ignore_index, ctx.inplace), None, None, None
 
 
+@recordable
 def softmax_cross_entropy(logits, labels, ignore_index=-100, inplace_backward=False):
     """Per-row loss (fp32) for logits [N, V] and int labels [N]."""
     logits, labels = raw(logits), raw(labels)
@@ -77,5 +80,6 @@ class _VocabParallelCE(torch.autograd.Function):
         return g, None, None, None, None
 
 
+@recordable
 def vocab_parallel_cross_entropy(logits, labels, vocab_start, group, ignore_index=-100):
     return wrap(_VocabParallelCE.apply(raw(logits), raw(labels).long(), int(vocab_start), group, int(ignore_index)))

@@ -4,6 +4,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
+from ..framework.recording import recordable
 from . import ext, raw, use_fused, wrap
 
 _FUSED_DTYPES = (torch.float32, torch.float16, torch.bfloat16)
@@ -48,6 +49,7 @@ def rms_norm_ref(x, w, eps, bias=None):
     return y.to(x.dtype)
 
 
+@recordable
 def rms_norm(x, weight=None, eps=1e-6, bias=None, residual=None):
     """y = rmsnorm(x [+ residual]) * weight (+ bias).  With ``residual`` returns (y, x + residual)."""
     x, weight, bias, residual = raw(x), raw(weight), raw(bias), raw(residual)
@@ -83,6 +85,7 @@ class _LayerNorm(torch.autograd.Function):
         return dx, (dw if w is not None else None), (db if ctx.has_b else None), None
 
 
+@recordable
 def layer_norm(x, normalized_shape, weight=None, bias=None, eps=1e-5):
     x, weight, bias = raw(x), raw(weight), raw(bias)
     width = 1

@@ -3,6 +3,8 @@ from __future__ import annotations
 
 import torch
 
+from ..framework.recording import recordable
+
 from . import ext, raw, use_fused, wrap
 
 _table_cache = {}
@@ -75,6 +77,7 @@ class _RopePacked(torch.autograd.Function):
         return g, None, None, None, None, None, None, None, None
 
 
+@recordable
 def apply_rope_packed(qkv, cos_t, sin_t, rope_heads, total_heads, dim, position_ids=None, neox=True):
     """qkv: [B, S, total_heads*dim] (or [B,S,total_heads,dim]); rotates heads [0, rope_heads) in place."""
     q = raw(qkv)
@@ -91,6 +94,7 @@ def apply_rope_packed(qkv, cos_t, sin_t, rope_heads, total_heads, dim, position_
     return wrap(torch.cat([rot, x4[:, :, rope_heads:]], 2).reshape(q.shape))
 
 
+@recordable
 def apply_rope(x, cos_t, sin_t, position_ids=None, neox=True):
     """x: [B, S, H, D]; cos/sin fp32 [P, D/2]."""
     x = raw(x)

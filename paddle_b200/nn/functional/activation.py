@@ -144,7 +144,10 @@ def maxout(x, groups, axis=1, name=None):
 
 
 def softmax(x, axis=-1, dtype=None, name=None):
-    return F.softmax(T(x), dim=axis, dtype=_dt.convert_dtype(dtype))
+    from ...amp.auto_cast import black_dtype
+
+    x = T(x)
+    return F.softmax(x, dim=axis, dtype=black_dtype("softmax", x, _dt.convert_dtype(dtype)))
 
 
 def softmax_(x, axis=-1, dtype=None, name=None):
@@ -155,7 +158,10 @@ def softmax_(x, axis=-1, dtype=None, name=None):
 
 
 def log_softmax(x, axis=-1, dtype=None, name=None):
-    return F.log_softmax(T(x), dim=axis, dtype=_dt.convert_dtype(dtype))
+    from ...amp.auto_cast import black_dtype
+
+    x = T(x)
+    return F.log_softmax(x, dim=axis, dtype=black_dtype("softmax", x, _dt.convert_dtype(dtype)))
 
 
 def gumbel_softmax(x, temperature=1.0, hard=False, axis=-1, name=None):

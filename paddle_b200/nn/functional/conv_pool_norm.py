@@ -84,7 +84,11 @@ def _conv(n, x, weight, bias, stride, padding, dilation, groups, data_format):
     stride, dilation = _tup(stride, n), _tup(dilation, n)
     x, pad = _conv_padding(x, padding, n, w.shape[2:], stride, dilation)
     fn = (F.conv1d, F.conv2d, F.conv3d)[n - 1]
-    out = fn(x, w, None if bias is None else T(bias), stride, pad, dilation, groups)
+    from ...amp.auto_cast import fp32_guard
+
+    ctx, (x, w, bias) = fp32_guard(f"conv{n}d", x, w, None if bias is None else T(bias))
+    with ctx:
+        out = fn(x, w, bias, stride, pad, dilation, groups)
     return _from_cf(out, cl)
 
 

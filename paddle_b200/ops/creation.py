@@ -34,7 +34,7 @@ def full(shape, fill_value, dtype=None, name=None):
             d = torch.bool
         elif isinstance(fill_value, int):
             d = torch.int64
-        elif isinstance(fill_value, complex):
+        elif isinstance(fill_value, type(1j)):   # `complex` is shadowed by paddle.complex below
             d = torch.complex64
         else:
             d = _dt.default_dtype()

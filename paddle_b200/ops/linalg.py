@@ -13,6 +13,12 @@ def matmul(x, y, transpose_x=False, transpose_y=False, name=None):
         x = torch.transpose(x, -1, -2)
     if transpose_y and y.dim() >= 2:
         y = torch.transpose(y, -1, -2)
+    from ..amp.auto_cast import _state, fp32_guard
+
+    if _state["enabled"]:
+        ctx, (x, y) = fp32_guard("matmul", x, y)
+        with ctx:
+            return torch.matmul(x, y)
     return torch.matmul(x, y)
 
 

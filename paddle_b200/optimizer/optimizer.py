@@ -30,7 +30,11 @@ class Optimizer:
 
     def __init__(self, learning_rate=0.001, parameters=None, weight_decay=None, grad_clip=None, name=None, multi_precision=False):
         if parameters is None:
-            raise ValueError("parameters must be given in dygraph mode")
+            from .. import static
+
+            if not static.in_static_mode():
+                raise ValueError("parameters must be given in dygraph mode")
+            parameters = []   # static mode: collected from the program by minimize()
         parameters = list(parameters)
         self._param_groups = []
         if parameters and isinstance(parameters[0], dict):
@@ -196,6 +200,10 @@ class Optimizer:
         prog = static._recording[0]
         if prog is not None and (id(loss) in prog._vids):
             # static graph: defer backward+update to Executor.run (python/paddle/optimizer/optimizer.py:minimize appends ops)
+            if parameters is not None:
+                self._param_groups[0]["params"] = list(parameters)
+            elif not self._parameter_list:
+                self._param_groups[0]["params"] = [p for p in prog.all_parameters() if p.requires_grad]
             static._minimize_node(self, loss, prog)
             return None, None
         loss.backward()

@@ -10,7 +10,9 @@ from . import nn  # noqa: F401
 
 
 def _raw(t):
-    return t.as_subclass(torch.Tensor) if isinstance(t, torch.Tensor) and type(t) is not torch.Tensor else torch.as_tensor(np.asarray(t))
+    if isinstance(t, torch.Tensor):
+        return t.as_subclass(torch.Tensor) if type(t) is not torch.Tensor else t
+    return torch.as_tensor(np.asarray(t))
 
 
 def _w(t):

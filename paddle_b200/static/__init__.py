@@ -172,7 +172,7 @@ class Program:
 
 _main = [Program()]
 _startup = [Program()]
-_recording = [None]
+from ..framework.recording import current as _recording  # noqa: E402  (shared with the kernel wrappers' @recordable)
 
 
 def default_main_program():
@@ -499,6 +499,7 @@ def load_inference_model(path_prefix, executor, **kwargs):
     with open(path_prefix + ".pdmodel", "rb") as f:
         blob = pickle.load(f)
     prog = blob["program"]
+    prog._fetch_alias = {id(t): vid for vid, t in enumerate(prog._keep)}   # object ids changed across the pickle round trip
     fetch = [prog._keep[v] for v in blob["fetch_vids"]]
     return prog, blob["feeds"], fetch
 

@@ -20,6 +20,7 @@ ap.add_argument("--seq", type=int, default=4096)
 ap.add_argument("--batch", type=int, default=2)
 ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--no-fused", action="store_true")
+ap.add_argument("--accumulate", type=int, default=1)
 args = ap.parse_args()
 
 lr_ = int(os.environ.get("LOCAL_RANK", "0"))
@@ -53,20 +54,39 @@ bad = []
 def hook(name):
     def f(layer, inp, out):
         o = out[0] if isinstance(out, (tuple, list)) else out
+        if isinstance(o, torch.Tensor) and o.is_floating_point() and name.count(".") <= 2 and len(arms) < 60:
+            arms.append((name, float(o.as_subclass(torch.Tensor).float().pow(2).mean().sqrt())))
         if isinstance(o, torch.Tensor) and o.is_floating_point() and not bad:
             if not bool(torch.isfinite(o.as_subclass(torch.Tensor)).all()):
                 bad.append(name)
                 print(f"[rank {rank}] NON-FINITE activation after {name} shape={list(o.shape)}", flush=True)
+        if isinstance(o, torch.Tensor) and o.requires_grad:
+            def gh(g, name=name):
+                gr = g.as_subclass(torch.Tensor)
+                if len(gbad) < 3 and not bool(torch.isfinite(gr).all()):
+                    gbad.append(name)
+                    print(f"[rank {rank}] NON-FINITE grad flowing into output of {name} shape={list(g.shape)} "
+                          f"nan={int(torch.isnan(gr).sum())} inf={int(torch.isinf(gr).sum())}", flush=True)
+                elif len(gbad) == 0 and name.count(".") <= 2:
+                    gmax[name] = float(gr.abs().max())
+            o.register_hook(gh)
     return f
+
+
+gbad, gmax, arms = [], {}, []
 
 
 for n, sub in inner.named_sublayers():
     sub.register_forward_post_hook(hook(n))
 
 for step in range(args.steps):
-    tok = torch.randint(0, cfg.vocab_size, (args.batch, args.seq + 1), device="cuda").as_subclass(paddle.Tensor)
-    loss = model(tok[:, :-1], tok[:, 1:])
-    loss.backward()
+    for mb in range(args.accumulate):
+        tok = torch.randint(0, cfg.vocab_size, (args.batch, args.seq + 1), device="cuda").as_subclass(paddle.Tensor)
+        loss = model(tok[:, :-1], tok[:, 1:]) / args.accumulate
+        loss.backward()
+    if step == 0 and rank == 0:
+        print("activation rms in forward order:", [(k, f"{v:.3g}") for k, v in arms[:20]], flush=True)
+        print("grad |max| in backward order:", [(k, f"{v:.3g}") for k, v in list(gmax.items())[:14]], flush=True)
     nbad = 0
     for p in inner.parameters():
         g = p.grad

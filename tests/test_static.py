@@ -1,0 +1,96 @@
+"""Static-graph mode: Program recording, Executor replay, training through minimize, passes, inference model IO.
+Parity: test/legacy_test/test_executor_*.py, test_program.py, test/ir/pir/*pass*."""
+import numpy as np
+import pytest
+
+import paddle_b200 as paddle
+from paddle_b200 import static
+
+
+@pytest.fixture(autouse=True)
+def _static_mode():
+    paddle.enable_static()
+    yield
+    paddle.disable_static()
+
+
+def test_program_record_and_run():
+    main, start = static.Program(), static.Program()
+    with static.program_guard(main, start):
+        x = static.data("x", [-1, 4], "float32")
+        y = paddle.tanh(x * 2.0 + 1.0).sum(axis=1)
+    exe = static.Executor()
+    exe.run(start)
+    for bs in (2, 5):
+        a = np.random.rand(bs, 4).astype("float32")
+        out, = exe.run(main, feed={"x": a}, fetch_list=[y])
+        np.testing.assert_allclose(out, np.tanh(a * 2 + 1).sum(1), rtol=1e-5)
+
+
+def test_static_training_converges():
+    paddle.seed(0)
+    main, start = static.Program(), static.Program()
+    with static.program_guard(main, start):
+        x = static.data("x", [-1, 3], "float32")
+        t = static.data("t", [-1, 1], "float32")
+        h = static.nn.fc(x, 8, activation="tanh")
+        pred = static.nn.fc(h, 1)
+        loss = paddle.nn.functional.mse_loss(pred, t)
+        paddle.optimizer.Adam(0.05).minimize(loss)
+    exe = static.Executor()
+    exe.run(start)
+    rng = np.random.RandomState(0)
+    X = rng.rand(64, 3).astype("float32")
+    T = (X @ np.array([[1.0], [-2.0], [0.5]], dtype="float32"))
+    losses = [float(exe.run(main, feed={"x": X, "t": T}, fetch_list=[loss])[0]) for _ in range(60)]
+    assert losses[-1] < losses[0] * 0.2
+    test_prog = main.clone(for_test=True)
+    l1 = float(exe.run(test_prog, feed={"x": X, "t": T}, fetch_list=[loss])[0])
+    l2 = float(exe.run(test_prog, feed={"x": X, "t": T}, fetch_list=[loss])[0])
+    assert abs(l1 - l2) < 1e-7   # no update in the test clone
+
+
+def test_passes():
+    from paddle_b200.static import passes
+
+    main = static.Program()
+    w = paddle.to_tensor(np.random.rand(4, 6).astype("float32"))
+    b = paddle.to_tensor(np.random.rand(6).astype("float32"))
+    with static.program_guard(main):
+        x = static.data("x", [-1, 4], "float32")
+        c = paddle.ones([6]) * 3.0 + 1.0          # constant sub-graph
+        y1 = paddle.matmul(x, w) + b               # gemm + bias
+        e1 = paddle.exp(x)
+        e2 = paddle.exp(x)                         # CSE
+        dead = paddle.sin(x) * 2.0                 # unused
+        out = y1 * c + (e1 + e2).sum(axis=1, keepdim=True)
+    n0 = len(main.nodes)
+    a = np.random.rand(3, 4).astype("float32")
+    exe = static.Executor()
+    ref, = exe.run(main, feed={"x": a}, fetch_list=[out])
+    keep = {main._fetch_alias[id(out)]}
+    pm = passes.PassManager()
+    pm.apply(main, keep)
+    assert pm.stats["dead_code_elimination"] >= 2 and pm.stats["common_subexpression_elimination"] >= 1
+    # constants built from literals never enter the tape (they are evaluated while recording), so nothing is left to fold here
+    assert pm.stats["constant_folding"] == 0 and pm.stats["fuse_gemm_epilogue"] == 1
+    assert len(main.nodes) < n0
+    got, = exe.run(main, feed={"x": a}, fetch_list=[out])
+    np.testing.assert_allclose(got, ref, rtol=1e-5)
+    np.testing.assert_allclose(ref, (a @ w.numpy() + b.numpy()) * 4.0 + 2 * np.exp(a).sum(1, keepdims=True), rtol=1e-5)
+
+
+def test_save_load_inference_model(tmp_path):
+    paddle.seed(1)
+    main, start = static.Program(), static.Program()
+    with static.program_guard(main, start):
+        x = static.data("x", [-1, 5], "float32")
+        y = static.nn.fc(x, 3, activation="relu")
+    exe = static.Executor()
+    exe.run(start)
+    a = np.random.rand(2, 5).astype("float32")
+    ref, = exe.run(main, feed={"x": a}, fetch_list=[y])
+    static.save_inference_model(str(tmp_path / "m"), [x], [y], exe, program=main)
+    prog, feeds, fetches = static.load_inference_model(str(tmp_path / "m"), exe)
+    got, = exe.run(prog, feed={feeds[0]: a}, fetch_list=fetches)
+    np.testing.assert_allclose(got, ref, rtol=1e-6)
