@@ -157,7 +157,10 @@ def main():
     vocab, seq = cfg.vocab_size, args.seq
     steps_total = args.warmup + args.steps
     # synthetic token stream in pinned host memory (one fresh batch per step: e2e copies it H2D every step)
-    host = torch.randint(0, vocab, (steps_total * 2 + 2, seqs_per_replica, seq + 1), dtype=torch.int64).pin_memory()
+    # every rank of one model replica (its mp and pp group) must see the same tokens: the stream is seeded by the dp index only
+    dp_rank = fleet.get_hybrid_communicate_group().get_data_parallel_rank() if n > 1 else 0
+    gen = torch.Generator().manual_seed(4321 + dp_rank)
+    host = torch.randint(0, vocab, (steps_total * 2 + 2, seqs_per_replica, seq + 1), dtype=torch.int64, generator=gen).pin_memory()
     h2d_bytes = seqs_per_replica * (seq + 1) * 8
     dev_batches = [host[i].cuda(non_blocking=True) for i in range(2)]
 

@@ -1,0 +1,450 @@
+// Flash-attention forward for sm_100a (head_dim 128, bf16/fp16): S = Q K^T and O += P V run on tcgen05 tensor cores with
+// the S tiles double-buffered in TMEM, K/V tiles streamed by TMA (4-D maps straight over the strided [B,S,H,D] views of a
+// packed QKV tensor, so no q/k/v split copies), online softmax in registers (one thread = one query row = one TMEM lane),
+// lazy O rescaling in TMEM.  Hand-written PTX; no CUTLASS, no library attention.
+//
+// Parity (behaviour): paddle.nn.functional.flash_attention / scaled_dot_product_attention
+// (python/paddle/nn/functional/flash_attention.py -> phi flash_attn kernels calling the flash-attention library).
+//
+// CTA = 128 query rows of one (batch, head).  Warps 0-3: softmax + epilogue, warp 4: TMA producer, warp 5: TMEM alloc + MMA issuer.
+// TMEM columns: [0,128) S buffer 0, [128,256) S buffer 1, [256,384) O accumulator.
+#include <cuda.h>
+#include <cstdio>
+#include <string>
+
+#include "include/b200_common.cuh"
+#include "include/b200_ops.h"
+
+namespace b200 {
+namespace attn {
+
+constexpr int BM = 128, BN = 128, HD = 128;
+constexpr int kThreads = 192;
+constexpr uint32_t TILE_BYTES = 128 * 128 * 2;   // 32 KB: every operand tile (Q, K, V, P)
+constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;  // one 64-wide K-block of a tile
+constexpr uint32_t SMEM_BYTES = 6 * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t O_COL = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t gtimer() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  uint64_t t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins == 2048) t0 = gtimer();
+    if (spins > 2048 && (spins & 1023) == 0 && gtimer() - t0 > 4000000000ull) {  // protocol bug: trap, never hang the GPU
+      printf("b200 attention: mbarrier timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {   // SWIZZLE_128B smem descriptor
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n\t"
+      "tcgen05.wait::st.sync.aligned;"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct Params {
+  int b, sq, sk, h, hk;
+  float scale_log2;
+  int causal, causal_off;     // key j is visible to query i iff j <= i + causal_off
+  void* o;
+  float* lse;
+  int64_t o_sb, o_ss, o_sh;   // element strides of the output [B,S,H,D]
+  int dtype;
+  uint32_t idesc_qk, idesc_pv;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+           const __grid_constant__ CUtensorMap map_v, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base, sP = base + 5 * TILE_BYTES;
+  auto sK = [&](int s) { return base + (1 + s) * TILE_BYTES; };
+  auto sV = [&](int s) { return base + (3 + s) * TILE_BYTES; };
+  const uint32_t bars = base + 6 * TILE_BYTES;
+  const uint32_t q_full = bars, p_full = bars + 8 * 13, pv_done = bars + 8 * 14;
+  auto k_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto v_full = [&](int s) { return bars + 8u * (3 + s); };
+  auto k_empty = [&](int s) { return bars + 8u * (5 + s); };
+  auto v_empty = [&](int s) { return bars + 8u * (7 + s); };
+  auto s_full = [&](int s) { return bars + 8u * (9 + s); };
+  auto s_empty = [&](int s) { return bars + 8u * (11 + s); };
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + 6 * TILE_BYTES + 8 * 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = (int)gridDim.x - 1 - (int)blockIdx.x;   // long (late) rows first under the causal mask
+  const int head = blockIdx.y, batch = blockIdx.z;
+  const int kv_head = head / (p.h / p.hk);
+  const int m0 = m_tile * BM;
+  int n_tiles = (p.sk + BN - 1) / BN;
+  if (p.causal) {
+    const int last_key = min(p.sk - 1, m0 + BM - 1 + p.causal_off);
+    n_tiles = last_key < 0 ? 0 : min(n_tiles, last_key / BN + 1);
+  }
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full(s), 1); mbar_init(v_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_empty(s), 1);
+      mbar_init(s_full(s), 1); mbar_init(s_empty(s), 4);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  } else if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 4) {
+    if (lane == 0 && n_tiles > 0) {
+      // ================= TMA producer =================
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_4d(sQ, &map_q, q_full, 0, m0, head, batch);
+      tma_load_4d(sQ + HALF_BYTES, &map_q, q_full, 64, m0, head, batch);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1, n0 = j * BN;
+        const uint32_t ph = ((j >> 1) & 1) ^ 1;
+        mbar_wait(k_empty(s), ph);
+        mbar_expect_tx(k_full(s), TILE_BYTES);
+        tma_load_4d(sK(s), &map_k, k_full(s), 0, n0, kv_head, batch);               // box {64 d, 128 keys}: K-major B operand
+        tma_load_4d(sK(s) + HALF_BYTES, &map_k, k_full(s), 64, n0, kv_head, batch);
+        mbar_wait(v_empty(s), ph);
+        mbar_expect_tx(v_full(s), TILE_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)                                              // box {64 d, 64 keys}: MN-major B operand
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            tma_load_4d(sV(s) + kb * HALF_BYTES + i * 8192, &map_v, v_full(s), i * 64, n0 + kb * 64, kv_head, batch);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && n_tiles > 0) {
+      // ================= MMA issuer =================
+      mbar_wait(q_full, 0);
+      auto issue_qk = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(k_full(s), (j >> 1) & 1);
+        mbar_wait(s_empty(s), ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + s * BN, make_desc(sQ + kb * HALF_BYTES + k * 32, 16, 1024),
+                     make_desc(sK(s) + kb * HALF_BYTES + k * 32, 16, 1024), p.idesc_qk, (kb | k) != 0);
+        umma_commit(s_full(s));
+        umma_commit(k_empty(s));
+      };
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_qk(j + 1);     // S(j+1) is computed while the softmax warps work on S(j)
+        const int s = j & 1;
+        mbar_wait(p_full, j & 1);
+        mbar_wait(v_full(s), (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + O_COL, make_desc(sP + kb * HALF_BYTES + k * 32, 16, 1024),
+                     make_desc(sV(s) + kb * HALF_BYTES + k * 2048, 8192, 1024), p.idesc_pv, (j | kb | k) != 0);
+        umma_commit(pv_done);
+        umma_commit(v_empty(s));
+      }
+    }
+  } else {
+    // ================= softmax + epilogue (thread == query row == TMEM lane) =================
+    const int tid = threadIdx.x;
+    const int row = m0 + tid;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    float m_i = -INFINITY, l_i = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int sb = j & 1, n0 = j * BN;
+      mbar_wait(s_full(sb), (j >> 1) & 1);
+      tc_fence_after();
+      float s[BN];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_off + sb * BN + c * 32, r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(r[i]) * p.scale_log2;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty(sb));      // QK(j+2) may overwrite this S buffer
+      const bool edge = (n0 + BN > p.sk) || (p.causal && n0 + BN - 1 > m0 + p.causal_off);
+      if (edge) {
+        const int lim = p.causal ? min(p.sk - 1, row + p.causal_off) : p.sk - 1;   // last visible key
+#pragma unroll
+        for (int i = 0; i < BN; ++i)
+          if (n0 + i > lim) s[i] = -INFINITY;
+      }
+      float mx = s[0];
+#pragma unroll
+      for (int i = 1; i < BN; ++i) mx = fmaxf(mx, s[i]);
+      float m_new = fmaxf(m_i, mx);
+      if (m_new == -INFINITY) m_new = 0.f;          // fully masked so far: keep exp2 finite
+      if (j == 0) {
+        m_i = m_new;
+      } else {
+        mbar_wait(pv_done, (j - 1) & 1);            // O(j-1) final in TMEM, P buffer free
+        tc_fence_after();
+        const bool need = (m_new - m_i) > 8.f;      // lazy rescale: keep a stale max while exp2 stays <= 2^8
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? ex2(m_i - m_new) : 1.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + lane_off + O_COL + c * 32, r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st32(tmem_base + lane_off + O_COL + c * 32, r);
+          }
+          l_i *= alpha;
+          if (need) m_i = m_new;
+        }
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          Vec16<T> pk;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float pv = ex2(s[kb * 64 + c * 8 + e] - m_i);
+            sum += pv;
+            pk.v[e] = from_f<T>(pv);
+          }
+          // K-major SWIZZLE_128B: row r at r*128 B, 16-byte chunk index XOR (r % 8)
+          const uint32_t addr = sP + kb * HALF_BYTES + tid * 128 + ((c ^ (tid & 7)) << 4);
+          const uint4 u = *reinterpret_cast<const uint4*>(&pk);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+        }
+      }
+      l_i += sum;
+      fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    if (n_tiles > 0) {
+      mbar_wait(pv_done, (n_tiles - 1) & 1);
+      tc_fence_after();
+    }
+    const float inv = l_i > 0.f ? 1.f / l_i : 0.f;
+    T* orow = reinterpret_cast<T*>(p.o) + (int64_t)batch * p.o_sb + (int64_t)row * p.o_ss + (int64_t)head * p.o_sh;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      if (n_tiles > 0) {
+        tmem_ld32(tmem_base + lane_off + O_COL + c * 32, r);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      }
+      if (row < p.sq) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          Vec16<T> o;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o.v[e] = from_f<T>(__uint_as_float(r[q * 8 + e]) * inv);
+          st16(orow + c * 32 + q * 8, o);
+        }
+      }
+    }
+    if (row < p.sq && p.lse) p.lse[((int64_t)batch * p.h + head) * p.sq + row] = l_i > 0.f ? (m_i + log2f(l_i)) * 0.69314718055994531f : -INFINITY;
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 4-D map {d, s, h, b} over a strided [B,S,H,D] view (strides in elements), box {64, rows, 1, 1}, 128B swizzle
+static bool make_map4(CUtensorMap* out, const void* ptr, int d, int s, int h, int b, int64_t ss, int64_t sh, int64_t sb, uint32_t box_rows, int dtype) {
+  cudaFree(nullptr);
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable"); return false; }
+  cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)s, (cuuint64_t)h, (cuuint64_t)b};
+  cuuint64_t strides[3] = {(cuuint64_t)ss * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
+  cuuint32_t box[4] = {64, box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error(__FILE__, __LINE__, ("cuTensorMapEncodeTiled (attention) failed: " + std::to_string((int)r)).c_str());
+    return false;
+  }
+  return true;
+}
+
+static uint32_t make_idesc(int dtype, int n, bool b_mn) {
+  uint32_t d = 0;
+  d |= 1u << 4;                                  // fp32 accumulate
+  const uint32_t f = dtype == kBF16 ? 1u : 0u;
+  d |= f << 7;
+  d |= f << 10;
+  d |= (b_mn ? 1u : 0u) << 16;                   // B operand MN-major (V: head_dim contiguous)
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(BM >> 4) << 24;
+  return d;
+}
+
+}  // namespace attn
+
+int attention_fwd_supported(const AttnArgs& a) {
+  if (a.d != 128 || (a.dtype != kBF16 && a.dtype != kF16)) return 0;
+  if (a.h % a.hk) return 0;
+  const int64_t* st[3] = {a.q_strides, a.k_strides, a.v_strides};
+  for (auto s : st)
+    for (int i = 0; i < 3; ++i)
+      if (s[i] % 8) return 0;                    // TMA strides: multiples of 16 bytes
+  if ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v) | reinterpret_cast<uintptr_t>(a.o)) & 15) return 0;
+  if (a.o_strides[0] % 8 || a.o_strides[1] % 8 || a.o_strides[2] % 8) return 0;
+  return 1;
+}
+
+int attention_fwd(const AttnArgs& a, cudaStream_t s) {
+  using namespace attn;
+  if (!attention_fwd_supported(a)) return 1;
+  CUtensorMap mq, mk, mv;
+  // strides arrays are (batch, seq, head)
+  if (!make_map4(&mq, a.q, a.d, a.sq, a.h, a.b, a.q_strides[1], a.q_strides[2], a.q_strides[0], BM, a.dtype)) return 2;
+  if (!make_map4(&mk, a.k, a.d, a.sk, a.hk, a.b, a.k_strides[1], a.k_strides[2], a.k_strides[0], BN, a.dtype)) return 2;
+  if (!make_map4(&mv, a.v, a.d, a.sk, a.hk, a.b, a.v_strides[1], a.v_strides[2], a.v_strides[0], 64, a.dtype)) return 2;
+  Params p;
+  p.b = a.b; p.sq = a.sq; p.sk = a.sk; p.h = a.h; p.hk = a.hk;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.causal = a.causal; p.causal_off = a.sk - a.sq;
+  p.o = a.o; p.lse = a.lse;
+  p.o_sb = a.o_strides[0]; p.o_ss = a.o_strides[1]; p.o_sh = a.o_strides[2];
+  p.dtype = a.dtype;
+  p.idesc_qk = make_idesc(a.dtype, BN, false);
+  p.idesc_pv = make_idesc(a.dtype, HD, true);
+  dim3 grid((a.sq + BM - 1) / BM, a.h, a.b);
+  static bool attr_bf = false, attr_h = false;
+  if (a.dtype == kBF16) {
+    auto kern = fwd_kernel<__nv_bfloat16>;
+    if (!attr_bf) { B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_bf = true; }
+    kern<<<grid, kThreads, SMEM_BYTES, s>>>(mq, mk, mv, p);
+  } else {
+    auto kern = fwd_kernel<__half>;
+    if (!attr_h) { B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_h = true; }
+    kern<<<grid, kThreads, SMEM_BYTES, s>>>(mq, mk, mv, p);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return 3; }
+  return 0;
+}
+
+}  // namespace b200

@@ -343,7 +343,7 @@ bool gemm_supported(const Tensor& a, const Tensor& b, bool a_is_km, bool b_is_nk
 }
 
 Tensor gemm(const Tensor& a, const Tensor& b, const OptT& bias, bool a_is_km, bool b_is_nk, int64_t epilogue, const OptT& out,
-            const std::optional<at::ScalarType>& out_dtype) {
+            const std::optional<at::ScalarType>& out_dtype, const std::vector<int64_t>& rs_dst, int64_t rs_rows) {
   TORCH_CHECK(gemm_supported(a, b, a_is_km, b_is_nk), "paddle_b200.gemm: unsupported operands for the tcgen05 path");
   c10::cuda::CUDAGuard guard(a.device());
   b200::GemmArgs g;
@@ -369,6 +369,13 @@ Tensor gemm(const Tensor& a, const Tensor& b, const OptT& bias, bool a_is_km, bo
   g.stride_a = a.dim() == 3 ? a.stride(0) : 0;
   g.stride_b = b.dim() == 3 ? b.stride(0) : 0;
   g.stride_d = d.dim() == 3 ? d.stride(0) : 0;
+  if (!rs_dst.empty()) {   // fused reduce-scatter: rows are pushed into the owners' staging slots, `d` is not written
+    TORCH_CHECK(g.batch == 1 && rs_dst.size() <= 8 && rs_rows > 0 && (int64_t)g.m == rs_rows * (int64_t)rs_dst.size() && g.n % 8 == 0,
+                "gemm: bad reduce-scatter push arguments");
+    g.rs_world = (int)rs_dst.size();
+    g.rs_rows = (int)rs_rows;
+    for (size_t i = 0; i < rs_dst.size(); ++i) g.rs_dst[i] = reinterpret_cast<void*>(rs_dst[i]);
+  }
   if (g.bias) TORCH_CHECK(bias->scalar_type() == a.scalar_type() || bias->scalar_type() == at::kFloat, "gemm: bias dtype");
   if (g.bias && bias->scalar_type() == at::kFloat && a.scalar_type() != at::kFloat) {
     // epilogue reads bias in the input dtype
@@ -385,6 +392,44 @@ Tensor gemm(const Tensor& a, const Tensor& b, const OptT& bias, bool a_is_km, bo
   check_err();
   TORCH_CHECK(rc == 0, "paddle_b200.gemm launch failed rc=", rc);
   return d;
+}
+
+static bool fill_attn(b200::AttnArgs& a, const Tensor& q, const Tensor& k, const Tensor& v, double scale, bool causal) {
+  if (q.dim() != 4 || k.dim() != 4 || v.dim() != 4) return false;
+  if (q.stride(3) != 1 || k.stride(3) != 1 || v.stride(3) != 1) return false;
+  if (q.scalar_type() != k.scalar_type() || q.scalar_type() != v.scalar_type()) return false;
+  if (q.scalar_type() != at::kBFloat16 && q.scalar_type() != at::kHalf) return false;
+  a.q = q.data_ptr(); a.k = k.data_ptr(); a.v = v.data_ptr();
+  a.b = (int)q.size(0); a.sq = (int)q.size(1); a.h = (int)q.size(2); a.d = (int)q.size(3);
+  a.sk = (int)k.size(1); a.hk = (int)k.size(2);
+  if (k.size(0) != q.size(0) || v.size(0) != q.size(0) || v.size(1) != k.size(1) || v.size(2) != k.size(2) || k.size(3) != q.size(3) || v.size(3) != q.size(3)) return false;
+  for (int i = 0; i < 3; ++i) { a.q_strides[i] = q.stride(i); a.k_strides[i] = k.stride(i); a.v_strides[i] = v.stride(i); }
+  a.scale = (float)scale; a.causal = causal ? 1 : 0; a.dtype = dt_code(q);
+  a.o = nullptr; a.lse = nullptr;
+  a.o_strides[0] = (int64_t)a.sq * a.h * a.d; a.o_strides[1] = (int64_t)a.h * a.d; a.o_strides[2] = a.d;
+  return true;
+}
+
+bool attention_supported(const Tensor& q, const Tensor& k, const Tensor& v) {
+  b200::AttnArgs a;
+  if (!q.is_cuda() || !fill_attn(a, q, k, v, 1.0, false)) return false;
+  a.o = const_cast<void*>(a.q);   // alignment probe only
+  return b200::attention_fwd_supported(a) != 0;
+}
+
+// q [B,Sq,H,D], k/v [B,Sk,Hk,D] (strided views allowed) -> (out [B,Sq,H,D] contiguous, lse fp32 [B,H,Sq])
+std::vector<Tensor> attention_fwd(const Tensor& q, const Tensor& k, const Tensor& v, double scale, bool causal) {
+  c10::cuda::CUDAGuard guard(q.device());
+  b200::AttnArgs a;
+  TORCH_CHECK(fill_attn(a, q, k, v, scale, causal), "paddle_b200.attention_fwd: unsupported operands");
+  Tensor out = torch::empty({a.b, a.sq, a.h, a.d}, q.options());
+  Tensor lse = torch::empty({a.b, a.h, a.sq}, q.options().dtype(at::kFloat));
+  a.o = out.data_ptr(); a.lse = lse.data_ptr<float>();
+  int rc = b200::attention_fwd(a, cur_stream());
+  g_launches += 1;
+  check_err();
+  TORCH_CHECK(rc == 0, "paddle_b200.attention_fwd launch failed rc=", rc);
+  return {out, lse};
 }
 
 int64_t launch_count() { return g_launches.load(); }
@@ -413,7 +458,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("sgd_step", &sgd_step);
   m.def("lamb_step", &lamb_step);
   m.def("gemm_supported", &gemm_supported);
-  m.def("gemm", &gemm);
+  m.def("gemm", &gemm, pybind11::arg("a"), pybind11::arg("b"), pybind11::arg("bias") = pybind11::none(), pybind11::arg("a_is_km") = false,
+        pybind11::arg("b_is_nk") = false, pybind11::arg("epilogue") = 0, pybind11::arg("out") = pybind11::none(),
+        pybind11::arg("out_dtype") = pybind11::none(), pybind11::arg("rs_dst") = std::vector<int64_t>(), pybind11::arg("rs_rows") = 0);
+  m.def("attention_supported", &attention_supported);
+  m.def("attention_fwd", &attention_fwd);
   m.def("launch_count", &launch_count);
   m.def("reset_launch_count", &reset_launch_count);
   m.def("add_launches", &add_launches);

@@ -161,6 +161,46 @@ __global__ void __launch_bounds__(kThreads) reduce_scatter_kernel(Peers P, int64
   }
 }
 
+// ---------------------------------------------------------------------------------------------- reduce of pushed slots
+// Tail of the fused GEMM -> reduce-scatter: every rank's GEMM epilogue has stored its partial rows for rank r into slot
+// [src] of r's staging area (world slots of n elements at `off`).  Here rank r waits until all pushes have landed and
+// sums its slots from LOCAL HBM (the NVLink traffic already happened, tile by tile, under the GEMM main loop).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) reduce_slots_kernel(Peers P, int64_t off, T* __restrict__ out, int64_t n, int rank,
+                                                                int world, uint32_t epoch, uint32_t* counter) {
+  constexpr int N = Vec16<T>::N;
+  if (blockIdx.x == 0) {
+    __threadfence_system();
+    signal_all(P, rank, world, 0, epoch);   // stream order: my GEMM (and its pushes) completed before this kernel started
+  }
+  wait_all(P, rank, world, 0, epoch);
+  const T* base = reinterpret_cast<const T*>(P.base[rank] + off);
+  const int64_t nvec = n / N;
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    Vec16<T> in[kMaxRanks];
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r)
+      if (r < world) in[r] = ld16(base + (int64_t)r * n + v * N);
+    float acc[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r)
+      if (r < world) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) acc[j] += to_f(in[r].v[j]);
+      }
+    Vec16<T> o;
+#pragma unroll
+    for (int j = 0; j < N; ++j) o.v[j] = from_f<T>(acc[j]);
+    st16_stream(out + v * N, o);
+  }
+  if (last_cta(counter)) {                  // peers may push the next GEMM into my slots only after I have read them
+    signal_all(P, rank, world, 1, epoch);
+    wait_all(P, rank, world, 1, epoch);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- all-gather (pull)
 // every rank has its shard at [rank*chunk, (rank+1)*chunk) of the buffer at `off`; pull the other shards from their owners.
 __global__ void __launch_bounds__(kThreads) allgather_kernel(Peers P, int64_t off, int64_t chunk_bytes, int rank, int world,
@@ -231,6 +271,18 @@ void p2p_reduce_scatter(const int64_t* bases, int64_t off, void* out, int64_t n,
     constexpr int N = Vec16<T>::N;
     if (n % world || (n / world) % N) { set_last_error(__FILE__, __LINE__, "p2p_reduce_scatter: n/world must be a multiple of the 16B vector"); return; }
     reduce_scatter_kernel<T><<<comm_grid(n / world / N), kThreads, 0, s>>>(P, off, (T*)out, n, rank, world, epoch, counter);
+  });
+  B200_CUDA_CHECK(cudaGetLastError());
+}
+
+void p2p_reduce_slots(const int64_t* bases, int64_t off, void* out, int64_t n, int dtype, int rank, int world, uint32_t epoch,
+                      uint32_t* counter, cudaStream_t s) {
+  if (world > kMaxRanks) { set_last_error(__FILE__, __LINE__, "p2p collectives support up to 8 ranks"); return; }
+  Peers P = make_peers(bases, world);
+  B200_DISPATCH_DTYPE(dtype, T, {
+    constexpr int N = Vec16<T>::N;
+    if (n % N) { set_last_error(__FILE__, __LINE__, "p2p_reduce_slots: slot size must be a multiple of the 16B vector"); return; }
+    reduce_slots_kernel<T><<<comm_grid(n / N), kThreads, 0, s>>>(P, off, (T*)out, n, rank, world, epoch, counter);
   });
   B200_CUDA_CHECK(cudaGetLastError());
 }

@@ -147,6 +147,8 @@ struct Params {
   int in_dtype, out_dtype;
   int has_bias, act, accumulate;
   uint32_t idesc;
+  int rs_world, rs_rows;   // fused reduce-scatter push (see GemmArgs)
+  void* rs_dst[8];
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -332,10 +334,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (row_ok) {
-          const int64_t off = (int64_t)bz * p.stride_d + (int64_t)row * p.ldd + col0;
-          if (p.out_dtype == kBF16) store_row_chunk((__nv_bfloat16*)p.d + off, v, valid, p.accumulate);
-          else if (p.out_dtype == kF16) store_row_chunk((__half*)p.d + off, v, valid, p.accumulate);
-          else store_row_chunk((float*)p.d + off, v, valid, p.accumulate);
+          void* dptr = p.d;
+          int64_t off = (int64_t)bz * p.stride_d + (int64_t)row * p.ldd + col0;
+          if (p.rs_world > 1) {   // fused reduce-scatter: push this row's partial into its owner's staging slot (peer HBM)
+            const int owner = row / p.rs_rows;
+            dptr = p.rs_dst[owner];
+            off = (int64_t)(row - owner * p.rs_rows) * p.ldd + col0;
+          }
+          if (p.out_dtype == kBF16) store_row_chunk((__nv_bfloat16*)dptr + off, v, valid, p.accumulate);
+          else if (p.out_dtype == kF16) store_row_chunk((__half*)dptr + off, v, valid, p.accumulate);
+          else store_row_chunk((float*)dptr + off, v, valid, p.accumulate);
         }
       }
       tc_fence_before();
@@ -383,6 +391,10 @@ static int launch(const GemmArgs& g, cudaStream_t s) {
   p.has_bias = (g.epilogue >= 1 && g.epilogue <= 3 && g.bias) ? 1 : 0;
   p.act = g.epilogue == 2 ? 1 : (g.epilogue == 3 ? 2 : 0);
   p.accumulate = g.epilogue == 4 ? 1 : 0;
+  p.rs_world = g.rs_world > 1 ? g.rs_world : 0;
+  p.rs_rows = g.rs_rows;
+  for (int i = 0; i < 8; ++i) p.rs_dst[i] = g.rs_dst[i];
+  if (p.rs_world) p.ldd = g.n;
   p.idesc = make_idesc(g.dtype, A_MN, B_MN);
   static bool attr_set = false;
   auto kern = gemm2_kernel<A_MN, B_MN>;

@@ -10,6 +10,10 @@ void p2p_allreduce(const int64_t* bases, int64_t off, int64_t n, int dtype, int 
                    cudaStream_t s);
 void p2p_reduce_scatter(const int64_t* bases, int64_t off, void* out, int64_t n, int dtype, int rank, int world, uint32_t epoch,
                         uint32_t* counter, cudaStream_t s);
+// out[i] = sum_s staging[s][i]: `world` slots of n elements at byte offset `off` of THIS rank's heap, filled by the peers'
+// GEMM epilogues (GemmArgs::rs_dst). Cross-rank barriers before (all pushes landed) and after (slots may be reused).
+void p2p_reduce_slots(const int64_t* bases, int64_t off, void* out, int64_t n, int dtype, int rank, int world, uint32_t epoch,
+                      uint32_t* counter, cudaStream_t s);
 void p2p_allgather(const int64_t* bases, int64_t off, int64_t chunk_bytes, int rank, int world, uint32_t epoch, uint32_t* counter,
                    cudaStream_t s);
 void p2p_alltoall(const int64_t* bases, int64_t off_send, int64_t off_recv, int64_t chunk_bytes, int rank, int world, uint32_t epoch,

@@ -88,11 +88,32 @@ struct GemmArgs {
   int out_dtype;   // kF16 / kBF16 / kF32
   int batch;       // >1: strided batched
   int64_t stride_a, stride_b, stride_d;
+  // Fused GEMM -> reduce-scatter (push): when rs_world > 1 the epilogue does not write `d`; output row r belongs to rank
+  // r / rs_rows and is stored straight into that rank's staging slot over NVLink (rs_dst[owner] = peer pointer of the slot
+  // reserved for THIS rank's partials, row-major [rs_rows, n]). The owner sums its `rs_world` slots afterwards
+  // (comm::p2p_reduce_slots). Requires batch == 1 and m == rs_world * rs_rows.
+  int rs_world = 0;
+  int rs_rows = 0;
+  void* rs_dst[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 // returns 0 on success, nonzero if the shape is unsupported by the tcgen05 path (caller falls back)
 int gemm_tcgen05(const GemmArgs& g, cudaStream_t s);
 // CTA-pair variant (cta_group::2, UMMA M=256): gemm_sm100_2cta.cu
 int gemm_tcgen05_2cta(const GemmArgs& g, cudaStream_t s);
 int gemm_tcgen05_supported(int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd, int a_is_km, int b_is_nk);
+
+// ---- attention_sm100.cu ---------------------------------------------------------------------------------------
+// Flash-attention forward (head_dim 128, fp16/bf16). q [B,Sq,H,D], k/v [B,Sk,Hk,D], o [B,Sq,H,D] as strided views (element
+// strides given as {batch, seq, head}; the head_dim stride must be 1). lse: fp32 [B,H,Sq] (natural log) or nullptr.
+struct AttnArgs {
+  const void* q; const void* k; const void* v; void* o; float* lse;
+  int b, sq, sk, h, hk, d;
+  int64_t q_strides[3], k_strides[3], v_strides[3], o_strides[3];
+  float scale;
+  int causal;      // bottom-right aligned: key j visible to query i iff j <= i + (sk - sq)
+  int dtype;
+};
+int attention_fwd_supported(const AttnArgs& a);
+int attention_fwd(const AttnArgs& a, cudaStream_t s);
 
 }  // namespace b200

@@ -134,6 +134,13 @@ class SymmHeap {
                              at::cuda::getCurrentCUDAStream().stream());
     finish();
   }
+  void reduce_slots(int64_t off, torch::Tensor out, int64_t n, int64_t epoch) {
+    c10::cuda::CUDAGuard g(device_);
+    auto b = bases();
+    comm::p2p_reduce_slots(b.data(), off, out.data_ptr(), n, dcode(out.scalar_type()), rank_, world_, (uint32_t)epoch, counter(),
+                           at::cuda::getCurrentCUDAStream().stream());
+    finish();
+  }
   void allgather(int64_t off, int64_t chunk_bytes, int64_t epoch) {
     c10::cuda::CUDAGuard g(device_);
     auto b = bases();
@@ -178,6 +185,7 @@ void bind_symm(pybind11::module_& m) {
       .def("world", &SymmHeap::world)
       .def("allreduce", &SymmHeap::allreduce)
       .def("reduce_scatter", &SymmHeap::reduce_scatter)
+      .def("reduce_slots", &SymmHeap::reduce_slots)
       .def("allgather", &SymmHeap::allgather)
       .def("alltoall", &SymmHeap::alltoall);
 }

@@ -149,6 +149,31 @@ class TensorParallel(MetaParallelBase):
         broadcast_dp_parameters(self._layers, self._hcg)
         mpu.register_sequence_parallel_allreduce_hooks(self._layers)
 
+    def forward(self, *inputs, **kwargs):
+        # all ranks of a tensor-parallel group must consume the same batch: broadcast it from the group's first rank
+        # (parity: fleet/utils/hybrid_parallel_util.py:broadcast_input_data called by TensorParallel._pre_forward)
+        inputs, kwargs = broadcast_input_data(self._hcg, *inputs, **kwargs)
+        return self._layers(*inputs, **kwargs)
+
+
+def broadcast_input_data(hcg, *inputs, **kwargs):
+    group = hcg.get_model_parallel_group()
+    if _n(group) <= 1:
+        return inputs, kwargs
+    src = hcg.get_model_parallel_group_src_rank()
+
+    def bc(t):
+        if isinstance(t, torch.Tensor):
+            raw = _raw(t)
+            if not raw.is_contiguous():
+                raw = raw.contiguous()
+                dist.broadcast(raw, src=src, group=_pg(group))
+                return raw.as_subclass(type(t)) if type(t) is not torch.Tensor else raw
+            dist.broadcast(raw, src=src, group=_pg(group))
+        return t
+
+    return tuple(bc(t) for t in inputs), {k: bc(v) for k, v in kwargs.items()}
+
 
 class ShardingParallel(MetaParallelBase):
     def _prepare_for_model(self):

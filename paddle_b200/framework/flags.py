@@ -10,6 +10,7 @@ _FLAGS = {
     "FLAGS_b200_sync_debug": False,        # serialise side streams (race triage)
     "FLAGS_b200_p2p_collectives": True,    # fused compute+collective kernels over peer memory
     "FLAGS_b200_gemm_backend": "tcgen05",  # "tcgen05" | "cublas"
+    "FLAGS_b200_flash_attention": True,    # tcgen05 flash-attention forward (csrc/attention_sm100.cu)
     "FLAGS_embedding_deterministic": 0,
     "FLAGS_eager_delete_tensor_gb": 0.0,
     "FLAGS_fraction_of_gpu_memory_to_use": 0.92,

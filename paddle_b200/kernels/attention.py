@@ -1,17 +1,21 @@
-"""Attention entry point ([B,S,H,D] layout). Parity: paddle flash_attention / scaled_dot_product_attention.
+"""Attention entry point ([B,S,H,D] layout). Parity: paddle flash_attention / scaled_dot_product_attention
+(python/paddle/nn/functional/flash_attention.py).
 
-Dispatch: the sm_100a flash kernel (csrc/attention.cu) when available for the shape, else PyTorch SDPA (library path).
+Dispatch: the sm_100a tcgen05 flash kernel (csrc/attention_sm100.cu) for fp16/bf16, head_dim 128, no explicit mask and no
+dropout — it reads q/k/v in place as strided views of a packed QKV projection; everything else takes the PyTorch SDPA
+(library) path.  Backward of the fused forward re-uses the saved (out, logsumexp) with the library flash backward until the
+sm_100a backward kernel lands.
 """
 from __future__ import annotations
 
 import math
 
 import torch
-
-from ..framework.recording import recordable
 import torch.nn.functional as F
 
-from . import raw, use_fused, wrap
+from ..framework.flags import flag
+from ..framework.recording import recordable
+from . import ext, raw, use_fused, wrap
 
 
 def attention_ref(q, k, v, mask=None, dropout_p=0.0, causal=False, scale=None):
@@ -28,9 +32,41 @@ def attention_ref(q, k, v, mask=None, dropout_p=0.0, causal=False, scale=None):
     return out.transpose(1, 2)
 
 
+class _FlashAttn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, scale, causal):
+        out, lse = ext().attention_fwd(q, k, v, scale, causal)
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.scale, ctx.causal = scale, causal
+        return out
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, out, lse = ctx.saved_tensors
+        do = do.contiguous()
+        empty = torch.empty(0, dtype=torch.int64, device=q.device)
+        rng = torch.zeros(2, dtype=torch.int64, device=q.device)
+        dq, dk, dv = torch.ops.aten._flash_attention_backward(do, q, k, v, out, lse, None, None, q.shape[1], k.shape[1], 0.0, ctx.causal,
+                                                               rng, empty, scale=ctx.scale)
+        return dq, dk, dv, None, None
+
+
+def fused_ok(q, k, v, mask, dropout_p, causal):
+    if not (use_fused(q) and flag("FLAGS_b200_flash_attention", True)) or mask is not None or dropout_p != 0.0:
+        return False
+    if q.dtype not in (torch.float16, torch.bfloat16) or q.dim() != 4 or q.shape[-1] != 128:
+        return False
+    if causal and q.shape[1] != k.shape[1]:
+        return False
+    return bool(ext().attention_supported(q, k, v))
+
+
 @recordable
 def attention(q, k, v, mask=None, dropout_p=0.0, causal=False, scale=None):
     q, k, v, mask = raw(q), raw(k), raw(v), raw(mask)
+    if fused_ok(q, k, v, mask, dropout_p, causal):
+        sc = float(scale) if scale is not None else 1.0 / math.sqrt(q.shape[-1])
+        return wrap(_FlashAttn.apply(q, k, v, sc, bool(causal)))
     if causal and mask is not None:
         sq, sk = q.shape[1], k.shape[1]
         cm = torch.ones(sq, sk, dtype=torch.bool, device=q.device).tril(sk - sq)

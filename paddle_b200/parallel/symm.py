@@ -130,6 +130,21 @@ class SymmContext:
         x2 = x.reshape(-1, x.shape[-1])
         m = x2.shape[0]
         n = w.shape[0] if b_is_nk else w.shape[1]
+        if os.environ.get("B200_RS_PUSH", "1") == "1" and m % self.world == 0 and n % 8 == 0 and KG._tc_ok(x2, w, False, b_is_nk):
+            # single-pass fused path: the GEMM epilogue stores each output row into its owner's staging slot over NVLink while
+            # the tensor cores work on the next tile; the tail kernel only sums `world` local slots
+            rows = m // self.world
+            _, off = self.buffer("grs_push", (self.world, rows, n), x.dtype)
+            slot = rows * n * x.element_size()
+            dst = [self.heap.peer_ptr(r) + off + self.rank * slot for r in range(self.world)]
+            key = ("dummy", n, x.dtype)
+            dummy = self._bufs.get(key)
+            if dummy is None:
+                dummy = self._bufs[key] = torch.empty((1, n), dtype=x.dtype, device=x.device)
+            self.ext.gemm(x2, w, None, False, b_is_nk, 0, dummy, None, dst, rows)
+            out = torch.empty((rows, n), dtype=x.dtype, device=x.device)
+            self.heap.reduce_slots(off, out, rows * n, self.next_epoch())
+            return out.reshape(x.shape[0] // self.world, *x.shape[1:-1], n)
         buf, off = self.buffer("grs", (m, n), x.dtype)
         KG.gemm(x2, w, b_is_nk=b_is_nk, out=buf)
         out = torch.empty((m // self.world, n), dtype=x.dtype, device=x.device)

@@ -94,6 +94,24 @@ def bw_bench():
     return rows
 
 
+def attn_bench():
+    """tcgen05 flash-attention forward vs the library flash kernel (torch SDPA) on Llama-2-13B attention shapes."""
+    import torch.nn.functional as F
+
+    rows = []
+    peak = PEAKS.get("bf16_tflops_sustained", 1433.6)
+    for (b, s, h, causal) in ((1, 4096, 40, True), (4, 4096, 20, True), (2, 8192, 40, True), (4, 2048, 40, False)):
+        q, k, v = (torch.randn(b, s, h, 128, device="cuda", dtype=torch.bfloat16) for _ in range(3))
+        flops = 4.0 * b * h * s * s * 128 * (0.5 if causal else 1.0)
+        t = timeit(lambda: E.attention_fwd(q, k, v, 128 ** -0.5, causal))
+        qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
+        t_lib = timeit(lambda: F.scaled_dot_product_attention(qt, kt, vt, is_causal=causal))
+        rows.append(dict(kernel="flash_attn_fwd", b=b, s=s, h=h, causal=causal, ms=round(t, 4), tflops=round(flops / t / 1e9, 1),
+                         lib_ms=round(t_lib, 4), lib_tflops=round(flops / t_lib / 1e9, 1), frac_of_measured_bf16_peak=round(flops / t / 1e9 / peak, 3)))
+        print(json.dumps(rows[-1]), flush=True)
+    return rows
+
+
 if __name__ == "__main__":
     out = {"gpu": torch.cuda.get_device_name(0), "peaks": PEAKS}
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -101,5 +119,7 @@ if __name__ == "__main__":
         out["gemm"] = gemm_bench()
     if which in ("all", "bw"):
         out["bw"] = bw_bench()
+    if which in ("all", "attn"):
+        out["attn"] = attn_bench()
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open("gpurun_out/bench_kernels.json", "w"), indent=1)
+    json.dump(out, open(f"gpurun_out/bench_kernels_{which}.json", "w"), indent=1)

@@ -60,9 +60,17 @@ def hook(name):
             if not bool(torch.isfinite(o.as_subclass(torch.Tensor)).all()):
                 bad.append(name)
                 print(f"[rank {rank}] NON-FINITE activation after {name} shape={list(o.shape)}", flush=True)
+        if name in ("llama", "lm_head.norm") and isinstance(o, torch.Tensor):
+            r = o.as_subclass(torch.Tensor).detach().float().reshape(-1, o.shape[-1]).pow(2).mean(-1).sqrt()
+            print(f"[rank {rank}] fwd {name}: shape {list(o.shape)} strides {o.stride()} row-rms min {float(r.min()):.4g} (row {int(r.argmin())}) "
+                  f"max {float(r.max()):.4g} (row {int(r.argmax())}) median {float(r.median()):.4g}", flush=True)
         if isinstance(o, torch.Tensor) and o.requires_grad:
             def gh(g, name=name):
                 gr = g.as_subclass(torch.Tensor)
+                if name in ("llama", "lm_head.norm"):
+                    rr = gr.detach().float().reshape(-1, gr.shape[-1]).abs().amax(-1)
+                    print(f"[rank {rank}] bwd grad into {name}: shape {list(gr.shape)} strides {gr.stride()} row-max: max {float(rr.max()):.4g} (row {int(rr.argmax())}) "
+                          f"median {float(rr.median()):.4g} top rows {rr.topk(5).indices.tolist()}", flush=True)
                 if len(gbad) < 3 and not bool(torch.isfinite(gr).all()):
                     gbad.append(name)
                     print(f"[rank {rank}] NON-FINITE grad flowing into output of {name} shape={list(g.shape)} "
@@ -79,9 +87,10 @@ gbad, gmax, arms = [], {}, []
 for n, sub in inner.named_sublayers():
     sub.register_forward_post_hook(hook(n))
 
+gen = torch.Generator().manual_seed(99)   # identical tokens on every mp rank (a replica shares its input)
 for step in range(args.steps):
     for mb in range(args.accumulate):
-        tok = torch.randint(0, cfg.vocab_size, (args.batch, args.seq + 1), device="cuda").as_subclass(paddle.Tensor)
+        tok = torch.randint(0, cfg.vocab_size, (args.batch, args.seq + 1), generator=gen).cuda().as_subclass(paddle.Tensor)
         loss = model(tok[:, :-1], tok[:, 1:]) / args.accumulate
         loss.backward()
     if step == 0 and rank == 0:
