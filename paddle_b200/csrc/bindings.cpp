@@ -343,7 +343,9 @@ bool gemm_supported(const Tensor& a, const Tensor& b, bool a_is_km, bool b_is_nk
 }
 
 Tensor gemm(const Tensor& a, const Tensor& b, const OptT& bias, bool a_is_km, bool b_is_nk, int64_t epilogue, const OptT& out,
-            const std::optional<at::ScalarType>& out_dtype, const std::vector<int64_t>& rs_dst, int64_t rs_rows) {
+            const std::optional<at::ScalarType>& out_dtype, const std::vector<int64_t>& rs_dst, int64_t rs_rows,
+            const std::vector<int64_t>& ag_src, const std::vector<int64_t>& ag_pad, const OptT& ag_flags, int64_t ag_rank, int64_t ag_rows,
+            int64_t ag_epoch) {
   TORCH_CHECK(gemm_supported(a, b, a_is_km, b_is_nk), "paddle_b200.gemm: unsupported operands for the tcgen05 path");
   c10::cuda::CUDAGuard guard(a.device());
   b200::GemmArgs g;
@@ -375,6 +377,13 @@ Tensor gemm(const Tensor& a, const Tensor& b, const OptT& bias, bool a_is_km, bo
     g.rs_world = (int)rs_dst.size();
     g.rs_rows = (int)rs_rows;
     for (size_t i = 0; i < rs_dst.size(); ++i) g.rs_dst[i] = reinterpret_cast<void*>(rs_dst[i]);
+  }
+  if (!ag_src.empty()) {   // fused all-gather of the A rows (see GemmArgs)
+    TORCH_CHECK(ag_src.size() <= 8 && ag_pad.size() == ag_src.size() && ag_flags.has_value() && ag_flags->defined() && !a_is_km &&
+                a.is_contiguous() && ag_rows > 0, "gemm: bad fused all-gather arguments");
+    g.ag_world = (int)ag_src.size(); g.ag_rank = (int)ag_rank; g.ag_rows = (int)ag_rows; g.ag_epoch = (uint32_t)ag_epoch;
+    for (size_t i = 0; i < ag_src.size(); ++i) { g.ag_src[i] = reinterpret_cast<const void*>(ag_src[i]); g.ag_pad[i] = reinterpret_cast<void*>(ag_pad[i]); }
+    g.ag_flags = ag_flags->data_ptr();
   }
   if (g.bias) TORCH_CHECK(bias->scalar_type() == a.scalar_type() || bias->scalar_type() == at::kFloat, "gemm: bias dtype");
   if (g.bias && bias->scalar_type() == at::kFloat && a.scalar_type() != at::kFloat) {
@@ -460,7 +469,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_supported", &gemm_supported);
   m.def("gemm", &gemm, pybind11::arg("a"), pybind11::arg("b"), pybind11::arg("bias") = pybind11::none(), pybind11::arg("a_is_km") = false,
         pybind11::arg("b_is_nk") = false, pybind11::arg("epilogue") = 0, pybind11::arg("out") = pybind11::none(),
-        pybind11::arg("out_dtype") = pybind11::none(), pybind11::arg("rs_dst") = std::vector<int64_t>(), pybind11::arg("rs_rows") = 0);
+        pybind11::arg("out_dtype") = pybind11::none(), pybind11::arg("rs_dst") = std::vector<int64_t>(), pybind11::arg("rs_rows") = 0,
+        pybind11::arg("ag_src") = std::vector<int64_t>(), pybind11::arg("ag_pad") = std::vector<int64_t>(), pybind11::arg("ag_flags") = pybind11::none(),
+        pybind11::arg("ag_rank") = 0, pybind11::arg("ag_rows") = 0, pybind11::arg("ag_epoch") = 0);
   m.def("attention_supported", &attention_supported);
   m.def("attention_fwd", &attention_fwd);
   m.def("launch_count", &launch_count);

@@ -494,6 +494,7 @@ int gemm_tcgen05(const GemmArgs& g, cudaStream_t s) {
   if (g.dtype != kBF16 && g.dtype != kF16) return 1;
   // large problems: CTA-pair kernel (cta_group::2, 256x256 cluster tile); B200_GEMM_2CTA=0 forces the 1-CTA kernel
   static const int use_2cta = [] { const char* e = getenv("B200_GEMM_2CTA"); return e ? atoi(e) : 1; }();
+  if (g.ag_world > 1) return gemm_tcgen05_2cta(g, s);   // the fused all-gather lives in the CTA-pair kernel only
   if (use_2cta && g.m >= 256 && g.n >= 256) return gemm_tcgen05_2cta(g, s);
   // tile-N choice: widest tile that keeps the last wave reasonably full
   const int sms = sm_count();

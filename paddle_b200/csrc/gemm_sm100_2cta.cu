@@ -149,7 +149,95 @@ struct Params {
   uint32_t idesc;
   int rs_world, rs_rows;   // fused reduce-scatter push (see GemmArgs)
   void* rs_dst[8];
+  // fused all-gather -> GEMM (see GemmArgs): warp 3 of every CTA pulls the peers' row shards into the local A buffer
+  int ag_world, ag_rank, ag_rows, ag_chunks;
+  const char* ag_src[8];
+  char* ag_dst;
+  uint32_t* ag_flags;
+  uint32_t* ag_pad[8];
+  uint32_t ag_epoch;
 };
+
+constexpr int kAgChunkBytes = 16384;
+constexpr int kAgReadySlot = 4, kAgDoneSlot = 5, kPadRanks = 8;
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// bounded spins: a dead peer / protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void spin_sys_ge(const uint32_t* p, uint32_t target, const char* what) {
+  const uint64_t t0 = globaltimer_ns();
+  while ((int32_t)(ld_acquire_sys_u32(p) - target) < 0) {
+    if (globaltimer_ns() - t0 > 10000000000ull) { printf("b200 gemm2 all-gather: timeout waiting for %s\n", what); __trap(); }
+  }
+}
+__device__ __forceinline__ void spin_gpu_ge(const uint32_t* p, uint32_t target) {
+  const uint64_t t0 = globaltimer_ns();
+  while (ld_acquire_gpu_u32(p) < target) {
+    if (globaltimer_ns() - t0 > 10000000000ull) { printf("b200 gemm2 all-gather: timeout waiting for a gathered row block\n"); __trap(); }
+  }
+}
+
+// Copy role of the fused all-gather: chunk g of the remote data is handled by warp (g % #CTAs); finished chunks bump the
+// counter of their 128-row block, which the TMA producers poll before loading A rows of that block.
+__device__ __forceinline__ void ag_copy_role(const Params& p, int lane) {
+  const int nwarps = gridDim.x, wid = blockIdx.x;
+  const int blocks_per_rank = p.ag_rows / BLOCK_M;
+  const int64_t block_bytes = (int64_t)BLOCK_M * p.k * 2;
+  const int64_t per_src = (int64_t)blocks_per_rank * p.ag_chunks;
+  const int64_t total = (int64_t)(p.ag_world - 1) * per_src;
+  uint32_t* my_pad = p.ag_pad[p.ag_rank];
+  if (wid == 0 && lane < p.ag_world && lane != p.ag_rank)        // my shard is in place (stream order before this kernel)
+    st_release_sys_u32(p.ag_pad[lane] + kAgReadySlot * kPadRanks + p.ag_rank, p.ag_epoch);
+  int cur_src = -1;
+  for (int64_t g = wid; g < total; g += nwarps) {
+    const int pr = (int)(g / per_src) + 1;
+    const int src = (p.ag_rank + pr) % p.ag_world;
+    const int64_t rem = g - (int64_t)(pr - 1) * per_src;
+    const int blk_in = (int)(rem / p.ag_chunks), ch = (int)(rem % p.ag_chunks);
+    if (src != cur_src) {
+      if (lane == 0) spin_sys_ge(my_pad + kAgReadySlot * kPadRanks + src, p.ag_epoch, "a peer shard");
+      __syncwarp();
+      cur_src = src;
+    }
+    const uint4* sp = reinterpret_cast<const uint4*>(p.ag_src[src] + blk_in * block_bytes + (int64_t)ch * kAgChunkBytes);
+    uint4* dp = reinterpret_cast<uint4*>(p.ag_dst + ((int64_t)src * blocks_per_rank + blk_in) * block_bytes + (int64_t)ch * kAgChunkBytes);
+#pragma unroll
+    for (int it = 0; it < kAgChunkBytes / 16 / 32 / 8; ++it) {
+      uint4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = sp[(it * 8 + j) * 32 + lane];     // 8 independent 16 B loads over NVLink in flight
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dp[(it * 8 + j) * 32 + lane] = v[j];
+    }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      atomicAdd(p.ag_flags + src * blocks_per_rank + blk_in, 1u);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence();
+    const int done_idx = p.ag_world * blocks_per_rank;
+    if (atomicAdd(p.ag_flags + done_idx, 1u) == (uint32_t)nwarps - 1) {    // every pull of this rank has completed
+      for (int r = 0; r < p.ag_world; ++r)
+        if (r != p.ag_rank) st_release_sys_u32(p.ag_pad[r] + kAgDoneSlot * kPadRanks + p.ag_rank, p.ag_epoch);
+    }
+  }
+  if (wid == 0 && lane < p.ag_world && lane != p.ag_rank)        // peers finished reading my shard: it may be reused after exit
+    spin_sys_ge(my_pad + kAgDoneSlot * kPadRanks + lane, p.ag_epoch, "a peer to finish reading");
+}
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
@@ -228,6 +316,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     const int r = t - g * in_group;
     mb = first_m + r % gsz;
     nb = r / gsz;
+    if (p.ag_world > 1) {   // fused all-gather: start with the row blocks that are already local
+      mb += p.ag_rank * (p.ag_rows / (2 * BLOCK_M));
+      if (mb >= num_m) mb -= num_m;
+    }
   };
 
   if (warp == 0) {
@@ -241,6 +333,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         tile_coords(tile, bz, mb, nb);
         const int m0 = mb * 2 * BLOCK_M + (int)cta_rank * BLOCK_M;
         const int n0 = nb * BLOCK_N + (int)cta_rank * HALF_N;
+        if (p.ag_world > 1) {
+          const int blk = m0 / BLOCK_M;
+          if (blk / (p.ag_rows / BLOCK_M) != p.ag_rank) {        // rows owned by a peer: wait until the copy warps landed them
+            spin_gpu_ge(p.ag_flags + blk, (uint32_t)p.ag_chunks);
+            asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy writes (other SMs) -> TMA (async proxy) reads
+          }
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
@@ -292,6 +391,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         umma_commit_2sm(tfull_bar(as));
       }
     }
+  } else if (warp == 3) {
+    if (p.ag_world > 1) ag_copy_role(p, lane);
   } else if (warp >= 4) {
     // ================= epilogue (both CTAs: own 128 rows x 256 columns) =================
     const int ew = warp - 4;
@@ -395,6 +496,21 @@ static int launch(const GemmArgs& g, cudaStream_t s) {
   p.rs_rows = g.rs_rows;
   for (int i = 0; i < 8; ++i) p.rs_dst[i] = g.rs_dst[i];
   if (p.rs_world) p.ldd = g.n;
+  p.ag_world = 0;
+  if (g.ag_world > 1) {
+    // preconditions of the fused all-gather (checked by the caller as well): A is K-major with lda == k, whole 256-row tiles per rank
+    if (A_MN || g.lda != g.k || g.ag_rows % (2 * BLOCK_M) || g.m != g.ag_world * g.ag_rows || batch != 1 ||
+        ((int64_t)BLOCK_M * g.k * 2) % kAgChunkBytes) {
+      set_last_error(__FILE__, __LINE__, "gemm_tcgen05_2cta: unsupported shape for the fused all-gather");
+      return 4;
+    }
+    p.ag_world = g.ag_world; p.ag_rank = g.ag_rank; p.ag_rows = g.ag_rows;
+    p.ag_chunks = (int)(((int64_t)BLOCK_M * g.k * 2) / kAgChunkBytes);
+    for (int i = 0; i < 8; ++i) { p.ag_src[i] = (const char*)g.ag_src[i]; p.ag_pad[i] = (uint32_t*)g.ag_pad[i]; }
+    p.ag_dst = (char*)const_cast<void*>(g.a);
+    p.ag_flags = (uint32_t*)g.ag_flags;
+    p.ag_epoch = g.ag_epoch;
+  }
   p.idesc = make_idesc(g.dtype, A_MN, B_MN);
   static bool attr_set = false;
   auto kern = gemm2_kernel<A_MN, B_MN>;

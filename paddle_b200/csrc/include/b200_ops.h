@@ -95,6 +95,15 @@ struct GemmArgs {
   int rs_world = 0;
   int rs_rows = 0;
   void* rs_dst[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // Fused all-gather -> GEMM: `a` is the LOCAL gathered buffer [ag_world*ag_rows, k] (row-major, lda == k) of which only
+  // rank ag_rank's row shard is valid at launch; one warp per CTA pulls the other shards from ag_src[r] (peer pointers to
+  // each rank's shard) over NVLink while the tensor cores start on the local rows; ag_flags = zeroed uint32 counters
+  // (one per 128-row block + 1); ag_pad[r] = signal pad of rank r; ag_epoch = fresh epoch of this call.
+  int ag_world = 0, ag_rank = 0, ag_rows = 0;
+  const void* ag_src[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void* ag_pad[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void* ag_flags = nullptr;
+  uint32_t ag_epoch = 0;
 };
 // returns 0 on success, nonzero if the shape is unsupported by the tcgen05 path (caller falls back)
 int gemm_tcgen05(const GemmArgs& g, cudaStream_t s);

@@ -55,7 +55,7 @@ class DataParallel(Layer):
 
     def _setup_reducer(self):
         existing = getattr(self._params[0], "__dict__", {}).get("_arena_grad") is not None
-        self._arena = ParamArena(self._params) if not existing else None
+        self._arena = ParamArena(self._params, grad_allocator=self._symm_grad_allocator()) if not existing else None
         if self._arena is None:  # an optimizer already flattened them: fall back to per-parameter reduction
             self._buckets = []
             return
@@ -77,6 +77,27 @@ class DataParallel(Layer):
             p.register_post_accumulate_grad_hook(self._make_hook(p))
         if self._params[0].is_cuda:
             self._stream = torch.cuda.Stream()
+
+    def _symm_grad_allocator(self):
+        """Gradient slabs are placed in the symmetric peer heap when they fit: the bucket all-reduce then runs in place over
+        NVLink (two-shot peer-memory kernel) with no staging copies."""
+        if not self._params[0].is_cuda:
+            return None
+        from ..parallel import symm
+
+        ctx = symm.context_for(self.group if self.group is not None else self._pg)
+        if ctx is None:
+            return None
+        need = sum((p.numel() + 127) // 128 * 128 * p.element_size() for p in self._params)
+        if need > (ctx.heap.size() - ctx.heap.cursor()) // 2:
+            return None
+
+        def alloc(n, dt):
+            t, _ = ctx.buffer(("dp_grad", id(self), n), (n,), dt)
+            t.zero_()
+            return t
+
+        return alloc
 
     def _make_hook(self, p):
         def hook(_param):

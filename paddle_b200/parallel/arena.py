@@ -19,7 +19,7 @@ _ALIGN = 128  # elements; keeps every view 256B-aligned for 16B vector access an
 
 
 class Slab:
-    def __init__(self, dtype, device, params, grad_dtype=None, allocator=None):
+    def __init__(self, dtype, device, params, grad_dtype=None, allocator=None, grad_allocator=None):
         self.dtype, self.device = dtype, device
         self.grad_dtype = grad_dtype or dtype
         self.params = list(params)
@@ -31,7 +31,7 @@ class Slab:
         self.numel = off
         alloc = allocator or (lambda n, dt: torch.zeros(n, dtype=dt, device=device))
         self.data = alloc(self.numel, dtype)
-        self.grad = alloc(self.numel, self.grad_dtype)
+        self.grad = (grad_allocator or alloc)(self.numel, self.grad_dtype)
         with torch.no_grad():
             for p in self.params:
                 o, n = self.offsets[p.name]
@@ -60,7 +60,7 @@ class Slab:
 class ParamArena:
     """Groups parameters by (dtype, device, decay-class) into slabs."""
 
-    def __init__(self, params, group_fn=None, grad_dtype=None, allocator=None):
+    def __init__(self, params, group_fn=None, grad_dtype=None, allocator=None, grad_allocator=None):
         params = [p for p in params if not p.stop_gradient]
         groups = OrderedDict()
         for p in params:
@@ -68,7 +68,7 @@ class ParamArena:
             groups.setdefault(key, []).append(p)
         self.slabs = OrderedDict()
         for key, ps in groups.items():
-            self.slabs[key] = Slab(key[0], key[1], ps, grad_dtype=grad_dtype, allocator=allocator)
+            self.slabs[key] = Slab(key[0], key[1], ps, grad_dtype=grad_dtype, allocator=allocator, grad_allocator=grad_allocator)
 
     def zero_grad(self):
         for s in self.slabs.values():

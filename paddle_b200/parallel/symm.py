@@ -160,6 +160,24 @@ class SymmContext:
         ml, k = x2.shape
         full, off = self.buffer("agg", (ml * self.world, k), x.dtype)
         full[self.rank * ml:(self.rank + 1) * ml].copy_(x2)
+        nout = w.shape[0] if b_is_nk else w.shape[1]
+        if os.environ.get("B200_AG_FUSED", "1") == "1" and ml % 256 == 0 and k % 64 == 0 and nout >= 256 and KG._tc_ok(full, w, False, b_is_nk):
+            # one kernel: a copy warp per CTA pulls the peers' shards into `full` over NVLink (per-row-block flags) while the
+            # tensor cores start on the local rows; the TMA producers wait on the flag of a row block before loading it
+            shard_bytes = ml * k * x.element_size()
+            src = [self.heap.peer_ptr(r) + off + r * shard_bytes for r in range(self.world)]
+            pads = [self.heap.peer_ptr(r) for r in range(self.world)]
+            nblk = (ml * self.world) // 128
+            fkey = ("agflags", nblk)
+            flags = self._bufs.get(fkey)
+            if flags is None:
+                flags = self._bufs[fkey] = torch.zeros(nblk + 1, dtype=torch.int32, device=x.device)
+            flags.zero_()
+            y = self.ext.gemm(full, w, None, False, b_is_nk, 0, None, None, [], 0, src, pads, flags, self.rank, ml, self.next_epoch())
+            y = y.reshape(x.shape[0] * self.world, *x.shape[1:-1], nout)
+            if return_gathered:
+                return y, full.clone().reshape(x.shape[0] * self.world, *x.shape[1:])
+            return y
         self.heap.allgather(off, ml * k * x.element_size(), self.next_epoch())
         y = KG.gemm(full, w, b_is_nk=b_is_nk)
         n = y.shape[-1]

@@ -510,6 +510,24 @@ def case_p2p_kernels():
     ref_dw2 = xfull.reshape(-1, 512).t() @ g2.float().reshape(-1, 256)
     e = ((wc.grad.float() - ref_dw2).norm() / ref_dw2.norm()).item()
     assert e < 2e-2, f"allgather_gemm dw {e}"
+    # repeated larger calls through the same symmetric buffers (slot / flag reuse, start+end barriers) with no host sync between them
+    sc2 = symm.context_for(grp)
+    for it in range(4):
+        torch.manual_seed(1000 + 10 * it + r)
+        xb = (torch.randn(1024, 1024, device="cuda") * 0.05).to(torch.bfloat16)
+        wb = (torch.randn(1024, 1536, device="cuda") * 0.05).to(torch.bfloat16)
+        ya = sc2.allgather_gemm(xb, wb)
+        yr = sc2.gemm_reduce_scatter(ya[:, :1024].contiguous(), wb)
+        gl = [torch.empty_like(xb) for _ in range(w)]
+        torch.distributed.all_gather(gl, xb)
+        ref_a = torch.cat(gl, 0).float() @ wb.float()
+        e = ((ya.float() - ref_a).norm() / ref_a.norm()).item()
+        assert e < 2e-2, f"iter {it} fused all-gather GEMM {e}"
+        ref_r = ya[:, :1024].float() @ wb.float()
+        torch.distributed.all_reduce(ref_r)
+        ref_r = ref_r.chunk(w, 0)[r]
+        e = ((yr.float() - ref_r).norm() / ref_r.norm()).item()
+        assert e < 2e-2, f"iter {it} fused GEMM reduce-scatter {e}"
     # vocab-parallel fused cross entropy kernels vs dense fp32
     from paddle_b200.kernels import loss as KL
 
