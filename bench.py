@@ -204,7 +204,7 @@ def main():
         barrier()
         wall = time.perf_counter() - t0
         ms = ev0.elapsed_time(ev1)
-        t = torch.tensor([ms], device="cuda")
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)   # explicit: the default dtype is bf16 here
         if n > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         clocks = sampler.stop()

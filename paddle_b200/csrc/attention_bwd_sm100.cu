@@ -1,0 +1,446 @@
+// Flash-attention backward for sm_100a (head_dim 128, bf16/fp16), tcgen05 + TMA.
+//
+// One CTA owns a 128-key K/V tile of one (batch, kv head) and walks the query tiles that can see it (and, under GQA, every
+// query head of the group).  Per query tile five 128x128x128 tensor-core GEMMs:
+//   S   = Q K^T          dP  = dO V^T                      (TMEM, lane = query row)
+//   dV += P^T dO         dK += dS^T Q                      (TMEM accumulators, lane = key row, live across the whole loop)
+//   dQ^T = K^T dS^T                                        (TMEM, lane = head dim; reduced into fp32 dQ with coalesced atomics)
+// P and dS are produced by the 128 softmax threads (thread = query row) from S, dP, the forward's logsumexp and
+// delta = rowsum(dO * O), and are written ONCE to shared memory in the 128B-swizzled [key-half][query row] layout that
+// serves both as MN-major A operand (P^T, dS^T) and as K-major B operand (dS^T of the dQ GEMM) by choice of descriptor
+// strides; the K tile is likewise consumed K-major (S) and MN-major (dQ^T) from one copy.
+//
+// Parity (behaviour): flash_attn_grad (paddle/phi/kernels/gpu/flash_attn_grad_kernel.cu -> flash-attention library).
+// Warps 0-3: softmax / dQ reduction / epilogue, warp 4: TMA producer, warp 5: TMEM alloc + MMA issuer.
+// TMEM columns: [0,128) S then dQ^T, [128,256) dP, [256,384) dV, [384,512) dK.
+#include <cuda.h>
+#include <cstdio>
+#include <string>
+
+#include "include/b200_common.cuh"
+#include "include/b200_ops.h"
+
+namespace b200 {
+namespace attn_bwd {
+
+constexpr int BM = 128, BN = 128, HD = 128;
+constexpr int kThreads = 192;
+constexpr uint32_t TILE_BYTES = 128 * 128 * 2;
+constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;
+constexpr uint32_t SMEM_BYTES = 6 * TILE_BYTES + 1024 + 256;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 384;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t gtimer() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  uint64_t t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins == 2048) t0 = gtimer();
+    if (spins > 2048 && (spins & 1023) == 0 && gtimer() - t0 > 4000000000ull) {
+      printf("b200 attention bwd: mbarrier timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Operand descriptors for one 128x128 bf16 tile stored as two 64-wide halves [half][row 0..127][128 B swizzled]:
+//   K-major use   (rows = M or N index, inner = K):   K step k (16 elems) inside half kb -> +kb*HALF + k*32,  LBO 16, SBO 1024
+//   MN-major use  (rows = K index, inner = M or N):   K step k (16 rows)                 -> +k*2048,         LBO HALF (next 64 M/N), SBO 1024
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kb, int k) { return make_desc(tile + kb * HALF_BYTES + k * 32, 16, 1024); }
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kk) { return make_desc(tile + kk * 2048, HALF_BYTES, 1024); }
+
+struct Params {
+  int b, sq, sk, h, hk;
+  float scale, scale_log2;
+  int causal, causal_off;
+  const float* lse;      // [B,H,Sq] natural log
+  const float* delta;    // [B,H,Sq]
+  float* dq;             // fp32 [B,Sq,H,D] (zero-initialised; reduced with atomics)
+  void* dk;              // [B,Sk,Hk,D] contiguous
+  void* dv;
+  uint32_t idesc_kk;     // A K-major, B K-major   (S, dP)
+  uint32_t idesc_mm;     // A MN-major, B MN-major (dV, dK)
+  uint32_t idesc_mk;     // A MN-major, B K-major  (dQ^T)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+           const __grid_constant__ CUtensorMap map_do, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sK = base, sV = base + TILE_BYTES, sQ = base + 2 * TILE_BYTES, sDO = base + 3 * TILE_BYTES, sP = base + 4 * TILE_BYTES,
+                 sDS = base + 5 * TILE_BYTES;
+  const uint32_t bars = base + 6 * TILE_BYTES;
+  const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 16, s_full = bars + 24, s_free = bars + 32, pds_full = bars + 40,
+                 dq_full = bars + 48, acc_done = bars + 56;
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + 6 * TILE_BYTES + 8 * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x, kv_head = blockIdx.y, batch = blockIdx.z;
+  const int n0 = n_tile * BN;
+  const int group = p.h / p.hk;
+  const int num_m = (p.sq + BM - 1) / BM;
+  int m_first = 0;
+  if (p.causal) {                       // first query row that can see key n0: i >= n0 - causal_off
+    const int r0 = max(0, n0 - p.causal_off);
+    m_first = min(num_m, r0 / BM);
+  }
+  const int tiles_per_head = num_m - m_first;
+  const int total = tiles_per_head * group;    // iteration it -> (query head = kv_head*group + it / tiles_per_head, m tile = m_first + it % tiles_per_head)
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_do) : "memory");
+    mbar_init(kv_full, 1); mbar_init(qdo_full, 1); mbar_init(qdo_empty, 1); mbar_init(s_full, 1); mbar_init(s_free, 4);
+    mbar_init(pds_full, 4); mbar_init(dq_full, 1); mbar_init(acc_done, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  } else if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 4) {
+    if (lane == 0 && total > 0) {
+      // ================= TMA producer =================
+      mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+      tma_load_4d(sK, &map_k, kv_full, 0, n0, kv_head, batch);
+      tma_load_4d(sK + HALF_BYTES, &map_k, kv_full, 64, n0, kv_head, batch);
+      tma_load_4d(sV, &map_v, kv_full, 0, n0, kv_head, batch);
+      tma_load_4d(sV + HALF_BYTES, &map_v, kv_full, 64, n0, kv_head, batch);
+      for (int it = 0; it < total; ++it) {
+        const int head = kv_head * group + it / tiles_per_head;
+        const int m0 = (m_first + it % tiles_per_head) * BM;
+        mbar_wait(qdo_empty, (it & 1) ^ 1);
+        mbar_expect_tx(qdo_full, 2 * TILE_BYTES);
+        tma_load_4d(sQ, &map_q, qdo_full, 0, m0, head, batch);
+        tma_load_4d(sQ + HALF_BYTES, &map_q, qdo_full, 64, m0, head, batch);
+        tma_load_4d(sDO, &map_do, qdo_full, 0, m0, head, batch);
+        tma_load_4d(sDO + HALF_BYTES, &map_do, qdo_full, 64, m0, head, batch);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && total > 0) {
+      // ================= MMA issuer =================
+      mbar_wait(kv_full, 0);
+      for (int it = 0; it < total; ++it) {
+        const uint32_t ph = it & 1;
+        mbar_wait(qdo_full, ph);
+        mbar_wait(s_free, ph ^ 1);        // S / dQ^T columns drained by the softmax warps (previous iteration)
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_f16(tmem_base + S_COL, desc_kmajor(sQ, kb, k), desc_kmajor(sK, kb, k), p.idesc_kk, (kb | k) != 0);    // S = Q K^T
+            umma_f16(tmem_base + DP_COL, desc_kmajor(sDO, kb, k), desc_kmajor(sV, kb, k), p.idesc_kk, (kb | k) != 0);  // dP = dO V^T
+          }
+        umma_commit(s_full);
+        mbar_wait(pds_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {     // K dimension = 128 query rows, 16 per MMA
+          umma_f16(tmem_base + DV_COL, desc_mnmajor(sP, kk), desc_mnmajor(sDO, kk), p.idesc_mm, (it | kk) != 0);   // dV += P^T dO
+          umma_f16(tmem_base + DK_COL, desc_mnmajor(sDS, kk), desc_mnmajor(sQ, kk), p.idesc_mm, (it | kk) != 0);   // dK += dS^T Q
+        }
+        umma_commit(qdo_empty);              // Q / dO tiles may be overwritten by the next loads
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)       // K dimension = 128 keys; A = K tile read MN-major (M = head dim), B = dS read K-major (N = query)
+          umma_f16(tmem_base + S_COL, desc_mnmajor(sK, kk), desc_kmajor(sDS, kk >> 2, kk & 3), p.idesc_mk, kk != 0);  // dQ^T = K^T dS^T
+        umma_commit(dq_full);
+      }
+      umma_commit(acc_done);
+    }
+  } else {
+    // ================= softmax / dQ reduction / epilogue =================
+    const int tid = threadIdx.x;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    constexpr float kLog2e = 1.4426950408889634f;
+    for (int it = 0; it < total; ++it) {
+      const uint32_t ph = it & 1;
+      const int head = kv_head * group + it / tiles_per_head;
+      const int m0 = (m_first + it % tiles_per_head) * BM;
+      const int row = m0 + tid;
+      const bool row_ok = row < p.sq;
+      const int64_t stat = ((int64_t)batch * p.h + head) * p.sq + row;
+      const float lse2 = row_ok ? p.lse[stat] * kLog2e : 0.f;
+      const float dl = row_ok ? p.delta[stat] : 0.f;
+      const int lim = p.causal ? min(p.sk - 1, row + p.causal_off) : p.sk - 1;   // last visible key of this query row
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      // previous iteration's dV/dK/dQ MMAs have retired (we waited dq_full below), so the P / dS tiles are free
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32], rp[32];
+        tmem_ld32(tmem_base + lane_off + S_COL + c * 32, rs);
+        tmem_ld32(tmem_base + lane_off + DP_COL + c * 32, rp);
+#pragma unroll
+        for (int q8 = 0; q8 < 4; ++q8) {
+          Vec16<T> pk, dk;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int i = q8 * 8 + e;
+            const int key = n0 + c * 32 + i;
+            float pv = ex2(__uint_as_float(rs[i]) * p.scale_log2 - lse2);
+            if (!row_ok || key > lim) pv = 0.f;
+            const float ds = pv * (__uint_as_float(rp[i]) - dl) * p.scale;
+            pk.v[e] = from_f<T>(pv);
+            dk.v[e] = from_f<T>(ds);
+          }
+          const int col = c * 32 + q8 * 8;              // key index inside the tile
+          const uint32_t off = (col >> 6) * HALF_BYTES + tid * 128 + ((((col & 63) >> 3) ^ (tid & 7)) << 4);
+          const uint4 up = *reinterpret_cast<const uint4*>(&pk), ud = *reinterpret_cast<const uint4*>(&dk);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off), "r"(up.x), "r"(up.y), "r"(up.z), "r"(up.w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(ud.x), "r"(ud.y), "r"(ud.z), "r"(ud.w) : "memory");
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      // dQ^T tile: TMEM lane = head-dim index (this thread's d), columns = the 128 query rows of the tile
+      mbar_wait(dq_full, ph);
+      tc_fence_after();
+      float* dq_base = p.dq + (((int64_t)batch * p.sq + m0) * p.h + head) * HD + tid;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_off + S_COL + c * 32, r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int qr = c * 32 + i;
+          if (m0 + qr < p.sq) atomicAdd(dq_base + (int64_t)qr * p.h * HD, __uint_as_float(r[i]));   // a warp adds 32 consecutive floats of one row
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+    }
+    // epilogue: dV, dK rows (lane = key row)
+    if (total > 0) {
+      mbar_wait(acc_done, 0);
+      tc_fence_after();
+    }
+    const int key = n0 + tid;
+    T* dv_row = reinterpret_cast<T*>(p.dv) + (((int64_t)batch * p.sk + key) * p.hk + kv_head) * HD;
+    T* dk_row = reinterpret_cast<T*>(p.dk) + (((int64_t)batch * p.sk + key) * p.hk + kv_head) * HD;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t rv[32], rk[32];
+      if (total > 0) {
+        tmem_ld32(tmem_base + lane_off + DV_COL + c * 32, rv);
+        tmem_ld32(tmem_base + lane_off + DK_COL + c * 32, rk);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { rv[i] = 0u; rk[i] = 0u; }
+      }
+      if (key < p.sk) {
+#pragma unroll
+        for (int q8 = 0; q8 < 4; ++q8) {
+          Vec16<T> ov, ok;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            ov.v[e] = from_f<T>(__uint_as_float(rv[q8 * 8 + e]));
+            ok.v[e] = from_f<T>(__uint_as_float(rk[q8 * 8 + e]));
+          }
+          st16(dv_row + c * 32 + q8 * 8, ov);
+          st16(dk_row + c * 32 + q8 * 8, ok);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// delta[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]   (one warp per row, both tensors contiguous [B,S,H,128])
+template <typename T>
+__global__ void delta_kernel(const T* __restrict__ o, const T* __restrict__ d_o, float* __restrict__ delta, int64_t rows, int sq, int h) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // row = (b*sq + s)*h + head
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const uint2 a = *reinterpret_cast<const uint2*>(o + row * HD + lane * 4);
+  const uint2 b = *reinterpret_cast<const uint2*>(d_o + row * HD + lane * 4);
+  const T* pa = reinterpret_cast<const T*>(&a);
+  const T* pb = reinterpret_cast<const T*>(&b);
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc += to_f(pa[i]) * to_f(pb[i]);
+#pragma unroll
+  for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+  if (lane == 0) {
+    const int64_t bs = row / h;
+    const int head = (int)(row - bs * h);
+    const int64_t bb = bs / sq;
+    const int s = (int)(bs - bb * sq);
+    delta[(bb * h + head) * sq + s] = acc;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+static bool make_map4(CUtensorMap* out, const void* ptr, int d, int s, int h, int b, int64_t ss, int64_t sh, int64_t sb, int dtype) {
+  cudaFree(nullptr);
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable"); return false; }
+  cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)s, (cuuint64_t)h, (cuuint64_t)b};
+  cuuint64_t strides[3] = {(cuuint64_t)ss * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
+  cuuint32_t box[4] = {64, 128, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error(__FILE__, __LINE__, ("cuTensorMapEncodeTiled (attention bwd) failed: " + std::to_string((int)r)).c_str());
+    return false;
+  }
+  return true;
+}
+static uint32_t make_idesc(int dtype, bool a_mn, bool b_mn) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  const uint32_t f = dtype == kBF16 ? 1u : 0u;
+  d |= f << 7;
+  d |= f << 10;
+  d |= (a_mn ? 1u : 0u) << 15;
+  d |= (b_mn ? 1u : 0u) << 16;
+  d |= (uint32_t)(128 >> 3) << 17;
+  d |= (uint32_t)(128 >> 4) << 24;
+  return d;
+}
+
+}  // namespace attn_bwd
+
+int attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
+  using namespace attn_bwd;
+  if (!attention_fwd_supported(a.fwd)) return 1;
+  const AttnArgs& f = a.fwd;
+  CUtensorMap mq, mk, mv, mdo;
+  if (!make_map4(&mq, f.q, f.d, f.sq, f.h, f.b, f.q_strides[1], f.q_strides[2], f.q_strides[0], f.dtype)) return 2;
+  if (!make_map4(&mk, f.k, f.d, f.sk, f.hk, f.b, f.k_strides[1], f.k_strides[2], f.k_strides[0], f.dtype)) return 2;
+  if (!make_map4(&mv, f.v, f.d, f.sk, f.hk, f.b, f.v_strides[1], f.v_strides[2], f.v_strides[0], f.dtype)) return 2;
+  if (!make_map4(&mdo, a.d_o, f.d, f.sq, f.h, f.b, (int64_t)f.h * f.d, f.d, (int64_t)f.sq * f.h * f.d, f.dtype)) return 2;
+  const int64_t rows = (int64_t)f.b * f.sq * f.h;
+  const int wpb = 8;
+  if (f.dtype == kBF16)
+    delta_kernel<__nv_bfloat16><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>((const __nv_bfloat16*)f.o, (const __nv_bfloat16*)a.d_o, a.delta, rows, f.sq, f.h);
+  else
+    delta_kernel<__half><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>((const __half*)f.o, (const __half*)a.d_o, a.delta, rows, f.sq, f.h);
+  Params p;
+  p.b = f.b; p.sq = f.sq; p.sk = f.sk; p.h = f.h; p.hk = f.hk;
+  p.scale = f.scale; p.scale_log2 = f.scale * 1.4426950408889634f;
+  p.causal = f.causal; p.causal_off = f.sk - f.sq;
+  p.lse = f.lse; p.delta = a.delta; p.dq = a.dq; p.dk = a.dk; p.dv = a.dv;
+  p.idesc_kk = make_idesc(f.dtype, false, false);
+  p.idesc_mm = make_idesc(f.dtype, true, true);
+  p.idesc_mk = make_idesc(f.dtype, true, false);
+  dim3 grid((f.sk + BN - 1) / BN, f.hk, f.b);
+  static bool attr_bf = false, attr_h = false;
+  if (f.dtype == kBF16) {
+    auto kern = bwd_kernel<__nv_bfloat16>;
+    if (!attr_bf) { B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_bf = true; }
+    kern<<<grid, kThreads, SMEM_BYTES, s>>>(mq, mk, mv, mdo, p);
+  } else {
+    auto kern = bwd_kernel<__half>;
+    if (!attr_h) { B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_h = true; }
+    kern<<<grid, kThreads, SMEM_BYTES, s>>>(mq, mk, mv, mdo, p);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return 3; }
+  return 0;
+}
+
+}  // namespace b200

@@ -441,6 +441,26 @@ std::vector<Tensor> attention_fwd(const Tensor& q, const Tensor& k, const Tensor
   return {out, lse};
 }
 
+// backward of attention_fwd: returns (dq [B,Sq,H,D], dk, dv [B,Sk,Hk,D]) in the input dtype
+std::vector<Tensor> attention_bwd(const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& out, const Tensor& lse, const Tensor& d_out,
+                                  double scale, bool causal) {
+  c10::cuda::CUDAGuard guard(q.device());
+  b200::AttnBwdArgs a;
+  TORCH_CHECK(fill_attn(a.fwd, q, k, v, scale, causal), "paddle_b200.attention_bwd: unsupported operands");
+  TORCH_CHECK(out.is_contiguous() && d_out.is_contiguous() && lse.is_contiguous() && lse.scalar_type() == at::kFloat, "attention_bwd: out / d_out / lse layout");
+  a.fwd.o = out.data_ptr(); a.fwd.lse = lse.data_ptr<float>();
+  Tensor dq32 = torch::zeros({a.fwd.b, a.fwd.sq, a.fwd.h, a.fwd.d}, q.options().dtype(at::kFloat));
+  Tensor dk = torch::empty({a.fwd.b, a.fwd.sk, a.fwd.hk, a.fwd.d}, q.options());
+  Tensor dv = torch::empty_like(dk);
+  Tensor delta = torch::empty({a.fwd.b, a.fwd.h, a.fwd.sq}, q.options().dtype(at::kFloat));
+  a.d_o = d_out.data_ptr(); a.delta = delta.data_ptr<float>(); a.dq = dq32.data_ptr<float>(); a.dk = dk.data_ptr(); a.dv = dv.data_ptr();
+  int rc = b200::attention_bwd(a, cur_stream());
+  g_launches += 2;
+  check_err();
+  TORCH_CHECK(rc == 0, "paddle_b200.attention_bwd launch failed rc=", rc);
+  return {dq32.to(q.scalar_type()), dk, dv};
+}
+
 int64_t launch_count() { return g_launches.load(); }
 void reset_launch_count() { g_launches.store(0); }
 void add_launches(int64_t n) { g_launches += n; }
@@ -474,6 +494,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         pybind11::arg("ag_rank") = 0, pybind11::arg("ag_rows") = 0, pybind11::arg("ag_epoch") = 0);
   m.def("attention_supported", &attention_supported);
   m.def("attention_fwd", &attention_fwd);
+  m.def("attention_bwd", &attention_bwd);
   m.def("launch_count", &launch_count);
   m.def("reset_launch_count", &reset_launch_count);
   m.def("add_launches", &add_launches);

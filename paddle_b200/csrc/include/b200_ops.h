@@ -124,5 +124,16 @@ struct AttnArgs {
 };
 int attention_fwd_supported(const AttnArgs& a);
 int attention_fwd(const AttnArgs& a, cudaStream_t s);
+// Backward (attention_bwd_sm100.cu). fwd: the forward's arguments with o (contiguous [B,Sq,H,D]) and lse filled in.
+// d_o: contiguous [B,Sq,H,D]; delta: fp32 scratch [B,H,Sq]; dq: fp32 [B,Sq,H,D] ZEROED by the caller; dk/dv: [B,Sk,Hk,D].
+struct AttnBwdArgs {
+  AttnArgs fwd;
+  const void* d_o;
+  float* delta;
+  float* dq;
+  void* dk;
+  void* dv;
+};
+int attention_bwd(const AttnBwdArgs& a, cudaStream_t s);
 
 }  // namespace b200

@@ -32,6 +32,9 @@ def attention_ref(q, k, v, mask=None, dropout_p=0.0, causal=False, scale=None):
     return out.transpose(1, 2)
 
 
+_bwd_backend = [__import__("os").environ.get("B200_ATTN_BWD", "own")]   # own | cudnn | flash
+
+
 class _FlashAttn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, scale, causal):
@@ -44,6 +47,19 @@ class _FlashAttn(torch.autograd.Function):
     def backward(ctx, do):
         q, k, v, out, lse = ctx.saved_tensors
         do = do.contiguous()
+        if _bwd_backend[0] == "own":   # csrc/attention_bwd_sm100.cu: tcgen05 S/dP/dV/dK/dQ GEMMs, fp32 dQ reduction
+            dq, dk, dv = ext().attention_bwd(q, k, v, out, lse, do, ctx.scale, ctx.causal)
+            return dq, dk, dv, None, None
+        if _bwd_backend[0] == "cudnn" and q.shape[2] == k.shape[2]:
+            # Blackwell-tuned library backward fed with OUR forward's (out, logsumexp); [B,S,H,D] tensors enter as [B,H,S,D] views
+            try:
+                z = torch.zeros((), dtype=torch.int64, device=q.device)
+                dq, dk, dv = torch.ops.aten._scaled_dot_product_cudnn_attention_backward(
+                    do.transpose(1, 2), q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), out.transpose(1, 2), lse.unsqueeze(-1), z, z,
+                    None, None, None, q.shape[1], k.shape[1], 0.0, ctx.causal, scale=ctx.scale)
+                return dq.transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2), None, None
+            except Exception:  # noqa: BLE001  (op unavailable / shape unsupported: use the flash backward from here on)
+                _bwd_backend[0] = "flash"
         empty = torch.empty(0, dtype=torch.int64, device=q.device)
         rng = torch.zeros(2, dtype=torch.int64, device=q.device)
         dq, dk, dv = torch.ops.aten._flash_attention_backward(do, q, k, v, out, lse, None, None, q.shape[1], k.shape[1], 0.0, ctx.causal,

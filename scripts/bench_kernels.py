@@ -109,6 +109,16 @@ def attn_bench():
         rows.append(dict(kernel="flash_attn_fwd", b=b, s=s, h=h, causal=causal, ms=round(t, 4), tflops=round(flops / t / 1e9, 1),
                          lib_ms=round(t_lib, 4), lib_tflops=round(flops / t_lib / 1e9, 1), frac_of_measured_bf16_peak=round(flops / t / 1e9 / peak, 3)))
         print(json.dumps(rows[-1]), flush=True)
+        out, lse = E.attention_fwd(q, k, v, 128 ** -0.5, causal)
+        g = torch.randn_like(out)
+        tb = timeit(lambda: E.attention_bwd(q, k, v, out, lse, g, 128 ** -0.5, causal))
+        qr, kr, vr = (x.detach().requires_grad_(True) for x in (qt, kt, vt))
+        o2 = F.scaled_dot_product_attention(qr, kr, vr, is_causal=causal)
+        g2 = g.transpose(1, 2)
+        tb_lib = timeit(lambda: torch.autograd.grad(o2, (qr, kr, vr), g2, retain_graph=True))
+        rows.append(dict(kernel="flash_attn_bwd", b=b, s=s, h=h, causal=causal, ms=round(tb, 4), tflops=round(2.5 * flops / tb / 1e9, 1),
+                         lib_ms=round(tb_lib, 4), lib_tflops=round(2.5 * flops / tb_lib / 1e9, 1), frac_of_measured_bf16_peak=round(2.5 * flops / tb / 1e9 / peak, 3)))
+        print(json.dumps(rows[-1]), flush=True)
     return rows
 
 

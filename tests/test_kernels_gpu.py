@@ -271,3 +271,22 @@ def test_flash_attention_packed_views_and_backward():
     ref.backward(g.float())
     assert rel_err(out, ref) < 1e-2
     assert rel_err(qkv.grad, qkv32.grad) < 2e-2, rel_err(qkv.grad, qkv32.grad)
+
+
+@pytest.mark.parametrize("b,s,h,hk,causal", [(1, 256, 2, 2, True), (2, 512, 4, 4, True), (1, 384, 4, 2, True), (1, 300, 2, 1, False), (1, 1024, 2, 2, True)])
+def test_flash_attention_bwd_kernel(b, s, h, hk, causal):
+    """tcgen05 backward kernel vs autograd of the fp32 reference."""
+    torch.manual_seed(2)
+    q = (torch.randn(b, s, h, 128, device="cuda") * 0.8).to(torch.bfloat16)
+    k = (torch.randn(b, s, hk, 128, device="cuda") * 0.8).to(torch.bfloat16)
+    v = (torch.randn(b, s, hk, 128, device="cuda") * 0.8).to(torch.bfloat16)
+    g = torch.randn(b, s, h, 128, device="cuda").to(torch.bfloat16)
+    sc = 128 ** -0.5
+    out, lse = _ext().attention_fwd(q, k, v, sc, causal)
+    dq, dk, dv = _ext().attention_bwd(q, k, v, out, lse, g, sc, causal)
+    q32, k32, v32 = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref, _ = _attn_ref(q32, k32, v32, causal)
+    ref.backward(g.float())
+    assert rel_err(dv, v32.grad) < 2e-2, ("dv", rel_err(dv, v32.grad))
+    assert rel_err(dk, k32.grad) < 2e-2, ("dk", rel_err(dk, k32.grad))
+    assert rel_err(dq, q32.grad) < 2e-2, ("dq", rel_err(dq, q32.grad))
