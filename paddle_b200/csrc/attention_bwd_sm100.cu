@@ -118,6 +118,16 @@ __device__ __forceinline__ float ex2(float x) {
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kb, int k) { return make_desc(tile + kb * HALF_BYTES + k * 32, 16, 1024); }
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kk) { return make_desc(tile + kk * 2048, HALF_BYTES, 1024); }
 
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  const __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
 struct Params {
   int b, sq, sk, h, hk;
   float scale, scale_log2;
@@ -125,8 +135,9 @@ struct Params {
   const float* lse;      // [B,H,Sq] natural log
   const float* delta;    // [B,H,Sq]
   float* dq;             // fp32 [B,Sq,H,D] (zero-initialised; reduced with atomics)
-  void* dk;              // [B,Sk,Hk,D] contiguous
+  void* dk;              // [B,Sk,Hk,D] with element strides (dkv_sb, dkv_ss, dkv_sh): may be slices of a packed dQKV tensor
   void* dv;
+  int64_t dkv_sb, dkv_ss, dkv_sh;
   uint32_t idesc_kk;     // A K-major, B K-major   (S, dP)
   uint32_t idesc_mm;     // A MN-major, B MN-major (dV, dK)
   uint32_t idesc_mk;     // A MN-major, B K-major  (dQ^T)
@@ -253,22 +264,26 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         tmem_ld32(tmem_base + lane_off + DP_COL + c * 32, rp);
 #pragma unroll
         for (int q8 = 0; q8 < 4; ++q8) {
-          Vec16<T> pk, dk;
+          uint32_t up[4], ud[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int i = q8 * 8 + e;
-            const int key = n0 + c * 32 + i;
-            float pv = ex2(__uint_as_float(rs[i]) * p.scale_log2 - lse2);
-            if (!row_ok || key > lim) pv = 0.f;
-            const float ds = pv * (__uint_as_float(rp[i]) - dl) * p.scale;
-            pk.v[e] = from_f<T>(pv);
-            dk.v[e] = from_f<T>(ds);
+          for (int e = 0; e < 4; ++e) {
+            float pv[2], ds[2];
+#pragma unroll
+            for (int t2 = 0; t2 < 2; ++t2) {
+              const int i = q8 * 8 + 2 * e + t2;
+              const int key = n0 + c * 32 + i;
+              float x = ex2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse2));
+              if (!row_ok || key > lim) x = 0.f;
+              pv[t2] = x;
+              ds[t2] = x * (__uint_as_float(rp[i]) - dl) * p.scale;
+            }
+            up[e] = pack2<T>(pv[0], pv[1]);
+            ud[e] = pack2<T>(ds[0], ds[1]);
           }
           const int col = c * 32 + q8 * 8;              // key index inside the tile
           const uint32_t off = (col >> 6) * HALF_BYTES + tid * 128 + ((((col & 63) >> 3) ^ (tid & 7)) << 4);
-          const uint4 up = *reinterpret_cast<const uint4*>(&pk), ud = *reinterpret_cast<const uint4*>(&dk);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off), "r"(up.x), "r"(up.y), "r"(up.z), "r"(up.w) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(ud.x), "r"(ud.y), "r"(ud.z), "r"(ud.w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off), "r"(up[0]), "r"(up[1]), "r"(up[2]), "r"(up[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(ud[0]), "r"(ud[1]), "r"(ud[2]), "r"(ud[3]) : "memory");
         }
       }
       fence_proxy_async();
@@ -278,18 +293,27 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       // dQ^T tile: TMEM lane = head-dim index (this thread's d), columns = the 128 query rows of the tile
       mbar_wait(dq_full, ph);
       tc_fence_after();
-      float* dq_base = p.dq + (((int64_t)batch * p.sq + m0) * p.h + head) * HD + tid;
+      // Transpose through shared memory (the P + dS tiles are free: every MMA of this iteration has retired) into a row-major
+      // fp32 [query][d] tile, then let the TMA engine reduce each 512-byte row into dQ (cp.reduce.async.bulk ... add.f32):
+      // 128 bulk reductions per tile instead of 16K scalar atomics.
+      const uint32_t sDQ = sP;   // 64 KB: sP and sDS are adjacent
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_base + lane_off + S_COL + c * 32, r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int qr = c * 32 + i;
-          if (m0 + qr < p.sq) atomicAdd(dq_base + (int64_t)qr * p.h * HD, __uint_as_float(r[i]));   // a warp adds 32 consecutive floats of one row
-        }
+        for (int i = 0; i < 32; ++i)
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(sDQ + (uint32_t)(c * 32 + i) * 512u + (uint32_t)tid * 4u), "r"(r[i]) : "memory");
       }
       tc_fence_before();
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 softmax warps only
+      if (m0 + tid < p.sq) {
+        float* dst = p.dq + (((int64_t)batch * p.sq + m0 + tid) * p.h + head) * HD;
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 512;" ::"l"(dst), "r"(sDQ + (uint32_t)tid * 512u) : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tile in shared memory may be overwritten
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);
     }
@@ -299,8 +323,9 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       tc_fence_after();
     }
     const int key = n0 + tid;
-    T* dv_row = reinterpret_cast<T*>(p.dv) + (((int64_t)batch * p.sk + key) * p.hk + kv_head) * HD;
-    T* dk_row = reinterpret_cast<T*>(p.dk) + (((int64_t)batch * p.sk + key) * p.hk + kv_head) * HD;
+    const int64_t kv_off = (int64_t)batch * p.dkv_sb + (int64_t)key * p.dkv_ss + (int64_t)kv_head * p.dkv_sh;
+    T* dv_row = reinterpret_cast<T*>(p.dv) + kv_off;
+    T* dk_row = reinterpret_cast<T*>(p.dk) + kv_off;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t rv[32], rk[32];
@@ -424,6 +449,7 @@ int attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
   p.scale = f.scale; p.scale_log2 = f.scale * 1.4426950408889634f;
   p.causal = f.causal; p.causal_off = f.sk - f.sq;
   p.lse = f.lse; p.delta = a.delta; p.dq = a.dq; p.dk = a.dk; p.dv = a.dv;
+  p.dkv_sb = a.dkv_strides[0]; p.dkv_ss = a.dkv_strides[1]; p.dkv_sh = a.dkv_strides[2];
   p.idesc_kk = make_idesc(f.dtype, false, false);
   p.idesc_mm = make_idesc(f.dtype, true, true);
   p.idesc_mk = make_idesc(f.dtype, true, false);

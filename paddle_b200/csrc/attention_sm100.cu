@@ -7,7 +7,8 @@
 // (python/paddle/nn/functional/flash_attention.py -> phi flash_attn kernels calling the flash-attention library).
 //
 // CTA = 128 query rows of one (batch, head).  Warps 0-3: softmax + epilogue, warp 4: TMA producer, warp 5: TMEM alloc + MMA issuer.
-// TMEM columns: [0,128) S buffer 0, [128,256) S buffer 1, [256,384) O accumulator.
+// TMEM columns: [0,128) S buffer 0, [128,256) S buffer 1, [256,384) O accumulator.  P is double-buffered in shared memory so
+// the softmax of tile j+1 overlaps the P V MMA of tile j (it only waits for that MMA when a row maximum really moved).
 #include <cuda.h>
 #include <cstdio>
 #include <string>
@@ -22,7 +23,7 @@ constexpr int BM = 128, BN = 128, HD = 128;
 constexpr int kThreads = 192;
 constexpr uint32_t TILE_BYTES = 128 * 128 * 2;   // 32 KB: every operand tile (Q, K, V, P)
 constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;  // one 64-wide K-block of a tile
-constexpr uint32_t SMEM_BYTES = 6 * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t SMEM_BYTES = 7 * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;   // Q, 2x K, 2x V, 2x P
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t O_COL = 256;
 
@@ -120,6 +121,16 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  const __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
 struct Params {
   int b, sq, sk, h, hk;
   float scale_log2;
@@ -138,18 +149,21 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sQ = base, sP = base + 5 * TILE_BYTES;
+  const uint32_t sQ = base;
+  auto sP = [&](int s) { return base + (5 + s) * TILE_BYTES; };
   auto sK = [&](int s) { return base + (1 + s) * TILE_BYTES; };
   auto sV = [&](int s) { return base + (3 + s) * TILE_BYTES; };
-  const uint32_t bars = base + 6 * TILE_BYTES;
-  const uint32_t q_full = bars, p_full = bars + 8 * 13, pv_done = bars + 8 * 14;
+  const uint32_t bars = base + 7 * TILE_BYTES;
+  const uint32_t q_full = bars, pv_done = bars + 8 * 13;
+  auto p_full = [&](int s) { return bars + 8u * (14 + s); };
+  auto p_free = [&](int s) { return bars + 8u * (16 + s); };
   auto k_full = [&](int s) { return bars + 8u * (1 + s); };
   auto v_full = [&](int s) { return bars + 8u * (3 + s); };
   auto k_empty = [&](int s) { return bars + 8u * (5 + s); };
   auto v_empty = [&](int s) { return bars + 8u * (7 + s); };
   auto s_full = [&](int s) { return bars + 8u * (9 + s); };
   auto s_empty = [&](int s) { return bars + 8u * (11 + s); };
-  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + 6 * TILE_BYTES + 8 * 15);
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + 7 * TILE_BYTES + 8 * 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = (int)gridDim.x - 1 - (int)blockIdx.x;   // long (late) rows first under the causal mask
@@ -170,8 +184,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     for (int s = 0; s < 2; ++s) {
       mbar_init(k_full(s), 1); mbar_init(v_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_empty(s), 1);
       mbar_init(s_full(s), 1); mbar_init(s_empty(s), 4);
+      mbar_init(p_full(s), 4); mbar_init(p_free(s), 1);
     }
-    mbar_init(p_full, 4);
     mbar_init(pv_done, 1);
     fence_barrier_init();
     fence_proxy_async();
@@ -228,16 +242,17 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       for (int j = 0; j < n_tiles; ++j) {
         if (j + 1 < n_tiles) issue_qk(j + 1);     // S(j+1) is computed while the softmax warps work on S(j)
         const int s = j & 1;
-        mbar_wait(p_full, j & 1);
+        mbar_wait(p_full(s), (j >> 1) & 1);
         mbar_wait(v_full(s), (j >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_base + O_COL, make_desc(sP + kb * HALF_BYTES + k * 32, 16, 1024),
+            umma_f16(tmem_base + O_COL, make_desc(sP(s) + kb * HALF_BYTES + k * 32, 16, 1024),
                      make_desc(sV(s) + kb * HALF_BYTES + k * 2048, 8192, 1024), p.idesc_pv, (j | kb | k) != 0);
         umma_commit(pv_done);
+        umma_commit(p_free(s));
         umma_commit(v_empty(s));
       }
     }
@@ -257,7 +272,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         uint32_t r[32];
         tmem_ld32(tmem_base + lane_off + sb * BN + c * 32, r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(r[i]) * p.scale_log2;
+        for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(r[i]);   // raw logits; the softmax scale is folded into the exp2 FFMA
       }
       tc_fence_before();
       __syncwarp();
@@ -269,18 +284,22 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         for (int i = 0; i < BN; ++i)
           if (n0 + i > lim) s[i] = -INFINITY;
       }
-      float mx = s[0];
+      // one softmax warp per scheduler: keep dependent chains short (8 independent partial maxima, then a tree)
+      float mxp[8];
 #pragma unroll
-      for (int i = 1; i < BN; ++i) mx = fmaxf(mx, s[i]);
+      for (int i = 0; i < 8; ++i) mxp[i] = s[i];
+#pragma unroll
+      for (int i = 8; i < BN; ++i) mxp[i & 7] = fmaxf(mxp[i & 7], s[i]);
+      const float mx = fmaxf(fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])), fmaxf(fmaxf(mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7]))) * p.scale_log2;   // scale > 0
       float m_new = fmaxf(m_i, mx);
       if (m_new == -INFINITY) m_new = 0.f;          // fully masked so far: keep exp2 finite
       if (j == 0) {
         m_i = m_new;
       } else {
-        mbar_wait(pv_done, (j - 1) & 1);            // O(j-1) final in TMEM, P buffer free
-        tc_fence_after();
         const bool need = (m_new - m_i) > 8.f;      // lazy rescale: keep a stale max while exp2 stays <= 2^8
-        if (__any_sync(0xffffffffu, need)) {
+        if (__any_sync(0xffffffffu, need)) {         // rare: only then must P V (j-1) have landed in TMEM before we touch O
+          mbar_wait(pv_done, (j - 1) & 1);
+          tc_fence_after();
           const float alpha = need ? ex2(m_i - m_new) : 1.f;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -294,29 +313,33 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
           if (need) m_i = m_new;
         }
       }
-      float sum = 0.f;
+      mbar_wait(p_free(sb), ((j >> 1) & 1) ^ 1);    // P V (j-2) has finished reading this P buffer
+      float sump[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sump[e] = 0.f;
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          Vec16<T> pk;
+          uint32_t u[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float pv = ex2(s[kb * 64 + c * 8 + e] - m_i);
-            sum += pv;
-            pk.v[e] = from_f<T>(pv);
+          for (int e = 0; e < 4; ++e) {
+            const float p0 = ex2(fmaf(s[kb * 64 + c * 8 + 2 * e], p.scale_log2, -m_i));
+            const float p1 = ex2(fmaf(s[kb * 64 + c * 8 + 2 * e + 1], p.scale_log2, -m_i));
+            sump[2 * e] += p0;
+            sump[2 * e + 1] += p1;
+            u[e] = pack2<T>(p0, p1);          // one cvt.rn.{bf16x2,f16x2}.f32 per pair
           }
           // K-major SWIZZLE_128B: row r at r*128 B, 16-byte chunk index XOR (r % 8)
-          const uint32_t addr = sP + kb * HALF_BYTES + tid * 128 + ((c ^ (tid & 7)) << 4);
-          const uint4 u = *reinterpret_cast<const uint4*>(&pk);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+          const uint32_t addr = sP(sb) + kb * HALF_BYTES + tid * 128 + ((c ^ (tid & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
         }
       }
-      l_i += sum;
+      l_i += ((sump[0] + sump[1]) + (sump[2] + sump[3])) + ((sump[4] + sump[5]) + (sump[6] + sump[7]));
       fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(p_full(sb));
     }
     if (n_tiles > 0) {
       mbar_wait(pv_done, (n_tiles - 1) & 1);

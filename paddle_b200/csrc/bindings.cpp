@@ -454,11 +454,37 @@ std::vector<Tensor> attention_bwd(const Tensor& q, const Tensor& k, const Tensor
   Tensor dv = torch::empty_like(dk);
   Tensor delta = torch::empty({a.fwd.b, a.fwd.h, a.fwd.sq}, q.options().dtype(at::kFloat));
   a.d_o = d_out.data_ptr(); a.delta = delta.data_ptr<float>(); a.dq = dq32.data_ptr<float>(); a.dk = dk.data_ptr(); a.dv = dv.data_ptr();
+  for (int i = 0; i < 3; ++i) a.dkv_strides[i] = dk.stride(i);
   int rc = b200::attention_bwd(a, cur_stream());
   g_launches += 2;
   check_err();
   TORCH_CHECK(rc == 0, "paddle_b200.attention_bwd launch failed rc=", rc);
   return {dq32.to(q.scalar_type()), dk, dv};
+}
+
+// packed variant: qkv [B,S,nh+2*nkv,D] (q heads | k heads | v heads); returns d(qkv) of the same shape, written in place by
+// the kernel (dk/dv slices) plus one cast-copy of the fp32 dq accumulator - no slice-backward zero fills / adds
+Tensor attention_bwd_packed(const Tensor& qkv, int64_t nh, int64_t nkv, const Tensor& out, const Tensor& lse, const Tensor& d_out, double scale,
+                            bool causal) {
+  c10::cuda::CUDAGuard guard(qkv.device());
+  TORCH_CHECK(qkv.dim() == 4 && qkv.is_contiguous() && qkv.size(2) == nh + 2 * nkv, "attention_bwd_packed: qkv layout");
+  Tensor q = qkv.narrow(2, 0, nh), k = qkv.narrow(2, nh, nkv), v = qkv.narrow(2, nh + nkv, nkv);
+  b200::AttnBwdArgs a;
+  TORCH_CHECK(fill_attn(a.fwd, q, k, v, scale, causal), "paddle_b200.attention_bwd_packed: unsupported operands");
+  TORCH_CHECK(out.is_contiguous() && d_out.is_contiguous() && lse.is_contiguous(), "attention_bwd_packed: out / d_out / lse layout");
+  a.fwd.o = out.data_ptr(); a.fwd.lse = lse.data_ptr<float>();
+  Tensor dqkv = torch::empty_like(qkv);
+  Tensor dk = dqkv.narrow(2, nh, nkv), dv = dqkv.narrow(2, nh + nkv, nkv);
+  Tensor dq32 = torch::zeros({a.fwd.b, a.fwd.sq, a.fwd.h, a.fwd.d}, qkv.options().dtype(at::kFloat));
+  Tensor delta = torch::empty({a.fwd.b, a.fwd.h, a.fwd.sq}, qkv.options().dtype(at::kFloat));
+  a.d_o = d_out.data_ptr(); a.delta = delta.data_ptr<float>(); a.dq = dq32.data_ptr<float>(); a.dk = dk.data_ptr(); a.dv = dv.data_ptr();
+  for (int i = 0; i < 3; ++i) a.dkv_strides[i] = dk.stride(i);
+  int rc = b200::attention_bwd(a, cur_stream());
+  g_launches += 2;
+  check_err();
+  TORCH_CHECK(rc == 0, "paddle_b200.attention_bwd_packed launch failed rc=", rc);
+  dqkv.narrow(2, 0, nh).copy_(dq32);
+  return dqkv;
 }
 
 int64_t launch_count() { return g_launches.load(); }
@@ -495,6 +521,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attention_supported", &attention_supported);
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_bwd", &attention_bwd);
+  m.def("attention_bwd_packed", &attention_bwd_packed);
   m.def("launch_count", &launch_count);
   m.def("reset_launch_count", &reset_launch_count);
   m.def("add_launches", &add_launches);

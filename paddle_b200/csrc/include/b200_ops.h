@@ -125,7 +125,7 @@ struct AttnArgs {
 int attention_fwd_supported(const AttnArgs& a);
 int attention_fwd(const AttnArgs& a, cudaStream_t s);
 // Backward (attention_bwd_sm100.cu). fwd: the forward's arguments with o (contiguous [B,Sq,H,D]) and lse filled in.
-// d_o: contiguous [B,Sq,H,D]; delta: fp32 scratch [B,H,Sq]; dq: fp32 [B,Sq,H,D] ZEROED by the caller; dk/dv: [B,Sk,Hk,D].
+// d_o: contiguous [B,Sq,H,D]; delta: fp32 scratch [B,H,Sq]; dq: fp32 [B,Sq,H,D] ZEROED by the caller; dk/dv: [B,Sk,Hk,D] views (dkv_strides).
 struct AttnBwdArgs {
   AttnArgs fwd;
   const void* d_o;
@@ -133,6 +133,7 @@ struct AttnBwdArgs {
   float* dq;
   void* dk;
   void* dv;
+  int64_t dkv_strides[3];   // element strides (batch, seq, head) of dk and dv (16-byte aligned rows)
 };
 int attention_bwd(const AttnBwdArgs& a, cudaStream_t s);
 

@@ -3,8 +3,8 @@
 
 Dispatch: the sm_100a tcgen05 flash kernel (csrc/attention_sm100.cu) for fp16/bf16, head_dim 128, no explicit mask and no
 dropout — it reads q/k/v in place as strided views of a packed QKV projection; everything else takes the PyTorch SDPA
-(library) path.  Backward of the fused forward re-uses the saved (out, logsumexp) with the library flash backward until the
-sm_100a backward kernel lands.
+(library) path.  Backward: csrc/attention_bwd_sm100.cu (B200_ATTN_BWD=own, default) or, for comparison, a library backward
+fed with our forward's (out, logsumexp) (B200_ATTN_BWD=cudnn|flash).
 """
 from __future__ import annotations
 
@@ -65,6 +65,35 @@ class _FlashAttn(torch.autograd.Function):
         dq, dk, dv = torch.ops.aten._flash_attention_backward(do, q, k, v, out, lse, None, None, q.shape[1], k.shape[1], 0.0, ctx.causal,
                                                                rng, empty, scale=ctx.scale)
         return dq, dk, dv, None, None
+
+
+class _FlashAttnPacked(torch.autograd.Function):
+    """Attention over a packed projection qkv [B,S,nh+2*nkv,D]: the kernels read q/k/v in place and the backward writes d(qkv)
+    in place (dk/dv slices straight from the kernel epilogue), so autograd never builds zero-filled slice gradients."""
+
+    @staticmethod
+    def forward(ctx, qkv, nh, nkv, scale, causal):
+        q, k, v = qkv[:, :, :nh], qkv[:, :, nh:nh + nkv], qkv[:, :, nh + nkv:]
+        out, lse = ext().attention_fwd(q, k, v, scale, causal)
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.cfg = (nh, nkv, scale, causal)
+        return out
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, out, lse = ctx.saved_tensors
+        nh, nkv, scale, causal = ctx.cfg
+        return ext().attention_bwd_packed(qkv, nh, nkv, out, lse, do.contiguous(), scale, causal), None, None, None, None
+
+
+def attention_packed(qkv, nh, nkv, causal=True, scale=None):
+    """qkv: [B,S,nh+2*nkv,D] contiguous (q heads | k heads | v heads). Returns [B,S,nh,D]."""
+    x = raw(qkv)
+    q, k, v = x[:, :, :nh], x[:, :, nh:nh + nkv], x[:, :, nh + nkv:]
+    if _bwd_backend[0] == "own" and x.is_contiguous() and fused_ok(q, k, v, None, 0.0, causal):
+        sc = float(scale) if scale is not None else 1.0 / math.sqrt(x.shape[-1])
+        return wrap(_FlashAttnPacked.apply(x, int(nh), int(nkv), sc, bool(causal)))
+    return attention(q, k, v, None, 0.0, causal, scale)
 
 
 def fused_ok(q, k, v, mask, dropout_p, causal):

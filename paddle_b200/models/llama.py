@@ -123,9 +123,7 @@ class LlamaAttention(nn.Layer):
         nh, nkv, hd = self.num_heads, self.num_kv_heads, self.head_dim
         total = nh + 2 * nkv
         qkv = KR.apply_rope_packed(qkv, cos, sin, nh + nkv, total, hd, position_ids, neox=True)
-        q4 = _raw(qkv).view(b, s, total, hd)
-        q, k, v = q4[:, :, :nh], q4[:, :, nh:nh + nkv], q4[:, :, nh + nkv:]
-        out = KAT.attention(q, k, v, None, 0.0, True, None)           # [B, S, nh, hd]
+        out = KAT.attention_packed(_raw(qkv).view(b, s, total, hd), nh, nkv, True, None)   # [B, S, nh, hd]; q/k/v read in place
         out = _raw(out).reshape(b, s, nh * hd)
         if cfg.sequence_parallel and self.mp > 1:
             out = out.transpose(0, 1).contiguous()

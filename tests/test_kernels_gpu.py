@@ -290,3 +290,20 @@ def test_flash_attention_bwd_kernel(b, s, h, hk, causal):
     assert rel_err(dv, v32.grad) < 2e-2, ("dv", rel_err(dv, v32.grad))
     assert rel_err(dk, k32.grad) < 2e-2, ("dk", rel_err(dk, k32.grad))
     assert rel_err(dq, q32.grad) < 2e-2, ("dq", rel_err(dq, q32.grad))
+
+
+def test_flash_attention_packed_api():
+    """attention_packed: q/k/v read in place from the packed projection, d(qkv) written in place by the backward kernel."""
+    from paddle_b200.kernels import attention as KAT
+
+    torch.manual_seed(3)
+    b, s, nh, nkv = 1, 640, 4, 4
+    qkv = (torch.randn(b, s, nh + 2 * nkv, 128, device="cuda") * 0.7).to(torch.bfloat16).requires_grad_(True)
+    out = KAT.attention_packed(qkv, nh, nkv, True, None)
+    g = torch.randn_like(out)
+    out.backward(g)
+    qkv32 = qkv.detach().float().requires_grad_(True)
+    ref, _ = _attn_ref(qkv32[:, :, :nh], qkv32[:, :, nh:nh + nkv], qkv32[:, :, nh + nkv:], True)
+    ref.backward(g.float())
+    assert rel_err(out, ref) < 1e-2
+    assert rel_err(qkv.grad, qkv32.grad) < 2e-2, rel_err(qkv.grad, qkv32.grad)
