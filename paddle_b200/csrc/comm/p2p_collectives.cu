@@ -239,6 +239,56 @@ __global__ void __launch_bounds__(kThreads) alltoall_kernel(Peers P, int64_t off
   }
 }
 
+// ---------------------------------------------------------------------------------------------- MoE dispatch / combine
+// Variable-size all-to-all with an optional row gather, fused into one push kernel (MoE expert dispatch: the routed copy
+// x[tok] is never materialised; combine: gather == nullptr).  Parity (role): global_scatter / global_gather
+// (paddle/fluid/operators/collective/global_scatter_op.cu.cc) which issue ncclSend/ncclRecv per (rank, expert).
+//   src            local rows [*, row_bytes]
+//   gather[i]      source row of sorted slot i (nullptr: slot i = row i)
+//   meta_off       byte offset of a symmetric int64 [world] array: THIS rank stored its send counts there before the launch
+//                  (send count to rank r = number of sorted slots destined to r; slots are grouped by destination rank)
+//   recv_off       byte offset of the symmetric receive buffer; rank r's buffer is filled in source-rank order, so the rows
+//                  this rank sends to r start at row sum_{s < me} count[s][r]  (read from the peers' meta arrays)
+__global__ void __launch_bounds__(kThreads) a2av_kernel(Peers P, const char* __restrict__ src, const int64_t* __restrict__ gather,
+                                                        int64_t meta_off, int64_t recv_off, int64_t row_bytes, int rank, int world,
+                                                        uint32_t epoch, uint32_t* counter) {
+  __shared__ int64_t seg_start[kMaxRanks + 1];   // first sorted slot going to rank r
+  __shared__ int64_t dst_row0[kMaxRanks];        // first row of rank r's receive buffer reserved for this rank
+  if (blockIdx.x == 0) {
+    __threadfence_system();
+    signal_all(P, rank, world, 0, epoch);        // my meta array is in place; my previous receive buffer has been consumed (stream order)
+  }
+  wait_all(P, rank, world, 0, epoch);
+  if (threadIdx.x == 0) {
+    const int64_t* mine = reinterpret_cast<const int64_t*>(P.base[rank] + meta_off);
+    int64_t acc = 0;
+    for (int r = 0; r < world; ++r) { seg_start[r] = acc; acc += mine[r]; }
+    seg_start[world] = acc;
+    for (int r = 0; r < world; ++r) {
+      int64_t before = 0;
+      for (int sr = 0; sr < rank; ++sr) before += reinterpret_cast<const volatile int64_t*>(P.base[sr] + meta_off)[r];
+      dst_row0[r] = before;
+    }
+  }
+  __syncthreads();
+  const int64_t total = seg_start[world];
+  const int vec_per_row = (int)(row_bytes / 16);
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < total; i += warps) {   // one warp per row
+    int r = 0;
+    while (i >= seg_start[r + 1]) ++r;
+    const int64_t srow = gather ? gather[i] : i;
+    const uint4* sp = reinterpret_cast<const uint4*>(src + srow * row_bytes);
+    uint4* dp = reinterpret_cast<uint4*>(P.base[r] + recv_off + (dst_row0[r] + (i - seg_start[r])) * row_bytes);
+    for (int v = lane; v < vec_per_row; v += 32) dp[v] = sp[v];
+  }
+  if (last_cta(counter)) {
+    signal_all(P, rank, world, 1, epoch);
+    wait_all(P, rank, world, 1, epoch);
+  }
+}
+
 static Peers make_peers(const int64_t* bases, int world) {
   Peers P;
   for (int r = 0; r < kMaxRanks; ++r) P.base[r] = r < world ? reinterpret_cast<char*>(bases[r]) : nullptr;
@@ -300,6 +350,14 @@ void p2p_alltoall(const int64_t* bases, int64_t off_send, int64_t off_recv, int6
   if (world > kMaxRanks || chunk_bytes % 16) { set_last_error(__FILE__, __LINE__, "p2p_alltoall: bad world/chunk"); return; }
   Peers P = make_peers(bases, world);
   alltoall_kernel<<<comm_grid(chunk_bytes / 16), kThreads, 0, s>>>(P, off_send, off_recv, chunk_bytes, rank, world, epoch, counter);
+  B200_CUDA_CHECK(cudaGetLastError());
+}
+
+void p2p_a2av(const int64_t* bases, const void* src, const int64_t* gather, int64_t meta_off, int64_t recv_off, int64_t row_bytes,
+              int64_t rows_hint, int rank, int world, uint32_t epoch, uint32_t* counter, cudaStream_t s) {
+  if (world > kMaxRanks || row_bytes % 16) { set_last_error(__FILE__, __LINE__, "p2p_a2av: bad world / row size"); return; }
+  Peers P = make_peers(bases, world);
+  a2av_kernel<<<comm_grid(rows_hint * 32), kThreads, 0, s>>>(P, (const char*)src, gather, meta_off, recv_off, row_bytes, rank, world, epoch, counter);
   B200_CUDA_CHECK(cudaGetLastError());
 }
 

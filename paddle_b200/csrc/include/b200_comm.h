@@ -18,5 +18,8 @@ void p2p_allgather(const int64_t* bases, int64_t off, int64_t chunk_bytes, int r
                    cudaStream_t s);
 void p2p_alltoall(const int64_t* bases, int64_t off_send, int64_t off_recv, int64_t chunk_bytes, int rank, int world, uint32_t epoch,
                   uint32_t* counter, cudaStream_t s);
+// MoE dispatch / combine: variable all-to-all push with optional row gather (see a2av_kernel). rows_hint sizes the grid.
+void p2p_a2av(const int64_t* bases, const void* src, const int64_t* gather, int64_t meta_off, int64_t recv_off, int64_t row_bytes,
+              int64_t rows_hint, int rank, int world, uint32_t epoch, uint32_t* counter, cudaStream_t s);
 }  // namespace comm
 }  // namespace b200

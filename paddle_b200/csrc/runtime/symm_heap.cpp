@@ -147,6 +147,15 @@ class SymmHeap {
     comm::p2p_allgather(b.data(), off, chunk_bytes, rank_, world_, (uint32_t)epoch, counter(), at::cuda::getCurrentCUDAStream().stream());
     finish();
   }
+  // src: local rows [*, H]; gather: optional int64 slot->row map; meta_off: symmetric int64[world] send counts; recv_off: receive buffer
+  void a2av(torch::Tensor src, c10::optional<torch::Tensor> gather, int64_t meta_off, int64_t recv_off, int64_t rows_hint, int64_t epoch) {
+    c10::cuda::CUDAGuard g(device_);
+    auto b = bases();
+    const int64_t row_bytes = src.size(-1) * src.element_size();
+    comm::p2p_a2av(b.data(), src.data_ptr(), gather.has_value() && gather->defined() ? gather->data_ptr<int64_t>() : nullptr, meta_off, recv_off,
+                   row_bytes, rows_hint, rank_, world_, (uint32_t)epoch, counter(), at::cuda::getCurrentCUDAStream().stream());
+    finish();
+  }
   void alltoall(int64_t off_send, int64_t off_recv, int64_t chunk_bytes, int64_t epoch) {
     c10::cuda::CUDAGuard g(device_);
     auto b = bases();
@@ -187,6 +196,7 @@ void bind_symm(pybind11::module_& m) {
       .def("reduce_scatter", &SymmHeap::reduce_scatter)
       .def("reduce_slots", &SymmHeap::reduce_slots)
       .def("allgather", &SymmHeap::allgather)
+      .def("a2av", &SymmHeap::a2av)
       .def("alltoall", &SymmHeap::alltoall);
 }
 

@@ -49,6 +49,12 @@ def _reduce_scatter(out, flat, group):
         n = out.numel()
         out.copy_(tmp[_rank(group) * n:(_rank(group) + 1) * n])
     else:
+        sc = _symm(group, flat)
+        if sc is not None:
+            from ..parallel import symm_ops
+
+            if symm_ops.reduce_scatter_into(sc, out, flat):   # peer-memory kernel over NVLink (no NCCL)
+                return
         dist.reduce_scatter_tensor(out, flat, group=pg)
 
 
@@ -58,7 +64,25 @@ def _all_gather(flat_out, shard, group):
         outs = list(flat_out.chunk(_world(group)))
         dist.all_gather(outs, shard.contiguous(), group=pg)
     else:
+        sc = _symm(group, flat_out)
+        if sc is not None:
+            from ..parallel import symm_ops
+
+            if symm_ops.all_gather_into(sc, flat_out, shard.contiguous()):
+                return
         dist.all_gather_into_tensor(flat_out, shard.contiguous(), group=pg)
+
+
+def _symm(group, t):
+    if not t.is_cuda or t.dtype not in (torch.bfloat16, torch.float16, torch.float32) or not t.is_contiguous():
+        return None
+    from ..framework.flags import flag
+
+    if not flag("FLAGS_b200_p2p_collectives", True):
+        return None
+    from ..parallel import symm
+
+    return symm.context_for(group)
 
 
 class _ShardedArena:

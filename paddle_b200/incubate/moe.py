@@ -113,6 +113,51 @@ def _a2a_single(x, in_splits, out_splits, group):
     return out
 
 
+def _symm_ctx(group, x):
+    """Peer-memory context for the expert-parallel group (None -> NCCL path)."""
+    if not x.is_cuda or x.dtype not in (torch.bfloat16, torch.float16, torch.float32) or (x.shape[-1] * x.element_size()) % 16:
+        return None
+    from ..framework.flags import flag
+
+    if not flag("FLAGS_b200_p2p_collectives", True):
+        return None
+    from ..parallel import symm
+
+    return symm.context_for(group)
+
+
+class _FusedDispatch(torch.autograd.Function):
+    """x[tok] + all-to-all in ONE peer-memory push kernel (csrc/comm/p2p_collectives.cu:a2av_kernel); backward = combine push
+    followed by the scatter-add into dx."""
+
+    @staticmethod
+    def forward(ctx, x, tok, in_splits, out_splits, sc, cap):
+        out = sc.a2av(x, in_splits, sum(out_splits), cap, gather=tok, tag="moe_dispatch")
+        ctx.cfg = (in_splits, out_splits, sc, x.shape[0], cap)
+        ctx.save_for_backward(tok)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        in_splits, out_splits, sc, n, cap = ctx.cfg
+        (tok,) = ctx.saved_tensors
+        rows = sc.a2av(g.contiguous(), out_splits, sum(in_splits), cap, tag="moe_combine")
+        dx = torch.zeros((n, g.shape[-1]), dtype=g.dtype, device=g.device).index_add_(0, tok, rows)
+        return dx, None, None, None, None, None
+
+
+class _FusedCombine(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, in_splits, out_splits, sc, cap):
+        ctx.cfg = (in_splits, out_splits, sc, cap)
+        return sc.a2av(y, in_splits, sum(out_splits), cap, tag="moe_combine")
+
+    @staticmethod
+    def backward(ctx, g):
+        in_splits, out_splits, sc, cap = ctx.cfg
+        return sc.a2av(g.contiguous(), out_splits, sum(in_splits), cap, tag="moe_dispatch"), None, None, None, None
+
+
 class _AllToAll(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, in_splits, out_splits, group):
@@ -353,7 +398,15 @@ class MoELayer(Layer):
                 global_count = torch.cat([l.reshape(self.world_size, self.num_expert)[me] for l in lst])
             else:
                 dist.all_to_all_single(global_count, local_count, group=pg)
-            xs = _raw(global_scatter(x[tok], local_count, global_count, self.group))
+            sc = _symm_ctx(self.group, x)
+            ins = local_count.reshape(self.world_size, self.num_expert).sum(1).tolist()
+            outs = global_count.reshape(self.world_size, self.num_expert).sum(1).tolist()
+            cap = sc.a2av_capacity(sum(ins), sum(outs), x) if sc is not None else 0
+            fused = cap > 0
+            if fused:   # gather + dispatch in one kernel, rows land directly in the expert ranks' HBM over NVLink
+                xs = _FusedDispatch.apply(x, tok, ins, outs, sc, cap)
+            else:
+                xs = _raw(global_scatter(x[tok], local_count, global_count, self.group))
             # received rows are ordered (src rank, local expert): regroup by local expert
             gc = global_count.reshape(self.world_size, self.num_expert)
             seg_e = torch.arange(self.num_expert, device=x.device).repeat(self.world_size)
@@ -363,7 +416,10 @@ class MoELayer(Layer):
             y = self._run_experts(xs[perm], counts)
             inv = torch.empty_like(perm)
             inv[perm] = torch.arange(perm.numel(), device=perm.device)
-            y = _raw(global_gather(y[inv], local_count, global_count, self.group))
+            if fused:
+                y = _FusedCombine.apply(y[inv].contiguous(), outs, ins, sc, cap)
+            else:
+                y = _raw(global_gather(y[inv], local_count, global_count, self.group))
         else:
             y = self._run_experts(x[tok], local_count.tolist())
         out = torch.zeros_like(x).index_add(0, tok, y * w[:, None].to(y.dtype))

@@ -158,14 +158,17 @@ class SymmContext:
 
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
         ml, k = x2.shape
-        full, off = self.buffer("agg", (ml * self.world, k), x.dtype)
-        full[self.rank * ml:(self.rank + 1) * ml].copy_(x2)
         nout = w.shape[0] if b_is_nk else w.shape[1]
-        if os.environ.get("B200_AG_FUSED", "1") == "1" and ml % 256 == 0 and k % 64 == 0 and nout >= 256 and KG._tc_ok(full, w, False, b_is_nk):
-            # one kernel: a copy warp per CTA pulls the peers' shards into `full` over NVLink (per-row-block flags) while the
-            # tensor cores start on the local rows; the TMA producers wait on the flag of a row block before loading it
-            shard_bytes = ml * k * x.element_size()
-            src = [self.heap.peer_ptr(r) + off + r * shard_bytes for r in range(self.world)]
+        if os.environ.get("B200_AG_FUSED", "1") == "1" and ml % 256 == 0 and k % 64 == 0 and nout >= 256 and KG._tc_ok(x2, w, False, b_is_nk):
+            # one kernel: a copy warp per CTA pulls the peers' shards over NVLink (per-row-block flags) while the tensor cores
+            # start on the local rows; the TMA producers wait on the flag of a row block before loading it.  Only this rank's
+            # shard lives in symmetric memory (the peers read it there); the gathered operand is an ordinary fresh tensor, so it
+            # can be handed to autograd for the weight-gradient GEMM without a copy.
+            shard, soff = self.buffer("agg_shard", (ml, k), x.dtype)
+            shard.copy_(x2)
+            gathered = torch.empty((ml * self.world, k), dtype=x.dtype, device=x.device)
+            gathered[self.rank * ml:(self.rank + 1) * ml].copy_(x2)
+            src = [self.heap.peer_ptr(r) + soff for r in range(self.world)]
             pads = [self.heap.peer_ptr(r) for r in range(self.world)]
             nblk = (ml * self.world) // 128
             fkey = ("agflags", nblk)
@@ -173,11 +176,13 @@ class SymmContext:
             if flags is None:
                 flags = self._bufs[fkey] = torch.zeros(nblk + 1, dtype=torch.int32, device=x.device)
             flags.zero_()
-            y = self.ext.gemm(full, w, None, False, b_is_nk, 0, None, None, [], 0, src, pads, flags, self.rank, ml, self.next_epoch())
+            y = self.ext.gemm(gathered, w, None, False, b_is_nk, 0, None, None, [], 0, src, pads, flags, self.rank, ml, self.next_epoch())
             y = y.reshape(x.shape[0] * self.world, *x.shape[1:-1], nout)
             if return_gathered:
-                return y, full.clone().reshape(x.shape[0] * self.world, *x.shape[1:])
+                return y, gathered.reshape(x.shape[0] * self.world, *x.shape[1:])
             return y
+        full, off = self.buffer("agg", (ml * self.world, k), x.dtype)
+        full[self.rank * ml:(self.rank + 1) * ml].copy_(x2)
         self.heap.allgather(off, ml * k * x.element_size(), self.next_epoch())
         y = KG.gemm(full, w, b_is_nk=b_is_nk)
         n = y.shape[-1]
@@ -185,3 +190,33 @@ class SymmContext:
         if return_gathered:
             return y, full.clone().reshape(x.shape[0] * self.world, *x.shape[1:])
         return y
+
+
+
+def _a2av(self, src, in_splits, out_rows, cap, gather=None, tag="a2av"):
+    """Variable all-to-all of rows over peer memory (one push kernel; MoE dispatch when `gather` maps sorted slots to source rows).
+    in_splits[r]: rows sent to rank r (slots grouped by destination); out_rows: rows this rank receives; cap: receive-buffer
+    capacity in rows, IDENTICAL on every rank (symmetric allocation) - see a2av_capacity. Returns [out_rows, H] ordered by source."""
+    h = src.shape[-1]
+    recv, roff = self.buffer((tag, "recv"), (cap, h), src.dtype)
+    meta, moff = self.buffer((tag, "meta"), (self.world,), torch.int64)
+    meta.copy_(torch.as_tensor(list(in_splits), dtype=torch.int64))
+    self.heap.a2av(src.contiguous(), gather, moff, roff, max(int(sum(in_splits)), 1), self.next_epoch())
+    return recv[:int(out_rows)].clone()
+
+
+def _a2av_capacity(self, rows_in, rows_out, x):
+    """Receive-buffer capacity (rows) agreed by all ranks with one tiny MAX all-reduce; 0 = does not fit -> NCCL path everywhere."""
+    h = x.shape[-1]
+    t = torch.tensor([max(int(rows_in), int(rows_out), 1)], device=x.device, dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=_pg(self.group))
+    need = int(t.item())
+    cap = 1024
+    while cap < 2 * need:
+        cap *= 2
+    limit = (self.heap.size() - self._base_cursor) // 8
+    return cap if cap * h * x.element_size() <= limit else 0
+
+
+SymmContext.a2av = _a2av
+SymmContext.a2av_capacity = _a2av_capacity

@@ -550,6 +550,42 @@ def case_p2p_kernels():
     dist.barrier()
 
 
+def case_moe_fused_a2a():
+    """MoE layer over the fused peer-memory dispatch/combine kernel == the NCCL global_scatter/global_gather path (fwd + grads)."""
+    assert GPU
+    dist.init_parallel_env()
+    r, w = dist.get_rank(), dist.get_world_size()
+    from paddle_b200.incubate.moe import ExpertFFN, MoELayer
+
+    grp = dist.collective._global_group()
+
+    def build():
+        paddle.seed(100 + r)
+        return MoELayer(256, ExpertFFN(2, 256, 512, activation="swiglu"), gate={"type": "naive", "top_k": 2}, moe_group=grp)
+
+    torch.manual_seed(7 + r)
+    x0 = (torch.randn(4, 96, 256, device="cuda") * 0.5).to(torch.bfloat16)
+    outs, grads = [], []
+    for fused in (True, False):
+        paddle.set_flags({"FLAGS_b200_p2p_collectives": fused})
+        paddle.set_default_dtype("bfloat16")
+        m = build()
+        paddle.set_default_dtype("float32")
+        x = x0.clone().as_subclass(paddle.Tensor)
+        x.stop_gradient = False
+        y = m(x)
+        (y.float() ** 2).mean().backward()
+        outs.append(y.as_subclass(torch.Tensor).float())
+        grads.append((x.grad.as_subclass(torch.Tensor).float(), m.experts.w1.grad.as_subclass(torch.Tensor).float()))
+    paddle.set_flags({"FLAGS_b200_p2p_collectives": True})
+    e = ((outs[0] - outs[1]).norm() / outs[1].norm()).item()
+    assert e < 1e-2, f"fused MoE forward {e}"
+    for a, b, name in ((grads[0][0], grads[1][0], "dx"), (grads[0][1], grads[1][1], "dw1")):
+        e = ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+        assert e < 2e-2, f"fused MoE {name} {e}"
+    dist.barrier()
+
+
 def case_mp_sp_bf16():
     """bf16 GPU run of the mp2+SP tiny Llama through the fused peer-memory paths: loss tracks the dense bf16 model."""
     assert GPU
@@ -619,6 +655,9 @@ def case_mp_sp_bf16():
 
 if __name__ == "__main__":
     case = sys.argv[1]
+    if GPU:
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        paddle.set_device(f"gpu:{os.environ['LOCAL_RANK']}")
     globals()["case_" + case]()
     if dist.is_initialized():
         dist.barrier()

@@ -30,3 +30,20 @@ def test_mp_sp_bf16_fused_paths():
 def test_pp_gpu():
     _need(2)
     run_dist("pp", 2, extra_env={"B200_TEST_GPU": "1"})
+
+
+def test_moe_fused_dispatch_combine():
+    _need(2)
+    run_dist("moe_fused_a2a", 2, extra_env={"B200_TEST_GPU": "1"})
+
+
+def test_data_parallel_gpu():
+    """DataParallel with the gradient slab in the symmetric heap (in-place peer-memory all-reduce per bucket)."""
+    _need(2)
+    run_dist("dp", 2, extra_env={"B200_TEST_GPU": "1"})
+
+
+def test_group_sharded_gpu():
+    """GroupSharded stage 2/3 over the windowed peer-memory reduce-scatter / all-gather."""
+    _need(2)
+    run_dist("sharding", 2, extra_env={"B200_TEST_GPU": "1"})
