@@ -11,7 +11,8 @@
 // strides; the K tile is likewise consumed K-major (S) and MN-major (dQ^T) from one copy.
 //
 // Parity (behaviour): flash_attn_grad (paddle/phi/kernels/gpu/flash_attn_grad_kernel.cu -> flash-attention library).
-// Warps 0-3: softmax / dQ reduction / epilogue, warp 4: TMA producer, warp 5: TMEM alloc + MMA issuer.
+// Warps 0-7: softmax / dQ reduction / epilogue (two warpgroups, one 64-column half each), warp 8: TMA producer,
+// warp 9: TMEM alloc + MMA issuer.
 // TMEM columns: [0,128) S then dQ^T, [128,256) dP, [256,384) dV, [384,512) dK.
 #include <cuda.h>
 #include <cstdio>
@@ -24,7 +25,7 @@ namespace b200 {
 namespace attn_bwd {
 
 constexpr int BM = 128, BN = 128, HD = 128;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warps 0-7: softmax / dQ / epilogue (2 warpgroups), warp 8: TMA producer, warp 9: TMEM alloc + MMA issuer
 constexpr uint32_t TILE_BYTES = 128 * 128 * 2;
 constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;
 constexpr uint32_t SMEM_BYTES = 6 * TILE_BYTES + 1024 + 256;
@@ -170,16 +171,16 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   const int tiles_per_head = num_m - m_first;
   const int total = tiles_per_head * group;    // iteration it -> (query head = kv_head*group + it / tiles_per_head, m tile = m_first + it % tiles_per_head)
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_do) : "memory");
-    mbar_init(kv_full, 1); mbar_init(qdo_full, 1); mbar_init(qdo_empty, 1); mbar_init(s_full, 1); mbar_init(s_free, 4);
-    mbar_init(pds_full, 4); mbar_init(dq_full, 1); mbar_init(acc_done, 1);
+    mbar_init(kv_full, 1); mbar_init(qdo_full, 1); mbar_init(qdo_empty, 1); mbar_init(s_full, 1); mbar_init(s_free, 8);
+    mbar_init(pds_full, 8); mbar_init(dq_full, 1); mbar_init(acc_done, 1);
     fence_barrier_init();
     fence_proxy_async();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -188,7 +189,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0 && total > 0) {
       // ================= TMA producer =================
       mbar_expect_tx(kv_full, 2 * TILE_BYTES);
@@ -207,7 +208,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         tma_load_4d(sDO + HALF_BYTES, &map_do, qdo_full, 64, m0, head, batch);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0 && total > 0) {
       // ================= MMA issuer =================
       mbar_wait(kv_full, 0);
@@ -240,15 +241,16 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       umma_commit(acc_done);
     }
   } else {
-    // ================= softmax / dQ reduction / epilogue =================
-    const int tid = threadIdx.x;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    // ================= softmax / dQ reduction / epilogue: 2 warpgroups, each owns one 64-column half =================
+    const int half = warp >> 2;                      // key half for S/dP, query half for dQ^T, head-dim half for dV/dK
+    const int rl = (warp & 3) * 32 + lane;           // TMEM lane
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     constexpr float kLog2e = 1.4426950408889634f;
     for (int it = 0; it < total; ++it) {
       const uint32_t ph = it & 1;
       const int head = kv_head * group + it / tiles_per_head;
       const int m0 = (m_first + it % tiles_per_head) * BM;
-      const int row = m0 + tid;
+      const int row = m0 + rl;
       const bool row_ok = row < p.sq;
       const int64_t stat = ((int64_t)batch * p.h + head) * p.sq + row;
       const float lse2 = row_ok ? p.lse[stat] * kLog2e : 0.f;
@@ -258,10 +260,10 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       tc_fence_after();
       // previous iteration's dV/dK/dQ MMAs have retired (we waited dq_full below), so the P / dS tiles are free
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t rs[32], rp[32];
-        tmem_ld32(tmem_base + lane_off + S_COL + c * 32, rs);
-        tmem_ld32(tmem_base + lane_off + DP_COL + c * 32, rp);
+        tmem_ld32(tmem_base + lane_off + S_COL + half * 64 + c * 32, rs);
+        tmem_ld32(tmem_base + lane_off + DP_COL + half * 64 + c * 32, rp);
 #pragma unroll
         for (int q8 = 0; q8 < 4; ++q8) {
           uint32_t up[4], ud[4];
@@ -271,7 +273,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 #pragma unroll
             for (int t2 = 0; t2 < 2; ++t2) {
               const int i = q8 * 8 + 2 * e + t2;
-              const int key = n0 + c * 32 + i;
+              const int key = n0 + half * 64 + c * 32 + i;
               float x = ex2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse2));
               if (!row_ok || key > lim) x = 0.f;
               pv[t2] = x;
@@ -280,8 +282,8 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             up[e] = pack2<T>(pv[0], pv[1]);
             ud[e] = pack2<T>(ds[0], ds[1]);
           }
-          const int col = c * 32 + q8 * 8;              // key index inside the tile
-          const uint32_t off = (col >> 6) * HALF_BYTES + tid * 128 + ((((col & 63) >> 3) ^ (tid & 7)) << 4);
+          const int col = c * 32 + q8 * 8;              // key index inside this 64-key half
+          const uint32_t off = half * HALF_BYTES + rl * 128 + (((col >> 3) ^ (rl & 7)) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off), "r"(up[0]), "r"(up[1]), "r"(up[2]), "r"(up[3]) : "memory");
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(ud[0]), "r"(ud[1]), "r"(ud[2]), "r"(ud[3]) : "memory");
         }
@@ -289,49 +291,48 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
-      // dQ^T tile: TMEM lane = head-dim index (this thread's d), columns = the 128 query rows of the tile
+      if (lane == 0) mbar_arrive(pds_full);          // 8 warp arrivals
+      // dQ^T tile: TMEM lane = head-dim index (d = rl), columns = query rows; this warpgroup handles query columns [half*64, +64)
       mbar_wait(dq_full, ph);
       tc_fence_after();
       // Transpose through shared memory (the P + dS tiles are free: every MMA of this iteration has retired) into a row-major
-      // fp32 [query][d] tile, then let the TMA engine reduce each 512-byte row into dQ (cp.reduce.async.bulk ... add.f32):
-      // 128 bulk reductions per tile instead of 16K scalar atomics.
+      // fp32 [query][d] tile, then let the TMA engine reduce each 512-byte row into dQ (cp.reduce.async.bulk ... add.f32).
       const uint32_t sDQ = sP;   // 64 KB: sP and sDS are adjacent
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + lane_off + S_COL + c * 32, r);
+        tmem_ld32(tmem_base + lane_off + S_COL + half * 64 + c * 32, r);
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(sDQ + (uint32_t)(c * 32 + i) * 512u + (uint32_t)tid * 4u), "r"(r[i]) : "memory");
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(sDQ + (uint32_t)(half * 64 + c * 32 + i) * 512u + (uint32_t)rl * 4u), "r"(r[i]) : "memory");
       }
       tc_fence_before();
       fence_proxy_async();
-      asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 softmax warps only
-      if (m0 + tid < p.sq) {
-        float* dst = p.dq + (((int64_t)batch * p.sq + m0 + tid) * p.h + head) * HD;
-        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 512;" ::"l"(dst), "r"(sDQ + (uint32_t)tid * 512u) : "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // both softmax warpgroups: the whole [128][128] fp32 tile is in smem
+      if (half == 0 && m0 + rl < p.sq) {
+        float* dst = p.dq + (((int64_t)batch * p.sq + m0 + rl) * p.h + head) * HD;
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 512;" ::"l"(dst), "r"(sDQ + (uint32_t)rl * 512u) : "memory");
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tile in shared memory may be overwritten
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_free);
+      if (lane == 0) mbar_arrive(s_free);            // 8 warp arrivals
     }
-    // epilogue: dV, dK rows (lane = key row)
+    // epilogue: dV, dK rows (lane = key row); this warpgroup writes head-dim columns [half*64, +64)
     if (total > 0) {
       mbar_wait(acc_done, 0);
       tc_fence_after();
     }
-    const int key = n0 + tid;
-    const int64_t kv_off = (int64_t)batch * p.dkv_sb + (int64_t)key * p.dkv_ss + (int64_t)kv_head * p.dkv_sh;
+    const int key = n0 + rl;
+    const int64_t kv_off = (int64_t)batch * p.dkv_sb + (int64_t)key * p.dkv_ss + (int64_t)kv_head * p.dkv_sh + half * 64;
     T* dv_row = reinterpret_cast<T*>(p.dv) + kv_off;
     T* dk_row = reinterpret_cast<T*>(p.dk) + kv_off;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t rv[32], rk[32];
       if (total > 0) {
-        tmem_ld32(tmem_base + lane_off + DV_COL + c * 32, rv);
-        tmem_ld32(tmem_base + lane_off + DK_COL + c * 32, rk);
+        tmem_ld32(tmem_base + lane_off + DV_COL + half * 64 + c * 32, rv);
+        tmem_ld32(tmem_base + lane_off + DK_COL + half * 64 + c * 32, rk);
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) { rv[i] = 0u; rk[i] = 0u; }
@@ -339,14 +340,17 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       if (key < p.sk) {
 #pragma unroll
         for (int q8 = 0; q8 < 4; ++q8) {
-          Vec16<T> ov, ok;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            ov.v[e] = from_f<T>(__uint_as_float(rv[q8 * 8 + e]));
-            ok.v[e] = from_f<T>(__uint_as_float(rk[q8 * 8 + e]));
-          }
-          st16(dv_row + c * 32 + q8 * 8, ov);
-          st16(dk_row + c * 32 + q8 * 8, ok);
+          uint4 ov, ok;
+          ov.x = pack2<T>(__uint_as_float(rv[q8 * 8 + 0]), __uint_as_float(rv[q8 * 8 + 1]));
+          ov.y = pack2<T>(__uint_as_float(rv[q8 * 8 + 2]), __uint_as_float(rv[q8 * 8 + 3]));
+          ov.z = pack2<T>(__uint_as_float(rv[q8 * 8 + 4]), __uint_as_float(rv[q8 * 8 + 5]));
+          ov.w = pack2<T>(__uint_as_float(rv[q8 * 8 + 6]), __uint_as_float(rv[q8 * 8 + 7]));
+          ok.x = pack2<T>(__uint_as_float(rk[q8 * 8 + 0]), __uint_as_float(rk[q8 * 8 + 1]));
+          ok.y = pack2<T>(__uint_as_float(rk[q8 * 8 + 2]), __uint_as_float(rk[q8 * 8 + 3]));
+          ok.z = pack2<T>(__uint_as_float(rk[q8 * 8 + 4]), __uint_as_float(rk[q8 * 8 + 5]));
+          ok.w = pack2<T>(__uint_as_float(rk[q8 * 8 + 6]), __uint_as_float(rk[q8 * 8 + 7]));
+          *reinterpret_cast<uint4*>(dv_row + c * 32 + q8 * 8) = ov;
+          *reinterpret_cast<uint4*>(dk_row + c * 32 + q8 * 8) = ok;
         }
       }
     }
@@ -354,7 +358,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   }
 
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }

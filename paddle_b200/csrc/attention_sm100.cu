@@ -6,7 +6,8 @@
 // Parity (behaviour): paddle.nn.functional.flash_attention / scaled_dot_product_attention
 // (python/paddle/nn/functional/flash_attention.py -> phi flash_attn kernels calling the flash-attention library).
 //
-// CTA = 128 query rows of one (batch, head).  Warps 0-3: softmax + epilogue, warp 4: TMA producer, warp 5: TMEM alloc + MMA issuer.
+// CTA = 128 query rows of one (batch, head).  Warps 0-7: softmax + epilogue (two warpgroups, one 64-key half of each S tile
+// each), warp 8: TMA producer, warp 9: TMEM alloc + MMA issuer.
 // TMEM columns: [0,128) S buffer 0, [128,256) S buffer 1, [256,384) O accumulator.  P is double-buffered in shared memory so
 // the softmax of tile j+1 overlaps the P V MMA of tile j (it only waits for that MMA when a row maximum really moved).
 #include <cuda.h>
@@ -20,10 +21,10 @@ namespace b200 {
 namespace attn {
 
 constexpr int BM = 128, BN = 128, HD = 128;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warps 0-7: softmax (2 warpgroups), warp 8: TMA producer, warp 9: TMEM alloc + MMA issuer
 constexpr uint32_t TILE_BYTES = 128 * 128 * 2;   // 32 KB: every operand tile (Q, K, V, P)
 constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;  // one 64-wide K-block of a tile
-constexpr uint32_t SMEM_BYTES = 7 * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;   // Q, 2x K, 2x V, 2x P
+constexpr uint32_t SMEM_BYTES = 7 * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*row max / sum exchange*/;   // Q, 2x K, 2x V, 2x P
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t O_COL = 256;
 
@@ -176,20 +177,20 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     n_tiles = last_key < 0 ? 0 : min(n_tiles, last_key / BN + 1);
   }
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(k_full(s), 1); mbar_init(v_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_empty(s), 1);
-      mbar_init(s_full(s), 1); mbar_init(s_empty(s), 4);
-      mbar_init(p_full(s), 4); mbar_init(p_free(s), 1);
+      mbar_init(s_full(s), 1); mbar_init(s_empty(s), 8);
+      mbar_init(p_full(s), 8); mbar_init(p_free(s), 1);
     }
     mbar_init(pv_done, 1);
     fence_barrier_init();
     fence_proxy_async();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -198,7 +199,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0 && n_tiles > 0) {
       // ================= TMA producer =================
       mbar_expect_tx(q_full, TILE_BYTES);
@@ -220,7 +221,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             tma_load_4d(sV(s) + kb * HALF_BYTES + i * 8192, &map_v, v_full(s), i * 64, n0 + kb * 64, kv_head, batch);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0 && n_tiles > 0) {
       // ================= MMA issuer =================
       mbar_wait(q_full, 0);
@@ -257,57 +258,64 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       }
     }
   } else {
-    // ================= softmax + epilogue (thread == query row == TMEM lane) =================
-    const int tid = threadIdx.x;
-    const int row = m0 + tid;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    // ================= softmax + epilogue: 2 warpgroups, each owns one 64-key half of every S tile =================
+    // thread -> (query row = TMEM lane, key half).  Two warps per scheduler hide each other's latencies; the row maximum is
+    // agreed between the two halves through shared memory once per tile, the row sums stay separate until the epilogue.
+    const int half = warp >> 2;                      // 0: keys [0,64) of the tile, 1: keys [64,128)
+    const int rl = (warp & 3) * 32 + lane;           // row inside the tile == TMEM lane
+    const int row = m0 + rl;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    float* xch = reinterpret_cast<float*>(gen + 7 * TILE_BYTES + 8 * 20);   // [2 (half)][128] floats
     float m_i = -INFINITY, l_i = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
-      const int sb = j & 1, n0 = j * BN;
+      const int sb = j & 1, n0 = j * BN + half * 64;
       mbar_wait(s_full(sb), (j >> 1) & 1);
       tc_fence_after();
-      float s[BN];
+      float s[64];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + lane_off + sb * BN + c * 32, r);
+        tmem_ld32(tmem_base + lane_off + sb * BN + half * 64 + c * 32, r);
 #pragma unroll
         for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(r[i]);   // raw logits; the softmax scale is folded into the exp2 FFMA
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty(sb));      // QK(j+2) may overwrite this S buffer
-      const bool edge = (n0 + BN > p.sk) || (p.causal && n0 + BN - 1 > m0 + p.causal_off);
+      if (lane == 0) mbar_arrive(s_empty(sb));      // QK(j+2) may overwrite this S buffer (8 warp arrivals)
+      const bool edge = (j * BN + BN > p.sk) || (p.causal && j * BN + BN - 1 > m0 + p.causal_off);
       if (edge) {
         const int lim = p.causal ? min(p.sk - 1, row + p.causal_off) : p.sk - 1;   // last visible key
 #pragma unroll
-        for (int i = 0; i < BN; ++i)
+        for (int i = 0; i < 64; ++i)
           if (n0 + i > lim) s[i] = -INFINITY;
       }
-      // one softmax warp per scheduler: keep dependent chains short (8 independent partial maxima, then a tree)
       float mxp[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) mxp[i] = s[i];
 #pragma unroll
-      for (int i = 8; i < BN; ++i) mxp[i & 7] = fmaxf(mxp[i & 7], s[i]);
-      const float mx = fmaxf(fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])), fmaxf(fmaxf(mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7]))) * p.scale_log2;   // scale > 0
+      for (int i = 8; i < 64; ++i) mxp[i & 7] = fmaxf(mxp[i & 7], s[i]);
+      float mx = fmaxf(fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])), fmaxf(fmaxf(mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7])));
+      xch[half * 128 + rl] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, xch[(half ^ 1) * 128 + rl]) * p.scale_log2;   // scale > 0
+      asm volatile("bar.sync 1, 256;" ::: "memory");              // exchange slots may be rewritten (shared memory is full: one slot set)
       float m_new = fmaxf(m_i, mx);
       if (m_new == -INFINITY) m_new = 0.f;          // fully masked so far: keep exp2 finite
       if (j == 0) {
         m_i = m_new;
       } else {
-        const bool need = (m_new - m_i) > 8.f;      // lazy rescale: keep a stale max while exp2 stays <= 2^8
+        const bool need = (m_new - m_i) > 8.f;      // lazy rescale: keep a stale max while exp2 stays <= 2^8 (same decision in both halves)
         if (__any_sync(0xffffffffu, need)) {         // rare: only then must P V (j-1) have landed in TMEM before we touch O
           mbar_wait(pv_done, (j - 1) & 1);
           tc_fence_after();
           const float alpha = need ? ex2(m_i - m_new) : 1.f;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {              // this half rescales its 64 columns of O
             uint32_t r[32];
-            tmem_ld32(tmem_base + lane_off + O_COL + c * 32, r);
+            tmem_ld32(tmem_base + lane_off + O_COL + half * 64 + c * 32, r);
 #pragma unroll
             for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st32(tmem_base + lane_off + O_COL + c * 32, r);
+            tmem_st32(tmem_base + lane_off + O_COL + half * 64 + c * 32, r);
           }
           l_i *= alpha;
           if (need) m_i = m_new;
@@ -318,40 +326,41 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 #pragma unroll
       for (int e = 0; e < 8; ++e) sump[e] = 0.f;
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
+      for (int c = 0; c < 8; ++c) {
+        uint32_t u[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint32_t u[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float p0 = ex2(fmaf(s[kb * 64 + c * 8 + 2 * e], p.scale_log2, -m_i));
-            const float p1 = ex2(fmaf(s[kb * 64 + c * 8 + 2 * e + 1], p.scale_log2, -m_i));
-            sump[2 * e] += p0;
-            sump[2 * e + 1] += p1;
-            u[e] = pack2<T>(p0, p1);          // one cvt.rn.{bf16x2,f16x2}.f32 per pair
-          }
-          // K-major SWIZZLE_128B: row r at r*128 B, 16-byte chunk index XOR (r % 8)
-          const uint32_t addr = sP(sb) + kb * HALF_BYTES + tid * 128 + ((c ^ (tid & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
+        for (int e = 0; e < 4; ++e) {
+          const float p0 = ex2(fmaf(s[c * 8 + 2 * e], p.scale_log2, -m_i));
+          const float p1 = ex2(fmaf(s[c * 8 + 2 * e + 1], p.scale_log2, -m_i));
+          sump[2 * e] += p0;
+          sump[2 * e + 1] += p1;
+          u[e] = pack2<T>(p0, p1);          // one cvt.rn.{bf16x2,f16x2}.f32 per pair
         }
+        // K-major SWIZZLE_128B: the 64-key block `half`, row r at r*128 B, 16-byte chunk index XOR (r % 8)
+        const uint32_t addr = sP(sb) + half * HALF_BYTES + rl * 128 + ((c ^ (rl & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
       }
       l_i += ((sump[0] + sump[1]) + (sump[2] + sump[3])) + ((sump[4] + sump[5]) + (sump[6] + sump[7]));
       fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full(sb));
+      if (lane == 0) mbar_arrive(p_full(sb));      // 8 warp arrivals
     }
     if (n_tiles > 0) {
       mbar_wait(pv_done, (n_tiles - 1) & 1);
       tc_fence_after();
     }
-    const float inv = l_i > 0.f ? 1.f / l_i : 0.f;
-    T* orow = reinterpret_cast<T*>(p.o) + (int64_t)batch * p.o_sb + (int64_t)row * p.o_ss + (int64_t)head * p.o_sh;
+    // combine the two halves' row sums
+    xch[half * 128 + rl] = l_i;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l_tot = l_i + xch[(half ^ 1) * 128 + rl];
+    const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+    T* orow = reinterpret_cast<T*>(p.o) + (int64_t)batch * p.o_sb + (int64_t)row * p.o_ss + (int64_t)head * p.o_sh + half * 64;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {                   // this half writes its 64 output columns
       uint32_t r[32];
       if (n_tiles > 0) {
-        tmem_ld32(tmem_base + lane_off + O_COL + c * 32, r);
+        tmem_ld32(tmem_base + lane_off + O_COL + half * 64 + c * 32, r);
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) r[i] = 0u;
@@ -359,19 +368,21 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       if (row < p.sq) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          Vec16<T> o;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o.v[e] = from_f<T>(__uint_as_float(r[q * 8 + e]) * inv);
-          st16(orow + c * 32 + q * 8, o);
+          uint4 o;
+          o.x = pack2<T>(__uint_as_float(r[q * 8 + 0]) * inv, __uint_as_float(r[q * 8 + 1]) * inv);
+          o.y = pack2<T>(__uint_as_float(r[q * 8 + 2]) * inv, __uint_as_float(r[q * 8 + 3]) * inv);
+          o.z = pack2<T>(__uint_as_float(r[q * 8 + 4]) * inv, __uint_as_float(r[q * 8 + 5]) * inv);
+          o.w = pack2<T>(__uint_as_float(r[q * 8 + 6]) * inv, __uint_as_float(r[q * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = o;
         }
       }
     }
-    if (row < p.sq && p.lse) p.lse[((int64_t)batch * p.h + head) * p.sq + row] = l_i > 0.f ? (m_i + log2f(l_i)) * 0.69314718055994531f : -INFINITY;
+    if (half == 0 && row < p.sq && p.lse) p.lse[((int64_t)batch * p.h + head) * p.sq + row] = l_tot > 0.f ? (m_i + log2f(l_tot)) * 0.69314718055994531f : -INFINITY;
     tc_fence_before();
   }
 
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
