@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--micro-batch", type=int, default=1)
     ap.add_argument("--layers", type=int, default=0, help="debug only: override layer count (result is then marked invalid)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--recompute-skip", type=int, default=-1,
+                    help="N=1 only: number of trailing decoder layers that keep their activations (default: as many as fit in HBM)")
     return ap.parse_args()
 
 
@@ -86,6 +88,9 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+DEFAULT_RECOMPUTE_SKIP = 0
+
+
 def layout_for(n):
     return {1: (1, 1, 1), 2: (1, 2, 1), 4: (1, 2, 2), 8: (2, 2, 2)}.get(n, (n, 1, 1))  # (dp, mp, pp)
 
@@ -127,6 +132,8 @@ def main():
     cfg.sequence_parallel = mp > 1
     # single GPU: 13B params + AdamW state fill HBM -> full activation recompute; model-parallel runs keep activations
     cfg.recompute = (n == 1)
+    if n == 1:   # 156 GB of weights + optimizer state leave room for the activations of a few layers (~0.7 GB each)
+        cfg.recompute_skip_layers = args.recompute_skip if args.recompute_skip >= 0 else DEFAULT_RECOMPUTE_SKIP
     paddle.seed(1234 + rank)
     paddle.set_default_dtype("bfloat16")
 
@@ -227,7 +234,7 @@ def main():
                    "parallelism": f"dp{dp}xmp{mp}xpp{pp}", "sequence_parallel": bool(cfg.sequence_parallel), "recompute": "full" if cfg.recompute else "none",
                    "optimizer": "AdamW fp32 master weights, bf16 moments, global-norm clip 1.0 (fused, device-side)",
                    "l2": "working set (weights+optimizer state >= 26 GB per GPU) >> 126 MB L2; no explicit flush needed",
-                   "params_per_gpu": n_params_local},
+                   "params_per_gpu": n_params_local, "recompute_skip_layers": int(getattr(cfg, "recompute_skip_layers", 0))},
         "gpu_launches": int(launches), "clocks": clocks, "wall_s": round(wall, 3),
     }
     if args.layers:
@@ -242,6 +249,7 @@ def main():
     except Exception:
         pass
     flops_per_token = 6 * 13.0e9 + 12 * cfg.num_hidden_layers * cfg.hidden_size * seq  # fwd+bwd model FLOPs
+    out["peak_mem_gb"] = round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)
     out["model_tflops_per_gpu"] = round(value * flops_per_token / n / 1e12, 1)
     if peaks.get("bf16_tflops_sustained"):
         out["mfu_of_measured_sustained_peak"] = round(out["model_tflops_per_gpu"] / peaks["bf16_tflops_sustained"], 3)

@@ -403,6 +403,52 @@ Tensor gemm(const Tensor& a, const Tensor& b, const OptT& bias, bool a_is_km, bo
   return d;
 }
 
+// D = act(scale * A[M,K] @ B[N,K]^T + bias), A/B fp8 (e4m3 / e5m2), D half / bf16 / fp32
+Tensor gemm_fp8(const Tensor& a, const Tensor& b, const OptT& bias, double scale, int64_t act, at::ScalarType out_dtype) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.dim() == 2 && b.dim() == 2 && a.is_contiguous() && b.is_contiguous() && a.size(1) == b.size(1),
+              "gemm_fp8: operands must be contiguous [M,K] and [N,K]");
+  auto is8 = [](const Tensor& t) { return t.scalar_type() == at::kFloat8_e4m3fn || t.scalar_type() == at::kFloat8_e5m2; };
+  TORCH_CHECK(is8(a) && is8(b), "gemm_fp8: fp8 operands required");
+  c10::cuda::CUDAGuard guard(a.device());
+  b200::GemmFp8Args g;
+  g.m = (int)a.size(0); g.k = (int)a.size(1); g.n = (int)b.size(0);
+  Tensor d = torch::empty({g.m, g.n}, a.options().dtype(out_dtype));
+  g.a = a.data_ptr(); g.b = b.data_ptr(); g.d = d.data_ptr();
+  g.bias = nullptr;
+  if (bias.has_value() && bias->defined()) {
+    TORCH_CHECK(bias->scalar_type() == out_dtype && bias->numel() == g.n, "gemm_fp8: bias must be [N] in the output dtype");
+    g.bias = bias->data_ptr();
+  }
+  g.lda = a.stride(0); g.ldb = b.stride(0); g.ldd = d.stride(0);
+  g.a_e5m2 = a.scalar_type() == at::kFloat8_e5m2; g.b_e5m2 = b.scalar_type() == at::kFloat8_e5m2;
+  g.scale = (float)scale; g.act = (int)act; g.out_dtype = dt_code(d); g.batch = 1;
+  g.stride_a = g.stride_b = g.stride_d = 0;
+  int rc = b200::gemm_fp8_tcgen05(g, cur_stream());
+  g_launches += 1;
+  check_err();
+  TORCH_CHECK(rc == 0, "paddle_b200.gemm_fp8 launch failed rc=", rc);
+  return d;
+}
+
+// q [B,H,D], k_cache / v_cache [B,Hkv,S_max,D] contiguous, lens int32 [B] -> out [B,H,D]
+Tensor decode_attention(const Tensor& q, const Tensor& k_cache, const Tensor& v_cache, const Tensor& lens, double scale) {
+  TORCH_CHECK(q.is_cuda() && q.dim() == 3 && k_cache.dim() == 4 && v_cache.dim() == 4 && q.is_contiguous() && k_cache.is_contiguous() && v_cache.is_contiguous(),
+              "decode_attention: q [B,H,D], caches [B,Hkv,S,D] contiguous");
+  TORCH_CHECK(lens.scalar_type() == at::kInt && lens.is_contiguous() && lens.numel() == q.size(0), "decode_attention: lens must be int32 [B]");
+  c10::cuda::CUDAGuard guard(q.device());
+  const int b = (int)q.size(0), h = (int)q.size(1), d = (int)q.size(2), hkv = (int)k_cache.size(1), smax = (int)k_cache.size(2);
+  const int splits = b200::decode_attention_splits(b, h, smax);
+  Tensor out = torch::empty_like(q);
+  Tensor pacc = torch::empty({b, h, splits, d}, q.options().dtype(at::kFloat));
+  Tensor pml = torch::empty({b, h, splits, 2}, q.options().dtype(at::kFloat));
+  int rc = b200::decode_attention(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), lens.data_ptr<int>(), out.data_ptr(), pacc.data_ptr<float>(),
+                                  pml.data_ptr<float>(), b, h, hkv, smax, d, splits, (float)scale, dt_code(q), cur_stream());
+  g_launches += 2;
+  check_err();
+  TORCH_CHECK(rc == 0, "paddle_b200.decode_attention: unsupported shape (head_dim 128, fp16/bf16 only) rc=", rc);
+  return out;
+}
+
 static bool fill_attn(b200::AttnArgs& a, const Tensor& q, const Tensor& k, const Tensor& v, double scale, bool causal) {
   if (q.dim() != 4 || k.dim() != 4 || v.dim() != 4) return false;
   if (q.stride(3) != 1 || k.stride(3) != 1 || v.stride(3) != 1) return false;
@@ -518,6 +564,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         pybind11::arg("out_dtype") = pybind11::none(), pybind11::arg("rs_dst") = std::vector<int64_t>(), pybind11::arg("rs_rows") = 0,
         pybind11::arg("ag_src") = std::vector<int64_t>(), pybind11::arg("ag_pad") = std::vector<int64_t>(), pybind11::arg("ag_flags") = pybind11::none(),
         pybind11::arg("ag_rank") = 0, pybind11::arg("ag_rows") = 0, pybind11::arg("ag_epoch") = 0);
+  m.def("gemm_fp8", &gemm_fp8);
+  m.def("decode_attention", &decode_attention);
   m.def("attention_supported", &attention_supported);
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_bwd", &attention_bwd);

@@ -1,0 +1,415 @@
+// FP8 (E4M3 / E5M2) GEMM for sm_100a: same persistent warp-specialised structure as gemm_sm100.cu (TMA -> 128B-swizzled smem
+// ring -> tcgen05.mma -> TMEM double-buffered accumulators -> tcgen05.ld epilogue), with `kind::f8f6f4` MMAs (K = 32 per
+// instruction, 2x the bf16 rate), fp32 accumulation and a per-tensor dequantisation scale (+ bias / activation) fused in the
+// epilogue.  Both operands are K-major ("TN" GEMM): A [M,K], B [N,K], 1 byte per element.
+//
+// Parity (behaviour): fp8_fp8_half_gemm_fused (paddle/phi/kernels/fusion/fp8_gemm/fp8_gemm_with_cublasLt/*) which calls cuBLASLt.
+#include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "include/b200_common.cuh"
+#include "include/b200_ops.h"
+
+namespace b200 {
+namespace gemm8 {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 128;  // 128 x 1B = 128B = one swizzle atom row
+constexpr int UMMA_K = 32;    // kind::f8f6f4: 32 elements (32 bytes) per MMA along K
+constexpr int kStages = 4;
+constexpr int kThreads = 256;
+constexpr int kAccStages = 2;
+constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K;      // 16 KB
+
+template <int BN> struct Cfg {
+  static constexpr uint32_t B_STAGE_BYTES = BN * BLOCK_K;
+  static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr uint32_t TMEM_COLS = kAccStages * BN;  // 512 / 256 / 128: powers of two >= 32
+  static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug must trap (visible error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins == 1024) t0 = globaltimer_ns();
+    if (spins > 1024 && (spins & 1023) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+      printf("b200 gemm fp8: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// smem matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address  [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;  // leading byte offset [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;  // stride byte offset  [32,46)
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+
+// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread (thread == TMEM lane == output row)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct Params {
+  int m, n, k, batch;
+  void* d;
+  const void* bias;
+  int64_t ldd, stride_d;
+  int in_dtype, out_dtype;
+  int has_bias, act, accumulate;
+  float scale;
+  uint32_t idesc;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+template <typename TO>
+__device__ __forceinline__ void store_row_chunk(TO* __restrict__ dst, const float (&v)[32], int valid, bool accumulate) {
+  if (valid >= 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    constexpr int N = Vec16<TO>::N;
+#pragma unroll
+    for (int q = 0; q < 32 / N; ++q) {
+      Vec16<TO> o;
+      if (accumulate) {
+        Vec16<TO> old = ld16(dst + q * N);
+#pragma unroll
+        for (int j = 0; j < N; ++j) o.v[j] = from_f<TO>(v[q * N + j] + to_f(old.v[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) o.v[j] = from_f<TO>(v[q * N + j]);
+      }
+      st16(dst + q * N, o);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < valid) dst[j] = from_f<TO>(accumulate ? v[j] + to_f(dst[j]) : v[j]);
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_fp8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024B alignment
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + kStages * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + kAccStages + s); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * C::STAGE_BYTES + 8 * (2 * kStages + 2 * kAccStages));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (p.m + BLOCK_M - 1) / BLOCK_M, num_n = (p.n + BN - 1) / BN;
+  const int tiles_per_batch = num_m * num_n;
+  const int num_tiles = tiles_per_batch * p.batch;
+  const int num_kb = (p.k + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    fence_barrier_init();
+    fence_proxy_async();
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // tile order: groups of 8 M-tiles sweep N (operand panels stay L2-resident across the wave)
+  auto tile_coords = [&](int tile, int& bz, int& mb, int& nb) {
+    bz = tile / tiles_per_batch;
+    const int t = tile - bz * tiles_per_batch;
+    constexpr int GROUP_M = 8;
+    const int in_group = GROUP_M * num_n;
+    const int g = t / in_group;
+    const int first_m = g * GROUP_M;
+    const int gsz = min(num_m - first_m, GROUP_M);
+    const int r = t - g * in_group;
+    mb = first_m + r % gsz;
+    nb = r / gsz;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer =================
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint64_t hint = 0x1000000000000000ull;  // EVICT_NORMAL
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int bz, mb, nb;
+        tile_coords(tile, bz, mb, nb);
+        const int m0 = mb * BLOCK_M, n0 = nb * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          const int k0 = kb * BLOCK_K;
+          tma_load_3d(sa, &map_a, full_bar(stage), k0, m0, bz, hint);  // box {128 k bytes, 128 m}
+          tma_load_3d(sb, &map_b, full_bar(stage), k0, n0, bz, hint);  // box {128 k bytes, BN n}
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer =================
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(tempty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t adesc = make_smem_desc(sa + k * 32, 16, 1024);   // K-major: 32 fp8 elements = 32 B per step
+            const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, 1024);
+            umma_f8(tmem_d, adesc, bdesc, p.idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(as));      // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int ew = warp - 4;  // TMEM lane quadrant (warp id % 4)
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      int bz, mb, nb;
+      tile_coords(tile, bz, mb, nb);
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int row = mb * BLOCK_M + ew * 32 + lane;
+      const bool row_ok = row < p.m;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = nb * BN + c * 32;
+        if (col0 >= p.n) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const int valid = min(32, p.n - col0);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= p.scale;      // per-tensor dequantisation scale (scale_a * scale_b)
+        if (p.has_bias) {
+          if (p.out_dtype == kBF16) {
+            const __nv_bfloat16* b = (const __nv_bfloat16*)p.bias + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < valid) v[j] += __bfloat162float(b[j]);
+          } else if (p.out_dtype == kF16) {
+            const __half* b = (const __half*)p.bias + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < valid) v[j] += __half2float(b[j]);
+          } else {
+            const float* b = (const float*)p.bias + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < valid) v[j] += b[j];
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (row_ok) {
+          void* dptr = p.d;
+          int64_t off = (int64_t)bz * p.stride_d + (int64_t)row * p.ldd + col0;
+          if (p.out_dtype == kBF16) store_row_chunk((__nv_bfloat16*)dptr + off, v, valid, p.accumulate);
+          else if (p.out_dtype == kF16) store_row_chunk((__half*)dptr + off, v, valid, p.accumulate);
+          else store_row_chunk((float*)dptr + off, v, valid, p.accumulate);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// 3-D byte map {k (contiguous), rows, batch}
+static bool make_map8(CUtensorMap* out, const void* ptr, uint64_t k, uint64_t rows, uint64_t batch, uint64_t ld, uint64_t bstride, uint32_t box_rows) {
+  cudaFree(nullptr);
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable"); return false; }
+  cuuint64_t dims[3] = {k, rows, batch};
+  cuuint64_t strides[2] = {ld, batch > 1 ? bstride : rows * ld};
+  cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error(__FILE__, __LINE__, ("cuTensorMapEncodeTiled (fp8) failed: " + std::to_string((int)r)).c_str());
+    return false;
+  }
+  return true;
+}
+static uint32_t make_idesc(int a_e5m2, int b_e5m2, int bn) {
+  uint32_t d = 0;
+  d |= 1u << 4;                                   // c_format = F32
+  d |= (a_e5m2 ? 1u : 0u) << 7;                   // a_format: E4M3 = 0, E5M2 = 1
+  d |= (b_e5m2 ? 1u : 0u) << 10;                  // b_format
+  d |= (uint32_t)(bn >> 3) << 17;                 // n_dim
+  d |= (uint32_t)(BLOCK_M >> 4) << 24;            // m_dim
+  return d;
+}
+
+template <int BN>
+static int launch(const GemmFp8Args& g, cudaStream_t s) {
+  using C = Cfg<BN>;
+  CUtensorMap ma, mb;
+  const uint64_t batch = g.batch > 1 ? g.batch : 1;
+  if (!make_map8(&ma, g.a, g.k, g.m, batch, g.lda, g.stride_a, BLOCK_M)) return 2;
+  if (!make_map8(&mb, g.b, g.k, g.n, batch, g.ldb, g.stride_b, BN)) return 2;
+  Params p;
+  p.m = g.m; p.n = g.n; p.k = g.k; p.batch = (int)batch;
+  p.d = g.d; p.bias = g.bias; p.ldd = g.ldd; p.stride_d = g.stride_d;
+  p.in_dtype = 0; p.out_dtype = g.out_dtype;
+  p.has_bias = g.bias ? 1 : 0;
+  p.act = g.act;
+  p.accumulate = 0;
+  p.scale = g.scale;
+  p.idesc = make_idesc(g.a_e5m2, g.b_e5m2, BN);
+  static bool attr_set = false;
+  auto kern = gemm_fp8_kernel<BN>;
+  if (!attr_set) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_tiles = ((g.m + BLOCK_M - 1) / BLOCK_M) * ((g.n + BN - 1) / BN) * (int)batch;
+  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  kern<<<grid, kThreads, C::SMEM_BYTES, s>>>(ma, mb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return 3; }
+  return 0;
+}
+
+}  // namespace gemm8
+
+int gemm_fp8_tcgen05(const GemmFp8Args& g, cudaStream_t s) {
+  if (g.m <= 0 || g.n <= 0 || g.k <= 0 || g.k % 16 || g.lda % 16 || g.ldb % 16) return 1;   // TMA strides: multiples of 16 bytes
+  if ((reinterpret_cast<uintptr_t>(g.a) | reinterpret_cast<uintptr_t>(g.b)) & 15) return 1;
+  if (g.n <= 128) return gemm8::launch<128>(g, s);
+  return gemm8::launch<256>(g, s);
+}
+
+}  // namespace b200

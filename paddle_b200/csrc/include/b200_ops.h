@@ -111,6 +111,28 @@ int gemm_tcgen05(const GemmArgs& g, cudaStream_t s);
 int gemm_tcgen05_2cta(const GemmArgs& g, cudaStream_t s);
 int gemm_tcgen05_supported(int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd, int a_is_km, int b_is_nk);
 
+// ---- gemm_fp8_sm100.cu ----------------------------------------------------------------------------------------
+// D[M,N] = act(scale * (A[M,K] * B[N,K]^T) + bias): A, B fp8 (E4M3 or E5M2, 1 byte, K contiguous); D bf16 / fp16 / fp32.
+struct GemmFp8Args {
+  const void* a; const void* b; void* d; const void* bias;   // bias in the output dtype (or nullptr)
+  int m, n, k;
+  int64_t lda, ldb, ldd;
+  int a_e5m2, b_e5m2;
+  float scale;
+  int act;          // 0 none, 1 gelu, 2 relu
+  int out_dtype;
+  int batch;
+  int64_t stride_a, stride_b, stride_d;
+};
+int gemm_fp8_tcgen05(const GemmFp8Args& g, cudaStream_t s);
+
+// ---- decode_attention.cu --------------------------------------------------------------------------------------
+// Single-token decode attention: q [B,H,128], k/v cache [B,Hkv,S_max,128], lens[b] valid positions; out [B,H,128].
+// part_acc: fp32 [B,H,splits,128] scratch, part_ml: fp32 [B,H,splits,2] scratch.
+int decode_attention_splits(int b, int h, int smax);
+int decode_attention(const void* q, const void* k_cache, const void* v_cache, const int* lens, void* out, float* part_acc, float* part_ml, int b,
+                     int h, int hkv, int smax, int d, int splits, float scale, int dtype, cudaStream_t s);
+
 // ---- attention_sm100.cu ---------------------------------------------------------------------------------------
 // Flash-attention forward (head_dim 128, fp16/bf16). q [B,Sq,H,D], k/v [B,Sk,Hk,D], o [B,Sq,H,D] as strided views (element
 // strides given as {batch, seq, head}; the head_dim stride must be 1). lse: fp32 [B,H,Sq] (natural log) or nullptr.

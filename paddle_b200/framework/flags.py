@@ -10,6 +10,7 @@ _FLAGS = {
     "FLAGS_b200_sync_debug": False,        # serialise side streams (race triage)
     "FLAGS_b200_p2p_collectives": True,    # fused compute+collective kernels over peer memory
     "FLAGS_b200_gemm_backend": "tcgen05",  # "tcgen05" | "cublas"
+    "FLAGS_b200_fp8_linear": False,        # nn.Linear / F.linear run as fp8 tcgen05 GEMMs (per-tensor scaling, e4m3 fwd / e5m2 grads)
     "FLAGS_b200_flash_attention": True,    # tcgen05 flash-attention forward (csrc/attention_sm100.cu)
     "FLAGS_embedding_deterministic": 0,
     "FLAGS_eager_delete_tensor_gb": 0.0,

@@ -220,6 +220,12 @@ def masked_multihead_attention(x, cache_kv=None, bias=None, src_mask=None, cum_o
     bi = torch.arange(b, device=xr.device)
     ck[0, bi, :, lens] = k.to(ck.dtype)
     ck[1, bi, :, lens] = v.to(ck.dtype)
+    if src_mask is None and xr.is_cuda and hd == 128 and ck.dtype in (torch.bfloat16, torch.float16) and ck.is_contiguous():
+        # HBM-bound split-KV decode kernel (csrc/decode_attention.cu): each cached row is read once with 16-byte loads
+        from ...._build import ext
+
+        out = ext().decode_attention(q.to(ck.dtype).contiguous(), ck[0], ck[1], (lens + 1).to(torch.int32).contiguous(), 1.0 / math.sqrt(hd))
+        return _w(out.reshape(b, nh * hd).to(xr.dtype)), _w(ck)
     scores = torch.einsum("bhd,bhsd->bhs", q.float(), ck[0].float()) / math.sqrt(hd)
     pos = torch.arange(smax, device=xr.device)[None, None]
     scores = scores.masked_fill(pos > lens[:, None, None], float("-inf"))

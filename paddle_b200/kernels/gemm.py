@@ -91,6 +91,10 @@ class _Linear(torch.autograd.Function):
 @recordable
 def linear(x, weight, bias=None):
     x, weight, bias = raw(x), raw(weight), raw(bias)
+    if flag("FLAGS_b200_fp8_linear", False) and x.is_cuda and weight.dim() == 2 and weight.dtype == x.dtype:
+        from .gemm_fp8 import fp8_linear   # O2-fp8 recipe: e4m3 forward operands, e5m2 output gradients (csrc/gemm_fp8_sm100.cu)
+
+        return fp8_linear(x, weight, bias)
     if x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and weight.dim() == 2 and weight.dtype == x.dtype \
             and flag("FLAGS_use_fused_kernels", True) and flag("FLAGS_b200_gemm_backend", "tcgen05") == "tcgen05" \
             and x.shape[-1] % 8 == 0 and weight.shape[1] % 8 == 0 and weight.is_contiguous() \

@@ -307,3 +307,76 @@ def test_flash_attention_packed_api():
     ref.backward(g.float())
     assert rel_err(out, ref) < 1e-2
     assert rel_err(qkv.grad, qkv32.grad) < 2e-2, rel_err(qkv.grad, qkv32.grad)
+
+
+@pytest.mark.parametrize("m,n,k", [(256, 512, 1024), (300, 136, 256), (4096, 5120, 5120)])
+@pytest.mark.parametrize("a_dt,b_dt", [(torch.float8_e4m3fn, torch.float8_e4m3fn), (torch.float8_e5m2, torch.float8_e4m3fn)])
+def test_gemm_fp8(m, n, k, a_dt, b_dt):
+    """tcgen05 kind::f8f6f4 GEMM vs fp32 matmul of the same fp8 values."""
+    from paddle_b200.kernels import gemm_fp8 as K8
+
+    torch.manual_seed(0)
+    a = (torch.randn(m, k, device="cuda") * 0.5).to(a_dt)
+    b = (torch.randn(n, k, device="cuda") * 0.5).to(b_dt)
+    bias = torch.randn(n, device="cuda").to(torch.bfloat16)
+    out = K8.fp8_gemm(a, b, False, True, bias, 0.37, torch.bfloat16, "relu")
+    ref = torch.relu(a.float() @ b.float().t() * 0.37 + bias.float())
+    assert rel_err(out, ref) < 1e-2, rel_err(out, ref)
+    out2 = K8.fp8_gemm(a, b.t().contiguous(), False, False, None, 1.0, torch.float32)     # non-TN layout -> transposed copy inside
+    assert rel_err(out2, a.float() @ b.float().t()) < 1e-3
+
+
+def test_fp8_linear_training_signal():
+    """fp8 Linear (e4m3 fwd, e5m2 grads) tracks the bf16 Linear within fp8 quantisation noise."""
+    from paddle_b200.kernels import gemm_fp8 as K8
+
+    torch.manual_seed(1)
+    x = (torch.randn(512, 1024, device="cuda")).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(1024, 768, device="cuda") * 0.03).to(torch.bfloat16).requires_grad_(True)
+    g = torch.randn(512, 768, device="cuda").to(torch.bfloat16)
+    y = K8.fp8_linear(x, w)
+    y.backward(g)
+    x32, w32 = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    (x32 @ w32).backward(g.float())
+    assert rel_err(y, x32 @ w32) < 6e-2
+    assert rel_err(x.grad, x32.grad) < 8e-2 and rel_err(w.grad, w32.grad) < 8e-2
+
+
+@pytest.mark.parametrize("b,h,hkv,smax", [(2, 8, 8, 777), (3, 16, 4, 2048), (1, 40, 40, 4096)])
+def test_decode_attention(b, h, hkv, smax):
+    """split-KV decode kernel vs fp32 reference, ragged lengths, GQA."""
+    torch.manual_seed(0)
+    q = torch.randn(b, h, 128, device="cuda").to(torch.bfloat16)
+    kc = torch.randn(b, hkv, smax, 128, device="cuda").to(torch.bfloat16)
+    vc = torch.randn(b, hkv, smax, 128, device="cuda").to(torch.bfloat16)
+    lens = torch.tensor([smax, max(1, smax // 3), 5][:b], device="cuda", dtype=torch.int32)
+    out = _ext().decode_attention(q, kc, vc, lens, 128 ** -0.5)
+    rep = h // hkv
+    kf, vf = kc.float().repeat_interleave(rep, 1), vc.float().repeat_interleave(rep, 1)
+    s = torch.einsum("bhd,bhsd->bhs", q.float(), kf) * 128 ** -0.5
+    s = s.masked_fill(torch.arange(smax, device="cuda")[None, None] >= lens[:, None, None], float("-inf"))
+    ref = torch.einsum("bhs,bhsd->bhd", s.softmax(-1), vf)
+    assert rel_err(out, ref) < 1e-2, rel_err(out, ref)
+
+
+def test_masked_multihead_attention_uses_decode_kernel():
+    import paddle_b200.incubate.nn.functional as IF
+
+    torch.manual_seed(1)
+    b, nh, smax = 2, 4, 300
+    cache = (torch.randn(2, b, nh, smax, 128, device="cuda") * 0.5).to(torch.bfloat16)
+    x = torch.randn(b, 3 * nh * 128, device="cuda").to(torch.bfloat16)
+    lens = torch.tensor([17, 250], device="cuda", dtype=torch.int32)
+    n0 = kernels.launch_count()
+    out, new_cache = IF.masked_multihead_attention(x.as_subclass(paddle.Tensor), cache.clone().as_subclass(paddle.Tensor), sequence_lengths=lens.as_subclass(paddle.Tensor))
+    assert kernels.launch_count() > n0
+    paddle.set_flags({"FLAGS_use_fused_kernels": True})
+    qkv = x.reshape(b, 3, nh, 128).float()
+    ck = cache.clone().float()
+    bi = torch.arange(b, device="cuda")
+    ck[0, bi, :, lens.long()] = qkv[:, 1]
+    ck[1, bi, :, lens.long()] = qkv[:, 2]
+    s = torch.einsum("bhd,bhsd->bhs", qkv[:, 0], ck[0]) * 128 ** -0.5
+    s = s.masked_fill(torch.arange(smax, device="cuda")[None, None] > lens[:, None, None], float("-inf"))
+    ref = torch.einsum("bhs,bhsd->bhd", s.softmax(-1), ck[1]).reshape(b, -1)
+    assert rel_err(out, ref) < 2e-2
