@@ -1,5 +1,6 @@
 // Flash-attention forward, ping-pong variant (two query tiles per CTA): see fwd2_kernel.  Same operands / outputs as
-// attention_sm100.cu; selected by default for sequences of at least 256 queries (B200_ATTN_FWD=1 picks the single-tile kernel).
+// attention_sm100.cu.  Experimental (B200_ATTN_FWD=2): measured slower than the single-tile kernel on B200 because the single
+// V stage puts the TMA latency of V(j+1) on the critical path; kept for the next iteration (P in TMEM frees the smem for it).
 #include <cuda.h>
 #include <cstdio>
 #include <string>

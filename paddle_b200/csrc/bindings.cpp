@@ -480,7 +480,7 @@ std::vector<Tensor> attention_fwd(const Tensor& q, const Tensor& k, const Tensor
   Tensor out = torch::empty({a.b, a.sq, a.h, a.d}, q.options());
   Tensor lse = torch::empty({a.b, a.h, a.sq}, q.options().dtype(at::kFloat));
   a.o = out.data_ptr(); a.lse = lse.data_ptr<float>();
-  static const int variant = [] { const char* e = getenv("B200_ATTN_FWD"); return e ? atoi(e) : 2; }();   // 2: ping-pong (default), 1: single tile
+  static const int variant = [] { const char* e = getenv("B200_ATTN_FWD"); return e ? atoi(e) : 1; }();   // 1: single query tile, key-split softmax warpgroups (default, fastest measured); 2: ping-pong (experimental)
   int rc = (variant == 2 && a.sq >= 256) ? b200::attention_fwd2(a, cur_stream()) : b200::attention_fwd(a, cur_stream());
   g_launches += 1;
   check_err();
