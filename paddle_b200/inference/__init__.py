@@ -168,13 +168,15 @@ class Predictor:
 
         self._config = config
         self._layer = jit.load(config._prefix)
-        spec = self._layer._spec.get("input_spec") or []
+        spec = (getattr(self._layer, "_spec", None) or {}).get("input_spec") or []
+        if not spec and hasattr(self._layer, "_blob"):   # traced-program artifact: feed names are recorded in the blob
+            spec = [(None, None, n) for n in self._layer._blob["feeds"]]
         names = [s[2] if s and s[2] else f"x{i}" for i, s in enumerate(spec)] or ["x0"]
         self._inputs = {n: _Handle(n) for n in names}
         self._outputs = {}
         if config._use_gpu and torch.cuda.is_available():
             self._layer.to(torch.device("cuda", config._gpu_id))
-            if config._precision in (PrecisionType.Half, PrecisionType.Bfloat16):
+            if config._precision in (PrecisionType.Half, PrecisionType.Bfloat16) and hasattr(self._layer, "_inner"):
                 self._layer._inner._cast_floating(torch.float16 if config._precision == PrecisionType.Half else torch.bfloat16)
         self._dev = torch.device("cuda", config._gpu_id) if (config._use_gpu and torch.cuda.is_available()) else torch.device("cpu")
 
@@ -200,7 +202,7 @@ class Predictor:
             args = [i if isinstance(i, torch.Tensor) else to_tensor(np.asarray(i)) for i in inputs]
         else:
             args = [h._t for h in self._inputs.values() if h._t is not None]
-        p0 = next(iter(self._layer._inner.parameters()), None)
+        p0 = next(iter(getattr(self._layer, "_inner", self._layer).parameters()), None)
         args = [a.to(self._dev) for a in args]
         if p0 is not None and p0.dtype in (torch.float16, torch.bfloat16):
             args = [a.to(p0.dtype) if a.is_floating_point() else a for a in args]

@@ -1,0 +1,141 @@
+"""Inference predictor, quantization, nn.quant, profiler, incubate optimizers, dlpack, audio features, regularizer, callbacks.
+Parity: test/legacy_test/test_inference_api.py, test/quantization/*, test_profiler.py, test_lookahead.py, test_dlpack.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import paddle_b200 as paddle
+from paddle_b200 import nn
+
+
+class TinyNet(nn.Layer):
+    def __init__(self):
+        super().__init__()
+        self.fc1, self.fc2 = nn.Linear(6, 12), nn.Linear(12, 3)
+
+    def forward(self, x):
+        return self.fc2(paddle.nn.functional.relu(self.fc1(x)))
+
+
+def test_inference_predictor_roundtrip(tmp_path):
+    from paddle_b200 import inference
+
+    paddle.seed(0)
+    net = TinyNet()
+    net.eval()
+    paddle.jit.save(net, str(tmp_path / "m"), input_spec=[paddle.static.InputSpec([None, 6], "float32", "x")])
+    cfg = inference.Config(str(tmp_path / "m.pdmodel"), str(tmp_path / "m.pdiparams"))
+    cfg.disable_gpu() if hasattr(cfg, "disable_gpu") else None
+    pred = inference.create_predictor(cfg)
+    x = np.random.rand(4, 6).astype("float32")
+    h = pred.get_input_handle(pred.get_input_names()[0])
+    h.copy_from_cpu(x)
+    pred.run()
+    out = pred.get_output_handle(pred.get_output_names()[0]).copy_to_cpu()
+    np.testing.assert_allclose(out, net(paddle.to_tensor(x)).numpy(), rtol=1e-5)
+    outs = pred.run([x])
+    np.testing.assert_allclose(outs[0].numpy(), out, rtol=1e-6)
+
+
+def test_quantization_qat_ptq_and_weight_only():
+    from paddle_b200.quantization import PTQ, QAT, AbsmaxObserver, FakeQuanterWithAbsMaxObserver, QuantConfig
+
+    paddle.seed(1)
+    net = TinyNet()
+    x = paddle.to_tensor(np.random.rand(8, 6).astype("float32"))
+    ref = net(x).numpy()
+    q = QAT(QuantConfig(activation=FakeQuanterWithAbsMaxObserver(moving_rate=0.9), weight=FakeQuanterWithAbsMaxObserver(moving_rate=0.9)))
+    qnet = q.quantize(net, inplace=False)
+    y = qnet(x)
+    y.sum().backward()                      # straight-through estimator keeps gradients flowing
+    assert np.abs(y.numpy() - ref).max() < 0.1 and any(p.grad is not None for p in qnet.parameters())
+    p = PTQ(QuantConfig(activation=AbsmaxObserver(), weight=AbsmaxObserver()))
+    pnet = p.quantize(net, inplace=False)
+    pnet(x)
+    conv = p.convert(pnet, inplace=False)
+    assert np.abs(conv(x).numpy() - ref).max() < 0.1
+    w = paddle.to_tensor(np.random.randn(16, 8).astype("float32"))
+    qw, sc = nn.quant.weight_quantize(w, algo="weight_only_int8")
+    xin = paddle.to_tensor(np.random.randn(4, 16).astype("float32"))
+    out = nn.quant.weight_only_linear(xin, qw, weight_scale=sc, weight_dtype="int8")
+    assert np.abs(out.numpy() - xin.numpy() @ w.numpy()).max() < 0.15
+    deq = nn.quant.weight_dequantize(qw, sc, out_dtype="float32")
+    assert np.abs(deq.numpy().reshape(w.shape) - w.numpy()).max() < 0.05 or np.abs(deq.numpy().T.reshape(w.shape) - w.numpy()).max() < 0.05
+
+
+def test_profiler_records_and_exports(tmp_path):
+    from paddle_b200 import profiler
+
+    net = TinyNet()
+    x = paddle.ones([2, 6])
+    prof = profiler.Profiler(targets=[profiler.ProfilerTarget.CPU], scheduler=profiler.make_scheduler(closed=0, ready=0, record=2, repeat=1),
+                             on_trace_ready=profiler.export_chrome_tracing(str(tmp_path)))
+    prof.start()
+    for _ in range(3):
+        with profiler.RecordEvent("fwd"):
+            net(x)
+        prof.step()
+    prof.stop()
+    prof.summary()
+    files = [f for f in os.listdir(tmp_path) if f.endswith(".json")]
+    assert files and "traceEvents" in json.load(open(tmp_path / files[0]))
+
+
+def test_incubate_optimizers():
+    from paddle_b200.incubate.optimizer import GradientMergeOptimizer, LookAhead, ModelAverage
+
+    paddle.seed(2)
+    p = paddle.create_parameter([3], "float32", default_initializer=nn.initializer.Constant(1.0))
+    la = LookAhead(paddle.optimizer.SGD(0.1, parameters=[p]), alpha=0.5, k=2)
+    for _ in range(4):
+        (p * p).sum().backward()
+        la.step()
+        la.clear_grad()
+    assert float(p.sum()) < 3.0
+    q = paddle.create_parameter([2], "float32", default_initializer=nn.initializer.Constant(1.0))
+    inner = paddle.optimizer.SGD(0.1, parameters=[q])
+    ma = ModelAverage(0.15, parameters=[q], min_average_window=2, max_average_window=4)
+    for _ in range(4):
+        (q * q).sum().backward()
+        inner.step()
+        ma.step()
+        inner.clear_grad()
+    cur = q.numpy().copy()
+    with ma.apply():
+        assert not np.allclose(q.numpy(), cur)     # averaged weights swapped in
+    np.testing.assert_allclose(q.numpy(), cur)
+    r = paddle.create_parameter([2], "float32", default_initializer=nn.initializer.Constant(1.0))
+    gm = GradientMergeOptimizer(paddle.optimizer.SGD(0.1, parameters=[r]), k_steps=2, avg=True)
+    for i in range(2):
+        (r * (i + 1.0)).sum().backward()
+        gm.step()
+        gm.clear_grad()
+    np.testing.assert_allclose(r.numpy(), 1.0 - 0.1 * 1.5, rtol=1e-6)
+
+
+def test_dlpack_hub_regularizer_callbacks(tmp_path):
+    x = paddle.to_tensor(np.arange(6, dtype="float32").reshape(2, 3))
+    y = paddle.utils.dlpack.from_dlpack(paddle.utils.dlpack.to_dlpack(x))
+    np.testing.assert_array_equal(y.numpy(), x.numpy())
+    (tmp_path / "hubconf.py").write_text("def tiny(n=2):\n    '''doc'''\n    import paddle_b200 as p\n    return p.nn.Linear(n, n)\n")
+    assert "tiny" in paddle.hub.list(str(tmp_path), source="local")
+    assert paddle.hub.load(str(tmp_path), "tiny", source="local", n=3).weight.shape == [3, 3]
+    p = paddle.create_parameter([2], "float32", default_initializer=nn.initializer.Constant(2.0))
+    opt = paddle.optimizer.SGD(0.1, parameters=[p], weight_decay=paddle.regularizer.L1Decay(0.5))
+    (p * 0).sum().backward()
+    opt.step()
+    np.testing.assert_allclose(p.numpy(), 2.0 - 0.1 * 0.5, rtol=1e-6)
+    es = paddle.callbacks.EarlyStopping(monitor="loss", patience=1, verbose=0)
+    assert hasattr(es, "on_eval_end") and paddle.callbacks.LRScheduler is not None and paddle.callbacks.ModelCheckpoint is not None
+
+
+def test_audio_features():
+    sig = paddle.to_tensor(np.random.randn(1, 4000).astype("float32"))
+    assert paddle.audio.features.Spectrogram(n_fft=256, hop_length=128)(sig).shape[1] == 129
+    mel = paddle.audio.features.MelSpectrogram(sr=8000, n_fft=256, hop_length=128, n_mels=20)(sig)
+    assert mel.shape[1] == 20
+    assert paddle.audio.features.MFCC(sr=8000, n_mfcc=13, n_fft=256, hop_length=128, n_mels=20)(sig).shape[1] == 13
+    w = paddle.audio.functional.get_window("hann", 16)
+    assert w.shape == [16] and abs(float(w[0])) < 1e-6
