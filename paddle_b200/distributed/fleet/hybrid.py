@@ -280,7 +280,7 @@ class HybridParallelOptimizer:
                 d = 1 if (decay_fn is None or decay_fn(p.name)) else 0
                 return (d, 1 if getattr(p, "is_distributed", False) else 0, 1 if mpu.is_sequence_parallel_parameter(p) else 0)
 
-            arena = ParamArena(self._params, group_fn=group_fn)
+            arena = ParamArena(self._params, group_fn=group_fn, grad_allocator=self._dp_grad_allocator())
             mp = hcg.get_model_parallel_world_size() if hcg is not None else 1
             for key, slab in arena.slabs.items():
                 d, is_dist, is_sp = key[2]
@@ -294,6 +294,28 @@ class HybridParallelOptimizer:
                 optimizer._arena_norm_split = True
         elif isinstance(clip, ClipGradByGlobalNorm) and self._need_hybrid_clip:
             optimizer._grad_clip = HybridParallelClipGrad(clip, hcg)
+
+    def _dp_grad_allocator(self):
+        """Data-parallel replicas all-reduce the whole gradient slab every step: place it in a symmetric heap sized for it, so
+        the peer-memory all-reduce runs in place (no staging copies, no NCCL)."""
+        hcg = self._hcg
+        if hcg is None or not (self._dp_enable or self._sharding_enable) or not self._params or not self._params[0].is_cuda:
+            return None
+        group = hcg.get_dp_sharding_parallel_group() if (self._dp_enable and self._sharding_enable) else \
+            (hcg.get_data_parallel_group() if self._dp_enable else hcg.get_sharding_parallel_group())
+        from ...parallel import symm
+
+        need = sum((p.numel() + 127) // 128 * 128 * p.element_size() for p in self._params if not p.stop_gradient)
+        ctx = symm.context_for(group, heap_bytes=need + (768 << 20))
+        if ctx is None or need > ctx.heap.size() - ctx.heap.cursor() - (256 << 20):
+            return None
+
+        def alloc(n, dt):
+            t, _ = ctx.buffer(("hybrid_dp_grad", n, str(dt)), (n,), dt)
+            t.zero_()
+            return t
+
+        return alloc
 
     # arena path: sq holds sum over ALL local slabs; replicated slabs must be counted once across mp -> recompute split
     def _arena_norm_allreduce(self, sq):

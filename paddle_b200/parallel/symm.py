@@ -27,15 +27,16 @@ def available():
     return m is not None and hasattr(m, "SymmHeap")
 
 
-def context_for(group):
-    """SymmContext for `group`, or None when fused P2P collectives are not usable."""
+def context_for(group, heap_bytes=None):
+    """SymmContext for `group`, or None when fused P2P collectives are not usable. `heap_bytes` sizes the heap when this
+    call creates the context (e.g. to hold a whole gradient slab); it must be the same on every rank of the group."""
     if not available():
         return None
     key = id(_pg(group)) if group is not None else 0
     ctx = _contexts.get(key)
     if ctx is None:
         try:
-            ctx = SymmContext(group)
+            ctx = SymmContext(group, heap_bytes=heap_bytes)
         except Exception as e:  # noqa: BLE001
             import warnings
 
