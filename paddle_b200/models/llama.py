@@ -43,6 +43,7 @@ class LlamaConfig:
     recompute: bool = False
     recompute_skip_layers: int = 0      # the last k layers of a stage keep their activations (memory permitting)
     tie_word_embeddings: bool = False
+    lean_activations: bool = True       # single-GPU: fused norm->linear / swiglu->linear nodes that do not keep the intermediate
     dtype: str = "bfloat16"
 
     @property
@@ -115,8 +116,11 @@ class LlamaAttention(nn.Layer):
             self.o_proj = nn.Linear(h, h, weight_attr=oattr, bias_attr=False)
 
     def forward(self, x, cos, sin, position_ids=None):
+        return self.attend(self.qkv_proj(x), cos, sin, position_ids)
+
+    def attend(self, qkv, cos, sin, position_ids=None):
+        """Everything after the QKV projection: rotary, attention, output projection."""
         cfg = self.config
-        qkv = self.qkv_proj(x)
         if cfg.sequence_parallel and self.mp > 1:   # [S, B, *] -> [B, S, *]
             qkv = qkv.transpose([1, 0, 2]).contiguous()
         b, s = qkv.shape[0], qkv.shape[1]
@@ -162,10 +166,25 @@ class LlamaDecoderLayer(nn.Layer):
         self.mlp = LlamaMLP(config)
 
     def _forward(self, h, cos, sin, position_ids=None):
+        if self._lean():
+            return self._forward_lean(h, cos, sin, position_ids)
         x = self.input_layernorm(h)
         a = self.self_attn(x, cos, sin, position_ids)
         x, h = self.post_attention_layernorm(a, residual=h)     # fused: h = h + a ; x = rmsnorm(h)
         return h + self.mlp(x)
+
+    def _lean(self):
+        # single-GPU (no tensor parallel) CUDA training: norm->linear and swiglu->linear run as memory-lean fused autograd nodes
+        return self.self_attn.mp == 1 and self.training and self.input_layernorm.weight.is_cuda and self.config.lean_activations
+
+    def _forward_lean(self, h, cos, sin, position_ids=None):
+        from ..kernels import fused_blocks as FB
+
+        at, mlp = self.self_attn, self.mlp
+        qkv = FB.norm_linear(h, self.input_layernorm.weight, at.qkv_proj.weight, self.input_layernorm.eps)
+        a = at.attend(qkv, cos, sin, position_ids)
+        gu, h = FB.norm_linear(a, self.post_attention_layernorm.weight, mlp.gate_up_proj.weight, self.post_attention_layernorm.eps, residual=h)
+        return h + FB.swiglu_linear(gu, mlp.down_proj.weight)
 
     def forward(self, h, cos=None, sin=None, position_ids=None):
         if cos is None:

@@ -380,3 +380,35 @@ def test_masked_multihead_attention_uses_decode_kernel():
     s = s.masked_fill(torch.arange(smax, device="cuda")[None, None] > lens[:, None, None], float("-inf"))
     ref = torch.einsum("bhs,bhsd->bhd", s.softmax(-1), ck[1]).reshape(b, -1)
     assert rel_err(out, ref) < 2e-2
+
+
+def test_lean_fused_blocks_match_plain_layer():
+    """norm->linear / swiglu->linear fused autograd nodes (no saved intermediates) == the plain decoder layer, fwd + all grads."""
+    from paddle_b200.models import llama as L
+
+    paddle.set_default_dtype("bfloat16")
+    paddle.set_device("gpu:0")
+    try:
+        paddle.seed(5)
+        cfg = L.llama_tiny(hidden_size=256, intermediate_size=512, num_attention_heads=2, num_key_value_heads=2, max_position_embeddings=256)
+        layer = L.LlamaDecoderLayer(cfg)
+        layer.train()
+        h0 = (torch.randn(2, 256, 256, device="cuda") * 2).to(torch.bfloat16)
+        g = torch.randn_like(h0)
+        res = []
+        for lean in (True, False):
+            cfg.lean_activations = lean
+            for p in layer.parameters():
+                p.clear_grad()
+            h = h0.clone().as_subclass(paddle.Tensor)
+            h.stop_gradient = False
+            out = layer(h)
+            out.backward(g.as_subclass(paddle.Tensor))
+            res.append((out.as_subclass(torch.Tensor).float(), h.grad.as_subclass(torch.Tensor).float(),
+                        [p.grad.as_subclass(torch.Tensor).float().clone() for p in layer.parameters()]))
+        assert rel_err(res[0][0], res[1][0]) < 1e-2 and rel_err(res[0][1], res[1][1]) < 2e-2
+        for a, b in zip(res[0][2], res[1][2]):
+            assert rel_err(a, b) < 2e-2
+    finally:
+        paddle.set_default_dtype("float32")
+        paddle.set_device("cpu")
