@@ -198,6 +198,10 @@ def distributed_model(model, hcg, strategy):
             broadcast_sharding_parameters(model, hcg)
         broadcast_dp_parameters(model, hcg)
         mpu.register_sequence_parallel_allreduce_hooks(model)
+        if getattr(model, "_num_virtual", 1) > 1:
+            from .pipeline import PipelineParallelWithInterleave
+
+            return PipelineParallelWithInterleave(model, hcg, strategy)
         return PipelineParallel(model, hcg, strategy)
     if hcg.get_model_parallel_world_size() > 1:
         return TensorParallel(model, hcg, strategy)

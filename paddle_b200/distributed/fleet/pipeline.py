@@ -410,4 +410,106 @@ class PipelineParallel(Layer):
         return outs
 
 
-PipelineParallelWithInterleave = PipelineParallel
+class PipelineParallelWithInterleave(PipelineParallel):
+    """Virtual-pipeline (interleaved) engine. Parity: pipeline_parallel.py:PipelineParallelWithInterleave.
+
+    Every rank owns V model chunks (global stage g = v * pp + rank).  The schedule is the lock-step diagonal: at forward tick
+    t global stage g runs micro-batch t - g, so a rank works on up to V chunks per tick and the pipeline fills after pp - 1
+    ticks of ONE CHUNK each — the ramp (bubble) is 1/V of the plain schedule.  Each tick ends with exactly one batched
+    isend/irecv per rank (sends to the next rank, receives what it needs for the next tick), which keeps the ring
+    (last rank -> first rank for the next chunk) deadlock-free.  Backward mirrors it.  Activations of all micro-batches stay
+    alive between the two phases (F-then-B)."""
+
+    def __init__(self, layers, hcg, strategy):
+        super().__init__(layers, hcg, strategy)
+        self.V = layers._num_virtual
+        self.pp = self.num_stages
+        self.G = self.V * self.pp
+
+    def _exchange(self, sends, recv_shapes, dst, src):
+        """One batched p2p round: `sends` to rank dst, receive len(recv_shapes) tensors from rank src (same order on both sides)."""
+        p2p = self._p2p
+        bufs = [torch.empty(shape, dtype=dt, device=p2p.dev) for shape, dt in recv_shapes]
+        ops = [dist.P2POp(dist.isend, t.contiguous(), dst, p2p.group) for t in sends] + [dist.P2POp(dist.irecv, b, src, p2p.group) for b in bufs]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return bufs
+
+    def forward_backward_pipeline(self, data, scaler=None):
+        inputs, labels = data if isinstance(data, (tuple, list)) and len(data) == 2 else (data, None)
+        M, V, pp, G, r = self.accumulate_steps, self.V, self.pp, self.G, self.stage_id
+        p2p = self._p2p
+        nxt, prv = p2p.next_rank, p2p.prev_rank
+        scale = 1.0 / M
+        self.total_loss = None
+        acts = {}
+
+        def work(t, backward=False):
+            out = []
+            for v in (range(V - 1, -1, -1) if backward else range(V)):
+                g = r + v * pp
+                m = t - ((G - 1 - g) if backward else g)
+                if 0 <= m < M:
+                    out.append((v, m))
+            return out
+
+        # ---- activation shape between stages: learnt once (rank 0 runs its first chunk on one micro-batch without autograd) ----
+        if getattr(self, "_meta", None) is None:
+            info = [None]
+            if r == 0:
+                with torch.no_grad():
+                    o = self._layers(self._micro(inputs, 0), chunk_id=0)
+                info = [(tuple(o.shape), str(o.dtype).split(".")[-1])]
+            dist.broadcast_object_list(info, src=self._hcg.get_rank_from_stage(0), group=p2p.group)
+            self._meta = (tuple(info[0][0]), getattr(torch, info[0][1]))
+        meta = self._meta
+        # ---- forward ticks ---------------------------------------------------------------------------------------------
+        recv_next = {}
+        for t in range(G + M - 1):
+            sends = []
+            for v, m in work(t):
+                g = r + v * pp
+                if g == 0:
+                    leaf = None
+                    x = self._micro(inputs, m)
+                else:
+                    leaf = recv_next.pop((v, m)).requires_grad_(True)    # the received buffer is the autograd leaf of this chunk
+                    x = _w(leaf)
+                out = self._layers(x, chunk_id=v)
+                if g == G - 1:
+                    loss = self._layers._loss_fn(out, self._micro(labels, m)) * scale
+                    self.total_loss = loss.detach() if self.total_loss is None else self.total_loss + loss.detach()
+                    acts[(v, m)] = (leaf, loss)
+                else:
+                    acts[(v, m)] = (leaf, out)
+                    sends.append(_raw(out).detach())
+            # what arrives for tick t+1: my (v, m) at t+1 with g != 0 (sent by the previous rank at this tick, same order)
+            want = [(v, m) for v, m in work(t + 1) if r + v * pp != 0] if t + 1 < G + M - 1 else []
+            got = self._exchange(sends, [meta] * len(want), nxt, prv)
+            for key, buf in zip(want, got):
+                recv_next[key] = buf
+        # ---- backward ticks ------------------------------------------------------------------------------------------
+        grad_next = {}
+        for t in range(G + M - 1):
+            sends = []
+            for v, m in work(t, backward=True):
+                g = r + v * pp
+                x, out = acts.pop((v, m))
+                if g == G - 1:
+                    (scaler.scale(out) if scaler is not None else out).backward()
+                else:
+                    torch.autograd.backward(_raw(out), grad_tensors=grad_next.pop((v, m)))
+                if g != 0:
+                    sends.append(x.grad)
+            want = [(v, m) for v, m in work(t + 1, backward=True) if r + v * pp != G - 1] if t + 1 < G + M - 1 else []
+            got = self._exchange(sends, [meta] * len(want), prv, nxt)
+            for key, buf in zip(want, got):
+                grad_next[key] = buf
+        self._layers.allreduce_shared_weight_gradients()
+        return self._broadcast_loss()
+
+    def _broadcast_loss(self):
+        # the loss lives on the last rank (global stage G - 1 = chunk V - 1 of the last rank)
+        self.is_last = self.stage_id == self.num_stages - 1
+        return super()._broadcast_loss()

@@ -213,6 +213,46 @@ def case_pp():
         close(p.numpy(), sd[mapping[name]].numpy(), 2e-3)
 
 
+def case_pp_interleave():
+    """Virtual pipeline (pp=2 x 2 chunks per rank, 4 micro-batches) == single-process training. Parity: hybrid_parallel_pp_interleave*.py."""
+    s, hcg = setup(pp=2)
+    L, cfg = _tiny_llama({"num_hidden_layers": 4})
+    ids = paddle.to_tensor(np.random.RandomState(0).randint(0, cfg.vocab_size, (4, 33)))
+    s.pipeline_configs = {"accumulate_steps": 4, "micro_batch_size": 1}
+    paddle.seed(11)
+    from paddle_b200.distributed.fleet.pipeline import PipelineLayer, PipelineParallelWithInterleave
+
+    ref, _ = _train_ref(L, cfg, ids, 0)
+    ref_sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    pl = PipelineLayer(L.pipeline_layer_descs(cfg), num_stages=2, loss_fn=L.LlamaPretrainingCriterion(cfg), seg_method="layer:LlamaDecoderLayer",
+                       num_virtual_pipeline_stages=2)
+    mapping = {}
+    for name, _ in pl.named_parameters():
+        idx, rest = name.split(".", 1)
+        i = int(idx.split("_")[-1])
+        if i == 0:
+            mapping[name] = "llama.embedding." + rest
+        elif i == cfg.num_hidden_layers + 1:
+            mapping[name] = "lm_head." + rest
+        else:
+            mapping[name] = f"llama.layers.{i - 1}." + rest
+    pl.set_state_dict({k: ref_sd[v] for k, v in mapping.items()})
+    model = fleet.distributed_model(pl)
+    assert isinstance(model, PipelineParallelWithInterleave)
+    opt = fleet.distributed_optimizer(paddle.optimizer.AdamW(1e-2, parameters=pl.parameters(), weight_decay=0.0))
+    ropt = paddle.optimizer.AdamW(1e-2, parameters=ref.parameters(), weight_decay=0.0)
+    for _ in range(3):
+        loss = model.train_batch([ids[:, :-1], ids[:, 1:]], opt)
+        rl = ref(ids[:, :-1], ids[:, 1:])
+        rl.backward()
+        ropt.step()
+        ropt.clear_grad()
+        close(loss.item(), rl.item(), 2e-4)
+    sd = ref.state_dict()
+    for name, p in pl.named_parameters():
+        close(p.numpy(), sd[mapping[name]].numpy(), 8e-3)   # Adam turns accumulation-order noise into +-lr steps on near-zero grads
+
+
 def case_hybrid_mp_pp():
     """mp2 x pp2 (4 ranks) with sequence parallel: loss decreases and matches across ranks."""
     s, hcg = setup(mp=2, pp=2)
