@@ -32,7 +32,7 @@ def parse():
     ap.add_argument("--model", default="llama2-13b")
     ap.add_argument("--seq", type=int, default=4096)
     ap.add_argument("--seqs-per-gpu", type=int, default=4)
-    ap.add_argument("--micro-batch", type=int, default=1)
+    ap.add_argument("--micro-batch", type=int, default=0, help="sequences per micro-batch (0 = per-layout default)")
     ap.add_argument("--layers", type=int, default=0, help="debug only: override layer count (result is then marked invalid)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--recompute-skip", type=int, default=-1,
@@ -138,6 +138,10 @@ def main():
     paddle.seed(1234 + rank)
     paddle.set_default_dtype("bfloat16")
 
+    if args.micro_batch <= 0:
+        # measured on B200: without a pipeline, larger micro-batches give fuller GEMM waves (mp2: 2 fits the activations of all
+        # layers); with pp > 1 the bubble (pp-1)/(accumulate+pp-1) dominates, so keep as many micro-batches as possible
+        args.micro_batch = 2 if (mp > 1 and pp == 1) else 1
     seqs_per_replica = args.seqs_per_gpu * mp * pp
     global_batch = seqs_per_replica * dp
     accumulate = seqs_per_replica // args.micro_batch
