@@ -139,9 +139,9 @@ def main():
     paddle.set_default_dtype("bfloat16")
 
     if args.micro_batch <= 0:
-        # measured on B200: without a pipeline, larger micro-batches give fuller GEMM waves (mp2: 2 fits the activations of all
+        # measured on B200: without a pipeline, larger micro-batches give fuller GEMM waves (mp2: 4 sequences fit the activations of all
         # layers); with pp > 1 the bubble (pp-1)/(accumulate+pp-1) dominates, so keep as many micro-batches as possible
-        args.micro_batch = 2 if (mp > 1 and pp == 1) else 1
+        args.micro_batch = 4 if (mp > 1 and pp == 1) else 1
     seqs_per_replica = args.seqs_per_gpu * mp * pp
     global_batch = seqs_per_replica * dp
     accumulate = seqs_per_replica // args.micro_batch
