@@ -139,6 +139,7 @@ struct Params {
   void* dk;              // [B,Sk,Hk,D] with element strides (dkv_sb, dkv_ss, dkv_sh): may be slices of a packed dQKV tensor
   void* dv;
   int64_t dkv_sb, dkv_ss, dkv_sh;
+  int64_t dq_sb, dq_ss, dq_sh;   // element strides of the fp32 dQ accumulator [B,Sq,H,D] (may be laid out seq-major)
   uint32_t idesc_kk;     // A K-major, B K-major   (S, dP)
   uint32_t idesc_mm;     // A MN-major, B MN-major (dV, dK)
   uint32_t idesc_mk;     // A MN-major, B K-major  (dQ^T)
@@ -310,7 +311,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       fence_proxy_async();
       asm volatile("bar.sync 1, 256;" ::: "memory");      // both softmax warpgroups: the whole [128][128] fp32 tile is in smem
       if (half == 0 && m0 + rl < p.sq) {
-        float* dst = p.dq + (((int64_t)batch * p.sq + m0 + rl) * p.h + head) * HD;
+        float* dst = p.dq + (int64_t)batch * p.dq_sb + (int64_t)(m0 + rl) * p.dq_ss + (int64_t)head * p.dq_sh;
         asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 512;" ::"l"(dst), "r"(sDQ + (uint32_t)rl * 512u) : "memory");
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -364,14 +365,20 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   }
 }
 
-// delta[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]   (one warp per row, both tensors contiguous [B,S,H,128])
+// delta[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]   (one warp per row; O and dO share the element strides (sb, ss, sh), d contiguous)
 template <typename T>
-__global__ void delta_kernel(const T* __restrict__ o, const T* __restrict__ d_o, float* __restrict__ delta, int64_t rows, int sq, int h) {
+__global__ void delta_kernel(const T* __restrict__ o, const T* __restrict__ d_o, float* __restrict__ delta, int64_t rows, int sq, int h,
+                             int64_t sb, int64_t ss, int64_t sh) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // row = (b*sq + s)*h + head
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const uint2 a = *reinterpret_cast<const uint2*>(o + row * HD + lane * 4);
-  const uint2 b = *reinterpret_cast<const uint2*>(d_o + row * HD + lane * 4);
+  const int64_t bs = row / h;
+  const int head = (int)(row - bs * h);
+  const int64_t bb = bs / sq;
+  const int sidx = (int)(bs - bb * sq);
+  const int64_t off = bb * sb + (int64_t)sidx * ss + (int64_t)head * sh + lane * 4;
+  const uint2 a = *reinterpret_cast<const uint2*>(o + off);
+  const uint2 b = *reinterpret_cast<const uint2*>(d_o + off);
   const T* pa = reinterpret_cast<const T*>(&a);
   const T* pb = reinterpret_cast<const T*>(&b);
   float acc = 0.f;
@@ -379,13 +386,7 @@ __global__ void delta_kernel(const T* __restrict__ o, const T* __restrict__ d_o,
   for (int i = 0; i < 4; ++i) acc += to_f(pa[i]) * to_f(pb[i]);
 #pragma unroll
   for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
-  if (lane == 0) {
-    const int64_t bs = row / h;
-    const int head = (int)(row - bs * h);
-    const int64_t bb = bs / sq;
-    const int s = (int)(bs - bb * sq);
-    delta[(bb * h + head) * sq + s] = acc;
-  }
+  if (lane == 0) delta[(bb * h + head) * sq + sidx] = acc;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -441,19 +442,21 @@ int attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
   if (!make_map4(&mq, f.q, f.d, f.sq, f.h, f.b, f.q_strides[1], f.q_strides[2], f.q_strides[0], f.dtype)) return 2;
   if (!make_map4(&mk, f.k, f.d, f.sk, f.hk, f.b, f.k_strides[1], f.k_strides[2], f.k_strides[0], f.dtype)) return 2;
   if (!make_map4(&mv, f.v, f.d, f.sk, f.hk, f.b, f.v_strides[1], f.v_strides[2], f.v_strides[0], f.dtype)) return 2;
-  if (!make_map4(&mdo, a.d_o, f.d, f.sq, f.h, f.b, (int64_t)f.h * f.d, f.d, (int64_t)f.sq * f.h * f.d, f.dtype)) return 2;
+  if (!make_map4(&mdo, a.d_o, f.d, f.sq, f.h, f.b, a.o_strides[1], a.o_strides[2], a.o_strides[0], f.dtype)) return 2;
   const int64_t rows = (int64_t)f.b * f.sq * f.h;
   const int wpb = 8;
   if (f.dtype == kBF16)
-    delta_kernel<__nv_bfloat16><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>((const __nv_bfloat16*)f.o, (const __nv_bfloat16*)a.d_o, a.delta, rows, f.sq, f.h);
+    delta_kernel<__nv_bfloat16><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>((const __nv_bfloat16*)f.o, (const __nv_bfloat16*)a.d_o, a.delta, rows, f.sq, f.h,
+                                                                                     a.o_strides[0], a.o_strides[1], a.o_strides[2]);
   else
-    delta_kernel<__half><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>((const __half*)f.o, (const __half*)a.d_o, a.delta, rows, f.sq, f.h);
+    delta_kernel<__half><<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>((const __half*)f.o, (const __half*)a.d_o, a.delta, rows, f.sq, f.h, a.o_strides[0], a.o_strides[1], a.o_strides[2]);
   Params p;
   p.b = f.b; p.sq = f.sq; p.sk = f.sk; p.h = f.h; p.hk = f.hk;
   p.scale = f.scale; p.scale_log2 = f.scale * 1.4426950408889634f;
   p.causal = f.causal; p.causal_off = f.sk - f.sq;
   p.lse = f.lse; p.delta = a.delta; p.dq = a.dq; p.dk = a.dk; p.dv = a.dv;
   p.dkv_sb = a.dkv_strides[0]; p.dkv_ss = a.dkv_strides[1]; p.dkv_sh = a.dkv_strides[2];
+  p.dq_sb = a.dq_strides[0]; p.dq_ss = a.dq_strides[1]; p.dq_sh = a.dq_strides[2];
   p.idesc_kk = make_idesc(f.dtype, false, false);
   p.idesc_mm = make_idesc(f.dtype, true, true);
   p.idesc_mk = make_idesc(f.dtype, true, false);

@@ -473,11 +473,13 @@ bool attention_supported(const Tensor& q, const Tensor& k, const Tensor& v) {
 }
 
 // q [B,Sq,H,D], k/v [B,Sk,Hk,D] (strided views allowed) -> (out [B,Sq,H,D] contiguous, lse fp32 [B,H,Sq])
-std::vector<Tensor> attention_fwd(const Tensor& q, const Tensor& k, const Tensor& v, double scale, bool causal) {
+std::vector<Tensor> attention_fwd(const Tensor& q, const Tensor& k, const Tensor& v, double scale, bool causal, bool out_seq_major) {
   c10::cuda::CUDAGuard guard(q.device());
   b200::AttnArgs a;
   TORCH_CHECK(fill_attn(a, q, k, v, scale, causal), "paddle_b200.attention_fwd: unsupported operands");
-  Tensor out = torch::empty({a.b, a.sq, a.h, a.d}, q.options());
+  // out_seq_major: the output is laid out [Sq,B,H,D] (sequence-parallel layers consume it without a transpose copy)
+  Tensor out = out_seq_major ? torch::empty({a.sq, a.b, a.h, a.d}, q.options()) : torch::empty({a.b, a.sq, a.h, a.d}, q.options());
+  if (out_seq_major) { a.o_strides[0] = (int64_t)a.h * a.d; a.o_strides[1] = (int64_t)a.b * a.h * a.d; a.o_strides[2] = a.d; }
   Tensor lse = torch::empty({a.b, a.h, a.sq}, q.options().dtype(at::kFloat));
   a.o = out.data_ptr(); a.lse = lse.data_ptr<float>();
   static const int variant = [] { const char* e = getenv("B200_ATTN_FWD"); return e ? atoi(e) : 1; }();   // 1: single query tile, key-split softmax warpgroups (default, fastest measured); 2: ping-pong (experimental)
@@ -501,7 +503,7 @@ std::vector<Tensor> attention_bwd(const Tensor& q, const Tensor& k, const Tensor
   Tensor dv = torch::empty_like(dk);
   Tensor delta = torch::empty({a.fwd.b, a.fwd.h, a.fwd.sq}, q.options().dtype(at::kFloat));
   a.d_o = d_out.data_ptr(); a.delta = delta.data_ptr<float>(); a.dq = dq32.data_ptr<float>(); a.dk = dk.data_ptr(); a.dv = dv.data_ptr();
-  for (int i = 0; i < 3; ++i) a.dkv_strides[i] = dk.stride(i);
+  for (int i = 0; i < 3; ++i) { a.dkv_strides[i] = dk.stride(i); a.o_strides[i] = out.stride(i); a.dq_strides[i] = dq32.stride(i); }
   int rc = b200::attention_bwd(a, cur_stream());
   g_launches += 2;
   check_err();
@@ -512,25 +514,29 @@ std::vector<Tensor> attention_bwd(const Tensor& q, const Tensor& k, const Tensor
 // packed variant: qkv [B,S,nh+2*nkv,D] (q heads | k heads | v heads); returns d(qkv) of the same shape, written in place by
 // the kernel (dk/dv slices) plus one cast-copy of the fp32 dq accumulator - no slice-backward zero fills / adds
 Tensor attention_bwd_packed(const Tensor& qkv, int64_t nh, int64_t nkv, const Tensor& out, const Tensor& lse, const Tensor& d_out, double scale,
-                            bool causal) {
+                            bool causal, bool seq_major) {
   c10::cuda::CUDAGuard guard(qkv.device());
   TORCH_CHECK(qkv.dim() == 4 && qkv.is_contiguous() && qkv.size(2) == nh + 2 * nkv, "attention_bwd_packed: qkv layout");
-  Tensor q = qkv.narrow(2, 0, nh), k = qkv.narrow(2, nh, nkv), v = qkv.narrow(2, nh + nkv, nkv);
+  // seq_major: qkv / out / d_out memory is [S,B,*,D]; the kernels see [B,S,*,D] views of it (strides only, no copies)
+  auto bs = [&](const Tensor& t) { return seq_major ? t.transpose(0, 1) : t; };
+  Tensor q = bs(qkv.narrow(2, 0, nh)), k = bs(qkv.narrow(2, nh, nkv)), v = bs(qkv.narrow(2, nh + nkv, nkv));
   b200::AttnBwdArgs a;
   TORCH_CHECK(fill_attn(a.fwd, q, k, v, scale, causal), "paddle_b200.attention_bwd_packed: unsupported operands");
-  TORCH_CHECK(out.is_contiguous() && d_out.is_contiguous() && lse.is_contiguous(), "attention_bwd_packed: out / d_out / lse layout");
+  TORCH_CHECK(out.is_contiguous() && d_out.is_contiguous() && lse.is_contiguous() && out.sizes() == d_out.sizes(), "attention_bwd_packed: out / d_out / lse layout");
+  Tensor ov = bs(out);
   a.fwd.o = out.data_ptr(); a.fwd.lse = lse.data_ptr<float>();
   Tensor dqkv = torch::empty_like(qkv);
-  Tensor dk = dqkv.narrow(2, nh, nkv), dv = dqkv.narrow(2, nh + nkv, nkv);
-  Tensor dq32 = torch::zeros({a.fwd.b, a.fwd.sq, a.fwd.h, a.fwd.d}, qkv.options().dtype(at::kFloat));
+  Tensor dk = bs(dqkv.narrow(2, nh, nkv)), dv = bs(dqkv.narrow(2, nh + nkv, nkv));
+  Tensor dq32_mem = torch::zeros(out.sizes(), qkv.options().dtype(at::kFloat));     // same memory order as `out`
+  Tensor dq32 = bs(dq32_mem);
   Tensor delta = torch::empty({a.fwd.b, a.fwd.h, a.fwd.sq}, qkv.options().dtype(at::kFloat));
-  a.d_o = d_out.data_ptr(); a.delta = delta.data_ptr<float>(); a.dq = dq32.data_ptr<float>(); a.dk = dk.data_ptr(); a.dv = dv.data_ptr();
-  for (int i = 0; i < 3; ++i) a.dkv_strides[i] = dk.stride(i);
+  a.d_o = d_out.data_ptr(); a.delta = delta.data_ptr<float>(); a.dq = dq32_mem.data_ptr<float>(); a.dk = dk.data_ptr(); a.dv = dv.data_ptr();
+  for (int i = 0; i < 3; ++i) { a.dkv_strides[i] = dk.stride(i); a.o_strides[i] = ov.stride(i); a.dq_strides[i] = dq32.stride(i); }
   int rc = b200::attention_bwd(a, cur_stream());
   g_launches += 2;
   check_err();
   TORCH_CHECK(rc == 0, "paddle_b200.attention_bwd_packed launch failed rc=", rc);
-  dqkv.narrow(2, 0, nh).copy_(dq32);
+  dqkv.narrow(2, 0, nh).copy_(dq32_mem);
   return dqkv;
 }
 
@@ -568,9 +574,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_fp8", &gemm_fp8);
   m.def("decode_attention", &decode_attention);
   m.def("attention_supported", &attention_supported);
-  m.def("attention_fwd", &attention_fwd);
+  m.def("attention_fwd", &attention_fwd, pybind11::arg("q"), pybind11::arg("k"), pybind11::arg("v"), pybind11::arg("scale"), pybind11::arg("causal"),
+        pybind11::arg("out_seq_major") = false);
   m.def("attention_bwd", &attention_bwd);
-  m.def("attention_bwd_packed", &attention_bwd_packed);
+  m.def("attention_bwd_packed", &attention_bwd_packed, pybind11::arg("qkv"), pybind11::arg("nh"), pybind11::arg("nkv"), pybind11::arg("out"),
+        pybind11::arg("lse"), pybind11::arg("d_out"), pybind11::arg("scale"), pybind11::arg("causal"), pybind11::arg("seq_major") = false);
   m.def("launch_count", &launch_count);
   m.def("reset_launch_count", &reset_launch_count);
   m.def("add_launches", &add_launches);

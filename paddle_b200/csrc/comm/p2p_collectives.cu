@@ -332,7 +332,11 @@ void p2p_reduce_slots(const int64_t* bases, int64_t off, void* out, int64_t n, i
   B200_DISPATCH_DTYPE(dtype, T, {
     constexpr int N = Vec16<T>::N;
     if (n % N) { set_last_error(__FILE__, __LINE__, "p2p_reduce_slots: slot size must be a multiple of the 16B vector"); return; }
-    reduce_slots_kernel<T><<<comm_grid(n / N), kThreads, 0, s>>>(P, off, (T*)out, n, rank, world, epoch, counter);
+    // purely local HBM traffic (the NVLink part happened in the GEMM epilogue): use the whole machine, not the comm-sized grid
+    int64_t blocks = (n / N + kThreads * 4 - 1) / (kThreads * 4);
+    const int cap = sm_count() * 4;
+    const int grid = (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+    reduce_slots_kernel<T><<<grid, kThreads, 0, s>>>(P, off, (T*)out, n, rank, world, epoch, counter);
   });
   B200_CUDA_CHECK(cudaGetLastError());
 }

@@ -68,32 +68,37 @@ class _FlashAttn(torch.autograd.Function):
 
 
 class _FlashAttnPacked(torch.autograd.Function):
-    """Attention over a packed projection qkv [B,S,nh+2*nkv,D]: the kernels read q/k/v in place and the backward writes d(qkv)
-    in place (dk/dv slices straight from the kernel epilogue), so autograd never builds zero-filled slice gradients."""
+    """Attention over a packed projection qkv [B,S,nh+2*nkv,D] (or [S,B,...] when seq_major): the kernels read q/k/v in place
+    through strided TMA maps and the backward writes d(qkv) in place (dk/dv slices straight from the kernel epilogue), so
+    autograd never builds zero-filled slice gradients and the sequence-parallel layout needs no transpose copies."""
 
     @staticmethod
-    def forward(ctx, qkv, nh, nkv, scale, causal):
-        q, k, v = qkv[:, :, :nh], qkv[:, :, nh:nh + nkv], qkv[:, :, nh + nkv:]
-        out, lse = ext().attention_fwd(q, k, v, scale, causal)
+    def forward(ctx, qkv, nh, nkv, scale, causal, seq_major):
+        x = qkv.transpose(0, 1) if seq_major else qkv
+        q, k, v = x[:, :, :nh], x[:, :, nh:nh + nkv], x[:, :, nh + nkv:]
+        out, lse = ext().attention_fwd(q, k, v, scale, causal, seq_major)    # out: same memory order as qkv
         ctx.save_for_backward(qkv, out, lse)
-        ctx.cfg = (nh, nkv, scale, causal)
+        ctx.cfg = (nh, nkv, scale, causal, seq_major)
         return out
 
     @staticmethod
     def backward(ctx, do):
         qkv, out, lse = ctx.saved_tensors
-        nh, nkv, scale, causal = ctx.cfg
-        return ext().attention_bwd_packed(qkv, nh, nkv, out, lse, do.contiguous(), scale, causal), None, None, None, None
+        nh, nkv, scale, causal, seq_major = ctx.cfg
+        return ext().attention_bwd_packed(qkv, nh, nkv, out, lse, do.contiguous(), scale, causal, seq_major), None, None, None, None, None
 
 
-def attention_packed(qkv, nh, nkv, causal=True, scale=None):
-    """qkv: [B,S,nh+2*nkv,D] contiguous (q heads | k heads | v heads). Returns [B,S,nh,D]."""
+def attention_packed(qkv, nh, nkv, causal=True, scale=None, seq_major=False):
+    """qkv: [B,S,nh+2*nkv,D] contiguous (q heads | k heads | v heads), or [S,B,...] with seq_major=True (the layout of
+    sequence-parallel layers). Returns [B,S,nh,D] (resp. [S,B,nh,D])."""
     x = raw(qkv)
-    q, k, v = x[:, :, :nh], x[:, :, nh:nh + nkv], x[:, :, nh + nkv:]
+    xb = x.transpose(0, 1) if seq_major else x
+    q, k, v = xb[:, :, :nh], xb[:, :, nh:nh + nkv], xb[:, :, nh + nkv:]
     if _bwd_backend[0] == "own" and x.is_contiguous() and fused_ok(q, k, v, None, 0.0, causal):
         sc = float(scale) if scale is not None else 1.0 / math.sqrt(x.shape[-1])
-        return wrap(_FlashAttnPacked.apply(x, int(nh), int(nkv), sc, bool(causal)))
-    return attention(q, k, v, None, 0.0, causal, scale)
+        return wrap(_FlashAttnPacked.apply(x, int(nh), int(nkv), sc, bool(causal), bool(seq_major)))
+    out = attention(q, k, v, None, 0.0, causal, scale)
+    return wrap(raw(out).transpose(0, 1).contiguous()) if seq_major else out
 
 
 def fused_ok(q, k, v, mask, dropout_p, causal):

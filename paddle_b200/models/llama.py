@@ -121,11 +121,19 @@ class LlamaAttention(nn.Layer):
     def attend(self, qkv, cos, sin, position_ids=None):
         """Everything after the QKV projection: rotary, attention, output projection."""
         cfg = self.config
+        nh, nkv, hd = self.num_heads, self.num_kv_heads, self.head_dim
+        total = nh + 2 * nkv
+        if cfg.sequence_parallel and self.mp > 1 and position_ids is None and _raw(qkv).is_cuda:
+            # sequence-parallel layout [S, B, *] is kept end to end: rotary gets explicit positions (token t = s*B + b -> s) and the
+            # attention kernels address [B, S, h, d] views of the [S, B, ...] memory through their TMA strides - no transpose copies
+            s, b = qkv.shape[0], qkv.shape[1]
+            pid = _seq_major_positions(s, b, _raw(qkv).device)
+            qkv = KR.apply_rope_packed(qkv, cos, sin, nh + nkv, total, hd, pid, neox=True)   # in place on the GEMM output (explicit positions)
+            out = KAT.attention_packed(_raw(qkv).view(s, b, total, hd), nh, nkv, True, None, seq_major=True)   # [S, B, nh, hd]
+            return self.o_proj(_w(_raw(out).reshape(s, b, nh * hd)))
         if cfg.sequence_parallel and self.mp > 1:   # [S, B, *] -> [B, S, *]
             qkv = qkv.transpose([1, 0, 2]).contiguous()
         b, s = qkv.shape[0], qkv.shape[1]
-        nh, nkv, hd = self.num_heads, self.num_kv_heads, self.head_dim
-        total = nh + 2 * nkv
         qkv = KR.apply_rope_packed(qkv, cos, sin, nh + nkv, total, hd, position_ids, neox=True)
         out = KAT.attention_packed(_raw(qkv).view(b, s, total, hd), nh, nkv, True, None)   # [B, S, nh, hd]; q/k/v read in place
         out = _raw(out).reshape(b, s, nh * hd)
@@ -192,6 +200,19 @@ class LlamaDecoderLayer(nn.Layer):
         if self.config.recompute and self.training and torch.is_grad_enabled() and not getattr(self, "_skip_recompute", False):
             return recompute(self._forward, h, cos, sin, position_ids)
         return self._forward(h, cos, sin, position_ids)
+
+
+_pid_cache = {}
+
+
+def _seq_major_positions(s, b, device):
+    key = (s, b, str(device))
+    t = _pid_cache.get(key)
+    if t is None:
+        if len(_pid_cache) > 16:
+            _pid_cache.clear()
+        t = _pid_cache[key] = torch.arange(s, device=device, dtype=torch.int64).repeat_interleave(b).reshape(1, s * b)
+    return t
 
 
 def rope_cache(config, device):

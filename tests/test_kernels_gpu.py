@@ -412,3 +412,21 @@ def test_lean_fused_blocks_match_plain_layer():
     finally:
         paddle.set_default_dtype("float32")
         paddle.set_device("cpu")
+
+
+def test_flash_attention_seq_major_layout():
+    """Sequence-parallel layout: qkv memory is [S,B,heads,D]; kernels address it through strides, fwd + bwd match the batch-major path."""
+    from paddle_b200.kernels import attention as KAT
+
+    torch.manual_seed(4)
+    s, b, nh, nkv = 384, 3, 4, 4
+    base = (torch.randn(s, b, nh + 2 * nkv, 128, device="cuda") * 0.7).to(torch.bfloat16)
+    x_sb = base.clone().requires_grad_(True)
+    out_sb = KAT.attention_packed(x_sb, nh, nkv, True, None, seq_major=True)            # [S,B,nh,D]
+    g = torch.randn_like(out_sb)
+    out_sb.backward(g)
+    x_bs = base.transpose(0, 1).contiguous().requires_grad_(True)
+    out_bs = KAT.attention_packed(x_bs, nh, nkv, True, None)                            # [B,S,nh,D]
+    out_bs.backward(g.transpose(0, 1).contiguous())
+    assert rel_err(out_sb.transpose(0, 1), out_bs) < 1e-3
+    assert rel_err(x_sb.grad.transpose(0, 1), x_bs.grad) < 1e-2
