@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--micro-batch", type=int, default=0, help="sequences per micro-batch (0 = per-layout default)")
     ap.add_argument("--layers", type=int, default=0, help="debug only: override layer count (result is then marked invalid)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--layout", default="", help="dp,mp,pp override of the per-N layout (experiments)")
     ap.add_argument("--recompute-skip", type=int, default=-1,
                     help="N=1 only: number of trailing decoder layers that keep their activations (default: as many as fit in HBM)")
     return ap.parse_args()
@@ -119,6 +120,9 @@ def main():
     torch.cuda.set_device(local_rank)
     paddle.set_device(f"gpu:{local_rank}")
     dp, mp, pp = layout_for(n)
+    if args.layout:
+        dp, mp, pp = (int(v) for v in args.layout.split(","))
+        assert dp * mp * pp == n, "layout must multiply to --gpus"
     if n > 1:
         strategy = fleet.DistributedStrategy()
         strategy.hybrid_configs = {"dp_degree": dp, "mp_degree": mp, "pp_degree": pp}
