@@ -27,6 +27,10 @@ def __getattr__(name):
     if name in ("save_state_dict", "load_state_dict"):
         mod = importlib.import_module(".checkpoint", __name__)
         return getattr(mod, name)
+    if name in ("gloo_init_parallel_env", "gloo_barrier", "gloo_release", "QueueDataset", "InMemoryDataset", "CountFilterEntry", "ShowClickEntry",
+                "ProbabilityEntry", "ParallelMode", "ReduceType", "io"):
+        mod = importlib.import_module(".extras", __name__)
+        return getattr(mod, name)
     if name in ("group_sharded_parallel", "save_group_sharded_model"):
         mod = importlib.import_module(".sharding", __name__)
         return getattr(mod, name)

@@ -129,3 +129,11 @@ def __getattr__(name):
         except ModuleNotFoundError as e:
             raise AttributeError(name) from e
     raise AttributeError(name)
+
+
+def __getattr__(name):
+    if name == "inference":   # paddle.incubate.inference: the predictor API lives in paddle_b200.inference
+        import importlib
+
+        return importlib.import_module("paddle_b200.inference")
+    raise AttributeError(name)

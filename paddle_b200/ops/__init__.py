@@ -18,6 +18,8 @@ from .math import *  # noqa: F401,F403
 from .random import *  # noqa: F401,F403
 from .search import *  # noqa: F401,F403
 from .stat import *  # noqa: F401,F403
+from .extras import (LazyGuard, check_shape, disable_signal_handler, masked_scatter_, pdist, set_printoptions, sgn, sinc_, t_, transpose_,  # noqa: F401
+                     tril_, triu_)
 
 # names that must NOT become Tensor methods (list-first-arg functions, property clashes, torch-internal contracts)
 _NO_METHOD = {

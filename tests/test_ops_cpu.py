@@ -259,3 +259,31 @@ def test_fft_signal():
     spec = paddle.signal.stft(sig, n_fft=64, hop_length=16)
     rec = paddle.signal.istft(spec, n_fft=64, hop_length=16, length=256)
     np.testing.assert_allclose(rec.numpy(), sig.numpy(), atol=1e-4)
+
+
+def test_remaining_toplevel_names():
+    x = T(A.copy())
+    paddle.t_(x)
+    np.testing.assert_array_equal(x.numpy(), A.T)
+    y = T(A.copy())
+    paddle.transpose_(y, [1, 0])
+    assert y.shape == [4, 3]
+    z = T(A.copy())
+    paddle.triu_(z, 1)
+    np.testing.assert_array_equal(z.numpy(), np.triu(A, 1))
+    np.testing.assert_allclose(paddle.sgn(T(A - 0.5)).numpy(), np.sign(A - 0.5))
+    from scipy.spatial.distance import pdist as sp_pdist
+
+    np.testing.assert_allclose(paddle.pdist(T(A)).numpy(), sp_pdist(A), rtol=1e-5)
+    m = T(np.zeros((2, 2), "float32"))
+    paddle.masked_scatter_(m, T(np.array([[True, False], [False, True]])), T(np.array([5.0, 7.0], "float32")))
+    np.testing.assert_array_equal(m.numpy(), [[5, 0], [0, 7]])
+    paddle.set_printoptions(precision=4)
+    paddle.check_shape([1, 2], "op")
+    with pytest.raises(TypeError):
+        paddle.check_shape("x", "op")
+    with paddle.LazyGuard():
+        pass
+    import paddle_b200.distributed as D
+
+    assert D.ParallelMode.PIPELINE_PARALLEL == 2 and D.ReduceType.kRedSum == 0 and D.ShowClickEntry("s", "c")._to_attr() == "show_click_entry:s:c"
