@@ -88,12 +88,23 @@ def _fused_ok(y):
     return (not torch.is_grad_enabled()) and y.is_cuda and y.dtype in (torch.bfloat16, torch.float16)
 
 
+class TiedEmbedding(nn.Embedding):
+    """Token embedding that also serves as the (tied) output projection: `emb(h, project=True)` = h @ W^T.  Both uses go through
+    this layer's __call__, so parameter-sharding wrappers (GroupSharded stage 3 gathers a layer's weights in its forward hooks)
+    see the weight materialised for the LM head as well."""
+
+    def forward(self, x, project=False):
+        if project:
+            return F.linear(x, self.weight.t())
+        return super().forward(x)
+
+
 class GPTModel(nn.Layer):
     def __init__(self, cfg):
         super().__init__()
         self.cfg = cfg
         attr = nn.ParamAttr(initializer=I.Normal(0.0, cfg.initializer_range))
-        self.wte = nn.Embedding(cfg.vocab_size, cfg.hidden_size, weight_attr=attr)
+        self.wte = TiedEmbedding(cfg.vocab_size, cfg.hidden_size, weight_attr=attr)
         self.wpe = nn.Embedding(cfg.max_position_embeddings, cfg.hidden_size, weight_attr=attr)
         self.blocks = nn.LayerList([GPTBlock(cfg) for _ in range(cfg.num_hidden_layers)])
         self.ln_f = nn.LayerNorm(cfg.hidden_size, epsilon=cfg.layer_norm_eps)
@@ -117,7 +128,7 @@ class GPTForCausalLM(nn.Layer):
 
     def forward(self, input_ids, labels=None):
         h = self.gpt(input_ids)
-        logits = KG.linear(h, _raw(self.gpt.wte.weight).t()) if False else F.linear(h, self.gpt.wte.weight.t())
+        logits = self.gpt.wte(h, project=True)
         if labels is None:
             return logits
         v = logits.shape[-1]
