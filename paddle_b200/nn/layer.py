@@ -140,6 +140,12 @@ class Layer:
     def register_buffer(self, name, tensor, persistable=True):
         if tensor is not None and not isinstance(tensor, torch.Tensor):
             raise TypeError("register_buffer expects a Tensor or None")
+        if tensor is not None and tensor.device.type == "cpu":
+            from ..framework import place as _place
+
+            d = _place.to_torch_device(None)
+            if d.type != "cpu":            # buffers follow the current device like parameters do (paddle.set_device)
+                tensor = tensor.to(d)
         if tensor is not None and not isinstance(tensor, Tensor):
             tensor = tensor.as_subclass(Tensor)
         self._buffers[name] = tensor
