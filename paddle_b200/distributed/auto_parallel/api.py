@@ -156,13 +156,12 @@ def _global_shape(lshape, mesh, placements):
 
 
 def _offsets(gshape, mesh, placements):
-    lshape = _local_shape(gshape, mesh, placements)
     off = [0] * len(gshape)
     c = mesh.coord_of(env.get_rank()) or (0,) * mesh.ndim
     for md, p in enumerate(placements):
         if isinstance(p, Shard):
             d = p.dim % len(gshape)
-            off[d] = off[d] * mesh.shape[md] + c[md] * lshape[d] if False else off[d] + c[md] * _stride_of(gshape, mesh, placements, md, d)
+            off[d] += c[md] * _stride_of(gshape, mesh, placements, md, d)
     return off
 
 
@@ -610,11 +609,7 @@ def _rule_embedding(func, args, kwargs, mesh):
     ids, w = args[0], args[1]
     if not _is_dt(w) or not any(isinstance(p, Shard) for p in w.placements):
         ids_d = _to_dt(ids, mesh)
-        wl = _raw(w)
-        for md, p in enumerate(ids_d.placements):   # replicated table read by sharded ids: its grad is partial over that dim
-            if isinstance(p, Shard) and mesh.shape[md] > 1 and wl.requires_grad and False:
-                pass
-        out = func(_raw(ids_d), wl, *args[2:], **kwargs)
+        out = func(_raw(ids_d), _raw(w), *args[2:], **kwargs)   # replicated table: its grad is averaged over the dp dims by shard_optimizer
         return _mk(out, mesh, list(ids_d.placements))
     ids_d = _to_dt(ids, mesh)
     il, wl = _raw(ids_d), _raw(w)

@@ -34,8 +34,7 @@ def save_state_dict(state_dict, path, process_group=None, coordinator_rank=0, un
     for k, v in state_dict.items():
         if isinstance(v, dict):   # nested (e.g. optimizer master_weights)
             for kk, vv in v.items():
-                state_dict_flat_key = f"{k}.{kk}"
-                local[state_dict_flat_key] = vv
+                local[f"{k}.{kk}"] = vv
         else:
             local[k] = v
     tensors = {k: v for k, v in local.items() if isinstance(v, torch.Tensor)}

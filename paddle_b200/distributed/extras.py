@@ -31,9 +31,9 @@ _gloo = [None]
 def gloo_init_parallel_env(rank_id, rank_num, server_endpoint):
     """CPU-only rendezvous (gloo) for parameter-server style jobs. Parity: distributed/parallel.py:gloo_init_parallel_env."""
     host, port = server_endpoint.split(":")
-    store = dist.TCPStore(host, int(port), rank_num, is_master=(rank_id == 0))
-    _gloo[0] = dist.new_group if False else None
-    dist.init_process_group("gloo", store=store, rank=rank_id, world_size=rank_num) if not dist.is_initialized() else None
+    if not dist.is_initialized():
+        store = dist.TCPStore(host, int(port), rank_num, is_master=(rank_id == 0))
+        dist.init_process_group("gloo", store=store, rank=rank_id, world_size=rank_num)
     _gloo[0] = True
 
 
@@ -116,13 +116,9 @@ class InMemoryDataset:
         if dist.is_initialized() and dist.get_world_size() > 1:
             n, me = dist.get_world_size(), dist.get_rank()
             buckets = [[r for i, r in enumerate(self._rows) if hash((me, i)) % n == d] for d in range(n)]
-            out = [None] * n
-            dist.all_to_all_object_list(out, buckets) if hasattr(dist, "all_to_all_object_list") else None
-            if out[0] is None:
-                gathered = [None] * n
-                dist.all_gather_object(gathered, buckets)
-                out = [g[me] for g in gathered]
-            self._rows = [r for b in out for r in b]
+            gathered = [None] * n
+            dist.all_gather_object(gathered, buckets)
+            self._rows = [r for g in gathered for r in g[me]]
         self.local_shuffle()
 
     def get_memory_data_size(self, fleet=None):
