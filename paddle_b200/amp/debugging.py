@@ -103,3 +103,24 @@ def collect_operator_stats():
 
 def compare_accuracy(dump_path, another_dump_path, output_filename, loss_scale=1, dump_all_tensors=False):
     raise NotImplementedError("compare_accuracy needs dumped tensor logs (DebugMode.DUMP_ALL); not produced in this build")
+
+
+def check_layer_numerics(func):
+    """Decorator for Layer.forward: checks inputs and outputs for NaN / Inf. Parity: amp/debugging.py:check_layer_numerics."""
+    import functools
+
+    import torch
+
+    @functools.wraps(func)
+    def wrapper(self, *args, **kwargs):
+        def chk(t, what):
+            if isinstance(t, torch.Tensor) and t.is_floating_point() and not bool(torch.isfinite(t).all()):
+                raise RuntimeError(f"{type(self).__name__}: non-finite values in {what}")
+        for a in args:
+            chk(a, "input")
+        out = func(self, *args, **kwargs)
+        for o in (out if isinstance(out, (list, tuple)) else [out]):
+            chk(o, "output")
+        return out
+
+    return wrapper

@@ -114,15 +114,6 @@ def distributed_scaler(scaler):
     return hybrid.distributed_scaler(scaler, _state["hcg"])
 
 
-class _Utils:
-    @staticmethod
-    def recompute(function, *args, **kwargs):
-        return recompute(function, *args, **kwargs)
-
-
-utils = _Utils()
-
-
 class _MetaParallel:
     """fleet.meta_parallel namespace."""
 
@@ -140,3 +131,6 @@ class _MetaParallel:
 
 
 meta_parallel = _MetaParallel()
+
+from .base_extras import Fleet, MultiSlotDataGenerator, MultiSlotStringDataGenerator, Role, UtilBase  # noqa: F401,E402
+from . import utils  # noqa: F401,E402

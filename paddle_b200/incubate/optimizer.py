@@ -153,3 +153,6 @@ class RecomputeOptimizer:
 
     def __getattr__(self, n):
         return getattr(self._opt, n)
+
+
+from ..optimizer import LBFGS  # noqa: F401,E402  (paddle.incubate.optimizer.LBFGS is the same class)

@@ -273,3 +273,9 @@ def convert_to_mixed_precision(model_file, params_file, mixed_model_file, mixed_
 
 Tensor = _Handle
 XpuConfig = InternalUtils = None
+
+
+def _get_phi_kernel_name(op_name):
+    """Fluid op name -> phi kernel name (the two differ only for a handful of legacy ops)."""
+    return {"matmul_v2": "matmul", "elementwise_add": "add", "elementwise_sub": "subtract", "elementwise_mul": "multiply", "elementwise_div": "divide",
+            "reduce_sum": "sum", "reduce_mean": "mean", "fill_constant": "full", "lookup_table_v2": "embedding"}.get(op_name, op_name)

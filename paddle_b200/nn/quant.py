@@ -72,3 +72,15 @@ def llm_int8_linear(x, weight, bias=None, weight_scale=None, threshold=6.0):
 
 def apply_per_channel_scale(x, scales):
     return x * scales
+
+
+class Stub:
+    """Placeholder marking where an observer / quanter is inserted by QAT / PTQ. Parity: nn/quant/stub.py:Stub."""
+
+    def __init__(self, observer=None):
+        self._observer = observer
+
+    def __call__(self, x):
+        return x
+
+    forward = __call__

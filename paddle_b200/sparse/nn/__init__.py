@@ -97,3 +97,26 @@ class MaxPool3D(Layer):
 
     def forward(self, x):
         return functional.max_pool3d(x, *self._cfg)
+
+
+class _SpConv2D(Layer):
+    _subm = False
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, padding_mode="zeros", key=None,
+                 weight_attr=None, bias_attr=None, data_format="NHWC"):
+        super().__init__()
+        k = (kernel_size,) * 2 if isinstance(kernel_size, int) else tuple(kernel_size)
+        self._cfg = (stride, padding, dilation, groups)
+        self.weight = self.create_parameter([*k, in_channels // groups, out_channels], attr=weight_attr)   # HWIO like the reference
+        self.bias = self.create_parameter([out_channels], attr=bias_attr, is_bias=True)
+
+    def forward(self, x):
+        return functional._conv2d(x, self.weight, self.bias, *self._cfg, subm=self._subm)
+
+
+class Conv2D(_SpConv2D):
+    pass
+
+
+class SubmConv2D(_SpConv2D):
+    _subm = True

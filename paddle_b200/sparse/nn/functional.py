@@ -101,3 +101,36 @@ def attention(query, key, value, sparse_mask, key_padding_mask=None, attn_mask=N
     if attn_mask is not None:
         s = s + _raw(attn_mask)
     return _w(torch.softmax(s, -1).nan_to_num(0.0) @ v)
+
+
+def _conv2d(x, weight, bias, stride, padding, dilation, groups, subm=False):
+    """Sparse NHWC conv: same dense-compute / sparse-pattern strategy as _conv3d (weight layout HWIO)."""
+    xr = _raw(x).coalesce()
+    dense = xr.to_dense().permute(0, 3, 1, 2)
+    w = _raw(weight).permute(3, 2, 0, 1)
+    if subm:
+        padding = tuple((kk - 1) // 2 for kk in w.shape[2:])
+        stride = 1
+    out = F.conv2d(dense, w, None if bias is None else _raw(bias), stride, padding, dilation, groups).permute(0, 2, 3, 1)
+    if subm:
+        idx = xr.indices()[:3]
+        return _w(torch.sparse_coo_tensor(idx, out[idx[0], idx[1], idx[2]], out.shape))
+    active = F.conv2d((dense.abs().sum(1, keepdim=True) > 0).float(), torch.ones(1, 1, *w.shape[2:], device=w.device), None, stride, padding, dilation) > 0
+    mask = active[:, 0]
+    return _w(torch.sparse_coo_tensor(mask.nonzero().t(), out[mask], out.shape))
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, data_format="NHWC", name=None):
+    return _conv2d(x, weight, bias, stride, padding, dilation, groups, False)
+
+
+def subm_conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, data_format="NHWC", key=None, name=None):
+    return _conv2d(x, weight, bias, stride, padding, dilation, groups, True)
+
+
+def subm_conv2d_igemm(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, data_format="NHWC", key=None, name=None):
+    return _conv2d(x, weight, bias, stride, padding, dilation, groups, True)
+
+
+def subm_conv3d_igemm(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, data_format="NDHWC", key=None, name=None):
+    return _conv3d(x, weight, bias, stride, padding, dilation, groups, True)

@@ -1,0 +1,79 @@
+"""API-surface fillers: fleet utils / Role / UtilBase / data generators, sparse 2-D conv, distribution.transform, misc."""
+import numpy as np
+import pytest
+
+import paddle_b200 as paddle
+
+
+def test_fleet_utils_and_roles(tmp_path):
+    from paddle_b200.distributed import fleet
+    from paddle_b200.distributed.fleet.utils import hybrid_parallel_util, sequence_parallel_utils, tensor_fusion_helper
+
+    assert fleet.Role.SERVER == 2
+    u = fleet.UtilBase()
+    assert np.allclose(u.all_reduce([1, 2]), [1, 2]) and u.all_gather(5) == [5]
+    assert u.get_file_shard(["a", "b", "c"]) == ["a", "b", "c"]
+    fs = fleet.utils.LocalFS()
+    d = str(tmp_path / "x")
+    fs.mkdirs(d)
+    fs.touch(d + "/f")
+    assert fs.ls_dir(str(tmp_path)) == (["x"], []) and fs.is_file(d + "/f")
+    fs.mv(d + "/f", d + "/g")
+    assert fs.is_exist(d + "/g")
+    fs.delete(d)
+    assert not fs.is_exist(d)
+    with pytest.raises(RuntimeError):
+        fleet.utils.HDFSClient("/none", {}).mkdirs("/x")
+    assert fleet.utils.recompute is fleet.recompute
+    assert hasattr(sequence_parallel_utils, "ColumnSequenceParallelLinear") and hasattr(hybrid_parallel_util, "fused_allreduce_gradients")
+    lin = paddle.nn.Linear(4, 4)
+    decay, fused, buckets = tensor_fusion_helper.fused_parameters(lin.parameters())
+    assert sum(int(t.numel()) for t in fused) >= 20 and buckets
+
+
+def test_data_generator():
+    from paddle_b200.distributed import fleet
+
+    class G(fleet.MultiSlotDataGenerator):
+        def generate_sample(self, line):
+            def it():
+                yield [("words", [1, 2, 3]), ("label", [0])]
+            return it
+
+    assert G().run_from_memory() == ["3 1 2 3 1 0\n"]
+
+
+def test_sparse_conv2d():
+    idx = np.array([[0, 0], [1, 2], [1, 3]])
+    sp = paddle.sparse.sparse_coo_tensor(idx, np.random.rand(2, 3).astype("float32"), [1, 4, 4, 3])
+    sub = paddle.sparse.nn.SubmConv2D(3, 5, 3)
+    y = sub(sp)
+    assert list(y.shape) == [1, 4, 4, 5] and y.nnz() == 2
+    conv = paddle.sparse.nn.Conv2D(3, 5, 3)
+    z = conv(sp)
+    assert list(z.shape) == [1, 2, 2, 5]
+    import torch
+    import torch.nn.functional as F
+
+    ref = F.conv2d(sp.to_dense().permute(0, 3, 1, 2), conv.weight.permute(3, 2, 0, 1), conv.bias).permute(0, 2, 3, 1)
+    zd = z.to_dense()
+    mask = zd.abs().sum(-1) > 0
+    assert torch.allclose(torch.as_tensor(zd)[mask], torch.as_tensor(ref)[mask], atol=1e-5)
+    assert paddle.sparse.nn.functional.subm_conv2d_igemm(sp, sub.weight, sub.bias).nnz() == 2
+
+
+def test_misc_fillers():
+    import paddle_b200.distribution.transform as T
+
+    assert T.ExpTransform is paddle.distribution.ExpTransform
+    assert paddle.nn.quant.Stub()(3) == 3
+    assert paddle.inference._get_phi_kernel_name("elementwise_add") == "add"
+    assert paddle.incubate.optimizer.LBFGS is paddle.optimizer.LBFGS
+
+    class L(paddle.nn.Layer):
+        @paddle.amp.debugging.check_layer_numerics
+        def forward(self, x):
+            return x / 0.0
+
+    with pytest.raises(RuntimeError):
+        L()(paddle.ones([2]))
