@@ -64,3 +64,16 @@ class XPUPlace:
 
 
 IPUPlace = XPUPlace
+
+
+def side_stream(device=None):
+    """A stream for work that overlaps the compute stream (H2D prefetch, bucket reductions). With `FLAGS_b200_sync_debug`
+    the current stream is returned instead, which serialises everything: a failure that disappears under the flag is a
+    missing event / record_stream (docs/race_detection.md)."""
+    import torch
+
+    from ..framework.flags import get_flags
+
+    if get_flags("FLAGS_b200_sync_debug")["FLAGS_b200_sync_debug"]:
+        return torch.cuda.current_stream(device)
+    return torch.cuda.Stream(device=device)

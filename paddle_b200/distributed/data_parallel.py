@@ -76,7 +76,9 @@ class DataParallel(Layer):
         for p in self._params:
             p.register_post_accumulate_grad_hook(self._make_hook(p))
         if self._params[0].is_cuda:
-            self._stream = torch.cuda.Stream()
+            from ..device import side_stream
+
+            self._stream = side_stream()
 
     def _symm_grad_allocator(self):
         """Gradient slabs are placed in the symmetric peer heap when they fit: the bucket all-reduce then runs in place over

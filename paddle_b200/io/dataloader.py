@@ -247,7 +247,9 @@ class DataLoader:
             for i, samples in enumerate(self._sample_batches()):
                 yield self._collate(samples, i % nslots)
             return
-        stream = torch.cuda.Stream(device=self._device)
+        from ..device import side_stream
+
+        stream = side_stream(self._device)
         q = queue.Queue(maxsize=self.prefetch_factor)
         stop = object()
 

@@ -77,3 +77,61 @@ def test_misc_fillers():
 
     with pytest.raises(RuntimeError):
         L()(paddle.ones([2]))
+
+
+def test_distributed_passes_and_communication():
+    import paddle_b200.distributed.communication as comm
+    from paddle_b200.distributed.passes import PassContext, PassManager, new_pass
+
+    assert comm.all_reduce is paddle.distributed.all_reduce and hasattr(comm.group, "new_group") and hasattr(comm.stream, "all_reduce")
+    paddle.enable_static()
+    try:
+        main = paddle.static.Program()
+        with paddle.static.program_guard(main):
+            x = paddle.static.data("x", [4, 8], "float32")
+            w = paddle.static.create_parameter([8, 8], "float32")
+            y = paddle.matmul(x, w)
+            z = paddle.nn.functional.relu(y)
+        pm = PassManager([new_pass("auto_parallel_bf16"), new_pass("auto_parallel_gradient_merge_pass", {"k_steps": 4})], context=PassContext())
+        ctx = pm.apply([main])
+        assert main._dist_attrs["amp"]["wrapped"] >= 1 and main._dist_attrs["gradient_merge"]["k_steps"] == 4 and len(ctx.passes) == 2
+        exe = paddle.static.Executor()
+        out, = exe.run(main, feed={"x": np.ones((4, 8), "float32")}, fetch_list=[z])
+        assert out.shape == (4, 8)
+    finally:
+        paddle.disable_static()
+
+
+def test_elastic_manager_membership():
+    import time
+
+    from paddle_b200.distributed.fleet import elastic
+
+    a = elastic.ElasticManager(np="1:2", host="a", heartbeat_s=0.05, ttl_s=0.3).start_heartbeat()
+    assert a.wait(2) and a.status() == "running"
+    b = elastic.ElasticManager(np="1:2", host="b", store=a.store, heartbeat_s=0.05, ttl_s=0.3).start_heartbeat()
+    time.sleep(0.15)
+    assert a.status() == elastic.ElasticStatus.RESTART and a.hosts() == ["a", "b"]
+    b.exit()
+    time.sleep(0.5)
+    assert a.hosts() == ["a"]
+    a.exit()
+    c = elastic.ElasticManager(np="2", host="c", heartbeat_s=0.05, ttl_s=0.3).start_heartbeat()
+    assert c.status() == elastic.ElasticStatus.HOLD and not c.wait(0.3)
+    c.exit()
+
+
+def test_tensorrt_convert_api(tmp_path):
+    import paddle_b200.tensorrt as trt
+
+    net = paddle.nn.Sequential(paddle.nn.Linear(8, 16), paddle.nn.ReLU(), paddle.nn.Linear(16, 4))
+    cfg = trt.TensorRTConfig([trt.Input(min_input_shape=(1, 8), optim_input_shape=(4, 8), max_input_shape=(8, 8))], precision_mode=trt.PrecisionMode.FP32)
+    fn = trt.convert_loaded_model(net, cfg)
+    x = paddle.ones([4, 8])
+    assert np.allclose(fn(x).numpy(), net(x).numpy(), atol=1e-6)
+    prefix = str(tmp_path / "m")
+    paddle.jit.save(net, prefix, input_spec=[paddle.static.InputSpec([None, 8], "float32")])
+    cfg.save_model_dir = str(tmp_path / "out" / "m")
+    fn2 = trt.convert(prefix, cfg)
+    assert np.allclose(fn2(x).numpy(), net(x).numpy(), atol=1e-5)
+    assert np.allclose(paddle.jit.load(cfg.save_model_dir)(x).numpy(), net(x).numpy(), atol=1e-5)
