@@ -8,6 +8,7 @@
 
 #include "include/b200_ops.h"
 #include "runtime/runtime.h"
+#include "runtime/tracer.h"
 
 namespace {
 
@@ -540,6 +541,16 @@ Tensor attention_bwd_packed(const Tensor& qkv, int64_t nh, int64_t nkv, const Te
   return dqkv;
 }
 
+// Every kernel entry point is bound through traced(): when the tracer is on (profiler.Profiler) the call becomes a host range
+// plus a cudaEvent pair on the launching stream; when it is off the cost is one relaxed atomic load.
+template <typename R, typename... A>
+auto traced(const char* name, R (*f)(A...)) {
+  return [name, f](A... a) -> R {
+    b200::runtime::TraceScope scope(name);
+    return f(std::forward<A>(a)...);
+  };
+}
+
 int64_t launch_count() { return g_launches.load(); }
 void reset_launch_count() { g_launches.store(0); }
 void add_launches(int64_t n) { g_launches += n; }
@@ -547,37 +558,37 @@ void add_launches(int64_t n) { g_launches += n; }
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
-  m.def("rms_norm_fwd", &rms_norm_fwd);
-  m.def("rms_norm_bwd", &rms_norm_bwd);
-  m.def("layer_norm_fwd", &layer_norm_fwd);
-  m.def("layer_norm_bwd", &layer_norm_bwd);
-  m.def("swiglu_fwd", &swiglu_fwd);
-  m.def("swiglu_bwd", &swiglu_bwd);
-  m.def("rope", &rope);
-  m.def("rope_packed_", &rope_packed_);
-  m.def("softmax_ce_fwd", &softmax_ce_fwd);
-  m.def("softmax_ce_bwd", &softmax_ce_bwd);
-  m.def("vp_ce_max", &vp_ce_max);
-  m.def("vp_ce_sumexp", &vp_ce_sumexp);
-  m.def("vp_ce_bwd", &vp_ce_bwd);
-  m.def("adamw_step", &adamw_step);
-  m.def("grad_sq_norm", &grad_sq_norm);
-  m.def("scale_inplace", &scale_inplace);
-  m.def("sgd_step", &sgd_step);
-  m.def("lamb_step", &lamb_step);
+  m.def("rms_norm_fwd", traced("rms_norm_fwd", &rms_norm_fwd));
+  m.def("rms_norm_bwd", traced("rms_norm_bwd", &rms_norm_bwd));
+  m.def("layer_norm_fwd", traced("layer_norm_fwd", &layer_norm_fwd));
+  m.def("layer_norm_bwd", traced("layer_norm_bwd", &layer_norm_bwd));
+  m.def("swiglu_fwd", traced("swiglu_fwd", &swiglu_fwd));
+  m.def("swiglu_bwd", traced("swiglu_bwd", &swiglu_bwd));
+  m.def("rope", traced("rope", &rope));
+  m.def("rope_packed_", traced("rope_packed_", &rope_packed_));
+  m.def("softmax_ce_fwd", traced("softmax_ce_fwd", &softmax_ce_fwd));
+  m.def("softmax_ce_bwd", traced("softmax_ce_bwd", &softmax_ce_bwd));
+  m.def("vp_ce_max", traced("vp_ce_max", &vp_ce_max));
+  m.def("vp_ce_sumexp", traced("vp_ce_sumexp", &vp_ce_sumexp));
+  m.def("vp_ce_bwd", traced("vp_ce_bwd", &vp_ce_bwd));
+  m.def("adamw_step", traced("adamw_step", &adamw_step));
+  m.def("grad_sq_norm", traced("grad_sq_norm", &grad_sq_norm));
+  m.def("scale_inplace", traced("scale_inplace", &scale_inplace));
+  m.def("sgd_step", traced("sgd_step", &sgd_step));
+  m.def("lamb_step", traced("lamb_step", &lamb_step));
   m.def("gemm_supported", &gemm_supported);
-  m.def("gemm", &gemm, pybind11::arg("a"), pybind11::arg("b"), pybind11::arg("bias") = pybind11::none(), pybind11::arg("a_is_km") = false,
+  m.def("gemm", traced("gemm", &gemm), pybind11::arg("a"), pybind11::arg("b"), pybind11::arg("bias") = pybind11::none(), pybind11::arg("a_is_km") = false,
         pybind11::arg("b_is_nk") = false, pybind11::arg("epilogue") = 0, pybind11::arg("out") = pybind11::none(),
         pybind11::arg("out_dtype") = pybind11::none(), pybind11::arg("rs_dst") = std::vector<int64_t>(), pybind11::arg("rs_rows") = 0,
         pybind11::arg("ag_src") = std::vector<int64_t>(), pybind11::arg("ag_pad") = std::vector<int64_t>(), pybind11::arg("ag_flags") = pybind11::none(),
         pybind11::arg("ag_rank") = 0, pybind11::arg("ag_rows") = 0, pybind11::arg("ag_epoch") = 0);
-  m.def("gemm_fp8", &gemm_fp8);
-  m.def("decode_attention", &decode_attention);
+  m.def("gemm_fp8", traced("gemm_fp8", &gemm_fp8));
+  m.def("decode_attention", traced("decode_attention", &decode_attention));
   m.def("attention_supported", &attention_supported);
-  m.def("attention_fwd", &attention_fwd, pybind11::arg("q"), pybind11::arg("k"), pybind11::arg("v"), pybind11::arg("scale"), pybind11::arg("causal"),
+  m.def("attention_fwd", traced("attention_fwd", &attention_fwd), pybind11::arg("q"), pybind11::arg("k"), pybind11::arg("v"), pybind11::arg("scale"), pybind11::arg("causal"),
         pybind11::arg("out_seq_major") = false);
-  m.def("attention_bwd", &attention_bwd);
-  m.def("attention_bwd_packed", &attention_bwd_packed, pybind11::arg("qkv"), pybind11::arg("nh"), pybind11::arg("nkv"), pybind11::arg("out"),
+  m.def("attention_bwd", traced("attention_bwd", &attention_bwd));
+  m.def("attention_bwd_packed", traced("attention_bwd_packed", &attention_bwd_packed), pybind11::arg("qkv"), pybind11::arg("nh"), pybind11::arg("nkv"), pybind11::arg("out"),
         pybind11::arg("lse"), pybind11::arg("d_out"), pybind11::arg("scale"), pybind11::arg("causal"), pybind11::arg("seq_major") = false);
   m.def("launch_count", &launch_count);
   m.def("reset_launch_count", &reset_launch_count);

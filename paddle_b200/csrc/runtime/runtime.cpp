@@ -6,6 +6,7 @@ void bind(pybind11::module_& m) {
   bind_symm(m);
   bind_loader(m);
   bind_graph(m);
+  bind_tracer(m);
 }
 }  // namespace runtime
 }  // namespace b200

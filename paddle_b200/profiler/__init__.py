@@ -99,6 +99,25 @@ def export_protobuf(dir_name, worker_name=None):
 _active = [None]
 
 
+def _native():
+    """The C++ range tracer (csrc/runtime/tracer.cpp) when the extension is built; None otherwise."""
+    try:
+        from .. import _build
+
+        return _build.load(required=False)
+    except Exception:
+        return None
+
+
+def kernel_statistics(prof):
+    """{kernel entry: (calls, host_ms, device_ms)} of the last recorded cycles."""
+    out = {}
+    for name, typ, tid, depth, t0, t1, d0, dd in prof._kernel_events:
+        c, h, g = out.get(name, (0, 0.0, 0.0))
+        out[name] = (c + 1, h + (t1 - t0) / 1e6, g + max(dd, 0.0) / 1e3)
+    return out
+
+
 class RecordEvent:
     """User range. Works as context manager / begin-end pair. Parity: profiler/utils.py:RecordEvent."""
 
@@ -150,6 +169,7 @@ class Profiler:
         self.timer_only = timer_only
         self.step_num = 0
         self._events, self._recording = [], False
+        self._kernel_events = []   # (name, type, tid, depth, t0_ns, t1_ns, dev_t0_us, dev_dur_us) from the native tracer
         self._step_times, self._t_step = [], None
         self._torch_prof = None
         self._mem = profile_memory
@@ -166,6 +186,11 @@ class Profiler:
             acts = [torch.profiler.ProfilerActivity.CPU] + ([torch.profiler.ProfilerActivity.CUDA] if torch.cuda.is_available() and ProfilerTarget.GPU in self.targets else [])
             self._torch_prof = torch.profiler.profile(activities=acts, profile_memory=self._mem)
             self._torch_prof.__enter__()
+        if rec and not self._recording:
+            C = _native()
+            if C is not None:
+                C.tracer_collect()   # drop anything recorded outside a cycle
+                C.tracer_enable(2 if (ProfilerTarget.GPU in self.targets and torch.cuda.is_available()) else 1)
         self._recording = rec
         self._state = st
 
@@ -185,6 +210,10 @@ class Profiler:
             self._torch_prof.__exit__(None, None, None)
             self._last_prof, self._torch_prof = self._torch_prof, None
         self._recording = False
+        C = _native()
+        if C is not None and C.tracer_mode():
+            self._kernel_events.extend(C.tracer_collect())
+            C.tracer_enable(0)
         if self.on_trace_ready:
             self.on_trace_ready(self)
 
@@ -219,6 +248,10 @@ class Profiler:
             evs.append({"name": name, "cat": typ, "ph": "X", "ts": t0 / 1e3, "dur": (t1 - t0) / 1e3, "pid": os.getpid(), "tid": 0})
             if ev is not None:
                 evs.append({"name": name, "cat": "gpu:" + typ, "ph": "X", "ts": t0 / 1e3, "dur": ev[0].elapsed_time(ev[1]) * 1e3, "pid": os.getpid(), "tid": 1})
+        for name, typ, tid, depth, t0, t1, d0, dd in self._kernel_events:
+            evs.append({"name": name, "cat": "kernel_launch", "ph": "X", "ts": t0 / 1e3, "dur": (t1 - t0) / 1e3, "pid": os.getpid(), "tid": 100 + tid})
+            if dd >= 0:
+                evs.append({"name": name, "cat": "kernel", "ph": "X", "ts": d0, "dur": dd, "pid": os.getpid(), "tid": "stream"})
         d = os.path.dirname(path)
         if d:
             os.makedirs(d, exist_ok=True)
@@ -244,6 +277,15 @@ class Profiler:
         for name, typ, t0, t1, ev in self._events:
             agg[name][0] += 1
             agg[name][1] += (t1 - t0) / 1e6
+        kagg = defaultdict(lambda: [0, 0.0, 0.0])
+        for name, typ, tid, depth, t0, t1, d0, dd in self._kernel_events:
+            kagg[name][0] += 1
+            kagg[name][1] += (t1 - t0) / 1e6
+            kagg[name][2] += max(dd, 0.0) / 1e3
+        if kagg:
+            print(f"{'kernel entry (native tracer)':<40}{'calls':>8}{'host ms':>14}{'device ms':>14}")
+            for k, (c, h, g) in sorted(kagg.items(), key=lambda kv: -(kv[1][2] or kv[1][1])):
+                print(f"{k:<40}{c:>8}{h:>14.3f}{g:>14.3f}")
         if agg:
             print(f"{'user range':<40}{'calls':>8}{'total ms':>14}")
             for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):

@@ -135,3 +135,47 @@ def test_tensorrt_convert_api(tmp_path):
     fn2 = trt.convert(prefix, cfg)
     assert np.allclose(fn2(x).numpy(), net(x).numpy(), atol=1e-5)
     assert np.allclose(paddle.jit.load(cfg.save_model_dir)(x).numpy(), net(x).numpy(), atol=1e-5)
+
+
+def test_native_tracer_and_profiler(tmp_path):
+    """C++ range tracer (csrc/runtime/tracer.cpp): nesting, threads, chrome export; wired into profiler.Profiler."""
+    import json
+    import threading
+
+    from paddle_b200 import _build, profiler
+
+    C = _build.load(required=False)
+    if C is None:
+        pytest.skip("native extension not built")
+    C.tracer_collect()
+    C.tracer_enable(1)
+    C.tracer_begin("outer", 0)
+    C.tracer_begin("inner", 1)
+    C.tracer_end()
+    C.tracer_end()
+    t = threading.Thread(target=lambda: (C.tracer_begin("thr", 2), C.tracer_end()))
+    t.start()
+    t.join()
+    evs = {e[0]: e for e in C.tracer_collect()}
+    assert set(evs) == {"outer", "inner", "thr"} and evs["inner"][3] == 1 and evs["outer"][3] == 0
+    assert evs["outer"][4] <= evs["inner"][4] <= evs["inner"][5] <= evs["outer"][5] and evs["thr"][2] != evs["outer"][2]
+    C.tracer_begin('we"ird', 0)
+    C.tracer_end()
+    p = str(tmp_path / "t.json")
+    assert C.tracer_export_chrome(p, 1) == 1 and json.load(open(p))["traceEvents"][0]["name"] == 'we"ird'
+    C.tracer_enable(0)
+    C.tracer_begin("ignored", 0)
+    C.tracer_end()
+    assert C.tracer_collect() == []
+
+    with profiler.Profiler(targets=[profiler.ProfilerTarget.CPU]) as prof:
+        with profiler.RecordEvent("user"):
+            C.tracer_begin("fake_kernel", 1)
+            C.tracer_end()
+        prof.step()
+    stats = profiler.kernel_statistics(prof)
+    assert stats["fake_kernel"][0] == 1
+    out = str(tmp_path / "trace.json")
+    prof.export(out)
+    names = {e.get("name") for e in json.load(open(out))["traceEvents"]}
+    assert "fake_kernel" in names and "user" in names
