@@ -18,6 +18,7 @@
 #include "runtime.h"
 #include "../include/b200_comm.h"
 #include "../include/b200_ops.h"
+#include "offset_allocator.h"
 
 namespace b200 {
 namespace runtime {
@@ -35,7 +36,7 @@ class SymmHeap {
     ck(cudaMalloc(&base_, bytes_), "cudaMalloc");
     ck(cudaMemset(base_, 0, bytes_), "cudaMemset");
     ck(cudaDeviceSynchronize(), "sync");
-    cursor_ = (signal_bytes_ + 1023) / 1024 * 1024;
+    alloc_ = std::make_unique<BestFitAllocator>((signal_bytes_ + 1023) / 1024 * 1024, bytes_, 256);
   }
   ~SymmHeap() {
     for (size_t i = 0; i < peers_.size(); ++i)
@@ -72,15 +73,31 @@ class SymmHeap {
   // Single-process mode (world 1, or tests): the "peer" table just points at ourselves.
   void open_self() { open_peers(std::vector<std::string>(1), 0); }
 
+  // Best-fit with coalescing; with no frees in between this degenerates to the bump order, and identical call sequences
+  // give identical offsets on every rank (the heap stays symmetric).
   int64_t alloc(int64_t nbytes, int64_t align) {
-    if (align < 256) align = 256;
-    int64_t off = (cursor_ + align - 1) / align * align;
-    if (off + nbytes > bytes_) throw std::runtime_error("symm_heap: out of symmetric memory (" + std::to_string(off + nbytes) + " > " + std::to_string(bytes_) + ")");
-    cursor_ = off + nbytes;
-    return off;
+    try {
+      return alloc_->alloc(nbytes, align);
+    } catch (const std::exception& e) {
+      throw std::runtime_error(std::string("symm_heap: out of symmetric memory: ") + e.what());
+    }
   }
-  void reset_cursor(int64_t to) { cursor_ = to; }
-  int64_t cursor() const { return cursor_; }
+  void free(int64_t off) { alloc_->free(off); }
+  void reset_cursor(int64_t to) { alloc_->release_from(to); }
+  // size() - cursor() = largest block that can still be allocated
+  int64_t cursor() const { return bytes_ - alloc_->largest_free(); }
+  pybind11::dict stats() const {
+    pybind11::dict d;
+    d["capacity"] = alloc_->capacity();
+    d["allocated"] = alloc_->in_use();
+    d["peak_allocated"] = alloc_->peak();
+    d["largest_free_block"] = alloc_->largest_free();
+    d["free_blocks"] = alloc_->num_free_blocks();
+    d["live_blocks"] = alloc_->num_live();
+    d["num_allocs"] = alloc_->num_allocs();
+    d["num_frees"] = alloc_->num_frees();
+    return d;
+  }
 
   torch::Tensor tensor(int64_t offset, std::vector<int64_t> sizes, at::ScalarType dtype, int peer) {
     void* b = peer < 0 ? base_ : peers_.at(peer);
@@ -168,7 +185,7 @@ class SymmHeap {
   int64_t bytes_, signal_bytes_;
   int device_;
   void* base_ = nullptr;
-  int64_t cursor_ = 0;
+  std::unique_ptr<BestFitAllocator> alloc_;
   int rank_ = 0, world_ = 1;
   std::vector<void*> peers_;
   void* peer_table_dev_ = nullptr;
@@ -176,12 +193,27 @@ class SymmHeap {
 };
 
 void bind_symm(pybind11::module_& m) {
+  pybind11::class_<BestFitAllocator>(m, "BestFitAllocator")
+      .def(pybind11::init<int64_t, int64_t, int64_t>(), pybind11::arg("begin"), pybind11::arg("end"), pybind11::arg("min_align") = 256)
+      .def("alloc", &BestFitAllocator::alloc, pybind11::arg("nbytes"), pybind11::arg("align") = 256)
+      .def("free", &BestFitAllocator::free)
+      .def("release_from", &BestFitAllocator::release_from)
+      .def("block_size", &BestFitAllocator::block_size)
+      .def("largest_free", &BestFitAllocator::largest_free)
+      .def("free_bytes", &BestFitAllocator::free_bytes)
+      .def("in_use", &BestFitAllocator::in_use)
+      .def("peak", &BestFitAllocator::peak)
+      .def("reset_peak", &BestFitAllocator::reset_peak)
+      .def("num_live", &BestFitAllocator::num_live)
+      .def("num_free_blocks", &BestFitAllocator::num_free_blocks);
   pybind11::class_<SymmHeap, std::shared_ptr<SymmHeap>>(m, "SymmHeap")
       .def(pybind11::init<int64_t, int64_t, int>())
       .def("ipc_handle", &SymmHeap::ipc_handle)
       .def("open_peers", &SymmHeap::open_peers)
       .def("open_self", &SymmHeap::open_self)
       .def("alloc", &SymmHeap::alloc)
+      .def("free", &SymmHeap::free)
+      .def("stats", &SymmHeap::stats)
       .def("reset_cursor", &SymmHeap::reset_cursor)
       .def("cursor", &SymmHeap::cursor)
       .def("tensor", &SymmHeap::tensor)

@@ -82,6 +82,15 @@ class SymmContext:
             self._bufs[key] = off
         return self.heap.tensor(off, list(shape), dtype, -1), off
 
+    def release(self, tag=None):
+        """Give symmetric scratch buffers back to the heap's best-fit allocator (all of them, or those of one tag). Collective in
+        the same sense as `buffer`: every rank must release the same set so later offsets stay symmetric."""
+        for key in [k for k in self._bufs if tag is None or k[0] == tag]:
+            self.heap.free(self._bufs.pop(key))
+
+    def memory_stats(self):
+        return dict(self.heap.stats())
+
     def next_epoch(self):
         self._epoch += 1
         return self._epoch

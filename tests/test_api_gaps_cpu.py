@@ -179,3 +179,43 @@ def test_native_tracer_and_profiler(tmp_path):
     prof.export(out)
     names = {e.get("name") for e in json.load(open(out))["traceEvents"]}
     assert "fake_kernel" in names and "user" in names
+
+
+def test_native_best_fit_allocator():
+    """csrc/runtime/offset_allocator.h (backs the symmetric heap): alignment, reuse, coalescing, no overlap under churn."""
+    import random
+
+    from paddle_b200 import _build
+
+    C = _build.load(required=False)
+    if C is None:
+        pytest.skip("native extension not built")
+    cap = 1 << 20
+    a = C.BestFitAllocator(1024, cap)
+    o1, o2, o3 = a.alloc(1000, 1024), a.alloc(5000, 1024), a.alloc(300)
+    assert (o1, o2) == (1024, 2048) and a.block_size(o2) == 5120 and a.in_use() == 1024 + 5120 + 512
+    a.free(o2)
+    assert a.num_free_blocks() == 2 and a.alloc(4096, 1024) == o2   # best fit reuses the hole
+    rng, live = random.Random(0), {}
+    for _ in range(3000):
+        if live and rng.random() < 0.45:
+            k = rng.choice(list(live))
+            a.free(k)
+            del live[k]
+            continue
+        n, al = rng.randint(1, 20000), rng.choice([256, 1024, 4096])
+        try:
+            o = a.alloc(n, al)
+        except RuntimeError:
+            continue
+        assert o % al == 0 and o >= 1024 and o + n <= cap
+        assert all(o + n <= k or k + v <= o for k, v in live.items())
+        live[o] = n
+    for k in live:
+        a.free(k)
+    a.release_from(0)
+    assert a.in_use() == 0 and a.num_free_blocks() == 1 and a.largest_free() == cap - 1024 and a.peak() > 0
+    with pytest.raises(RuntimeError, match="out of memory"):
+        a.alloc(cap * 2)
+    with pytest.raises(RuntimeError):
+        a.free(12345)
