@@ -7,6 +7,7 @@ void bind(pybind11::module_& m) {
   bind_loader(m);
   bind_graph(m);
   bind_tracer(m);
+  bind_data_feed(m);
 }
 }  // namespace runtime
 }  // namespace b200

@@ -9,5 +9,6 @@ void bind_symm(pybind11::module_& m);
 void bind_loader(pybind11::module_& m);
 void bind_graph(pybind11::module_& m);
 void bind_tracer(pybind11::module_& m);
+void bind_data_feed(pybind11::module_& m);
 }  // namespace runtime
 }  // namespace b200

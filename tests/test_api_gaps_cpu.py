@@ -219,3 +219,58 @@ def test_native_best_fit_allocator():
         a.alloc(cap * 2)
     with pytest.raises(RuntimeError):
         a.free(12345)
+
+
+def test_multislot_dataset_native_feed(tmp_path):
+    """InMemoryDataset / QueueDataset over the native multi-slot feed (csrc/runtime/data_feed.cpp), fed by MultiSlotDataGenerator."""
+    from paddle_b200 import _build
+    from paddle_b200.distributed import InMemoryDataset, QueueDataset, fleet
+
+    if _build.load(required=False) is None:
+        pytest.skip("native extension not built")
+
+    class Gen(fleet.MultiSlotDataGenerator):
+        def __init__(self, base):
+            super().__init__()
+            self.base = base
+
+        def generate_sample(self, line):
+            def it():
+                for i in range(5):
+                    k = self.base + i
+                    yield [("ids", list(range(k, k + 1 + i % 3))), ("dense", [k * 0.5, k * 0.25]), ("label", [k % 2])]
+            return it
+
+    files = []
+    for j, base in enumerate((0, 100)):
+        p = tmp_path / f"part-{j}"
+        p.write_text("".join(Gen(base).run_from_memory()))
+        files.append(str(p))
+    ds = InMemoryDataset()
+    ds.init(batch_size=4, thread_num=2, use_var=[("ids", "int64"), ("dense", "float32"), ("label", "int64")])
+    ds.set_filelist(files)
+    ds.load_into_memory()
+    assert ds.get_memory_data_size() == 10
+    batches = list(ds)
+    assert [len(b["label"]) for b in batches] == [4, 4, 2]
+    b0 = batches[0]
+    vals, lod = b0["ids"]                       # ragged slot -> (values, lod)
+    assert list(lod) == [0, 1, 3, 6, 7] and list(vals[:3]) == [0, 1, 2]
+    assert b0["dense"].shape == (4, 2) and np.allclose(b0["dense"][1], [0.5, 0.25]) and b0["label"].shape == (4, 1)
+    ds.local_shuffle(seed=3)
+    labels = np.concatenate([b["dense"][:, 0] for b in ds])
+    assert sorted(labels) == sorted(k * 0.5 for k in list(range(5)) + list(range(100, 105))) and list(labels) != sorted(labels)
+    ds.global_shuffle()
+    assert ds.get_shuffle_data_size() == 10
+    ds.release_memory()
+    assert ds.get_memory_data_size() == 0
+
+    q = QueueDataset()
+    q.init(batch_size=3, use_var=[("ids", "int64"), ("dense", "float32"), ("label", "int64")])
+    q.set_filelist(files)
+    assert sum(len(b["label"]) for b in q) == 10
+    bad = tmp_path / "bad"
+    bad.write_text("2 1\n")
+    ds.set_filelist([str(bad)])
+    with pytest.raises(RuntimeError, match="line 1"):
+        ds.load_into_memory()
