@@ -54,7 +54,15 @@ Maxout = _act("Maxout", F.maxout, ["groups", "axis"], dict(axis=1))
 Softmax = _act("Softmax", F.softmax, ["axis"], dict(axis=-1))
 LogSoftmax = _act("LogSoftmax", F.log_softmax, ["axis"], dict(axis=-1))
 GLU = _act("GLU", F.glu, ["axis"], dict(axis=-1))
-RReLU = _act("RReLU", lambda x, lower=1. / 8, upper=1. / 3: F.rrelu(x, lower, upper, True), ["lower", "upper"], dict(lower=1. / 8, upper=1. / 3))
+class RReLU(Layer):
+    """Randomised leaky ReLU: slope ~ U(lower, upper) in training, (lower + upper) / 2 in eval. Parity: nn/layer/activation.py:RReLU."""
+
+    def __init__(self, lower=1. / 8, upper=1. / 3, name=None):
+        super().__init__()
+        self.lower, self.upper = lower, upper
+
+    def forward(self, x):
+        return F.rrelu(x, self.lower, self.upper, self.training)
 
 
 class Softmax2D(Layer):
@@ -148,3 +156,19 @@ class AdaptiveLogSoftmaxWithLoss(Layer):
 
     def forward(self, input, label):
         return F.adaptive_log_softmax_with_loss(input, label, self.head_weight, self.tail_weights, self.cutoffs, self.head_bias)
+
+    def log_prob(self, input):
+        """Full [N, n_classes] log-probabilities."""
+        import torch
+
+        x = input
+        head = x @ self.head_weight + (self.head_bias if self.head_bias is not None else 0)
+        head_lp = F.log_softmax(head, -1)
+        parts = [head_lp[:, :self.shortlist]]
+        for i, (p, c) in enumerate(self.tail_weights):
+            tail_lp = F.log_softmax((x @ p) @ c, -1)
+            parts.append(tail_lp + head_lp[:, self.shortlist + i:self.shortlist + i + 1])
+        return torch.cat(parts, -1)
+
+    def predict(self, input):
+        return self.log_prob(input).argmax(-1)
