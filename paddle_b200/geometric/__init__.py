@@ -89,13 +89,19 @@ def reindex_graph(x, neighbors, count, value_buffer=None, index_buffer=None, nam
 
 
 def reindex_heter_graph(x, neighbors, count, value_buffer=None, index_buffer=None, name=None):
+    """Several edge types over the same centre nodes: one shared id space, per-type (src, dst) lists concatenated."""
     nb = torch.cat([_raw(n) for n in neighbors])
-    src, _, out_nodes = reindex_graph(x, nb, torch.cat([_raw(c) for c in count]))
-    dsts, off = [], 0
     xr = _raw(x)
-    rank = {int(v): i for i, v in enumerate(_raw(out_nodes).tolist())}
-    for c in count:
-        dsts.append(torch.repeat_interleave(torch.tensor([rank[int(v)] for v in xr.tolist()]), _raw(c).long()))
+    nodes = torch.cat([xr, nb])
+    uniq, inv = torch.unique(nodes, return_inverse=True)
+    first = torch.full((uniq.numel(),), nodes.numel(), dtype=torch.int64, device=nodes.device)
+    first.scatter_reduce_(0, inv, torch.arange(nodes.numel(), device=nodes.device), "amin")
+    order = torch.argsort(first)
+    rank = torch.empty_like(order)
+    rank[order] = torch.arange(order.numel(), device=order.device)
+    new_ids = rank[inv]
+    src, out_nodes = _w(new_ids[xr.numel():]), _w(uniq[order])
+    dsts = [torch.repeat_interleave(new_ids[: xr.numel()], _raw(c).long()) for c in count]
     return src, _w(torch.cat(dsts)), out_nodes
 
 

@@ -199,7 +199,7 @@ def mask_as(x, mask, name=None):
 
 
 def pca_lowrank(x, q=None, center=True, niter=2, name=None):
-    u, s, v = torch.pca_lowrank(_dense(x), q=q, center=center, niter=niter)
+    u, s, v = torch.pca_lowrank(_dense(x).as_subclass(torch.Tensor), q=q, center=center, niter=niter)
     return _w(u), _w(s), _w(v)
 
 

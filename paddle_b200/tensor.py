@@ -162,6 +162,8 @@ class Tensor(torch.Tensor):
         t = self.detach().as_subclass(torch.Tensor)
         if t.device.type != "cpu":
             t = t.cpu()
+        if t.is_conj() or t.is_neg():   # lazy conj / neg views (fft, linalg) have no numpy form
+            t = t.resolve_conj().resolve_neg()
         if t.dtype == torch.bfloat16:
             return t.view(torch.int16).numpy().view(np.uint16)
         if t.dtype in (torch.float8_e4m3fn, torch.float8_e5m2):

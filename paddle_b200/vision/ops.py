@@ -75,6 +75,20 @@ def _bilinear(feat, y, x):
     return v * valid.to(v.dtype)
 
 
+def _bilinear_zero(feat, y, x):
+    """Bilinear sampling with zero padding: every out-of-range corner contributes 0 (deformable-conv semantics)."""
+    C, H, W = feat.shape
+    y0, x0 = y.floor(), x.floor()
+    ly, lx = y - y0, x - x0
+    out = 0
+    for dy, wy in ((0, 1 - ly), (1, ly)):
+        for dx, wx in ((0, 1 - lx), (1, lx)):
+            yi, xi = (y0 + dy).long(), (x0 + dx).long()
+            ok = (yi >= 0) & (yi < H) & (xi >= 0) & (xi < W)
+            out = out + feat[:, yi.clamp(0, H - 1), xi.clamp(0, W - 1)] * (wy * wx * ok.to(feat.dtype))
+    return out
+
+
 def roi_align(x, boxes, boxes_num, output_size, spatial_scale=1.0, sampling_ratio=-1, aligned=True, name=None):
     x, boxes = _raw(x), _raw(boxes).float()
     nums = _raw(boxes_num).tolist()
@@ -170,7 +184,7 @@ def deform_conv2d(x, offset, weight, bias=None, stride=1, padding=0, dilation=1,
                 ky, kx = divmod(k, kw)
                 yy = base_y + ky * d[0] + off[n, g, k, 0]
                 xx = base_x + kx * d[1] + off[n, g, k, 1]
-                v = _bilinear(feat, yy, xx)
+                v = _bilinear_zero(feat, yy, xx)
                 if m is not None:
                     v = v * m[n, g, k]
                 cols[n, g * cpg:(g + 1) * cpg, k] = v

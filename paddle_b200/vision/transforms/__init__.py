@@ -214,8 +214,8 @@ def rotate(img, angle, interpolation="nearest", expand=False, center=None, fill=
     c, s = math.cos(th), math.sin(th)
     oh, ow = h, w
     if expand:
-        ow = int(math.ceil(abs(w * c) + abs(h * s)))
-        oh = int(math.ceil(abs(w * s) + abs(h * c)))
+        ow = int(math.ceil(round(abs(w * c) + abs(h * s), 6)))
+        oh = int(math.ceil(round(abs(w * s) + abs(h * c), 6)))
     ocx, ocy = (ow - 1) / 2.0, (oh - 1) / 2.0
     m = [[c, -s, cx - c * ocx + s * ocy], [s, c, cy - s * ocx - c * ocy]]
     return _like(_affine_grid_sample(a, m, (oh, ow), interpolation, fill if isinstance(fill, numbers.Number) else 0), img)
