@@ -24,7 +24,8 @@ class IterableDataset(Dataset):
         raise RuntimeError("IterableDataset does not support __getitem__")
 
     def __len__(self):
-        raise RuntimeError("IterableDataset does not support __len__")
+        # TypeError (not RuntimeError) so that list(ds) / length_hint fall back to plain iteration
+        raise TypeError("IterableDataset does not support __len__")
 
 
 class TensorDataset(Dataset):
