@@ -12,3 +12,9 @@ def in_dygraph_mode():
     from ..static import in_dynamic_mode
 
     return in_dynamic_mode()
+
+
+def create_lod_tensor(data, recursive_seq_lens, place=None):
+    from ..static.nn.sequence import create_lod_tensor as _c
+
+    return _c(data, recursive_seq_lens, place)

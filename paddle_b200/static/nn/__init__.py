@@ -204,13 +204,6 @@ def py_func(func, x, out, backward_func=None, skip_vars_in_backward_input=None):
     return func(*x) if isinstance(x, (list, tuple)) else func(x)
 
 
-def sequence_softmax(input, use_cudnn=False, name=None):
-    return F.softmax(input, -1)
-
-
-def _seq_unsupported(*a, **k):
-    raise NotImplementedError("LoD sequence ops require LoDTensor inputs; use padded tensors + sequence_mask instead")
-
-
-sequence_conv = sequence_pool = sequence_first_step = sequence_last_step = sequence_slice = sequence_expand = _seq_unsupported
-sequence_expand_as = sequence_pad = sequence_unpad = sequence_reshape = sequence_scatter = sequence_enumerate = sequence_reverse = sequence_concat = _seq_unsupported
+from .sequence import (sequence_concat, sequence_conv, sequence_enumerate, sequence_expand, sequence_expand_as, sequence_first_step,  # noqa: F401,E402
+                       sequence_last_step, sequence_pad, sequence_pool, sequence_reshape, sequence_reverse, sequence_scatter, sequence_slice,
+                       sequence_softmax, sequence_unpad)

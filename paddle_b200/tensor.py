@@ -170,6 +170,31 @@ class Tensor(torch.Tensor):
             return t.view(torch.uint8).numpy()
         return t.numpy()
 
+    # ---- LoD (level-of-detail offsets of packed variable-length sequences; used by static.nn.sequence_* ops) ----
+    def lod(self):
+        return [list(o) for o in self.__dict__.get("_lod", [])]
+
+    def set_lod(self, lod):
+        self.__dict__["_lod"] = [[int(v) for v in o] for o in lod]
+        return self
+
+    def recursive_sequence_lengths(self):
+        return [[b - a for a, b in zip(o[:-1], o[1:])] for o in self.__dict__.get("_lod", [])]
+
+    def set_recursive_sequence_lengths(self, lens):
+        lod = []
+        for l in lens:
+            o = [0]
+            for n in l:
+                o.append(o[-1] + int(n))
+            lod.append(o)
+        self.__dict__["_lod"] = lod
+        return self
+
+    def has_valid_recursive_sequence_lengths(self):
+        lod = self.__dict__.get("_lod", [])
+        return bool(lod) and lod[-1][-1] == self.shape[0] and all(a <= b for o in lod for a, b in zip(o[:-1], o[1:]))
+
     def __array__(self, dtype=None, copy=None):
         a = self.numpy()
         if a.dtype == np.uint16 and self.dtype == torch.bfloat16:
