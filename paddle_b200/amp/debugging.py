@@ -50,12 +50,24 @@ def enable_tensor_checker(checker_config):
     _checker["enabled"] = bool(checker_config.enable)
     if checker_config.enable:
         torch.autograd.set_detect_anomaly(True, check_nan=True)
+        if checker_config.output_dir and checker_config.debug_mode in (DebugMode.DUMP_ALL, DebugMode.CHECK_ALL, DebugMode.CHECK_ALL_AND_ABORT,
+                                                                       DebugMode.CHECK_ALL_FOR_OVERFLOW):
+            from .accuracy_compare import TensorDumpMode
+
+            mode = TensorDumpMode(checker_config.output_dir, checker_config.checked_op_list, checker_config.skipped_op_list,
+                                  abort_on_nonfinite=checker_config.debug_mode == DebugMode.CHECK_ALL_AND_ABORT)
+            mode.__enter__()
+            _checker["dump"] = mode
 
 
 def disable_tensor_checker():
     set_flags({"FLAGS_check_nan_inf": False})
     _checker["enabled"] = False
     torch.autograd.set_detect_anomaly(False)
+    mode = _checker.pop("dump", None)
+    if mode is not None:
+        mode.__exit__(None, None, None)
+        mode.close()
 
 
 _op_stats = defaultdict(lambda: [0, 0, 0, 0])  # fp16, bf16, fp32, other
@@ -102,7 +114,10 @@ def collect_operator_stats():
 
 
 def compare_accuracy(dump_path, another_dump_path, output_filename, loss_scale=1, dump_all_tensors=False):
-    raise NotImplementedError("compare_accuracy needs dumped tensor logs (DebugMode.DUMP_ALL); not produced in this build")
+    """Compare the per-op tensor logs of two runs (TensorCheckerConfig(output_dir=..., debug_mode=DebugMode.DUMP_ALL))."""
+    from .accuracy_compare import compare_accuracy as _cmp
+
+    return _cmp(dump_path, another_dump_path, output_filename, loss_scale, dump_all_tensors)
 
 
 def check_layer_numerics(func):

@@ -118,7 +118,29 @@ def get_window(window, win_length, fftbins=True, dtype="float64"):
         a = [0.3635819, 0.4891775, 0.1365995, 0.0106411]
         w = a[0] - a[1] * torch.cos(2 * math.pi * n / (M - 1)) + a[2] * torch.cos(4 * math.pi * n / (M - 1)) - a[3] * torch.cos(6 * math.pi * n / (M - 1))
     elif name == "taylor":
-        raise NotImplementedError("taylor window")
+        # Taylor window (nbar nearly-constant sidelobes at `sll` dB below the main lobe), normalised to 1 at the centre
+        nbar = int(args[0]) if len(args) > 0 else 4
+        sll = float(args[1]) if len(args) > 1 else 30.0
+        norm = bool(args[2]) if len(args) > 2 else True
+        B_ = 10 ** (sll / 20)
+        A_ = math.acosh(B_) / math.pi
+        s2 = nbar ** 2 / (A_ ** 2 + (nbar - 0.5) ** 2)
+        ma = torch.arange(1, nbar, dtype=torch.float64)
+        Fm = torch.zeros(nbar - 1, dtype=torch.float64)
+        signs = torch.ones(nbar - 1, dtype=torch.float64)
+        signs[1::2] = -1
+        m2 = ma * ma
+        for mi in range(nbar - 1):
+            numer = signs[mi] * torch.prod(1 - m2[mi] / s2 / (A_ ** 2 + (ma - 0.5) ** 2))
+            denom = 2 * torch.prod(1 - m2[mi] / m2[:mi]) * torch.prod(1 - m2[mi] / m2[mi + 1:])
+            Fm[mi] = numer / denom
+
+        def W(nn_):
+            return 1 + 2 * (Fm[None, :] * torch.cos(2 * math.pi * ma[None, :] * (nn_[:, None] - M / 2.0 + 0.5) / M)).sum(1)
+
+        w = W(n)
+        if norm:
+            w = w / W(torch.tensor([(M - 1) / 2.0], dtype=torch.float64))
     else:
         raise ValueError(f"unknown window {name}")
     if fftbins:

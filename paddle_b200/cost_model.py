@@ -24,5 +24,41 @@ class CostModel:
     def allreduce_ms(self, nbytes, world, bus_gbs=725.0):
         return 0.0 if world <= 1 else 2.0 * (world - 1) / world * nbytes / (bus_gbs * 1e6)
 
-    def profile_measure(self, *a, **k):
-        raise NotImplementedError("use paddle_b200.profiler for measured costs")
+    def profile_measure(self, main_program=None, startup_program=None, device="gpu", fetch_cost_list=("time",), feed=None, fetch_list=None, repeat=5):
+        """Run a static Program (or any zero-argument callable) `repeat` times and return measured costs:
+        {"time": ms per run (CUDA events on GPU, perf_counter on CPU), "kernel_launches": own-kernel launches per run}."""
+        import time
+
+        import torch
+
+        if callable(main_program):
+            run = main_program
+        else:
+            from . import static
+
+            exe = static.Executor()
+            if startup_program is not None:
+                exe.run(startup_program)
+            run = lambda: exe.run(main_program, feed=feed or {}, fetch_list=fetch_list or [])  # noqa: E731
+        run()
+        from . import _build
+
+        C = _build.load(required=False)
+        l0 = C.launch_count() if C is not None else 0
+        on_gpu = torch.cuda.is_available() and device != "cpu"
+        if on_gpu:
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(repeat):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / repeat
+        else:
+            t0 = time.perf_counter()
+            for _ in range(repeat):
+                run()
+            ms = (time.perf_counter() - t0) * 1e3 / repeat
+        out = {"time": ms, "kernel_launches": ((C.launch_count() - l0) / repeat) if C is not None else 0}
+        return {k: out[k] for k in out if k in fetch_cost_list or k == "time"}

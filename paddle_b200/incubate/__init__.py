@@ -112,9 +112,27 @@ asp = _ASP
 
 
 class _Autotune:
-    @staticmethod
-    def set_config(config=None):
-        pass
+    """paddle.incubate.autotune. Parity: python/paddle/incubate/autotune.py:set_config (kernel / layout / dataloader tuning switches).
+    Kernel choice here is static (hand-written sm_100a kernels, shapes dispatched in C++), so `kernel` and `layout` are recorded
+    only; `dataloader.enable` turns on the DataLoader's worker-count probe."""
+
+    config = {"kernel": {"enable": False, "tuning_range": [1, 10]}, "layout": {"enable": False}, "dataloader": {"enable": False}}
+
+    @classmethod
+    def set_config(cls, config=None):
+        import json
+
+        if config is None:
+            for v in cls.config.values():
+                v["enable"] = True
+            return
+        if isinstance(config, str):
+            with open(config) as f:
+                config = json.load(f)
+        for k, v in config.items():
+            if k not in cls.config:
+                raise ValueError(f"autotune.set_config: unknown section {k!r}")
+            cls.config[k].update(v)
 
 
 autotune = _Autotune
@@ -128,12 +146,6 @@ def __getattr__(name):
             return importlib.import_module("." + name, __name__)
         except ModuleNotFoundError as e:
             raise AttributeError(name) from e
-    raise AttributeError(name)
-
-
-def __getattr__(name):
     if name == "inference":   # paddle.incubate.inference: the predictor API lives in paddle_b200.inference
-        import importlib
-
         return importlib.import_module("paddle_b200.inference")
     raise AttributeError(name)

@@ -107,7 +107,20 @@ class Hessian(Jacobian):
 
 
 def forward_grad(outputs, inputs, grad_inputs=None):
-    raise NotImplementedError("forward_grad is a static-graph primitive API; use incubate.autograd.jvp in dygraph")
+    """Forward-mode derivative of already-computed `outputs` w.r.t. `inputs` in direction `grad_inputs` (default ones), by the
+    double-backward identity  J v = d/du [ (J^T u) . v ].  Parity: python/paddle/incubate/autograd/primapi.py:forward_grad."""
+    outs = list(outputs) if isinstance(outputs, (list, tuple)) else [outputs]
+    ins = list(inputs) if isinstance(inputs, (list, tuple)) else [inputs]
+    vs = [torch.ones_like(_raw(i)) for i in ins] if grad_inputs is None else [_raw(v) for v in (grad_inputs if isinstance(grad_inputs, (list, tuple)) else [grad_inputs])]
+    res = []
+    for o in outs:
+        u = torch.zeros_like(_raw(o), requires_grad=True)
+        with torch._C.DisableTorchFunctionSubclass():   # the tensors themselves (an as_subclass alias is not the graph leaf)
+            gs = torch.autograd.grad(o, ins, u, create_graph=True, allow_unused=True)
+            terms = [(g * v).sum() for g, v in zip(gs, vs) if g is not None]
+            jv = torch.autograd.grad(torch.stack(terms).sum(), u, allow_unused=True)[0] if terms else None
+        res.append(_w(torch.zeros_like(_raw(o)) if jv is None else _raw(jv)))
+    return res if isinstance(outputs, (list, tuple)) else res[0]
 
 
 def grad(outputs, inputs, grad_outputs=None):

@@ -561,7 +561,15 @@ def auc(input, label, curve="ROC", num_thresholds=4095, topk=1, slide_steps=1, i
 
 
 def ctr_metric_bundle(input, label, ins_tag_weight=None):
-    raise NotImplementedError("ctr_metric_bundle belongs to the parameter-server stack")
+    """Running CTR statistics of a batch: (sqrerr, abserr, prob, q, pos_num, ins_num), each a [1] tensor that the caller
+    accumulates (the reference keeps them in persistable variables). Parity: python/paddle/static/nn/metric.py:ctr_metric_bundle."""
+    import torch
+
+    p = input.as_subclass(torch.Tensor).reshape(-1).float()
+    y = label.as_subclass(torch.Tensor).reshape(-1).float()
+    w = torch.ones_like(p) if ins_tag_weight is None else ins_tag_weight.as_subclass(torch.Tensor).reshape(-1).float()
+    outs = (((p - y) ** 2 * w).sum(), ((p - y).abs() * w).sum(), (p * w).sum(), (p * w).sum(), (y * w).sum(), w.sum())
+    return tuple(o.reshape(1).as_subclass(Tensor) for o in outs)
 
 
 class WeightNormParamAttr(ParamAttr):
