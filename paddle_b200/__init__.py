@@ -6,7 +6,7 @@ and hand-written sm_100a CUDA kernels (``paddle_b200/csrc``) for the hot paths.
 """
 from __future__ import annotations
 
-__version__ = "0.1.0"
+__version__ = "3.0.0"   # API level (see version.py); paddle_b200.version.b200_version is the framework's own version
 
 import torch as _torch
 

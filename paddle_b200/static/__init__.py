@@ -489,8 +489,7 @@ def save_inference_model(path_prefix, feed_vars, fetch_vars, executor, program=N
     d = os.path.dirname(path_prefix)
     if d:
         os.makedirs(d, exist_ok=True)
-    infer = program.clone(for_test=True)
-    blob = {"program": infer, "feeds": [v.name for v in feed_vars], "fetch_vids": [program._fetch_alias[id(v)] for v in fetch_vars]}
+    blob = _inference_blob(feed_vars, fetch_vars, program)
     with open(path_prefix + ".pdmodel", "wb") as f:
         pickle.dump(blob, f)
 
@@ -508,21 +507,32 @@ def normalize_program(program, feed_vars, fetch_vars, **kwargs):
     return program.clone(for_test=True)
 
 
+def _inference_blob(feed_vars, fetch_vars, program):
+    feed_vars = feed_vars if isinstance(feed_vars, (list, tuple)) else [feed_vars]
+    fetch_vars = fetch_vars if isinstance(fetch_vars, (list, tuple)) else [fetch_vars]
+    return {"program": program.clone(for_test=True), "feeds": [v.name for v in feed_vars], "fetch_vids": [program._fetch_alias[id(v)] for v in fetch_vars]}
+
+
 def serialize_program(feed_vars, fetch_vars, **kwargs):
-    return pickle.dumps({"feeds": [v.name for v in feed_vars]})
+    """Bytes of the pruned inference program (same content as the `.pdmodel` written by save_inference_model)."""
+    return pickle.dumps(_inference_blob(feed_vars, fetch_vars, kwargs.get("program") or _main[0]))
 
 
 def serialize_persistables(feed_vars, fetch_vars, executor, **kwargs):
-    return pickle.dumps({p.name: p.numpy() for p in _main[0].all_parameters()})
+    return pickle.dumps({p.name: p.numpy() for p in (kwargs.get("program") or _main[0]).all_parameters()})
 
 
 def deserialize_program(data):
-    return pickle.loads(data)
+    """Program from serialize_program bytes; the feed names / fetch variables ride along as `_feed_names` / `_fetch_vars`."""
+    blob = pickle.loads(data)
+    prog = blob["program"]
+    prog._fetch_alias = {id(t): vid for vid, t in enumerate(prog._keep)}
+    prog._feed_names, prog._fetch_vars = blob["feeds"], [prog._keep[v] for v in blob["fetch_vids"]]
+    return prog
 
 
 def deserialize_persistables(program, data, executor):
-    sd = pickle.loads(data)
-    set_program_state(program, sd)
+    set_program_state(program, pickle.loads(data))
 
 
 def save_to_file(path, content):

@@ -38,8 +38,11 @@ def require_version(min_version, max_version=None):
     def key(v):
         return tuple(int(x) for x in str(v).split(".")[:3] if x.isdigit())
 
-    if key(__version__) < key(min_version) and key(__version__) != (0, 0, 0):
-        pass  # paddle_b200 versions are independent of the reference's; accepted
+    cur = key(__version__)
+    if cur == (0, 0, 0):   # development build: every requirement is accepted, as in the reference
+        return
+    if cur < key(min_version) or (max_version is not None and cur > key(max_version)):
+        raise Exception(f"paddle version {__version__} does not satisfy the requirement [{min_version}, {max_version or 'inf'}]")
 
 
 def run_check():

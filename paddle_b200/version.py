@@ -1,6 +1,8 @@
 """paddle.version."""
-full_version = "0.1.0"
-major, minor, patch, rc = "0", "1", "0", "0"
+# API level of the reference this build tracks (what paddle.utils.require_version checks); the framework's own version is b200_version
+full_version = "3.0.0"
+major, minor, patch, rc = "3", "0", "0", "0"
+b200_version = "0.1.0"
 cuda_version = "12.9"
 cudnn_version = "none (hand-written sm_100a kernels)"
 istaged = True
