@@ -54,3 +54,4 @@ def _patch():
 
 
 _patch()
+from . import method_extras  # noqa: E402,F401

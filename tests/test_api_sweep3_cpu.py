@@ -351,3 +351,35 @@ def test_nn_utils_and_autograd_leftovers():
     Sq.apply(z).sum().backward()
     close(z.grad, [6.0])
     assert paddle.amp.is_bfloat16_supported() in (True, False) and paddle.amp.is_float16_supported() in (True, False)
+
+
+def test_tensor_method_extras():
+    x = t(np.arange(6.0).reshape(2, 3))
+    close(x.apply(lambda v: v * 2), np.arange(6.0).reshape(2, 3) * 2)
+    assert x.strides == [3, 1] and x.offset == 0 and x[1].offset == 3 * 8 and x.matrix_transpose().shape == [3, 2] and x.is_same_shape(x)
+    v0 = x.inplace_version
+    x.apply_(lambda v: v + 1)
+    assert x.inplace_version > v0 and x._inplace_version() == x.inplace_version and x.numpy()[0, 0] == 1
+    y = paddle.zeros([2, 3], "float64")
+    x._share_buffer_to(y)
+    assert x._is_shared_buffer_with(y) and not x._is_shared_buffer_with(t(np.zeros(3)))
+    assert len(x._md5sum()) == 32 and x._md5sum() == y._md5sum() and x._numel() == 6 and x._slice(0, 1).shape == [1, 3]
+    close(paddle.zeros([3, 3]).fill_diagonal_tensor(paddle.ones([3])), np.eye(3))
+    d = paddle.zeros([3, 3])
+    d.fill_diagonal_tensor_(paddle.ones([2]), offset=1)
+    close(d, np.diag(np.ones(2), 1))
+    close(torch.utils.dlpack.from_dlpack(x.to_dlpack()), x.numpy())
+    z = paddle.to_tensor([1.0, 2.0], stop_gradient=False)
+    w = z * 2
+    w.retain_grads()
+    w.sum().backward()
+    close(w.grad, [1, 1])
+    close(z._grad_ivar(), [2, 2])
+    with pytest.raises(RuntimeError):
+        z.apply(lambda v: v)
+    assert not x.is_selected_rows() and x._use_gpudnn(False) is x
+    for name in ("add_n", "concat", "stack", "multi_dot", "broadcast_tensors", "atleast_2d", "polar", "scatter_nd", "where_", "is_tensor"):
+        assert hasattr(paddle.Tensor, name), name
+    tmp = t(np.ones(3))
+    tmp._clear_data()
+    assert tmp._numel() == 0
