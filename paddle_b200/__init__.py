@@ -83,3 +83,7 @@ def install_as_paddle():
     for k, v in list(sys.modules.items()):
         if k.startswith(__name__ + "."):
             sys.modules.setdefault("paddle" + k[len(__name__):], v)
+
+
+from . import _compat_paths as _compat_paths  # noqa: E402
+_compat_paths.install()

@@ -403,7 +403,7 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 static bool make_map4(CUtensorMap* out, const void* ptr, int d, int s, int h, int b, int64_t ss, int64_t sh, int64_t sb, int dtype) {
-  cudaFree(nullptr);
+  bind_primary_context();
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable"); return false; }
   cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)s, (cuuint64_t)h, (cuuint64_t)b};

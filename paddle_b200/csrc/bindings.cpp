@@ -265,8 +265,9 @@ Tensor vp_ce_bwd(const Tensor& logits, const Tensor& labels, const Tensor& row_m
 }
 
 // ------------------------------------------------------------------------------------------------ optimizer
-void adamw_step(Tensor p, const Tensor& g, const OptT& master, Tensor m, Tensor v, double lr, double beta1, double beta2, double eps,
-                double weight_decay, int64_t step, const OptT& grad_sq_norm, double max_norm, const OptT& found_inf, const OptT& inv_scale) {
+static void adamw_step_impl(Tensor p, const Tensor& g, const OptT& master, Tensor m, Tensor v, double lr, double beta1, double beta2, double eps,
+                            double weight_decay, int64_t step, const OptT& grad_sq_norm, double max_norm, const OptT& found_inf, const OptT& inv_scale,
+                            const OptT& dyn) {
   check_cuda_contig(p, "param");
   check_cuda_contig(g, "grad");
   c10::cuda::CUDAGuard guard(p.device());
@@ -278,10 +279,23 @@ void adamw_step(Tensor p, const Tensor& g, const OptT& master, Tensor m, Tensor 
   a.max_norm = (float)max_norm;
   a.found_inf = (const float*)optp(found_inf);
   a.inv_scale = (const float*)optp(inv_scale);
+  a.dyn = (const float*)optp(dyn);
+  if (a.dyn) TORCH_CHECK(dyn->scalar_type() == at::kFloat && dyn->numel() >= 3 && dyn->is_cuda(), "adamw dyn hparams: float32 CUDA tensor of 3");
   float* mp = master.has_value() && master->defined() ? master->data_ptr<float>() : nullptr;
   b200::adamw_step(p.data_ptr(), g.data_ptr(), mp, m.data_ptr(), v.data_ptr(), p.numel(), dt_code(p), dt_code(g), dt_code(m), a, cur_stream());
   g_launches += 1;
   check_err();
+}
+
+void adamw_step(Tensor p, const Tensor& g, const OptT& master, Tensor m, Tensor v, double lr, double beta1, double beta2, double eps,
+                double weight_decay, int64_t step, const OptT& grad_sq_norm, double max_norm, const OptT& found_inf, const OptT& inv_scale) {
+  adamw_step_impl(p, g, master, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_sq_norm, max_norm, found_inf, inv_scale, std::nullopt);
+}
+
+// Graph-capturable form: lr and the bias corrections come from the device tensor `dyn` = {lr, 1-b1^t, 1-b2^t}; `lr_mult` scales dyn[0].
+void adamw_step_dyn(Tensor p, const Tensor& g, const OptT& master, Tensor m, Tensor v, double lr_mult, double beta1, double beta2, double eps,
+                    double weight_decay, const OptT& grad_sq_norm, double max_norm, const OptT& found_inf, const OptT& inv_scale, const Tensor& dyn) {
+  adamw_step_impl(p, g, master, m, v, lr_mult, beta1, beta2, eps, weight_decay, 1, grad_sq_norm, max_norm, found_inf, inv_scale, dyn);
 }
 
 void grad_sq_norm(const Tensor& g, Tensor out, const OptT& found_inf) {
@@ -572,6 +586,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("vp_ce_sumexp", traced("vp_ce_sumexp", &vp_ce_sumexp));
   m.def("vp_ce_bwd", traced("vp_ce_bwd", &vp_ce_bwd));
   m.def("adamw_step", traced("adamw_step", &adamw_step));
+  m.def("adamw_step_dyn", traced("adamw_step", &adamw_step_dyn));
   m.def("grad_sq_norm", traced("grad_sq_norm", &grad_sq_norm));
   m.def("scale_inplace", traced("scale_inplace", &scale_inplace));
   m.def("sgd_step", traced("sgd_step", &sgd_step));

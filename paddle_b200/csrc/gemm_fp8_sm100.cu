@@ -348,7 +348,7 @@ static EncodeTiledFn get_encode() {
 }
 // 3-D byte map {k (contiguous), rows, batch}
 static bool make_map8(CUtensorMap* out, const void* ptr, uint64_t k, uint64_t rows, uint64_t batch, uint64_t ld, uint64_t bstride, uint32_t box_rows) {
-  cudaFree(nullptr);
+  bind_primary_context();
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable"); return false; }
   cuuint64_t dims[3] = {k, rows, batch};

@@ -399,7 +399,7 @@ bool make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, 
     auto it = cache.find(key);
     if (it != cache.end()) { *out = it->second; return true; }
   }
-  cudaFree(nullptr);  // bind the primary context on this thread (autograd worker threads call the driver API cold)
+  bind_primary_context();
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable"); return false; }
   cuuint64_t dims[3] = {inner, rows, batch};

@@ -106,6 +106,17 @@ __device__ __forceinline__ float block_max(float v, float* smem) {
     default: b200::set_last_error(__FILE__, __LINE__, "unsupported dtype"); \
   }
 
+// Driver-API entry points (cuTensorMapEncodeTiled) need the primary context current on the calling thread; autograd worker threads
+// arrive cold.  Once per thread is enough, and doing it only once keeps cudaFree (an "unsafe" call under global-mode stream
+// capture) out of recorded regions: every thread has been through a warm-up step before a capture starts.
+inline void bind_primary_context() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
+  }
+}
+
 inline int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -59,6 +59,10 @@ struct AdamWArgs {
   float max_norm;              // clip threshold (<=0: none)
   const float* found_inf;      // device flag (nullptr = none): skip update if != 0
   const float* inv_scale;      // device: 1/loss_scale (nullptr = 1)
+  // device float[3] = {lr, 1 - beta1^t, 1 - beta2^t} (nullptr = use the host values above).  With it the launch has no
+  // step-dependent host argument, so a captured CUDA graph of the whole training step can be replayed while lr / t change;
+  // `lr` then acts as a per-slab multiplier on dyn[0].
+  const float* dyn = nullptr;
 };
 // p (param dtype), g (grad dtype), master fp32 (may be null), m/v in `state_dtype` (fp32 or bf16)
 void adamw_step(void* p, const void* g, float* master, void* m, void* v, int64_t n, int p_dtype, int g_dtype,

@@ -17,9 +17,10 @@ __global__ void __launch_bounds__(256) adamw_kernel(TP* __restrict__ p, const TG
     const float norm = sqrtf(*a.grad_sq_norm) * gscale;
     if (norm > a.max_norm) gscale *= a.max_norm / (norm + 1e-6f);
   }
-  const float step_size = a.lr / a.bias_c1;
-  const float inv_c2 = rsqrtf(a.bias_c2);
-  const float decay = 1.f - a.lr * a.weight_decay;
+  const float lr = a.dyn ? a.dyn[0] * a.lr : a.lr;
+  const float step_size = lr / (a.dyn ? a.dyn[1] : a.bias_c1);
+  const float inv_c2 = rsqrtf(a.dyn ? a.dyn[2] : a.bias_c2);
+  const float decay = 1.f - lr * a.weight_decay;
   constexpr int U = 4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t base = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; base < n; base += stride * U) {
@@ -83,9 +84,10 @@ __global__ void __launch_bounds__(256) adamw_vec_kernel(TP* __restrict__ p, cons
     const float norm = sqrtf(*a.grad_sq_norm) * gscale;
     if (norm > a.max_norm) gscale *= a.max_norm / (norm + 1e-6f);
   }
-  const float step_size = a.lr / a.bias_c1;
-  const float inv_c2 = rsqrtf(a.bias_c2);
-  const float decay = 1.f - a.lr * a.weight_decay;
+  const float lr = a.dyn ? a.dyn[0] * a.lr : a.lr;
+  const float step_size = lr / (a.dyn ? a.dyn[1] : a.bias_c1);
+  const float inv_c2 = rsqrtf(a.dyn ? a.dyn[2] : a.bias_c2);
+  const float decay = 1.f - lr * a.weight_decay;
   const float omb1 = 1.f - a.beta1, omb2 = 1.f - a.beta2;
   const int64_t npack = n / 8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npack; i += (int64_t)gridDim.x * blockDim.x) {

@@ -277,3 +277,6 @@ def marker_unified(*a, **k):
 
 
 __all__ = ["to_static", "save", "load", "TranslatedLayer", "not_to_static", "enable_to_static", "ignore_module", "set_code_level", "set_verbosity"]
+
+
+from .train_step import CapturedTrainStep, capture_train_step  # noqa: F401,E402

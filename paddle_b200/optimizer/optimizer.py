@@ -257,6 +257,9 @@ class _NativeOps:
     def adamw_step(self, *a):
         self._e.adamw_step(*a)
 
+    def adamw_step_dyn(self, *a):
+        self._e.adamw_step_dyn(*a)
+
 
 class _TorchOps:
     """Reference implementation of the same slab ops in plain PyTorch (CPU tests / fallback)."""
@@ -448,8 +451,27 @@ class Adam(Optimizer):
                 s.state["m"] = torch.zeros(s.numel, dtype=sdt, device=dev)
                 s.state["v"] = torch.zeros(s.numel, dtype=sdt, device=dev)
             wd = float(self._weight_decay or 0.0) if getattr(s, "decay", True) else 0.0
+            hp = self._aux.get("dyn_hparams") if cuda else None
+            if hp is not None:   # graph-capturable launch: lr and bias corrections are read from device memory (jit.CapturedTrainStep)
+                E.adamw_step_dyn(s.data, s.grad, s.master, s.state["m"], s.state["v"], float(getattr(s, "lr_scale", 1.0)), b1, b2,
+                                 float(self._epsilon), wd, sq, max_norm, found_inf, inv_scale, hp)
+                continue
             E.adamw_step(s.data, s.grad, s.master, s.state["m"], s.state["v"], lr * getattr(s, "lr_scale", 1.0), b1, b2,
                          float(self._epsilon), wd, self._step_count, sq, max_norm, found_inf, inv_scale)
+
+    def _refresh_dyn_hparams(self):
+        """Write {lr, 1 - b1^t, 1 - b2^t} for the *next* update into the device tensor the captured AdamW launches read."""
+        hp = self._aux.get("dyn_hparams")
+        if hp is None:
+            dev = self._arena.all_slabs()[0].data.device
+            hp = self._aux["dyn_hparams"] = torch.zeros(3, dtype=torch.float32, device=dev)
+            self._aux["dyn_hparams_host"] = torch.zeros(3, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(3)
+        b1, b2 = self._betas()
+        t = self._step_count + 1
+        host = self._aux["dyn_hparams_host"]
+        host[0], host[1], host[2] = float(self.get_lr()), 1.0 - b1 ** t, 1.0 - b2 ** t
+        hp.copy_(host, non_blocking=True)
+        return hp
 
     def state_dict(self):
         sd = super().state_dict()

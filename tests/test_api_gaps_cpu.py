@@ -274,3 +274,14 @@ def test_multislot_dataset_native_feed(tmp_path):
     ds.set_filelist([str(bad)])
     with pytest.raises(RuntimeError, match="line 1"):
         ds.load_into_memory()
+
+
+def test_capture_train_step_cpu_falls_back_to_eager():
+    paddle.seed(3)
+    net = paddle.nn.Linear(4, 2)
+    opt = paddle.optimizer.AdamW(1e-2, parameters=net.parameters())
+    opt.enable_flat_arena()
+    step = paddle.jit.capture_train_step(lambda x: (net(x) ** 2).mean(), opt, warmup=1)
+    x = paddle.ones([3, 4])
+    losses = [float(step(x)) for _ in range(5)]
+    assert not step.captured and losses[-1] < losses[0] and opt._step_count == 5

@@ -44,3 +44,47 @@ def test_symm_heap_best_fit_single_rank():
     assert st["live_blocks"] == 2 and st["allocated"] == (16 << 20) + (4 << 20) and st["peak_allocated"] >= 24 << 20
     with pytest.raises(RuntimeError, match="out of symmetric memory"):
         heap.alloc(128 << 20, 1024)
+
+
+def _mlp_and_opt(seed, lr):
+    import paddle_b200 as paddle
+
+    paddle.seed(seed)
+    net = paddle.nn.Sequential(paddle.nn.Linear(64, 128), paddle.nn.GELU(), paddle.nn.Linear(128, 10))
+    net.to("gpu")
+    opt = paddle.optimizer.AdamW(lr, parameters=net.parameters(), weight_decay=0.01, grad_clip=paddle.nn.ClipGradByGlobalNorm(1.0))
+    opt.enable_flat_arena()
+    return net, opt
+
+
+def test_captured_train_step_matches_eager():
+    """jit.capture_train_step: forward + backward + clip + fused AdamW + clear_grad replayed from one CUDA graph, with a changing lr."""
+    import numpy as np
+
+    import paddle_b200 as paddle
+
+    sched_a = paddle.optimizer.lr.StepDecay(1e-2, step_size=3, gamma=0.5)
+    sched_b = paddle.optimizer.lr.StepDecay(1e-2, step_size=3, gamma=0.5)
+    net_a, opt_a = _mlp_and_opt(7, sched_a)
+    net_b, opt_b = _mlp_and_opt(7, sched_b)
+    ce = paddle.nn.CrossEntropyLoss()
+    step = paddle.jit.capture_train_step(lambda x, y: ce(net_b(x), y), opt_b, warmup=2)
+    rng = np.random.RandomState(0)
+    losses_a, losses_b = [], []
+    for i in range(10):
+        x = paddle.to_tensor(rng.randn(32, 64).astype("float32")).cuda()
+        y = paddle.to_tensor(rng.randint(0, 10, (32,))).cuda()
+        la = ce(net_a(x), y)
+        la.backward()
+        opt_a.step()
+        opt_a.clear_grad()
+        sched_a.step()
+        losses_a.append(float(la))
+        losses_b.append(float(step(x, y)))
+        sched_b.step()
+    assert step.captured, step.failure
+    assert step.replays >= 6 and opt_b._step_count == opt_a._step_count == 10
+    np.testing.assert_allclose(losses_b, losses_a, rtol=2e-4, atol=2e-5)
+    for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+        np.testing.assert_allclose(pb.numpy(), pa.numpy(), rtol=2e-4, atol=2e-5)
+    assert losses_a[-1] < losses_a[0]
