@@ -154,7 +154,8 @@ _reexport(_FLEET + ".meta_parallel.sharding.group_sharded_utils", "group_sharded
 _reexport(_FLEET + ".layers", "paddle.distributed.fleet.layers", [_FLEET + ".mp_layers"])
 _reexport(_FLEET + ".layers.mpu", "paddle.distributed.fleet.layers.mpu", [_FLEET + ".mp_layers", _FLEET + ".random"])
 _reexport(_FLEET + ".layers.mpu.mp_layers", "mpu.mp_layers", [_FLEET + ".mp_layers"])
-_reexport(_FLEET + ".layers.mpu.mp_ops", "mpu.mp_ops", [_FLEET + ".mp_layers"])
+_reexport(_FLEET + ".layers.mpu.mp_ops", "mpu.mp_ops", [_FLEET + ".mp_layers", "distributed"],
+          ["_c_identity", "_mp_allreduce", "_c_concat", "_c_split", "split", "ParallelCrossEntropy", "ScatterOp", "GatherOp", "AllGatherOp", "ReduceScatterOp"])
 _reexport(_FLEET + ".layers.mpu.random", "mpu.random", [_FLEET + ".random"])
 _reexport(_FLEET + ".base", "paddle.distributed.fleet.base", [_FLEET + ".topology", _FLEET + ".strategy", _FLEET + ".base_extras"])
 _reexport(_FLEET + ".base.topology", "fleet.base.topology", [_FLEET + ".topology"])
