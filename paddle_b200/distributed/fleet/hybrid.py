@@ -362,6 +362,21 @@ class HybridParallelOptimizer:
             group = hcg.get_data_parallel_group()
         elif self._sharding_enable:
             group = hcg.get_sharding_parallel_group()
+        if hcg.get_sep_parallel_world_size() > 1:
+            # sep (segment / context parallel) ranks hold replicated parameters and see different sequence segments: their gradients
+            # are averaged like data-parallel ones (reference: fused_allreduce_gradients over the dp x sep group)
+            if self._sharding_enable:
+                sep_group = hcg.get_sep_parallel_group()
+                ns = _n(sep_group)
+                if arena is not None:
+                    for s in arena.all_slabs():
+                        _allreduce_flat(s.grad, sep_group)
+                        s.grad.mul_(1.0 / ns)
+                else:
+                    grads = [torch.Tensor.grad.__get__(p) for p in self._params if torch.Tensor.grad.__get__(p) is not None]
+                    _allreduce_tensors(grads, sep_group, 1.0 / ns)
+            else:
+                group = hcg.get_dp_sep_parallel_group()
         if group is None or _n(group) <= 1:
             return
         n = _n(group)

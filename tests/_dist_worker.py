@@ -693,6 +693,111 @@ def case_mp_sp_bf16():
     paddle.set_default_dtype("float32")
 
 
+def case_moe_ep():
+    """Expert parallel MoELayer (2 ranks x 2 local experts) == one process holding all 4 experts (forward, dx, expert grads).
+    Parity: test/collective/parallel_dygraph_moe / moe_layer tests."""
+    dist.init_parallel_env()
+    r, w = dist.get_rank(), dist.get_world_size()
+    from paddle_b200.incubate.moe import MoELayer
+
+    grp = dist.collective._global_group()
+    D, EL = 16, 2
+
+    def experts(seed_base, n, first):
+        ls = []
+        for e in range(n):
+            paddle.seed(seed_base + first + e)
+            ls.append(nn.Sequential(nn.Linear(D, 32), nn.GELU(), nn.Linear(32, D)))
+        return nn.LayerList(ls)
+
+    par_experts, ref_experts = experts(500, EL, r * EL), experts(500, EL * w, 0)
+    paddle.seed(3)          # the gate is replicated: same seed on every rank (the experts above reseed per expert)
+    par = MoELayer(D, par_experts, gate={"type": "naive", "top_k": 2}, moe_group=grp)
+    paddle.seed(3)
+    ref = MoELayer(D, ref_experts, gate={"type": "naive", "top_k": 2}, moe_group=None)
+    xs = []
+    for k in range(w):
+        torch.manual_seed(40 + k)
+        xs.append(torch.randn(12, D))
+    x = xs[r].clone().as_subclass(paddle.Tensor)
+    x.stop_gradient = False
+    y = par(x)
+    (y ** 2).sum().backward()
+    ref_x = [t.clone().as_subclass(paddle.Tensor) for t in xs]
+    for t in ref_x:
+        t.stop_gradient = False
+    ref_y = [ref(t) for t in ref_x]
+    sum((o ** 2).sum() for o in ref_y).backward()
+    close(y.numpy(), ref_y[r].numpy(), 1e-4)
+    close(x.grad.numpy(), ref_x[r].grad.numpy(), 1e-4)
+    for e in range(EL):
+        for (_, pa), (_, pb) in zip(par.experts[e].named_parameters(), ref.experts[r * EL + e].named_parameters()):
+            close(pa.grad.numpy(), pb.grad.numpy(), 1e-4)
+    # gate weight gradient: each rank sees its own tokens only; the sum over ranks is the single-process gradient
+    g = par.gate.gate.weight.grad.clone()
+    dist.all_reduce(g)
+    close(g.numpy(), ref.gate.gate.weight.grad.numpy(), 1e-4)
+
+
+def case_dp_no_sync():
+    """DataParallel.no_sync gradient accumulation (2 micro-batches, one all-reduce) == one big batch. Parity: parallel_dygraph_no_sync."""
+    dist.init_parallel_env()
+    r, w = dist.get_rank(), dist.get_world_size()
+    paddle.seed(9)
+    net = nn.Sequential(nn.Linear(6, 12), nn.Tanh(), nn.Linear(12, 3))
+    ref = nn.Sequential(nn.Linear(6, 12), nn.Tanh(), nn.Linear(12, 3))
+    ref.set_state_dict(net.state_dict())
+    x, y = paddle.randn([16, 6]), paddle.randn([16, 3])
+    dp = paddle.DataParallel(net)
+    opt = paddle.optimizer.SGD(0.05, parameters=dp.parameters())
+    ropt = paddle.optimizer.SGD(0.05, parameters=ref.parameters())
+    for _ in range(2):
+        mine = slice(r * 8, (r + 1) * 8)
+        xa, ya = x[mine], y[mine]
+        with dp.no_sync():
+            (((dp(xa[:4]) - ya[:4]) ** 2).mean() / 2).backward()
+        (((dp(xa[4:]) - ya[4:]) ** 2).mean() / 2).backward()
+        opt.step()
+        opt.clear_grad()
+        ((ref(x) - y) ** 2).mean().backward()
+        ropt.step()
+        ropt.clear_grad()
+    for (k, a), (_, b) in zip(net.state_dict().items(), ref.state_dict().items()):
+        close(a.numpy(), b.numpy(), 1e-4)
+
+
+def case_sep_parallel():
+    """sep (segment / context parallel) degree 2: parameters are broadcast over the sep group and gradients of the two sequence halves
+    are averaged over the dp x sep group — training on the halves equals training on the full sequence (loss / sep degree). Parity: hybrid_parallel_sep_model.py."""
+    s = fleet.DistributedStrategy()
+    s.hybrid_configs = {"dp_degree": 1, "mp_degree": 1, "pp_degree": 1, "sep_degree": 2}
+    fleet.init(is_collective=True, strategy=s)
+    hcg = fleet.get_hybrid_communicate_group()
+    r = hcg.get_sep_parallel_rank()
+    assert hcg.get_sep_parallel_world_size() == 2
+    paddle.seed(11 + r)           # different init per rank: the wrapper must broadcast rank 0's parameters
+    net = nn.Sequential(nn.Linear(8, 16), nn.GELU(), nn.Linear(16, 8))
+    model = fleet.distributed_model(net)
+    paddle.seed(11)
+    ref = nn.Sequential(nn.Linear(8, 16), nn.GELU(), nn.Linear(16, 8))
+    for (k, a), (_, b) in zip(net.state_dict().items(), ref.state_dict().items()):
+        close(a.numpy(), b.numpy(), 1e-6)
+    opt = fleet.distributed_optimizer(paddle.optimizer.SGD(0.1, parameters=net.parameters()))
+    ropt = paddle.optimizer.SGD(0.1, parameters=ref.parameters())
+    torch.manual_seed(2)
+    x = torch.randn(2, 6, 8).as_subclass(paddle.Tensor)      # [batch, seq, hidden]; position-wise model: sequence halves are independent
+    for _ in range(2):
+        half = x[:, r * 3:(r + 1) * 3]
+        (model(half) ** 2).sum().backward()
+        opt.step()
+        opt.clear_grad()
+        ((ref(x) ** 2).sum() / 2).backward()     # gradients are averaged over the dp x sep group
+        ropt.step()
+        ropt.clear_grad()
+    for (k, a), (_, b) in zip(net.state_dict().items(), ref.state_dict().items()):
+        close(a.numpy(), b.numpy(), 1e-4)
+
+
 if __name__ == "__main__":
     case = sys.argv[1]
     if GPU:
