@@ -99,6 +99,35 @@ class PipelineLayer(Layer):
             self._chunks.append(self._build(lo, hi, v))
         self.run_function = self._chunks[0]
         self._start, self._end = self.segment_parts[self._stage_id], self.segment_parts[self._stage_id + 1]
+        self._shared_groups = {}
+        self._init_shared_weight_comm()
+
+    def _init_shared_weight_comm(self):
+        """For every SharedLayerDesc key: a communicator over exactly the stages that own a copy, and the first owner's initial value
+        broadcast to the others (stages build their layers in different order, so equal seeds do not give equal copies).
+        Parity: pp_layers.py:_construct_shared_comm / _synchronize_shared_weights."""
+        hcg = self._hcg
+        keys = {}
+        for idx, d in enumerate(self._layers_desc):
+            if isinstance(d, SharedLayerDesc):
+                part = next(p for p in range(len(self.segment_parts) - 1) if self.segment_parts[p] <= idx < self.segment_parts[p + 1])
+                keys.setdefault(d.layer_name, set()).add(part % self._num_stages)
+        if hcg is None or hcg.get_pipe_parallel_world_size() <= 1 or not keys or not dist.is_initialized():
+            return
+        from ..collective import new_group
+
+        my_pp = list(hcg.get_pipe_parallel_group().ranks)
+        for key in sorted(keys):                                     # every process creates every group, in the same order
+            stages = sorted(keys[key])
+            for pp_ranks in hcg.topology().get_comm_list("pipe"):
+                ranks = [pp_ranks[s] for s in stages]
+                g = new_group(ranks) if len(ranks) > 1 else None
+                if list(pp_ranks) == my_pp and self._stage_id in stages and g is not None:
+                    self._shared_groups[key] = (g, ranks[0])
+        for key, (g, src) in self._shared_groups.items():
+            w = getattr(self.shared_layers[key], self.shared_weight_attrs[key])
+            with torch.no_grad():
+                dist.broadcast(_raw(w), src=src, group=g.pg)
 
     def _build(self, lo, hi, chunk):
         fns = []
@@ -160,16 +189,16 @@ class PipelineLayer(Layer):
 
     def allreduce_shared_weight_gradients(self):
         """Tied weights living on several stages (e.g. embedding / lm head): sum their grads over the owning stages."""
-        if self._hcg is None or not self.shared_layers:
+        if self._hcg is None or not self._shared_groups:
             return
-        pg = self._hcg.get_pipe_parallel_group()
-        for key, layer in self.shared_layers.items():
-            w = getattr(layer, self.shared_weight_attrs[key])
+        for key in sorted(self._shared_groups):
+            group, _ = self._shared_groups[key]
+            w = getattr(self.shared_layers[key], self.shared_weight_attrs[key])
             g = torch.Tensor.grad.__get__(w)
             if g is None:
                 g = torch.zeros_like(_raw(w))
                 torch.Tensor.grad.__set__(w, g)
-            dist.all_reduce(g, group=pg.pg)
+            dist.all_reduce(g, group=group.pg)
 
 
 # ---------------------------------------------------------------------------------------------------- p2p

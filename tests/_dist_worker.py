@@ -798,6 +798,165 @@ def case_sep_parallel():
         close(a.numpy(), b.numpy(), 1e-4)
 
 
+def case_pp_shared_embedding():
+    """Pipeline with tied input / output embedding (SharedLayerDesc on the first and last stage): the shared weight's gradient is
+    all-reduced between its two owners, training == single process with a truly tied weight. Parity: hybrid_parallel_shared_weight.py."""
+    s, hcg = setup(pp=2)
+    from paddle_b200.distributed.fleet.pipeline import LayerDesc, PipelineLayer, SharedLayerDesc
+
+    V, H = 24, 16
+    s.pipeline_configs = {"accumulate_steps": 2, "micro_batch_size": 2}
+
+    class Emb(nn.Layer):
+        def __init__(self):
+            super().__init__()
+            self.weight = self.create_parameter([V, H])
+
+        def forward(self, ids):
+            return paddle.nn.functional.embedding(ids, self.weight)
+
+    def head(layer, x):
+        return paddle.matmul(x, layer.weight, transpose_y=True)
+
+    class Block(nn.Layer):
+        def __init__(self):
+            super().__init__()
+            self.fc = nn.Linear(H, H)
+
+        def forward(self, x):
+            return x + paddle.tanh(self.fc(x))
+
+    def loss_fn(logits, labels):
+        return paddle.nn.functional.cross_entropy(logits.reshape([-1, V]), labels.reshape([-1]))
+
+    paddle.seed(31)
+    descs = [SharedLayerDesc("embed", Emb), LayerDesc(Block), LayerDesc(Block), SharedLayerDesc("embed", Emb, forward_func=head)]
+    pl = PipelineLayer(descs, num_stages=2, loss_fn=loss_fn)
+    # single-process reference with the same initial values: gather every stage's parameters
+    local = {n: p.numpy() for n, p in pl.named_parameters()}
+    allp = [None, None]
+    dist.all_gather_object(allp, local)
+    paddle.seed(31)
+    emb, b0, b1 = Emb(), Block(), Block()
+    emb_w = [v for d in allp for n, v in d.items() if "weight" in n and v.shape == (V, H)][0]
+    emb.weight.set_value(emb_w)
+    blocks = {}
+    for d in allp:
+        for n, v in d.items():
+            if v.shape != (V, H):
+                blocks[n] = v
+    names = sorted(blocks)      # "1.fc.weight", "1.fc.bias", "2.fc..."
+    for blk, idx in ((b0, "1"), (b1, "2")):
+        blk.fc.weight.set_value(blocks[f"{idx}.fc.weight"])
+        blk.fc.bias.set_value(blocks[f"{idx}.fc.bias"])
+    ref_params = list(emb.parameters()) + list(b0.parameters()) + list(b1.parameters())
+    model = fleet.distributed_model(pl)
+    opt = fleet.distributed_optimizer(paddle.optimizer.SGD(0.1, parameters=pl.parameters()))
+    ropt = paddle.optimizer.SGD(0.1, parameters=ref_params)
+    rs = np.random.RandomState(1)
+    for _ in range(3):
+        ids = paddle.to_tensor(rs.randint(0, V, (4, 5)))
+        lab = paddle.to_tensor(rs.randint(0, V, (4, 5)))
+        loss = model.train_batch([ids, lab], opt)
+        rl = loss_fn(head(emb, b1(b0(emb(ids)))), lab)
+        rl.backward()
+        ropt.step()
+        ropt.clear_grad()
+        close(loss.item(), rl.item(), 1e-4)
+    shared = [p for n, p in pl.named_parameters() if tuple(p.shape) == (V, H)][0]
+    close(shared.numpy(), emb.weight.numpy(), 1e-4)
+
+
+def case_dp_unused_params():
+    """DataParallel(find_unused_parameters=True): a branch that is skipped on some steps must not stall the bucket reduction."""
+    dist.init_parallel_env()
+    r, w = dist.get_rank(), dist.get_world_size()
+
+    class Net(nn.Layer):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b, self.out = nn.Linear(6, 6), nn.Linear(6, 6), nn.Linear(6, 2)
+
+        def forward(self, x, use_b):
+            h = self.a(x)
+            if use_b:
+                h = h + self.b(x)
+            return self.out(paddle.tanh(h))
+
+    paddle.seed(13)
+    net, ref = Net(), Net()
+    ref.set_state_dict(net.state_dict())
+    dp = paddle.DataParallel(net, find_unused_parameters=True, comm_buffer_size=1)
+    opt = paddle.optimizer.SGD(0.1, parameters=dp.parameters())
+    ropt = paddle.optimizer.SGD(0.1, parameters=ref.parameters())
+    x, y = paddle.randn([8, 6]), paddle.randn([8, 2])
+    for step in range(4):
+        use_b = step % 2 == 0
+        sl = slice(r * 4, (r + 1) * 4)
+        ((dp(x[sl], use_b) - y[sl]) ** 2).mean().backward()
+        opt.step()
+        opt.clear_grad()
+        ((ref(x, use_b) - y) ** 2).mean().backward()
+        ropt.step()
+        ropt.clear_grad()
+    for (k, a), (_, b) in zip(net.state_dict().items(), ref.state_dict().items()):
+        close(a.numpy(), b.numpy(), 1e-4)
+
+
+def case_hybrid_scaler():
+    """fleet.distributed_scaler under mp=2: an overflow seen by one rank only must skip the update on every rank and shrink the scale."""
+    s, hcg = setup(mp=2)
+    r = hcg.get_model_parallel_rank()
+    paddle.seed(17)
+    net = nn.Linear(4, 4)
+    model = fleet.distributed_model(net)
+    opt = fleet.distributed_optimizer(paddle.optimizer.SGD(0.1, parameters=net.parameters()))
+    scaler = fleet.distributed_scaler(paddle.amp.GradScaler(init_loss_scaling=1024.0, decr_every_n_nan_or_inf=1, incr_every_n_steps=1000))
+    before = net.weight.numpy().copy()
+    x = paddle.ones([2, 4])
+    loss = (model(x) ** 2).mean()
+    scaler.scale(loss).backward()
+    if r == 1:
+        net.weight.grad[0, 0] = float("inf")     # overflow on one mp rank only
+    scaler.step(opt)
+    scaler.update()
+    opt.clear_grad()
+    close(net.weight.numpy(), before, 1e-7)       # skipped everywhere
+    assert abs(float(scaler._scale if hasattr(scaler, "_scale") else scaler.get_loss_scaling()) - 512.0) < 1e-3, "scale must halve on every rank"
+    loss = (model(x) ** 2).mean()
+    scaler.scale(loss).backward()
+    scaler.step(opt)
+    scaler.update()
+    assert not np.allclose(net.weight.numpy(), before)
+
+
+def case_fleet_sharding_degree():
+    """hybrid_configs sharding_degree=2 through fleet.distributed_model / distributed_optimizer == single-process training on the full
+    batch. Parity: hybrid_parallel_sharding_model.py."""
+    s, hcg = setup(sharding=2)
+    r = hcg.get_sharding_parallel_rank()
+    paddle.seed(19 + r)
+    net = nn.Sequential(nn.Linear(8, 16), nn.GELU(), nn.Linear(16, 4))
+    model = fleet.distributed_model(net)
+    paddle.seed(19)
+    ref = nn.Sequential(nn.Linear(8, 16), nn.GELU(), nn.Linear(16, 4))
+    opt = fleet.distributed_optimizer(paddle.optimizer.AdamW(1e-2, parameters=net.parameters(), weight_decay=0.01,
+                                                             grad_clip=paddle.nn.ClipGradByGlobalNorm(0.5)))
+    ropt = paddle.optimizer.AdamW(1e-2, parameters=ref.parameters(), weight_decay=0.01, grad_clip=paddle.nn.ClipGradByGlobalNorm(0.5))
+    torch.manual_seed(4)
+    x, y = torch.randn(8, 8).as_subclass(paddle.Tensor), torch.randn(8, 4).as_subclass(paddle.Tensor)
+    for _ in range(3):
+        sl = slice(r * 4, (r + 1) * 4)
+        ((model(x[sl]) - y[sl]) ** 2).mean().backward()
+        opt.step()
+        opt.clear_grad()
+        ((ref(x) - y) ** 2).mean().backward()
+        ropt.step()
+        ropt.clear_grad()
+    for (k, a), (_, b) in zip(net.state_dict().items(), ref.state_dict().items()):
+        close(a.numpy(), b.numpy(), 2e-4)
+
+
 if __name__ == "__main__":
     case = sys.argv[1]
     if GPU:
