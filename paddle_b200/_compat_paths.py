@@ -214,6 +214,14 @@ def _reexport_now(src, names, **renames):
     return m
 
 
+class _CallableModule(types.ModuleType):
+    """A synthesised sub-module whose name is also a function of its parent (`paddle.text.viterbi_decode`, `F.flash_attention`):
+    importing the module rebinds the parent attribute to it, so it keeps behaving as that function when called."""
+
+    def __call__(self, *args, **kwargs):
+        return self.__dict__["_shadowed"](*args, **kwargs)
+
+
 class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
     def find_spec(self, fullname, path=None, target=None):
         if fullname.startswith(_PKG + "."):
@@ -235,7 +243,17 @@ class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
         name = spec.name
         if name.startswith("paddle."):
             return importlib.import_module(_PKG + name[len("paddle"):])      # the one and only module object, under a second name
-        return _ALIASES[name[len(_PKG) + 1:]]()
+        m = _ALIASES[name[len(_PKG) + 1:]]()
+        parent = sys.modules.get(name.rsplit(".", 1)[0])
+        shadowed = vars(parent).get(name.rsplit(".", 1)[1]) if parent is not None else None      # vars(): no lazy __getattr__ re-entry
+        if shadowed is not None and callable(shadowed) and not isinstance(shadowed, types.ModuleType):
+            cm = _CallableModule(m.__name__, m.__doc__)
+            cm.__dict__.update({k: v for k, v in m.__dict__.items() if k not in ("__name__", "__doc__")})
+            cm.__dict__["_shadowed"] = shadowed
+            if getattr(shadowed, "__name__", None) and shadowed.__name__ not in cm.__dict__:
+                cm.__dict__[shadowed.__name__] = shadowed
+            m = cm
+        return m
 
     def exec_module(self, module):
         pass
