@@ -250,8 +250,10 @@ class HybridParallelClipGrad:
         return out
 
 
-def _reduce_norm_sq(dist_sq, nondist_sq, hcg):
-    """total = sum over the model: mp-sharded params summed over mp; replicated params counted once; then pp and sharding sums."""
+def _reduce_norm_sq(dist_sq, nondist_sq, hcg, grads_sharded=False):
+    """total = sum over the model: mp-sharded params summed over mp; replicated params counted once; then the pp sum.  The sum over
+    the sharding group applies only when every rank holds a distinct shard of the gradients (`grads_sharded`); on this non-arena
+    path the gradients were averaged over the sharding group and are replicated, so they are counted once."""
     mp = hcg.get_model_parallel_world_size()
     total = dist_sq + nondist_sq / mp
     total = total.reshape(1).clone()
@@ -259,7 +261,7 @@ def _reduce_norm_sq(dist_sq, nondist_sq, hcg):
         dist.all_reduce(total, group=_pg(hcg.get_model_parallel_group()))
     if hcg.get_pipe_parallel_world_size() > 1:
         dist.all_reduce(total, group=_pg(hcg.get_pipe_parallel_group()))
-    if hcg.get_sharding_parallel_world_size() > 1:
+    if grads_sharded and hcg.get_sharding_parallel_world_size() > 1:
         dist.all_reduce(total, group=_pg(hcg.get_sharding_parallel_group()))
     return total.reshape([])
 
@@ -293,6 +295,11 @@ class HybridParallelOptimizer:
                     for p in slab.params:
                         p.__dict__["_sp_reduce_in_optimizer"] = True
             optimizer.enable_flat_arena(arena)
+            if self._sharding_enable:
+                # sharding stage 1 (DygraphShardingOptimizer): each rank of the sharding group keeps moments / master weights for, and
+                # updates, 1/N of every slab, then the owners publish their ranges; the clip norm is summed over the group
+                g = hcg.get_sharding_parallel_group()
+                optimizer._aux["shard"] = (hcg.get_sharding_parallel_rank(), hcg.get_sharding_parallel_world_size(), g)
             if isinstance(clip, ClipGradByGlobalNorm) and self._need_hybrid_clip:
                 optimizer._aux["norm_allreduce"] = self._arena_norm_allreduce
                 optimizer._arena_norm_split = True
@@ -330,12 +337,15 @@ class HybridParallelOptimizer:
             rep = torch.zeros(1, dtype=torch.float32, device=sq.device)
             for s in self._inner_opt._arena.all_slabs():
                 if not s.is_distributed:
+                    lo, hi = self._inner_opt._shard_bounds(s.numel)     # the range this rank contributed to `sq`
+                    if hi <= lo:
+                        continue
                     if s.grad.is_cuda:
                         from ..._build import ext
 
-                        ext().grad_sq_norm(s.grad, rep, None)
+                        ext().grad_sq_norm(s.grad[lo:hi], rep, None)
                     else:
-                        rep.add_(s.grad.float().pow(2).sum())
+                        rep.add_(s.grad[lo:hi].float().pow(2).sum())
             sq.sub_(rep * (1.0 - 1.0 / mp))
             dist.all_reduce(sq, group=_pg(hcg.get_model_parallel_group()))
         if hcg.get_pipe_parallel_world_size() > 1:

@@ -419,6 +419,15 @@ class Adam(Optimizer):
             return False
         return True
 
+    def _shard_bounds(self, numel):
+        """[lo, hi) of a slab that this rank updates under optimizer-state sharding (stage 1); the whole slab otherwise."""
+        sh = self._aux.get("shard")
+        if sh is None:
+            return 0, numel
+        rank, world, _ = sh
+        per = ((numel + world - 1) // world + 7) // 8 * 8          # 16-byte aligned shard starts for the vectorised kernel
+        return min(rank * per, numel), min((rank + 1) * per, numel)
+
     def _arena_step(self):
         cuda = all(s.data.is_cuda for s in self._arena.all_slabs())
         E = _NativeOps() if cuda else _TorchOps()   # same slab algorithm; CPU path = plain torch (used by the gloo tests)
@@ -426,6 +435,10 @@ class Adam(Optimizer):
         lr = self.get_lr()
         slabs = self._arena.all_slabs()
         dev = slabs[0].data.device
+        shard = self._aux.get("shard")     # (rank, world, group): sharding stage 1 — every rank owns 1/world of each slab's state
+        pending = self._aux.pop("pending_state", None)
+        if pending is not None:
+            self._arena_restore(pending)
         sq = None
         max_norm = 0.0
         if self._grad_clip is not None:
@@ -436,7 +449,9 @@ class Adam(Optimizer):
             sq.zero_()
             for s in slabs:
                 if getattr(s, "clip_weight", 1.0) != 0.0:
-                    E.grad_sq_norm(s.grad, sq, self._aux["found_inf"])
+                    lo, hi = self._shard_bounds(s.numel)      # sharded: own range only, the hook sums over the sharding group
+                    if hi > lo:
+                        E.grad_sq_norm(s.grad[lo:hi], sq, self._aux["found_inf"])
             hook = self._aux.get("norm_allreduce")
             if hook is not None:
                 hook(sq)          # hybrid parallel: sum the squared norm over mp/pp/sharding groups
@@ -444,20 +459,92 @@ class Adam(Optimizer):
         found_inf = self._aux.get("scaler_found_inf")
         inv_scale = self._aux.get("scaler_inv_scale")
         for s in slabs:
+            lo, hi = self._shard_bounds(s.numel)
+            n = hi - lo
             if self._multi_precision and s.dtype != torch.float32 and s.master is None:
-                s.master = s.data.float()
+                s.master = s.data[lo:hi].float()
             if "m" not in s.state:
                 sdt = self._moment_dtype or (torch.float32 if (self._multi_precision or s.dtype == torch.float32) else s.dtype)
-                s.state["m"] = torch.zeros(s.numel, dtype=sdt, device=dev)
-                s.state["v"] = torch.zeros(s.numel, dtype=sdt, device=dev)
-            wd = float(self._weight_decay or 0.0) if getattr(s, "decay", True) else 0.0
-            hp = self._aux.get("dyn_hparams") if cuda else None
-            if hp is not None:   # graph-capturable launch: lr and bias corrections are read from device memory (jit.CapturedTrainStep)
-                E.adamw_step_dyn(s.data, s.grad, s.master, s.state["m"], s.state["v"], float(getattr(s, "lr_scale", 1.0)), b1, b2,
-                                 float(self._epsilon), wd, sq, max_norm, found_inf, inv_scale, hp)
+                s.state["m"] = torch.zeros(n, dtype=sdt, device=dev)
+                s.state["v"] = torch.zeros(n, dtype=sdt, device=dev)
+            if n > 0:
+                wd = float(self._weight_decay or 0.0) if getattr(s, "decay", True) else 0.0
+                data, grad = (s.data, s.grad) if shard is None else (s.data[lo:hi], s.grad[lo:hi])
+                hp = self._aux.get("dyn_hparams") if cuda else None
+                if hp is not None:   # graph-capturable launch: lr and bias corrections are read from device memory (jit.CapturedTrainStep)
+                    E.adamw_step_dyn(data, grad, s.master, s.state["m"], s.state["v"], float(getattr(s, "lr_scale", 1.0)), b1, b2,
+                                     float(self._epsilon), wd, sq, max_norm, found_inf, inv_scale, hp)
+                else:
+                    E.adamw_step(data, grad, s.master, s.state["m"], s.state["v"], lr * getattr(s, "lr_scale", 1.0), b1, b2,
+                                 float(self._epsilon), wd, self._step_count, sq, max_norm, found_inf, inv_scale)
+            if shard is not None:
+                self._gather_shards(s, shard)
+
+    def _arena_restore(self, state_dict):
+        """Checkpoint -> slab state (moments, fp32 master weights), honouring the shard range. Called from set_state_dict; when the
+        arena is created later the dict waits in `_aux['pending_state']` until the first step."""
+        slabs = self._arena.all_slabs()
+        dev = slabs[0].data.device
+        masters = state_dict.get("master_weights", {}) or {}
+        for s in slabs:
+            lo, hi = self._shard_bounds(s.numel)
+            n = hi - lo
+            if not any(f"{p.name}_moment1_0" in state_dict for p in s.params):
                 continue
-            E.adamw_step(s.data, s.grad, s.master, s.state["m"], s.state["v"], lr * getattr(s, "lr_scale", 1.0), b1, b2,
-                         float(self._epsilon), wd, self._step_count, sq, max_norm, found_inf, inv_scale)
+            sdt = self._moment_dtype or (torch.float32 if (self._multi_precision or s.dtype == torch.float32) else s.dtype)
+            if "m" not in s.state:
+                s.state["m"] = torch.zeros(n, dtype=sdt, device=dev)
+                s.state["v"] = torch.zeros(n, dtype=sdt, device=dev)
+            if self._multi_precision and s.dtype != torch.float32 and s.master is None:
+                s.master = s.data[lo:hi].float()
+            for p in s.params:
+                o, cnt = s.offsets[p.name]
+                a, b = max(o, lo), min(o + cnt, hi)          # part of this parameter that falls into the local range
+                if a >= b:
+                    continue
+                for key, dst in ((f"{p.name}_moment1_0", s.state["m"]), (f"{p.name}_moment2_0", s.state["v"])):
+                    src = state_dict.get(key)
+                    if src is not None:
+                        dst[a - lo:b - lo].copy_(torch.as_tensor(np.asarray(src) if not isinstance(src, torch.Tensor) else src).reshape(-1)[a - o:b - o].to(dst.dtype))
+                mw = masters.get(p.name)
+                if mw is not None and s.master is not None:
+                    s.master[a - lo:b - lo].copy_(torch.as_tensor(np.asarray(mw) if not isinstance(mw, torch.Tensor) else mw).reshape(-1)[a - o:b - o].float())
+
+    def _gather_shards(self, slab, shard):
+        """Every owner publishes its updated range of the parameter slab (stage 1: parameters stay replicated)."""
+        import torch.distributed as dist
+
+        rank, world, group = shard
+        pg = getattr(group, "pg", group)
+        saved = self._aux["shard"]
+        for r in range(world):
+            self._aux["shard"] = (r, world, group)
+            lo, hi = self._shard_bounds(slab.numel)
+            if hi > lo:
+                dist.broadcast(slab.data[lo:hi], src=dist.get_global_rank(pg, r) if pg is not None else r, group=pg)
+        self._aux["shard"] = saved
+
+    def _full_state(self, slab, key):
+        """Full-length view of a (possibly sharded) per-slab state tensor: shards are gathered for checkpoints."""
+        shard = self._aux.get("shard")
+        t = slab.master if key == "master" else slab.state[key]
+        if shard is None or t is None:
+            return t
+        import torch.distributed as dist
+
+        rank, world, group = shard
+        pg = getattr(group, "pg", group)
+        full = torch.zeros(slab.numel, dtype=t.dtype, device=t.device)
+        saved = self._aux["shard"]
+        for r in range(world):
+            self._aux["shard"] = (r, world, group)
+            lo, hi = self._shard_bounds(slab.numel)
+            if hi > lo:
+                if r == rank:
+                    full[lo:hi].copy_(t)
+                dist.broadcast(full[lo:hi], src=dist.get_global_rank(pg, r) if pg is not None else r, group=pg)
+        self._aux["shard"] = saved
+        return full
 
     def _refresh_dyn_hparams(self):
         """Write {lr, 1 - b1^t, 1 - b2^t} for the *next* update into the device tensor the captured AdamW launches read."""
@@ -479,16 +566,22 @@ class Adam(Optimizer):
             for s in self._arena.all_slabs():
                 if "m" not in s.state:
                     continue
+                fm, fv, fmaster = self._full_state(s, "m"), self._full_state(s, "v"), self._full_state(s, "master")
                 for p in s.params:
                     o, n = s.offsets[p.name]
-                    sd[f"{p.name}_moment1_0"] = s.state["m"][o:o + n].view(tuple(p.size())).as_subclass(Tensor)
-                    sd[f"{p.name}_moment2_0"] = s.state["v"][o:o + n].view(tuple(p.size())).as_subclass(Tensor)
-                    if s.master is not None:
-                        sd.setdefault("master_weights", {})[p.name] = s.master[o:o + n].view(tuple(p.size())).as_subclass(Tensor)
+                    sd[f"{p.name}_moment1_0"] = fm[o:o + n].view(tuple(p.size())).as_subclass(Tensor)
+                    sd[f"{p.name}_moment2_0"] = fv[o:o + n].view(tuple(p.size())).as_subclass(Tensor)
+                    if fmaster is not None:
+                        sd.setdefault("master_weights", {})[p.name] = fmaster[o:o + n].view(tuple(p.size())).as_subclass(Tensor)
         return sd
 
     def set_state_dict(self, state_dict):
         super().set_state_dict(state_dict)
+        if self._arena is not None:
+            with torch.no_grad():
+                self._arena_restore(state_dict)
+        else:
+            self._aux["pending_state"] = state_dict      # the flat arena may be enabled after loading
         steps = self._aux.setdefault("steps", {})
         b1, _ = self._betas()
         for pname, t in self._accumulators.get("beta1_pow_acc", {}).items():

@@ -932,29 +932,45 @@ def case_hybrid_scaler():
 
 def case_fleet_sharding_degree():
     """hybrid_configs sharding_degree=2 through fleet.distributed_model / distributed_optimizer == single-process training on the full
-    batch. Parity: hybrid_parallel_sharding_model.py."""
+    batch, with a global-norm clip that is active (SGD, and AdamW with a large epsilon so that the clip coefficient matters).
+    Parity: hybrid_parallel_sharding_model.py."""
     s, hcg = setup(sharding=2)
     r = hcg.get_sharding_parallel_rank()
-    paddle.seed(19 + r)
-    net = nn.Sequential(nn.Linear(8, 16), nn.GELU(), nn.Linear(16, 4))
-    model = fleet.distributed_model(net)
-    paddle.seed(19)
-    ref = nn.Sequential(nn.Linear(8, 16), nn.GELU(), nn.Linear(16, 4))
-    opt = fleet.distributed_optimizer(paddle.optimizer.AdamW(1e-2, parameters=net.parameters(), weight_decay=0.01,
-                                                             grad_clip=paddle.nn.ClipGradByGlobalNorm(0.5)))
-    ropt = paddle.optimizer.AdamW(1e-2, parameters=ref.parameters(), weight_decay=0.01, grad_clip=paddle.nn.ClipGradByGlobalNorm(0.5))
-    torch.manual_seed(4)
-    x, y = torch.randn(8, 8).as_subclass(paddle.Tensor), torch.randn(8, 4).as_subclass(paddle.Tensor)
-    for _ in range(3):
-        sl = slice(r * 4, (r + 1) * 4)
-        ((model(x[sl]) - y[sl]) ** 2).mean().backward()
-        opt.step()
-        opt.clear_grad()
-        ((ref(x) - y) ** 2).mean().backward()
-        ropt.step()
-        ropt.clear_grad()
-    for (k, a), (_, b) in zip(net.state_dict().items(), ref.state_dict().items()):
-        close(a.numpy(), b.numpy(), 2e-4)
+    for kind in ("sgd", "adamw"):
+        def make_opt(params):
+            clip = paddle.nn.ClipGradByGlobalNorm(0.05)
+            if kind == "sgd":
+                return paddle.optimizer.SGD(0.5, parameters=params, grad_clip=clip)
+            return paddle.optimizer.AdamW(0.05, parameters=params, weight_decay=0.01, epsilon=1.0, grad_clip=clip)
+
+        paddle.seed(19 + r)
+        net = nn.Sequential(nn.Linear(8, 16), nn.GELU(), nn.Linear(16, 4))
+        model = fleet.distributed_model(net)
+        paddle.seed(19)
+        ref = nn.Sequential(nn.Linear(8, 16), nn.GELU(), nn.Linear(16, 4))
+        opt = fleet.distributed_optimizer(make_opt(net.parameters()))
+        ropt = make_opt(ref.parameters())
+        torch.manual_seed(4)
+        x, y = torch.randn(8, 8).as_subclass(paddle.Tensor), torch.randn(8, 4).as_subclass(paddle.Tensor)
+        for _ in range(3):
+            sl = slice(r * 4, (r + 1) * 4)
+            ((model(x[sl]) - y[sl]) ** 2).mean().backward()
+            opt.step()
+            opt.clear_grad()
+            ((ref(x) - y) ** 2).mean().backward()
+            ropt.step()
+            ropt.clear_grad()
+        for (k, a), (_, b) in zip(net.state_dict().items(), ref.state_dict().items()):
+            close(a.numpy(), b.numpy(), 2e-4)
+        if kind == "adamw":
+            inner = opt._inner_opt
+            slabs = inner._arena.all_slabs()
+            held, total = sum(sl.state["m"].numel() for sl in slabs), sum(sl.numel for sl in slabs)
+            assert held <= total // 2 + 8 * len(slabs), f"stage 1 keeps 1/2 of the moments per rank, holds {held} of {total}"
+            sd, rsd = opt.state_dict(), ropt.state_dict()      # checkpoints see full-length state, equal to the unsharded run
+            for p, rp in zip(net.parameters(), ref.parameters()):
+                close(sd[f"{p.name}_moment1_0"].numpy(), rsd[f"{rp.name}_moment1_0"].numpy(), 2e-4)
+                assert list(sd[f"{p.name}_moment2_0"].shape) == list(p.shape)
 
 
 if __name__ == "__main__":

@@ -188,3 +188,56 @@ def test_amp_autocast_and_scaler():
     np.testing.assert_allclose(p.numpy(), [0.8, 0.8], rtol=1e-6)
     st = sc.state_dict()
     assert st["scale"] < 16.0 or float(np.asarray(st["scale"])) < 16.0
+
+
+def test_flat_arena_adamw_checkpoint_resume():
+    """AdamW on flat arenas: optimizer state_dict -> new optimizer -> set_state_dict continues exactly like the uninterrupted run,
+    whether the arena is enabled before or after loading."""
+    import numpy as np
+
+    import paddle_b200 as paddle
+
+    def make(seed=0):
+        paddle.seed(seed)
+        net = paddle.nn.Sequential(paddle.nn.Linear(6, 12), paddle.nn.Tanh(), paddle.nn.Linear(12, 3))
+        opt = paddle.optimizer.AdamW(5e-2, parameters=net.parameters(), weight_decay=0.1, grad_clip=paddle.nn.ClipGradByGlobalNorm(0.5))
+        return net, opt
+
+    rng = np.random.RandomState(0)
+    data = [(paddle.to_tensor(rng.randn(5, 6).astype("float32")), paddle.to_tensor(rng.randn(5, 3).astype("float32"))) for _ in range(5)]
+
+    def run(net, opt, batches):
+        for x, y in batches:
+            ((net(x) - y) ** 2).mean().backward()
+            opt.step()
+            opt.clear_grad()
+
+    net_a, opt_a = make()
+    opt_a.enable_flat_arena()
+    run(net_a, opt_a, data)
+    for arena_first in (True, False):
+        net_b, opt_b = make()
+        opt_b.enable_flat_arena()
+        run(net_b, opt_b, data[:3])
+        msd = {k: v.numpy().copy() for k, v in net_b.state_dict().items()}
+        osd = opt_b.state_dict()
+        net_c, opt_c = make(seed=123)                    # different init: everything must come from the checkpoint
+        net_c.set_state_dict({k: paddle.to_tensor(v) for k, v in msd.items()})
+        # parameter names differ between instances: remap the optimizer entries by position
+        remap = {}
+        for pb, pc in zip(net_b.parameters(), net_c.parameters()):
+            for suf in ("_moment1_0", "_moment2_0", "_beta1_pow_acc_0", "_beta2_pow_acc_0"):
+                if pb.name + suf in osd:
+                    remap[pc.name + suf] = osd[pb.name + suf]
+        for k, v in osd.items():
+            if not any(k.startswith(p.name + "_") for p in net_b.parameters()):
+                remap[k] = v
+        if arena_first:
+            opt_c.enable_flat_arena()
+            opt_c.set_state_dict(remap)
+        else:
+            opt_c.set_state_dict(remap)
+            opt_c.enable_flat_arena()
+        run(net_c, opt_c, data[3:])
+        for (k, a), (_, c) in zip(net_a.state_dict().items(), net_c.state_dict().items()):
+            np.testing.assert_allclose(c.numpy(), a.numpy(), rtol=1e-5, atol=1e-6, err_msg=f"{k} arena_first={arena_first}")
