@@ -33,6 +33,13 @@ def init(role_maker=None, is_collective=False, strategy=None, log_level="INFO"):
     """fleet.init: builds the hybrid topology (dp/pp/sharding/sep/mp) and its process groups."""
     strategy = strategy or DistributedStrategy()
     _state["strategy"] = strategy
+    from . import ps_mode
+
+    if not is_collective and ps_mode.ps_env_present():      # parameter-server job (TRAINING_ROLE / PADDLE_PSERVERS_IP_PORT_LIST)
+        _state["ps"] = ps_mode.init(strategy)
+        _state["initialized"] = True
+        return None
+    _state["ps"] = None
     if not _env.is_initialized():
         _env.init_parallel_env()
     hc = strategy.hybrid_configs
@@ -55,38 +62,86 @@ def init(role_maker=None, is_collective=False, strategy=None, log_level="INFO"):
     return None
 
 
+def _ps():
+    return _state.get("ps")
+
+
 def is_first_worker():
-    return _env.get_rank() == 0
+    return (_ps().index == 0 and not _ps().is_server) if _ps() else _env.get_rank() == 0
 
 
 def worker_index():
-    return _env.get_rank()
+    return _ps().index if _ps() else _env.get_rank()
 
 
 def worker_num():
-    return _env.get_world_size()
+    return _ps().n_workers if _ps() else _env.get_world_size()
+
+
+def server_num():
+    return _ps().n_servers if _ps() else 0
+
+
+def server_index():
+    return _ps().index if (_ps() and _ps().is_server) else -1
+
+
+def server_endpoints(to_string=False):
+    eps = list(_ps().endpoints) if _ps() else []
+    return ",".join(eps) if to_string else eps
 
 
 def is_worker():
-    return True
+    return not _ps().is_server if _ps() else True
 
 
 def is_server():
-    return False
+    return _ps().is_server if _ps() else False
 
 
 def barrier_worker():
+    if _ps():
+        return
     from .. import collective
 
     collective.barrier()
 
 
-def init_worker():
-    pass
+def init_server(*args, **kwargs):
+    from . import ps_mode
+
+    return ps_mode.init_server(*args, **kwargs)
+
+
+def run_server():
+    from . import ps_mode
+
+    return ps_mode.run_server()
+
+
+def init_worker(scopes=None):
+    if _ps():
+        from . import ps_mode
+
+        return ps_mode.init_worker()
 
 
 def stop_worker():
-    pass
+    if _ps():
+        from . import ps_mode
+
+        ps_mode.stop_worker()
+
+
+def save_persistables(executor=None, dirname=None, main_program=None, mode=0):
+    """PS mode: every server writes its tables to `dirname`; collective mode: plain static persistables save."""
+    if _ps():
+        from . import ps_mode
+
+        return ps_mode.client().save(dirname)
+    from .. import extras
+
+    return extras.io.save_persistables(executor, dirname, main_program)
 
 
 def get_strategy():
