@@ -29,12 +29,64 @@ def parse(argv=None):
     ap.add_argument("--run_mode", default="collective")
     ap.add_argument("--max_restart", type=int, default=0)
     ap.add_argument("--elastic_timeout", type=int, default=30)
+    ap.add_argument("--server_num", type=int, default=None, help="parameter-server mode: servers started on this node")
+    ap.add_argument("--trainer_num", type=int, default=None, help="parameter-server mode: trainers started on this node")
+    ap.add_argument("--servers", default="", help="parameter-server mode: explicit ip:port list of the servers")
     ap.add_argument("training_script")
     ap.add_argument("training_script_args", nargs=argparse.REMAINDER)
     return ap.parse_args(argv)
 
 
+def launch_ps(args):
+    """Parameter-server controller: starts the servers and trainers of this node with the TRAINING_ROLE / PADDLE_PSERVERS_IP_PORT_LIST
+    protocol (Parity: launch/controllers/ps.py). A failing process tears the job down; servers exit by themselves when every trainer
+    called fleet.stop_worker()."""
+    n_srv = args.server_num or (len(args.servers.split(",")) if args.servers else 1)
+    n_trn = args.trainer_num or 1
+    endpoints = args.servers.split(",") if args.servers else [f"127.0.0.1:{_free_port()}" for _ in range(n_srv)]
+    os.makedirs(args.log_dir, exist_ok=True)
+    base = dict(os.environ, PADDLE_PSERVERS_IP_PORT_LIST=",".join(endpoints), PADDLE_TRAINERS_NUM=str(n_trn), PADDLE_JOB_ID=args.job_id)
+    procs = []
+    for i in range(n_srv):
+        ip, port = endpoints[i].rsplit(":", 1)
+        env = dict(base, TRAINING_ROLE="PSERVER", POD_IP=ip, PADDLE_PORT=port, PADDLE_PSERVER_ID=str(i))
+        log = open(os.path.join(args.log_dir, f"serverlog.{i}"), "w")
+        procs.append((subprocess.Popen([sys.executable, "-u", args.training_script, *args.training_script_args], env=env, stdout=log, stderr=subprocess.STDOUT), log))
+    for i in range(n_trn):
+        env = dict(base, TRAINING_ROLE="TRAINER", PADDLE_TRAINER_ID=str(i))
+        log = open(os.path.join(args.log_dir, f"workerlog.{i}"), "w")
+        procs.append((subprocess.Popen([sys.executable, "-u", args.training_script, *args.training_script_args], env=env,
+                                       stdout=log if i != 0 else None, stderr=subprocess.STDOUT if i != 0 else None), log))
+    failed = None
+    while True:
+        alive = False
+        for p, _ in procs:
+            rc = p.poll()
+            if rc is None:
+                alive = True
+            elif rc != 0 and failed is None:
+                failed = rc
+        if failed is not None or not alive:
+            break
+        time.sleep(0.3)
+    if failed is not None:
+        for p, _ in procs:
+            if p.poll() is None:
+                p.send_signal(signal.SIGTERM)
+        for p, _ in procs:
+            try:
+                p.wait(timeout=10)
+            except subprocess.TimeoutExpired:
+                p.kill()
+        print(f"[launch] ps job failed with exit code {failed}; see {args.log_dir}/serverlog.* and workerlog.*", file=sys.stderr)
+    for _, log in procs:
+        log.close()
+    return failed or 0
+
+
 def launch(args):
+    if args.run_mode == "ps" or args.server_num or args.servers:
+        return launch_ps(args)
     import torch
 
     devices = [d for d in args.devices.split(",")] if args.devices else [str(i) for i in range(max(1, torch.cuda.device_count()))]

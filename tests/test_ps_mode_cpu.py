@@ -45,3 +45,13 @@ def test_ps_job(tmp_path, a_sync):
         _launch(tmp_path, a_sync, load=True)
         resumed_first = float((tmp_path / "worker0.ok").read_text().split()[0])
         assert resumed_first < first_run * 1.6 + 0.1
+
+
+def test_launch_ps_controller(tmp_path):
+    """python -m paddle_b200.distributed.launch --server_num 1 --trainer_num 2 <script>: role env wiring + logs."""
+    r = subprocess.run([sys.executable, "-m", "paddle_b200.distributed.launch", "--server_num", "1", "--trainer_num", "2", "--log_dir", str(tmp_path / "log"),
+                        os.path.join(ROOT, "tests", "_ps_worker.py"), str(tmp_path)], env=dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="1"),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "server done" in (tmp_path / "log" / "serverlog.0").read_text()
+    assert (tmp_path / "worker0.ok").exists() and (tmp_path / "worker1.ok").exists()
