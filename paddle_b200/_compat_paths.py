@@ -171,6 +171,7 @@ _reexport(_FLEET + ".meta_optimizers.dygraph_optimizer.hybrid_parallel_optimizer
 _reexport(_FLEET + ".data_generator", "fleet.data_generator", [_FLEET + ".base_extras"], ["MultiSlotDataGenerator", "MultiSlotStringDataGenerator"])
 _reexport(_FLEET + ".dataset", "fleet.dataset", ["distributed.extras"], ["InMemoryDataset", "QueueDataset"])
 _reexport(_FLEET + ".scaler", "fleet.scaler", [_FLEET], ["distributed_scaler"])
+_reexport(_FLEET + ".auto", "paddle.distributed.fleet.auto (semi-auto parallel entry points)", ["distributed.auto_parallel"])
 _reexport(_FLEET + ".fleet", "fleet.fleet", [_FLEET + ".base_extras", _FLEET], ["Fleet"])
 _reexport("distributed.parallel", "paddle.distributed.parallel", ["distributed", "distributed.data_parallel"], ["DataParallel", "init_parallel_env", "ParallelEnv", "get_rank", "get_world_size"])
 _reexport("distributed.collective", "paddle.distributed.collective", ["distributed.collective"])

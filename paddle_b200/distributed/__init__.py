@@ -35,3 +35,5 @@ def __getattr__(name):
         mod = importlib.import_module(".sharding", __name__)
         return getattr(mod, name)
     raise AttributeError(f"module 'paddle_b200.distributed' has no attribute '{name}'")
+
+from .auto_parallel import Engine, LocalLayer, ShardDataloader, enable_auto_dp, to_distributed  # noqa: F401,E402

@@ -12,3 +12,5 @@ from .api import (DistAttr, DistModel, DistTensor, ShardingStage1, ShardingStage
                   reshard, shard_dataloader, shard_layer, shard_optimizer, shard_scaler, shard_tensor, to_static, unshard_dtensor)
 from .intermediate import (ColWiseParallel, PrepareLayerInput, PrepareLayerOutput, RowWiseParallel, SequenceParallelBegin,  # noqa: F401
                            SequenceParallelDisable, SequenceParallelEnable, SequenceParallelEnd, SplitPoint, parallelize)
+from .api import _ShardDataLoader as ShardDataloader  # noqa: F401,E402
+from .engine import Engine, LocalLayer, enable_auto_dp, in_auto_dp_mode, to_distributed  # noqa: F401,E402

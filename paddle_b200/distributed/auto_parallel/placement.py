@@ -52,7 +52,8 @@ class Shard(Placement):
 class Partial(Placement):
     def __init__(self, reduce_type="sum"):
         rt = getattr(reduce_type, "name", reduce_type)
-        self.reduce_type = str(rt).lower().replace("reduceop.", "").replace("k_red_", "")
+        rt = str(rt).lower().replace("reduceop.", "").replace("k_red_", "")
+        self.reduce_type = rt[4:] if rt.startswith("kred") else rt          # ReduceType.kRedSum -> "sum"
 
     def is_partial(self):
         return True

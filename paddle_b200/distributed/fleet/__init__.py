@@ -189,3 +189,11 @@ meta_parallel = _MetaParallel()
 
 from .base_extras import Fleet, MultiSlotDataGenerator, MultiSlotStringDataGenerator, Role, UtilBase  # noqa: F401,E402
 from . import utils  # noqa: F401,E402
+
+
+def __getattr__(name):
+    if name == "auto":      # paddle.distributed.fleet.auto
+        import importlib
+
+        return importlib.import_module(__name__ + ".auto")
+    raise AttributeError(name)

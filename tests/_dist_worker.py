@@ -973,6 +973,69 @@ def case_fleet_sharding_degree():
                 assert list(sd[f"{p.name}_moment2_0"].shape) == list(p.shape)
 
 
+def case_auto_engine():
+    """fleet.auto.Engine.fit over 2 ranks (batch-sharded data, replicated params averaged) == single-process training; evaluate / predict /
+    save / load; LocalLayer; to_distributed. Parity: test/auto_parallel/engine_api.py."""
+    dist.init_parallel_env()
+    r, w = dist.get_rank(), dist.get_world_size()
+    from paddle_b200.distributed.fleet import auto
+
+    class DS(paddle.io.Dataset):
+        def __init__(self, n):
+            rs = np.random.RandomState(0)
+            self.x, self.y = rs.randn(n, 6).astype("float32"), rs.randn(n, 2).astype("float32")
+
+        def __len__(self):
+            return len(self.x)
+
+        def __getitem__(self, i):
+            return self.x[i], self.y[i]
+
+    paddle.seed(23)
+    net = nn.Sequential(nn.Linear(6, 12), nn.Tanh(), nn.Linear(12, 2))
+    ref = nn.Sequential(nn.Linear(6, 12), nn.Tanh(), nn.Linear(12, 2))
+    ref.set_state_dict(net.state_dict())
+    loss = nn.MSELoss()
+    eng = auto.Engine(net, loss, paddle.optimizer.SGD(0.1, parameters=net.parameters()), strategy=auto.Strategy())
+    ds = DS(16)
+    logs = eng.fit(ds, batch_size=8, epochs=2)
+    assert len(logs["loss"]) == 4
+    ropt = paddle.optimizer.SGD(0.1, parameters=ref.parameters())
+    for _ in range(2):
+        for lo in (0, 8):
+            # DistributedBatchSampler deals sample i to rank i % world: the global batch of a step is samples [lo, lo + 8)
+            x, y = paddle.to_tensor(ds.x[lo:lo + 8]), paddle.to_tensor(ds.y[lo:lo + 8])
+            loss(ref(x), y).backward()
+            ropt.step()
+            ropt.clear_grad()
+    for (k, a), (_, b) in zip(net.state_dict().items(), ref.state_dict().items()):
+        close(a.numpy(), b.numpy(), 1e-4)
+    ev = eng.evaluate(ds, batch_size=8)
+    assert ev["loss"] is not None and ev["loss"] < logs["loss"][0]
+    preds = eng.predict(ds, batch_size=8, steps=1)
+    assert preds[0].shape == [4, 2]
+    tmp = os.environ.get("B200_TEST_TMP", "/tmp")
+    eng.save(os.path.join(tmp, "eng", "ck"))
+    dist.barrier()
+    eng.load(os.path.join(tmp, "eng", "ck"))
+    mesh = dist.ProcessMesh([0, 1], dim_names=["x"])
+
+    class Masked(auto.LocalLayer):
+        def __init__(self):
+            super().__init__(out_dist_attrs=[(mesh, [dist.Partial(dist.ReduceType.kRedSum)])])
+
+        def forward(self, v):
+            return (v * (v > 0)).sum().reshape([1])
+
+    full = np.arange(-4, 4, dtype="float32").reshape(4, 2)
+    dt = dist.shard_tensor(paddle.to_tensor(full), mesh, [dist.Shard(0)])
+    tot = dist.reshard(Masked()(dt), mesh, [dist.Replicate()])
+    close(tot.numpy(), [full[full > 0].sum()], 1e-6)
+    m2, o2, l2 = dist.to_distributed(net, paddle.optimizer.SGD(0.1, parameters=net.parameters()), paddle.io.DataLoader(ds, batch_size=4), device_num=2)
+    xb, yb = next(iter(l2))
+    assert list(xb.shape)[0] == 4 * w or list(xb.shape)[0] == 4
+
+
 if __name__ == "__main__":
     case = sys.argv[1]
     if GPU:
