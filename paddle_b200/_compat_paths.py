@@ -184,6 +184,17 @@ _reexport("distributed.utils.moe_utils", "distributed.utils.moe_utils", ["incuba
 _reexport("distributed.models", "paddle.distributed.models", [])
 _reexport("distributed.models.moe", "paddle.distributed.models.moe", ["incubate.moe"])
 
+@alias("incubate.asp")
+def _asp_module():
+    inc = importlib.import_module(_PKG + ".incubate")
+    a = inc.__dict__["asp"]
+    m = _mod(_PKG + ".incubate.asp", "paddle.incubate.asp: 2:4 structured sparsity")
+    for k in ("calculate_density", "decorate", "prune_model", "set_excluded_layers", "reset_excluded_layers", "add_supported_layer"):
+        if hasattr(a, k):
+            setattr(m, k, getattr(a, k))
+    return m
+
+
 # ---- incubate paths ---------------------------------------------------------------------------------------------------------------
 _reexport("incubate.distributed", "paddle.incubate.distributed", [])
 _reexport("incubate.distributed.fleet", "paddle.incubate.distributed.fleet", [_FLEET + ".recompute"], ["recompute_sequential", "recompute_hybrid"])
@@ -194,6 +205,7 @@ _reexport("incubate.distributed.models.moe.gate", "moe.gate", ["incubate.moe"], 
 _reexport("incubate.distributed.models.moe.grad_clip", "moe.grad_clip", ["incubate.moe"], ["ClipGradForMOEByGlobalNorm"])
 _reexport("incubate.distributed.utils", "paddle.incubate.distributed.utils", [])
 _reexport("incubate.distributed.utils.io", "incubate.distributed.utils.io", ["distributed.extras"], ["save_for_auto_inference"])
+_reexport("incubate.optimizer.functional", "paddle.incubate.optimizer.functional", ["incubate.optimizer_functional"], ["minimize_bfgs", "minimize_lbfgs"])
 _reexport("incubate.tensor", "paddle.incubate.tensor", ["geometric"], ["segment_sum", "segment_mean", "segment_max", "segment_min"])
 _reexport("incubate.tensor.math", "paddle.incubate.tensor.math", ["geometric"], ["segment_sum", "segment_mean", "segment_max", "segment_min"])
 _reexport("incubate.operators", "paddle.incubate.operators", ["incubate"],

@@ -80,7 +80,10 @@ class _ASP:
         from ..nn import Conv2D, Linear
 
         for name, layer in model.named_sublayers(include_self=True):
-            if isinstance(layer, (Linear, Conv2D)) and layer.weight.name not in cls._excluded:
+            extra = tuple(t for t, _ in cls._supported if isinstance(t, type))
+            names = {t for t, _ in cls._supported if isinstance(t, str)}
+            if (isinstance(layer, (Linear, Conv2D) + extra) or type(layer).__name__ in names) and getattr(layer, "weight", None) is not None \
+                    and layer.weight.name not in cls._excluded:
                 w = _raw(layer.weight)
                 flat = w.detach().reshape(-1, m) if w.numel() % m == 0 else None
                 if flat is None:
@@ -91,6 +94,13 @@ class _ASP:
                     w.mul_(mask)
                 cls._masks[layer.weight.name] = mask
         return cls._masks
+
+    _supported = []
+
+    @classmethod
+    def add_supported_layer(cls, layer, pruning_func=None):
+        """Register an extra layer type (class or name) whose `weight` takes part in prune_model."""
+        cls._supported.append((layer, pruning_func))
 
     @classmethod
     def decorate(cls, optimizer):

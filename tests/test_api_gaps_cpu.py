@@ -285,3 +285,35 @@ def test_capture_train_step_cpu_falls_back_to_eager():
     x = paddle.ones([3, 4])
     losses = [float(step(x)) for _ in range(5)]
     assert not step.captured and losses[-1] < losses[0] and opt._step_count == 5
+
+
+def test_quasi_newton_minimizers_asp_module_groupwise_observer():
+    from paddle_b200.incubate.optimizer.functional import minimize_bfgs, minimize_lbfgs
+
+    def rosen(x):
+        return (1 - x[0]) ** 2 + 100 * (x[1] - x[0] ** 2) ** 2
+
+    conv, calls, pos, val, grad, H = minimize_bfgs(rosen, paddle.to_tensor([-1.2, 1.0]), max_iters=200, dtype="float64")
+    assert bool(conv) and np.allclose(pos.numpy(), [1, 1], atol=1e-5) and float(val) < 1e-10 and H.shape == [2, 2] and int(calls) > 10
+    conv, calls, pos, val, grad = minimize_lbfgs(rosen, paddle.to_tensor([-1.2, 1.0]), max_iters=200, dtype="float64", history_size=5)
+    assert bool(conv) and np.allclose(pos.numpy(), [1, 1], atol=1e-5) and float(grad.abs().max()) < 1e-5
+    import paddle_b200.incubate.asp as asp
+
+    class MyProj(paddle.nn.Layer):
+        def __init__(self):
+            super().__init__()
+            self.weight = self.create_parameter([8, 8])
+
+        def forward(self, x):
+            return x @ self.weight
+
+    asp.add_supported_layer(MyProj)
+    m = MyProj()
+    asp.prune_model(m)
+    assert abs(asp.calculate_density(m.weight) - 0.5) < 1e-6
+    from paddle_b200.quantization.observers import GroupWiseWeightObserver, GroupWiseWeightObserverLayer
+
+    ob = GroupWiseWeightObserverLayer(None, quant_bits=4, group_size=4)
+    w = paddle.to_tensor(np.arange(32, dtype="float32").reshape(8, 4) - 10)
+    ob(w)
+    assert ob.scales().shape == [2, 4] and float(ob.scales()[1, 3]) == 21.0 and ob.bit_length() == 4 and GroupWiseWeightObserver(4, 4) is not None
