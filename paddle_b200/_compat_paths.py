@@ -195,6 +195,23 @@ def _asp_module():
     return m
 
 
+_reexport("geometric.message_passing", "paddle.geometric.message_passing", ["geometric"], ["send_u_recv", "send_ue_recv", "send_uv"])
+_reexport("geometric.sampling", "paddle.geometric.sampling", ["geometric"], ["sample_neighbors", "weighted_sample_neighbors"])
+_reexport("geometric.reindex", "paddle.geometric.reindex", ["geometric"], ["reindex_graph", "reindex_heter_graph"])
+_reexport("geometric.math", "paddle.geometric.math", ["geometric"], ["segment_sum", "segment_mean", "segment_min", "segment_max"])
+_reexport("base.layers", "paddle.base.layers (legacy op-builder namespace)", ["static.nn", "ops"])
+_reexport(_FLEET + ".runtime", "paddle.distributed.fleet.runtime", [_FLEET + ".ps_mode"])
+
+
+@alias("device.xpu")
+def _xpu_module():
+    def _none(*a, **k):
+        raise RuntimeError("XPU devices are not supported by paddle_b200 (sm_100a only)")
+
+    return _mod(_PKG + ".device.xpu", "paddle.device.xpu: not available on this target", synchronize=_none, device_count=lambda: 0, set_debug_level=lambda level=1: None,
+                empty_cache=lambda: None, max_memory_allocated=lambda device=None: 0, memory_allocated=lambda device=None: 0)
+
+
 # ---- incubate paths ---------------------------------------------------------------------------------------------------------------
 _reexport("incubate.distributed", "paddle.incubate.distributed", [])
 _reexport("incubate.distributed.fleet", "paddle.incubate.distributed.fleet", [_FLEET + ".recompute"], ["recompute_sequential", "recompute_hybrid"])
