@@ -353,7 +353,8 @@ def _cross_mesh(x, t, mesh, placements):
     return full
 
 
-def unshard_dtensor(t):
+def unshard_dtensor(dist_tensor):
+    t = dist_tensor
     if not _is_dt(t):
         return t
     r = reshard(t, t.process_mesh, [Replicate()] * t.process_mesh.ndim)
@@ -695,7 +696,11 @@ def _set_grad(p, g):
 class _ShardingStage:
     stage = 0
 
-    def __init__(self, sharding_mesh_dim=None, mesh=None):
+    def __init__(self, mesh=None, sharding_mesh_dim=None):
+        if isinstance(mesh, (str, int)) and sharding_mesh_dim is None:      # older call style: ShardingStage1("dp", mesh)
+            mesh, sharding_mesh_dim = None, mesh
+        elif isinstance(mesh, (str, int)):
+            mesh, sharding_mesh_dim = sharding_mesh_dim, mesh
         self.mesh_dim, self.mesh = sharding_mesh_dim, mesh
 
     def __call__(self, key, param, accumulator):
@@ -800,8 +805,8 @@ def shard_scaler(scaler):
 
 
 class _ShardDataLoader:
-    def __init__(self, loader, meshes, input_keys=None, shard_dims=None, is_dataset_splitted=False):
-        self.loader, self.meshes = loader, meshes if isinstance(meshes, (list, tuple)) else [meshes]
+    def __init__(self, dataloader, meshes, input_keys=None, shard_dims=None, is_dataset_splitted=False):
+        self.loader, self.meshes = dataloader, meshes if isinstance(meshes, (list, tuple)) else [meshes]
         self.shard_dims = shard_dims if isinstance(shard_dims, (list, tuple)) else [shard_dims] * len(self.meshes)
         self.keys, self.splitted = input_keys, is_dataset_splitted
 

@@ -27,8 +27,8 @@ _OP = {ReduceOp.SUM: dist.ReduceOp.SUM, ReduceOp.MAX: dist.ReduceOp.MAX, ReduceO
 class Group:
     """Process group handle. Parity: communication/group.py:Group."""
 
-    def __init__(self, rank_in_group, gid, ranks, pg=None, name=None):
-        self._rank_in_group, self._id, self._ranks, self.pg, self._name = rank_in_group, gid, list(ranks), pg, name
+    def __init__(self, rank_in_group, id, ranks, pg=None, name=None):  # noqa: A002  (reference parameter name)
+        self._rank_in_group, self._id, self._ranks, self.pg, self._name = rank_in_group, id, list(ranks), pg, name
 
     @property
     def rank(self):
@@ -92,8 +92,8 @@ def new_group(ranks=None, backend=None, timeout=None):
     return g
 
 
-def get_group(gid=0):
-    return _global_group() if gid == 0 else _groups.get(gid)
+def get_group(id=0):  # noqa: A002
+    return _global_group() if id == 0 else _groups.get(id)
 
 
 def _pg(group):
@@ -242,7 +242,7 @@ def gather(tensor, gather_list=None, dst=0, group=None, sync_op=True):
     return _Task(w)
 
 
-def alltoall(out_tensor_list, in_tensor_list, group=None, sync_op=True):
+def _alltoall_out_first(out_tensor_list, in_tensor_list, group=None, sync_op=True):
     if _single():
         out_tensor_list.clear()
         out_tensor_list.extend(in_tensor_list)
@@ -269,7 +269,7 @@ def alltoall(out_tensor_list, in_tensor_list, group=None, sync_op=True):
     return _Task(w)
 
 
-def alltoall_single(out_tensor, in_tensor, in_split_sizes=None, out_split_sizes=None, group=None, sync_op=True):
+def _alltoall_single_out_first(out_tensor, in_tensor, in_split_sizes=None, out_split_sizes=None, group=None, sync_op=True):
     if _single():
         _raw(out_tensor).copy_(_raw(in_tensor))
         return _Task()
@@ -281,11 +281,21 @@ def alltoall_single(out_tensor, in_tensor, in_split_sizes=None, out_split_sizes=
         o = _raw(out_tensor)
         outs = list(o.split(out_split_sizes, 0)) if out_split_sizes else list(o.chunk(n, 0))
         tmp = [torch.empty_like(x) for x in outs]
-        alltoall(tmp, ins, group)
+        _alltoall_out_first(tmp, ins, group)
         for a, b in zip(outs, tmp):
             a.copy_(b)
         return _Task()
     return _Task(dist.all_to_all_single(_raw(out_tensor), _raw(in_tensor).contiguous(), out_split_sizes, in_split_sizes, group=pg, async_op=not sync_op))
+
+
+def alltoall(in_tensor_list, out_tensor_list, group=None, sync_op=True):
+    """Parity: distributed/communication/all_to_all.py:alltoall — the *input* list comes first (the stream.* variant takes the output first)."""
+    return _alltoall_out_first(out_tensor_list, in_tensor_list, group, sync_op)
+
+
+def alltoall_single(in_tensor, out_tensor, in_split_sizes=None, out_split_sizes=None, group=None, sync_op=True):
+    """Parity: distributed/communication/all_to_all.py:alltoall_single (input first)."""
+    return _alltoall_single_out_first(out_tensor, in_tensor, in_split_sizes, out_split_sizes, group, sync_op)
 
 
 def send(tensor, dst=0, group=None, sync_op=True):

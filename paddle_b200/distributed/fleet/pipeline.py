@@ -78,8 +78,9 @@ class SegmentLayers:
 
 class PipelineLayer(Layer):
     def __init__(self, layers, num_stages=None, topology=None, loss_fn=None, seg_method="uniform", recompute_interval=0,
-                 recompute_ctx=None, num_virtual_pipeline_stages=None):
+                 recompute_ctx=None, num_virtual_pipeline_stages=None, use_cudagraph=False):
         super().__init__()
+        self._use_cudagraph = use_cudagraph       # accepted for parity; whole-step capture lives in jit.capture_train_step
         hcg = topo.get_hybrid_communicate_group()
         self._hcg = hcg
         self._loss_fn = loss_fn

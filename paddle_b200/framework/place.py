@@ -123,7 +123,7 @@ def is_compiled_with_xpu() -> bool:
     return False
 
 
-def is_compiled_with_custom_device(_name="") -> bool:
+def is_compiled_with_custom_device(device_type="") -> bool:
     return False
 
 

@@ -7,8 +7,8 @@ import numpy as np
 import torch
 
 
-def seed(s: int):
-    s = int(s)
+def seed(seed: int):
+    s = int(seed)
     torch.manual_seed(s)
     if torch.cuda.is_available():
         torch.cuda.manual_seed_all(s)

@@ -114,7 +114,8 @@ class FusedMultiTransformer(Layer):
     def __init__(self, embed_dim, num_heads, dim_feedforward, dropout_rate=0.0, activation="gelu", normalize_before=True, ln_scale_attrs=None,
                  ln_bias_attrs=None, qkv_weight_attrs=None, qkv_bias_attrs=None, linear_weight_attrs=None, linear_bias_attrs=None, ffn_ln_scale_attrs=None,
                  ffn_ln_bias_attrs=None, ffn1_weight_attrs=None, ffn1_bias_attrs=None, ffn2_weight_attrs=None, ffn2_bias_attrs=None, epsilon=1e-5,
-                 num_layers=-1, nranks=1, trans_qkvw=True, ring_id=-1, name=None):
+                 residual_alpha=1.0, num_layers=-1, nranks=1, trans_qkvw=True, ring_id=-1, norm_type="layernorm", use_neox_rotary_style=False,
+                 gqa_group_size=-1, name=None):
         super().__init__()
         if num_layers < 0:
             num_layers = len(qkv_weight_attrs) if isinstance(qkv_weight_attrs, (list, tuple)) else 1
@@ -146,8 +147,10 @@ class FusedMultiTransformer(Layer):
     def forward(self, src, attn_mask=None, caches=None, pre_caches=None, rotary_embs=None, rotary_emb_dims=0, seq_lens=None, time_step=None):
         return FF.fused_multi_transformer(src, self._ln_scales, self._ln_biases, self._qkv_weights, self._qkv_biases, self._linear_weights,
                                           self._linear_biases, self._ffn_ln_scales, self._ffn_ln_biases, self._ffn1_weights, self._ffn1_biases,
-                                          self._ffn2_weights, self._ffn2_biases, self.normalize_before, self.epsilon, caches, pre_caches, seq_lens,
-                                          rotary_embs, time_step, attn_mask, 0.0, rotary_emb_dims, self.activation, self.training, trans_qkvw=self.trans_qkvw)
+                                          self._ffn2_weights, self._ffn2_biases, pre_layer_norm=self.normalize_before, epsilon=self.epsilon,
+                                          cache_kvs=caches, pre_caches=pre_caches, seq_lens=seq_lens, rotary_embs=rotary_embs, time_step=time_step,
+                                          attn_mask=attn_mask, dropout_rate=0.0, rotary_emb_dims=rotary_emb_dims, activation=self.activation,
+                                          training=self.training, trans_qkvw=self.trans_qkvw)
 
 
 def memory_efficient_attention(query, key, value, attn_bias=None, p=0.0, scale=None, training=True):

@@ -139,7 +139,9 @@ def fused_bias_dropout_residual_layer_norm(x, residual, bias=None, ln_scale=None
     return F.layer_norm(h, [h.shape[-1]], ln_scale, ln_bias, ln_epsilon)
 
 
-def fused_dot_product_attention(q, k, v, attn_mask=None, dropout_prob=0.0, is_causal=False, scaling_factor=None, training=True, name=None):
+def fused_dot_product_attention(query, key, value, attn_mask=None, dropout_p=0.0, is_causal=False, scaling_factor=None, training=True, name=None, dropout_prob=None):
+    q, k, v = query, key, value
+    dropout_prob = dropout_p if dropout_prob is None else dropout_prob
     return KAT.attention(q, k, v, attn_mask, dropout_prob if training else 0.0, is_causal, scaling_factor)
 
 
@@ -295,7 +297,7 @@ def fused_gate_attention(query, key=None, query_weight=None, key_weight=None, va
     return _w(out)
 
 
-def fused_moe(x, gate_weight, ffn1_weight, ffn1_scale=None, ffn1_bias=None, ffn2_weight=None, ffn2_scale=None, ffn2_bias=None, quant_method="None",
+def fused_moe(x, gate_weight, ffn1_weight, ffn2_weight, ffn1_bias=None, ffn1_scale=None, ffn2_bias=None, ffn2_scale=None, quant_method="None",
               moe_topk=2, norm_topk_prob=True, group_moe=False):
     """Token-choice top-k MoE FFN (SwiGLU experts). Parity: incubate/nn/functional/fused_moe.py."""
     from ....incubate.moe import moe_ffn
@@ -310,9 +312,10 @@ __all__ = ["fused_multi_head_attention", "fused_feedforward", "fused_multi_trans
 
 
 def fused_multi_transformer(x, ln_scales, ln_biases, qkv_weights, qkv_biases, linear_weights, linear_biases, ffn_ln_scales, ffn_ln_biases,
-                            ffn1_weights, ffn1_biases, ffn2_weights, ffn2_biases, pre_layer_norm=True, epsilon=1e-05, cache_kvs=None, pre_caches=None,
-                            seq_lens=None, rotary_embs=None, time_step=None, attn_mask=None, dropout_rate=0.0, rotary_emb_dims=0, activation="gelu",
-                            training=False, mode="upscale_in_train", trans_qkvw=True, ring_id=-1, name=None):
+                            ffn1_weights, ffn1_biases, ffn2_weights, ffn2_biases, pre_layer_norm=True, epsilon=1e-05, residual_alpha=1.0, cache_kvs=None,
+                            beam_offset=None, pre_caches=None, seq_lens=None, rotary_embs=None, time_step=None, attn_mask=None, dropout_rate=0.0,
+                            rotary_emb_dims=0, activation="gelu", training=False, mode="upscale_in_train", trans_qkvw=True, ring_id=-1,
+                            norm_type="layernorm", use_neox_rotary_style=False, gqa_group_size=-1, name=None):
     """Stack of fused decoder layers with optional KV caches. Parity: fused_transformer.py:fused_multi_transformer."""
     from ....nn import functional as F
 

@@ -137,19 +137,19 @@ class HSigmoidLoss(Layer):
 
 
 class AdaptiveLogSoftmaxWithLoss(Layer):
-    def __init__(self, in_features, n_classes, cutoffs, div_value=4.0, head_bias=False, name=None):
+    def __init__(self, in_features, n_classes, cutoffs, weight_attr=None, bias_attr=None, div_value=4.0, head_bias=False, name=None):
         super().__init__()
         self.cutoffs = list(cutoffs) + [n_classes]
         self.shortlist = self.cutoffs[0]
         self.n_clusters = len(self.cutoffs) - 1
-        self.head_weight = self.create_parameter([in_features, self.shortlist + self.n_clusters])
-        self.head_bias = self.create_parameter([self.shortlist + self.n_clusters], is_bias=True) if head_bias else None
+        self.head_weight = self.create_parameter([in_features, self.shortlist + self.n_clusters], attr=weight_attr)
+        self.head_bias = self.create_parameter([self.shortlist + self.n_clusters], attr=bias_attr, is_bias=True) if head_bias else None
         self.tail_weights = []
         for i in range(self.n_clusters):
             hsz = max(1, int(in_features // (div_value ** (i + 1))))
             osz = self.cutoffs[i + 1] - self.cutoffs[i]
-            p = self.create_parameter([in_features, hsz])
-            c = self.create_parameter([hsz, osz])
+            p = self.create_parameter([in_features, hsz], attr=weight_attr)
+            c = self.create_parameter([hsz, osz], attr=weight_attr)
             self.add_parameter(f"tail_proj_{i}", p)
             self.add_parameter(f"tail_cls_{i}", c)
             self.tail_weights.append((p, c))

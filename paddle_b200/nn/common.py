@@ -35,7 +35,7 @@ class Linear(Layer):
 
 class Embedding(Layer):
     def __init__(self, num_embeddings, embedding_dim, padding_idx=None, max_norm=None, norm_type=2.0, sparse=False,
-                 scale_grad_by_freq=False, weight_attr=None, name=None):
+                 weight_attr=None, name=None, scale_grad_by_freq=False):
         super().__init__()
         self._num_embeddings, self._embedding_dim = num_embeddings, embedding_dim
         self._padding_idx = None if padding_idx is None else (padding_idx if padding_idx >= 0 else num_embeddings + padding_idx)

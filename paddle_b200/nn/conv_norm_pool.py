@@ -90,7 +90,7 @@ class Conv1DTranspose(_ConvNd):
 class Conv2DTranspose(_ConvNd):
     _n, _default_fmt, _transposed = 2, "NCHW", True
 
-    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, groups=1, dilation=1,
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, dilation=1, groups=1,
                  weight_attr=None, bias_attr=None, data_format="NCHW"):
         super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, "zeros", weight_attr, bias_attr, data_format, output_padding)
 
@@ -101,7 +101,7 @@ class Conv2DTranspose(_ConvNd):
 class Conv3DTranspose(_ConvNd):
     _n, _default_fmt, _transposed = 3, "NCDHW", True
 
-    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, groups=1, dilation=1,
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, dilation=1, groups=1,
                  weight_attr=None, bias_attr=None, data_format="NCDHW"):
         super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, "zeros", weight_attr, bias_attr, data_format, output_padding)
 
@@ -295,9 +295,9 @@ class LocalResponseNorm(Layer):
 
 
 class SpectralNorm(Layer):
-    def __init__(self, weight_shape, dim=0, power_iters=1, epsilon=1e-12, dtype="float32"):
+    def __init__(self, weight_shape, dim=0, power_iters=1, eps=1e-12, dtype="float32", epsilon=None):
         super().__init__()
-        self._dim, self._power_iters, self._epsilon = dim, power_iters, epsilon
+        self._dim, self._power_iters, self._epsilon = dim, power_iters, (eps if epsilon is None else epsilon)
         h = weight_shape[dim]
         w = int(np.prod(weight_shape)) // h
         self.weight_u = self.create_parameter([h], default_initializer=I.Normal(0, 1))

@@ -263,7 +263,7 @@ def gather_tree(ids, parents):
     return wrap(out)
 
 
-def temporal_shift(x, seg_num, shift_ratio=0.25, data_format="NCHW", name=None):
+def temporal_shift(x, seg_num, shift_ratio=0.25, name=None, data_format="NCHW"):
     x = T(x)
     if data_format == "NHWC":
         x = x.permute(0, 3, 1, 2)

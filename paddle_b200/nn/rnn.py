@@ -231,10 +231,25 @@ class _RNNBase(Layer):
 class SimpleRNN(_RNNBase):
     _mode = "RNN_TANH"
 
+    def __init__(self, input_size, hidden_size, num_layers=1, direction="forward", time_major=False, dropout=0.0, activation="tanh",
+                 weight_ih_attr=None, weight_hh_attr=None, bias_ih_attr=None, bias_hh_attr=None, name=None):
+        super().__init__(input_size, hidden_size, num_layers, direction, time_major, dropout, weight_ih_attr, weight_hh_attr, bias_ih_attr, bias_hh_attr,
+                         activation=activation, name=name)
+
 
 class LSTM(_RNNBase):
     _mode = "LSTM"
 
+    def __init__(self, input_size, hidden_size, num_layers=1, direction="forward", time_major=False, dropout=0.0,
+                 weight_ih_attr=None, weight_hh_attr=None, bias_ih_attr=None, bias_hh_attr=None, proj_size=0, name=None):
+        super().__init__(input_size, hidden_size, num_layers, direction, time_major, dropout, weight_ih_attr, weight_hh_attr, bias_ih_attr, bias_hh_attr,
+                         proj_size=proj_size, name=name)
+
 
 class GRU(_RNNBase):
     _mode = "GRU"
+
+    def __init__(self, input_size, hidden_size, num_layers=1, direction="forward", time_major=False, dropout=0.0,
+                 weight_ih_attr=None, weight_hh_attr=None, bias_ih_attr=None, bias_hh_attr=None, name=None):
+        super().__init__(input_size, hidden_size, num_layers, direction, time_major, dropout, weight_ih_attr, weight_hh_attr, bias_ih_attr, bias_hh_attr,
+                         name=name)

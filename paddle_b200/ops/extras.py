@@ -18,8 +18,8 @@ def _inplace(x, out):
     return x
 
 
-def t_(x, name=None):
-    x = T(x)
+def t_(input, name=None):
+    x = T(input)
     return _inplace(x, x.t().contiguous()) if x.dim() == 2 else x
 
 

@@ -42,8 +42,10 @@ def transpose(x, *perm, name=None):
     return torch.permute(x, tuple(p))
 
 
-def t(x, name=None):
-    x = T(x)
+def t(input, name=None):
+    x = T(input)
+    if x.dim() > 2:
+        raise ValueError(f"paddle.t only supports tensors of rank <= 2, got {x.dim()}; use paddle.transpose")
     return x if x.dim() < 2 else torch.transpose(x, 0, 1)
 
 

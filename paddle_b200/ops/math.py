@@ -426,16 +426,45 @@ def combinations(x, r=2, with_replacement=False, name=None):
     return torch.combinations(T(x), r, with_replacement)
 
 
+def round(x, decimals=0, name=None):
+    return torch.round(T(x), decimals=int(decimals))
+
+
+def round_(x, decimals=0, name=None):
+    with torch.no_grad():
+        torch.Tensor.round_(x, decimals=int(decimals))
+    return x
+
+
+def trunc(input, name=None):
+    return torch.trunc(T(input))
+
+
 def cartesian_prod(x, name=None):
     return torch.cartesian_prod(*[T(i) for i in x])
 
 
-def bitwise_left_shift(x, y, is_arithmetic=True, name=None):
-    return torch.bitwise_left_shift(T(x), T(y))
+def _store(out, res):
+    if out is None:
+        return res
+    T(out).copy_(res)
+    return out
 
 
-def bitwise_right_shift(x, y, is_arithmetic=True, name=None):
-    return torch.bitwise_right_shift(T(x), T(y))
+def bitwise_left_shift(x, y, is_arithmetic=True, out=None, name=None):
+    return _store(out, torch.bitwise_left_shift(T(x), T(y)))
+
+
+def bitwise_right_shift(x, y, is_arithmetic=True, out=None, name=None):
+    x, y = T(x), T(y)
+    if is_arithmetic or x.dtype in (torch.uint8, torch.bool):
+        return _store(out, torch.bitwise_right_shift(x, y))
+    # logical shift of a signed integer: shift the sign-extended value, then clear the bits that were shifted in
+    bits = x.element_size() * 8
+    shifted = torch.bitwise_right_shift(x, y)
+    ones = torch.full_like(x, -1)
+    mask = torch.where(y > 0, ~torch.bitwise_left_shift(ones, (bits - y).clamp(min=0, max=bits - 1)), ones)
+    return _store(out, torch.where(y >= bits, torch.zeros_like(x), shifted & mask))
 
 
 def reduce_as(x, target, name=None):

@@ -224,7 +224,8 @@ class PTQ(Quantization):
         return self._convert(model, inplace)
 
 
-def quanter(name):
+def quanter(class_name):
+    name = class_name
     def deco(cls):
         globals()[name] = lambda *a, **k: QuanterFactory(cls, *a, **k)
         return cls

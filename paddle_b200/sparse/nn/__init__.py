@@ -83,11 +83,18 @@ class _SpConv3D(Layer):
 
 
 class Conv3D(_SpConv3D):
-    pass
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, padding_mode="zeros",
+                 weight_attr=None, bias_attr=None, data_format="NDHWC"):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, padding_mode, None, weight_attr, bias_attr, data_format)
 
 
 class SubmConv3D(_SpConv3D):
     _subm = True
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, padding_mode="zeros", key=None,
+                 weight_attr=None, bias_attr=None, data_format="NDHWC", backend=None):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, padding_mode, key, weight_attr, bias_attr, data_format)
+        self._backend = backend
 
 
 class MaxPool3D(Layer):
@@ -115,8 +122,15 @@ class _SpConv2D(Layer):
 
 
 class Conv2D(_SpConv2D):
-    pass
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, padding_mode="zeros",
+                 weight_attr=None, bias_attr=None, data_format="NHWC"):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, padding_mode, None, weight_attr, bias_attr, data_format)
 
 
 class SubmConv2D(_SpConv2D):
     _subm = True
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, padding_mode="zeros", key=None,
+                 weight_attr=None, bias_attr=None, data_format="NHWC", backend=None):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, padding_mode, key, weight_attr, bias_attr, data_format)
+        self._backend = backend

@@ -37,7 +37,23 @@ def embedding(input, size, is_sparse=False, is_distributed=False, padding_idx=No
     return F.embedding(input, w, padding_idx)
 
 
-sparse_embedding = embedding
+def sparse_embedding(input, size, padding_idx=None, is_test=False, entry=None, table_class="MemorySparseTable", param_attr=None, dtype="float32", slot=None):
+    """Embedding whose table lives on the parameter servers when the job runs in PS mode (rows are pulled in forward, gradients pushed
+    in backward: fleet/ps_mode.py:DistributedEmbedding); a local embedding otherwise. Parity: static/nn/common.py:sparse_embedding."""
+    from ...distributed.fleet import ps_mode
+
+    role = ps_mode.role()
+    if role is not None and not role.is_server:
+        name = getattr(param_attr, "name", None) or f"sparse_embedding_{size[0]}x{size[1]}"
+        key = ("ps_emb", name)
+        layer = _ps_embeddings.get(key)
+        if layer is None:
+            layer = _ps_embeddings[key] = ps_mode.DistributedEmbedding(name, int(size[1]))
+        return layer(input)
+    return embedding(input, size, is_sparse=True, padding_idx=padding_idx, param_attr=param_attr, dtype=dtype)
+
+
+_ps_embeddings = {}
 
 
 def _conv(n, transpose, input, num_filters, filter_size, stride=1, padding=0, dilation=1, groups=1, param_attr=None, bias_attr=None, act=None,

@@ -68,7 +68,47 @@ def run_check():
     print("PaddlePaddle-compatible paddle_b200 is installed successfully!")
 
 
-def flops(net, input_size, custom_ops=None, print_detail=False):
-    from ..hapi.summary import flops as f
+def flops(op_type, input_shapes, attrs=None):
+    """FLOPs of one operator from its input shapes. Parity: python/paddle/utils/flops.py:flops (per-op registry; unknown ops give 0).
+    The model-level counter is `paddle.flops(net, input_size)`."""
+    from functools import reduce
+    from operator import mul
 
-    return f(net, input_size, custom_ops, print_detail)
+    attrs = attrs or {}
+
+    def numel(shape):
+        return reduce(mul, shape, 1)
+
+    def first(key):
+        v = input_shapes.get(key)
+        return v[0] if v and isinstance(v[0], (list, tuple)) else v
+
+    t = op_type
+    if t in ("matmul", "matmul_v2"):
+        x, y = list(first("X")), list(first("Y"))
+        if attrs.get("transpose_X") or attrs.get("trans_x"):
+            x[-1], x[-2] = x[-2], x[-1]
+        if attrs.get("transpose_Y") or attrs.get("trans_y"):
+            y[-1], y[-2] = y[-2], y[-1]
+        batch = x[:-2] if len(x) >= len(y) else y[:-2]
+        return 2 * numel(batch) * x[-2] * x[-1] * y[-1]
+    if t in ("elementwise_add", "elementwise_sub", "elementwise_mul", "elementwise_div", "add", "subtract", "multiply", "divide"):
+        x, y = first("X"), first("Y")
+        return max(numel(x), numel(y))
+    if t in ("relu", "gelu", "silu", "sigmoid", "tanh", "dropout", "softmax"):
+        x = first("X")
+        return numel(x) * (3 if t == "softmax" else 1)
+    if t == "layer_norm":
+        x = first("X")
+        return numel(x) * (8 if attrs.get("epsilon") is not None else 7)
+    if t in ("conv2d", "depthwise_conv2d"):
+        x, w = first("Input"), first("Filter")
+        stride, pad, dil = attrs.get("strides", [1, 1]), attrs.get("paddings", [0, 0]), attrs.get("dilations", [1, 1])
+        ho = (x[2] + 2 * pad[0] - dil[0] * (w[2] - 1) - 1) // stride[0] + 1
+        wo = (x[3] + 2 * pad[1] - dil[1] * (w[3] - 1) - 1) // stride[1] + 1
+        return 2 * x[0] * w[0] * ho * wo * w[1] * w[2] * w[3]
+    if t in ("reshape2", "transpose2", "slice", "concat", "split", "unsqueeze2", "squeeze2", "c_embedding", "lookup_table_v2"):
+        return 0
+    return 0
+
+

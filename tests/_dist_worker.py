@@ -46,8 +46,11 @@ def case_collectives():
     assert [o["r"] for o in objs] == list(range(w))
     ins = [paddle.to_tensor([float(r * 10 + j)]) for j in range(w)]
     res = []
-    dist.alltoall(res, ins)
+    dist.alltoall(ins, res)
     close([x.item() for x in res], [j * 10 + r for j in range(w)])
+    res2 = []
+    dist.stream.alltoall(res2, ins)          # the stream variant takes the output first
+    close([x.item() for x in res2], [j * 10 + r for j in range(w)])
     g = dist.new_group(list(range(w)))
     x = paddle.to_tensor([1.0])
     dist.all_reduce(x, group=g)

@@ -317,3 +317,30 @@ def test_quasi_newton_minimizers_asp_module_groupwise_observer():
     w = paddle.to_tensor(np.arange(32, dtype="float32").reshape(8, 4) - 10)
     ob(w)
     assert ob.scales().shape == [2, 4] and float(ob.scales()[1, 3]) == 21.0 and ob.bit_length() == 4 and GroupWiseWeightObserver(4, 4) is not None
+
+
+def test_reference_signatures_spot_checks():
+    """Argument names / order that differ from a naive guess (found by an AST scan of the reference sources)."""
+    import inspect
+
+    import paddle_b200.distributed as dist
+
+    def names(f):
+        return list(inspect.signature(f).parameters)
+
+    assert names(dist.alltoall)[:2] == ["in_tensor_list", "out_tensor_list"] and names(dist.alltoall_single)[:2] == ["in_tensor", "out_tensor"]
+    assert names(dist.stream.alltoall)[:2] == ["out_tensor_or_tensor_list", "in_tensor_or_tensor_list"] and "use_calc_stream" in names(dist.stream.all_reduce)
+    assert names(dist.get_group) == ["id"] and names(dist.unshard_dtensor) == ["dist_tensor"]
+    assert names(paddle.nn.Conv2DTranspose.__init__)[7:9] == ["dilation", "groups"] and names(paddle.nn.Conv1DTranspose.__init__)[7:9] == ["groups", "dilation"]
+    assert names(paddle.nn.SimpleRNN.__init__)[7] == "activation" and "proj_size" in names(paddle.nn.LSTM.__init__) and "proj_size" not in names(paddle.nn.GRU.__init__)
+    assert names(paddle.nn.Embedding.__init__)[7] == "weight_attr" and names(paddle.nn.SpectralNorm.__init__)[4] == "eps"
+    assert names(paddle.round)[:2] == ["x", "decimals"] and names(paddle.t)[0] == "input" and names(paddle.seed) == ["seed"]
+    assert names(paddle.nn.functional.temporal_shift)[3:] == ["name", "data_format"]
+    I = paddle.incubate.nn.functional
+    assert names(I.fused_moe)[:4] == ["x", "gate_weight", "ffn1_weight", "ffn2_weight"] and names(I.fused_dot_product_attention)[:5] == ["query", "key", "value", "attn_mask", "dropout_p"]
+    assert paddle.utils.flops("matmul_v2", {"X": [[4, 8]], "Y": [[8, 16]]}, {}) == 2 * 4 * 8 * 16
+    assert paddle.utils.flops("conv2d", {"Input": [[1, 3, 8, 8]], "Filter": [[4, 3, 3, 3]]}, {"strides": [1, 1], "paddings": [1, 1], "dilations": [1, 1]}) == 2 * 4 * 8 * 8 * 27
+    x = paddle.to_tensor(np.array([-8, 8, -1], "int32"))
+    y = paddle.to_tensor(np.array([1, 2, 31], "int32"))
+    assert paddle.bitwise_right_shift(x, y, is_arithmetic=False).numpy().tolist() == [2147483644, 2, 1]
+    assert np.allclose(paddle.round(paddle.to_tensor([1.2345, -2.555]), decimals=2).numpy(), [1.23, -2.56], atol=1e-6)

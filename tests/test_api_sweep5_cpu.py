@@ -248,7 +248,10 @@ def test_distributed_single_process_names(tmp_path):
         D.reduce_scatter(rs, [x])
         D.reduce_scatter_tensor(rs, x)
         a2a = paddle.zeros([2], "float32")
-        D.alltoall_single(a2a, x)
+        D.alltoall_single(x, a2a)
+        D.stream.alltoall_single(a2a, x, use_calc_stream=True)
+        with pytest.raises(RuntimeError):
+            D.stream.all_reduce(x, sync_op=False, use_calc_stream=True)
         np.testing.assert_allclose(a2a.numpy(), x.numpy())
         objs = [{"a": 1}]
         D.broadcast_object_list(objs, 0)
