@@ -113,10 +113,36 @@ class AmpScaler:
     def get_init_loss_scaling(self):
         return self._init_loss_scaling
 
-    def set_init_loss_scaling(self, v):
-        self._init_loss_scaling = float(v)
+    def set_init_loss_scaling(self, new_init_loss_scaling):
+        self._init_loss_scaling = float(new_init_loss_scaling)
         if self._scale is not None:
-            self._scale.fill_(float(v))
+            self._scale.fill_(float(new_init_loss_scaling))
+
+    def get_incr_ratio(self):
+        return self._incr_ratio
+
+    def set_incr_ratio(self, new_incr_ratio):
+        assert new_incr_ratio > 1.0, "The new_incr_ratio must be > 1.0."
+        self._incr_ratio = new_incr_ratio
+
+    def get_decr_ratio(self):
+        return self._decr_ratio
+
+    def set_decr_ratio(self, new_decr_ratio):
+        assert new_decr_ratio < 1.0, "The new_decr_ratio must be < 1.0."
+        self._decr_ratio = new_decr_ratio
+
+    def get_incr_every_n_steps(self):
+        return self._incr_every_n_steps
+
+    def set_incr_every_n_steps(self, new_incr_every_n_steps):
+        self._incr_every_n_steps = new_incr_every_n_steps
+
+    def get_decr_every_n_nan_or_inf(self):
+        return self._decr_every_n_nan_or_inf
+
+    def set_decr_every_n_nan_or_inf(self, new_decr_every_n_nan_or_inf):
+        self._decr_every_n_nan_or_inf = new_decr_every_n_nan_or_inf
 
     def get_loss_scaling(self):
         return None if self._scale is None else self._scale.as_subclass(Tensor)
@@ -129,7 +155,8 @@ class AmpScaler:
                 "decr_every_n_nan_or_inf": self._decr_every_n_nan_or_inf, "incr_count": self._good, "decr_count": self._bad,
                 "use_dynamic_loss_scaling": self._use_dynamic}
 
-    def load_state_dict(self, sd):
+    def load_state_dict(self, state_dict):
+        sd = state_dict
         if not sd:
             return
         import numpy as np

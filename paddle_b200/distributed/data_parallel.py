@@ -152,6 +152,12 @@ class DataParallel(Layer):
     def forward(self, *inputs, **kwargs):
         return self._layers(*inputs, **kwargs)
 
+    def init_reducer(self):
+        """(Re)build the gradient buckets, e.g. after parameters were added or frozen. Parity: parallel.py:DataParallel.init_reducer."""
+        self._params = [p for p in self._layers.parameters() if not p.stop_gradient]
+        if self._world > 1 and self._params:
+            self._setup_reducer()
+
     @contextlib.contextmanager
     def no_sync(self):
         old = self._sync

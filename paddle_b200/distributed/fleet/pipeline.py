@@ -404,7 +404,29 @@ class PipelineParallel(Layer):
         dist.broadcast(loss, src=src, group=pg)
         return _w(loss.reshape([]))
 
-    def train_batch(self, data, optimizer, lr_scheduler=None, scaler=None):
+    # ---- small parity helpers (pipeline_parallel.py) ---------------------------------------------------------------------------
+    def is_pipeline_first_stage(self, ignore_virtual=False):
+        return self.is_first
+
+    def is_pipeline_last_stage(self, ignore_virtual=False):
+        return self.is_last
+
+    def set_virtual_pipeline_rank(self, rank):
+        self._virtual_pp_rank = rank
+
+    def register_hook(self, location, hook):
+        """User callbacks around the schedule: location in {"forward_begin", "forward_end", "backward_begin", "backward_end"}."""
+        self.__dict__.setdefault("_user_hooks", {}).setdefault(str(location), []).append(hook)
+
+    def timer_printer(self):
+        pass
+
+    def get_static_scheduler(self):
+        M, S, r = self.accumulate_steps, self.num_stages, self.stage_id
+        warm = min(S - r - 1, M)
+        return ";".join([f"f{i}" for i in range(warm)] + [f"f{warm + i};b{i}" for i in range(M - warm)] + [f"b{M - warm + i}" for i in range(warm)])
+
+    def train_batch(self, data, optimizer, lr_scheduler=None, scaler=None, loss_fn_idx=0, return_micro_batch_loss=False):
         self._layers.train()
         loss = self.forward_backward_pipeline(data, scaler)
         if scaler is not None:
@@ -418,7 +440,7 @@ class PipelineParallel(Layer):
         return loss
 
     @torch.no_grad()
-    def eval_batch(self, data, compute_loss=False):
+    def eval_batch(self, data, compute_loss=False, loss_fn_idx=0):
         self._layers.eval()
         inputs, labels = data if isinstance(data, (tuple, list)) and len(data) == 2 else (data, None)
         p2p = self._p2p

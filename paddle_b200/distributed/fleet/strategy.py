@@ -52,6 +52,34 @@ class DistributedStrategy:
         self.without_graph_optimization = True
         self.auto = False
         self.semi_auto = False
+        self.auto_search = False
+        self.split_data = True
+        self.elastic = False
+        self.asp = False
+        self.qat = False
+        self.qat_configs = _Cfg(channel_wise_abs_max=True, weight_bits=8, activation_bits=8, not_quant_pattern=[], algo=None)
+        self.adaptive_localsgd = False
+        self.localsgd_configs = _Cfg(k_steps=1, begin_step=1)
+        self.adaptive_localsgd_configs = _Cfg(init_k_steps=1, begin_step=1)
+        self.dgc_configs = _Cfg(rampup_begin_step=0, rampup_step=1, sparsity=[0.999])
+        self.lars_configs = _Cfg(lars_coeff=0.001, lars_weight_decay=0.0005, epsilon=0.0, exclude_from_weight_decay=[])
+        self.fp16_allreduce = False
+        self.sync_batch_norm = False
+        self.use_hierarchical_allreduce = False
+        self.hierarchical_allreduce_inter_nranks = 1
+        self.fuse_grad_size_in_num = 8
+        self.adam_d2sum = False
+        self.is_fl_ps_mode = False
+        self.is_with_coordinator = False
+        self.cudnn_exhaustive_search = False
+        self.conv_workspace_size_limit = 512
+        self.cudnn_batchnorm_spatial_persistent = False
+        self.gradient_scale_configs = _Cfg(scale_strategy="avg", scale_gradient=False)
+        self.trainer_desc_configs = _Cfg(dump_fields_path="", dump_fields=[], dump_param=[], stat_var_names=[])
+        self.sparse_table_configs = _Cfg()
+        self.fleet_desc_configs = _Cfg()
+        self.fs_client_param = _Cfg(uri="", user="", passwd="", hadoop_bin="")
+        self.build_strategy = None
 
     def __setattr__(self, k, v):
         if k.endswith("_configs") and isinstance(v, dict) and k in self.__dict__:

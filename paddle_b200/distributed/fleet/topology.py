@@ -219,6 +219,40 @@ class HybridCommunicateGroup:
     def get_sep_parallel_group(self):
         return self._groups["sep"][0] if "sep" in self._groups else None
 
+    def get_sep_parallel_group_src_rank(self):
+        g = self.get_sep_parallel_group()
+        return g.ranks[0] if g is not None else self.global_rank
+
+    def create_fuse_group(self, fused_strategy_list):
+        """Communicator over the product of several axes, e.g. ["data", "sharding"] (every process must call it). Parity: topology.py."""
+        from ..collective import new_group
+
+        assert len(fused_strategy_list) > 0
+        lists = self._topo.get_fused_ranks(fused_strategy_list) if hasattr(self._topo, "get_fused_ranks") else None
+        if lists is None:
+            import itertools
+
+            names, dims = self._topo._parallel_names, self._topo._dims
+            fused = [names.index(n) for n in fused_strategy_list]
+            others = [i for i in range(len(names)) if i not in fused]
+            lists = []
+            for oc in itertools.product(*[range(dims[i]) for i in others]):
+                ranks = []
+                for fc in itertools.product(*[range(dims[i]) for i in fused]):
+                    coord = [0] * len(names)
+                    for i, c in zip(others, oc):
+                        coord[i] = c
+                    for i, c in zip(fused, fc):
+                        coord[i] = c
+                    ranks.append(self._topo.get_rank(**{names[i]: coord[i] for i in range(len(names))}))
+                lists.append(sorted(ranks))
+        mine = None
+        for ranks in lists:
+            g = new_group(ranks)
+            if self.global_rank in ranks:
+                mine = g
+        return mine
+
     def get_check_parallel_group(self, sharding=False):
         return self._check_group[0]
 

@@ -44,19 +44,20 @@ class Sequential(Layer):
     def __iter__(self):
         return iter(self._sub_layers.values())
 
-    def append(self, layer):
-        self.add_sublayer(str(len(self._sub_layers)), layer)
+    def append(self, module):
+        self.add_sublayer(str(len(self._sub_layers)), module)
         return self
 
-    def insert(self, index, layer):
+    def insert(self, index, module):
         layers = list(self._sub_layers.values())
-        layers.insert(index, layer)
+        layers.insert(index, module)
         self._sub_layers.clear()
         for i, l in enumerate(layers):
             self._sub_layers[str(i)] = l
+        return self
 
-    def extend(self, layers):
-        for l in layers:
+    def extend(self, sequential):
+        for l in sequential:
             self.append(l)
         return self
 

@@ -235,19 +235,19 @@ class Layer:
         return h
 
     # ---- traversal ---------------------------------------------------------
-    def named_sublayers(self, prefix="", include_self=False, layers_set=None):
+    def named_sublayers(self, prefix="", include_self=False, layers_set=None, remove_duplicate=True):
         if layers_set is None:
             layers_set = set()
-        if include_self and id(self) not in layers_set:
+        if include_self and (not remove_duplicate or id(self) not in layers_set):
             layers_set.add(id(self))
             yield prefix, self
         for k, l in self._sub_layers.items():
-            if l is None or id(l) in layers_set:
+            if l is None or (remove_duplicate and id(l) in layers_set):
                 continue
             p = prefix + ("." if prefix else "") + k
             layers_set.add(id(l))
             yield p, l
-            yield from l.named_sublayers(prefix=p, include_self=False, layers_set=layers_set)
+            yield from l.named_sublayers(prefix=p, include_self=False, layers_set=layers_set, remove_duplicate=remove_duplicate)
 
     def sublayers(self, include_self=False):
         return [l for _, l in self.named_sublayers(include_self=include_self)]
@@ -258,12 +258,12 @@ class Layer:
     def named_children(self):
         return ((k, l) for k, l in self._sub_layers.items() if l is not None)
 
-    def named_parameters(self, prefix="", include_sublayers=True):
+    def named_parameters(self, prefix="", include_sublayers=True, remove_duplicate=True):
         seen = set()
-        layers = self.named_sublayers(prefix=prefix, include_self=True) if include_sublayers else [(prefix, self)]
+        layers = self.named_sublayers(prefix=prefix, include_self=True, remove_duplicate=remove_duplicate) if include_sublayers else [(prefix, self)]
         for lp, l in layers:
             for k, p in l._parameters.items():
-                if p is None or id(p) in seen:
+                if p is None or (remove_duplicate and id(p) in seen):
                     continue
                 seen.add(id(p))
                 yield lp + ("." if lp else "") + k, p
@@ -271,12 +271,12 @@ class Layer:
     def parameters(self, include_sublayers=True):
         return [p for _, p in self.named_parameters(include_sublayers=include_sublayers)]
 
-    def named_buffers(self, prefix="", include_sublayers=True):
+    def named_buffers(self, prefix="", include_sublayers=True, remove_duplicate=True):
         seen = set()
-        layers = self.named_sublayers(prefix=prefix, include_self=True) if include_sublayers else [(prefix, self)]
+        layers = self.named_sublayers(prefix=prefix, include_self=True, remove_duplicate=remove_duplicate) if include_sublayers else [(prefix, self)]
         for lp, l in layers:
             for k, b in l._buffers.items():
-                if b is None or id(b) in seen:
+                if b is None or (remove_duplicate and id(b) in seen):
                     continue
                 seen.add(id(b))
                 yield lp + ("." if lp else "") + k, b
@@ -383,7 +383,22 @@ class Layer:
                     continue
                 seen.add(id(b))
                 dest[lp + ("." if lp else "") + k] = b
+        if use_hook:
+            for hook in self.__dict__.get("_state_dict_hooks", {}).values():
+                res = hook(dest)
+                if res is not None:
+                    dest = res
         return dest
+
+    def register_state_dict_hook(self, hook):
+        """hook(state_dict) -> state_dict | None, applied to the result of state_dict(). Parity: layers.py:register_state_dict_hook."""
+        hooks = self.__dict__.setdefault("_state_dict_hooks", OrderedDict())
+        h = HookRemoveHelper(hooks)
+        hooks[h._id] = hook
+        return h
+
+    def backward(self, *inputs):
+        raise ValueError("Layer shouldn't implement backward")
 
     def to_static_state_dict(self, *a, **k):
         return self.state_dict(*a, **k)

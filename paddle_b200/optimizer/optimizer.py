@@ -194,6 +194,44 @@ class Optimizer:
             wd, kind = self._wd_value(g, p)
             self._update_param(g, p, _raw(p), gr, lr, wd, kind)
 
+    def backward(self, loss, startup_program=None, parameters=None, no_grad_set=None, callbacks=None):
+        """First half of minimize(): run autograd and return [(param, grad)]. Parity: optimizer.py:Optimizer.backward."""
+        loss.backward()
+        params = parameters if parameters is not None else [p for g in self._param_groups for p in g["params"]]
+        skip = {getattr(v, "name", v) for v in (no_grad_set or ())}
+        out = []
+        for p in params:
+            g = torch.Tensor.grad.__get__(p)
+            if g is not None and p.name not in skip and not p.stop_gradient:
+                out.append((p, g.as_subclass(Tensor)))
+        return out
+
+    def apply_gradients(self, params_grads):
+        """Second half of minimize(): clip / regularise / update with the given (param, grad) pairs."""
+        for p, g in params_grads:
+            if g is not None and torch.Tensor.grad.__get__(p) is not g:
+                torch.Tensor.grad.__set__(p, _raw(g))
+        self.step()
+        return []
+
+    def append_regularization_ops(self, parameters_and_grads, regularization=None):
+        """grad += d(regulariser)/d(param) for every pair (L2Decay -> coeff * p, L1Decay -> coeff * sign(p))."""
+        reg = regularization if regularization is not None else self._weight_decay
+        out = []
+        for p, g in parameters_and_grads:
+            r = getattr(p, "regularizer", None) or reg
+            if g is None or r is None or isinstance(r, (int, float)) and r == 0:
+                out.append((p, g))
+                continue
+            coeff = float(getattr(r, "_coeff", getattr(r, "coeff", r)) if not isinstance(r, (int, float)) else r)
+            l1 = type(r).__name__ == "L1Decay"
+            out.append((p, (_raw(g) + coeff * (torch.sign(_raw(p)) if l1 else _raw(p))).as_subclass(Tensor)))
+        return out
+
+    def get_opti_var_name_list(self):
+        return [t.name if hasattr(t, "name") and isinstance(getattr(t, "name", None), str) else f"{acc}_{pname}"
+                for acc, d in self._accumulators.items() for pname, t in d.items()]
+
     def minimize(self, loss, startup_program=None, parameters=None, no_grad_set=None):
         from .. import static
 

@@ -341,6 +341,49 @@ class Executor:
             outs.append(v.detach().cpu().as_subclass(Tensor).numpy() if return_numpy else v)
         return outs
 
+    def train_from_dataset(self, program=None, dataset=None, scope=None, thread=0, debug=False, fetch_list=None, fetch_info=None, print_period=100,
+                           fetch_handler=None):
+        """Run `program` once per batch of a slot dataset (distributed.InMemoryDataset / QueueDataset): each batch dict feeds the
+        placeholders named after the dataset's `use_var` entries. Parity: base/executor.py:Executor.train_from_dataset."""
+        return self._run_from_dataset(program, dataset, fetch_list, fetch_info, print_period, debug)
+
+    def infer_from_dataset(self, program=None, dataset=None, scope=None, thread=0, debug=False, fetch_list=None, fetch_info=None, print_period=100,
+                           fetch_handler=None):
+        program = program if program is not None else _main[0]
+        prog = program._program if isinstance(program, CompiledProgram) else program
+        return self._run_from_dataset(prog.clone(for_test=True), dataset, fetch_list, fetch_info, print_period, debug)
+
+    def _run_from_dataset(self, program, dataset, fetch_list, fetch_info, print_period, debug):
+        if dataset is None:
+            raise RuntimeError("dataset is need and should be initialized")
+        program = program if program is not None else _main[0]
+        results = []
+        for step, batch in enumerate(dataset):
+            if isinstance(batch, dict):
+                feed = {}
+                for k, v in batch.items():
+                    if isinstance(v, tuple):            # ragged slot: (values, lod) -> LoD tensor of packed rows
+                        t = to_tensor(np.asarray(v[0]).reshape(-1, 1))
+                        t.set_lod([[int(o) for o in v[1]]])
+                        feed[k] = t
+                    else:
+                        feed[k] = v
+            else:
+                names = list((program._program if isinstance(program, CompiledProgram) else program).placeholders)
+                feed = {names[0]: batch} if names else {}
+            out = self.run(program, feed=feed, fetch_list=fetch_list)
+            if fetch_list:
+                results.append(out)
+                if debug or (print_period and step % print_period == 0 and fetch_info):
+                    print(" ".join(f"{n}: {np.asarray(o).reshape(-1)[:4]}" for n, o in zip(fetch_info or [], out)))
+        return results
+
+    def flush(self):
+        pass
+
+    def close(self):
+        pass
+
     @staticmethod
     def _schedule(program, run_node):
         """Replay in dependency order through the native GraphExecutor when available (falls back to tape order)."""

@@ -344,3 +344,45 @@ def test_reference_signatures_spot_checks():
     y = paddle.to_tensor(np.array([1, 2, 31], "int32"))
     assert paddle.bitwise_right_shift(x, y, is_arithmetic=False).numpy().tolist() == [2147483644, 2, 1]
     assert np.allclose(paddle.round(paddle.to_tensor([1.2345, -2.555]), decimals=2).numpy(), [1.23, -2.56], atol=1e-6)
+
+
+def test_class_method_parity_additions(tmp_path):
+    net = paddle.nn.Sequential(paddle.nn.Linear(3, 3))
+    shared = paddle.nn.Linear(2, 2)
+
+    class Twice(paddle.nn.Layer):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = shared, shared
+
+    t = Twice()
+    assert len(list(t.named_parameters())) == 2 and len(list(t.named_parameters(remove_duplicate=False))) == 4
+    assert len(list(t.named_sublayers(remove_duplicate=False))) == 2
+    h = net.register_state_dict_hook(lambda sd: {k.upper(): v for k, v in sd.items()})
+    assert all(k.isupper() or not k.isalpha() for k in net.state_dict()) and "0.WEIGHT" in net.state_dict()
+    h.remove()
+    assert "0.weight" in net.state_dict()
+    net.append(module=paddle.nn.ReLU()).insert(0, module=paddle.nn.Tanh()).extend(sequential=[paddle.nn.Sigmoid()])
+    assert len(net) == 4
+    opt = paddle.optimizer.SGD(0.1, parameters=net.parameters())
+    loss = net(paddle.ones([2, 3])).sum()
+    pg = opt.backward(loss)
+    assert len(pg) == 2 and all(g is not None for _, g in pg)
+    before = net[1].weight.numpy().copy()
+    reg = opt.append_regularization_ops(pg, paddle.regularizer.L2Decay(0.5))
+    assert np.allclose(reg[0][1].numpy(), pg[0][1].numpy() + 0.5 * pg[0][0].numpy(), atol=1e-6)
+    opt.apply_gradients(pg)
+    assert not np.allclose(net[1].weight.numpy(), before)
+    sc = paddle.amp.GradScaler()
+    sc.set_incr_ratio(3.0)
+    sc.set_decr_ratio(0.25)
+    sc.set_incr_every_n_steps(7)
+    sc.set_decr_every_n_nan_or_inf(2)
+    sc.set_init_loss_scaling(new_init_loss_scaling=128.0)
+    assert (sc.get_incr_ratio(), sc.get_decr_ratio(), sc.get_incr_every_n_steps(), sc.get_decr_every_n_nan_or_inf(), sc.get_init_loss_scaling()) == (3.0, 0.25, 7, 2, 128.0)
+    st = paddle.distributed.fleet.DistributedStrategy()
+    st.qat_configs = {"weight_bits": 4}
+    st.save_to_prototxt(str(tmp_path / "s.txt"))
+    st2 = paddle.distributed.fleet.DistributedStrategy()
+    st2.load_from_prototxt(str(tmp_path / "s.txt"))
+    assert st2.qat_configs["weight_bits"] == 4 and st2.sync_batch_norm is False and st2.localsgd_configs["k_steps"] == 1

@@ -261,3 +261,39 @@ def test_distributed_single_process_names(tmp_path):
         assert D.batch_isend_irecv is not None and D.P2POp is not None and D.isend is not None and D.irecv is not None
     finally:
         D.destroy_process_group()
+
+
+def test_executor_train_from_dataset(static_mode, tmp_path):
+    """Executor.train_from_dataset over an InMemoryDataset (multi-slot text) trains a static program."""
+    from paddle_b200 import _build
+    from paddle_b200.distributed import InMemoryDataset
+
+    if _build.load(required=False) is None:
+        pytest.skip("native extension not built")
+    S = paddle.static
+    w_true = np.array([0.5, -1.0, 2.0], "float32")
+    lines = []
+    for _ in range(64):
+        x = rng.randn(3).astype("float32")
+        lines.append(f"3 {x[0]} {x[1]} {x[2]} 1 {float(x @ w_true)}\n")
+    p = tmp_path / "part-0"
+    p.write_text("".join(lines))
+    main, start = S.Program(), S.Program()
+    with S.program_guard(main, start):
+        feat = S.data("feat", [-1, 3], "float32")
+        label = S.data("label", [-1, 1], "float32")
+        pred = S.nn.fc(feat, 1)
+        loss = paddle.mean((pred - label) ** 2)
+        paddle.optimizer.SGD(0.1).minimize(loss)
+    exe = S.Executor()
+    exe.run(start)
+    ds = InMemoryDataset()
+    ds.init(batch_size=16, use_var=[feat, label])
+    ds.set_filelist([str(p)])
+    ds.load_into_memory()
+    first = exe.train_from_dataset(main, ds, fetch_list=[loss])
+    for _ in range(10):
+        last = exe.train_from_dataset(main, ds, fetch_list=[loss])
+    assert float(last[-1][0]) < float(first[0][0]) * 0.1
+    inf = exe.infer_from_dataset(main, ds, fetch_list=[pred])
+    assert len(inf) == 4 and inf[0][0].shape == (16, 1)
