@@ -1039,6 +1039,31 @@ def case_auto_engine():
     assert list(xb.shape)[0] == 4 * w or list(xb.shape)[0] == 4
 
 
+def case_recompute_hybrid_partition():
+    """recompute_hybrid with the kept inputs sharded over the mp group (and offload flag on): gradients equal the plain forward."""
+    s, hcg = setup(mp=2)
+    from paddle_b200.distributed.fleet import recompute_hybrid
+
+    paddle.seed(41)
+    net = nn.Sequential(nn.Linear(8, 16), nn.GELU(), nn.Dropout(0.2), nn.Linear(16, 8))
+    ref = nn.Sequential(nn.Linear(8, 16), nn.GELU(), nn.Dropout(0.2), nn.Linear(16, 8))
+    ref.set_state_dict(net.state_dict())
+    torch.manual_seed(6)
+    x = torch.randn(4, 8)
+    res = []
+    for m, hybrid in ((net, True), (ref, False)):
+        paddle.seed(99)
+        inp = x.clone().as_subclass(paddle.Tensor)
+        inp.stop_gradient = False
+        y = recompute_hybrid({"mp_group": hcg.get_model_parallel_group(), "offload": True, "partition": True}, m, inp) if hybrid else m(inp)
+        (y ** 2).sum().backward()
+        res.append((y.numpy(), inp.grad.numpy(), [p.grad.numpy() for p in m.parameters()]))
+    close(res[0][0], res[1][0], 1e-6)
+    close(res[0][1], res[1][1], 1e-5)
+    for a, b in zip(res[0][2], res[1][2]):
+        close(a, b, 1e-5)
+
+
 if __name__ == "__main__":
     case = sys.argv[1]
     if GPU:

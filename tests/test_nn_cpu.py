@@ -243,3 +243,39 @@ def test_containers_and_utils():
     assert any("weight_g" in n for n, _ in wn.named_parameters())
     sn = nn.utils.spectral_norm(nn.Linear(4, 4))
     assert sn(T(np.ones((1, 4), "float32"))).shape == [1, 4]
+
+
+def test_recompute_matches_plain_with_dropout_and_sequential():
+    """recompute / recompute_sequential: same loss and gradients as the plain forward, dropout masks replayed in the re-run."""
+    import numpy as np
+
+    import paddle_b200 as paddle
+    from paddle_b200.distributed.fleet import recompute, recompute_hybrid, recompute_sequential
+
+    def make():
+        paddle.seed(5)
+        return paddle.nn.Sequential(paddle.nn.Linear(8, 16), paddle.nn.GELU(), paddle.nn.Dropout(0.3), paddle.nn.Linear(16, 8), paddle.nn.Tanh(), paddle.nn.Linear(8, 4))
+
+    x = paddle.to_tensor(np.random.RandomState(0).randn(6, 8).astype("float32"))
+    results = []
+    for mode in ("plain", "recompute", "sequential", "hybrid_offload"):
+        net = make()
+        paddle.seed(77)                           # same dropout stream in every mode
+        inp = paddle.to_tensor(x.numpy())
+        inp.stop_gradient = False
+        if mode == "plain":
+            y = net(inp)
+        elif mode == "recompute":
+            y = recompute(net, inp)
+        elif mode == "sequential":
+            y = recompute_sequential({"segments": 2}, net, inp)
+        else:
+            y = recompute_hybrid({"mp_group": None, "offload": True, "partition": False}, net, inp)
+        loss = (y ** 2).sum()
+        loss.backward()
+        results.append((float(loss), inp.grad.numpy().copy(), [p.grad.numpy().copy() for p in net.parameters()]))
+    for loss, dx, grads in results[1:]:
+        assert abs(loss - results[0][0]) < 1e-5
+        np.testing.assert_allclose(dx, results[0][1], rtol=1e-5, atol=1e-6)
+        for a, b in zip(grads, results[0][2]):
+            np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6)
