@@ -158,24 +158,32 @@ class GroupShardedOptimizerStage2:
         if name in ("Adam", "AdamW"):
             b1, b2 = o._betas()
             st = slab["state"]
+            wd = float(o._weight_decay or 0.0) if o._decoupled else 0.0
+            if self.offload and p_sh.is_cuda:
+                # offload: fp32 master shard + moments live in pinned host memory and the update runs on the CPU; only the bf16 / fp16
+                # shard travels (gradient down, updated parameters up).  Parity: GroupShardedOptimizerStage2(offload=True).
+                if "m" not in st:
+                    st["m"] = torch.zeros(p_sh.shape, dtype=torch.float32).pin_memory()
+                    st["v"] = torch.zeros(p_sh.shape, dtype=torch.float32).pin_memory()
+                    slab["master"] = p_sh.float().cpu().pin_memory()
+                    st["g_host"] = torch.zeros(p_sh.shape, dtype=torch.float32).pin_memory()
+                st["g_host"].copy_(g_sh.float(), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                self._adam_math(slab["master"], st["g_host"], st, lr, wd, b1, b2, float(o._epsilon))
+                p_sh.copy_(slab["master"], non_blocking=True)
+                return
             if "m" not in st:
                 st["m"] = torch.zeros_like(p_sh, dtype=torch.float32)
                 st["v"] = torch.zeros_like(p_sh, dtype=torch.float32)
                 if p_sh.dtype != torch.float32:
                     slab["master"] = p_sh.float()
-            wd = float(o._weight_decay or 0.0) if o._decoupled else 0.0
             if p_sh.is_cuda:
                 from .._build import ext
 
                 ext().adamw_step(p_sh, g_sh.contiguous(), slab["master"], st["m"], st["v"], lr, b1, b2, float(o._epsilon), wd, self._step, None, 0.0, None, None)
             else:
                 pf = slab["master"] if slab["master"] is not None else p_sh
-                gf = g_sh.float()
-                pf.mul_(1 - lr * wd)
-                st["m"].mul_(b1).add_(gf, alpha=1 - b1)
-                st["v"].mul_(b2).addcmul_(gf, gf, value=1 - b2)
-                denom = (st["v"] / (1 - b2 ** self._step)).sqrt_().add_(o._epsilon)
-                pf.addcdiv_(st["m"], denom, value=-lr / (1 - b1 ** self._step))
+                self._adam_math(pf, g_sh.float(), st, lr, wd, b1, b2, float(o._epsilon))
                 if pf is not p_sh:
                     p_sh.copy_(pf)
         else:  # SGD / Momentum
@@ -191,6 +199,13 @@ class GroupShardedOptimizerStage2:
                 st["vel"].mul_(mom).add_(gf)
                 gf = st["vel"]
             p_sh.copy_(pf - lr * gf)
+
+    def _adam_math(self, pf, gf, st, lr, wd, b1, b2, eps):
+        pf.mul_(1 - lr * wd)
+        st["m"].mul_(b1).add_(gf, alpha=1 - b1)
+        st["v"].mul_(b2).addcmul_(gf, gf, value=1 - b2)
+        denom = (st["v"] / (1 - b2 ** self._step)).sqrt_().add_(eps)
+        pf.addcdiv_(st["m"], denom, value=-lr / (1 - b1 ** self._step))
 
     @torch.no_grad()
     def step(self):

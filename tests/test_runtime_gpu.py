@@ -88,3 +88,30 @@ def test_captured_train_step_matches_eager():
     for pa, pb in zip(net_a.parameters(), net_b.parameters()):
         np.testing.assert_allclose(pb.numpy(), pa.numpy(), rtol=2e-4, atol=2e-5)
     assert losses_a[-1] < losses_a[0]
+
+
+def test_sharded_optimizer_offload_matches_device_update():
+    """GroupShardedOptimizerStage2(offload=True): master weights + moments in pinned host memory, CPU update — same result as the
+    device-resident update (single rank: the shard is the whole slab)."""
+    import numpy as np
+
+    import paddle_b200 as paddle
+    from paddle_b200.distributed.sharding import GroupShardedOptimizerStage2
+
+    def run(offload):
+        paddle.seed(3)
+        net = paddle.nn.Sequential(paddle.nn.Linear(32, 64), paddle.nn.GELU(), paddle.nn.Linear(64, 8))
+        net.to("gpu")
+        inner = paddle.optimizer.AdamW(1e-2, parameters=net.parameters(), weight_decay=0.01)
+        opt = GroupShardedOptimizerStage2(params=net.parameters(), optim=inner, group=None, offload=offload)
+        rs = np.random.RandomState(0)
+        for _ in range(4):
+            x = paddle.to_tensor(rs.randn(16, 32).astype("float32")).cuda()
+            (net(x) ** 2).mean().backward()
+            opt.step()
+            opt.clear_grad()
+        return [p.numpy() for p in net.parameters()]
+
+    a, b = run(False), run(True)
+    for x, y in zip(a, b):
+        np.testing.assert_allclose(y, x, rtol=2e-5, atol=2e-6)
