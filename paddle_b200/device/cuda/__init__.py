@@ -70,11 +70,13 @@ def memory_reserved(device=None):
 
 
 def reset_max_memory_allocated(device=None):
-    torch.cuda.reset_peak_memory_stats()
+    if torch.cuda.is_available():
+        torch.cuda.reset_peak_memory_stats()
 
 
 def reset_max_memory_reserved(device=None):
-    torch.cuda.reset_peak_memory_stats()
+    if torch.cuda.is_available():
+        torch.cuda.reset_peak_memory_stats()
 
 
 def get_device_properties(device=None):
