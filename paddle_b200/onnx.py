@@ -1,27 +1,39 @@
 """paddle.onnx.export. Parity: python/paddle/onnx/export.py (delegates to paddle2onnx in the reference).
-Here the Layer is a torch-backed module, so export goes through torch.onnx on a thin nn.Module adapter."""
-import torch
+
+The layer is traced into a Program (`jit._trace_program`) and written by the self-contained ONNX writer (`onnx_writer.py`, hand-emitted
+protobuf, opset 17) — neither `onnx` nor `paddle2onnx` is required.  Ops without a converter raise NotImplementedError with the list of
+supported ops."""
+from . import onnx_writer
 
 
-def export(layer, path, input_spec=None, opset_version=9, **configs):
-    class _Adapter(torch.nn.Module):
-        def __init__(self, l):
-            super().__init__()
-            self._l = l
-            for i, p in enumerate(l.parameters()):
-                self.register_parameter(f"p{i}", torch.nn.Parameter(p.as_subclass(torch.Tensor), requires_grad=False))
-
-        def forward(self, *a):
-            out = self._l(*a)
-            return out.as_subclass(torch.Tensor) if isinstance(out, torch.Tensor) else out
-
+def export(layer, path, input_spec=None, opset_version=17, **configs):
     if not input_spec:
         raise ValueError("input_spec is required for onnx export")
-    from .tensor import Tensor
+    import torch
 
-    args = tuple(torch.zeros([1 if (s is None or s < 0) else s for s in spec.shape], dtype=spec.dtype).as_subclass(Tensor) if not isinstance(spec, torch.Tensor) else spec for spec in input_spec)
+    from .jit import _trace_program
+    from .static import InputSpec
+
+    specs = []
+    for i, spec in enumerate(input_spec):
+        if isinstance(spec, InputSpec):
+            specs.append(([1 if (d is None or d < 0) else int(d) for d in spec.shape], str(spec.dtype), spec.name or f"x{i}"))
+        elif isinstance(spec, torch.Tensor):
+            specs.append((list(torch.Tensor.size(spec)), str(spec.dtype), f"x{i}"))
+        else:
+            raise TypeError("input_spec entries must be InputSpec or Tensor")
+    was_training = getattr(layer, "training", False)
     layer.eval()
     try:
-        torch.onnx.export(_Adapter(layer), args, path + ".onnx", opset_version=max(opset_version, 13))
-    except Exception as e:  # onnx package is not part of this image
-        raise RuntimeError(f"onnx export unavailable in this environment: {e}") from e
+        blob = _trace_program(layer, specs)
+    finally:
+        if was_training:
+            layer.train()
+    out = path if path.endswith(".onnx") else path + ".onnx"
+    import os
+
+    d = os.path.dirname(out)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    onnx_writer.export_program(blob, out, opset_version=max(int(opset_version), 17))
+    return out
