@@ -92,11 +92,6 @@ _reexport("nn.layer.transformer", "paddle.nn.layer.transformer", ["nn.transforme
 _reexport("nn.layer.container", "paddle.nn.layer.container", ["nn"], ["Sequential", "LayerList", "LayerDict", "ParameterList", "ParameterDict"])
 _reexport("text.datasets", "paddle.text.datasets", ["text"], ["Conll05st", "Imdb", "Imikolov", "Movielens", "UCIHousing", "WMT14", "WMT16"])
 _reexport("text.viterbi_decode", "paddle.text.viterbi_decode", ["text"], ["ViterbiDecoder", "viterbi_decode"])
-_reexport("static.amp", "paddle.static.amp", ["amp"], ["decorate", "auto_cast", "GradScaler"],
-          extra=lambda: {"AutoMixedPrecisionLists": importlib.import_module(_PKG + ".amp").AutoMixedPrecisionLists
-                         if hasattr(importlib.import_module(_PKG + ".amp"), "AutoMixedPrecisionLists") else _amp_lists(),
-                         "CustomOpLists": _amp_lists(), "fp16_guard": importlib.import_module(_PKG + ".amp.auto_cast").fp32_guard,
-                         "bf16": _mod(_PKG + ".static.amp.bf16", "paddle.static.amp.bf16", AutoMixedPrecisionListsBF16=_amp_lists())})
 _reexport("static.quantization", "paddle.static.quantization", ["quantization"])
 _reexport("static.io", "paddle.static.io", ["static"], ["save", "load", "save_inference_model", "load_inference_model", "serialize_program", "deserialize_program",
                                                       "serialize_persistables", "deserialize_persistables", "save_to_file", "load_from_file", "normalize_program",
@@ -118,19 +113,6 @@ _reexport("base.executor", "paddle.base.executor", ["static"], ["Executor", "glo
 _reexport("base.data_feeder", "paddle.base.data_feeder", ["framework.dtype"], ["convert_dtype"])
 _reexport("base.layer_helper", "paddle.base.layer_helper", ["nn.layer"], ["_make_parameter"])
 _reexport("framework.random", "paddle.framework.random", ["framework.random", ""], ["seed", "get_rng_state", "set_rng_state", "get_cuda_rng_state", "set_cuda_rng_state"])
-
-
-def _amp_lists():
-    class AutoMixedPrecisionLists:
-        """White / black op lists of static-graph AMP. Parity: python/paddle/static/amp/fp16_lists.py."""
-
-        def __init__(self, custom_white_list=None, custom_black_list=None, custom_black_varnames=None, dtype="float16"):
-            self.white_list, self.black_list = set(custom_white_list or ()), set(custom_black_list or ())
-            self.black_varnames, self.dtype = set(custom_black_varnames or ()), dtype
-            both = self.white_list & self.black_list
-            if both:
-                raise ValueError(f"ops in both the custom white and black list: {sorted(both)}")
-    return AutoMixedPrecisionLists
 
 
 # ---- distributed paths ------------------------------------------------------------------------------------------------------------

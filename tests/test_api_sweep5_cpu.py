@@ -297,3 +297,28 @@ def test_executor_train_from_dataset(static_mode, tmp_path):
     assert float(last[-1][0]) < float(first[0][0]) * 0.1
     inf = exe.infer_from_dataset(main, ds, fetch_list=[pred])
     assert len(inf) == 4 and inf[0][0].shape == (16, 1)
+
+
+def test_static_amp_decorate(static_mode):
+    S = paddle.static
+    import paddle_b200.static.amp as samp
+
+    main, start = S.Program(), S.Program()
+    with S.program_guard(main, start):
+        x = S.data("x", [8, 4], "float32")
+        y = S.data("y", [8, 1], "float32")
+        pred = S.nn.fc(x, 1)
+        loss = paddle.mean((pred - y) ** 2)
+        opt = samp.decorate(paddle.optimizer.SGD(0.1), samp.AutoMixedPrecisionLists(custom_black_list=["mean"]), dtype="bfloat16", level="O1")
+        opt.minimize(loss)
+    assert main._dist_attrs["amp"]["dtype"] == "bfloat16" and main._dist_attrs["amp"]["wrapped"] >= 1
+    exe = S.Executor()
+    exe.run(start)
+    xs, ws = rng.randn(8, 4).astype("float32"), np.array([[1.0], [-2.0], [0.5], [0.0]], "float32")
+    first = exe.run(main, feed={"x": xs, "y": xs @ ws}, fetch_list=[loss])[0]
+    for _ in range(40):
+        last = exe.run(main, feed={"x": xs, "y": xs @ ws}, fetch_list=[loss])[0]
+    assert float(last) < float(first) * 0.3
+    with pytest.raises(ValueError):
+        samp.AutoMixedPrecisionLists(custom_white_list=["matmul"], custom_black_list=["matmul"])
+    assert samp.bf16.AutoMixedPrecisionListsBF16 is samp.AutoMixedPrecisionLists
