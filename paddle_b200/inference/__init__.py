@@ -127,6 +127,189 @@ class Config:
     def summary(self):
         return f"Config(prefix={self._prefix}, gpu={self._use_gpu}, precision={self._precision.name})"
 
+    # ---- optimisation pipeline switches.  The reference drives an IR pass list + TensorRT / oneDNN sub-graph engines; here the saved
+    # model runs through the hand-written kernels and CUDA-graph replay, so these calls record the request (visible in `summary()` /
+    # `pass_builder().all_passes()`), and the ones that map to something real act on it (precision, cuda graph, memory pool, streams).
+    _PASSES = ["constant_folding", "common_subexpression_elimination", "fuse_gemm_epilogue", "dead_code_elimination"]
+
+    def _opt(self):
+        return self.__dict__.setdefault("_options", {"passes": list(self._PASSES)})
+
+    def pass_builder(self):
+        cfg = self
+
+        class _PassBuilder:
+            def all_passes(self):
+                return list(cfg._opt()["passes"])
+
+            def append_pass(self, name):
+                cfg._opt()["passes"].append(name)
+
+            def insert_pass(self, idx, name):
+                cfg._opt()["passes"].insert(idx, name)
+
+            def delete_pass(self, name):
+                cfg.delete_pass(name)
+
+            def set_passes(self, passes):
+                cfg._opt()["passes"] = list(passes)
+
+            def turn_on_debug(self):
+                cfg._opt()["ir_debug"] = True
+
+        return _PassBuilder()
+
+    def delete_pass(self, name):
+        p = self._opt()["passes"]
+        if name in p:
+            p.remove(name)
+
+    def enable_custom_passes(self, passes, custom_pass_only=False):
+        self._opt()["passes"] = (list(passes) if custom_pass_only else self._opt()["passes"] + list(passes))
+
+    def switch_ir_debug(self, x=True, passes=None):
+        self._opt()["ir_debug"] = bool(x)
+
+    def set_optimization_level(self, level):
+        self._opt()["opt_level"] = int(level)
+
+    def set_optim_cache_dir(self, d):
+        self._opt()["optim_cache_dir"] = d
+
+    def enable_save_optim_model(self, flag=True):
+        self._opt()["save_optim_model"] = bool(flag)
+
+    def use_optimized_model(self, flag=True):
+        self._opt()["use_optimized_model"] = bool(flag)
+
+    def enable_new_executor(self, x=True):
+        self._opt()["new_executor"] = bool(x)
+
+    def enable_new_ir(self, x=True):
+        self._opt()["new_ir"] = bool(x)
+
+    def new_ir_enabled(self):
+        return self._opt().get("new_ir", True)
+
+    def enable_profile(self):
+        self._opt()["profile"] = True
+
+    def enable_low_precision_io(self, x=True):
+        self._opt()["low_precision_io"] = bool(x)
+
+    def exp_enable_mixed_precision_ops(self, ops):
+        self._opt().setdefault("mixed_white", set()).update(ops)
+
+    def exp_disable_mixed_precision_ops(self, ops):
+        self._opt().setdefault("mixed_black", set()).update(ops)
+
+    def exp_enable_use_cutlass(self):
+        self._opt()["cutlass"] = True
+
+    def enable_cinn(self):
+        self._opt()["cinn"] = True
+
+    def memory_pool_init_size_mb(self):
+        return self._opt().get("pool_mb", 100)
+
+    def fraction_of_gpu_memory_for_pool(self):
+        if not torch.cuda.is_available():
+            return 0.0
+        return self.memory_pool_init_size_mb() * (1 << 20) / torch.cuda.get_device_properties(self._gpu_id).total_memory
+
+    def glog_info_disabled(self):
+        return not self._glog
+
+    def disable_mkldnn(self):
+        self._opt()["mkldnn"] = False
+
+    def mkldnn_enabled(self):
+        return False
+
+    def set_mkldnn_cache_capacity(self, n):
+        pass
+
+    def enable_mkldnn_bfloat16(self):
+        self._precision = PrecisionType.Bfloat16
+
+    def set_bfloat16_op(self, ops):
+        self.exp_enable_mixed_precision_ops(ops)
+
+    def set_model_buffer(self, prog_buffer, prog_size, params_buffer, params_size):
+        """Model from memory: the two buffers are spooled to a private temp prefix and loaded from there."""
+        import tempfile
+
+        d = tempfile.mkdtemp(prefix="paddle_b200_infer_")
+        with open(os.path.join(d, "m.pdmodel"), "wb") as f:
+            f.write(bytes(prog_buffer)[:prog_size])
+        with open(os.path.join(d, "m.pdiparams"), "wb") as f:
+            f.write(bytes(params_buffer)[:params_size])
+        self._prefix = os.path.join(d, "m")
+        self._opt()["from_memory"] = True
+
+    def model_from_memory(self):
+        return self._opt().get("from_memory", False)
+
+    def set_exec_stream(self, stream):
+        self._opt()["exec_stream"] = stream
+
+    def enable_tuned_tensorrt_dynamic_shape(self, path=None, allow_build_at_runtime=True):
+        self._opt()["shape_range_info_path"] = path
+
+    def tuned_tensorrt_dynamic_shape(self):
+        return "shape_range_info_path" in self._opt()
+
+    def collect_shape_range_info(self, path):
+        self._opt()["collect_shape_range_info"] = path
+
+    def shape_range_info_path(self):
+        return self._opt().get("collect_shape_range_info", "")
+
+    def shape_range_info_collected(self):
+        return "collect_shape_range_info" in self._opt()
+
+    def tensorrt_dynamic_shape_enabled(self):
+        return False
+
+    def tensorrt_precision_mode(self):
+        return self._precision
+
+    def enable_tensorrt_memory_optim(self, *a, **k):
+        pass
+
+    def enable_tensorrt_dla(self, *a, **k):
+        pass
+
+    def tensorrt_dla_enabled(self):
+        return False
+
+    def use_xpu(self):
+        return False
+
+    def enable_xpu(self, *a, **k):
+        raise RuntimeError("XPU is not supported by paddle_b200 (sm_100a only)")
+
+    def enable_custom_device(self, device_type, device_id=0, precision_mode=PrecisionType.Float32):
+        raise RuntimeError(f"custom device '{device_type}' is not supported by paddle_b200 (sm_100a only)")
+
+    def enable_onnxruntime(self):
+        raise RuntimeError("onnxruntime is not part of this build; export with paddle.onnx.export and serve it externally")
+
+    def onnxruntime_enabled(self):
+        return False
+
+    def disable_onnxruntime(self):
+        pass
+
+    def use_feed_fetch_ops_enabled(self):
+        return False
+
+    def specify_input_name(self):
+        return True
+
+    def to_native_config(self):
+        return {"prefix": self._prefix, "use_gpu": self._use_gpu, "device": self._gpu_id, "precision": self._precision.name, **{k: v for k, v in self._opt().items()}}
+
 
 class _Handle:
     """Input/output tensor handle (paddle_infer.Tensor)."""
@@ -156,10 +339,21 @@ class _Handle:
         return None if self._t is None else self._t.dtype
 
     def lod(self):
-        return []
+        return self._t.lod() if (self._t is not None and hasattr(self._t, "lod")) else getattr(self, "_lod", [])
 
     def set_lod(self, lod):
-        pass
+        self._lod = [list(l) for l in lod]
+        if self._t is not None and hasattr(self._t, "set_lod"):
+            self._t.set_lod(lod)
+
+    def share_external_data_by_ptr_name(self, *a, **k):
+        raise RuntimeError("raw pointer sharing is not exposed; use share_external_data(tensor)")
+
+    def as_ndarray(self):
+        return self.copy_to_cpu()
+
+    def tolist(self):
+        return self.copy_to_cpu().tolist()
 
 
 class Predictor:
@@ -203,6 +397,9 @@ class Predictor:
         else:
             args = [h._t for h in self._inputs.values() if h._t is not None]
         p0 = next(iter(getattr(self._layer, "_inner", self._layer).parameters()), None)
+        for hook in self.__dict__.get("_in_hooks", []):
+            for n, a in zip(self._inputs, args):
+                hook(n, a)
         args = [a.to(self._dev) for a in args]
         if p0 is not None and p0.dtype in (torch.float16, torch.bfloat16):
             args = [a.to(p0.dtype) if a.is_floating_point() else a for a in args]
@@ -210,10 +407,26 @@ class Predictor:
         outs = list(out) if isinstance(out, (list, tuple)) else [out]
         for i, o in enumerate(outs):
             self.get_output_handle(f"out{i}")._t = o
+            for hook in self.__dict__.get("_out_hooks", []):
+                hook(f"out{i}", o)
         return outs if inputs is not None else True
 
-    def clone(self):
+    def clone(self, stream=None):
         return Predictor(self._config)
+
+    def zero_copy_run(self):
+        return self.run()
+
+    def register_input_hook(self, hook):
+        """hook(name, tensor) before every run. Parity: analysis_predictor RegisterInputHook."""
+        self.__dict__.setdefault("_in_hooks", []).append(hook)
+
+    def register_output_hook(self, hook):
+        self.__dict__.setdefault("_out_hooks", []).append(hook)
+
+    def get_serialized_program(self):
+        with open(self._config._prefix + ".pdmodel", "rb") as f:
+            return f.read()
 
     def clear_intermediate_tensor(self):
         pass

@@ -139,3 +139,51 @@ def test_audio_features():
     assert paddle.audio.features.MFCC(sr=8000, n_mfcc=13, n_fft=256, hop_length=128, n_mels=20)(sig).shape[1] == 13
     w = paddle.audio.functional.get_window("hann", 16)
     assert w.shape == [16] and abs(float(w[0])) < 1e-6
+
+
+def test_inference_config_switches_hooks_and_memory_model(tmp_path):
+    import numpy as np
+
+    import paddle_b200 as paddle
+    from paddle_b200 import inference as I
+
+    paddle.seed(0)
+    net = paddle.nn.Sequential(paddle.nn.Linear(4, 8), paddle.nn.ReLU(), paddle.nn.Linear(8, 2))
+    prefix = str(tmp_path / "m")
+    paddle.jit.save(net, prefix, input_spec=[paddle.static.InputSpec([None, 4], "float32", "x")])
+    cfg = I.Config(prefix + ".pdmodel", prefix + ".pdiparams")
+    pb = cfg.pass_builder()
+    n0 = len(pb.all_passes())
+    pb.append_pass("my_pass")
+    cfg.delete_pass("constant_folding")
+    cfg.switch_ir_debug(True)
+    cfg.set_optimization_level(2)
+    cfg.exp_disable_mixed_precision_ops({"softmax"})
+    cfg.enable_low_precision_io(False)
+    cfg.collect_shape_range_info(str(tmp_path / "shape.txt"))
+    assert len(pb.all_passes()) == n0 and "my_pass" in pb.all_passes() and cfg.shape_range_info_collected() and not cfg.mkldnn_enabled()
+    assert cfg.to_native_config()["opt_level"] == 2 and cfg.glog_info_disabled() is False and cfg.new_ir_enabled()
+    import pytest
+
+    with pytest.raises(RuntimeError):
+        cfg.enable_xpu()
+    pred = I.create_predictor(cfg)
+    seen = []
+    pred.register_input_hook(lambda name, t: seen.append(("in", name)))
+    pred.register_output_hook(lambda name, t: seen.append(("out", name)))
+    x = np.random.RandomState(0).randn(3, 4).astype("float32")
+    h = pred.get_input_handle(pred.get_input_names()[0])
+    h.copy_from_cpu(x)
+    assert pred.zero_copy_run() and ("in", "x") in seen and ("out", "out0") in seen
+    out = pred.get_output_handle(pred.get_output_names()[0])
+    np.testing.assert_allclose(out.as_ndarray(), net(paddle.to_tensor(x)).numpy(), rtol=1e-5, atol=1e-6)
+    assert out.tolist() == out.copy_to_cpu().tolist() and len(pred.get_serialized_program()) > 0
+    # model from memory
+    cfg2 = I.Config()
+    pm, pp = open(prefix + ".pdmodel", "rb").read(), open(prefix + ".pdiparams", "rb").read()
+    cfg2.set_model_buffer(pm, len(pm), pp, len(pp))
+    assert cfg2.model_from_memory()
+    outs = I.create_predictor(cfg2).run([x])
+    np.testing.assert_allclose(outs[0].numpy(), net(paddle.to_tensor(x)).numpy(), rtol=1e-5, atol=1e-6)
+    pool = I.PredictorPool(cfg, 2)
+    assert pool.retrieve(1) is not pool.retrieve(0)
