@@ -56,7 +56,7 @@ class LocalLayer(Layer):
         outs = [outs] if single else list(outs)
         for i, (mesh, placements) in enumerate(self.out_dist_attrs[:len(outs)]):
             outs[i] = _api.dtensor_from_local(outs[i], mesh, placements)
-        return outs[0] if single else type(outs)(outs) if not isinstance(outs, list) else outs
+        return outs[0] if single else outs
 
 
 def to_distributed(model, optimizer, dataloader, device_num=None, node_num=1, config=None):

@@ -135,9 +135,8 @@ class _Ctx:
 
 def _binary(op):
     def f(c, a, k):
-        x, y = a[0], a[1]
-        other = torch.float32 if not isinstance(y, (int, np.integer)) or True else torch.int64
-        return c.g.node(op, [c.val(x, torch.float32), c.val(y, other)])
+        # python scalars become float32 constants (the recorded graphs are floating point; integer arithmetic keeps tensors on both sides)
+        return c.g.node(op, [c.val(a[0], torch.float32), c.val(a[1], torch.float32)])
     return f
 
 

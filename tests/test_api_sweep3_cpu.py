@@ -211,14 +211,15 @@ def test_top_level_leftovers_vs_numpy():
     x = t(np.array([1.0]))
     close(paddle.increment(x, 2.0), [3.0])
     assert paddle.from_numpy(np.ones(3)).shape == [3] and paddle.create_tensor("float32") is not None
-    assert paddle.double is not None or True
+    assert paddle.double is not None
     paddle.seed(1)
     assert paddle.rand_like(t(A)).shape == [3, 4] and paddle.randint_like(t(I), 0, 5).numpy().max() < 5
     assert paddle.standard_normal([1000]).numpy().std() > 0.8 and (paddle.standard_gamma(t(np.full(1000, 2.0))).numpy() > 0).all()
     assert abs(float(paddle.binomial(t(np.full(2000, 10)), t(np.full(2000, 0.3))).numpy().mean()) - 3) < 0.3
     assert (paddle.log_normal(shape=[100]).numpy() > 0).all()
-    ids, scores = paddle.top_p_sampling(t(np.array([[0.9, 0.05, 0.05]], "float32")), t(np.array([0.5], "float32")))[:2]
-    assert True
+    picked = paddle.top_p_sampling(t(np.array([[0.9, 0.05, 0.05]], "float32")), t(np.array([0.5], "float32")))
+    vals = [np.asarray(v.numpy()).reshape(-1) for v in picked[:2]]
+    assert any(int(v[0]) == 0 for v in vals if v.dtype.kind in "iu")     # nucleus of mass 0.5 only contains token 0
 
 
 def test_state_switches_and_places():

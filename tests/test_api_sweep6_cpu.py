@@ -275,7 +275,7 @@ def test_callbacks_device_version_misc(tmp_path):
     assert issubclass(paddle.regularizer.L2Decay, paddle.regularizer.WeightDecayRegularizer)
     from paddle_b200.distributed import fleet
 
-    assert fleet.is_worker() and fleet.server_index() == -1 and fleet.server_endpoints() == [] and fleet.get_strategy() is None or True
+    assert fleet.is_worker() and fleet.server_index() == -1 and fleet.server_endpoints() == []
     assert fleet.PaddleCloudRoleMaker(is_collective=True)._is_collective and fleet.UserDefinedRoleMaker is not None and fleet.Fleet().util is not None
     hub_dir = tmp_path / "hubrepo"
     hub_dir.mkdir()
