@@ -30,8 +30,28 @@ class Model:
         self._amp_level = "O0"
         self.stop_training = False
         self._save_dir = None
+        self._nranks, self._rank, self._ddp = 1, 0, None
+
+    def _init_distributed(self):
+        """Launched with several trainers (paddle.distributed.launch / spawn): train through DataParallel, shard the data with a
+        DistributedBatchSampler, gather evaluation outputs. Parity: hapi/model.py (DynamicGraphAdapter with ParallelEnv().nranks > 1)."""
+        import os as _os
+
+        from ..distributed import env as _env
+
+        world = int(_os.environ.get("PADDLE_TRAINERS_NUM", _os.environ.get("WORLD_SIZE", "1")))
+        if world <= 1 and not (_env.is_initialized() and _env.get_world_size() > 1):
+            return
+        if not _env.is_initialized():
+            _env.init_parallel_env()
+        self._nranks, self._rank = _env.get_world_size(), _env.get_rank()
+        if self._nranks > 1 and self._ddp is None:
+            from ..distributed.data_parallel import DataParallel
+
+            self._ddp = DataParallel(self.network)
 
     def prepare(self, optimizer=None, loss=None, metrics=None, amp_configs=None):
+        self._init_distributed()
         self._optimizer, self._loss = optimizer, loss
         self._metrics = _to_list(metrics)
         for m in self._metrics:
@@ -55,12 +75,27 @@ class Model:
         return batch[:n_in], batch[n_in:]
 
     def _forward(self, inputs):
+        net = self._ddp if (self._ddp is not None and self.network.training) else self.network
         if self._amp_level != "O0":
             from .. import amp
 
             with amp.auto_cast(level=self._amp_level, dtype=self._amp_dtype):
-                return self.network(*inputs)
-        return self.network(*inputs)
+                return net(*inputs)
+        return net(*inputs)
+
+    def _gather(self, tensors):
+        """Evaluation under several trainers: metrics see every rank's outputs (equal batch shapes per rank)."""
+        if self._nranks <= 1:
+            return tensors
+        import torch.distributed as dist
+
+        out = []
+        for t in tensors:
+            raw = t.as_subclass(torch.Tensor).contiguous()
+            parts = [torch.empty_like(raw) for _ in range(self._nranks)]
+            dist.all_gather(parts, raw)
+            out.append(torch.cat(parts, 0).as_subclass(type(t)))
+        return out
 
     def train_batch(self, inputs, labels=None, update=True):
         self.network.train()
@@ -95,6 +130,8 @@ class Model:
         outs = _to_list(self._forward(inputs))
         losses = _to_list(self._loss(*(outs + labels))) if self._loss is not None else []
         metrics = []
+        if self._metrics and self._nranks > 1:
+            outs, labels = self._gather(outs), self._gather(labels)
         for m in self._metrics:
             metrics.append(m.update(*_to_list(m.compute(*(outs + labels)))))
         lv = [float(l.item()) for l in losses]
@@ -109,6 +146,11 @@ class Model:
         if data is None or isinstance(data, DataLoader):
             return data
         if isinstance(data, Dataset):
+            if self._nranks > 1:
+                from ..io import DistributedBatchSampler
+
+                bs = DistributedBatchSampler(data, batch_size=batch_size, num_replicas=self._nranks, rank=self._rank, shuffle=shuffle, drop_last=drop_last)
+                return DataLoader(data, batch_sampler=bs, num_workers=num_workers)
             return DataLoader(data, batch_size=batch_size, shuffle=shuffle, num_workers=num_workers, drop_last=drop_last)
         return data
 
@@ -210,6 +252,8 @@ class Model:
         return res
 
     def save(self, path, training=True):
+        if self._rank != 0:       # one writer per job
+            return
         d = os.path.dirname(path)
         if d:
             os.makedirs(d, exist_ok=True)

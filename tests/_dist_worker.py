@@ -1064,6 +1064,52 @@ def case_recompute_hybrid_partition():
         close(a, b, 1e-5)
 
 
+def case_hapi_fit():
+    """paddle.Model.fit under 2 trainers (DataParallel + DistributedBatchSampler) == single-process fit on the global batches;
+    evaluate() gathers every rank's outputs for the metric."""
+    dist.init_parallel_env()
+    r, w = dist.get_rank(), dist.get_world_size()
+
+    class DS(paddle.io.Dataset):
+        def __init__(self, n):
+            rs = np.random.RandomState(3)
+            self.x = rs.randn(n, 5).astype("float32")
+            self.y = (self.x.sum(1) > 0).astype("int64")
+
+        def __len__(self):
+            return len(self.x)
+
+        def __getitem__(self, i):
+            return self.x[i], self.y[i]
+
+    ds = DS(16)
+    paddle.seed(29)
+    net = nn.Sequential(nn.Linear(5, 8), nn.ReLU(), nn.Linear(8, 2))
+    ref = nn.Sequential(nn.Linear(5, 8), nn.ReLU(), nn.Linear(8, 2))
+    ref.set_state_dict(net.state_dict())
+    model = paddle.Model(net)
+    model.prepare(paddle.optimizer.SGD(0.2, parameters=net.parameters()), nn.CrossEntropyLoss(), paddle.metric.Accuracy())
+    model.fit(ds, batch_size=4, epochs=2, shuffle=False, verbose=0)
+    ropt = paddle.optimizer.SGD(0.2, parameters=ref.parameters())
+    ce = nn.CrossEntropyLoss()
+    for _ in range(2):
+        for lo in (0, 8):       # per step the two ranks consume samples lo..lo+8 (4 each, dealt round-robin)
+            x, y = paddle.to_tensor(ds.x[lo:lo + 8]), paddle.to_tensor(ds.y[lo:lo + 8])
+            ce(ref(x), y).backward()
+            ropt.step()
+            ropt.clear_grad()
+    for (k, a), (_, b) in zip(net.state_dict().items(), ref.state_dict().items()):
+        close(a.numpy(), b.numpy(), 1e-4)
+    res = model.evaluate(ds, batch_size=4, verbose=0)
+    with paddle.no_grad():
+        acc = float((ref(paddle.to_tensor(ds.x)).argmax(-1).numpy() == ds.y).mean())
+    close(res["acc"], acc, 1e-6)
+    tmp = os.environ.get("B200_TEST_TMP", "/tmp")
+    model.save(os.path.join(tmp, "hapi", "ck"))
+    dist.barrier()
+    assert os.path.exists(os.path.join(tmp, "hapi", "ck.pdparams"))
+
+
 if __name__ == "__main__":
     case = sys.argv[1]
     if GPU:
