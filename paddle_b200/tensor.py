@@ -170,6 +170,69 @@ class Tensor(torch.Tensor):
             return t.view(torch.uint8).numpy()
         return t.numpy()
 
+    # ---- indexing: negative slice steps (numpy / paddle semantics; torch itself rejects them) ----------------------------------
+    @staticmethod
+    def _has_neg_step(idx):
+        if type(idx) is slice:
+            return idx.step is not None and idx.step < 0
+        if type(idx) is tuple:
+            for i in idx:
+                if type(i) is slice and i.step is not None and i.step < 0:
+                    return True
+        return False
+
+    def _dims_of_index(self, idx):
+        """[(position in idx, tensor dim)] of the slice entries of a basic / mixed index."""
+        items = list(idx)
+        n_consumed = 0
+        for i in items:
+            if i is None or i is Ellipsis:
+                continue
+            n_consumed += i.dim() if (isinstance(i, torch.Tensor) and i.dtype == torch.bool) else 1
+        out, d = [], 0
+        for pos, i in enumerate(items):
+            if i is None:
+                continue
+            if i is Ellipsis:
+                d += self.dim() - n_consumed
+                continue
+            if type(i) is slice:
+                out.append((pos, d))
+            d += i.dim() if (isinstance(i, torch.Tensor) and i.dtype == torch.bool) else 1
+        return out
+
+    def __getitem__(self, idx):
+        if not Tensor._has_neg_step(idx):
+            return torch.Tensor.__getitem__(self, idx)
+        items = list(idx) if type(idx) is tuple else [idx]
+        t, flips = self, []
+        for pos, d in self._dims_of_index(items):
+            sl = items[pos]
+            if sl.step is not None and sl.step < 0:
+                size = int(torch.Tensor.size(self, d))
+                start, stop, step = sl.indices(size)
+                n = len(range(start, stop, step))
+                flips.append(d)
+                # the same elements in a flipped axis: i' = size - 1 - i, visited with a positive step
+                items[pos] = slice(size - 1 - start, size - 1 - start + n * (-step), -step) if n else slice(0, 0, 1)
+        if flips:
+            t = torch.flip(self, flips)
+        return torch.Tensor.__getitem__(t, tuple(items))
+
+    def __setitem__(self, idx, value):
+        if not Tensor._has_neg_step(idx):
+            return torch.Tensor.__setitem__(self, idx, value)
+        items = list(idx) if type(idx) is tuple else [idx]
+        if any(isinstance(i, (torch.Tensor, list)) for i in items):
+            raise NotImplementedError("assignment through a negative-step slice combined with tensor / list indices")
+        neg = [(pos, d) for pos, d in self._dims_of_index(items) if items[pos].step is not None and items[pos].step < 0]
+        if len(neg) > 1:
+            raise NotImplementedError("assignment through more than one negative-step slice")
+        pos, d = neg[0]
+        size = int(torch.Tensor.size(self, d))
+        items[pos] = torch.arange(*items[pos].indices(size), device=self.device)      # one index vector keeps basic-index result layout
+        return torch.Tensor.__setitem__(self, tuple(items), value)
+
     # ---- LoD (level-of-detail offsets of packed variable-length sequences; used by static.nn.sequence_* ops) ----
     def lod(self):
         return [list(o) for o in self.__dict__.get("_lod", [])]
