@@ -310,7 +310,7 @@ class Executor:
             return x
 
         def run_node(n):
-            if n.kind == "train":
+            if n.kind in ("train", "control"):      # backward + update / run-time control flow: the node works on the value table
                 n.fn(env)
                 return
             out = n.fn(*decode(n.args), **decode(n.kwargs))

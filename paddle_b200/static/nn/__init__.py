@@ -180,36 +180,7 @@ def row_conv(input, future_context_size, param_attr=None, act=None):
 
 
 # control flow (python-side at record time, matching dygraph semantics)
-def cond(pred, true_fn=None, false_fn=None, name=None, return_names=None):
-    p = bool(pred.item()) if isinstance(pred, torch.Tensor) else bool(pred)
-    if p:
-        return true_fn() if true_fn is not None else None
-    return false_fn() if false_fn is not None else None
-
-
-def case(pred_fn_pairs, default=None, name=None):
-    for pred, fn in pred_fn_pairs:
-        if bool(pred.item() if isinstance(pred, torch.Tensor) else pred):
-            return fn()
-    return default() if default is not None else pred_fn_pairs[-1][1]()
-
-
-def switch_case(branch_index, branch_fns, default=None, name=None):
-    i = int(branch_index.item() if isinstance(branch_index, torch.Tensor) else branch_index)
-    fns = dict(branch_fns) if not isinstance(branch_fns, dict) else branch_fns
-    if isinstance(branch_fns, (list, tuple)) and branch_fns and not isinstance(branch_fns[0], (list, tuple)):
-        fns = dict(enumerate(branch_fns))
-    if i in fns:
-        return fns[i]()
-    return default() if default is not None else fns[max(fns)]()
-
-
-def while_loop(cond, body, loop_vars, is_test=False, name=None):
-    vs = list(loop_vars)
-    while bool(cond(*vs).item() if isinstance(cond(*vs), torch.Tensor) else cond(*vs)):
-        out = body(*vs)
-        vs = list(out) if isinstance(out, (list, tuple)) else [out]
-    return vs
+from .control_flow import case, cond, switch_case, while_loop  # noqa: F401,E402
 
 
 def static_pylayer(forward_fn, inputs, backward_fn=None, name=None):

@@ -94,3 +94,44 @@ def test_save_load_inference_model(tmp_path):
     prog, feeds, fetches = static.load_inference_model(str(tmp_path / "m"), exe)
     got, = exe.run(prog, feed={feeds[0]: a}, fetch_list=fetches)
     np.testing.assert_allclose(got, ref, rtol=1e-6)
+
+
+def test_data_dependent_control_flow():
+    """cond / case / switch_case / while_loop whose predicates are only known at run time (values come from feeds)."""
+    import numpy as np
+
+    import paddle_b200 as paddle
+
+    paddle.enable_static()
+    try:
+        S = paddle.static
+        main, start = S.Program(), S.Program()
+        with S.program_guard(main, start):
+            x = S.data("x", [1], "float32")
+            n = S.data("n", [1], "int64")
+            w = S.create_parameter([1], "float32", name="cf_w", default_initializer=paddle.nn.initializer.Constant(3.0))
+            out = S.nn.cond(x > 0, lambda: x * w, lambda: x - 1)
+            c = S.nn.case([(x > 5, lambda: x * 0 + 100), (x > 0, lambda: x * 0 + 10)], default=lambda: x * 0 - 1)
+            sw = S.nn.switch_case(n, {0: lambda: x + 1, 1: lambda: x + 2}, default=lambda: x * 0)
+            i0, acc0 = paddle.full([1], 0, "int64"), paddle.zeros([1])
+            i_f, acc_f = S.nn.while_loop(lambda i, acc: i < n, lambda i, acc: [i + 1, acc + x], [i0, acc0])
+            y = acc_f * 10
+            loss = paddle.mean(out)
+            grads = S.gradients([loss], [w])
+        exe = S.Executor()
+        exe.run(start)
+        for v, k in ((3.0, 0), (-2.0, 1), (7.0, 4)):
+            o, cc, s, i, acc, yy, g = exe.run(main, feed={"x": np.array([v], "float32"), "n": np.array([k])}, fetch_list=[out, c, sw, i_f, acc_f, y, grads[0]])
+            assert float(o[0]) == (v * 3 if v > 0 else v - 1)
+            assert float(cc[0]) == (100 if v > 5 else 10 if v > 0 else -1)
+            assert float(s[0]) == {0: v + 1, 1: v + 2}.get(k, 0.0)
+            assert int(i[0]) == k and float(acc[0]) == k * v and float(yy[0]) == 10 * k * v
+            assert float(g[0]) == (v if v > 0 else 0.0)          # the gradient flows through the selected branch only
+        # constant predicates keep the eager semantics (the untaken branch is not even traced)
+        main2 = S.Program()
+        with S.program_guard(main2):
+            a = S.data("a", [1], "float32")
+            r = S.nn.cond(paddle.full([1], 1.0) > 0, lambda: a + 1, lambda: 1 / 0)
+        assert float(exe.run(main2, feed={"a": np.array([1.0], "float32")}, fetch_list=[r])[0][0]) == 2.0
+    finally:
+        paddle.disable_static()
