@@ -9,16 +9,35 @@ import functools
 import torch
 
 current = [None]   # the static.Program being recorded, if any
+_inside = [0]      # > 0 while the body of a recordable runs: nested recordables belong to the enclosing node
+
+
+def _rewrap(o):
+    """Bodies run with torch-function dispatch off, so ops that rely on it to keep the paddle Tensor type hand back base tensors."""
+    if isinstance(o, torch.Tensor):
+        if type(o) is torch.Tensor:
+            from ..tensor import Tensor
+
+            return o.as_subclass(Tensor)
+        return o
+    if isinstance(o, (list, tuple)):
+        return type(o)(_rewrap(i) for i in o)
+    return o
 
 
 def recordable(fn):
     @functools.wraps(fn)
     def wrapper(*args, **kwargs):
         prog = current[0]
-        if prog is None or not (prog._touches_program(args) or prog._touches_program(kwargs)):
+        if prog is None or _inside[0] or not (prog._touches_program(args) or prog._touches_program(kwargs)):
             return fn(*args, **kwargs)
-        with torch._C.DisableTorchFunction():
-            out = fn(*args, **kwargs)
+        _inside[0] += 1
+        try:
+            with torch._C.DisableTorchFunction():
+                out = fn(*args, **kwargs)
+        finally:
+            _inside[0] -= 1
+        out = _rewrap(out)
         prog._record(wrapper, args, kwargs, out)
         return out
 

@@ -15,18 +15,23 @@ __all__ = [
 ]
 
 
+from ..framework.recording import recordable as _recordable  # noqa: E402
+
 def _fd(dtype):
     return dt(dtype, _dt.default_dtype())
 
 
+@_recordable
 def zeros(shape, dtype=None, name=None):
     return wrap(torch.zeros(shp(shape), dtype=_fd(dtype), device=dev()))
 
 
+@_recordable
 def ones(shape, dtype=None, name=None):
     return wrap(torch.ones(shp(shape), dtype=_fd(dtype), device=dev()))
 
 
+@_recordable
 def full(shape, fill_value, dtype=None, name=None):
     fill_value = to_int(fill_value) if not isinstance(fill_value, torch.Tensor) else fill_value.item()
     if dtype is None:
@@ -47,26 +52,32 @@ def fill_constant(shape, dtype, value, force_cpu=False, out=None, name=None):
     return full(shape, value, dtype)
 
 
+@_recordable
 def empty(shape, dtype=None, name=None):
     return wrap(torch.empty(shp(shape), dtype=_fd(dtype), device=dev()))
 
 
+@_recordable
 def zeros_like(x, dtype=None, name=None):
     return wrap(torch.zeros_like(raw(x), dtype=dt(dtype)))
 
 
+@_recordable
 def ones_like(x, dtype=None, name=None):
     return wrap(torch.ones_like(raw(x), dtype=dt(dtype)))
 
 
+@_recordable
 def full_like(x, fill_value, dtype=None, name=None):
     return wrap(torch.full_like(raw(x), to_int(fill_value), dtype=dt(dtype)))
 
 
+@_recordable
 def empty_like(x, dtype=None, name=None):
     return wrap(torch.empty_like(raw(x), dtype=dt(dtype)))
 
 
+@_recordable
 def arange(start=0, end=None, step=1, dtype=None, name=None):
     start, end, step = to_int(start), to_int(end), to_int(step)
     if end is None:
@@ -81,6 +92,7 @@ def arange(start=0, end=None, step=1, dtype=None, name=None):
 range = arange  # noqa: A001
 
 
+@_recordable
 def linspace(start, stop, num, dtype=None, name=None):
     return wrap(torch.linspace(to_int(start), to_int(stop), int(to_int(num)), dtype=_fd(dtype), device=dev()))
 
@@ -89,6 +101,7 @@ def logspace(start, stop, num, base=10.0, dtype=None, name=None):
     return wrap(torch.logspace(to_int(start), to_int(stop), int(to_int(num)), base=to_int(base), dtype=_fd(dtype), device=dev()))
 
 
+@_recordable
 def eye(num_rows, num_columns=None, dtype=None, name=None):
     n = int(to_int(num_rows))
     m = n if num_columns is None else int(to_int(num_columns))
@@ -103,11 +116,13 @@ def triu(x, diagonal=0, name=None):
     return torch.triu(T(x), diagonal)
 
 
+@_recordable
 def tril_indices(row, col=None, offset=0, dtype="int64"):
     col = row if col is None else col
     return wrap(torch.tril_indices(row, col, offset, dtype=dt(dtype), device=dev()))
 
 
+@_recordable
 def triu_indices(row, col=None, offset=0, dtype="int64"):
     col = row if col is None else col
     return wrap(torch.triu_indices(row, col, offset, dtype=dt(dtype), device=dev()))

@@ -9,6 +9,9 @@ import torch
 from ._helpers import T, ax, dt, raw, shp, to_int, to_tensor, wrap
 
 
+from ..framework.recording import recordable as _recordable  # noqa: E402
+
+@_recordable
 def reshape(x, *shape, name=None):
     x = T(x)
     s = shp(shape[0] if len(shape) == 1 else list(shape))
@@ -23,6 +26,7 @@ def reshape_(x, shape, name=None):
     return x
 
 
+@_recordable
 def view(x, shape_or_dtype, name=None):
     x = T(x)
     if isinstance(shape_or_dtype, (list, tuple)):
@@ -88,6 +92,7 @@ def row_stack(x, name=None):
     return torch.vstack([T(i) for i in x])
 
 
+@_recordable
 def split(x, num_or_sections, axis=0, name=None):
     x = T(x)
     axis = int(to_int(axis))
@@ -131,6 +136,7 @@ def unstack(x, axis=0, num=None):
     return list(torch.unbind(T(x), axis))
 
 
+@_recordable
 def squeeze(x, axis=None, name=None):
     x = T(x)
     a = ax(axis)
@@ -142,6 +148,7 @@ def squeeze(x, axis=None, name=None):
     return torch.squeeze(x, a) if a else x
 
 
+@_recordable
 def unsqueeze(x, axis, name=None):
     x = T(x)
     a = ax(axis)
@@ -164,6 +171,7 @@ def unsqueeze_(x, axis, name=None):
     return x
 
 
+@_recordable
 def flatten(x, start_axis=0, stop_axis=-1, name=None):
     x = T(x)
     if x.dim() == 0:
@@ -177,18 +185,22 @@ def flatten_(x, start_axis=0, stop_axis=-1, name=None):
     return x
 
 
+@_recordable
 def unflatten(x, axis, shape, name=None):
     return torch.unflatten(T(x), axis, shp(shape))
 
 
+@_recordable
 def expand(x, *shape, name=None):
     return torch.Tensor.expand(T(x), *shp(shape[0] if len(shape) == 1 else list(shape)))
 
 
+@_recordable
 def expand_as(x, y, name=None):
     return torch.Tensor.expand(T(x), *y.size())
 
 
+@_recordable
 def broadcast_to(x, shape, name=None):
     return torch.broadcast_to(T(x), shp(shape))
 
@@ -197,10 +209,12 @@ def broadcast_tensors(input, name=None):
     return list(torch.broadcast_tensors(*[T(i) for i in input]))
 
 
+@_recordable
 def tile(x, *repeat_times, name=None):
     return torch.tile(T(x), tuple(shp(repeat_times[0] if len(repeat_times) == 1 else list(repeat_times))))
 
 
+@_recordable
 def repeat_interleave(x, repeats, axis=None, name=None):
     r = repeats if not isinstance(repeats, torch.Tensor) else T(repeats)
     return torch.repeat_interleave(T(x), r, dim=axis)
@@ -219,6 +233,7 @@ def rot90(x, k=1, axes=(0, 1), name=None):
     return torch.rot90(T(x), k, list(axes))
 
 
+@_recordable
 def roll(x, shifts, axis=None, name=None):
     return torch.roll(T(x), ax(shifts) if not isinstance(shifts, int) else shifts, ax(axis))
 
@@ -232,6 +247,7 @@ def cast_(x, dtype):
     return x
 
 
+@_recordable
 def slice(input, axes, starts, ends):  # noqa: A001
     x = T(input)
     idx = [builtins.slice(None)] * x.dim()
@@ -240,6 +256,7 @@ def slice(input, axes, starts, ends):  # noqa: A001
     return x[tuple(idx)]
 
 
+@_recordable
 def strided_slice(x, axes, starts, ends, strides, name=None):
     x = T(x)
     idx = [builtins.slice(None)] * x.dim()
@@ -256,6 +273,7 @@ def strided_slice(x, axes, starts, ends, strides, name=None):
     return x[tuple(idx)]
 
 
+@_recordable
 def crop(x, shape=None, offsets=None, name=None):
     x = T(x)
     s = shp(shape) if shape is not None else list(x.size())
@@ -470,20 +488,24 @@ def tolist(x):
     return torch.Tensor.tolist(T(x))
 
 
+# shape / numel read metadata, which a recorded program must do at run time (dynamic batch): recorded as whole nodes
+@_recordable
 def numel(x, name=None):
-    return wrap(torch.tensor(T(x).numel(), dtype=torch.int64))
+    return wrap(torch.tensor(torch.Tensor.numel(T(x)), dtype=torch.int64))
 
 
+@_recordable
 def shape(input):  # noqa: A001
-    return wrap(torch.tensor(list(T(input).size()), dtype=torch.int32))
+    return wrap(torch.tensor(list(torch.Tensor.size(T(input))), dtype=torch.int32))
 
 
 def rank(input):
     return wrap(torch.tensor(T(input).dim(), dtype=torch.int32))
 
 
+@_recordable
 def is_empty(x, name=None):
-    return wrap(torch.tensor(T(x).numel() == 0))
+    return wrap(torch.tensor(torch.Tensor.numel(T(x)) == 0))
 
 
 def tensordot(x, y, axes=2, name=None):

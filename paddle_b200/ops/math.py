@@ -28,6 +28,8 @@ _UNARY = {
 _UNARY.pop("logit_")
 
 
+from ..framework.recording import recordable as _recordable  # noqa: E402
+
 def _mk_unary(name, fn):
     def op(x, name=None):
         return fn(T(x))
@@ -156,6 +158,7 @@ def kron(x, y, name=None):
     return torch.kron(T(x), T(y))
 
 
+@_recordable
 def scale(x, scale=1.0, bias=0.0, bias_after_scale=True, act=None, name=None):
     x = T(x)
     s = scale if not isinstance(scale, torch.Tensor) else scale
@@ -177,6 +180,7 @@ def multiplex(inputs, index, name=None):
     return stacked[idx, torch.arange(stacked.size(1), device=stacked.device)]
 
 
+@_recordable
 def clip(x, min=None, max=None, name=None):  # noqa: A002
     x = T(x)
     mn = min.item() if isinstance(min, torch.Tensor) and min.numel() == 1 else min

@@ -7,14 +7,18 @@ from ..framework import dtype as _dt
 from ._helpers import T, dev, dt, raw, shp, to_int, wrap
 
 
+from ..framework.recording import recordable as _recordable  # noqa: E402
+
 def _fd(dtype):
     return dt(dtype, _dt.default_dtype())
 
 
+@_recordable
 def rand(shape, dtype=None, name=None):
     return wrap(torch.rand(shp(shape), dtype=_fd(dtype), device=dev()))
 
 
+@_recordable
 def randn(shape, dtype=None, name=None):
     return wrap(torch.randn(shp(shape), dtype=_fd(dtype), device=dev()))
 
@@ -23,6 +27,7 @@ def standard_normal(shape, dtype=None, name=None):
     return randn(shape, dtype)
 
 
+@_recordable
 def normal(mean=0.0, std=1.0, shape=None, name=None):
     if isinstance(mean, torch.Tensor) or isinstance(std, torch.Tensor):
         m = T(mean) if isinstance(mean, torch.Tensor) else mean
@@ -38,6 +43,7 @@ def normal_(x, mean=0.0, std=1.0, name=None):
     return x
 
 
+@_recordable
 def uniform(shape, dtype=None, min=-1.0, max=1.0, seed=0, name=None):  # noqa: A002
     g = None
     if seed:
@@ -51,12 +57,14 @@ def uniform_(x, min=-1.0, max=1.0, seed=0, name=None):  # noqa: A002
     return x
 
 
+@_recordable
 def randint(low=0, high=None, shape=(1,), dtype=None, name=None):
     if high is None:
         low, high = 0, low
     return wrap(torch.randint(int(to_int(low)), int(to_int(high)), shp(shape), dtype=dt(dtype, torch.int64), device=dev()))
 
 
+@_recordable
 def randint_like(x, low=0, high=None, dtype=None, name=None):
     if high is None:
         low, high = 0, low
@@ -110,10 +118,12 @@ def log_normal_(x, mean=1.0, std=2.0, name=None):
     return x
 
 
+@_recordable
 def rand_like(x, dtype=None, name=None):
     return wrap(torch.rand_like(raw(x), dtype=dt(dtype)))
 
 
+@_recordable
 def randn_like(x, dtype=None, name=None):
     return wrap(torch.randn_like(raw(x), dtype=dt(dtype)))
 

@@ -6,6 +6,8 @@ import torch
 from ._helpers import T, ax, dt, raw, scalar_or_tensor, to_int, wrap
 
 
+from ..framework.recording import recordable as _recordable  # noqa: E402
+
 def argmax(x, axis=None, keepdim=False, dtype="int64", name=None):
     x = T(x)
     out = torch.argmax(x, dim=ax(axis), keepdim=keepdim if axis is not None else False)
@@ -30,6 +32,7 @@ def sort(x, axis=-1, descending=False, stable=False, name=None):
     return torch.sort(T(x), dim=axis, descending=descending, stable=stable)[0]
 
 
+@_recordable
 def topk(x, k, axis=None, largest=True, sorted=True, name=None):
     x = T(x)
     v, i = torch.topk(x, int(to_int(k)), dim=-1 if axis is None else axis, largest=largest, sorted=sorted)

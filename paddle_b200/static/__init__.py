@@ -51,6 +51,12 @@ class Variable(Tensor):
     def desc_shape(self):
         return self.__dict__.get("_pd_desc_shape", list(self.size()))
 
+    @property
+    def shape(self):
+        """Declared shape: dynamic dimensions read -1 (their run-time extent is `paddle.shape(x)[i]`), as in the reference's static mode.
+        Python code that bakes `x.shape[0]` of the placeholder into the program would silently fix the batch size."""
+        return list(self.desc_shape)
+
 
 class _Node:
     __slots__ = ("fn", "args", "kwargs", "outs", "kind")

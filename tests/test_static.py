@@ -135,3 +135,30 @@ def test_data_dependent_control_flow():
         assert float(exe.run(main2, feed={"a": np.array([1.0], "float32")}, fetch_list=[r])[0][0]) == 2.0
     finally:
         paddle.disable_static()
+
+
+def test_dynamic_batch_shapes_are_resolved_at_run_time():
+    """x.shape reports -1 for dynamic dims; paddle.shape / numel and shape-taking ops (reshape, expand, full, arange, tile, slice) use the
+    run-time extent, so one recorded program serves every batch size."""
+    import numpy as np
+
+    import paddle_b200 as paddle
+
+    paddle.enable_static()
+    try:
+        S = paddle.static
+        main = S.Program()
+        with S.program_guard(main):
+            x = S.data("x", [-1, 4], "float32")
+            assert x.shape == [-1, 4]
+            bsz = paddle.shape(x)[0]
+            outs = [paddle.reshape(x, [bsz, 2, 2]), paddle.reshape(x, [x.shape[0], 2, 2]), paddle.expand(paddle.ones([1, 3]), [bsz, 3]), paddle.full([bsz, 2], 7.0),
+                    paddle.arange(0, bsz), paddle.tile(paddle.ones([1, 2]), [bsz, 1]), paddle.slice(x, [0], [0], [bsz - 3]),
+                    paddle.ones_like(x) * paddle.cast(paddle.numel(x), "float32"), S.nn.fc(x, 3)]
+        exe = S.Executor()
+        for b in (8, 5):
+            res = exe.run(main, feed={"x": np.ones((b, 4), "float32")}, fetch_list=outs)
+            assert [r.shape for r in res] == [(b, 2, 2), (b, 2, 2), (b, 3), (b, 2), (b,), (b, 2), (b - 3, 4), (b, 4), (b, 3)]
+            assert res[7][0, 0] == 4 * b and res[4].tolist() == list(range(b))
+    finally:
+        paddle.disable_static()
