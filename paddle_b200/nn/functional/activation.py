@@ -8,6 +8,8 @@ from ...framework import dtype as _dt
 from ...ops._helpers import T, raw, wrap
 
 
+from ...framework.recording import recordable as _recordable  # noqa: E402
+
 def relu(x, name=None):
     return F.relu(T(x))
 
@@ -35,6 +37,7 @@ def prelu(x, weight, data_format="NCHW", name=None):
     return F.prelu(x, w)
 
 
+@_recordable
 def rrelu(x, lower=1.0 / 8, upper=1.0 / 3, training=True, name=None):
     return F.rrelu(T(x), lower, upper, training)
 
@@ -164,6 +167,7 @@ def log_softmax(x, axis=-1, dtype=None, name=None):
     return F.log_softmax(x, dim=axis, dtype=black_dtype("softmax", x, _dt.convert_dtype(dtype)))
 
 
+@_recordable
 def gumbel_softmax(x, temperature=1.0, hard=False, axis=-1, name=None):
     return F.gumbel_softmax(T(x), tau=temperature, hard=hard, dim=axis)
 

@@ -10,6 +10,8 @@ from ...framework import dtype as _dt
 from ...ops._helpers import T, raw, shp, to_int, wrap
 
 
+from ...framework.recording import recordable as _recordable  # noqa: E402
+
 def linear(x, weight, bias=None, name=None):
     """y = x @ W + b with W laid out [in, out]. Parity: nn/functional/common.py:linear.
 
@@ -23,6 +25,7 @@ def linear(x, weight, bias=None, name=None):
     return K.linear(T(x), weight, bias)
 
 
+@_recordable
 def dropout(x, p=0.5, axis=None, training=True, mode="upscale_in_train", name=None):
     x = T(x)
     if isinstance(p, torch.Tensor):
@@ -42,18 +45,22 @@ def dropout(x, p=0.5, axis=None, training=True, mode="upscale_in_train", name=No
     return x * mask / (1.0 - p) if mode == "upscale_in_train" else x * mask
 
 
+@_recordable
 def dropout2d(x, p=0.5, training=True, data_format="NCHW", name=None):
     return dropout(x, p, axis=[0, 1] if data_format == "NCHW" else [0, 3], training=training)
 
 
+@_recordable
 def dropout3d(x, p=0.5, training=True, data_format="NCDHW", name=None):
     return dropout(x, p, axis=[0, 1] if data_format == "NCDHW" else [0, 4], training=training)
 
 
+@_recordable
 def alpha_dropout(x, p=0.5, training=True, name=None):
     return F.alpha_dropout(T(x), p, training)
 
 
+@_recordable
 def feature_alpha_dropout(x, p=0.5, training=True, name=None):
     return F.feature_alpha_dropout(T(x), p, training)
 

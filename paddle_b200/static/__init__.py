@@ -133,9 +133,36 @@ class Program:
     def global_block(self):
         return self
 
+    @staticmethod
+    def _eval_node(n):
+        """The inference twin of a node: ops with a `training` switch (dropout family, batch / instance norm, rrelu) get it turned off."""
+        import inspect
+
+        if n.kind != "op":
+            return n
+        if n.kwargs.get("training") is True or n.kwargs.get("train") is True:
+            kw = dict(n.kwargs)
+            kw["training" if "training" in kw else "train"] = False
+            return _Node(n.fn, n.args, kw, n.outs, n.kind)
+        try:
+            params = list(inspect.signature(n.fn).parameters)
+        except (TypeError, ValueError):
+            return n
+        if "training" in params:
+            i = params.index("training")
+            if i < len(n.args) and n.args[i] is True:
+                args = list(n.args)
+                args[i] = False
+                return _Node(n.fn, type(n.args)(args), n.kwargs, n.outs, n.kind)
+            if i >= len(n.args) and "training" not in n.kwargs:
+                default = inspect.signature(n.fn).parameters["training"].default
+                if default is True:
+                    return _Node(n.fn, n.args, dict(n.kwargs, training=False), n.outs, n.kind)
+        return n
+
     def clone(self, for_test=False):
         p = Program()
-        p.nodes = [n for n in self.nodes if not (for_test and n.kind == "train")]
+        p.nodes = [self._eval_node(n) if for_test else n for n in self.nodes if not (for_test and n.kind == "train")]
         p.placeholders = dict(self.placeholders)
         p._fetch_alias, p._name2vid, p._next, p._keep = dict(self._fetch_alias), dict(self._name2vid), self._next, list(self._keep)
         return p

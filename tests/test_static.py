@@ -162,3 +162,36 @@ def test_dynamic_batch_shapes_are_resolved_at_run_time():
             assert res[7][0, 0] == 4 * b and res[4].tolist() == list(range(b))
     finally:
         paddle.disable_static()
+
+
+def test_clone_for_test_switches_random_ops_to_eval():
+    """dropout family / rrelu are re-sampled every run of the training program and become identities in `clone(for_test=True)`;
+    batch_norm uses its running statistics there."""
+    import numpy as np
+
+    import paddle_b200 as paddle
+
+    paddle.enable_static()
+    try:
+        S = paddle.static
+        main, start = S.Program(), S.Program()
+        with S.program_guard(main, start):
+            x = S.data("x", [4, 6], "float32")
+            h = paddle.nn.functional.dropout(x, 0.5, training=True)
+            d2 = paddle.nn.Dropout2D(0.5)(paddle.reshape(x, [4, 6, 1, 1]))
+            ad = paddle.nn.functional.alpha_dropout(x, 0.5)
+            rr = paddle.nn.functional.rrelu(x - 2.0)
+            bn = paddle.nn.BatchNorm1D(6)(x * paddle.arange(1, 5).astype("float32").reshape([4, 1]))
+        test_prog = main.clone(for_test=True)
+        exe = S.Executor()
+        exe.run(start)
+        X = np.ones((4, 6), "float32")
+        a1 = exe.run(main, feed={"x": X}, fetch_list=[h, d2, ad, rr, bn])
+        a2 = exe.run(main, feed={"x": X}, fetch_list=[h, d2, ad, rr])
+        assert all(not np.allclose(u, v) for u, v in zip(a1[:4], a2))          # fresh masks per run
+        assert abs(a1[4].mean()) < 1e-5                                        # training: batch statistics
+        b = exe.run(test_prog, feed={"x": X}, fetch_list=[h, d2, ad, rr, bn])
+        assert np.allclose(b[0], X) and np.allclose(b[1].reshape(4, 6), X) and np.allclose(b[2], X) and np.allclose(b[3], (X - 2) * (1 / 8 + 1 / 3) / 2)
+        assert abs(b[4].mean()) > 0.1                                          # eval: running statistics, not the batch's own
+    finally:
+        paddle.disable_static()
