@@ -64,6 +64,38 @@ class _Node:
     def __init__(self, fn, args, kwargs, outs, kind="op"):
         self.fn, self.args, self.kwargs, self.outs, self.kind = fn, args, kwargs, outs, kind
 
+    # Saved programs pickle their nodes.  Tensor method descriptors / builtins recorded through __torch_function__ (e.g. `Tensor.pow` from
+    # `x ** 2`) are not picklable by reference, so they travel by name and are looked up again on load.
+    def __getstate__(self):
+        fn = self.fn
+        try:
+            pickle.dumps(fn)
+            enc = ("obj", fn)
+        except Exception:  # noqa: BLE001
+            name = getattr(fn, "__name__", None)
+            objclass = getattr(fn, "__objclass__", None)
+            owner = None
+            if name and objclass is not None and issubclass(torch.Tensor, objclass) and hasattr(torch.Tensor, name):
+                owner = "tensor"                 # method descriptor of Tensor / TensorBase (x.mean(), ...)
+            elif name:
+                for cand in (name, f"__{name}__", f"__r{name}__", f"__i{name}__"):      # python wrappers such as Tensor.__pow__ (`x ** 2`)
+                    if getattr(torch.Tensor, cand, None) is fn:
+                        owner, name = "tensor", cand
+                        break
+            if owner is None and name and getattr(torch, name, None) is fn:
+                owner = "torch"
+            elif owner is None and name and getattr(torch.nn.functional, name, None) is fn:
+                owner = "functional"
+            if owner is None:
+                raise pickle.PicklingError(f"program node '{name or fn}' cannot be saved: its function is neither importable nor a torch op")
+            enc = (owner, name)
+        return (enc, self.args, self.kwargs, self.outs, self.kind)
+
+    def __setstate__(self, state):
+        enc, self.args, self.kwargs, self.outs, self.kind = state
+        kind, v = enc
+        self.fn = v if kind == "obj" else getattr({"tensor": torch.Tensor, "torch": torch, "functional": torch.nn.functional}[kind], v)
+
 
 class _Ref:
     __slots__ = ("vid",)
@@ -586,7 +618,12 @@ def normalize_program(program, feed_vars, fetch_vars, **kwargs):
 def _inference_blob(feed_vars, fetch_vars, program):
     feed_vars = feed_vars if isinstance(feed_vars, (list, tuple)) else [feed_vars]
     fetch_vars = fetch_vars if isinstance(fetch_vars, (list, tuple)) else [fetch_vars]
-    return {"program": program.clone(for_test=True), "feeds": [v.name for v in feed_vars], "fetch_vids": [program._fetch_alias[id(v)] for v in fetch_vars]}
+    infer = program.clone(for_test=True)
+    fetch_vids = [program._fetch_alias[id(v)] for v in fetch_vars]
+    from . import passes as _passes
+
+    _passes.dead_code_elimination(infer, keep=set(fetch_vids))      # prune to what the fetch targets need (drops the loss sub-graph)
+    return {"program": infer, "feeds": [v.name for v in feed_vars], "fetch_vids": fetch_vids}
 
 
 def serialize_program(feed_vars, fetch_vars, **kwargs):

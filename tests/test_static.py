@@ -195,3 +195,45 @@ def test_clone_for_test_switches_random_ops_to_eval():
         assert abs(b[4].mean()) > 0.1                                          # eval: running statistics, not the batch's own
     finally:
         paddle.disable_static()
+
+
+def test_save_inference_model_prunes_and_pickles_dunder_ops(tmp_path):
+    """The saved inference program keeps only what the fetch targets need (the loss sub-graph with `** 2` is dropped), nodes recorded from
+    Tensor dunder wrappers survive pickling, and the reloaded program serves any batch size; LR schedulers drive static updates."""
+    import os
+
+    import numpy as np
+
+    import paddle_b200 as paddle
+
+    paddle.enable_static()
+    try:
+        S = paddle.static
+        main, start = S.Program(), S.Program()
+        with S.program_guard(main, start):
+            x = S.data("x", [-1, 3], "float32")
+            y = S.data("y", [-1, 1], "float32")
+            pred = S.nn.fc(x, 1) ** 2
+            loss = paddle.mean((pred - y) ** 2)
+            sched = paddle.optimizer.lr.StepDecay(0.05, step_size=2, gamma=0.1)
+            paddle.optimizer.SGD(sched).minimize(loss)
+        exe = S.Executor()
+        exe.run(start)
+        X = np.random.RandomState(0).randn(16, 3).astype("float32")
+        w = [p for p in main.all_parameters() if p.shape == [3, 1]][0]
+        deltas = []
+        for i in range(4):
+            before = w.numpy().copy()
+            exe.run(main, feed={"x": X, "y": X[:, :1]}, fetch_list=[loss])
+            deltas.append(float(np.abs(w.numpy() - before).max()))
+            sched.step()
+        assert deltas[2] < deltas[0] * 0.5                      # lr dropped 10x after two steps
+        ref, = exe.run(main.clone(for_test=True), feed={"x": X[:5], "y": X[:5, :1]}, fetch_list=[pred])
+        S.save_inference_model(str(tmp_path / "m"), [x], [pred], exe, program=main)
+        prog2, feeds, fetches = S.load_inference_model(str(tmp_path / "m"), exe)
+        assert len(prog2.nodes) < len(main.nodes) and feeds == ["x"]
+        for b in (2, 5):
+            out, = exe.run(prog2, feed={"x": X[:b]}, fetch_list=fetches)
+            np.testing.assert_allclose(out, ref[:b], rtol=1e-6)
+    finally:
+        paddle.disable_static()
