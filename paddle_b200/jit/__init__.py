@@ -176,11 +176,24 @@ def save(layer, path, input_spec=None, **configs):
     except Exception:
         spec["pickled_layer"] = None
     if spec["pickled_layer"] is None and spec["input_spec"] and all(s is not None for s in spec["input_spec"]):
-        # classes that cannot be re-imported (defined in a function / __main__): store the traced forward as a static Program
+        # classes that cannot be re-imported (defined in a function / __main__): store the traced forward as a static Program.
+        # The saved artifact is the inference program: trace in eval mode (dropout off, batch norm on running statistics).
+        was_training = bool(getattr(layer, "training", False))
+        layer.eval()
         try:
             spec["program"] = pickle.dumps(_trace_program(layer, spec["input_spec"]))
-        except Exception:
+        except Exception as e:  # noqa: BLE001
             spec["program"] = None
+            trace_error = e
+        finally:
+            if was_training:
+                layer.train()
+    if spec["pickled_layer"] is None and not spec.get("program"):
+        cls = type(layer)
+        importable = "<locals>" not in cls.__qualname__ and cls.__module__ != "__main__"
+        if not importable:
+            raise RuntimeError(f"jit.save: {cls.__qualname__} can neither be pickled nor re-imported, and tracing it failed"
+                               + (f" ({type(trace_error).__name__}: {trace_error})" if "trace_error" in locals() else " (pass input_spec so that the forward can be traced)"))
     with open(path + ".pdmodel", "wb") as f:
         pickle.dump(spec, f)
 

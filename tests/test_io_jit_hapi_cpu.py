@@ -215,3 +215,32 @@ def test_distribution_sparse_geometric_text():
     trans = paddle.to_tensor(np.random.rand(3, 3).astype("float32"))
     sc, path = paddle.text.viterbi_decode(pot, trans, paddle.to_tensor(np.array([4])), include_bos_eos_tag=False)
     assert path.shape == [1, 4] and sc.shape == [1]
+
+
+def test_jit_save_of_local_class_is_the_eval_program(tmp_path):
+    """A Layer whose class cannot be re-imported is saved as its traced inference program: traced in eval mode (dropout off, batch norm on
+    running statistics) even when the layer is training, dynamic batch on reload, clear error when nothing can be saved."""
+    def make():
+        class Local(paddle.nn.Layer):
+            def __init__(self):
+                super().__init__()
+                self.fc, self.drop, self.bn = paddle.nn.Linear(4, 4), paddle.nn.Dropout(0.5), paddle.nn.BatchNorm1D(4)
+
+            def forward(self, x):
+                return self.bn(self.drop(self.fc(x)))
+
+        return Local()
+
+    net = make()
+    net.train()
+    paddle.jit.save(net, str(tmp_path / "m"), input_spec=[paddle.static.InputSpec([None, 4], "float32", "x")])
+    assert net.training
+    loaded = paddle.jit.load(str(tmp_path / "m"))
+    x = paddle.to_tensor(np.random.RandomState(0).randn(6, 4).astype("float32"))
+    a, b = loaded(x).numpy(), loaded(x).numpy()
+    net.eval()
+    np.testing.assert_allclose(a, b)
+    np.testing.assert_allclose(a, net(x).numpy(), rtol=1e-5, atol=1e-6)
+    assert loaded(x[:3]).shape == [3, 4]
+    with pytest.raises(RuntimeError, match="input_spec"):
+        paddle.jit.save(make(), str(tmp_path / "n"))
