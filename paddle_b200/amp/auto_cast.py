@@ -25,6 +25,13 @@ def fp32_guard(op, *tensors):
     if _state["enabled"] and op in _state["black"]:
         dev = "cuda" if torch.cuda.is_available() else "cpu"
         return torch.autocast(device_type=dev, enabled=False), tuple(t.float() if isinstance(t, torch.Tensor) and t.is_floating_point() else t for t in tensors)
+    if _state["enabled"] and _state["level"] == "O2" and len(tensors) >= 2:
+        # O2: parameters are low precision; an fp32 activation (typically the model input) meeting them is cast down, like the
+        # reference's O2 autocast of white-list op inputs.  Only reached on paths where the dtypes would otherwise clash.
+        x, w = tensors[0], tensors[1]
+        if isinstance(x, torch.Tensor) and isinstance(w, torch.Tensor) and x.is_floating_point() and w.dtype in (torch.float16, torch.bfloat16) and x.dtype != w.dtype:
+            rest = tuple(t.to(w.dtype) if isinstance(t, torch.Tensor) and t.is_floating_point() and t.dtype != w.dtype else t for t in tensors[2:])
+            tensors = (x.to(w.dtype), w) + rest
     return contextlib.nullcontext(), tensors
 
 

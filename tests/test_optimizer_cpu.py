@@ -241,3 +241,60 @@ def test_flat_arena_adamw_checkpoint_resume():
         run(net_c, opt_c, data[3:])
         for (k, a), (_, c) in zip(net_a.state_dict().items(), net_c.state_dict().items()):
             np.testing.assert_allclose(c.numpy(), a.numpy(), rtol=1e-5, atol=1e-6, err_msg=f"{k} arena_first={arena_first}")
+
+
+def test_amp_o2_fp32_input_and_checkpoint_roundtrip(tmp_path):
+    """O2-decorated bf16 model fed with fp32 data (the input is cast down at the first white-list op); .pdparams / .pdopt round trip with fp32
+    master weights reproduces the run bit for bit."""
+    import os
+
+    import numpy as np
+
+    import paddle_b200 as paddle
+
+    def build():
+        paddle.seed(0)
+        net = paddle.nn.Sequential(paddle.nn.Conv1D(2, 4, 3, padding=1), paddle.nn.Flatten(), paddle.nn.Linear(16, 8), paddle.nn.LayerNorm(8), paddle.nn.Linear(8, 2))
+        opt = paddle.optimizer.AdamW(1e-2, parameters=net.parameters(), multi_precision=True)
+        return paddle.amp.decorate(models=net, optimizers=opt, level="O2", dtype="bfloat16")
+
+    net, opt = build()
+    assert {str(p.dtype) for p in net.parameters()} == {"torch.bfloat16", "torch.float32"}        # norm layers stay fp32
+    x = paddle.to_tensor(np.random.RandomState(0).randn(3, 2, 4).astype("float32"))
+    scaler = paddle.amp.GradScaler(init_loss_scaling=128)
+
+    def loss_of(m):
+        with paddle.amp.auto_cast(level="O2", dtype="bfloat16"):
+            return m(x).astype("float32").square().mean()
+
+    for _ in range(3):
+        scaler.scale(loss_of(net)).backward()
+        scaler.step(opt)
+        scaler.update()
+        opt.clear_grad()
+    paddle.save(net.state_dict(), str(tmp_path / "m.pdparams"))
+    paddle.save(opt.state_dict(), str(tmp_path / "m.pdopt"))
+    sd, od = paddle.load(str(tmp_path / "m.pdparams")), paddle.load(str(tmp_path / "m.pdopt"))
+    assert "master_weights" in od
+    net2, opt2 = build()
+    net2.set_state_dict(sd)
+    n1, n2 = [p.name for p in net.parameters()], [p.name for p in net2.parameters()]
+    remap = {}
+    for k, v in od.items():
+        if k == "master_weights":
+            remap[k] = {n2[n1.index(n)]: t for n, t in v.items()}
+            continue
+        for a, b in zip(n1, n2):
+            if k.startswith(a + "_"):
+                k = b + k[len(a):]
+                break
+        remap[k] = v
+    opt2.set_state_dict(remap)
+    l1, l2 = loss_of(net), loss_of(net2)
+    assert float(l1) == float(l2)
+    l1.backward()
+    opt.step()
+    l2.backward()
+    opt2.step()
+    for a, b in zip(net.parameters(), net2.parameters()):
+        np.testing.assert_array_equal(a.astype("float32").numpy(), b.astype("float32").numpy())
