@@ -40,6 +40,18 @@ def _convert(ret):
     return ret
 
 
+class _BoolCall(int):
+    """0 / 1 that can also be called to get the bool (attribute-style and method-style spellings of the same predicate)."""
+
+    def __call__(self):
+        return bool(self)
+
+    def __repr__(self):
+        return "True" if self else "False"
+
+    __str__ = __repr__
+
+
 class Tensor(torch.Tensor):
     """Eager tensor with paddle semantics."""
 
@@ -141,6 +153,11 @@ class Tensor(torch.Tensor):
     @property
     def is_leaf(self):
         return torch.Tensor.is_leaf.__get__(self)
+
+    @property
+    def is_sparse(self):
+        """paddle spells it `x.is_sparse()`, torch `x.is_sparse`: the value answers both (truthy int that is also callable)."""
+        return _BoolCall(torch.Tensor.layout.__get__(self) != torch.strided)
 
     def is_dense(self):
         return self.layout == torch.strided

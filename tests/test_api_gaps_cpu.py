@@ -386,3 +386,13 @@ def test_class_method_parity_additions(tmp_path):
     st2 = paddle.distributed.fleet.DistributedStrategy()
     st2.load_from_prototxt(str(tmp_path / "s.txt"))
     assert st2.qat_configs["weight_bits"] == 4 and st2.sync_batch_norm is False and st2.localsgd_configs["k_steps"] == 1
+
+
+def test_is_sparse_method_and_attribute_spellings():
+    import copy
+
+    x = paddle.to_tensor(np.eye(2, dtype="float32"))
+    assert x.is_sparse() is False and not x.is_sparse and x.is_dense() and repr(x.is_sparse) == "False"
+    assert copy.deepcopy(x).shape == [2, 2]
+    sp = x.to_sparse_coo(2)
+    assert sp.is_sparse_coo() and bool(sp.is_sparse) and sp.nnz() == 2      # sparse results are torch sparse tensors with paddle methods patched on
