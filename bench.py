@@ -8,6 +8,14 @@ synthetic tokens, random-init weights.  Parallel layout per N: 1 -> single GPU; 
   python bench.py --gpus 1 --steps 5 --warmup 3
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 ...
   python bench.py --impl reference ...   -> {"impl": "reference", "unavailable": ...}
+  python bench.py --impl library ...     -> same model and engine with the spec's hot ops on LIBRARY kernels (cuBLAS GEMMs, cuDNN / flash
+                                            SDPA attention, NCCL collectives and p2p): the "NCCL + cuBLAS baseline" the fused paths are
+                                            compared against on the same box.  It is NOT the reference framework.
+
+Besides tokens/s the JSON line carries `exposed_comm`: device-measured milliseconds per step in which the compute stream waited on
+communication (pipeline mailbox waits counted by the wait kernels, NCCL collectives / gradient all-reduce bracketed by CUDA events on
+the compute stream) and, for the fused all-gather->GEMM / GEMM->reduce-scatter kernels, a calibrated estimate (fused kernel time minus
+the same GEMM without the collective, times the calls per step).
 """
 from __future__ import annotations
 
@@ -36,6 +44,9 @@ def parse():
     ap.add_argument("--layers", type=int, default=0, help="debug only: override layer count (result is then marked invalid)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--layout", default="", help="dp,mp,pp override of the per-N layout (experiments)")
+    ap.add_argument("--pp-schedule", default="ZBH1", help="pipeline schedule when pp > 1: ZBH1 (zero bubble, default) | 1F1B | FThenB | VPP")
+    ap.add_argument("--vpp", type=int, default=1, help="virtual pipeline chunks per rank (with --pp-schedule VPP)")
+    ap.add_argument("--no-comm-calibration", action="store_true")
     ap.add_argument("--recompute-skip", type=int, default=-1,
                     help="N=1 only: number of trailing decoder layers that keep their activations (default: as many as fit in HBM)")
     return ap.parse_args()
@@ -98,6 +109,95 @@ def layout_for(n):
     return {1: (1, 1, 1), 2: (1, 2, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(n, (n, 1, 1))
 
 
+def exposed_comm_report(regions, args, cfg, mp, pp, dp, accumulate, n, local_rank, ms_per_step):
+    """Max over ranks of the per-step exposed communication (see the module docstring); adds the calibrated in-kernel part of the fused
+    tensor-parallel GEMMs when they are in use."""
+    import torch
+    import torch.distributed as dist
+
+    keys = ["pp_mailbox_wait", "pp_recv_wait", "grad_all_reduce", "mp_all_gather", "mp_reduce_scatter", "mp_all_reduce"]
+    vec = torch.tensor([float(regions.get(k, 0.0)) for k in keys], device="cuda", dtype=torch.float64)
+    fused = None
+    if mp > 1 and args.impl == "ours" and not args.no_comm_calibration:
+        try:
+            fused = calibrate_fused_mp(args, cfg, mp, pp, accumulate)
+        except Exception as e:  # noqa: BLE001
+            fused = {"error": str(e)[:200]}
+    extra = torch.tensor([float((fused or {}).get("ms_per_step", 0.0))], device="cuda", dtype=torch.float64)
+    dist.all_reduce(vec, op=dist.ReduceOp.MAX)
+    dist.all_reduce(extra, op=dist.ReduceOp.MAX)
+    rep = {k: round(float(v), 3) for k, v in zip(keys, vec.tolist()) if v > 0}
+    out = {"unit": "ms/step, max over ranks, device-timed", "regions": rep}
+    if fused is not None:
+        fused["ms_per_step"] = round(float(extra.item()), 3)
+        out["fused_mp_gemm_collective"] = fused
+    total = sum(rep.values()) + float(extra.item())
+    out["total_ms_per_step"] = round(total, 3)
+    out["fraction_of_step"] = round(total / ms_per_step, 4)
+    if "pp_mailbox_wait" in rep or "pp_recv_wait" in rep:
+        out["note"] = "pipeline waits include the schedule's bubble (idle stages), not only transfer time"
+    return out
+
+
+def calibrate_fused_mp(args, cfg, mp, pp, accumulate):
+    """Exposed part of the in-kernel collectives: time each fused tensor-parallel GEMM (all-gather->GEMM, GEMM->reduce-scatter) against
+    the same GEMM on already-gathered / not-scattered operands, on the model's shapes, and scale by the calls per step."""
+    import torch
+
+    from paddle_b200.distributed import fleet
+    from paddle_b200.kernels import gemm as KG
+    from paddle_b200.parallel import symm
+
+    hcg = fleet.get_hybrid_communicate_group()
+    grp = hcg.get_model_parallel_group()
+    sc = symm.context_for(grp)
+    if sc is None:
+        return {"ms_per_step": 0.0, "note": "fused kernels not in use"}
+    h, f = cfg.hidden_size, cfg.intermediate_size
+    rows = args.micro_batch * args.seq            # tokens per micro-batch (full sequence inside the tensor-parallel region)
+    dev = torch.device("cuda")
+    dt = torch.bfloat16
+    layers_local = cfg.num_hidden_layers // pp
+    shapes = {"qkv": (h, 3 * h // mp), "gate_up": (h, 2 * f // mp), "o": (h // mp, h), "down": (f // mp, h)}
+    res, total = {}, 0.0
+
+    def t(fn, it=6):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.distributed.barrier()
+        a.record()
+        for _ in range(it):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / it
+
+    for name in ("qkv", "gate_up"):          # forward: all-gather -> GEMM ; backward dX: GEMM -> reduce-scatter
+        k, nn_ = shapes[name]
+        w = torch.randn(k, nn_, device=dev, dtype=dt) * 0.02
+        xs = torch.randn(rows // mp, 1, k, device=dev, dtype=dt)
+        xf = torch.randn(rows, k, device=dev, dtype=dt)
+        dy = torch.randn(rows, 1, nn_, device=dev, dtype=dt)
+        ag = t(lambda: sc.allgather_gemm(xs, w)) - t(lambda: KG.gemm(xf, w))
+        rs = t(lambda: sc.gemm_reduce_scatter(dy, w, b_is_nk=True)) - t(lambda: KG.gemm(dy.view(rows, nn_), w, b_is_nk=True))
+        res[name] = {"ag_gemm_minus_gemm_ms": round(ag, 4), "gemm_rs_minus_gemm_ms": round(rs, 4)}
+        total += max(ag, 0.0) + max(rs, 0.0)
+    for name in ("o", "down"):               # forward: GEMM -> reduce-scatter ; backward dX: all-gather -> GEMM
+        k, nn_ = shapes[name]
+        w = torch.randn(k, nn_, device=dev, dtype=dt) * 0.02
+        x = torch.randn(rows, 1, k, device=dev, dtype=dt)
+        dys = torch.randn(rows // mp, 1, nn_, device=dev, dtype=dt)
+        dyf = torch.randn(rows, nn_, device=dev, dtype=dt)
+        rs = t(lambda: sc.gemm_reduce_scatter(x, w)) - t(lambda: KG.gemm(x.view(rows, k), w))
+        ag = t(lambda: sc.allgather_gemm(dys, w, b_is_nk=True)) - t(lambda: KG.gemm(dyf, w, b_is_nk=True))
+        res[name] = {"gemm_rs_minus_gemm_ms": round(rs, 4), "ag_gemm_minus_gemm_ms": round(ag, 4)}
+        total += max(ag, 0.0) + max(rs, 0.0)
+    calls = layers_local * accumulate
+    return {"ms_per_step": total * calls, "per_layer_per_microbatch_ms": round(total, 4), "calls_per_step": calls, "detail": res}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -105,6 +205,12 @@ def main():
                                                               "and build dependency 'opteinsum' is not in /opt/wheelhouse (see DESIGN.md)"}))
         return 0
 
+    if args.impl not in ("ours", "library"):
+        print(json.dumps({"impl": args.impl, "unavailable": "unknown --impl (ours | library | reference)"}))
+        return 0
+    if args.impl == "library":   # must be set before paddle_b200 reads the flags
+        os.environ.update({"FLAGS_b200_gemm_backend": "cublas", "FLAGS_b200_flash_attention": "0", "FLAGS_b200_p2p_collectives": "0",
+                           "FLAGS_b200_pp_mailbox": "0", "FLAGS_b200_fused_wgrad": "0", "B200_DISABLE_SYMM": "1"})
     os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")   # 164 of 179 GB live at N=1: avoid fragmentation
     import torch
 
@@ -146,8 +252,9 @@ def main():
 
     if args.micro_batch <= 0:
         # measured on B200: without a pipeline, larger micro-batches give fuller GEMM waves (mp2: 4 sequences fit the activations of all
-        # layers); with pp > 1 the bubble (pp-1)/(accumulate+pp-1) dominates, so keep as many micro-batches as possible
-        args.micro_batch = 4 if (mp > 1 and pp == 1) else (2 if pp > 1 else 1)   # pp2: 2 measured +3 % over 1 despite the larger bubble
+        # layers); with pp > 1 the bubble (pp-1)/(accumulate+pp-1) dominates, so keep as many micro-batches as possible.
+        # single GPU: 2 sequences (M = 8192 rows) turn the 4.3-wave N=5120 GEMMs (320 tiles on 74 CTA pairs) into 8.6 waves
+        args.micro_batch = 4 if (mp > 1 and pp == 1) else 2
     seqs_per_replica = args.seqs_per_gpu * mp * pp
     global_batch = seqs_per_replica * dp
     accumulate = seqs_per_replica // args.micro_batch
@@ -155,9 +262,10 @@ def main():
     if pp > 1:
         from paddle_b200.distributed.fleet.pipeline import PipelineLayer
 
-        strategy.pipeline_configs = {"accumulate_steps": accumulate, "micro_batch_size": args.micro_batch}
+        vpp = args.vpp if args.pp_schedule.upper() in ("VPP", "FTHENB") and args.vpp > 1 else 1
+        strategy.pipeline_configs = {"accumulate_steps": accumulate, "micro_batch_size": args.micro_batch, "schedule_mode": args.pp_schedule}
         model = PipelineLayer(layers=L.pipeline_layer_descs(cfg), num_stages=pp, loss_fn=L.LlamaPretrainingCriterion(cfg),
-                              seg_method="layer:LlamaDecoderLayer")
+                              seg_method="layer:LlamaDecoderLayer", num_virtual_pipeline_stages=vpp if vpp > 1 else None)
     else:
         model = L.LlamaForCausalLM(cfg)
     n_params_local = sum(p.numel() for p in model.parameters())
@@ -203,8 +311,17 @@ def main():
             paddle.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed(nsteps, e2e, offset):
+    from paddle_b200.distributed import comm_timer
+
+    def pp_wait(reset=True):
+        fn = getattr(model, "exposed_wait", None)
+        return fn(reset) if (pp > 1 and fn is not None) else None
+
+    def timed(nsteps, e2e, offset, measure_comm=False):
         barrier()
+        if measure_comm:
+            comm_timer.enable(True)
+            pp_wait(True)
         sampler = ClockSampler(local_rank)
         sampler.start()
         kernels.reset_launch_count()
@@ -226,6 +343,14 @@ def main():
         if n > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         clocks = sampler.stop()
+        if measure_comm:
+            regions = comm_timer.summary()
+            comm_timer.enable(False)
+            w = pp_wait(True)
+            ex = {k: round(v["ms"] / nsteps, 3) for k, v in regions.items()}
+            if w is not None:
+                ex["pp_mailbox_wait"] = round(w["wait_ms"] / nsteps, 3)
+            timed.exposed = ex
         return float(t.item()), wall, kernels.launch_count(), clocks, last
 
     # warm-up (also materialises optimizer state and tensor maps).  Single GPU: if keeping every layer's activations does not
@@ -248,7 +373,7 @@ def main():
             torch.cuda.empty_cache()
             set_recompute_skip(max(0, int(cfg.recompute_skip_layers) - 8))
             w_done = 0
-    ms, wall, launches, clocks, last = timed(args.steps, e2e=False, offset=0)
+    ms, wall, launches, clocks, last = timed(args.steps, e2e=False, offset=0, measure_comm=n > 1)
     tokens_per_step = global_batch * seq
     value = tokens_per_step * args.steps / (ms / 1e3)
     out = {
@@ -266,6 +391,14 @@ def main():
                    "params_per_gpu": n_params_local, "recompute_skip_layers": int(getattr(cfg, "recompute_skip_layers", 0))},
         "gpu_launches": int(launches), "clocks": clocks, "wall_s": round(wall, 3),
     }
+    if args.impl == "library":
+        out["impl"] = "library"
+        out["config"]["library_arm"] = "same model/engine; GEMM = cuBLAS (torch.matmul), attention = PyTorch SDPA (cuDNN / flash), mp/dp collectives and pipeline p2p = NCCL; no fused GEMM+collective kernels, no peer-memory mailbox"
+    if pp > 1:
+        out["config"]["pp_schedule"] = str(getattr(model, "schedule_mode", args.pp_schedule))
+        out["config"]["pp_transport"] = model.transport_name() if hasattr(model, "transport_name") else None
+    if n > 1:
+        out["exposed_comm"] = exposed_comm_report(getattr(timed, "exposed", {}), args, cfg, mp, pp, dp, accumulate, n, local_rank, ms / args.steps)
     if args.layers:
         out["invalid"] = "debug run with reduced layer count"
     if not args.no_e2e:
@@ -277,7 +410,7 @@ def main():
         peaks = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    flops_per_token = 6 * 13.0e9 + 12 * cfg.num_hidden_layers * cfg.hidden_size * seq  # fwd+bwd model FLOPs
+    flops_per_token = 6 * 13.0e9 + 6 * cfg.num_hidden_layers * cfg.hidden_size * seq  # fwd+bwd model FLOPs (attention counted causal: half of 12 L h s)
     out["peak_mem_gb"] = round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)
     out["model_tflops_per_gpu"] = round(value * flops_per_token / n / 1e12, 1)
     if peaks.get("bf16_tflops_sustained"):

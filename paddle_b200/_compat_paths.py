@@ -122,7 +122,7 @@ _reexport(_FLEET + ".meta_parallel.parallel_layers", "fleet.meta_parallel.parall
 _reexport(_FLEET + ".meta_parallel.parallel_layers.pp_layers", "pp_layers", [_FLEET + ".pipeline"], ["PipelineLayer", "LayerDesc", "SharedLayerDesc", "SegmentLayers"])
 _reexport(_FLEET + ".meta_parallel.parallel_layers.mp_layers", "mp_layers", [_FLEET + ".mp_layers"])
 _reexport(_FLEET + ".meta_parallel.parallel_layers.random", "random", [_FLEET + ".random"])
-_reexport(_FLEET + ".meta_parallel.pipeline_parallel", "pipeline_parallel", [_FLEET + ".pipeline"], ["PipelineParallel", "PipelineParallelWithInterleave"])
+_reexport(_FLEET + ".meta_parallel.pipeline_parallel", "pipeline_parallel", [_FLEET + ".pipeline"], ["PipelineParallel", "PipelineParallelWithInterleave", "PipelineParallelWithInterleaveFthenB", "PipelineParallelZeroBubble"])
 _reexport(_FLEET + ".meta_parallel.tensor_parallel", "tensor_parallel", [_FLEET + ".hybrid"], ["TensorParallel"])
 _reexport(_FLEET + ".meta_parallel.sharding_parallel", "sharding_parallel", [_FLEET + ".hybrid"], ["ShardingParallel"])
 _reexport(_FLEET + ".meta_parallel.segment_parallel", "segment_parallel", [_FLEET + ".hybrid"], ["SegmentParallel"])

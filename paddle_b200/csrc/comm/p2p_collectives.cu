@@ -289,6 +289,42 @@ __global__ void __launch_bounds__(kThreads) a2av_kernel(Peers P, const char* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------- mailbox signal / wait
+// Point-to-point "mailbox" used by the pipeline engine (distributed/fleet/pipeline.py): the producer copies a tensor into a slot
+// of the consumer's heap with the copy engine (cudaMemcpyAsync on the IPC-mapped pointer: no SM work), then this one-thread kernel
+// publishes the slot with a release store; the consumer's stream runs wait_flag_kernel before the first kernel that reads the
+// slot.  The waiting thread accounts the time it spun into stats[0] (ns) / stats[1] (waits) = exposed pipeline wait on the device.
+__global__ void signal_flag_kernel(uint32_t* remote_flag, uint32_t value) {
+  __threadfence_system();
+  st_release_sys(remote_flag, value);
+}
+
+__global__ void wait_flag_kernel(const uint32_t* flag, uint32_t value, unsigned long long* stats, unsigned long long timeout_ns) {
+  const uint64_t t0 = gtimer();
+  while ((int32_t)(ld_acquire_sys(flag) - value) < 0) {
+    if (gtimer() - t0 > timeout_ns) {
+      printf("b200 p2p mailbox: timeout waiting for flag value %u (have %u)\n", value, ld_acquire_sys(flag));
+      __trap();
+    }
+    __nanosleep(200);
+  }
+  if (stats) {
+    atomicAdd(stats, (unsigned long long)(gtimer() - t0));
+    atomicAdd(stats + 1, 1ull);
+  }
+}
+
+void p2p_signal_flag(void* remote_flag, uint32_t value, cudaStream_t s) {
+  signal_flag_kernel<<<1, 1, 0, s>>>(static_cast<uint32_t*>(remote_flag), value);
+  B200_CUDA_CHECK(cudaGetLastError());
+}
+
+void p2p_wait_flag(const void* flag, uint32_t value, void* stats, double timeout_s, cudaStream_t s) {
+  wait_flag_kernel<<<1, 1, 0, s>>>(static_cast<const uint32_t*>(flag), value, static_cast<unsigned long long*>(stats),
+                                   (unsigned long long)(timeout_s * 1e9));
+  B200_CUDA_CHECK(cudaGetLastError());
+}
+
 static Peers make_peers(const int64_t* bases, int world) {
   Peers P;
   for (int r = 0; r < kMaxRanks; ++r) P.base[r] = r < world ? reinterpret_cast<char*>(bases[r]) : nullptr;

@@ -42,6 +42,7 @@ class SymmHeap {
     for (size_t i = 0; i < peers_.size(); ++i)
       if (peers_[i] && (int)i != rank_) cudaIpcCloseMemHandle(peers_[i]);
     if (peer_table_dev_) cudaFree(peer_table_dev_);
+    if (wait_stats_) cudaFree(wait_stats_);
     if (base_) cudaFree(base_);
   }
 
@@ -173,6 +174,35 @@ class SymmHeap {
                    row_bytes, rows_hint, rank_, world_, (uint32_t)epoch, counter(), at::cuda::getCurrentCUDAStream().stream());
     finish();
   }
+  // ---- mailbox primitives (pipeline p2p): flags live in the symmetric data region at byte offset `flag_off` ----
+  void signal_flag(int peer, int64_t flag_off, int64_t value) {
+    c10::cuda::CUDAGuard g(device_);
+    comm::p2p_signal_flag(static_cast<char*>(peers_.at(peer)) + flag_off, (uint32_t)value, at::cuda::getCurrentCUDAStream().stream());
+    finish();
+  }
+  void wait_flag(int64_t flag_off, int64_t value, double timeout_s) {
+    c10::cuda::CUDAGuard g(device_);
+    comm::p2p_wait_flag(static_cast<char*>(base_) + flag_off, (uint32_t)value, wait_stats_dev(), timeout_s,
+                        at::cuda::getCurrentCUDAStream().stream());
+    finish();
+  }
+  void* wait_stats_dev() {
+    if (!wait_stats_) {
+      c10::cuda::CUDAGuard g(device_);
+      ck(cudaMalloc(&wait_stats_, 16), "cudaMalloc wait stats");
+      ck(cudaMemset(wait_stats_, 0, 16), "memset wait stats");
+    }
+    return wait_stats_;
+  }
+  // (spun nanoseconds, number of waits) accumulated by wait_flag since the last reset; synchronises the device
+  std::vector<int64_t> wait_stats(bool reset) {
+    c10::cuda::CUDAGuard g(device_);
+    unsigned long long h[2] = {0, 0};
+    ck(cudaDeviceSynchronize(), "sync");
+    ck(cudaMemcpy(h, wait_stats_dev(), 16, cudaMemcpyDeviceToHost), "memcpy wait stats");
+    if (reset) ck(cudaMemset(wait_stats_, 0, 16), "memset wait stats");
+    return {(int64_t)h[0], (int64_t)h[1]};
+  }
   void alltoall(int64_t off_send, int64_t off_recv, int64_t chunk_bytes, int64_t epoch) {
     c10::cuda::CUDAGuard g(device_);
     auto b = bases();
@@ -190,6 +220,7 @@ class SymmHeap {
   std::vector<void*> peers_;
   void* peer_table_dev_ = nullptr;
   void* counter_ = nullptr;
+  void* wait_stats_ = nullptr;
 };
 
 void bind_symm(pybind11::module_& m) {
@@ -229,7 +260,10 @@ void bind_symm(pybind11::module_& m) {
       .def("reduce_slots", &SymmHeap::reduce_slots)
       .def("allgather", &SymmHeap::allgather)
       .def("a2av", &SymmHeap::a2av)
-      .def("alltoall", &SymmHeap::alltoall);
+      .def("alltoall", &SymmHeap::alltoall)
+      .def("signal_flag", &SymmHeap::signal_flag)
+      .def("wait_flag", &SymmHeap::wait_flag, pybind11::arg("flag_off"), pybind11::arg("value"), pybind11::arg("timeout_s") = 300.0)
+      .def("wait_stats", &SymmHeap::wait_stats, pybind11::arg("reset") = true);
 }
 
 }  // namespace runtime

@@ -95,6 +95,13 @@ def _allreduce_tensors(tensors, group, scale):
 
 def _allreduce_flat(flat, group):
     """In-place all-reduce of one contiguous buffer: peer-memory kernel on NVSwitch when available, else NCCL/gloo."""
+    from .. import comm_timer as CT
+
+    with CT.region("grad_all_reduce"):
+        _allreduce_flat_impl(flat, group)
+
+
+def _allreduce_flat_impl(flat, group):
     if flat.is_cuda and flat.dtype in (torch.bfloat16, torch.float16, torch.float32):
         from ...framework.flags import flag
 
@@ -198,10 +205,14 @@ def distributed_model(model, hcg, strategy):
             broadcast_sharding_parameters(model, hcg)
         broadcast_dp_parameters(model, hcg)
         mpu.register_sequence_parallel_allreduce_hooks(model)
-        if getattr(model, "_num_virtual", 1) > 1:
-            from .pipeline import PipelineParallelWithInterleave
+        from .pipeline import PipelineParallelWithInterleave, PipelineParallelWithInterleaveFthenB, PipelineParallelZeroBubble
 
-            return PipelineParallelWithInterleave(model, hcg, strategy)
+        mode = str(strategy.pipeline_configs.get("schedule_mode", "1F1B") or "1F1B").upper().replace("-", "")
+        if getattr(model, "_num_virtual", 1) > 1:
+            cls = PipelineParallelWithInterleaveFthenB if mode == "FTHENB" else PipelineParallelWithInterleave
+            return cls(model, hcg, strategy)
+        if mode.startswith("ZB"):
+            return PipelineParallelZeroBubble(model, hcg, strategy)
         return PipelineParallel(model, hcg, strategy)
     if hcg.get_model_parallel_world_size() > 1:
         return TensorParallel(model, hcg, strategy)
@@ -400,11 +411,13 @@ class HybridParallelOptimizer:
 
     @torch.no_grad()
     def step(self):
-        if not getattr(self, "_grads_synced_externally", False):
+        if not self.__dict__.get("_grads_synced_externally", False):
             self._sync_grads()
+        self.__dict__["_grads_synced_externally"] = False
         self._inner_opt.step()
 
     def clear_grad(self, set_to_zero=True):
+        self.__dict__["_grads_synced_externally"] = False
         self._inner_opt.clear_grad(set_to_zero)
 
     clear_gradients = clear_grad
@@ -423,9 +436,18 @@ def distributed_scaler(scaler, hcg):
     orig_unscale = scaler.unscale_
 
     def unscale_(optimizer):
+        # The dp / sep / sharding gradient reduction lives in HybridParallelOptimizer.step(), which GradScaler.step() skips on an
+        # overflow: run it BEFORE the found_inf decision, so (a) every replica enters the collective on every step and (b) an
+        # inf / nan produced by one replica reaches all of them through the reduced gradients.  The check group (mp / pp / sharding)
+        # then agrees on the flag; data-parallel replicas already agree because they now hold identical gradients.
+        if isinstance(optimizer, HybridParallelOptimizer) and not optimizer.__dict__.get("_grads_synced_externally", False):
+            optimizer._sync_grads()
+            optimizer.__dict__["_grads_synced_externally"] = True
         orig_unscale(getattr(optimizer, "_inner_opt", optimizer))
         if scaler._found_inf is not None and hcg is not None and env.get_world_size() > 1:
             dist.all_reduce(scaler._found_inf, op=dist.ReduceOp.MAX, group=_pg(hcg.get_check_parallel_group()))
+            if hcg.get_data_parallel_world_size() > 1:     # belt and braces: low-precision sums can turn one replica's nan into a finite value
+                dist.all_reduce(scaler._found_inf, op=dist.ReduceOp.MAX, group=_pg(hcg.get_data_parallel_group()))
 
     scaler.unscale_ = unscale_
     return scaler

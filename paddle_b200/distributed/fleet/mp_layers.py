@@ -66,8 +66,11 @@ class _Identity(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         if _nranks(ctx.group) > 1:
+            from .. import comm_timer as CT
+
             g = g.contiguous()
-            dist.all_reduce(g, group=_pg(ctx.group))
+            with CT.region("mp_all_reduce"):
+                dist.all_reduce(g, group=_pg(ctx.group))
         return g, None
 
 
@@ -77,8 +80,11 @@ class _AllReduce(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, group):
         if _nranks(group) > 1:
+            from .. import comm_timer as CT
+
             x = x.contiguous().clone()
-            dist.all_reduce(x, group=_pg(group))
+            with CT.region("mp_all_reduce"):
+                dist.all_reduce(x, group=_pg(group))
         return x
 
     @staticmethod
@@ -125,8 +131,11 @@ class _Split(torch.autograd.Function):
 
 def _all_gather_dim0(x, group):
     n = _nranks(group)
+    from .. import comm_timer as CT
+
     out = torch.empty((x.shape[0] * n, *x.shape[1:]), dtype=x.dtype, device=x.device)
-    dist.all_gather_into_tensor(out, x.contiguous(), group=_pg(group))
+    with CT.region("mp_all_gather"):
+        dist.all_gather_into_tensor(out, x.contiguous(), group=_pg(group))
     return out
 
 
@@ -139,7 +148,10 @@ def _reduce_scatter_dim0(x, group):
         dist.all_reduce(y, group=_pg(group))
         out.copy_(y.chunk(n, 0)[_rank(group)])
     else:
-        dist.reduce_scatter_tensor(out, x, group=_pg(group))
+        from .. import comm_timer as CT
+
+        with CT.region("mp_reduce_scatter"):
+            dist.reduce_scatter_tensor(out, x, group=_pg(group))
     return out
 
 

@@ -2,12 +2,25 @@
 (LayerDesc, SharedLayerDesc, PipelineLayer, segment methods) and pipeline_parallel.py (PipelineParallel 1F1B /
 FThenB / interleaved-VPP entry points, train_batch / eval_batch), pp_utils/p2p_communication.py.
 
-Stage-to-stage activations travel over NCCL p2p (batched isend/irecv on a dedicated stream so they overlap compute);
-shapes/dtypes are exchanged once and cached.
+One engine runs every schedule: `pp_schedule.build` turns (schedule_mode, stages, chunks, micro-batches) into per-stage op lists
+(F / B / W), the engine executes its own list and moves activations through a transport:
+
+* CUDA + symmetric peer heap: a **mailbox** per hop (csrc/comm/p2p_collectives.cu:signal_flag_kernel / wait_flag_kernel): the producer
+  copies the tensor into a slot of the consumer's heap with the copy engine on a side stream (no SM work, the compute stream never
+  waits on a send), then publishes the slot with a release store; the consumer's compute stream runs a one-thread wait kernel before
+  the first kernel that reads the slot and then uses the slot in place.  The wait kernel accounts the nanoseconds it spun, which is
+  the exposed pipeline wait per step reported by bench.py.
+* otherwise (NCCL without peer memory, gloo in the CPU tests): one communicator per directed hop and direction, asynchronous isend,
+  irecv at the point of use - the role of the reference's overlap_p2p_comm (pp_utils/p2p_communication.py:837-864).
+
+Zero-bubble mode (schedule_mode="ZBH1") splits the backward: B computes input gradients only and parks the weight-gradient GEMMs
+(kernels/wgrad.py); W ops run them where the schedule has gaps.
 """
 from __future__ import annotations
 
+import contextlib
 import math
+import os
 import re
 
 import torch
@@ -15,6 +28,7 @@ import torch.distributed as dist
 
 from ...nn.layer import Layer
 from ...tensor import Tensor
+from . import pp_schedule
 from . import topology as topo
 from .recompute import recompute as _recompute
 
@@ -203,74 +217,132 @@ class PipelineLayer(Layer):
 
 
 # ---------------------------------------------------------------------------------------------------- p2p
-class _P2P:
-    """Stage <-> stage tensor transport with cached meta."""
+_DT = [torch.float32, torch.float16, torch.bfloat16, torch.int64, torch.int32, torch.float64, torch.bool, torch.uint8]
 
-    def __init__(self, hcg):
+
+class _GroupTransport:
+    """torch.distributed transport (NCCL or gloo): one communicator per directed hop and kind, so every channel is a FIFO with a
+    single sender and a single receiver - asynchronous sends can never block a receive of the opposite direction."""
+
+    name = "torch.distributed"
+
+    def __init__(self, hcg, ring):
+        from ..collective import new_group
+
         self.hcg = hcg
-        self.group = hcg.get_pipe_parallel_group().pg
-        self.next_rank, self.prev_rank = hcg.next_rank, hcg.prev_rank
-        self.fwd_meta = None   # (shape, dtype) of activations received from prev
-        self.bwd_meta = None   # (shape, dtype) of grads received from next
-        self.dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() and dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+        pipe = hcg.get_pipe_parallel_group()
+        self.pipe_pg = pipe.pg
+        self.my_ranks = list(pipe.ranks)
+        self.stage = hcg.get_stage_id()
+        S = len(self.my_ranks)
+        self.S = S
+        self.chan = {}
+        backend = dist.get_backend(self.pipe_pg)
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        hops = [(a, a + 1) for a in range(S - 1)] + ([(S - 1, 0)] if ring and S > 1 else [])
+        if S == 2 and ring:
+            hops = [(0, 1), (1, 0)]
+        # every process creates every communicator in the same order (new_group is collective over the world)
+        for pp_ranks in hcg.topology().get_comm_list("pipe"):
+            for a, b in hops:
+                for kind in ("f", "b"):
+                    ranks = sorted({pp_ranks[a], pp_ranks[b]})
+                    g = new_group(ranks)
+                    if list(pp_ranks) == self.my_ranks and self.stage in (a, b):
+                        self.chan[(a, b, kind)] = g.pg
+        self.pending = []
 
-    _DT = [torch.float32, torch.float16, torch.bfloat16, torch.int64, torch.int32, torch.float64, torch.bool, torch.uint8]
+    def _pg(self, src, dst, kind):
+        # forward traffic of hop (a -> b) uses channel (a, b, 'f'); backward traffic (b -> a) uses (a, b, 'b')
+        return self.chan[(src, dst, "f")] if kind == "f" else self.chan[(dst, src, "b")]
 
-    def _send_meta(self, t, dst):
-        meta = torch.zeros(10, dtype=torch.int64, device=self.dev)
-        meta[0] = t.dim()
-        meta[1] = self._DT.index(t.dtype)
-        for i, s in enumerate(t.shape):
-            meta[2 + i] = s
-        dist.send(meta, dst, group=self.group)
+    def send(self, kind, key, t, dst_stage, step):
+        pg = self._pg(self.stage, dst_stage, kind)
+        t = t.contiguous()
+        w = dist.isend(t, self.my_ranks[dst_stage], group=pg)
+        self.pending.append((w, t))
 
-    def _recv_meta(self, src):
-        meta = torch.zeros(10, dtype=torch.int64, device=self.dev)
-        dist.recv(meta, src, group=self.group)
-        m = meta.tolist()
-        return tuple(m[2:2 + m[0]]), self._DT[m[1]]
+    def recv(self, kind, key, shape, dtype, src_stage, step):
+        pg = self._pg(src_stage, self.stage, kind)
+        from .. import comm_timer as CT
 
-    def send_forward(self, t, first_time):
-        if first_time:
-            self._send_meta(t, self.next_rank)
-        dist.send(t.contiguous(), self.next_rank, group=self.group)
-
-    def recv_forward(self):
-        if self.fwd_meta is None:
-            self.fwd_meta = self._recv_meta(self.prev_rank)
-        shape, dt = self.fwd_meta
-        t = torch.empty(shape, dtype=dt, device=self.dev)
-        dist.recv(t, self.prev_rank, group=self.group)
-        return t
-
-    def send_backward(self, g):
-        dist.send(g.contiguous(), self.prev_rank, group=self.group)
-
-    def recv_backward(self, like):
-        g = torch.empty_like(like)
-        dist.recv(g, self.next_rank, group=self.group)
-        return g
-
-    def send_forward_recv_backward(self, t, first_time):
-        if first_time:
-            self._send_meta(t, self.next_rank)
-        g = torch.empty_like(t)
-        ops = [dist.P2POp(dist.isend, t.contiguous(), self.next_rank, self.group), dist.P2POp(dist.irecv, g, self.next_rank, self.group)]
-        for w in dist.batch_isend_irecv(ops):
+        buf = torch.empty(shape, dtype=dtype, device=self.dev)
+        with CT.region("pp_recv_wait"):
+            w = dist.irecv(buf, self.my_ranks[src_stage], group=pg)
             w.wait()
-        return g
+        return buf
 
-    def send_backward_recv_forward(self, g):
-        shape, dt = self.fwd_meta
-        t = torch.empty(shape, dtype=dt, device=self.dev)
-        ops = [dist.P2POp(dist.isend, g.contiguous(), self.prev_rank, self.group), dist.P2POp(dist.irecv, t, self.prev_rank, self.group)]
-        for w in dist.batch_isend_irecv(ops):
+    def end_step(self):
+        for w, _ in self.pending:
             w.wait()
-        return t
+        self.pending.clear()
+
+    def exposed_wait(self, reset=True):
+        return None
+
+
+class _MailboxTransport:
+    """Peer-memory mailbox transport (see the module docstring)."""
+
+    name = "mailbox"
+
+    def __init__(self, hcg, ctx, slot_bytes, n_keys):
+        self.hcg, self.ctx = hcg, ctx
+        self.stage = hcg.get_stage_id()
+        self.slot_bytes = (int(slot_bytes) + 1023) // 1024 * 1024
+        self.n_keys = n_keys                        # slots per (kind, parity)
+        total = 2 * 2 * n_keys
+        self.data, self.data_off = ctx.buffer("pp_mailbox", (total * self.slot_bytes,), torch.uint8)
+        self.flags, self.flag_off = ctx.buffer("pp_mailbox_flags", (total,), torch.int32)
+        self.side = torch.cuda.Stream()
+        self.dev = self.data.device
+        self._peer_views = {}
+
+    @staticmethod
+    def heap_bytes(slot_bytes, n_keys):
+        slot = (int(slot_bytes) + 1023) // 1024 * 1024
+        return 2 * 2 * n_keys * slot + (8 << 20)
+
+    def _index(self, kind, key, step):
+        return ((0 if kind == "f" else 1) * 2 + (step & 1)) * self.n_keys + key
+
+    def send(self, kind, key, t, dst_stage, step):
+        idx = self._index(kind, key, step)
+        t = t.contiguous()
+        nbytes = t.numel() * t.element_size()
+        assert nbytes <= self.slot_bytes, "pipeline message larger than the mailbox slot"
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        dst = self._peer_views.get((dst_stage, idx))
+        if dst is None:
+            dst = self._peer_views[(dst_stage, idx)] = self.ctx.heap.tensor(self.data_off + idx * self.slot_bytes, [self.slot_bytes], torch.uint8, dst_stage)
+        with torch.cuda.stream(self.side):
+            dst[:nbytes].copy_(t.view(-1).view(torch.uint8), non_blocking=True)     # copy engine over NVLink into the consumer's slot
+            self.ctx.heap.signal_flag(dst_stage, self.flag_off + idx * 4, step)
+        t.record_stream(self.side)
+
+    def recv(self, kind, key, shape, dtype, src_stage, step):
+        idx = self._index(kind, key, step)
+        self.ctx.heap.wait_flag(self.flag_off + idx * 4, step, float(os.environ.get("B200_PP_WAIT_TIMEOUT_S", "600")))
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * torch.empty(0, dtype=dtype).element_size()
+        lo = idx * self.slot_bytes
+        return self.data[lo:lo + nbytes].view(dtype).view(tuple(shape))     # used in place: the slot is not rewritten before step + 2
+
+    def end_step(self):
+        torch.cuda.current_stream().wait_stream(self.side)
+
+    def exposed_wait(self, reset=True):
+        ns, n = self.ctx.heap.wait_stats(reset)
+        return {"wait_ms": ns / 1e6, "waits": int(n)}
 
 
 class PipelineParallel(Layer):
-    """1F1B pipeline engine. Parity: fleet/meta_parallel/pipeline_parallel.py:PipelineParallel."""
+    """Pipeline engine (1F1B / FThenB / interleaved VPP / zero-bubble H1). Parity: fleet/meta_parallel/pipeline_parallel.py."""
+
+    _default_mode = "1F1B"
 
     def __init__(self, layers, hcg, strategy):
         super().__init__()
@@ -285,10 +357,20 @@ class PipelineParallel(Layer):
         self.stage_id = hcg.get_stage_id()
         self.is_first = self.stage_id == 0
         self.is_last = self.stage_id == self.num_stages - 1
-        self._p2p = _P2P(hcg)
-        self._sent_meta = False
+        self.V = int(getattr(layers, "_num_virtual", 1) or 1)
+        self.G = self.V * self.num_stages
+        mode = pc.get("schedule_mode", None) or self._default_mode
+        if self.V > 1 and str(mode).upper() == "1F1B":
+            mode = self._default_mode if self._default_mode != "1F1B" else "VPP"
+        self.schedule_mode = mode
+        self.zb_pending = pc.get("zero_bubble_max_pending", None)
+        self._fallback = _GroupTransport(hcg, ring=self.V > 1) if dist.is_initialized() and self.num_stages > 1 else None
+        self._transport = None
+        self._meta = None
+        self._step = 0
+        self._ops_cache = {}
         self.total_loss = None
-        self.schedule_mode = pc.get("schedule_mode", "1F1B")
+        self._user_hooks = {}
 
     def parameters(self, include_sublayers=True):
         return self._layers.parameters(include_sublayers)
@@ -305,7 +387,7 @@ class PipelineParallel(Layer):
     def forward(self, *a, **k):
         return self._layers(*a, **k)
 
-    # ---- micro-batch helpers ---------------------------------------------------------------------------------
+    # ---- helpers -------------------------------------------------------------------------------------------------
     def _micro(self, data, i):
         if data is None:
             return None
@@ -314,92 +396,117 @@ class PipelineParallel(Layer):
             return type(data)(self._micro(d, i) for d in data)
         return data[lo:hi]
 
-    def _forward_step(self, inp, labels_mb, scale):
-        if not self.is_first:
-            inp = _w(inp.requires_grad_(True))
-        out = self._layers(inp)
-        if self.is_last:
-            assert self._layers._loss_fn is not None, "loss_fn is required on the last stage"
-            loss = self._layers._loss_fn(out, labels_mb)
-            loss = loss * scale
-            self.total_loss = loss.detach() if self.total_loss is None else self.total_loss + loss.detach()
-            return loss
-        return out
+    def _ops(self, M):
+        key = (self.schedule_mode, M)
+        ops = self._ops_cache.get(key)
+        if ops is None:
+            kw = {}
+            if str(self.schedule_mode).upper().startswith("ZB") and self.zb_pending is not None:
+                kw["max_pending_w"] = int(self.zb_pending)
+            all_ops = pp_schedule.build(self.schedule_mode, self.num_stages, M, self.V, **kw)
+            pp_schedule.simulate(all_ops, self.num_stages, self.V, merged_w=not any(o[0] == "W" for o in all_ops[0]))   # raises on a deadlock
+            ops = self._ops_cache[key] = all_ops[self.stage_id]
+        return ops
 
-    def _backward_step(self, inp, out, out_grad, scaler=None):
-        if self.is_last:
-            (scaler.scale(out) if scaler is not None else out).backward()
-        else:
-            torch.autograd.backward(_raw(out), grad_tensors=_raw(out_grad))
-        if self.is_first:
-            return None
-        return torch.Tensor.grad.__get__(inp)
+    def _learn_meta(self, inputs):
+        """Shape / dtype of the tensor that travels between stages, learnt once: global stage 0 runs its first chunk on one micro-batch
+        without autograd and broadcasts the result's meta over the pipe group; the mailbox is sized from it."""
+        if self._meta is not None:
+            return
+        info = [None]
+        if self.stage_id == 0:
+            with torch.no_grad():
+                o = self._layers(self._micro(inputs, 0), chunk_id=0)
+            info = [(tuple(o.shape), _DT.index(_raw(o).dtype))]
+            del o
+        pg = self._hcg.get_pipe_parallel_group().pg
+        dist.broadcast_object_list(info, src=self._hcg.get_rank_from_stage(0), group=pg)
+        self._meta = (tuple(info[0][0]), _DT[info[0][1]])
+        self._transport = self._fallback
+        from ...framework.flags import flag
+        from ...parallel import symm
 
-    # ---- schedule ------------------------------------------------------------------------------------------------
+        dev_ok = torch.cuda.is_available() and dist.get_backend(pg) == "nccl"
+        if dev_ok and flag("FLAGS_b200_pp_mailbox", True) and symm.available():
+            shape, dt = self._meta
+            nbytes = torch.empty(0, dtype=dt).element_size()
+            for d in shape:
+                nbytes *= int(d)
+            n_keys = self.V * self.accumulate_steps
+            ctx = symm.context_for(self._hcg.get_pipe_parallel_group(), heap_bytes=_MailboxTransport.heap_bytes(nbytes, n_keys))
+            if ctx is not None and ctx.heap.size() >= _MailboxTransport.heap_bytes(nbytes, n_keys):
+                self._transport = _MailboxTransport(self._hcg, ctx, nbytes, n_keys)
+
+    def transport_name(self):
+        return self._transport.name if self._transport is not None else None
+
+    def exposed_wait(self, reset=True):
+        """Exposed pipeline wait accounted on the device by the mailbox wait kernels since the last reset (None for NCCL / gloo)."""
+        return self._transport.exposed_wait(reset) if self._transport is not None else None
+
+    # ---- the engine ----------------------------------------------------------------------------------------------
     def forward_backward_pipeline(self, data, scaler=None):
+        from ...kernels import wgrad as WG
+
         inputs, labels = data if isinstance(data, (tuple, list)) and len(data) == 2 else (data, None)
-        M = self.accumulate_steps
+        M, S, V, G, s = self.accumulate_steps, self.num_stages, self.V, self.G, self.stage_id
+        self._learn_meta(inputs)
+        ops = self._ops(M)
+        zb = any(o[0] == "W" for o in ops)
+        self._step += 1
+        step, tr, meta = self._step, self._transport, self._meta
         scale = 1.0 / M
         self.total_loss = None
-        p2p = self._p2p
-        warm = min(self.num_stages - self.stage_id - 1, M)
-        steady = M - warm
-        in_q, out_q = [], []
-        fwd_i = 0
-
-        def first_input(i):
-            return self._micro(inputs, i) if self.is_first else None
-
-        def fwd(inp_recv):
-            nonlocal fwd_i
-            i = fwd_i
-            fwd_i += 1
-            x = first_input(i) if self.is_first else inp_recv
-            out = self._forward_step(x, self._micro(labels, i) if self.is_last else None, scale)
-            return x, out
-
-        for _ in range(warm):
-            r = None if self.is_first else p2p.recv_forward()
-            x, out = fwd(r)
-            if not self.is_last:
-                p2p.send_forward(_raw(out).detach(), not self._sent_meta)
-                self._sent_meta = True
-            in_q.append(x)
-            out_q.append(out)
-        r = None
-        if steady > 0 and not self.is_first:
-            r = p2p.recv_forward()
-        for k in range(steady):
-            last_iter = k == steady - 1
-            x, out = fwd(r)
-            if self.is_last:
-                og = None
-            else:
-                og = p2p.send_forward_recv_backward(_raw(out).detach(), not self._sent_meta)
-                self._sent_meta = True
-            in_q.append(x)
-            out_q.append(out)
-            x0, o0 = in_q.pop(0), out_q.pop(0)
-            ig = self._backward_step(x0, o0, og, scaler)
-            if not self.is_first:
-                if last_iter:
-                    p2p.send_backward(_raw(ig))
-                    r = None
-                else:
-                    r = p2p.send_backward_recv_forward(_raw(ig))
-        for _ in range(warm):
-            x0, o0 = in_q.pop(0), out_q.pop(0)
-            og = None if self.is_last else p2p.recv_backward(_raw(o0).detach())
-            ig = self._backward_step(x0, o0, og, scaler)
-            if not self.is_first:
-                p2p.send_backward(_raw(ig))
+        acts, wq = {}, {}
+        nxt, prv = (s + 1) % S, (s - 1) % S
+        plan = WG.planning() if zb else contextlib.nullcontext()
+        with plan:
+            for kind, v, m in ops:
+                g = v * S + s
+                key = v * M + m
+                if kind == "F":
+                    if g == 0:
+                        leaf, x = None, self._micro(inputs, m)
+                    else:
+                        # the message of global stage g-1 was sent under the key of ITS chunk (v for s > 0, v-1 across the ring)
+                        src_key = (v if s > 0 else v - 1) * M + m
+                        leaf = tr.recv("f", src_key, meta[0], meta[1], prv, step).detach().requires_grad_(True)
+                        x = _w(leaf)
+                    out = self._layers(x, chunk_id=v)
+                    if g == G - 1:
+                        assert self._layers._loss_fn is not None, "loss_fn is required on the last stage"
+                        loss = self._layers._loss_fn(out, self._micro(labels, m)) * scale
+                        self.total_loss = loss.detach() if self.total_loss is None else self.total_loss + loss.detach()
+                        acts[key] = (leaf, loss)
+                    else:
+                        acts[key] = (leaf, out)
+                        tr.send("f", key, _raw(out).detach(), nxt, step)
+                elif kind == "B":
+                    leaf, out = acts.pop(key)
+                    q = wq.setdefault(key, []) if zb else None
+                    with (WG.deferring(q) if zb else contextlib.nullcontext()):
+                        if g == G - 1:
+                            (scaler.scale(out) if scaler is not None else out).backward()
+                        else:
+                            og = tr.recv("b", key, tuple(_raw(out).shape), _raw(out).dtype, nxt, step)
+                            torch.autograd.backward(_raw(out), grad_tensors=og)
+                    if g != 0:
+                        dst_key = (v if s > 0 else v - 1) * M + m     # keyed like the forward message it answers
+                        tr.send("b", dst_key, torch.Tensor.grad.__get__(leaf), prv, step)
+                    del leaf, out
+                else:   # W
+                    WG.flush(wq.pop(key, []))
+        for q in wq.values():
+            WG.flush(q)
+        tr.end_step()
         self._layers.allreduce_shared_weight_gradients()
         return self._broadcast_loss()
 
     def _broadcast_loss(self):
         pg = self._hcg.get_pipe_parallel_group().pg
-        dev = self._p2p.dev
-        loss = self.total_loss.float().reshape(1).to(dev) if self.is_last else torch.zeros(1, dtype=torch.float32, device=dev)
+        dev = self._transport.dev if self._transport is not None else torch.device("cpu")
+        last = self.stage_id == self.num_stages - 1
+        loss = self.total_loss.float().reshape(1).to(dev) if last else torch.zeros(1, dtype=torch.float32, device=dev)
         src = self._hcg.get_rank_from_stage(self.num_stages - 1)
         dist.broadcast(loss, src=src, group=pg)
         return _w(loss.reshape([]))
@@ -422,9 +529,8 @@ class PipelineParallel(Layer):
         pass
 
     def get_static_scheduler(self):
-        M, S, r = self.accumulate_steps, self.num_stages, self.stage_id
-        warm = min(S - r - 1, M)
-        return ";".join([f"f{i}" for i in range(warm)] + [f"f{warm + i};b{i}" for i in range(M - warm)] + [f"b{M - warm + i}" for i in range(warm)])
+        """The op list of this stage as text, e.g. 'f0;f1;b0;f2;b1;w0;...' (chunk suffix '@v' with virtual stages)."""
+        return ";".join(f"{k.lower()}{m}" + (f"@{v}" if self.V > 1 else "") for k, v, m in self._ops(self.accumulate_steps))
 
     def train_batch(self, data, optimizer, lr_scheduler=None, scaler=None, loss_fn_idx=0, return_micro_batch_loss=False):
         self._layers.train()
@@ -443,125 +549,55 @@ class PipelineParallel(Layer):
     def eval_batch(self, data, compute_loss=False, loss_fn_idx=0):
         self._layers.eval()
         inputs, labels = data if isinstance(data, (tuple, list)) and len(data) == 2 else (data, None)
-        p2p = self._p2p
+        self._learn_meta(inputs)
+        M, S, V, G, s = self.accumulate_steps, self.num_stages, self.V, self.G, self.stage_id
+        self._step += 1
+        step, tr, meta = self._step, self._transport, self._meta
+        nxt, prv = (s + 1) % S, (s - 1) % S
         outs = []
         self.total_loss = None
-        for i in range(self.accumulate_steps):
-            x = self._micro(inputs, i) if self.is_first else _w(p2p.recv_forward())
-            out = self._layers(x)
-            if self.is_last:
+        for kind, v, m in pp_schedule.build("FThenB", S, M, V)[s]:
+            if kind != "F":
+                continue
+            g, key = v * S + s, v * M + m
+            if g == 0:
+                x = self._micro(inputs, m)
+            else:
+                x = _w(tr.recv("f", (v if s > 0 else v - 1) * M + m, meta[0], meta[1], prv, step))
+            out = self._layers(x, chunk_id=v)
+            if g == G - 1:
                 if compute_loss:
-                    l = self._layers._loss_fn(out, self._micro(labels, i)) / self.accumulate_steps
+                    l = self._layers._loss_fn(out, self._micro(labels, m)) / M
                     self.total_loss = l if self.total_loss is None else self.total_loss + l
                 outs.append(out)
             else:
-                p2p.send_forward(_raw(out), not self._sent_meta)
-                self._sent_meta = True
+                tr.send("f", key, _raw(out), nxt, step)
+        tr.end_step()
         if compute_loss:
             return self._broadcast_loss()
         return outs
 
 
 class PipelineParallelWithInterleave(PipelineParallel):
-    """Virtual-pipeline (interleaved) engine. Parity: pipeline_parallel.py:PipelineParallelWithInterleave.
+    """Virtual-pipeline (interleaved 1F1B) engine. Parity: pipeline_parallel.py:PipelineParallelWithInterleave.
+    Every rank owns V model chunks (global stage g = v * pp + rank); micro-batches advance in groups of pp through the chunks, which
+    cuts the ramp (bubble) to 1/V of the plain schedule at the price of V times as many hops (see pp_schedule._interleaved)."""
 
-    Every rank owns V model chunks (global stage g = v * pp + rank).  The schedule is the lock-step diagonal: at forward tick
-    t global stage g runs micro-batch t - g, so a rank works on up to V chunks per tick and the pipeline fills after pp - 1
-    ticks of ONE CHUNK each — the ramp (bubble) is 1/V of the plain schedule.  Each tick ends with exactly one batched
-    isend/irecv per rank (sends to the next rank, receives what it needs for the next tick), which keeps the ring
-    (last rank -> first rank for the next chunk) deadlock-free.  Backward mirrors it.  Activations of all micro-batches stay
-    alive between the two phases (F-then-B)."""
+    _default_mode = "VPP"
 
     def __init__(self, layers, hcg, strategy):
         super().__init__(layers, hcg, strategy)
-        self.V = layers._num_virtual
         self.pp = self.num_stages
-        self.G = self.V * self.pp
 
-    def _exchange(self, sends, recv_shapes, dst, src):
-        """One batched p2p round: `sends` to rank dst, receive len(recv_shapes) tensors from rank src (same order on both sides)."""
-        p2p = self._p2p
-        bufs = [torch.empty(shape, dtype=dt, device=p2p.dev) for shape, dt in recv_shapes]
-        ops = [dist.P2POp(dist.isend, t.contiguous(), dst, p2p.group) for t in sends] + [dist.P2POp(dist.irecv, b, src, p2p.group) for b in bufs]
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        return bufs
 
-    def forward_backward_pipeline(self, data, scaler=None):
-        inputs, labels = data if isinstance(data, (tuple, list)) and len(data) == 2 else (data, None)
-        M, V, pp, G, r = self.accumulate_steps, self.V, self.pp, self.G, self.stage_id
-        p2p = self._p2p
-        nxt, prv = p2p.next_rank, p2p.prev_rank
-        scale = 1.0 / M
-        self.total_loss = None
-        acts = {}
+class PipelineParallelWithInterleaveFthenB(PipelineParallelWithInterleave):
+    """All forwards of all chunks, then all backwards. Parity: pipeline_parallel.py:2256 PipelineParallelWithInterleaveFthenB."""
 
-        def work(t, backward=False):
-            out = []
-            for v in (range(V - 1, -1, -1) if backward else range(V)):
-                g = r + v * pp
-                m = t - ((G - 1 - g) if backward else g)
-                if 0 <= m < M:
-                    out.append((v, m))
-            return out
+    _default_mode = "FThenB"
 
-        # ---- activation shape between stages: learnt once (rank 0 runs its first chunk on one micro-batch without autograd) ----
-        if getattr(self, "_meta", None) is None:
-            info = [None]
-            if r == 0:
-                with torch.no_grad():
-                    o = self._layers(self._micro(inputs, 0), chunk_id=0)
-                info = [(tuple(o.shape), str(o.dtype).split(".")[-1])]
-            dist.broadcast_object_list(info, src=self._hcg.get_rank_from_stage(0), group=p2p.group)
-            self._meta = (tuple(info[0][0]), getattr(torch, info[0][1]))
-        meta = self._meta
-        # ---- forward ticks ---------------------------------------------------------------------------------------------
-        recv_next = {}
-        for t in range(G + M - 1):
-            sends = []
-            for v, m in work(t):
-                g = r + v * pp
-                if g == 0:
-                    leaf = None
-                    x = self._micro(inputs, m)
-                else:
-                    leaf = recv_next.pop((v, m)).requires_grad_(True)    # the received buffer is the autograd leaf of this chunk
-                    x = _w(leaf)
-                out = self._layers(x, chunk_id=v)
-                if g == G - 1:
-                    loss = self._layers._loss_fn(out, self._micro(labels, m)) * scale
-                    self.total_loss = loss.detach() if self.total_loss is None else self.total_loss + loss.detach()
-                    acts[(v, m)] = (leaf, loss)
-                else:
-                    acts[(v, m)] = (leaf, out)
-                    sends.append(_raw(out).detach())
-            # what arrives for tick t+1: my (v, m) at t+1 with g != 0 (sent by the previous rank at this tick, same order)
-            want = [(v, m) for v, m in work(t + 1) if r + v * pp != 0] if t + 1 < G + M - 1 else []
-            got = self._exchange(sends, [meta] * len(want), nxt, prv)
-            for key, buf in zip(want, got):
-                recv_next[key] = buf
-        # ---- backward ticks ------------------------------------------------------------------------------------------
-        grad_next = {}
-        for t in range(G + M - 1):
-            sends = []
-            for v, m in work(t, backward=True):
-                g = r + v * pp
-                x, out = acts.pop((v, m))
-                if g == G - 1:
-                    (scaler.scale(out) if scaler is not None else out).backward()
-                else:
-                    torch.autograd.backward(_raw(out), grad_tensors=grad_next.pop((v, m)))
-                if g != 0:
-                    sends.append(x.grad)
-            want = [(v, m) for v, m in work(t + 1, backward=True) if r + v * pp != G - 1] if t + 1 < G + M - 1 else []
-            got = self._exchange(sends, [meta] * len(want), prv, nxt)
-            for key, buf in zip(want, got):
-                grad_next[key] = buf
-        self._layers.allreduce_shared_weight_gradients()
-        return self._broadcast_loss()
 
-    def _broadcast_loss(self):
-        # the loss lives on the last rank (global stage G - 1 = chunk V - 1 of the last rank)
-        self.is_last = self.stage_id == self.num_stages - 1
-        return super()._broadcast_loss()
+class PipelineParallelZeroBubble(PipelineParallel):
+    """ZB-H1: input-gradient (B) and weight-gradient (W) passes scheduled separately. Parity (role):
+    passes/pipeline_scheduler_pass/pipeline_zero_bubble.py:62."""
+
+    _default_mode = "ZBH1"

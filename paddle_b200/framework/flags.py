@@ -11,6 +11,8 @@ _FLAGS = {
     "FLAGS_b200_p2p_collectives": True,    # fused compute+collective kernels over peer memory
     "FLAGS_b200_gemm_backend": "tcgen05",  # "tcgen05" | "cublas"
     "FLAGS_b200_fp8_linear": False,        # nn.Linear / F.linear run as fp8 tcgen05 GEMMs (per-tensor scaling, e4m3 fwd / e5m2 grads)
+    "FLAGS_b200_pp_mailbox": True,         # pipeline p2p through the peer-memory mailbox (copy engine + flag) instead of NCCL send/recv
+    "FLAGS_b200_fused_wgrad": True,        # weight-gradient GEMMs accumulate straight into the flat gradient arena (kernels/wgrad.py)
     "FLAGS_b200_flash_attention": True,    # tcgen05 flash-attention forward (csrc/attention_sm100.cu)
     "FLAGS_embedding_deterministic": 0,
     "FLAGS_eager_delete_tensor_gb": 0.0,

@@ -61,11 +61,12 @@ def gemm(a, b, bias=None, a_is_km=False, b_is_nk=False, epilogue=0, out=None, ou
 
 class _Linear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, sink=None):
         x2 = _rowmajor2d(x)
         ctx.save_for_backward(x2, w)
         ctx.x_shape = x.shape
         ctx.has_b = b is not None
+        ctx.sink = sink
         # allocate the result in its final shape: a view created inside a custom Function could not be modified in
         # place afterwards (the packed rotary embedding rotates q/k inside the fused QKV output)
         out = torch.empty((*x.shape[:-1], w.shape[1]), dtype=x.dtype, device=x.device)
@@ -82,14 +83,42 @@ class _Linear(torch.autograd.Function):
             dx = ext().gemm(dy2, w, None, False, True, 0, None, None).reshape(ctx.x_shape)
         if ctx.needs_input_grad[1]:
             # dW[K,N] = x^T[K,M] @ dy[M,N] : A = x stored [M,K] -> MN-major A ; B = dy stored [M,N] -> MN-major B
-            dw = ext().gemm(x2, dy2, None, True, False, 0, None, None)
+            from . import wgrad as WG
+
+            dw = WG.emit(ctx.sink, x2, dy2)     # fused accumulation into the gradient arena / parked for the pipeline's W pass
         if ctx.has_b and ctx.needs_input_grad[2]:
             db = dy2.sum(0)
-        return dx, dw, db
+        return dx, dw, db, None
+
+
+class _DeferLinear(torch.autograd.Function):
+    """Device-agnostic linear whose weight gradient goes through a wgrad sink (used while a zero-bubble pipeline schedule is
+    deferring W passes and the tcgen05 fast path does not apply, e.g. the CPU/gloo tests or fp32 parameters)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, sink):
+        ctx.save_for_backward(x, w)
+        ctx.has_b, ctx.sink = b is not None, sink
+        y = torch.matmul(x, w)
+        return y + b if b is not None else y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import wgrad as WG
+
+        x, w = ctx.saved_tensors
+        dy2, x2 = dy.reshape(-1, dy.shape[-1]), x.reshape(-1, x.shape[-1])
+        dx = torch.matmul(dy, w.t()) if ctx.needs_input_grad[0] else None
+        dw = WG.emit(ctx.sink, x2, dy2) if ctx.needs_input_grad[1] else None
+        db = dy2.sum(0) if ctx.has_b and ctx.needs_input_grad[2] else None
+        return dx, dw, db, None
 
 
 @recordable
 def linear(x, weight, bias=None):
+    from . import wgrad as WG
+
+    weight_in = weight
     x, weight, bias = raw(x), raw(weight), raw(bias)
     if flag("FLAGS_b200_fp8_linear", False) and x.is_cuda and weight.dim() == 2 and weight.dtype == x.dtype:
         from .gemm_fp8 import fp8_linear   # O2-fp8 recipe: e4m3 forward operands, e5m2 output gradients (csrc/gemm_fp8_sm100.cu)
@@ -101,7 +130,11 @@ def linear(x, weight, bias=None):
             and (bias is None or bias.dtype == x.dtype) and x.numel() > 0:
         m = x.numel() // x.shape[-1]
         if m % 8 == 0:  # dW needs the token count 16B-aligned for the MN-major map
-            return wrap(_Linear.apply(x, weight, bias))
+            return wrap(_Linear.apply(x, weight, bias, WG.sink_for(weight_in)))
+    if WG.is_planned() and weight.dim() == 2 and weight.dtype == x.dtype and torch.is_grad_enabled():
+        sink = WG.sink_for(weight_in)
+        if sink is not None:
+            return wrap(_DeferLinear.apply(x, weight, bias, sink))
     from ..amp.auto_cast import fp32_guard
 
     ctx, (x, weight, bias) = fp32_guard("linear", x, weight, bias)

@@ -12,6 +12,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+from ..kernels import wgrad as WG
 from ..tensor import Tensor
 
 
@@ -55,8 +56,11 @@ def _mm(x, w):
 
 
 def _all_gather0(x, group):
+    from ..distributed import comm_timer as CT
+
     out = torch.empty((x.shape[0] * _n(group), *x.shape[1:]), dtype=x.dtype, device=x.device)
-    dist.all_gather_into_tensor(out, x.contiguous(), group=_pg(group))
+    with CT.region("mp_all_gather"):
+        dist.all_gather_into_tensor(out, x.contiguous(), group=_pg(group))
     return out
 
 
@@ -68,20 +72,26 @@ def _reduce_scatter0(x, group):
         dist.all_reduce(y, group=_pg(group))
         out.copy_(y.chunk(n, 0)[_r(group)])
     else:
-        dist.reduce_scatter_tensor(out, x.contiguous(), group=_pg(group))
+        from ..distributed import comm_timer as CT
+
+        with CT.region("mp_reduce_scatter"):
+            dist.reduce_scatter_tensor(out, x.contiguous(), group=_pg(group))
     return out
 
 
 class _RowParallelLinear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, group):
+    def forward(ctx, x, w, group, sink=None):
         ctx.save_for_backward(x, w)
-        ctx.group = group
+        ctx.group, ctx.sink = group, sink
         sc = _fused_ctx(x, group)
         if sc is not None:
             return sc.gemm_allreduce(x, w)
+        from ..distributed import comm_timer as CT
+
         y = torch.matmul(x, w) if not x.is_cuda else _mm(x.detach(), w.detach())
-        dist.all_reduce(y, group=_pg(group))
+        with CT.region("mp_all_reduce"):
+            dist.all_reduce(y, group=_pg(group))
         return y
 
     @staticmethod
@@ -92,21 +102,21 @@ class _RowParallelLinear(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         x2 = x.reshape(-1, x.shape[-1])
         dx = KG.gemm(dy2, w, b_is_nk=True).reshape(x.shape) if ctx.needs_input_grad[0] else None
-        dw = KG.gemm(x2, dy2, a_is_km=True) if ctx.needs_input_grad[1] else None
-        return dx, dw, None
+        dw = WG.emit(ctx.sink, x2, dy2) if ctx.needs_input_grad[1] else None
+        return dx, dw, None, None
 
 
 def row_parallel_linear(x, w, group):
-    return _w(_RowParallelLinear.apply(_raw(x), _raw(w), group))
+    return _w(_RowParallelLinear.apply(_raw(x), _raw(w), group, WG.sink_for(w)))
 
 
 class _LinearReduceScatter(torch.autograd.Function):
     """x: [S, B, K_local] -> y: [S/p, B, N]"""
 
     @staticmethod
-    def forward(ctx, x, w, group):
+    def forward(ctx, x, w, group, sink=None):
         ctx.save_for_backward(x, w)
-        ctx.group = group
+        ctx.group, ctx.sink = group, sink
         sc = _fused_ctx(x, group)
         if sc is not None:
             return sc.gemm_reduce_scatter(x, w)
@@ -127,20 +137,20 @@ class _LinearReduceScatter(torch.autograd.Function):
             dy_full = _all_gather0(dy, ctx.group)
             dx = KG.gemm(dy_full.reshape(-1, dy_full.shape[-1]), w, b_is_nk=True).reshape(x.shape)
         if ctx.needs_input_grad[1]:
-            dw = KG.gemm(x.reshape(-1, x.shape[-1]), dy_full.reshape(-1, dy_full.shape[-1]), a_is_km=True)
-        return dx, dw, None
+            dw = WG.emit(ctx.sink, x.reshape(-1, x.shape[-1]), dy_full.reshape(-1, dy_full.shape[-1]))
+        return dx, dw, None, None
 
 
 def linear_reduce_scatter(x, w, group):
-    return _w(_LinearReduceScatter.apply(_raw(x), _raw(w), group))
+    return _w(_LinearReduceScatter.apply(_raw(x), _raw(w), group, WG.sink_for(w)))
 
 
 class _AllGatherLinear(torch.autograd.Function):
     """x: [S/p, B, K] -> y: [S, B, N_local]"""
 
     @staticmethod
-    def forward(ctx, x, w, group):
-        ctx.group = group
+    def forward(ctx, x, w, group, sink=None):
+        ctx.group, ctx.sink = group, sink
         sc = _fused_ctx(x, group)
         if sc is not None:
             y, x_full = sc.allgather_gemm(x, w, b_is_nk=False, return_gathered=True)
@@ -162,9 +172,9 @@ class _AllGatherLinear(torch.autograd.Function):
         else:
             dx_full = KG.gemm(dy2, w, b_is_nk=True).reshape(x_full.shape)
             dx = _reduce_scatter0(dx_full, ctx.group)
-        dw = KG.gemm(x_full.reshape(-1, x_full.shape[-1]), dy2, a_is_km=True) if ctx.needs_input_grad[1] else None
-        return dx, dw, None
+        dw = WG.emit(ctx.sink, x_full.reshape(-1, x_full.shape[-1]), dy2) if ctx.needs_input_grad[1] else None
+        return dx, dw, None, None
 
 
 def allgather_linear(x, w, group):
-    return _w(_AllGatherLinear.apply(_raw(x), _raw(w), group))
+    return _w(_AllGatherLinear.apply(_raw(x), _raw(w), group, WG.sink_for(w)))

@@ -181,7 +181,7 @@ def case_pp():
     s, hcg = setup(pp=2)
     L, cfg = _tiny_llama({})
     ids = paddle.to_tensor(np.random.RandomState(0).randint(0, cfg.vocab_size, (4, 33)))
-    s.pipeline_configs = {"accumulate_steps": 4, "micro_batch_size": 1}
+    s.pipeline_configs = {"accumulate_steps": 4, "micro_batch_size": 1, "schedule_mode": os.environ.get("B200_TEST_PP_MODE", "1F1B")}
     paddle.seed(11)
     from paddle_b200.distributed.fleet.pipeline import PipelineLayer
 
@@ -204,6 +204,9 @@ def case_pp():
     model = fleet.distributed_model(pl)
     opt = fleet.distributed_optimizer(paddle.optimizer.AdamW(1e-2, parameters=pl.parameters(), weight_decay=0.0))
     ropt = paddle.optimizer.AdamW(1e-2, parameters=ref.parameters(), weight_decay=0.0)
+    if os.environ.get("B200_TEST_PP_MODE", "1F1B").upper().startswith("ZB"):
+        sched = model.get_static_scheduler()
+        assert "w0" in sched and type(model).__name__ == "PipelineParallelZeroBubble", sched
     for _ in range(3):
         loss = model.train_batch([ids[:, :-1], ids[:, 1:]], opt)
         rl = ref(ids[:, :-1], ids[:, 1:])
@@ -214,6 +217,10 @@ def case_pp():
     sd = ref.state_dict()
     for name, p in pl.named_parameters():
         close(p.numpy(), sd[mapping[name]].numpy(), 2e-3)
+    ev = model.eval_batch([ids[:, :-1], ids[:, 1:]], compute_loss=True)
+    with paddle.no_grad():
+        ref.eval()
+        close(ev.item(), ref(ids[:, :-1], ids[:, 1:]).item(), 2e-3)
 
 
 def case_pp_interleave():
@@ -221,7 +228,7 @@ def case_pp_interleave():
     s, hcg = setup(pp=2)
     L, cfg = _tiny_llama({"num_hidden_layers": 4})
     ids = paddle.to_tensor(np.random.RandomState(0).randint(0, cfg.vocab_size, (4, 33)))
-    s.pipeline_configs = {"accumulate_steps": 4, "micro_batch_size": 1}
+    s.pipeline_configs = {"accumulate_steps": 4, "micro_batch_size": 1, "schedule_mode": os.environ.get("B200_TEST_PP_MODE", "1F1B")}
     paddle.seed(11)
     from paddle_b200.distributed.fleet.pipeline import PipelineLayer, PipelineParallelWithInterleave
 
@@ -931,6 +938,38 @@ def case_hybrid_scaler():
     scaler.step(opt)
     scaler.update()
     assert not np.allclose(net.weight.numpy(), before)
+
+
+def case_hybrid_scaler_dp():
+    """fleet.distributed_scaler under dp=2 with the flat-arena AdamW: an overflow on ONE data-parallel replica must not desynchronise the
+    gradient all-reduce (it runs before the found_inf decision) and must skip the update on both replicas."""
+    s, hcg = setup(dp=2)
+    r = hcg.get_data_parallel_rank()
+    paddle.seed(23)
+    net = nn.Sequential(nn.Linear(4, 8), nn.Linear(8, 4))
+    model = fleet.distributed_model(net)
+    opt = fleet.distributed_optimizer(paddle.optimizer.AdamW(0.1, parameters=net.parameters()))
+    scaler = fleet.distributed_scaler(paddle.amp.GradScaler(init_loss_scaling=1024.0, decr_every_n_nan_or_inf=1, incr_every_n_steps=1000))
+    inner = getattr(model, "_layers", model)
+    before = [p.numpy().copy() for p in net.parameters()]
+    x = paddle.ones([2, 4]) * (r + 1)
+    for it in range(3):
+        loss = (inner(x) ** 2).mean()
+        scaler.scale(loss).backward()
+        if it == 0 and r == 1:
+            net[0].weight.grad[0, 0] = float("inf")     # overflow on one replica only
+        scaler.step(opt)
+        scaler.update()
+        opt.clear_grad()
+        if it == 0:
+            for p, b in zip(net.parameters(), before):
+                close(p.numpy(), b, 1e-7)                # skipped on both replicas
+            assert abs(float(scaler._scale) - 512.0) < 1e-3
+    assert not np.allclose(net[0].weight.numpy(), before[0])
+    w = torch.tensor(net[0].weight.numpy())
+    lst = [torch.zeros_like(w) for _ in range(2)]
+    torch.distributed.all_gather(lst, w)
+    close(lst[0].numpy(), lst[1].numpy(), 1e-6)          # replicas stayed identical
 
 
 def case_fleet_sharding_degree():
