@@ -253,8 +253,9 @@ def main():
     if args.micro_batch <= 0:
         # measured on B200: without a pipeline, larger micro-batches give fuller GEMM waves (mp2: 4 sequences fit the activations of all
         # layers); with pp > 1 the bubble (pp-1)/(accumulate+pp-1) dominates, so keep as many micro-batches as possible.
-        # single GPU: 2 sequences (M = 8192 rows) turn the 4.3-wave N=5120 GEMMs (320 tiles on 74 CTA pairs) into 8.6 waves
-        args.micro_batch = 4 if (mp > 1 and pp == 1) else 2
+        # single GPU: split master weights (bf16 + int16 residual) free 26 GB, enough to keep the activations of all 4 sequences: one
+        # micro-batch of M = 16384 rows turns the 4.3-wave N=5120 GEMMs (320 tiles on 74 CTA pairs) into 17.3 waves
+        args.micro_batch = 4 if pp == 1 else 2
     seqs_per_replica = args.seqs_per_gpu * mp * pp
     global_batch = seqs_per_replica * dp
     accumulate = seqs_per_replica // args.micro_batch
@@ -292,6 +293,7 @@ def main():
 
     def train_step(tokens, read_loss):
         """One optimizer step over `accumulate` micro-batches; public-API calls only."""
+        nonlocal accumulate
         if pp > 1:
             loss = model.train_batch([tokens[:, :-1], tokens[:, 1:]], opt)
         else:
@@ -367,11 +369,15 @@ def main():
             train_step(dev_batches[w_done % 2].as_subclass(paddle.Tensor), read_loss=False)
             w_done += 1
         except torch.OutOfMemoryError:
-            if n != 1 or int(getattr(cfg, "recompute_skip_layers", 0)) <= 0:
+            if n != 1 or (int(getattr(cfg, "recompute_skip_layers", 0)) <= 0 and args.micro_batch <= 1):
                 raise
             opt.clear_grad()
             torch.cuda.empty_cache()
-            set_recompute_skip(max(0, int(cfg.recompute_skip_layers) - 8))
+            if args.micro_batch > 1:          # first give up micro-batch size, then start recomputing layers
+                args.micro_batch //= 2
+                accumulate = seqs_per_replica // args.micro_batch
+            else:
+                set_recompute_skip(max(0, int(cfg.recompute_skip_layers) - 8))
             w_done = 0
     ms, wall, launches, clocks, last = timed(args.steps, e2e=False, offset=0, measure_comm=n > 1)
     tokens_per_step = global_batch * seq

@@ -281,8 +281,14 @@ static void adamw_step_impl(Tensor p, const Tensor& g, const OptT& master, Tenso
   a.inv_scale = (const float*)optp(inv_scale);
   a.dyn = (const float*)optp(dyn);
   if (a.dyn) TORCH_CHECK(dyn->scalar_type() == at::kFloat && dyn->numel() >= 3 && dyn->is_cuda(), "adamw dyn hparams: float32 CUDA tensor of 3");
-  float* mp = master.has_value() && master->defined() ? master->data_ptr<float>() : nullptr;
-  b200::adamw_step(p.data_ptr(), g.data_ptr(), mp, m.data_ptr(), v.data_ptr(), p.numel(), dt_code(p), dt_code(g), dt_code(m), a, cur_stream());
+  float* mp = nullptr;
+  int16_t* lo = nullptr;
+  if (master.has_value() && master->defined()) {
+    TORCH_CHECK(master->numel() == p.numel() && master->is_cuda() && master->is_contiguous(), "adamw: master weights must match the parameter slab");
+    if (master->scalar_type() == at::kShort) lo = master->data_ptr<int16_t>();      // split master: bf16 parameter + int16 residual
+    else mp = master->data_ptr<float>();
+  }
+  b200::adamw_step(p.data_ptr(), g.data_ptr(), mp, m.data_ptr(), v.data_ptr(), p.numel(), dt_code(p), dt_code(g), dt_code(m), a, cur_stream(), lo);
   g_launches += 1;
   check_err();
 }

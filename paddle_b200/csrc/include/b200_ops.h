@@ -65,8 +65,9 @@ struct AdamWArgs {
   const float* dyn = nullptr;
 };
 // p (param dtype), g (grad dtype), master fp32 (may be null), m/v in `state_dtype` (fp32 or bf16)
+// master_lo (optional, bf16 parameters only): split master weights - int16 residual such that fp32 master = (bf16 bits << 16) + lo
 void adamw_step(void* p, const void* g, float* master, void* m, void* v, int64_t n, int p_dtype, int g_dtype,
-                int state_dtype, const AdamWArgs& a, cudaStream_t s);
+                int state_dtype, const AdamWArgs& a, cudaStream_t s, int16_t* master_lo = nullptr);
 // accumulates sum(g^2) into *out (fp32, must be zeroed by caller) and sets *found_inf if any non-finite
 void grad_sq_norm(const void* g, int64_t n, int dtype, float* out, float* found_inf, cudaStream_t s);
 // g *= *scale_dev (unscale / clip by precomputed coefficient)

@@ -23,6 +23,7 @@ import torch
 from ..framework.flags import flag
 
 _defer_stack = []     # innermost active queue (list) or nothing
+stats = {"parked": 0, "fused": 0, "returned": 0}   # counters for tests / profiling
 _planned = [0]        # >0 while a schedule that will defer W passes is running its forwards (see `planning`)
 
 
@@ -119,10 +120,13 @@ def emit(sink, x2, dy2):
         return _gemm_tn(x2, dy2)
     if _defer_stack:
         _defer_stack[-1].append((sink, x2, dy2))
+        stats["parked"] += 1
         return None
     if _live_gbuf(sink) is not None:
         _apply(sink, x2, dy2)
+        stats["fused"] += 1
         return None
+    stats["returned"] += 1
     return _gemm_tn(x2, dy2)
 
 

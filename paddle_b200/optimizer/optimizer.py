@@ -281,6 +281,20 @@ class Optimizer:
         return self._arena
 
 
+def split_master_join(w_bf16, lo):
+    """fp32 master weights from (bf16 parameter, int16 residual): bits = (bf16 bits << 16) + lo  (csrc/optim.cu:split_master_join)."""
+    hi = w_bf16.contiguous().view(torch.int16).to(torch.int32) << 16
+    return (hi + lo.to(torch.int32)).view(torch.float32)
+
+
+def split_master_split(master_f32):
+    """(bf16 parameter = round-to-nearest of the master, int16 residual) from fp32 master weights."""
+    w = master_f32.to(torch.bfloat16)
+    d = master_f32.contiguous().view(torch.int32) - (w.view(torch.int16).to(torch.int32) << 16)
+    d = torch.where(torch.isnan(master_f32), torch.zeros_like(d), d.clamp(-32768, 32767))
+    return w, d.to(torch.int16)
+
+
 class _NativeOps:
     """csrc/optim.cu launchers."""
 
@@ -317,7 +331,8 @@ class _TorchOps:
             if norm > max_norm:
                 gs *= max_norm / (norm + 1e-6)
         gf = g.float() * gs
-        pf = master if master is not None else p.float()
+        split = master is not None and master.dtype == torch.int16
+        pf = split_master_join(p, master) if split else (master if master is not None else p.float())
         mf, vf = m.float(), v.float()
         mf.mul_(b1).add_(gf, alpha=1 - b1)
         vf.mul_(b2).addcmul_(gf, gf, value=1 - b2)
@@ -325,7 +340,12 @@ class _TorchOps:
         pf.mul_(1 - lr * wd).addcdiv_(mf, (vf / c2).sqrt_().add_(eps), value=-lr / c1)
         m.copy_(mf)
         v.copy_(vf)
-        p.copy_(pf)
+        if split:
+            w, lo = split_master_split(pf)
+            p.copy_(w)
+            master.copy_(lo)
+        else:
+            p.copy_(pf)
 
 
 class SGD(Optimizer):
@@ -500,7 +520,7 @@ class Adam(Optimizer):
             lo, hi = self._shard_bounds(s.numel)
             n = hi - lo
             if self._multi_precision and s.dtype != torch.float32 and s.master is None:
-                s.master = s.data[lo:hi].float()
+                s.master = self._new_master(s, lo, hi)
             if "m" not in s.state:
                 sdt = self._moment_dtype or (torch.float32 if (self._multi_precision or s.dtype == torch.float32) else s.dtype)
                 s.state["m"] = torch.zeros(n, dtype=sdt, device=dev)
@@ -534,7 +554,7 @@ class Adam(Optimizer):
                 s.state["m"] = torch.zeros(n, dtype=sdt, device=dev)
                 s.state["v"] = torch.zeros(n, dtype=sdt, device=dev)
             if self._multi_precision and s.dtype != torch.float32 and s.master is None:
-                s.master = s.data[lo:hi].float()
+                s.master = self._new_master(s, lo, hi)
             for p in s.params:
                 o, cnt = s.offsets[p.name]
                 a, b = max(o, lo), min(o + cnt, hi)          # part of this parameter that falls into the local range
@@ -546,7 +566,22 @@ class Adam(Optimizer):
                         dst[a - lo:b - lo].copy_(torch.as_tensor(np.asarray(src) if not isinstance(src, torch.Tensor) else src).reshape(-1)[a - o:b - o].to(dst.dtype))
                 mw = masters.get(p.name)
                 if mw is not None and s.master is not None:
-                    s.master[a - lo:b - lo].copy_(torch.as_tensor(np.asarray(mw) if not isinstance(mw, torch.Tensor) else mw).reshape(-1)[a - o:b - o].float())
+                    mwf = torch.as_tensor(np.asarray(mw) if not isinstance(mw, torch.Tensor) else mw).reshape(-1)[a - o:b - o].float().to(dev)
+                    if s.master.dtype == torch.int16:      # split master: the parameter slab carries the high half
+                        w, r = split_master_split(mwf)
+                        s.data[a:b].copy_(w)
+                        s.master[a - lo:b - lo].copy_(r)
+                    else:
+                        s.master[a - lo:b - lo].copy_(mwf)
+
+    def _new_master(self, s, lo, hi):
+        """fp32 master weights of the slab range [lo, hi).  bf16 slabs use the split format (int16 residual next to the bf16 parameter:
+        4 instead of 6 bytes per parameter, see csrc/optim.cu) unless FLAGS_b200_split_master_weights is off."""
+        from ..framework.flags import flag
+
+        if s.dtype == torch.bfloat16 and flag("FLAGS_b200_split_master_weights", True):
+            return torch.zeros(hi - lo, dtype=torch.int16, device=s.data.device)      # residual 0: the master starts equal to the parameter
+        return s.data[lo:hi].float()
 
     def _gather_shards(self, slab, shard):
         """Every owner publishes its updated range of the parameter slab (stage 1: parameters stay replicated)."""
@@ -566,6 +601,9 @@ class Adam(Optimizer):
         """Full-length view of a (possibly sharded) per-slab state tensor: shards are gathered for checkpoints."""
         shard = self._aux.get("shard")
         t = slab.master if key == "master" else slab.state[key]
+        if key == "master" and t is not None and t.dtype == torch.int16:
+            lo, hi = self._shard_bounds(slab.numel)
+            t = split_master_join(slab.data[lo:hi], t)        # checkpoints always carry fp32 master weights
         if shard is None or t is None:
             return t
         import torch.distributed as dist

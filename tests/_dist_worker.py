@@ -223,6 +223,62 @@ def case_pp():
         close(ev.item(), ref(ids[:, :-1], ids[:, 1:]).item(), 2e-3)
 
 
+def case_pp_bf16_zero_bubble():
+    """GPU: bf16 Llama slice on pp=2 with the zero-bubble schedule: activations travel through the peer-memory mailbox, weight gradients
+    are parked by B and accumulated into the flat gradient arena by W (tcgen05 accumulate epilogue); loss tracks a single-GPU run."""
+    from paddle_b200.kernels import wgrad as WG
+    from paddle_b200.models import llama as LL
+
+    s, hcg = setup(pp=2)
+    mode = os.environ.get("B200_TEST_PP_MODE", "ZBH1")
+    s.pipeline_configs = {"accumulate_steps": 4, "micro_batch_size": 2, "schedule_mode": mode}
+    paddle.set_default_dtype("bfloat16")
+    cfg = LL.llama_tiny(hidden_size=512, intermediate_size=1024, num_attention_heads=4, num_key_value_heads=4, num_hidden_layers=4,
+                        vocab_size=1024, max_position_embeddings=256)
+    ids = paddle.to_tensor(np.random.RandomState(0).randint(0, cfg.vocab_size, (8, 257)))
+    paddle.seed(11)
+    ref = LL.LlamaForCausalLM(cfg)
+    ref_sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    from paddle_b200.distributed.fleet.pipeline import PipelineLayer
+
+    pl = PipelineLayer(LL.pipeline_layer_descs(cfg), num_stages=2, loss_fn=LL.LlamaPretrainingCriterion(cfg), seg_method="layer:LlamaDecoderLayer")
+    mapping = {}
+    for name, _ in pl.named_parameters():
+        idx, rest = name.split(".", 1)
+        i = int(idx)
+        mapping[name] = ("llama.embedding." if i == 0 else "lm_head." if i == cfg.num_hidden_layers + 1 else f"llama.layers.{i - 1}.") + rest
+    pl.set_state_dict({k: ref_sd[v] for k, v in mapping.items()})
+    model = fleet.distributed_model(pl)
+    mk = lambda ps: paddle.optimizer.AdamW(1e-3, parameters=ps, weight_decay=0.0, multi_precision=True, grad_clip=paddle.nn.ClipGradByGlobalNorm(1.0))  # noqa: E731
+    opt = fleet.distributed_optimizer(mk(pl.parameters()))
+    ropt = mk(ref.parameters())
+    ropt.enable_flat_arena()
+    WG.stats.update(parked=0, fused=0, returned=0)
+    losses, rlosses = [], []
+    for _ in range(4):
+        losses.append(float(model.train_batch([ids[:, :-1], ids[:, 1:]], opt).item()))
+        acc = 0.0
+        for mb in range(4):
+            sl = slice(2 * mb, 2 * mb + 2)
+            l = ref(ids[sl, :-1], ids[sl, 1:]) / 4
+            l.backward()
+            acc += float(l.item())
+        ropt.step()
+        ropt.clear_grad()
+        rlosses.append(acc)
+    if GPU:
+        assert model.transport_name() == "mailbox", model.transport_name()
+        w = model.exposed_wait()
+        assert w is not None and w["waits"] > 0, w
+        assert WG.stats["fused"] > 0, WG.stats                      # the single-GPU reference accumulates straight into its arena
+        if mode.upper().startswith("ZB"):
+            assert WG.stats["parked"] > 0, WG.stats                 # B passes parked their weight gradients for W
+    for a, b in zip(losses, rlosses):
+        assert abs(a - b) < 0.05 * abs(b) + 0.02, (losses, rlosses)
+    assert losses[-1] < losses[0]
+    paddle.set_default_dtype("float32")
+
+
 def case_pp_interleave():
     """Virtual pipeline (pp=2 x 2 chunks per rank, 4 micro-batches) == single-process training. Parity: hybrid_parallel_pp_interleave*.py."""
     s, hcg = setup(pp=2)

@@ -32,6 +32,18 @@ def test_pp_gpu():
     run_dist("pp", 2, extra_env={"B200_TEST_GPU": "1"})
 
 
+@pytest.mark.parametrize("mode", ["ZBH1", "1F1B"])
+def test_pp_bf16_mailbox_schedules(mode):
+    """pp=2 bf16 through the peer-memory mailbox; zero-bubble B/W split with arena-fused weight gradients."""
+    _need(2)
+    run_dist("pp_bf16_zero_bubble", 2, extra_env={"B200_TEST_GPU": "1", "B200_TEST_PP_MODE": mode})
+
+
+def test_pp_interleave_gpu():
+    _need(2)
+    run_dist("pp_interleave", 2, extra_env={"B200_TEST_GPU": "1"})
+
+
 def test_moe_fused_dispatch_combine():
     _need(2)
     run_dist("moe_fused_a2a", 2, extra_env={"B200_TEST_GPU": "1"})

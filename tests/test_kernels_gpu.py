@@ -430,3 +430,58 @@ def test_flash_attention_seq_major_layout():
     out_bs.backward(g.transpose(0, 1).contiguous())
     assert rel_err(out_sb.transpose(0, 1), out_bs) < 1e-3
     assert rel_err(x_sb.grad.transpose(0, 1), x_bs.grad) < 1e-2
+
+
+@pytest.mark.parametrize("lean", [True, False])
+def test_fused_wgrad_accumulates_into_arena(lean):
+    """Weight gradients of the Llama linears are added straight into the flat gradient arena by the GEMM's accumulate epilogue
+    (kernels/wgrad.py); two micro-batches must match the classic autograd accumulation within bf16 rounding."""
+    from paddle_b200.kernels import wgrad as WG
+    from paddle_b200.models import LlamaForCausalLM, llama_tiny
+
+    paddle.set_device("gpu:0")
+    paddle.set_default_dtype("bfloat16")
+    try:
+        cfg = llama_tiny(hidden_size=512, intermediate_size=1024, num_attention_heads=4, num_key_value_heads=4, num_hidden_layers=2,
+                         vocab_size=1024, max_position_embeddings=256, lean_activations=lean)
+        ids = paddle.randint(0, cfg.vocab_size, [4, 257])
+        grads = {}
+        for fused in (True, False):
+            paddle.set_flags({"FLAGS_b200_fused_wgrad": fused})
+            paddle.seed(5)
+            model = LlamaForCausalLM(cfg)
+            opt = paddle.optimizer.AdamW(1e-3, parameters=model.parameters(), multi_precision=True)
+            opt.enable_flat_arena()
+            WG.stats.update(parked=0, fused=0, returned=0)
+            for mb in range(2):
+                (model(ids[2 * mb:2 * mb + 2, :-1], ids[2 * mb:2 * mb + 2, 1:]) / 2).backward()
+            assert (WG.stats["fused"] > 0) == fused, WG.stats
+            grads[fused] = {n: p.grad.float().clone() for n, p in model.named_parameters()}
+        for n in grads[True]:
+            assert rel_err(grads[True][n], grads[False][n]) < 2e-2, (n, rel_err(grads[True][n], grads[False][n]))
+    finally:
+        paddle.set_flags({"FLAGS_b200_fused_wgrad": True})
+        paddle.set_default_dtype("float32")
+
+
+def test_adamw_split_master_kernel_matches_fp32_master():
+    """csrc/optim.cu split master weights (bf16 parameter + int16 residual) == the fp32-master kernel, step after step."""
+    from paddle_b200.optimizer.optimizer import split_master_join
+
+    torch.manual_seed(0)
+    n = 8 * 4096 + 24
+    p0 = (torch.randn(n, device="cuda") * 0.05).to(torch.bfloat16)
+    pa, pb = p0.clone(), p0.clone()
+    master = p0.float()
+    lo = torch.zeros(n, dtype=torch.int16, device="cuda")
+    ma, va = torch.zeros(n, device="cuda", dtype=torch.bfloat16), torch.zeros(n, device="cuda", dtype=torch.bfloat16)
+    mb, vb = ma.clone(), va.clone()
+    e = _ext()
+    for step in range(1, 6):
+        g = (torch.randn(n, device="cuda") * 0.01).to(torch.bfloat16)
+        e.adamw_step(pa, g, master, ma, va, 1e-3, 0.9, 0.95, 1e-8, 0.1, step, None, 0.0, None, None)
+        e.adamw_step(pb, g, lo, mb, vb, 1e-3, 0.9, 0.95, 1e-8, 0.1, step, None, 0.0, None, None)
+        assert torch.equal(pa, pb), f"parameters diverged at step {step}"
+        rebuilt = split_master_join(pb, lo)
+        assert (rebuilt.view(torch.int32) - master.view(torch.int32)).abs().max().item() <= 1
+    assert lo.abs().max().item() > 0

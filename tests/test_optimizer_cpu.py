@@ -298,3 +298,56 @@ def test_amp_o2_fp32_input_and_checkpoint_roundtrip(tmp_path):
     opt2.step()
     for a, b in zip(net.parameters(), net2.parameters()):
         np.testing.assert_array_equal(a.astype("float32").numpy(), b.astype("float32").numpy())
+
+
+def test_split_master_weights_match_fp32_master():
+    """bf16 arena AdamW: master weights stored as (bf16 parameter, int16 residual) follow the fp32-master trajectory bit for bit
+    (except round-to-even ties, 1 fp32 ulp), and checkpoints still carry fp32 master weights that restore exactly."""
+    import numpy as np
+    import torch
+
+    import paddle_b200 as paddle
+    from paddle_b200.optimizer.optimizer import split_master_join, split_master_split
+
+    x = torch.randn(4096) * 3
+    x[:4] = torch.tensor([0.0, -0.0, 1e-30, -65504.0])
+    w, lo = split_master_split(x)
+    back = split_master_join(w, lo)
+    assert (back.view(torch.int32) - x.view(torch.int32)).abs().max().item() <= 1
+    assert torch.equal(w, x.to(torch.bfloat16))
+
+    def run(split):
+        paddle.set_flags({"FLAGS_b200_split_master_weights": split})
+        paddle.seed(3)
+        paddle.set_default_dtype("bfloat16")
+        try:
+            net = paddle.nn.Sequential(paddle.nn.Linear(16, 32), paddle.nn.Linear(32, 8))
+            opt = paddle.optimizer.AdamW(1e-2, parameters=net.parameters(), weight_decay=0.05, multi_precision=True)
+            opt.enable_flat_arena()
+            g = torch.Generator().manual_seed(0)
+            for _ in range(6):
+                xx = torch.randn(4, 16, generator=g).to(torch.bfloat16).as_subclass(paddle.Tensor)
+                (net(xx).astype("float32") ** 2).mean().backward()
+                opt.step()
+                opt.clear_grad()
+            return net, opt
+        finally:
+            paddle.set_default_dtype("float32")
+            paddle.set_flags({"FLAGS_b200_split_master_weights": True})
+
+    n1, o1 = run(True)
+    n0, o0 = run(False)
+    slab = o1._arena.all_slabs()[0]
+    assert slab.master.dtype == torch.int16
+    for a, b in zip(n1.parameters(), n0.parameters()):
+        assert torch.equal(a.as_subclass(torch.Tensor).float(), b.as_subclass(torch.Tensor).float())
+    sd1, sd0 = o1.state_dict(), o0.state_dict()
+    for m1, m0 in zip(sd1["master_weights"].values(), sd0["master_weights"].values()):
+        assert m1.dtype == paddle.float32
+        assert np.abs(np.asarray(m1.numpy()).view(np.int32) - np.asarray(m0.numpy()).view(np.int32)).max() <= 1
+    # fp32 master weights from the checkpoint restore exactly into the split format
+    masters = [np.asarray(v.numpy()) for v in sd1["master_weights"].values()]
+    o1.set_state_dict(sd1)
+    sd2 = o1.state_dict()
+    for a, b in zip(masters, sd2["master_weights"].values()):
+        assert np.abs(a.view(np.int32) - np.asarray(b.numpy()).view(np.int32)).max() <= 1
