@@ -388,7 +388,7 @@ struct MapKeyHash {
   }
 };
 
-// 3-D map {inner (contiguous), rows, batch}; element = 2 bytes.
+// 3-D map {inner (contiguous), rows, batch}; element = 2 bytes (bf16 / fp16) or 4 bytes (kF32: TMA-store maps of fp32 outputs).
 bool make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t ld,
                      uint64_t bstride, uint32_t box_inner, uint32_t box_rows, int dtype) {
   static std::mutex mu;
@@ -403,10 +403,11 @@ bool make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, 
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable"); return false; }
   cuuint64_t dims[3] = {inner, rows, batch};
-  cuuint64_t strides[2] = {ld * 2, (batch > 1 ? bstride : rows * ld) * 2};
+  const uint64_t es = dtype == kF32 ? 4 : 2;
+  cuuint64_t strides[2] = {ld * es, (batch > 1 ? bstride : rows * ld) * es};
   cuuint32_t box[3] = {box_inner, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(out, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+  CUresult r = enc(out, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : (dtype == kF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), 3,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

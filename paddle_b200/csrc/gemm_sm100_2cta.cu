@@ -12,6 +12,8 @@
 //   tempty[a] (leader only)  : 8 arrivals = 4 epilogue warps x 2 CTAs (the peer arrives remotely through mapa)
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include "include/b200_common.cuh"
 #include "include/b200_ops.h"
@@ -35,7 +37,11 @@ constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 constexpr uint32_t B_STAGE_BYTES = HALF_N * BLOCK_K * 2;    // 16 KB
 constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr uint32_t TMEM_COLS = kAccStages * BLOCK_N;        // 512
-constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + 1024 + 256;
+// TMA-store epilogue: every epilogue warp stages [32 rows x 128 B] boxes (128B-swizzled) in two alternating 4 KB buffers
+constexpr uint32_t STG_BOX_BYTES = 32 * 128;
+constexpr uint32_t STG_OFF = kStages * STAGE_BYTES + 1024;                 // after the barrier page (1024-aligned)
+constexpr uint32_t STG_BYTES = 4 * 2 * STG_BOX_BYTES;                      // 32 KB
+constexpr uint32_t SMEM_BYTES = STG_OFF + STG_BYTES + 1024;                // + alignment slack = 231424 <= 232448 (227 KB)
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;              // clears the CTA-rank bit of a shared::cluster address
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -99,6 +105,26 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap*
       ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
       : "memory");
 }
+// smem box -> global (or peer) memory; completion tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack2_f16(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -139,7 +165,10 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "memory");
 }
 
+struct DMaps { CUtensorMap m[8]; };   // TMA-store maps of the output: [0] = D, or one per reduce-scatter owner slot
+
 struct Params {
+  int tma_store;           // epilogue goes TMEM -> registers -> swizzled smem -> cp.async.bulk.tensor (UTMASTG), also to peer HBM
   int m, n, k, batch;
   void* d;
   const void* bias;
@@ -267,7 +296,8 @@ __device__ __forceinline__ void store_row_chunk(TO* __restrict__ dst, const floa
 
 template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ DMaps dmaps,
+             const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -397,6 +427,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     // ================= epilogue (both CTAs: own 128 rows x 256 columns) =================
     const int ew = warp - 4;
     int local = 0;
+    int tma_buf = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
       int bz, mb, nb;
       tile_coords(tile, bz, mb, nb);
@@ -406,6 +437,78 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       tc_fence_after();
       const int row = mb * 2 * BLOCK_M + (int)cta_rank * BLOCK_M + ew * 32 + lane;
       const bool row_ok = row < p.m;
+      if (p.tma_store) {
+        // ---- TMA-store epilogue: [32 rows x 128 B] boxes through 128B-swizzled smem, one cp.async.bulk.tensor per box ----
+        const int row0 = mb * 2 * BLOCK_M + (int)cta_rank * BLOCK_M + ew * 32;      // first row of this warp's 32-row strip
+        const int owner = p.rs_world > 1 ? row0 / p.rs_rows : 0;
+        const int row_rel = p.rs_world > 1 ? row0 - owner * p.rs_rows : row0;
+        const int cpb = p.out_dtype == kF32 ? 32 : 64;                              // columns per 128-byte box row
+        const uint32_t stg = smem_base + STG_OFF + (uint32_t)ew * 2 * STG_BOX_BYTES;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / cpb; ++c) {
+          const int col0 = nb * BLOCK_N + c * cpb;
+          if (col0 >= p.n || row0 >= p.m) break;
+          if (lane == 0) bulk_wait_read_1();        // the box stored two iterations ago has been read out of this buffer
+          __syncwarp();
+          const uint32_t dst = stg + (uint32_t)tma_buf * STG_BOX_BYTES + (uint32_t)lane * 128;
+          const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h * 32 >= cpb) break;
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BLOCK_N + c * cpb + h * 32, r);
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.has_bias) {
+              const int cb = col0 + h * 32;
+              if (p.in_dtype == kBF16) {
+                const __nv_bfloat16* b = (const __nv_bfloat16*)p.bias + cb;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (cb + j < p.n) v[j] += __bfloat162float(b[j]);
+              } else {
+                const __half* b = (const __half*)p.bias + cb;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (cb + j < p.n) v[j] += __half2float(b[j]);
+              }
+            }
+            if (p.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            } else if (p.act == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (p.out_dtype == kF32) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                st_shared_v4(dst + (((uint32_t)q ^ sw) << 4), __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
+                             __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
+            } else if (p.out_dtype == kBF16) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                st_shared_v4(dst + (((uint32_t)(h * 4 + q) ^ sw) << 4), pack2_bf16(v[8 * q], v[8 * q + 1]), pack2_bf16(v[8 * q + 2], v[8 * q + 3]),
+                             pack2_bf16(v[8 * q + 4], v[8 * q + 5]), pack2_bf16(v[8 * q + 6], v[8 * q + 7]));
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                st_shared_v4(dst + (((uint32_t)(h * 4 + q) ^ sw) << 4), pack2_f16(v[8 * q], v[8 * q + 1]), pack2_f16(v[8 * q + 2], v[8 * q + 3]),
+                             pack2_f16(v[8 * q + 4], v[8 * q + 5]), pack2_f16(v[8 * q + 6], v[8 * q + 7]));
+            }
+          }
+          fence_proxy_async();                      // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&dmaps.m[owner], stg + (uint32_t)tma_buf * STG_BOX_BYTES, col0, row_rel, bz);
+            bulk_commit();
+          }
+          tma_buf ^= 1;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_bar(as), 0);
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         const int col0 = nb * BLOCK_N + c * 32;
@@ -451,6 +554,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar(as), 0);  // leader's barrier counts both CTAs' epilogue warps
     }
+    if (p.tma_store && lane == 0) bulk_wait_all();   // every box has been written before the CTA may exit
   }
 
   tc_fence_before();
@@ -511,6 +615,28 @@ static int launch(const GemmArgs& g, cudaStream_t s) {
     p.ag_flags = (uint32_t*)g.ag_flags;
     p.ag_epoch = g.ag_epoch;
   }
+  // TMA-store epilogue whenever the output rows are 16-byte aligned and the epilogue does not read D (accumulate keeps ld/st)
+  DMaps dm;
+  memset(&dm, 0, sizeof(dm));
+  p.tma_store = 0;
+  {
+    const int es = g.out_dtype == kF32 ? 4 : 2;
+    const uint32_t cpb = 128 / es;
+    static const bool enabled = []() { const char* e = getenv("B200_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
+    if (enabled && !p.accumulate) {
+      bool ok2 = true;
+      if (p.rs_world) {
+        ok2 = (g.n * es) % 16 == 0 && g.rs_rows % 32 == 0;
+        for (int r = 0; r < p.rs_world && ok2; ++r)
+          ok2 = ((uintptr_t)g.rs_dst[r] % 16 == 0) && gemm::make_map(&dm.m[r], g.rs_dst[r], g.n, g.rs_rows, 1, g.n, 0, cpb, 32, g.out_dtype);
+      } else {
+        ok2 = (g.ldd * es) % 16 == 0 && ((uintptr_t)g.d % 16 == 0) && (batch == 1 || (g.stride_d * es) % 16 == 0) &&
+              gemm::make_map(&dm.m[0], g.d, g.n, g.m, batch, g.ldd, g.stride_d, cpb, 32, g.out_dtype);
+      }
+      if (!ok2) take_last_error();     // an odd leading dimension just keeps the register-store epilogue
+      p.tma_store = ok2 ? 1 : 0;
+    }
+  }
   p.idesc = make_idesc(g.dtype, A_MN, B_MN);
   static bool attr_set = false;
   auto kern = gemm2_kernel<A_MN, B_MN>;
@@ -521,7 +647,7 @@ static int launch(const GemmArgs& g, cudaStream_t s) {
   const int num_tiles = ((g.m + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((g.n + BLOCK_N - 1) / BLOCK_N) * (int)batch;
   const int max_clusters = sm_count() / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-  kern<<<clusters * 2, kThreads, SMEM_BYTES, s>>>(ma, mb, p);
+  kern<<<clusters * 2, kThreads, SMEM_BYTES, s>>>(ma, mb, dm, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return 3; }
   return 0;
