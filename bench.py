@@ -253,9 +253,9 @@ def main():
     if args.micro_batch <= 0:
         # measured on B200: without a pipeline, larger micro-batches give fuller GEMM waves (mp2: 4 sequences fit the activations of all
         # layers); with pp > 1 the bubble (pp-1)/(accumulate+pp-1) dominates, so keep as many micro-batches as possible.
-        # single GPU: split master weights (bf16 + int16 residual) free 26 GB, enough to keep the activations of all 4 sequences: one
-        # micro-batch of M = 16384 rows turns the 4.3-wave N=5120 GEMMs (320 tiles on 74 CTA pairs) into 17.3 waves
-        args.micro_batch = 4 if pp == 1 else 2
+        # single GPU: split master weights (bf16 + int16 residual) free 26 GB, enough to keep the activations of 2 sequences per micro-batch
+        # with no recompute: M = 8192 rows turn the 4.3-wave N=5120 GEMMs (320 tiles on 74 CTA pairs) into 8.6 waves
+        args.micro_batch = 4 if (pp == 1 and mp > 1) else 2
     seqs_per_replica = args.seqs_per_gpu * mp * pp
     global_batch = seqs_per_replica * dp
     accumulate = seqs_per_replica // args.micro_batch

@@ -111,6 +111,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// same box, but added to the destination (bf16 / fp16 / fp32 add performed by the L2 reduction units): D += tile without reading D
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -499,7 +505,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
           fence_proxy_async();                      // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&dmaps.m[owner], stg + (uint32_t)tma_buf * STG_BOX_BYTES, col0, row_rel, bz);
+            if (p.accumulate) tma_reduce_add_3d(&dmaps.m[owner], stg + (uint32_t)tma_buf * STG_BOX_BYTES, col0, row_rel, bz);
+            else tma_store_3d(&dmaps.m[owner], stg + (uint32_t)tma_buf * STG_BOX_BYTES, col0, row_rel, bz);
             bulk_commit();
           }
           tma_buf ^= 1;
@@ -615,7 +622,8 @@ static int launch(const GemmArgs& g, cudaStream_t s) {
     p.ag_flags = (uint32_t*)g.ag_flags;
     p.ag_epoch = g.ag_epoch;
   }
-  // TMA-store epilogue whenever the output rows are 16-byte aligned and the epilogue does not read D (accumulate keeps ld/st)
+  // TMA-store epilogue whenever the output rows are 16-byte aligned; accumulate (D += AB, the fused weight-gradient path) becomes a
+  // TMA reduce-add (UTMAREDG): the addition happens in L2 and D is never read by the SMs
   DMaps dm;
   memset(&dm, 0, sizeof(dm));
   p.tma_store = 0;
@@ -623,7 +631,8 @@ static int launch(const GemmArgs& g, cudaStream_t s) {
     const int es = g.out_dtype == kF32 ? 4 : 2;
     const uint32_t cpb = 128 / es;
     static const bool enabled = []() { const char* e = getenv("B200_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
-    if (enabled && !p.accumulate) {
+    static const bool reduce_ok = []() { const char* e = getenv("B200_GEMM_TMA_REDUCE"); return !(e && e[0] == '0'); }();
+    if (enabled && (!p.accumulate || reduce_ok)) {
       bool ok2 = true;
       if (p.rs_world) {
         ok2 = (g.n * es) % 16 == 0 && g.rs_rows % 32 == 0;
