@@ -289,6 +289,55 @@ __global__ void __launch_bounds__(kThreads) a2av_kernel(Peers P, const char* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------- gather-pull (sharded parameters)
+// dst (ordinary local memory, [world, chunk_bytes]) <- every rank's `chunk_bytes` at byte offset src_off of ITS heap.  GroupSharded
+// stage 3 keeps each rank's parameter shards in the symmetric heap; a layer's full weights are pulled straight into a fresh
+// allocation that the layer's kernels then read (no staging window, no copy-out).
+__global__ void __launch_bounds__(kThreads) gather_pull_kernel(Peers P, int64_t src_off, char* __restrict__ dst, int64_t chunk_bytes,
+                                                               int rank, int world, uint32_t epoch, uint32_t* counter) {
+  if (blockIdx.x == 0) signal_all(P, rank, world, 0, epoch);
+  wait_all(P, rank, world, 0, epoch);
+  const int64_t nvec = chunk_bytes / 16;
+  const int64_t total = nvec * world;
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; base < total; base += stride * U) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + u * stride;
+      if (i < total) {
+        const int r = (int)(i / nvec);
+        const int64_t j = i - (int64_t)r * nvec;
+        v[u] = reinterpret_cast<const uint4*>(P.base[r] + src_off)[j];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + u * stride;
+      if (i < total) reinterpret_cast<uint4*>(dst)[i] = v[u];
+    }
+  }
+  if (last_cta(counter)) {
+    signal_all(P, rank, world, 1, epoch);
+    wait_all(P, rank, world, 1, epoch);
+  }
+}
+
+void p2p_gather_pull(const int64_t* bases, int64_t src_off, void* dst, int64_t chunk_bytes, int rank, int world, uint32_t epoch,
+                     uint32_t* counter, cudaStream_t s) {
+  if (world > kMaxRanks || chunk_bytes % 16 || src_off % 16 || (reinterpret_cast<uintptr_t>(dst) & 15)) {
+    set_last_error(__FILE__, __LINE__, "p2p_gather_pull: bad world / alignment");
+    return;
+  }
+  Peers P;
+  for (int r = 0; r < kMaxRanks; ++r) P.base[r] = r < world ? reinterpret_cast<char*>(bases[r]) : nullptr;
+  int64_t blocks = (chunk_bytes / 16 * world + kThreads * 4 - 1) / (kThreads * 4);
+  const int grid = (int)(blocks < 1 ? 1 : (blocks > 96 ? 96 : blocks));
+  gather_pull_kernel<<<grid, kThreads, 0, s>>>(P, src_off, static_cast<char*>(dst), chunk_bytes, rank, world, epoch, counter);
+  B200_CUDA_CHECK(cudaGetLastError());
+}
+
 // ---------------------------------------------------------------------------------------------- mailbox signal / wait
 // Point-to-point "mailbox" used by the pipeline engine (distributed/fleet/pipeline.py): the producer copies a tensor into a slot
 // of the consumer's heap with the copy engine (cudaMemcpyAsync on the IPC-mapped pointer: no SM work), then this one-thread kernel

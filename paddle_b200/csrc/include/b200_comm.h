@@ -21,6 +21,9 @@ void p2p_alltoall(const int64_t* bases, int64_t off_send, int64_t off_recv, int6
 // MoE dispatch / combine: variable all-to-all push with optional row gather (see a2av_kernel). rows_hint sizes the grid.
 void p2p_a2av(const int64_t* bases, const void* src, const int64_t* gather, int64_t meta_off, int64_t recv_off, int64_t row_bytes,
               int64_t rows_hint, int rank, int world, uint32_t epoch, uint32_t* counter, cudaStream_t s);
+// dst[r*chunk_bytes ...] (ordinary local memory) <- chunk_bytes at byte offset src_off of rank r's heap, for every r
+void p2p_gather_pull(const int64_t* bases, int64_t src_off, void* dst, int64_t chunk_bytes, int rank, int world, uint32_t epoch,
+                     uint32_t* counter, cudaStream_t s);
 // pipeline mailbox: release-store `value` into a flag in a peer's heap / spin (one thread) until the local flag reaches `value`;
 // stats (optional, device uint64[2]) accumulates the spun nanoseconds and the number of waits.
 void p2p_signal_flag(void* remote_flag, uint32_t value, cudaStream_t s);

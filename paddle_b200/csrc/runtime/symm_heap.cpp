@@ -174,6 +174,13 @@ class SymmHeap {
                    row_bytes, rows_hint, rank_, world_, (uint32_t)epoch, counter(), at::cuda::getCurrentCUDAStream().stream());
     finish();
   }
+  void gather_pull(torch::Tensor dst, int64_t src_off, int64_t chunk_bytes, int64_t epoch) {
+    c10::cuda::CUDAGuard g(device_);
+    auto b = bases();
+    comm::p2p_gather_pull(b.data(), src_off, dst.data_ptr(), chunk_bytes, rank_, world_, (uint32_t)epoch, counter(),
+                          at::cuda::getCurrentCUDAStream().stream());
+    finish();
+  }
   // ---- mailbox primitives (pipeline p2p): flags live in the symmetric data region at byte offset `flag_off` ----
   void signal_flag(int peer, int64_t flag_off, int64_t value) {
     c10::cuda::CUDAGuard g(device_);
@@ -261,6 +268,7 @@ void bind_symm(pybind11::module_& m) {
       .def("allgather", &SymmHeap::allgather)
       .def("a2av", &SymmHeap::a2av)
       .def("alltoall", &SymmHeap::alltoall)
+      .def("gather_pull", &SymmHeap::gather_pull)
       .def("signal_flag", &SymmHeap::signal_flag)
       .def("wait_flag", &SymmHeap::wait_flag, pybind11::arg("flag_off"), pybind11::arg("value"), pybind11::arg("timeout_s") = 300.0)
       .def("wait_stats", &SymmHeap::wait_stats, pybind11::arg("reset") = true);

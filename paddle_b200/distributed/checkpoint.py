@@ -93,7 +93,23 @@ def load_state_dict(state_dict, path, process_group=None, coordinator_rank=0, un
         hi = lo + np.array(_ls(t))
         out = np.zeros(_ls(t), dtype=np.float64)
         filled = False
-        for e in meta[k]:
+        entries = meta[k]
+        # several ranks saved a block with identical placement (e.g. a tensor-parallel parameter written without shard metadata by an
+        # older checkpoint, or replicated copies): take this rank's own copy when there is one, never silently "last writer wins"
+        same = {}
+        for e in entries:
+            same.setdefault((tuple(e["offsets"]), tuple(e["local_shape"])), []).append(e)
+        dedup = []
+        for group in same.values():
+            if len(group) > 1:
+                mine = [e for e in group if e["rank"] == env.get_rank()]
+                if not mine and getattr(t, "is_distributed", False):
+                    raise ValueError(f"distributed checkpoint: {len(group)} ranks saved '{k}' with identical offsets but the tensor is "
+                                     "model-parallel; the checkpoint carries no shard metadata for it (re-save with this version)")
+                dedup.append(mine[0] if mine else group[0])
+            else:
+                dedup.append(group[0])
+        for e in dedup:
             so, ss = np.array(e["offsets"]), np.array(e["local_shape"])
             a, b = np.maximum(lo, so), np.minimum(hi, so + ss)
             if (a >= b).any() and out.ndim > 0:

@@ -227,6 +227,20 @@ def _c_split(tensor, group=None):
     return _w(_Split.apply(_raw(tensor), _mp_group(group)))
 
 
+def _mark_dist_shard(p, axis, rank, world):
+    """Checkpoint metadata of a tensor-parallel parameter: (global shape, offsets of the local block) - read by
+    distributed/checkpoint.py so that save / load re-shard across mp degrees instead of treating every rank's block as the whole."""
+    if world <= 1:
+        return
+    local = [int(d) for d in torch.Tensor.size(p)]
+    gshape = list(local)
+    gshape[axis] = local[axis] * world
+    offs = [0] * len(local)
+    offs[axis] = local[axis] * rank
+    p.__dict__["_dist_shard"] = (tuple(gshape), tuple(offs))
+    p.split_axis = axis
+
+
 def mark_as_sequence_parallel_parameter(p):
     p.sequence_parallel = True
 
@@ -266,6 +280,7 @@ class VocabParallelEmbedding(Layer):
         with get_rng_state_tracker().rng_state():
             self.weight = self.create_parameter([self.per_part, embedding_dim], attr=weight_attr, default_initializer=I.Normal(0.0, 0.02))
         self.weight.is_distributed = self.world_size > 1
+        _mark_dist_shard(self.weight, 0, self.rank, self.world_size)
 
     def forward(self, x):
         if self.world_size == 1:
@@ -293,9 +308,11 @@ class ColumnParallelLinear(Layer):
         with get_rng_state_tracker().rng_state():
             self.weight = self.create_parameter([in_features, self.out_per_part], attr=weight_attr)
         self.weight.is_distributed = self.world_size > 1
+        _mark_dist_shard(self.weight, 1, self.rank, self.world_size)
         self.bias = self.create_parameter([self.out_per_part], is_bias=True) if has_bias else None
         if self.bias is not None:
             self.bias.is_distributed = self.world_size > 1
+            _mark_dist_shard(self.bias, 0, self.rank, self.world_size)
 
     def forward(self, x):
         if self.world_size > 1:
@@ -321,6 +338,7 @@ class RowParallelLinear(Layer):
         with get_rng_state_tracker().rng_state():
             self.weight = self.create_parameter([self.in_per_part, out_features], attr=weight_attr)
         self.weight.is_distributed = self.world_size > 1
+        _mark_dist_shard(self.weight, 0, self.rank, self.world_size)
         self.bias = self.create_parameter([out_features], is_bias=True) if has_bias else None
 
     def forward(self, x):
@@ -349,7 +367,11 @@ class ColumnSequenceParallelLinear(Layer):
         with get_rng_state_tracker().rng_state():
             self.weight = self.create_parameter([in_features, self.out_per_part], attr=weight_attr)
         self.weight.is_distributed = self.world_size > 1
+        _mark_dist_shard(self.weight, 1, self.rank, self.world_size)
         self.bias = self.create_parameter([self.out_per_part], is_bias=True) if has_bias else None
+        if self.bias is not None:
+            self.bias.is_distributed = self.world_size > 1
+            _mark_dist_shard(self.bias, 0, self.rank, self.world_size)
 
     def forward(self, x):
         if self.world_size > 1:
@@ -373,6 +395,7 @@ class RowSequenceParallelLinear(Layer):
         with get_rng_state_tracker().rng_state():
             self.weight = self.create_parameter([self.in_per_part, out_features], attr=weight_attr)
         self.weight.is_distributed = self.world_size > 1
+        _mark_dist_shard(self.weight, 0, self.rank, self.world_size)
         self.bias = self.create_parameter([out_features], is_bias=True) if has_bias else None
         if self.bias is not None:
             mark_as_sequence_parallel_parameter(self.bias)

@@ -252,6 +252,9 @@ class LlamaLMHead(nn.Layer):
         with get_rng_state_tracker().rng_state():
             self.weight = self.create_parameter([config.hidden_size, vocab_local], default_initializer=I.Normal(0.0, config.initializer_range))
         self.weight.is_distributed = mp > 1
+        if mp > 1:
+            hcg = topo.get_hybrid_communicate_group()
+            mpu._mark_dist_shard(self.weight, 1, hcg.get_model_parallel_rank(), mp)
 
     def forward(self, h):
         h = self.norm(h)

@@ -109,11 +109,22 @@ class Optimizer:
 
     def state_dict(self):
         sd = OrderedDict()
+        byname = {p.name: p for p in self._parameter_list} if self._parameter_list and not isinstance(self._parameter_list[0], dict) else {}
+
+        def tag(pname, t):
+            t = t.as_subclass(Tensor)
+            p = byname.get(pname)
+            ds = p.__dict__.get("_dist_shard") if p is not None else None
+            if ds is not None and tuple(t.shape) == tuple(p.shape):     # tensor-parallel parameter: its state is sharded the same way
+                t.__dict__["_dist_shard"] = ds
+                t.is_distributed = True
+            return t
+
         for acc, d in self._accumulators.items():
             for pname, t in d.items():
-                sd[f"{pname}_{acc}_0"] = t.as_subclass(Tensor)
+                sd[f"{pname}_{acc}_0"] = tag(pname, t)
         if self._master_weights:
-            sd["master_weights"] = {k: v.as_subclass(Tensor) for k, v in self._master_weights.items()}
+            sd["master_weights"] = {k: tag(k, v) for k, v in self._master_weights.items()}
         if isinstance(self._learning_rate, LRScheduler):
             sd["LR_Scheduler"] = self._learning_rate.state_dict()
         sd["@step@"] = self._step_count
@@ -475,7 +486,17 @@ class Adam(Optimizer):
             return False
         if self._grad_clip is not None and not isinstance(self._grad_clip, ClipGradByGlobalNorm):
             return False
-        return True
+        if getattr(self, "_lr_ratio", None) is not None or len(self._param_groups) > 1:
+            return False      # per-parameter lr scaling / param-group overrides: the one-launch-per-slab update cannot express them
+        ok = self._aux.get("arena_params_ok")
+        if ok is None:        # per-parameter attributes the slab kernel ignores (checked once: they do not change after construction)
+            ok = True
+            for sl in self._arena.all_slabs():
+                for p in sl.params:
+                    if getattr(p, "optimize_attr", {}).get("learning_rate", 1.0) != 1.0 or not getattr(p, "need_clip", True):
+                        ok = False
+            self._aux["arena_params_ok"] = ok
+        return ok
 
     def _shard_bounds(self, numel):
         """[lo, hi) of a slab that this rank updates under optimizer-state sharding (stage 1); the whole slab otherwise."""
@@ -649,6 +670,15 @@ class Adam(Optimizer):
                     sd[f"{p.name}_moment2_0"] = fv[o:o + n].view(tuple(p.size())).as_subclass(Tensor)
                     if fmaster is not None:
                         sd.setdefault("master_weights", {})[p.name] = fmaster[o:o + n].view(tuple(p.size())).as_subclass(Tensor)
+                    b1, b2 = self._betas()
+                    sd[f"{p.name}_beta1_pow_acc_0"] = torch.tensor([b1 ** self._step_count], dtype=torch.float32).as_subclass(Tensor)
+                    sd[f"{p.name}_beta2_pow_acc_0"] = torch.tensor([b2 ** self._step_count], dtype=torch.float32).as_subclass(Tensor)
+                    ds = p.__dict__.get("_dist_shard")
+                    if ds is not None:       # tensor-parallel parameter: its state is sharded the same way (distributed/checkpoint.py)
+                        for t in (sd[f"{p.name}_moment1_0"], sd[f"{p.name}_moment2_0"], sd.get("master_weights", {}).get(p.name)):
+                            if t is not None:
+                                t.__dict__["_dist_shard"] = ds
+                                t.is_distributed = True
         return sd
 
     def set_state_dict(self, state_dict):
@@ -660,10 +690,17 @@ class Adam(Optimizer):
             self._aux["pending_state"] = state_dict      # the flat arena may be enabled after loading
         steps = self._aux.setdefault("steps", {})
         b1, _ = self._betas()
+        derived = 0
         for pname, t in self._accumulators.get("beta1_pow_acc", {}).items():
             val = float(t.reshape(-1)[0])
             if 0 < val < 1 and 0 < b1 < 1:
                 steps[pname] = max(steps.get(pname, 0), int(round(math.log(val) / math.log(b1))))
+                derived = max(derived, steps[pname])
+        if "@step@" not in state_dict and derived:
+            self._step_count = derived          # a reference .pdopt has no '@step@': the bias correction continues from beta1_pow_acc
+        elif "@step@" in state_dict:
+            for p in self._parameter_list if self._parameter_list and not isinstance(self._parameter_list[0], dict) else []:
+                steps.setdefault(p.name, int(self._step_count))   # arena-written checkpoints loaded on the per-parameter path
 
 
 class AdamW(Adam):

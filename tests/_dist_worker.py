@@ -411,33 +411,86 @@ def case_mp_sp_parity():
 
 
 def case_sharding():
-    """group_sharded_parallel os_g and p_g_os == plain training. Parity: dygraph_group_sharded_stage2/3.py."""
+    """group_sharded_parallel os_g and p_g_os == plain training (AdamW + global-norm clip + weight decay, gradient accumulation over two
+    backward passes, loss scaling with an overflow on one rank), stage-2 optimizer checkpoints are rank-independent.
+    Parity: dygraph_group_sharded_stage2/3.py."""
     dist.init_parallel_env()
     r, w = dist.get_rank(), dist.get_world_size()
-    from paddle_b200.distributed.sharding import group_sharded_parallel
+    from paddle_b200.distributed.sharding import GroupShardedOptimizerStage2, group_sharded_parallel
 
+    dev_kw = {}
+    if GPU:
+        paddle.set_device(f"gpu:{os.environ['LOCAL_RANK']}")
+    os.environ["B200_SHARD_BUCKET_MB"] = "0.0005"     # several buckets even for this tiny model
     for level in ("os_g", "p_g_os"):
-        paddle.seed(21)
-        net = nn.Sequential(nn.Linear(8, 32), nn.GELU(), nn.Linear(32, 4))
-        ref = nn.Sequential(nn.Linear(8, 32), nn.GELU(), nn.Linear(32, 4))
-        ref.set_state_dict(net.state_dict())
-        x, y = paddle.randn([8, 8]), paddle.randn([8, 4])
-        opt = paddle.optimizer.AdamW(1e-2, parameters=net.parameters(), weight_decay=0.0)
-        ropt = paddle.optimizer.AdamW(1e-2, parameters=ref.parameters(), weight_decay=0.0)
-        model, opt, _ = group_sharded_parallel(net, opt, level)
-        for _ in range(3):
-            sl = slice(r * 4, (r + 1) * 4)
-            loss = ((model(x[sl]) - y[sl]) ** 2).mean()
-            loss.backward()
-            opt.step()
+        for kind in ("adamw", "momentum"):
+            paddle.seed(21)
+            net = nn.Sequential(nn.Linear(8, 32), nn.GELU(), nn.Linear(32, 16), nn.GELU(), nn.Linear(16, 4))
+            ref = nn.Sequential(nn.Linear(8, 32), nn.GELU(), nn.Linear(32, 16), nn.GELU(), nn.Linear(16, 4))
+            ref.set_state_dict(net.state_dict())
+            x, y = paddle.randn([8, 8]), paddle.randn([8, 4])
+
+            def mk(ps):
+                clip = paddle.nn.ClipGradByGlobalNorm(0.5)
+                if kind == "adamw":
+                    return paddle.optimizer.AdamW(1e-2, parameters=ps, weight_decay=0.05, grad_clip=clip)
+                return paddle.optimizer.Momentum(0.05, momentum=0.9, parameters=ps, grad_clip=clip)
+
+            opt, ropt = mk(net.parameters()), mk(ref.parameters())
+            model, opt, _ = group_sharded_parallel(net, opt, level)
+            for it in range(3):
+                for half in range(2):                      # two backward passes per step (gradient accumulation)
+                    sl = slice(r * 4 + half * 2, r * 4 + half * 2 + 2)
+                    loss = ((model(x[sl]) - y[sl]) ** 2).mean() / 2
+                    loss.backward()
+                opt.step()
+                opt.clear_grad()
+                rl = ((ref(x) - y) ** 2).mean()
+                rl.backward()
+                ropt.step()
+                ropt.clear_grad()
+            sd = model.state_dict()
+            for (k, a), (_, b) in zip(sd.items(), ref.state_dict().items()):
+                close(a.numpy(), b.numpy(), 2e-3)
+            if level == "os_g" and kind == "adamw":
+                assert isinstance(opt, GroupShardedOptimizerStage2) and len(opt.arena.slabs[0]["buckets"]) > 1
+                osd, rsd = opt.state_dict(), ropt.state_dict()
+                for p, rp in zip(net.parameters(), ref.parameters()):
+                    assert list(osd[f"{p.name}_moment1_0"].shape) == list(p.shape)
+                    close(osd[f"{p.name}_moment1_0"].numpy(), rsd[f"{rp.name}_moment1_0"].numpy(), 2e-3)
+                before = {k: v.numpy().copy() for k, v in model.state_dict().items()}
+                opt.set_state_dict(osd)                   # round trip keeps training identical
+                ((model(x[r * 4:(r + 1) * 4]) - y[r * 4:(r + 1) * 4]) ** 2).mean().backward()
+                opt.step()
+                opt.clear_grad()
+                ((ref(x) - y) ** 2).mean().backward()
+                ropt.step()
+                ropt.clear_grad()
+                for (k, a), (_, b) in zip(model.state_dict().items(), ref.state_dict().items()):
+                    close(a.numpy(), b.numpy(), 3e-3)
+        # loss scaling: an overflow seen by one rank only skips the update everywhere and halves the scale
+        paddle.seed(22)
+        net = nn.Sequential(nn.Linear(8, 16), nn.Linear(16, 4))
+        opt = paddle.optimizer.AdamW(1e-2, parameters=net.parameters())
+        scaler = paddle.amp.GradScaler(init_loss_scaling=1024.0, decr_every_n_nan_or_inf=1, incr_every_n_steps=1000)
+        model, opt, scaler = group_sharded_parallel(net, opt, level, scaler=scaler)
+        x = paddle.randn([4, 8])
+        w0 = {k: v.numpy().copy() for k, v in model.state_dict().items()}
+        for it in range(2):
+            xin = x * (float("inf") if (it == 0 and r == 1) else 1.0)
+            loss = (model(xin) ** 2).mean()
+            scaler.scale(loss).backward()
+            scaler.step(opt)
+            scaler.update()
             opt.clear_grad()
-            rl = ((ref(x) - y) ** 2).mean()
-            rl.backward()
-            ropt.step()
-            ropt.clear_grad()
-        sd = model.state_dict()
-        for (k, a), (_, b) in zip(sd.items(), ref.state_dict().items()):
-            close(a.numpy(), b.numpy(), 1e-3)
+            now = {k: v.numpy().copy() for k, v in model.state_dict().items()}
+            if it == 0:
+                for k in w0:
+                    close(now[k], w0[k], 1e-7)
+                assert abs(float(scaler._scale) - 512.0) < 1e-3
+            else:
+                assert any(not np.allclose(now[k], w0[k]) for k in w0)
+    os.environ.pop("B200_SHARD_BUCKET_MB", None)
 
 
 def case_auto_parallel():
@@ -546,6 +599,52 @@ def case_dist_checkpoint():
     D.load_state_dict(tgt, path)
     close(tgt["a"]._local_value().numpy(), g1[:, r * 6:(r + 1) * 6].numpy())
     close(tgt["b"]._local_value().numpy(), g2.numpy())
+
+
+def case_dist_checkpoint_mp():
+    """fleet tensor-parallel layers through the distributed checkpoint: every mp rank must get ITS OWN block back (shard metadata on
+    Column / Row / VocabParallel parameters and on their optimizer state), not the last writer's."""
+    s, hcg = setup(mp=2)
+    r = hcg.get_model_parallel_rank()
+    import paddle_b200.distributed as D
+    from paddle_b200.distributed.fleet import mp_layers as mpu
+
+    paddle.seed(7)
+    net = nn.Sequential(mpu.VocabParallelEmbedding(16, 8), mpu.ColumnParallelLinear(8, 12, has_bias=True, gather_output=False),
+                        mpu.RowParallelLinear(12, 8, has_bias=True, input_is_parallel=True))
+    fleet.distributed_model(net)
+    opt = paddle.optimizer.AdamW(1e-2, parameters=net.parameters())
+    ids = paddle.to_tensor(np.arange(8).reshape(2, 4))
+    (net(ids) ** 2).mean().backward()
+    opt.step()
+    opt.clear_grad()
+    assert net[1].weight.__dict__["_dist_shard"] == ((8, 12), (0, 6 * r)) and net[2].weight.__dict__["_dist_shard"][1] == (6 * r, 0)
+    want = {k: v.numpy().copy() for k, v in net.state_dict().items()}
+    osd = opt.state_dict()
+    want_m = {k: v.numpy().copy() for k, v in osd.items() if k.endswith("_moment1_0")}
+    path = os.environ.get("B200_TEST_TMP", "/tmp") + "/dist_ckpt_mp_case"
+    D.save_state_dict(net.state_dict(), path + "/model")
+    D.save_state_dict({k: v for k, v in osd.items() if hasattr(v, "shape")}, path + "/opt")
+    with paddle.no_grad():
+        for p in net.parameters():
+            p.zero_()
+    sd = net.state_dict()
+    D.load_state_dict(sd, path + "/model")
+    for k, v in net.state_dict().items():
+        close(v.numpy(), want[k], 1e-6)
+    tgt = {k: v for k, v in opt.state_dict().items() if hasattr(v, "shape")}
+    for k, v in tgt.items():
+        if k.endswith("_moment1_0"):
+            with paddle.no_grad():
+                v.zero_()
+    D.load_state_dict(tgt, path + "/opt")
+    for k, v in want_m.items():
+        close(tgt[k].numpy(), v, 1e-6)
+    # the two mp ranks really hold different blocks (otherwise the test proves nothing)
+    w = torch.tensor(want["1.weight"])
+    both = [torch.zeros_like(w) for _ in range(2)]
+    torch.distributed.all_gather(both, w)
+    assert not torch.allclose(both[0], both[1])
 
 
 def case_p2p_kernels():
