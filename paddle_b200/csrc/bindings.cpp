@@ -424,6 +424,143 @@ Tensor gemm(const Tensor& a, const Tensor& b, const OptT& bias, bool a_is_km, bo
   return d;
 }
 
+// Grouped GEMM over stacked expert weights (see GemmArgs::grouped == 1): a [Mpad, K] rows grouped by expert in 256-row aligned
+// segments, b [E, K, N] (or [E, N, K] with b_is_nk), tile_expert int32 [Mpad / 256] -> out [Mpad, N].
+Tensor gemm_grouped(const Tensor& a, const Tensor& b, const Tensor& tile_expert, bool b_is_nk, const OptT& out) {
+  TORCH_CHECK(a.is_cuda() && a.dim() == 2 && b.dim() == 3 && a.is_contiguous() && b.is_contiguous() && a.scalar_type() == b.scalar_type(),
+              "gemm_grouped: a [M,K] and stacked b [E,*,*] contiguous, same dtype");
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 || a.scalar_type() == at::kHalf, "gemm_grouped: bf16 / fp16 only");
+  const int64_t m = a.size(0), k = a.size(1), n = b_is_nk ? b.size(1) : b.size(2), kb = b_is_nk ? b.size(2) : b.size(1);
+  TORCH_CHECK(k == kb && m % 256 == 0 && m >= 256 && n >= 256 && k % 8 == 0 && n % 8 == 0, "gemm_grouped: M multiple of 256, N >= 256, K/N multiples of 8");
+  TORCH_CHECK(tile_expert.is_cuda() && tile_expert.scalar_type() == at::kInt && tile_expert.numel() == m / 256 && tile_expert.is_contiguous(),
+              "gemm_grouped: tile_expert must be int32 [M / 256] on the device");
+  c10::cuda::CUDAGuard guard(a.device());
+  Tensor d = out.has_value() && out->defined() ? *out : torch::empty({m, n}, a.options());
+  TORCH_CHECK(d.is_contiguous() && d.size(0) == m && d.size(1) == n, "gemm_grouped: out must be [M, N] contiguous");
+  b200::GemmArgs g;
+  g.m = (int)m; g.n = (int)n; g.k = (int)k; g.batch = 1;
+  g.a = a.data_ptr(); g.b = b.data_ptr(); g.d = d.data_ptr(); g.bias = nullptr;
+  g.lda = k; g.ldb = b.stride(1); g.ldd = n;
+  g.a_is_km = 0; g.b_is_nk = b_is_nk; g.epilogue = 0; g.dtype = dt_code(a); g.out_dtype = dt_code(d);
+  g.stride_a = 0; g.stride_b = b.stride(0); g.stride_d = 0;
+  g.grouped = 1; g.groups = (int)b.size(0); g.tile_expert = tile_expert.data_ptr<int>();
+  int rc = b200::gemm_tcgen05_2cta(g, cur_stream());
+  g_launches += 1;
+  check_err();
+  TORCH_CHECK(rc == 0, "paddle_b200.gemm_grouped launch failed rc=", rc);
+  return d;
+}
+
+// Per-expert weight gradients (GemmArgs::grouped == 2): out[e] += x[rows_e]^T @ dy[rows_e]; x [R, K_in], dy [R, N], out [E, K_in, N];
+// expert_k0 / expert_kb int32 [E] = first row and number of 64-row blocks of every expert's (padded) segment.
+void gemm_grouped_wgrad(const Tensor& x, const Tensor& dy, const Tensor& expert_k0, const Tensor& expert_kb, Tensor out) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && dy.dim() == 2 && x.is_contiguous() && dy.is_contiguous() && x.size(0) == dy.size(0) &&
+              x.scalar_type() == dy.scalar_type(), "gemm_grouped_wgrad: x [R,K] and dy [R,N] contiguous, same dtype");
+  TORCH_CHECK(out.dim() == 3 && out.is_contiguous() && out.size(1) == x.size(1) && out.size(2) == dy.size(1), "gemm_grouped_wgrad: out must be [E, K, N]");
+  TORCH_CHECK(expert_k0.scalar_type() == at::kInt && expert_kb.scalar_type() == at::kInt && expert_k0.numel() == out.size(0) && expert_kb.numel() == out.size(0) &&
+              expert_k0.is_cuda() && expert_kb.is_cuda(), "gemm_grouped_wgrad: expert_k0 / expert_kb int32 [E] on the device");
+  TORCH_CHECK(x.size(1) >= 256 && dy.size(1) >= 256 && x.size(1) % 8 == 0 && dy.size(1) % 8 == 0 && x.size(0) % 64 == 0, "gemm_grouped_wgrad: shapes");
+  c10::cuda::CUDAGuard guard(x.device());
+  b200::GemmArgs g;
+  g.m = (int)x.size(1); g.n = (int)dy.size(1); g.k = (int)x.size(0); g.batch = 1;
+  g.a = x.data_ptr(); g.b = dy.data_ptr(); g.d = out.data_ptr(); g.bias = nullptr;
+  g.lda = x.size(1); g.ldb = dy.size(1); g.ldd = out.size(2);
+  g.a_is_km = 1; g.b_is_nk = 0; g.epilogue = 4; g.dtype = dt_code(x); g.out_dtype = dt_code(out);
+  g.stride_a = 0; g.stride_b = 0; g.stride_d = out.stride(0);
+  g.grouped = 2; g.groups = (int)out.size(0); g.expert_k0 = expert_k0.data_ptr<int>(); g.expert_kb = expert_kb.data_ptr<int>();
+  int rc = b200::gemm_tcgen05_2cta(g, cur_stream());
+  g_launches += 1;
+  check_err();
+  TORCH_CHECK(rc == 0, "paddle_b200.gemm_grouped_wgrad launch failed rc=", rc);
+}
+
+// ------------------------------------------------------------------------------------------------ MoE routing (csrc/moe.cu)
+static void check_i64(const Tensor& t, const char* what) {
+  TORCH_CHECK(t.is_cuda() && t.is_contiguous() && t.scalar_type() == at::kLong, what, ": int64 CUDA contiguous tensor expected");
+}
+Tensor moe_number_count(const Tensor& idx, int64_t upper) {
+  check_i64(idx, "number_count");
+  c10::cuda::CUDAGuard guard(idx.device());
+  Tensor counts = torch::zeros({upper}, idx.options());
+  b200::moe_number_count(idx.data_ptr<int64_t>(), idx.numel(), counts.data_ptr<int64_t>(), (int)upper, cur_stream());
+  g_launches += 1; check_err();
+  return counts;
+}
+Tensor moe_assign_pos(const Tensor& idx, const Tensor& cum_count, int64_t n_valid) {
+  check_i64(idx, "assign_pos"); check_i64(cum_count, "assign_pos");
+  c10::cuda::CUDAGuard guard(idx.device());
+  Tensor cursor = cum_count.clone();
+  Tensor pos = torch::empty({n_valid}, idx.options());
+  b200::moe_assign_pos(idx.data_ptr<int64_t>(), idx.numel(), cursor.data_ptr<int64_t>(), pos.data_ptr<int64_t>(), cur_stream());
+  g_launches += 1; check_err();
+  return pos;
+}
+Tensor moe_limit_by_capacity(const Tensor& expert_count, const Tensor& capacity, int64_t n_worker) {
+  check_i64(expert_count, "limit_by_capacity"); check_i64(capacity, "limit_by_capacity");
+  c10::cuda::CUDAGuard guard(expert_count.device());
+  const int n_expert = (int)capacity.numel();
+  TORCH_CHECK(expert_count.numel() == n_expert * n_worker, "limit_by_capacity: expert_count must hold n_worker * n_expert entries");
+  Tensor out = torch::empty_like(expert_count);
+  b200::moe_limit_by_capacity(expert_count.data_ptr<int64_t>(), capacity.data_ptr<int64_t>(), out.data_ptr<int64_t>(), n_expert, (int)n_worker, cur_stream());
+  g_launches += 1; check_err();
+  return out;
+}
+Tensor moe_prune_gate_by_capacity(const Tensor& gate_idx, const Tensor& expert_count) {
+  check_i64(gate_idx, "prune_gate_by_capacity"); check_i64(expert_count, "prune_gate_by_capacity");
+  c10::cuda::CUDAGuard guard(gate_idx.device());
+  Tensor remaining = expert_count.clone();
+  Tensor out = torch::empty_like(gate_idx);
+  b200::moe_prune_gate(gate_idx.data_ptr<int64_t>(), gate_idx.numel(), remaining.data_ptr<int64_t>(), out.data_ptr<int64_t>(), cur_stream());
+  g_launches += 1; check_err();
+  return out;
+}
+// expert ids of the token slots ([S] int64, -1 = dropped) -> (dest int32 [S], tile_expert int32 [MT], expert_k0 int32 [E], expert_kb int32 [E],
+// seg_start int32 [E+1], counts int64 [E]); rows_cap = static upper bound of the padded row count (multiple of 256)
+std::vector<Tensor> moe_route(const Tensor& idx, int64_t n_expert, int64_t rows_cap) {
+  check_i64(idx, "moe_route");
+  TORCH_CHECK(rows_cap % 256 == 0 && rows_cap > 0, "moe_route: rows_cap must be a positive multiple of 256");
+  c10::cuda::CUDAGuard guard(idx.device());
+  auto i32 = idx.options().dtype(at::kInt);
+  Tensor counts = torch::zeros({n_expert}, idx.options());
+  Tensor dest = torch::empty({idx.numel()}, i32), tile_expert = torch::empty({rows_cap / 256}, i32);
+  Tensor k0 = torch::empty({n_expert}, i32), kb = torch::empty({n_expert}, i32), seg = torch::empty({n_expert + 1}, i32), cursor = torch::empty({n_expert}, i32);
+  auto st = cur_stream();
+  b200::moe_number_count(idx.data_ptr<int64_t>(), idx.numel(), counts.data_ptr<int64_t>(), (int)n_expert, st);
+  b200::moe_plan(counts.data_ptr<int64_t>(), (int)n_expert, (int)(rows_cap / 256), seg.data_ptr<int>(), cursor.data_ptr<int>(), tile_expert.data_ptr<int>(),
+                 k0.data_ptr<int>(), kb.data_ptr<int>(), st);
+  b200::moe_dest(idx.data_ptr<int64_t>(), idx.numel(), cursor.data_ptr<int>(), dest.data_ptr<int>(), st);
+  g_launches += 3; check_err();
+  return {dest, tile_expert, k0, kb, seg, counts};
+}
+Tensor moe_rows_scatter(const Tensor& src, const Tensor& dest, const OptT& scale, int64_t topk, int64_t rows_out) {
+  TORCH_CHECK(src.is_cuda() && src.dim() == 2 && src.is_contiguous() && dest.scalar_type() == at::kInt && dest.is_contiguous(), "moe_rows_scatter: bad operands");
+  c10::cuda::CUDAGuard guard(src.device());
+  Tensor dst = torch::zeros({rows_out, src.size(1)}, src.options());
+  const float* sc = scale.has_value() && scale->defined() ? scale->data_ptr<float>() : nullptr;
+  b200::moe_rows_scatter(src.data_ptr(), dest.data_ptr<int>(), sc, dest.numel(), (int)topk, (int)src.size(1), dst.data_ptr(), dt_code(src), cur_stream());
+  g_launches += 1; check_err();
+  return dst;
+}
+Tensor moe_rows_combine(const Tensor& src, const Tensor& dest, const OptT& w, int64_t topk) {
+  TORCH_CHECK(src.is_cuda() && src.dim() == 2 && src.is_contiguous() && dest.scalar_type() == at::kInt && dest.is_contiguous() && dest.numel() % topk == 0,
+              "moe_rows_combine: bad operands");
+  c10::cuda::CUDAGuard guard(src.device());
+  const int64_t n_tok = dest.numel() / topk;
+  Tensor out = torch::empty({n_tok, src.size(1)}, src.options());
+  const float* wp = w.has_value() && w->defined() ? w->data_ptr<float>() : nullptr;
+  b200::moe_rows_combine(src.data_ptr(), dest.data_ptr<int>(), wp, n_tok, (int)topk, (int)src.size(1), out.data_ptr(), dt_code(src), cur_stream());
+  g_launches += 1; check_err();
+  return out;
+}
+Tensor moe_rows_dot(const Tensor& src, const Tensor& dest, const Tensor& g, int64_t topk) {
+  TORCH_CHECK(src.is_cuda() && src.is_contiguous() && g.is_contiguous() && src.scalar_type() == g.scalar_type() && src.size(1) == g.size(1), "moe_rows_dot: bad operands");
+  c10::cuda::CUDAGuard guard(src.device());
+  Tensor dw = torch::empty({dest.numel()}, src.options().dtype(at::kFloat));
+  b200::moe_rows_dot(src.data_ptr(), dest.data_ptr<int>(), g.data_ptr(), dest.numel(), (int)topk, (int)src.size(1), dw.data_ptr<float>(), dt_code(src), cur_stream());
+  g_launches += 1; check_err();
+  return dw;
+}
+
 // D = act(scale * A[M,K] @ B[N,K]^T + bias), A/B fp8 (e4m3 / e5m2), D half / bf16 / fp32
 Tensor gemm_fp8(const Tensor& a, const Tensor& b, const OptT& bias, double scale, int64_t act, at::ScalarType out_dtype) {
   TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.dim() == 2 && b.dim() == 2 && a.is_contiguous() && b.is_contiguous() && a.size(1) == b.size(1),
@@ -603,6 +740,19 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         pybind11::arg("out_dtype") = pybind11::none(), pybind11::arg("rs_dst") = std::vector<int64_t>(), pybind11::arg("rs_rows") = 0,
         pybind11::arg("ag_src") = std::vector<int64_t>(), pybind11::arg("ag_pad") = std::vector<int64_t>(), pybind11::arg("ag_flags") = pybind11::none(),
         pybind11::arg("ag_rank") = 0, pybind11::arg("ag_rows") = 0, pybind11::arg("ag_epoch") = 0);
+  m.def("moe_number_count", traced("moe_number_count", &moe_number_count));
+  m.def("moe_assign_pos", traced("moe_assign_pos", &moe_assign_pos));
+  m.def("moe_limit_by_capacity", traced("moe_limit_by_capacity", &moe_limit_by_capacity));
+  m.def("moe_prune_gate_by_capacity", traced("moe_prune_gate_by_capacity", &moe_prune_gate_by_capacity));
+  m.def("moe_route", traced("moe_route", &moe_route));
+  m.def("moe_rows_scatter", traced("moe_rows_scatter", &moe_rows_scatter), pybind11::arg("src"), pybind11::arg("dest"), pybind11::arg("scale") = pybind11::none(),
+        pybind11::arg("topk") = 1, pybind11::arg("rows_out") = 0);
+  m.def("moe_rows_combine", traced("moe_rows_combine", &moe_rows_combine), pybind11::arg("src"), pybind11::arg("dest"), pybind11::arg("w") = pybind11::none(),
+        pybind11::arg("topk") = 1);
+  m.def("moe_rows_dot", traced("moe_rows_dot", &moe_rows_dot));
+  m.def("gemm_grouped", traced("gemm_grouped", &gemm_grouped), pybind11::arg("a"), pybind11::arg("b"), pybind11::arg("tile_expert"), pybind11::arg("b_is_nk") = false,
+        pybind11::arg("out") = pybind11::none());
+  m.def("gemm_grouped_wgrad", traced("gemm_grouped_wgrad", &gemm_grouped_wgrad));
   m.def("gemm_fp8", traced("gemm_fp8", &gemm_fp8));
   m.def("decode_attention", traced("decode_attention", &decode_attention));
   m.def("attention_supported", &attention_supported);

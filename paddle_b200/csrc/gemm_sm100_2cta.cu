@@ -182,6 +182,11 @@ struct Params {
   int in_dtype, out_dtype;
   int has_bias, act, accumulate;
   uint32_t idesc;
+  // grouped GEMM (MoE experts, see GemmArgs::grouped): 1 = rows grouped by expert (tile -> expert table), 2 = per-expert weight gradient
+  int grouped;
+  const int* tile_expert;
+  const int* expert_k0;
+  const int* expert_kb;
   int rs_world, rs_rows;   // fused reduce-scatter push (see GemmArgs)
   void* rs_dst[8];
   // fused all-gather -> GEMM (see GemmArgs): warp 3 of every CTA pulls the peers' row shards into the local A buffer
@@ -358,6 +363,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     }
   };
 
+  // grouped modes: which batch index each operand uses for this tile, the reduction range, and whether the tile exists at all
+  auto tile_group = [&](int bz, int mb, int& za, int& zb, int& zd, int& kbeg, int& nkb) -> bool {
+    za = zb = zd = bz; kbeg = 0; nkb = num_kb;
+    if (p.grouped == 1) {
+      const int e = p.tile_expert[mb];
+      if (e < 0) return false;           // padding tile beyond the last expert's rows
+      za = 0; zb = e; zd = 0;
+    } else if (p.grouped == 2) {
+      nkb = p.expert_kb[bz];
+      if (nkb <= 0) return false;        // expert received no rows: its weight gradient gets nothing added
+      kbeg = p.expert_k0[bz];
+      za = 0; zb = 0; zd = bz;
+    }
+    return true;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
       // ================= TMA producer (both CTAs: own A rows, own half of B) =================
@@ -367,6 +388,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         int bz, mb, nb;
         tile_coords(tile, bz, mb, nb);
+        int za, zb, zd, kbeg, nkb;
+        if (!tile_group(bz, mb, za, zb, zd, kbeg, nkb)) continue;
         const int m0 = mb * 2 * BLOCK_M + (int)cta_rank * BLOCK_M;
         const int n0 = nb * BLOCK_N + (int)cta_rank * HALF_N;
         if (p.ag_world > 1) {
@@ -376,23 +399,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy writes (other SMs) -> TMA (async proxy) reads
           }
         }
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
           if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
-          const int k0 = kb * BLOCK_K;
+          const int k0 = kbeg + kb * BLOCK_K;
           if constexpr (!A_MN) {
-            tma_load_3d_2sm(sa, &map_a, full_bar(stage), k0, m0, bz, hint);
+            tma_load_3d_2sm(sa, &map_a, full_bar(stage), k0, m0, za, hint);
           } else {
 #pragma unroll
-            for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_3d_2sm(sa + i * 8192, &map_a, full_bar(stage), m0 + i * 64, k0, bz, hint);
+            for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_3d_2sm(sa + i * 8192, &map_a, full_bar(stage), m0 + i * 64, k0, za, hint);
           }
           if constexpr (!B_MN) {
-            tma_load_3d_2sm(sb, &map_b, full_bar(stage), k0, n0, bz, hint);
+            tma_load_3d_2sm(sb, &map_b, full_bar(stage), k0, n0, zb, hint);
           } else {
 #pragma unroll
-            for (int i = 0; i < HALF_N / 64; ++i) tma_load_3d_2sm(sb + i * 8192, &map_b, full_bar(stage), n0 + i * 64, k0, bz, hint);
+            for (int i = 0; i < HALF_N / 64; ++i) tma_load_3d_2sm(sb + i * 8192, &map_b, full_bar(stage), n0 + i * 64, k0, zb, hint);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -404,13 +427,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int nkb = num_kb;
+        if (p.grouped) {
+          int bz, mb, nb, za, zb, zd, kbeg;
+          tile_coords(tile, bz, mb, nb);
+          if (!tile_group(bz, mb, za, zb, zd, kbeg, nkb)) continue;
+        }
         const int as = local & 1;
         const uint32_t aphase = (local >> 1) & 1;
+        ++local;
         mbar_wait(tempty_bar(as), aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
@@ -434,11 +464,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     const int ew = warp - 4;
     int local = 0;
     int tma_buf = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       int bz, mb, nb;
       tile_coords(tile, bz, mb, nb);
+      {
+        int za, zb, zd, kbeg, nkb;
+        if (!tile_group(bz, mb, za, zb, zd, kbeg, nkb)) continue;
+        bz = zd;                            // batch index of the OUTPUT for this tile
+      }
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
+      ++local;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const int row = mb * 2 * BLOCK_M + (int)cta_rank * BLOCK_M + ew * 32 + lane;
@@ -588,13 +624,16 @@ static uint32_t make_idesc(int in_dtype, bool a_mn, bool b_mn) {
 template <bool A_MN, bool B_MN>
 static int launch(const GemmArgs& g, cudaStream_t s) {
   CUtensorMap ma, mb;
-  const uint64_t batch = g.batch > 1 ? g.batch : 1;
+  uint64_t batch = g.batch > 1 ? g.batch : 1;
+  uint64_t batch_a = batch, batch_b = batch;
+  if (g.grouped == 1) { batch_a = 1; batch_b = g.groups; batch = 1; }             // rows grouped by expert: B = stacked expert weights
+  else if (g.grouped == 2) { batch_a = 1; batch_b = 1; batch = g.groups; }        // per-expert weight gradient: D = stacked [E, m, n]
   bool ok;
-  if (!A_MN) ok = gemm::make_map(&ma, g.a, g.k, g.m, batch, g.lda, g.stride_a, BLOCK_K, BLOCK_M, g.dtype);
-  else       ok = gemm::make_map(&ma, g.a, g.m, g.k, batch, g.lda, g.stride_a, 64, BLOCK_K, g.dtype);
+  if (!A_MN) ok = gemm::make_map(&ma, g.a, g.k, g.m, batch_a, g.lda, g.stride_a, BLOCK_K, BLOCK_M, g.dtype);
+  else       ok = gemm::make_map(&ma, g.a, g.m, g.k, batch_a, g.lda, g.stride_a, 64, BLOCK_K, g.dtype);
   if (!ok) return 2;
-  if (!B_MN) ok = gemm::make_map(&mb, g.b, g.k, g.n, batch, g.ldb, g.stride_b, BLOCK_K, HALF_N, g.dtype);
-  else       ok = gemm::make_map(&mb, g.b, g.n, g.k, batch, g.ldb, g.stride_b, 64, BLOCK_K, g.dtype);
+  if (!B_MN) ok = gemm::make_map(&mb, g.b, g.k, g.n, batch_b, g.ldb, g.stride_b, BLOCK_K, HALF_N, g.dtype);
+  else       ok = gemm::make_map(&mb, g.b, g.n, g.k, batch_b, g.ldb, g.stride_b, 64, BLOCK_K, g.dtype);
   if (!ok) return 2;
   Params p;
   p.m = g.m; p.n = g.n; p.k = g.k; p.batch = (int)batch;
@@ -603,6 +642,7 @@ static int launch(const GemmArgs& g, cudaStream_t s) {
   p.has_bias = (g.epilogue >= 1 && g.epilogue <= 3 && g.bias) ? 1 : 0;
   p.act = g.epilogue == 2 ? 1 : (g.epilogue == 3 ? 2 : 0);
   p.accumulate = g.epilogue == 4 ? 1 : 0;
+  p.grouped = g.grouped; p.tile_expert = g.tile_expert; p.expert_k0 = g.expert_k0; p.expert_kb = g.expert_kb;
   p.rs_world = g.rs_world > 1 ? g.rs_world : 0;
   p.rs_rows = g.rs_rows;
   for (int i = 0; i < 8; ++i) p.rs_dst[i] = g.rs_dst[i];

@@ -80,6 +80,17 @@ void lamb_stage1(const void* p, const void* g, const float* master, void* m, voi
 void lamb_stage2(void* p, float* master, const float* update, int64_t n, int p_dtype, float lr, const float* p_sq,
                  const float* u_sq, cudaStream_t s);
 
+// ---- moe.cu (routing on the device) ------------------------------------------------------------------------------
+void moe_number_count(const int64_t* idx, int64_t n, int64_t* counts, int upper, cudaStream_t s);
+void moe_assign_pos(const int64_t* idx, int64_t n, int64_t* cursor, int64_t* pos, cudaStream_t s);
+void moe_limit_by_capacity(const int64_t* ec, const int64_t* cap, int64_t* out, int n_expert, int n_worker, cudaStream_t s);
+void moe_prune_gate(const int64_t* idx, int64_t n, int64_t* remaining, int64_t* out, cudaStream_t s);
+void moe_plan(const int64_t* counts, int n_expert, int n_tiles, int* seg_start, int* cursor, int* tile_expert, int* k0, int* kb, cudaStream_t s);
+void moe_dest(const int64_t* idx, int64_t n, int* cursor, int* dest, cudaStream_t s);
+void moe_rows_scatter(const void* src, const int* dest, const float* scale, int64_t n_slots, int topk, int d, void* dst, int dtype, cudaStream_t s);
+void moe_rows_combine(const void* src, const int* dest, const float* w, int64_t n_tok, int topk, int d, void* out, int dtype, cudaStream_t s);
+void moe_rows_dot(const void* src, const int* dest, const void* g, int64_t n_slots, int topk, int d, float* dw, int dtype, cudaStream_t s);
+
 // ---- gemm_sm100.cu --------------------------------------------------------------------------------------------
 // D[M,N] = A[M,K] * B + bias, all row-major in memory.  b_is_nk: B stored [N,K] (K contiguous) else [K,N].
 // a_is_km: A stored [K,M] (M contiguous) else [M,K].  epilogue: 0 none, 1 bias, 2 bias+gelu, 3 bias+relu, 4 accumulate (D += )
@@ -109,6 +120,16 @@ struct GemmArgs {
   void* ag_pad[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void* ag_flags = nullptr;
   uint32_t ag_epoch = 0;
+  // Grouped GEMM over stacked expert weights (MoE), CTA-pair kernel only.  groups = number of experts E.
+  //   grouped == 1: A = [m, k] rows grouped by expert, every 256-row block belongs to ONE expert (segments padded to 256 rows);
+  //                 tile_expert[m / 256] (device int32) = expert of the block or -1 (padding past the last expert);
+  //                 B = stacked weights ([E, k, n] or [E, n, k] with b_is_nk, stride_b), D = [m, n].
+  //   grouped == 2: per-expert weight gradient D[e] (+)= A[rows_e, m]^T B[rows_e, n] (a_is_km, !b_is_nk): k = total rows,
+  //                 expert_k0[e] / expert_kb[e] (device int32) = first row and number of 64-row blocks of expert e; D = [E, m, n].
+  int grouped = 0, groups = 0;
+  const int* tile_expert = nullptr;
+  const int* expert_k0 = nullptr;
+  const int* expert_kb = nullptr;
 };
 // returns 0 on success, nonzero if the shape is unsupported by the tcgen05 path (caller falls back)
 int gemm_tcgen05(const GemmArgs& g, cudaStream_t s);

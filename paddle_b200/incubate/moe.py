@@ -29,22 +29,43 @@ def _w(t):
 
 
 # ---- gate utility ops (reference: moe/utils.py) -------------------------------------------------------------------
+def _dev_ext(t):
+    """The native extension when `t` lives on a GPU (csrc/moe.cu kernels: no host loop, no synchronisation), else None."""
+    if isinstance(t, torch.Tensor) and t.is_cuda:
+        from .._build import ext
+
+        return ext()
+    return None
+
+
 def _number_count(numbers, upper_range):
     n = _raw(numbers).reshape(-1).long()
+    e = _dev_ext(n)
+    if e is not None:
+        return _w(e.moe_number_count(n.contiguous(), int(upper_range)))
     return _w(torch.bincount(n[n >= 0], minlength=upper_range)[:upper_range])
 
 
 def _assign_pos(x, cum_count):
-    """Positions of tokens sorted by expert id (stable). cum_count = inclusive cumsum of per-expert counts."""
+    """Positions of tokens grouped by expert id. cum_count = inclusive cumsum of per-expert counts. CPU: stable order; GPU: the
+    reference kernel's semantics (assign_pos_kernel.cu: every token claims the next free position of its expert's range)."""
     idx = _raw(x).reshape(-1).long()
+    cum = _raw(cum_count).reshape(-1).long()
+    e = _dev_ext(idx)
+    if e is not None and cum.numel() > 0:
+        return _w(e.moe_assign_pos(idx.contiguous(), cum.contiguous(), int(idx.numel())))   # unclaimed tail entries only exist with dropped tokens
     order = torch.argsort(idx[idx >= 0] if bool((idx < 0).any()) else idx, stable=True)
     valid = torch.nonzero(idx >= 0).reshape(-1)
     return _w(valid[order])
 
 
 def _limit_by_capacity(expert_count, capacity, n_worker):
-    ec = _raw(expert_count).reshape(n_worker, -1)
-    cap = _raw(capacity).clone()
+    ec0, cap0 = _raw(expert_count).reshape(-1).long(), _raw(capacity).reshape(-1).long()
+    e = _dev_ext(ec0)
+    if e is not None:
+        return _w(e.moe_limit_by_capacity(ec0.contiguous(), cap0.contiguous(), int(n_worker)))
+    ec = ec0.reshape(n_worker, -1)
+    cap = cap0.clone()
     out = torch.zeros_like(ec)
     for w in range(n_worker):
         take = torch.minimum(ec[w], cap)
@@ -54,17 +75,18 @@ def _limit_by_capacity(expert_count, capacity, n_worker):
 
 
 def _prune_gate_by_capacity(gate_idx, expert_count, n_expert, n_worker):
-    g = _raw(gate_idx).reshape(-1).long().clone()
-    remaining = _raw(expert_count).reshape(-1).clone()
-    for i in range(g.numel()):
-        e = int(g[i])
-        if e < 0:
-            continue
-        if remaining[e] > 0:
-            remaining[e] -= 1
-        else:
-            g[i] = -1
-    return _w(g)
+    """Tokens beyond their expert's remaining capacity are dropped (-1).  CPU: arrival order, vectorised (rank of the token within its
+    expert via a one-hot cumulative sum); GPU: prune_gate_kernel (atomic countdown like prune_gate_by_capacity_kernel.cu:33)."""
+    g = _raw(gate_idx).reshape(-1).long()
+    remaining = _raw(expert_count).reshape(-1).long()
+    e = _dev_ext(g)
+    if e is not None:
+        return _w(e.moe_prune_gate_by_capacity(g.contiguous(), remaining.contiguous()))
+    valid = g >= 0
+    onehot = TF.one_hot(g.clamp(min=0), remaining.numel()) * valid.unsqueeze(-1)
+    rank_in_expert = (torch.cumsum(onehot, 0) * onehot).sum(-1)            # 1-based arrival rank inside the token's expert
+    keep = valid & (rank_in_expert <= remaining[g.clamp(min=0)])
+    return _w(torch.where(keep, g, torch.full_like(g, -1)))
 
 
 def _random_routing(topk_idx, topk_value, prob, topk=2):
@@ -156,6 +178,58 @@ class _FusedCombine(torch.autograd.Function):
     def backward(ctx, g):
         in_splits, out_splits, sc, cap = ctx.cfg
         return sc.a2av(g.contiguous(), out_splits, sum(in_splits), cap, tag="moe_dispatch"), None, None, None, None
+
+
+class _A2AVDev(torch.autograd.Function):
+    """Rows pushed to their destination ranks by the fused gather + all-to-all kernel, split sizes on the device.  backward = the
+    reverse push (+ scatter-add into the gathered source rows)."""
+
+    @staticmethod
+    def forward(ctx, x, gather, send_rows, recv_rows, sc, cap_out, cap_back, tag):
+        ctx.cfg = (sc, cap_back, tag, x.shape[0], gather is not None)
+        ctx.save_for_backward(send_rows, recv_rows, gather if gather is not None else send_rows)
+        out = sc.a2av_dev(x, send_rows, cap_out, gather=gather, tag=tag + "_f", rows_hint=(gather.numel() if gather is not None else x.shape[0]))
+        # dispatch: the consumer copies the rows into the grouped layout at once and keeps nothing -> hand out the symmetric buffer itself;
+        # return: the combine keeps its input for the gate-weight gradient, and the buffer is reused by the next layer -> copy ([S, d] only)
+        return out if gather is not None else out.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        sc, cap_back, tag, n_src, has_gather = ctx.cfg
+        send_rows, recv_rows, gather = ctx.saved_tensors
+        rows = sc.a2av_dev(g.contiguous(), recv_rows, cap_back, gather=None, tag=tag + "_b", rows_hint=g.shape[0])
+        if has_gather:
+            dx = torch.zeros((n_src, g.shape[-1]), dtype=g.dtype, device=g.device)
+            n = min(rows.shape[0], gather.shape[0])
+            # rows beyond what came back are stale: they belong to dropped slots, whose sorted position is past every valid one
+            valid = (torch.arange(n, device=g.device) < send_rows.sum()).unsqueeze(-1)
+            dx.index_add_(0, gather[:n], torch.where(valid, rows[:n], torch.zeros_like(rows[:n])))
+            return dx, None, None, None, None, None, None, None
+        return rows.clone(), None, None, None, None, None, None, None
+
+
+class _EPExperts(torch.autograd.Function):
+    """dispatch push -> grouped expert FFN -> return push, as one differentiable unit built from differentiable pieces."""
+
+    @staticmethod
+    def forward(ctx, *a):
+        raise RuntimeError("use _EPExperts.apply")
+
+    @classmethod
+    def apply(cls, x, tok_sorted, send_rows, recv_rows, row_e, w1, w2, layer, sc, cap, S):
+        from ..kernels import moe as KM
+
+        xs = _A2AVDev.apply(x, tok_sorted, send_rows, recv_rows, sc, cap, S, "moe_ep_dispatch")          # [cap, d], rows of my experts
+        plan = KM.route(row_e, layer.num_expert, KM.rows_cap(cap, layer.num_expert))
+        xp = KM._Dispatch.apply(xs, plan["dest"], 1, plan["cap"])
+        h = KM.grouped_linear(xp, layer.experts.w1, plan)
+        from ..kernels import activation as KA
+
+        act = layer.experts.activation
+        a = _raw(KA.swiglu(h)) if act == "swiglu" else (TF.gelu(h) if act == "gelu" else torch.relu(h))
+        y = KM.grouped_linear(a, layer.experts.w2, plan)
+        ys = KM._Combine.apply(y, plan["dest"], None, 1)                                                  # back in arrival order [cap, d]
+        return _A2AVDev.apply(ys, None, recv_rows, send_rows, sc, S, cap, "moe_ep_return")               # [S, d] in my sorted-slot order
 
 
 class _AllToAll(torch.autograd.Function):
@@ -314,6 +388,12 @@ def moe_ffn(x, gate_weight, ffn1_weight, ffn1_bias, ffn2_weight, ffn2_bias, topk
     if norm_topk_prob:
         val = val / val.sum(-1, keepdim=True)
     E = _raw(ffn1_weight).shape[0]
+    from ..kernels import moe as KM
+
+    if KM.grouped_ok(x2, _raw(ffn1_weight), _raw(ffn2_weight)) and ffn1_bias is None and ffn2_bias is None:
+        act_g = "swiglu" if _raw(ffn1_weight).shape[-1] == 2 * _raw(ffn2_weight).shape[1] else "gelu"
+        out = KM.expert_ffn_grouped(x2, idx, val.to(torch.float32), ffn1_weight, ffn2_weight, act_g)   # grouped tcgen05 GEMMs, routing on the device
+        return _w(out.reshape(shape))
     flat_e = idx.reshape(-1)
     order = torch.argsort(flat_e, stable=True)
     tok = torch.arange(x2.shape[0], device=x2.device).repeat_interleave(topk)[order]
@@ -349,9 +429,11 @@ class MoELayer(Layer):
     gate: dict(type='gshard'|'switch'|'naive', top_k=..) or a BaseGate instance. moe_group: expert-parallel group.
     """
 
-    def __init__(self, d_model, experts, gate=None, moe_group=None, mp_group=None, recompute_interval=0, recompute_ctx=None):
+    def __init__(self, d_model, experts, gate=None, moe_group=None, mp_group=None, recompute_interval=0, recompute_ctx=None,
+                 ep_capacity_factor=2.0):
         super().__init__()
         self.d_model, self.group = d_model, moe_group
+        self.ep_capacity_factor = float(ep_capacity_factor)   # device-side expert-parallel path: receive capacity = factor x local slots
         self.world_size = _world(moe_group) if (moe_group is not None or dist.is_initialized()) else 1
         if moe_group is None:
             self.world_size = 1
@@ -380,6 +462,16 @@ class MoELayer(Layer):
         val, idx = _raw(val), _raw(idx)
         k = idx.shape[-1]
         probs = torch.softmax(val.float(), -1) if not isinstance(self.gate, SwitchGate) else val.float()
+        from ..kernels import moe as KM
+
+        grouped = isinstance(self.experts, ExpertFFN) and KM.grouped_ok(x, _raw(self.experts.w1), _raw(self.experts.w2))
+        if grouped and self.world_size == 1:
+            out = KM.expert_ffn_grouped(x, idx.long(), probs, self.experts.w1, self.experts.w2, self.experts.activation)
+            return _w(out.reshape(shape))
+        if grouped and self.world_size > 1:
+            out = self._forward_ep_device(x, idx.long(), probs)
+            if out is not None:
+                return _w(out.reshape(shape))
         flat_e = idx.reshape(-1)
         keep = flat_e >= 0
         tok_all = torch.arange(x.shape[0], device=x.device).repeat_interleave(k)
@@ -424,6 +516,45 @@ class MoELayer(Layer):
             y = self._run_experts(x[tok], local_count.tolist())
         out = torch.zeros_like(x).index_add(0, tok, y * w[:, None].to(y.dtype))
         return _w(out.reshape(shape))
+
+    def _forward_ep_device(self, x, idx, probs):
+        """Expert parallelism with every decision on the device: slots are sorted by destination, the per-(rank, expert) counts are
+        exchanged with a tiny peer-memory all-to-all, rows travel with the fused gather + all-to-all push kernel (split sizes read from
+        device memory), the local experts run as grouped tcgen05 GEMMs over a device-built plan, and the reverse push + a weighted
+        top-k combine finish the layer.  No .item() / .tolist() / NCCL call anywhere."""
+        from ..kernels import moe as KM
+
+        sc = _symm_ctx(self.group, x)
+        if sc is None:
+            return None
+        W, El = self.world_size, self.num_expert
+        T, k = idx.shape
+        S, d = T * k, x.shape[-1]
+        tot = W * El
+        # static receive capacity: every source rank sends at most C slots to any one expert (slots beyond that are dropped, the
+        # usual capacity rule of GShard / Switch routing), so a rank receives at most W * El * C = ep_capacity_factor * S rows
+        cf = float(getattr(self, "ep_capacity_factor", 2.0))
+        C = max(1, math.ceil(cf * S / tot))
+        cap = (W * El * C + 255) // 256 * 256
+        need = (cap + S) * d * x.element_size() + (64 << 20)
+        if need > sc.heap.size() - sc._base_cursor:
+            return None
+        flat_e = _raw(_prune_gate_by_capacity(idx.reshape(-1), torch.full((tot,), C, dtype=torch.int64, device=x.device), tot, 1))
+        key = torch.where(flat_e >= 0, flat_e, torch.full_like(flat_e, tot))
+        order = torch.argsort(key, stable=True)                        # slots grouped by destination rank (then expert); dropped slots last
+        tok_sorted = torch.div(order, k, rounding_mode="floor")
+        local_count = _raw(_number_count(flat_e, tot)).reshape(W, El)  # what this rank sends, per (rank, expert)
+        global_count = sc.exchange_counts(local_count, tag="moe_counts")   # [src rank, local expert]: what arrives here
+        send_rows, recv_rows = local_count.sum(1), global_count.sum(1)
+        inv = torch.empty_like(order)
+        inv[order] = torch.arange(S, device=x.device)
+        dest_back = torch.where(flat_e >= 0, inv, torch.full_like(inv, -1)).to(torch.int32)   # slot -> row of the returned buffer
+        # rows received from (src rank, local expert) segments -> local expert id per row (-1 beyond what arrived)
+        bounds = torch.cumsum(global_count.reshape(-1), 0)
+        seg = torch.bucketize(torch.arange(cap, device=x.device), bounds, right=True)
+        row_e = torch.where(seg < tot, seg % El, torch.full_like(seg, -1))
+        y_back = _EPExperts.apply(x, tok_sorted, send_rows, recv_rows, row_e, _raw(self.experts.w1), _raw(self.experts.w2), self, sc, cap, S)
+        return KM._Combine.apply(y_back, dest_back, probs, k)
 
     def _run_experts(self, x, counts):
         if isinstance(self.experts, ExpertFFN):

@@ -228,5 +228,33 @@ def _a2av_capacity(self, rows_in, rows_out, x):
     return cap if cap * h * x.element_size() <= limit else 0
 
 
+def _a2av_dev(self, src, in_splits_dev, cap, gather=None, tag="a2av", rows_hint=None):
+    """Variable all-to-all whose split sizes stay on the device (no host synchronisation): in_splits_dev = int64 [world] CUDA tensor of
+    rows sent to every rank (slots grouped by destination).  Returns the whole symmetric receive buffer [cap, H]; the rows beyond what
+    the peers sent are stale - the caller masks them with the counts it exchanged (see exchange_counts)."""
+    h = src.shape[-1]
+    recv, roff = self.buffer((tag, "recv"), (int(cap), h), src.dtype)
+    meta, moff = self.buffer((tag, "meta"), (self.world,), torch.int64)
+    meta.copy_(in_splits_dev.reshape(-1).to(torch.int64))
+    hint = int(rows_hint if rows_hint is not None else (gather.numel() if gather is not None else src.shape[0]))
+    self.heap.a2av(src.contiguous(), gather, moff, roff, max(hint, 1), self.next_epoch())
+    return recv
+
+
+def _exchange_counts(self, counts, tag="a2a_counts"):
+    """counts: int64 [world, n] on the device (row r = what this rank sends to rank r). Returns [world, n]: row s = what rank s sends
+    to this rank.  One tiny peer-memory all-to-all; nothing touches the host."""
+    w, n = counts.shape
+    npad = (n + 1) // 2 * 2                      # 16-byte chunks
+    send, soff = self.buffer((tag, "send", npad), (w, npad), torch.int64)
+    recv, roff = self.buffer((tag, "recv", npad), (w, npad), torch.int64)
+    send.zero_()
+    send[:, :n].copy_(counts)
+    self.heap.alltoall(soff, roff, npad * 8, self.next_epoch())
+    return recv[:, :n].clone()
+
+
+SymmContext.a2av_dev = _a2av_dev
+SymmContext.exchange_counts = _exchange_counts
 SymmContext.a2av = _a2av
 SymmContext.a2av_capacity = _a2av_capacity

@@ -485,3 +485,70 @@ def test_adamw_split_master_kernel_matches_fp32_master():
         rebuilt = split_master_join(pb, lo)
         assert (rebuilt.view(torch.int32) - master.view(torch.int32)).abs().max().item() <= 1
     assert lo.abs().max().item() > 0
+
+
+def test_moe_gate_utility_kernels_match_cpu():
+    """number_count / assign_pos / limit_by_capacity / prune_gate_by_capacity on the device (csrc/moe.cu) vs the CPU implementations."""
+    from paddle_b200.incubate import moe as M
+
+    torch.manual_seed(0)
+    E, n = 8, 5000
+    idx = torch.randint(-1, E, (n,))
+    c_cpu = M.number_count(idx, E).as_subclass(torch.Tensor)
+    c_gpu = M.number_count(idx.cuda(), E).as_subclass(torch.Tensor)
+    assert torch.equal(c_cpu, c_gpu.cpu())
+    cum = torch.cumsum(c_cpu, 0)
+    pos = M.assign_pos(idx.cuda(), cum.cuda()).as_subclass(torch.Tensor).cpu()
+    valid = int(c_cpu.sum())
+    pos = pos[:valid]
+    assert sorted(pos.tolist()) == sorted(torch.nonzero(idx >= 0).reshape(-1).tolist())      # a permutation of the valid tokens ...
+    starts = torch.cat([torch.zeros(1, dtype=torch.long), cum[:-1]])
+    for e in range(E):                                                                          # ... grouped by expert
+        assert bool((idx[pos[starts[e]:cum[e]]] == e).all())
+    ec = torch.randint(0, 50, (3 * E,))
+    cap = torch.randint(20, 80, (E,))
+    assert torch.equal(M.limit_by_capacity(ec, cap, 3).as_subclass(torch.Tensor), M.limit_by_capacity(ec.cuda(), cap.cuda(), 3).as_subclass(torch.Tensor).cpu())
+    room = torch.randint(100, 700, (E,))
+    g_cpu = M.prune_gate_by_capacity(idx, room, E, 1).as_subclass(torch.Tensor)
+    g_gpu = M.prune_gate_by_capacity(idx.cuda(), room.cuda(), E, 1).as_subclass(torch.Tensor).cpu()
+    for e in range(E):                                     # same number of survivors per expert (which ones survive is order dependent)
+        assert int((g_cpu == e).sum()) == int((g_gpu == e).sum()) == min(int((idx == e).sum()), int(room[e]))
+    assert bool(((g_gpu == idx) | (g_gpu == -1)).all())
+
+
+@pytest.mark.parametrize("act", ["swiglu", "gelu"])
+def test_grouped_moe_ffn_matches_per_expert_loop(act):
+    """Grouped tcgen05 expert FFN (device routing + 2 grouped GEMM launches) == a per-expert fp32 loop, forward and all gradients."""
+    from paddle_b200.kernels import moe as KM
+
+    torch.manual_seed(1)
+    T, d, f, E, k = 700, 256, 512, 5, 2
+    f1 = 2 * f if act == "swiglu" else f
+    x = (torch.randn(T, d, device="cuda") * 0.5).to(torch.bfloat16).requires_grad_(True)
+    w1 = (torch.randn(E, d, f1, device="cuda") * 0.05).to(torch.bfloat16).requires_grad_(True)
+    w2 = (torch.randn(E, f, d, device="cuda") * 0.05).to(torch.bfloat16).requires_grad_(True)
+    logits = torch.randn(T, E, device="cuda")
+    val, idx = torch.softmax(logits, -1).topk(k, -1)
+    idx = idx.clone()
+    idx[::17, 1] = -1                                      # some dropped slots
+    idx[:, 0][idx[:, 0] == 3] = 0                          # expert 3 only through the second choice (small), keeps an almost empty expert
+    val = val.detach().requires_grad_(True)
+    assert KM.grouped_ok(x, w1, w2)
+    out = KM.expert_ffn_grouped(x, idx, val, w1, w2, act)
+    gout = torch.randn_like(out)
+    out.backward(gout)
+    got = [t.grad.float().clone() for t in (x, w1, w2, val)]
+    xr, w1r, w2r, vr = (t.detach().float().requires_grad_(True) for t in (x, w1, w2, val))
+    ref = torch.zeros(T, d, device="cuda")
+    for e in range(E):
+        for j in range(k):
+            sel = torch.nonzero(idx[:, j] == e).reshape(-1)
+            if sel.numel() == 0:
+                continue
+            h = xr[sel] @ w1r[e]
+            a = torch.nn.functional.silu(h[:, :f]) * h[:, f:] if act == "swiglu" else torch.nn.functional.gelu(h)
+            ref = ref.index_add(0, sel, (a @ w2r[e]) * vr[sel, j:j + 1])
+    assert rel_err(out, ref) < 2e-2, rel_err(out, ref)
+    ref.backward(gout.float())
+    for name, a, b in zip(("dx", "dw1", "dw2", "dval"), got, (xr.grad, w1r.grad, w2r.grad, vr.grad)):
+        assert rel_err(a, b) < 3e-2, (name, rel_err(a, b))
