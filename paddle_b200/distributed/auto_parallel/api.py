@@ -491,6 +491,14 @@ def _dispatch(func, args, kwargs):
             return _rule_rowwise(func, args, kwargs, mesh)
         if name in ("cross_entropy", "nll_loss", "mse_loss", "l1_loss", "binary_cross_entropy_with_logits", "smooth_l1_loss"):
             return _rule_loss(func, args, kwargs, mesh)
+        from . import spmd_rules
+
+        r = spmd_rules.lookup(name)
+        if r is not None and _is_dt(args[0] if not isinstance(args[0], (list, tuple)) else next((t for t in args[0] if _is_dt(t)), None)):
+            try:
+                return r(func, name, args, kwargs, mesh)
+            except (NotImplementedError, StopIteration):
+                pass
         return _fallback(func, args, kwargs, mesh)
 
 

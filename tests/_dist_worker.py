@@ -582,6 +582,63 @@ def case_auto_parallel():
     close(m(xin).numpy(), mr(xin).numpy(), 1e-4)
 
 
+def case_spmd_rules():
+    """SPMD rule library (auto_parallel/spmd_rules.py): ops on sharded DistTensors give the dense result and keep the sharding whenever
+    the op does not touch the sharded dimension. Parity: test/auto_parallel/spmd_rules/test_*_rule.py."""
+    dist.init_parallel_env()
+    r, w = dist.get_rank(), dist.get_world_size()
+    import paddle_b200.distributed as D
+    from paddle_b200.distributed.auto_parallel import ProcessMesh, Replicate, Shard
+
+    mesh = ProcessMesh(list(range(w)), dim_names=["x"])
+    paddle.seed(5)
+    g = paddle.randn([4 * w, 6, 8])
+    a = D.shard_tensor(g, mesh, [Shard(0)])
+    gt = g.as_subclass(torch.Tensor)
+
+    def check(dt, dense, placements=None, tol=1e-5):
+        full = D.unshard_dtensor(dt) if hasattr(dt, "placements") else dt
+        close(torch.as_tensor(full.numpy() if hasattr(full, "numpy") else full).double().numpy(), dense.double().numpy(), tol)
+        if placements is not None:
+            assert list(dt.placements) == placements, (dt.placements, placements)
+
+    check(torch.cumsum(a, dim=1), torch.cumsum(gt, 1), [Shard(0)])
+    check(torch.cumsum(a, dim=0), torch.cumsum(gt, 0))                       # touches the sharded dim: un-sharded just for this op
+    check(torch.argmax(a, dim=2), gt.argmax(2), [Shard(0)])
+    check(torch.amax(a, dim=1), gt.amax(1), [Shard(0)])
+    check(paddle.argmax(a, axis=1), gt.argmax(1), [Shard(0)])
+    check(torch.unsqueeze(a, 0), gt.unsqueeze(0), [Shard(1)])
+    check(paddle.unsqueeze(a, -1), gt.unsqueeze(-1), [Shard(0)])
+    check(torch.squeeze(torch.narrow(a, 1, 0, 1), 1), gt[:, :1].squeeze(1), [Shard(0)])
+    check(torch.flatten(a, 1, 2), gt.flatten(1, 2), [Shard(0)])
+    check(paddle.reshape(a, [4 * w, 48]), gt.reshape(4 * w, 48), [Shard(0)])
+    check(paddle.reshape(a, [4 * w * 6, 8]), gt.reshape(4 * w * 6, 8))
+    check(torch.cat([a, a], dim=1), torch.cat([gt, gt], 1), [Shard(0)])
+    check(torch.stack([a, a], dim=0), torch.stack([gt, gt], 0), [Shard(1)])
+    parts = torch.split(a, 3, dim=1)
+    check(parts[1], torch.split(gt, 3, 1)[1], [Shard(0)])
+    check(torch.flip(a, dims=[2]), torch.flip(gt, [2]), [Shard(0)])
+    check(torch.triu(a), torch.triu(gt), [Shard(0)])
+    check(torch.topk(a, 2, dim=2)[0], torch.topk(gt, 2, 2)[0], [Shard(0)])
+    check(paddle.expand(a, [2, 4 * w, 6, 8]), gt.expand(2, 4 * w, 6, 8), [Shard(1)])
+    check(torch.nn.functional.pad(a, (1, 1)), torch.nn.functional.pad(gt, (1, 1)), [Shard(0)])
+    idx = paddle.to_tensor(np.array([0, 2, 5]))
+    check(torch.index_select(a, 1, idx.as_subclass(torch.Tensor)), torch.index_select(gt, 1, idx.as_subclass(torch.Tensor)), [Shard(0)])
+    q = D.shard_tensor(paddle.randn([2 * w, 2, 5, 4]), mesh, [Shard(0)])
+    qt = D.unshard_dtensor(q).as_subclass(torch.Tensor)
+    check(torch.nn.functional.scaled_dot_product_attention(q, q, q), torch.nn.functional.scaled_dot_product_attention(qt, qt, qt), [Shard(0)], 1e-4)
+    img = D.shard_tensor(paddle.randn([2 * w, 3, 8, 8]), mesh, [Shard(0)])
+    wt = paddle.randn([4, 3, 3, 3])
+    it = D.unshard_dtensor(img).as_subclass(torch.Tensor)
+    check(torch.nn.functional.conv2d(img, wt.as_subclass(torch.Tensor)), torch.nn.functional.conv2d(it, wt.as_subclass(torch.Tensor)), [Shard(0)], 1e-4)
+    # gradients flow through a rule-driven op chain like through the dense one
+    gp = paddle.to_tensor(g.numpy(), stop_gradient=False)
+    ap = D.shard_tensor(paddle.to_tensor(g.numpy()), mesh, [Shard(0)], stop_gradient=False)
+    (torch.flatten(torch.cumsum(ap, dim=2), 1, 2) ** 2).sum().backward()
+    (torch.cumsum(gp.as_subclass(torch.Tensor), 2).flatten(1, 2) ** 2).sum().backward()
+    close(ap.grad._local_value().numpy(), gp.grad[r * 4:(r + 1) * 4].numpy(), 1e-4)
+
+
 def case_dist_checkpoint():
     """Sharded save on one layout, load on another. Parity: test/auto_parallel/semi_auto_parallel_checkpoint_*.py."""
     dist.init_parallel_env()

@@ -6,7 +6,7 @@ from dist_utils import run_dist
 
 
 @pytest.mark.parametrize("case,world", [("collectives", 2), ("mp_layers", 2), ("sequence_parallel", 2), ("dp", 2), ("pp", 2),
-                                        ("sharding", 2), ("mp_sp_parity", 2), ("hybrid_mp_pp", 4), ("auto_parallel", 2),
+                                        ("sharding", 2), ("mp_sp_parity", 2), ("hybrid_mp_pp", 4), ("auto_parallel", 2), ("spmd_rules", 2),
                                         ("dist_checkpoint", 2), ("dist_checkpoint_mp", 2), ("pp_interleave", 2), ("moe_ep", 2), ("dp_no_sync", 2), ("sep_parallel", 2), ("pp_shared_embedding", 2),
                                         ("dp_unused_params", 2), ("hybrid_scaler", 2), ("hybrid_scaler_dp", 2), ("fleet_sharding_degree", 2), ("auto_engine", 2), ("recompute_hybrid_partition", 2), ("hapi_fit", 2)])
 def test_dist_case(case, world, tmp_path):
