@@ -14,6 +14,8 @@ _FLAGS = {
     "FLAGS_b200_pp_mailbox": True,         # pipeline p2p through the peer-memory mailbox (copy engine + flag) instead of NCCL send/recv
     "FLAGS_b200_fused_wgrad": True,        # weight-gradient GEMMs accumulate straight into the flat gradient arena (kernels/wgrad.py)
     "FLAGS_b200_split_master_weights": True,   # bf16 arenas keep fp32 master weights as bf16 parameter + int16 residual (4 B instead of 6 B per parameter)
+    "FLAGS_b200_to_static_train_graph": True,  # to_static captures training calls (forward + backward CUDA graphs) after two eager warm-ups
+    "FLAGS_b200_moe_grouped_gemm": True,       # MoE experts run as grouped tcgen05 GEMMs with device-side routing
     "FLAGS_b200_flash_attention": True,    # tcgen05 flash-attention forward (csrc/attention_sm100.cu)
     "FLAGS_embedding_deterministic": 0,
     "FLAGS_eager_delete_tensor_gb": 0.0,

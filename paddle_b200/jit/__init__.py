@@ -57,21 +57,72 @@ class StaticFunction:
     """Callable produced by to_static. Eager warm-up, then CUDA-graph replay for inference-mode CUDA calls."""
 
     def __init__(self, fn, layer=None, input_spec=None, build_strategy=None, backend=None, full_graph=False):
+        self._dygraph_fn = fn
+        try:      # AST conversion of tensor-dependent control flow (jit/dy2static.py): `if tensor:` becomes run-both + device select
+            from .dy2static import convert_to_static
+
+            fn = convert_to_static(fn)
+        except Exception:  # noqa: BLE001  (source unavailable, exotic syntax): the function runs as written
+            fn = self._dygraph_fn
         self._fn, self._layer, self._input_spec = fn, layer, input_spec
         self._graphs = {}
+        self._train_graphs = {}
         self._warm = {}
         self._capture_after = 2
-        functools.update_wrapper(self, fn)
+        functools.update_wrapper(self, self._dygraph_fn)
 
     @property
     def dygraph_function(self):
-        return self._fn
+        return self._dygraph_fn
+
+    @property
+    def code(self):
+        """Source after the dy2static AST transform (reference: StaticFunction.code)."""
+        from .dy2static import get_code
+
+        return get_code(self._dygraph_fn)
 
     def concrete_program_specify_input_spec(self, *a, **k):
         return None
 
     def rollback(self):
-        return self._fn
+        return self._dygraph_fn
+
+    # ---- training capture: forward AND backward as CUDA graphs ------------------------------------------------------------------------
+    def _train_params(self):
+        if self._layer is None:
+            return []
+        return [p.as_subclass(torch.Tensor) if type(p) is not torch.Tensor else p for p in self._layer.parameters() if not p.stop_gradient]
+
+    def _can_train_graph(self, args, kwargs):
+        from ..framework.flags import flag
+
+        if kwargs or not flag("FLAGS_b200_to_static_train_graph", True) or not torch.is_grad_enabled():
+            return False
+        ts = [a for a in args if isinstance(a, torch.Tensor)]
+        if not ts or len(ts) != len(args) or not all(t.is_cuda for t in ts):
+            return False
+        return bool(self._train_params()) or any(t.requires_grad for t in ts)
+
+    def _capture_train(self, args):
+        """torch.cuda.make_graphed_callables over (inputs, *parameters): the parameters are passed as explicit (unused) arguments so that
+        the captured backward graph produces their gradients too - the role dy2static's program + run_program backward play in the
+        reference (python/paddle/jit/dy2static/pir_partial_program.py)."""
+        params = self._train_params()
+        n_in = len(args)
+        fn = self._fn
+
+        def pure(*flat):
+            out = fn(*[a.as_subclass(Tensor) if isinstance(a, torch.Tensor) and not isinstance(a, Tensor) else a for a in flat[:n_in]])
+            return out.as_subclass(torch.Tensor) if isinstance(out, torch.Tensor) and type(out) is not torch.Tensor else out
+
+        sample = tuple((a.as_subclass(torch.Tensor) if type(a) is not torch.Tensor else a).detach().clone().requires_grad_(a.requires_grad) for a in args)
+        try:
+            graphed = torch.cuda.make_graphed_callables(pure, sample + tuple(params), num_warmup_iters=2, allow_unused_input=True)
+        except Exception:  # noqa: BLE001  capture-unsafe body: stay eager for this signature
+            torch.cuda.synchronize()
+            return None
+        return graphed, params
 
     def _can_graph(self, args, kwargs):
         if torch.is_grad_enabled() and any(isinstance(a, torch.Tensor) and a.requires_grad for a in args):
@@ -82,7 +133,21 @@ class StaticFunction:
         return bool(ts) and all(t.is_cuda for t in ts)
 
     def __call__(self, *args, **kwargs):
-        if not _enabled[0] or getattr(self._fn, "_not_to_static", False):
+        if not _enabled[0] or getattr(self._dygraph_fn, "_not_to_static", False):
+            return self._dygraph_fn(*args, **kwargs)
+        if self._can_train_graph(args, kwargs):
+            key = ("train",) + _sig(args, kwargs)
+            entry = self._train_graphs.get(key, False)
+            if entry is False:
+                n = self._warm.get(key, 0) + 1
+                self._warm[key] = n
+                if n <= self._capture_after:
+                    return self._fn(*args, **kwargs)
+                entry = self._train_graphs[key] = self._capture_train(args)
+            if entry is not None:
+                graphed, params = entry
+                out = graphed(*[a.as_subclass(torch.Tensor) if type(a) is not torch.Tensor else a for a in args], *params)
+                return out.as_subclass(Tensor) if isinstance(out, torch.Tensor) else out
             return self._fn(*args, **kwargs)
         if not self._can_graph(args, kwargs) or torch.is_grad_enabled():
             return self._fn(*args, **kwargs)

@@ -244,3 +244,63 @@ def test_jit_save_of_local_class_is_the_eval_program(tmp_path):
     assert loaded(x[:3]).shape == [3, 4]
     with pytest.raises(RuntimeError, match="input_spec"):
         paddle.jit.save(make(), str(tmp_path / "n"))
+
+
+def test_dy2static_ast_conversion():
+    """to_static converts tensor-dependent `if` / logical ops (run both branches + device-side select), keeps Python control flow,
+    exposes the transformed code, and gradients follow the selected branch. Parity: test/dygraph_to_static/test_ifelse.py."""
+    import torch
+
+    import paddle_b200 as paddle
+    from paddle_b200.jit import dy2static as D
+
+    class Net(paddle.nn.Layer):
+        def __init__(self):
+            super().__init__()
+            self.fc = paddle.nn.Linear(4, 4)
+
+        def forward(self, x, scale):
+            h = self.fc(x)
+            if h.mean() > 0 and scale > 0:
+                out = h * scale
+                tag = paddle.ones([1])
+            else:
+                out = h - scale
+                tag = paddle.zeros([1])
+            k = 0
+            while k < 2:
+                out = out + 1
+                k += 1
+            return out, tag
+
+    paddle.seed(0)
+    net, ref = Net(), Net()
+    ref.set_state_dict(net.state_dict())
+    snet = paddle.jit.to_static(net)
+    assert "convert_ifelse" in snet.forward.code and "convert_logical_and" in snet.forward.code
+    for sign in (1.0, -1.0):
+        x = paddle.to_tensor(np.full((2, 4), sign, dtype=np.float32))
+        a, ta = snet(x, 3.0)
+        b, tb = ref(x, 3.0)
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-6)
+        np.testing.assert_allclose(ta.numpy(), tb.numpy())
+    x = paddle.to_tensor(np.ones((2, 4), dtype=np.float32), stop_gradient=False)
+    snet(x, 2.0)[0].sum().backward()
+    xr = paddle.to_tensor(np.ones((2, 4), dtype=np.float32), stop_gradient=False)
+    ref(xr, 2.0)[0].sum().backward()
+    np.testing.assert_allclose(x.grad.numpy(), xr.grad.numpy(), rtol=1e-6)
+    np.testing.assert_allclose(net.fc.weight.grad.numpy(), ref.fc.weight.grad.numpy(), rtol=1e-6)
+
+    def loop(x):
+        n = paddle.zeros([1])
+        while x.sum() < 50:
+            x = x * 2
+            n = n + 1
+        return x, n
+
+    g = D.convert_to_static(loop)
+    a, b = g(paddle.ones([3])), loop(paddle.ones([3]))
+    np.testing.assert_allclose(a[0].numpy(), b[0].numpy())
+    assert float(a[1]) == float(b[1]) == 5.0
+    pt = D.ProgramTranslator()
+    assert "convert_while_loop" in pt.get_code(loop)
