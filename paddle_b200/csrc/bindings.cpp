@@ -562,7 +562,25 @@ Tensor moe_rows_dot(const Tensor& src, const Tensor& dest, const Tensor& g, int6
 }
 
 // D = act(scale * A[M,K] @ B[N,K]^T + bias), A/B fp8 (e4m3 / e5m2), D half / bf16 / fp32
-Tensor gemm_fp8(const Tensor& a, const Tensor& b, const OptT& bias, double scale, int64_t act, at::ScalarType out_dtype) {
+// (q [M,K] fp8, qT [K,M] fp8 or undefined, inv_scale float[1]) of a 2-D bf16 / fp16 / fp32 tensor; two launches, no host sync
+std::vector<Tensor> quantize_fp8(const Tensor& x, bool e5m2, bool want_transpose) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous() && x.size(0) % 64 == 0 && x.size(1) % 64 == 0, "quantize_fp8: contiguous [M, K] with M, K multiples of 64");
+  c10::cuda::CUDAGuard guard(x.device());
+  const auto f8 = e5m2 ? at::kFloat8_e5m2 : at::kFloat8_e4m3fn;
+  Tensor q = torch::empty({x.size(0), x.size(1)}, x.options().dtype(f8));
+  Tensor qT = want_transpose ? torch::empty({x.size(1), x.size(0)}, x.options().dtype(f8)) : Tensor();
+  Tensor st = torch::zeros({2}, x.options().dtype(at::kFloat));      // [amax, inv_scale]
+  auto s = cur_stream();
+  b200::fp8_amax(x.data_ptr(), x.numel(), dt_code(x), st.data_ptr<float>(), s);
+  b200::fp8_cast_transpose(x.data_ptr(), x.size(0), x.size(1), dt_code(x), st.data_ptr<float>(), e5m2 ? 1 : 0, q.data_ptr(),
+                           want_transpose ? qT.data_ptr() : nullptr, st.data_ptr<float>() + 1, s);
+  g_launches += 2;
+  check_err();
+  return {q, qT, st.slice(0, 1, 2)};
+}
+
+Tensor gemm_fp8(const Tensor& a, const Tensor& b, const OptT& bias, double scale, int64_t act, at::ScalarType out_dtype, const OptT& scale_a,
+                const OptT& scale_b) {
   TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.dim() == 2 && b.dim() == 2 && a.is_contiguous() && b.is_contiguous() && a.size(1) == b.size(1),
               "gemm_fp8: operands must be contiguous [M,K] and [N,K]");
   auto is8 = [](const Tensor& t) { return t.scalar_type() == at::kFloat8_e4m3fn || t.scalar_type() == at::kFloat8_e5m2; };
@@ -580,6 +598,8 @@ Tensor gemm_fp8(const Tensor& a, const Tensor& b, const OptT& bias, double scale
   g.lda = a.stride(0); g.ldb = b.stride(0); g.ldd = d.stride(0);
   g.a_e5m2 = a.scalar_type() == at::kFloat8_e5m2; g.b_e5m2 = b.scalar_type() == at::kFloat8_e5m2;
   g.scale = (float)scale; g.act = (int)act; g.out_dtype = dt_code(d); g.batch = 1;
+  if (scale_a.has_value() && scale_a->defined()) { TORCH_CHECK(scale_a->is_cuda() && scale_a->scalar_type() == at::kFloat, "gemm_fp8: scale_a must be a CUDA float tensor"); g.scale_a_dev = scale_a->data_ptr<float>(); }
+  if (scale_b.has_value() && scale_b->defined()) { TORCH_CHECK(scale_b->is_cuda() && scale_b->scalar_type() == at::kFloat, "gemm_fp8: scale_b must be a CUDA float tensor"); g.scale_b_dev = scale_b->data_ptr<float>(); }
   g.stride_a = g.stride_b = g.stride_d = 0;
   int rc = b200::gemm_fp8_tcgen05(g, cur_stream());
   g_launches += 1;
@@ -753,7 +773,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_grouped", traced("gemm_grouped", &gemm_grouped), pybind11::arg("a"), pybind11::arg("b"), pybind11::arg("tile_expert"), pybind11::arg("b_is_nk") = false,
         pybind11::arg("out") = pybind11::none());
   m.def("gemm_grouped_wgrad", traced("gemm_grouped_wgrad", &gemm_grouped_wgrad));
-  m.def("gemm_fp8", traced("gemm_fp8", &gemm_fp8));
+  m.def("gemm_fp8", traced("gemm_fp8", &gemm_fp8), pybind11::arg("a"), pybind11::arg("b"), pybind11::arg("bias") = pybind11::none(), pybind11::arg("scale") = 1.0,
+        pybind11::arg("act") = 0, pybind11::arg("out_dtype") = at::kBFloat16, pybind11::arg("scale_a") = pybind11::none(), pybind11::arg("scale_b") = pybind11::none());
+  m.def("quantize_fp8", traced("quantize_fp8", &quantize_fp8), pybind11::arg("x"), pybind11::arg("e5m2") = false, pybind11::arg("want_transpose") = false);
   m.def("decode_attention", traced("decode_attention", &decode_attention));
   m.def("attention_supported", &attention_supported);
   m.def("attention_fwd", traced("attention_fwd", &attention_fwd), pybind11::arg("q"), pybind11::arg("k"), pybind11::arg("v"), pybind11::arg("scale"), pybind11::arg("causal"),

@@ -132,6 +132,8 @@ struct Params {
   int in_dtype, out_dtype;
   int has_bias, act, accumulate;
   float scale;
+  const float* scale_a;   // optional device scalars (per-tensor dequantisation factors produced by quantize_fp8): no host round trip
+  const float* scale_b;
   uint32_t idesc;
 };
 
@@ -275,6 +277,7 @@ gemm_fp8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       tc_fence_after();
       const int row = mb * BLOCK_M + ew * 32 + lane;
       const bool row_ok = row < p.m;
+      const float dq = p.scale * (p.scale_a ? *p.scale_a : 1.f) * (p.scale_b ? *p.scale_b : 1.f);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int col0 = nb * BN + c * 32;
@@ -287,7 +290,7 @@ gemm_fp8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         const int valid = min(32, p.n - col0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= p.scale;      // per-tensor dequantisation scale (scale_a * scale_b)
+        for (int j = 0; j < 32; ++j) v[j] *= dq;           // per-tensor dequantisation scale (scale_a * scale_b)
         if (p.has_bias) {
           if (p.out_dtype == kBF16) {
             const __nv_bfloat16* b = (const __nv_bfloat16*)p.bias + col0;
@@ -388,6 +391,7 @@ static int launch(const GemmFp8Args& g, cudaStream_t s) {
   p.act = g.act;
   p.accumulate = 0;
   p.scale = g.scale;
+  p.scale_a = g.scale_a_dev; p.scale_b = g.scale_b_dev;
   p.idesc = make_idesc(g.a_e5m2, g.b_e5m2, BN);
   static bool attr_set = false;
   auto kern = gemm_fp8_kernel<BN>;

@@ -145,12 +145,19 @@ struct GemmFp8Args {
   int64_t lda, ldb, ldd;
   int a_e5m2, b_e5m2;
   float scale;
+  const float* scale_a_dev = nullptr;   // device scalars multiplied into the dequantisation scale (quantize_fp8 outputs)
+  const float* scale_b_dev = nullptr;
   int act;          // 0 none, 1 gelu, 2 relu
   int out_dtype;
   int batch;
   int64_t stride_a, stride_b, stride_d;
 };
 int gemm_fp8_tcgen05(const GemmFp8Args& g, cudaStream_t s);
+// ---- quant_fp8.cu: fused per-tensor fp8 quantisation ----------------------------------------------------------
+// amax[0] = max(amax[0], max |x|)  (amax is a device float, zero it first)
+void fp8_amax(const void* x, int64_t n, int dtype, float* amax, cudaStream_t s);
+// q[M,K] (and qT[K,M] when non-null) = saturate_fp8(x * fmax / amax); inv_scale[0] = amax / fmax.  M, K multiples of 64.
+void fp8_cast_transpose(const void* x, int64_t m, int64_t k, int dtype, const float* amax, int e5m2, void* q, void* qT, float* inv_scale, cudaStream_t s);
 
 // ---- decode_attention.cu --------------------------------------------------------------------------------------
 // Single-token decode attention: q [B,H,128], k/v cache [B,Hkv,S_max,128], lens[b] valid positions; out [B,H,128].

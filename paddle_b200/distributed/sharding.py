@@ -628,13 +628,55 @@ class GroupShardedStage3(Layer):
         self._patch_optimizer()
 
     # ---- layout --------------------------------------------------------------------------------------------------------------------
+    def _collect_units(self):
+        """Sharding units: the largest sub-trees of the model whose parameters fit B200_S3_UNIT_MB (default 1 GB: one transformer block
+        of a 6.7B model), so that a block is gathered with ONE collective before its forward / backward instead of one per Linear or
+        LayerNorm.  0 = one unit per parameter-owning sublayer (the reference's granularity)."""
+        max_bytes = int(float(os.environ.get("B200_S3_UNIT_MB", "1024")) * (1 << 20))
+        seen = set()
+
+        def own(layer):
+            return [p for p in layer._parameters.values() if p is not None and not p.stop_gradient]
+
+        def under(layer):
+            out = []
+            for sub in layer.sublayers(include_self=True):
+                out.extend(own(sub))
+            return out
+
+        units = []
+
+        def add(root, ps):
+            ps = [p for p in ps if id(p) not in seen]
+            keyed = {}
+            for p in ps:
+                keyed.setdefault((p.dtype, p.device), []).append(p)
+            for group in keyed.values():          # a unit holds one dtype / device (mixed-precision models: one unit per class)
+                for p in group:
+                    seen.add(id(p))
+                units.append((root, group))
+
+        def walk(layer):
+            kids = [c for c in layer.children() if under(c)]
+            ps = under(layer)
+            total = sum(p.numel() * p.element_size() for p in ps)
+            if max_bytes > 0 and (total <= max_bytes or not kids):
+                add(layer, ps)
+                return
+            if max_bytes <= 0 and not kids:
+                add(layer, own(layer))
+                return
+            if own(layer):
+                add(layer, own(layer))
+            for c in kids:
+                walk(c)
+
+        walk(self._layer)
+        return units
+
     def _build_units(self):
         w = self.world
-        units = []
-        for sub in self._layer.sublayers(include_self=True):
-            ps = [p for p in sub._parameters.values() if p is not None and not p.stop_gradient]
-            if ps:
-                units.append((sub, ps))
+        units = self._collect_units()
         # shard arena per (dtype, device): [unit shards back to back]
         self._arenas = {}
         sizes = {}

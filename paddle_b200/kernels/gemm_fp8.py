@@ -45,8 +45,11 @@ def fp8_gemm(x, y, transpose_x=False, transpose_y=False, bias=None, scale=1.0, o
 
 
 def quantize_fp8(t, dtype=torch.float8_e4m3fn, amax=None):
-    """Per-tensor scaling: returns (t_fp8, inv_scale) with t ~= t_fp8 * inv_scale."""
+    """Per-tensor scaling: returns (t_fp8, inv_scale) with t ~= t_fp8 * inv_scale (inv_scale stays a device tensor on CUDA)."""
     t = raw(t)
+    if amax is None and _fused_quant_ok(t):
+        q, _, inv = ext().quantize_fp8(t.contiguous(), dtype == torch.float8_e5m2, False)
+        return q, inv
     fmax = E4M3_MAX if dtype == torch.float8_e4m3fn else E5M2_MAX
     amax = t.detach().abs().amax().float().clamp_min(1e-12) if amax is None else amax
     scale = fmax / amax
@@ -54,32 +57,55 @@ def quantize_fp8(t, dtype=torch.float8_e4m3fn, amax=None):
     return q, (1.0 / scale)
 
 
+def _fused_quant_ok(t):
+    return use_fused(t) and t.dim() == 2 and t.dtype in (torch.bfloat16, torch.float16, torch.float32) and t.shape[0] % 64 == 0 and t.shape[1] % 64 == 0
+
+
+def quantize_fp8_pair(t, dtype=torch.float8_e4m3fn):
+    """(q [M,K], qT [K,M], inv_scale): the tensor and its transpose quantised in one pass (csrc/quant_fp8.cu), scale on the device."""
+    t = raw(t)
+    if _fused_quant_ok(t):
+        q, qt, inv = ext().quantize_fp8(t.contiguous(), dtype == torch.float8_e5m2, True)
+        return q, qt, inv
+    q, inv = quantize_fp8(t, dtype)
+    return q, q.t().contiguous(), inv
+
+
+def _scaled_gemm(a, b, sa, sb, bias, out_dtype):
+    """a [M,K] fp8, b [N,K] fp8, sa / sb dequantisation factors (device tensors or floats) -> [M,N]."""
+    if use_fused(a) and isinstance(sa, torch.Tensor) and isinstance(sb, torch.Tensor) and a.shape[1] % 16 == 0 and b.shape[0] % 8 == 0:
+        bb = bias.to(out_dtype).contiguous() if bias is not None else None
+        return ext().gemm_fp8(a, b, bb, 1.0, 0, out_dtype, sa.reshape(1).float(), sb.reshape(1).float())
+    scale = (sa if isinstance(sa, torch.Tensor) else torch.tensor(float(sa))) * (sb if isinstance(sb, torch.Tensor) else torch.tensor(float(sb)))
+    out = torch.matmul(a.float(), b.float().t()) * scale.to(a.device).float()
+    if bias is not None:
+        out = out + bias.float()
+    return out.to(out_dtype)
+
+
 class _Fp8Linear(torch.autograd.Function):
-    """y = x @ W (W: [in, out]) with e4m3 activations / weights in the forward and e5m2 output gradients in the backward
-    (the fp8 recipe of the reference's O2-fp8 AMP): three tcgen05 fp8 GEMMs, all TN."""
+    """y = x @ W (W: [in, out]) with e4m3 activations / weights in the forward and e5m2 output gradients in the backward (the fp8 recipe of
+    the reference's O2-fp8 AMP): three tcgen05 fp8 GEMMs, all TN.  Every operand is quantised ONCE by the fused kernels, which emit the
+    transposed copy in the same pass; the dequantisation factors never leave the device."""
 
     @staticmethod
     def forward(ctx, x, w, bias):
         x2 = x.reshape(-1, x.shape[-1])
-        xq, sx = quantize_fp8(x2)
-        wq, sw = quantize_fp8(w.t())                     # [out, in]: K-major B operand
-        y = raw(fp8_gemm(xq, wq, False, True, bias, float(sx * sw), x.dtype))
-        ctx.save_for_backward(xq, wq)
-        ctx.scales = (sx, sw)
+        xq, xqt, sx = quantize_fp8_pair(x2)              # [M, in], [in, M]
+        wq, wqt, sw = quantize_fp8_pair(w)               # [in, out], [out, in]
+        y = _scaled_gemm(xq, wqt, sx, sw, bias, x.dtype)                  # B operand [N=out, K=in]
+        ctx.save_for_backward(xqt, wq, sx, sw)
         ctx.has_bias = bias is not None
         ctx.xshape = x.shape
         return y.reshape(*x.shape[:-1], w.shape[1])
 
     @staticmethod
     def backward(ctx, dy):
-        xq, wq = ctx.saved_tensors
-        sx, sw = ctx.scales
-        dy2 = dy.reshape(-1, dy.shape[-1])
-        gq, sg = quantize_fp8(dy2, torch.float8_e5m2)
-        # dx[M,in] = dy[M,out] @ W^T : B operand [N=in, K=out] = W (row-major [in,out]) -> wq^T copy
-        dx = raw(fp8_gemm(gq, wq.t().contiguous(), False, True, None, float(sg * sw), dy.dtype)).reshape(ctx.xshape)
-        # dW[in,out] = x^T[in,M] @ dy[M,out] : A = x^T [in, M] (K = tokens), B = dy^T [out, M]
-        dw = raw(fp8_gemm(xq.t().contiguous(), gq.t().contiguous(), False, True, None, float(sx * sg), dy.dtype))
+        xqt, wq, sx, sw = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        gq, gqt, sg = quantize_fp8_pair(dy2, torch.float8_e5m2)           # [M, out], [out, M]
+        dx = _scaled_gemm(gq, wq, sg, sw, None, dy.dtype).reshape(ctx.xshape)       # dx[M,in] = dy[M,out] @ W^T : B = W [N=in, K=out]
+        dw = _scaled_gemm(xqt, gqt, sx, sg, None, dy.dtype)                          # dW[in,out] = x^T[in,M] @ dy[M,out] : B = dy^T [out, M]
         db = dy2.sum(0) if ctx.has_bias else None
         return dx, dw, db
 

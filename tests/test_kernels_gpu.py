@@ -552,3 +552,20 @@ def test_grouped_moe_ffn_matches_per_expert_loop(act):
     ref.backward(gout.float())
     for name, a, b in zip(("dx", "dw1", "dw2", "dval"), got, (xr.grad, w1r.grad, w2r.grad, vr.grad)):
         assert rel_err(a, b) < 3e-2, (name, rel_err(a, b))
+
+
+@pytest.mark.parametrize("e5m2", [False, True])
+def test_fused_fp8_quantize_and_transpose(e5m2):
+    """csrc/quant_fp8.cu: amax + cast (+ transposed copy) without a host round trip == the eager per-tensor recipe."""
+    torch.manual_seed(2)
+    x = (torch.randn(320, 448, device="cuda") * 3).to(torch.bfloat16)
+    q, qt, inv = _ext().quantize_fp8(x, e5m2, True)
+    fmax = 57344.0 if e5m2 else 448.0
+    dt = torch.float8_e5m2 if e5m2 else torch.float8_e4m3fn
+    amax = x.float().abs().max()
+    ref = (x.float() * (fmax / amax)).clamp(-fmax, fmax).to(dt)
+    assert q.dtype == dt and torch.equal(q.float(), ref.float())
+    assert torch.equal(qt.float(), ref.float().t())
+    assert abs(float(inv) - float(amax / fmax)) < 1e-6 * float(amax / fmax) + 1e-12
+    back = q.float() * inv
+    assert rel_err(back, x) < (0.15 if e5m2 else 0.05)
