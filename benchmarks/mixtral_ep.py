@@ -30,10 +30,11 @@ tok = torch.randint(0, cfg.vocab_size, (args.batch, args.seq + 1), device="cuda"
 def step():
     loss = model(tok[:, :-1], tok[:, 1:])
     loss.backward()
-    if world > 1:   # non-expert parameters are data-parallel replicas
-        for p in model.parameters():
-            if p.grad is not None and not getattr(p, "no_sync", False):
-                torch.distributed.all_reduce(p.grad.as_subclass(torch.Tensor), op=torch.distributed.ReduceOp.AVG)
+    if world > 1:   # non-expert parameters are data-parallel replicas: one coalesced all-reduce (peer-memory kernel when available)
+        from paddle_b200.distributed.fleet.hybrid import _allreduce_tensors
+
+        grads = [p.grad.as_subclass(torch.Tensor) for p in model.parameters() if p.grad is not None and not getattr(p, "no_sync", False)]
+        _allreduce_tensors(grads, group, 1.0 / world)
     opt.step()
     opt.clear_grad()
     return loss

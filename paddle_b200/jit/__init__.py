@@ -92,7 +92,7 @@ class StaticFunction:
     def _train_params(self):
         if self._layer is None:
             return []
-        return [p.as_subclass(torch.Tensor) if type(p) is not torch.Tensor else p for p in self._layer.parameters() if not p.stop_gradient]
+        return [p for p in self._layer.parameters() if not p.stop_gradient]     # the leaf Parameters themselves (an alias would receive no gradient)
 
     def _can_train_graph(self, args, kwargs):
         from ..framework.flags import flag
