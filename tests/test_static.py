@@ -237,3 +237,40 @@ def test_save_inference_model_prunes_and_pickles_dunder_ops(tmp_path):
             np.testing.assert_allclose(out, ref[:b], rtol=1e-6)
     finally:
         paddle.disable_static()
+
+
+def test_decomposition_rewrites_composites_into_primitives():
+    """paddle.decomposition.decompose: softmax / gelu / layer_norm / silu / mean nodes become primitive nodes; results are unchanged."""
+    from paddle_b200 import decomposition as D
+
+    paddle.seed(0)
+    main, start = static.Program(), static.Program()
+    with static.program_guard(main, start):
+        x = static.data("x", [-1, 8], "float32")
+        w = paddle.create_parameter([8], "float32", default_initializer=paddle.nn.initializer.Constant(1.5))
+        h = paddle.nn.functional.layer_norm(x, [8], weight=w)
+        h = paddle.nn.functional.gelu(h) + paddle.nn.functional.silu(x)
+        y = paddle.nn.functional.softmax(h, axis=-1)
+        z = paddle.nn.functional.log_softmax(h, axis=1).mean()
+    exe = static.Executor()
+    exe.run(start)
+    a = np.random.RandomState(0).rand(5, 8).astype("float32")
+    before = exe.run(main, feed={"x": a}, fetch_list=[y, z])
+    names = lambda p: [getattr(n.fn, "__name__", str(n.fn)).strip("_") for n in p.nodes]  # noqa: E731
+    assert {"softmax", "gelu", "layer_norm", "silu", "log_softmax"} <= set(names(main))
+    n_before = len(main.nodes)
+    D.decompose(main)
+    left = set(names(main)) & {"softmax", "gelu", "layer_norm", "silu", "log_softmax", "mean"}
+    assert not left, left
+    assert len(main.nodes) > n_before and main.__dict__["_decomposed"] >= 5
+    after = exe.run(main, feed={"x": a}, fetch_list=[y, z])
+    for p, q in zip(before, after):
+        np.testing.assert_allclose(p, q, rtol=2e-5, atol=1e-6)
+    # whitelist / blacklist
+    m2, s2 = static.Program(), static.Program()
+    with static.program_guard(m2, s2):
+        x2 = static.data("x", [-1, 8], "float32")
+        y2 = paddle.nn.functional.softmax(paddle.nn.functional.gelu(x2), axis=-1)
+    D.decompose(m2, blacklist={"gelu"})
+    assert "gelu" in names(m2) and "softmax" not in names(m2)
+    assert D.has_decomp("rms_norm") and D.get_decomp_rule("softmax") is not None
