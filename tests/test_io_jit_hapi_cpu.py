@@ -304,3 +304,47 @@ def test_dy2static_ast_conversion():
     assert float(a[1]) == float(b[1]) == 5.0
     pt = D.ProgramTranslator()
     assert "convert_while_loop" in pt.get_code(loop)
+
+
+def test_sparse_conv_pool_rulebook_matches_dense():
+    """Sparse conv3d / subm_conv3d / conv2d / max_pool3d through the gather-GEMM-scatter rulebook (no densification) == dense conv on
+    the active output sites, for stride / padding / dilation / groups; gradients reach the weights."""
+    import torch
+
+    from paddle_b200.sparse.nn import functional as SF
+
+    torch.manual_seed(0)
+    def dense_ref3d(xd, w, b, stride, padding, dilation, groups):
+        return torch.nn.functional.conv3d(xd.permute(0,4,1,2,3), w.permute(4,3,0,1,2), b, stride, padding, dilation, groups).permute(0,2,3,4,1)
+    for (stride,padding,dilation,groups) in [(1,0,1,1),(2,1,1,1),(1,1,2,1),(1,1,1,2)]:
+        xd = torch.randn(2,6,7,5,4)*(torch.rand(2,6,7,5,1)>0.7)
+        x = xd.to_sparse(4)
+        w = torch.randn(3,3,3,4//groups,6); b = torch.randn(6)
+        out = SF.conv3d(x, w, b, stride, padding, dilation, groups).coalesce()
+        ref = dense_ref3d(xd, w, None, stride, padding, dilation, groups)
+        act = torch.nn.functional.conv3d((xd.abs().sum(-1,keepdim=True)>0).float().permute(0,4,1,2,3), torch.ones(1,1,3,3,3), None, stride, padding, dilation)[:,0]>0
+        od = out.to_dense()
+        assert torch.allclose(od[act], ref[act]+b, atol=1e-4), (stride,padding,dilation,groups)
+        assert out.indices().shape[1]==int(act.sum())
+        outs = SF.subm_conv3d(x, w, None, 1, 0, dilation, groups).coalesce()
+        pad = tuple(dilation*(3-1)//2 for _ in range(3))
+        refs = dense_ref3d(xd, w, None, 1, pad, dilation, groups)
+        xi = x.coalesce().indices()
+        assert torch.allclose(outs.to_dense()[xi[0],xi[1],xi[2],xi[3]], refs[xi[0],xi[1],xi[2],xi[3]], atol=1e-4)
+    xd = torch.randn(1,5,5,5,3)*(torch.rand(1,5,5,5,1)>0.6)
+    x = xd.to_sparse(4).requires_grad_(True)
+    w = torch.randn(3,3,3,3,4, requires_grad=True)
+    out = SF.conv3d(x, w, None, 1, 1, 1, 1)
+    out.coalesce().values().pow(2).sum().backward()
+    assert w.grad is not None and w.grad.abs().sum()>0
+    xp = (torch.rand(1,4,4,4,2)+0.1)*(torch.rand(1,4,4,4,1)>0.5)
+    o = SF.max_pool3d(xp.to_sparse(4), 2, 2).to_dense()
+    neg = torch.where(xp==0, torch.full_like(xp,float('-inf')), xp)
+    r = torch.nn.functional.max_pool3d(neg.permute(0,4,1,2,3),2,2).permute(0,2,3,4,1); r = torch.where(torch.isinf(r), torch.zeros_like(r), r)
+    assert torch.allclose(o, r)
+    x2 = torch.randn(2,6,6,3)*(torch.rand(2,6,6,1)>0.6)
+    w2 = torch.randn(3,3,3,5)
+    o2 = SF.conv2d(x2.to_sparse(3), w2, None, 1, 1).to_dense()
+    r2 = torch.nn.functional.conv2d(x2.permute(0,3,1,2), w2.permute(3,2,0,1), None, 1, 1).permute(0,2,3,1)
+    act2 = torch.nn.functional.conv2d((x2.abs().sum(-1,keepdim=True)>0).float().permute(0,3,1,2), torch.ones(1,1,3,3), None, 1, 1)[:,0]>0
+    assert torch.allclose(o2[act2], r2[act2], atol=1e-4)

@@ -57,3 +57,18 @@ def test_incubate_autograd_functional():
     Jb = IA.Jacobian(lambda t: t * 2.0, xb, is_batched=True)
     assert Jb.shape == [2, 3, 3]
     np.testing.assert_allclose(Jb[0].numpy(), 2 * np.eye(3), rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["tanh", "matmul", "softmax", "logsumexp", "gelu", "div_bcast", "cumsum"])
+def test_op_dtype_place_matrix(name):
+    """Every case over fp64 / fp32 / bf16 / fp16 on every available place (reference: OpTest's per-dtype, per-place checks)."""
+    from op_test import OpTestMatrix
+
+    op, ref, inputs = CASES[name]
+
+    class T(OpTestMatrix):
+        pass
+
+    T.op, T.ref, T.inputs = staticmethod(op), staticmethod(ref), inputs
+    ran = T().check_all()
+    assert len(ran) >= 4
