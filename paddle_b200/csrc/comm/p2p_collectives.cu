@@ -81,7 +81,9 @@ __device__ __forceinline__ bool last_cta(uint32_t* counter) {
 // ---------------------------------------------------------------------------------------------- two-shot all-reduce
 // buffer of n elements at `off` in every rank's heap. Rank r owns elements [r*chunk, (r+1)*chunk): it reads that range
 // from every peer, sums, and writes the result back into every peer's buffer.
-template <typename T>
+// U vectors per thread and iteration: U * world 16-byte peer loads are in flight per thread (8 in total for any world size), which is
+// what it takes to cover the ~2 us NVLink round trip with 64 CTAs (measured: 2 loads in flight per thread reach ~225 GB/s at world 2).
+template <typename T, int U>
 __global__ void __launch_bounds__(kThreads) allreduce_kernel(Peers P, int64_t off, int64_t n, int rank, int world,
                                                              uint32_t epoch, uint32_t* counter) {
   constexpr int N = Vec16<T>::N;
@@ -90,26 +92,36 @@ __global__ void __launch_bounds__(kThreads) allreduce_kernel(Peers P, int64_t of
   const int64_t nvec = n / N;
   const int64_t per = (nvec + world - 1) / world;
   const int64_t v0 = per * rank, v1 = min(nvec, v0 + per);
-  for (int64_t v = v0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < v1; v += (int64_t)gridDim.x * blockDim.x) {
-    float acc[N];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t vb = v0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; vb < v1; vb += stride * U) {
+    Vec16<T> in[U][kMaxRanks];
 #pragma unroll
-    for (int j = 0; j < N; ++j) acc[j] = 0.f;
-    Vec16<T> in[kMaxRanks];
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = vb + u * stride;
 #pragma unroll
-    for (int r = 0; r < kMaxRanks; ++r)
-      if (r < world) in[r] = ld16(reinterpret_cast<const T*>(P.base[r] + off) + v * N);   // all peer loads in flight
+      for (int r = 0; r < kMaxRanks; ++r)
+        if (r < world && v < v1) in[u][r] = ld16(reinterpret_cast<const T*>(P.base[r] + off) + v * N);   // all peer loads in flight
+    }
 #pragma unroll
-    for (int r = 0; r < kMaxRanks; ++r)
-      if (r < world) {
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = vb + u * stride;
+      if (v >= v1) continue;
+      float acc[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) acc[j] += to_f(in[r].v[j]);
-      }
-    Vec16<T> o;
+      for (int j = 0; j < N; ++j) acc[j] = 0.f;
 #pragma unroll
-    for (int j = 0; j < N; ++j) o.v[j] = from_f<T>(acc[j]);
+      for (int r = 0; r < kMaxRanks; ++r)
+        if (r < world) {
 #pragma unroll
-    for (int r = 0; r < kMaxRanks; ++r)
-      if (r < world) st16(reinterpret_cast<T*>(P.base[r] + off) + v * N, o);
+          for (int j = 0; j < N; ++j) acc[j] += to_f(in[u][r].v[j]);
+        }
+      Vec16<T> o;
+#pragma unroll
+      for (int j = 0; j < N; ++j) o.v[j] = from_f<T>(acc[j]);
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r)
+        if (r < world) st16(reinterpret_cast<T*>(P.base[r] + off) + v * N, o);
+    }
   }
   // scalar tail (n % N) handled by the last rank
   if (rank == world - 1 && blockIdx.x == 0) {
@@ -127,7 +139,7 @@ __global__ void __launch_bounds__(kThreads) allreduce_kernel(Peers P, int64_t of
 
 // ---------------------------------------------------------------------------------------------- reduce-scatter
 // input: n elements at `off` in every heap; rank r's output = sum over peers of elements [r*n/world, (r+1)*n/world)
-template <typename T>
+template <typename T, int U>
 __global__ void __launch_bounds__(kThreads) reduce_scatter_kernel(Peers P, int64_t off, T* __restrict__ out, int64_t n, int rank,
                                                                   int world, uint32_t epoch, uint32_t* counter) {
   constexpr int N = Vec16<T>::N;
@@ -136,24 +148,34 @@ __global__ void __launch_bounds__(kThreads) reduce_scatter_kernel(Peers P, int64
   const int64_t chunk = n / world;          // caller guarantees divisibility and chunk % N == 0
   const int64_t nvec = chunk / N;
   const int64_t base = chunk * rank;
-  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
-    float acc[N];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t vb = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; vb < nvec; vb += stride * U) {
+    Vec16<T> in[U][kMaxRanks];
 #pragma unroll
-    for (int j = 0; j < N; ++j) acc[j] = 0.f;
-    Vec16<T> in[kMaxRanks];
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = vb + u * stride;
 #pragma unroll
-    for (int r = 0; r < kMaxRanks; ++r)
-      if (r < world) in[r] = ld16(reinterpret_cast<const T*>(P.base[r] + off) + base + v * N);
+      for (int r = 0; r < kMaxRanks; ++r)
+        if (r < world && v < nvec) in[u][r] = ld16(reinterpret_cast<const T*>(P.base[r] + off) + base + v * N);
+    }
 #pragma unroll
-    for (int r = 0; r < kMaxRanks; ++r)
-      if (r < world) {
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = vb + u * stride;
+      if (v >= nvec) continue;
+      float acc[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) acc[j] += to_f(in[r].v[j]);
-      }
-    Vec16<T> o;
+      for (int j = 0; j < N; ++j) acc[j] = 0.f;
 #pragma unroll
-    for (int j = 0; j < N; ++j) o.v[j] = from_f<T>(acc[j]);
-    st16_stream(out + v * N, o);
+      for (int r = 0; r < kMaxRanks; ++r)
+        if (r < world) {
+#pragma unroll
+          for (int j = 0; j < N; ++j) acc[j] += to_f(in[u][r].v[j]);
+        }
+      Vec16<T> o;
+#pragma unroll
+      for (int j = 0; j < N; ++j) o.v[j] = from_f<T>(acc[j]);
+      st16_stream(out + v * N, o);
+    }
   }
   if (last_cta(counter)) {
     signal_all(P, rank, world, 1, epoch);
@@ -393,7 +415,10 @@ void p2p_allreduce(const int64_t* bases, int64_t off, int64_t n, int dtype, int 
   Peers P = make_peers(bases, world);
   B200_DISPATCH_DTYPE(dtype, T, {
     constexpr int N = Vec16<T>::N;
-    allreduce_kernel<T><<<comm_grid(n / N / world + 1), kThreads, 0, s>>>(P, off, n, rank, world, epoch, counter);
+    const int grid = comm_grid(n / N / world + 1);
+    if (world <= 2) allreduce_kernel<T, 4><<<grid, kThreads, 0, s>>>(P, off, n, rank, world, epoch, counter);
+    else if (world <= 4) allreduce_kernel<T, 2><<<grid, kThreads, 0, s>>>(P, off, n, rank, world, epoch, counter);
+    else allreduce_kernel<T, 1><<<grid, kThreads, 0, s>>>(P, off, n, rank, world, epoch, counter);
   });
   B200_CUDA_CHECK(cudaGetLastError());
 }
@@ -405,7 +430,10 @@ void p2p_reduce_scatter(const int64_t* bases, int64_t off, void* out, int64_t n,
   B200_DISPATCH_DTYPE(dtype, T, {
     constexpr int N = Vec16<T>::N;
     if (n % world || (n / world) % N) { set_last_error(__FILE__, __LINE__, "p2p_reduce_scatter: n/world must be a multiple of the 16B vector"); return; }
-    reduce_scatter_kernel<T><<<comm_grid(n / world / N), kThreads, 0, s>>>(P, off, (T*)out, n, rank, world, epoch, counter);
+    const int grid = comm_grid(n / world / N);
+    if (world <= 2) reduce_scatter_kernel<T, 4><<<grid, kThreads, 0, s>>>(P, off, (T*)out, n, rank, world, epoch, counter);
+    else if (world <= 4) reduce_scatter_kernel<T, 2><<<grid, kThreads, 0, s>>>(P, off, (T*)out, n, rank, world, epoch, counter);
+    else reduce_scatter_kernel<T, 1><<<grid, kThreads, 0, s>>>(P, off, (T*)out, n, rank, world, epoch, counter);
   });
   B200_CUDA_CHECK(cudaGetLastError());
 }

@@ -157,8 +157,8 @@ def case_dp():
     net = nn.Sequential(nn.Linear(8, 16), nn.Tanh(), nn.Linear(16, 4))
     ref = nn.Sequential(nn.Linear(8, 16), nn.Tanh(), nn.Linear(16, 4))
     ref.set_state_dict(net.state_dict())
-    x = paddle.randn([8, 8])
-    y = paddle.randn([8, 4])
+    x = paddle.randn([4 * w, 8])
+    y = paddle.randn([4 * w, 4])
     dp = paddle.DataParallel(net, comm_buffer_size=1)
     opt = paddle.optimizer.SGD(0.1, parameters=dp.parameters())
     ropt = paddle.optimizer.SGD(0.1, parameters=ref.parameters())
@@ -428,7 +428,7 @@ def case_sharding():
             net = nn.Sequential(nn.Linear(8, 32), nn.GELU(), nn.Linear(32, 16), nn.GELU(), nn.Linear(16, 4))
             ref = nn.Sequential(nn.Linear(8, 32), nn.GELU(), nn.Linear(32, 16), nn.GELU(), nn.Linear(16, 4))
             ref.set_state_dict(net.state_dict())
-            x, y = paddle.randn([8, 8]), paddle.randn([8, 4])
+            x, y = paddle.randn([4 * w, 8]), paddle.randn([4 * w, 4])
 
             def mk(ps):
                 clip = paddle.nn.ClipGradByGlobalNorm(0.5)
@@ -809,6 +809,50 @@ def case_p2p_kernels():
     gref = lref_in.grad[:, r * v:(r + 1) * v]
     e = ((loc.grad.float() - gref).norm() / gref.norm()).item()
     assert e < 3e-2, f"vocab parallel CE bwd {e}"
+    dist.barrier()
+
+
+def case_stress_dp_mp_overlap():
+    """Deadlock scenario of the round-1 review: a spinning peer-memory all-reduce of the DATA-PARALLEL group on a side stream while the main
+    stream runs persistent 148-CTA tcgen05 GEMMs that themselves wait on peers of the MODEL-PARALLEL group (fused all-gather -> GEMM and
+    GEMM -> reduce-scatter).  Both must make progress on every rank for many iterations (each group has its own heap / signal pad, and
+    the all-reduce grid leaves SM room next to the GEMM CTAs); results are checked against NCCL at the end."""
+    assert GPU
+    s, hcg = setup(dp=2, mp=2)
+    from paddle_b200.parallel import fused_mp, symm
+
+    dp_g, mp_g = hcg.get_data_parallel_group(), hcg.get_model_parallel_group()
+    sc_dp = symm.context_for(dp_g, heap_bytes=(256 << 20))
+    sc_mp = symm.context_for(mp_g)
+    assert sc_dp is not None and sc_mp is not None and sc_dp is not sc_mp
+    n = 8 << 20
+    grad, _ = sc_dp.buffer("stress_grad", (n,), torch.bfloat16)
+    side = torch.cuda.Stream()
+    torch.manual_seed(hcg.get_model_parallel_rank())
+    xa = (torch.randn(512, 1, 1024, device="cuda") * 0.05).to(torch.bfloat16)          # [S/p, B, K]
+    wc = (torch.randn(1024, 1024, device="cuda") * 0.05).to(torch.bfloat16)
+    xr = (torch.randn(1024, 1, 512, device="cuda") * 0.05).to(torch.bfloat16)         # [S, B, K_local]
+    wr = (torch.randn(512, 1024, device="cuda") * 0.05).to(torch.bfloat16)
+    iters = int(os.environ.get("B200_STRESS_ITERS", "1000"))
+    y1 = y2 = None
+    for it in range(iters):
+        grad.fill_(1.0)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            sc_dp.allreduce_(grad)                       # spins on the dp peer
+        y1 = fused_mp.allgather_linear(xa, wc, mp_g)    # persistent GEMM, copy warps pull the mp peer's shard
+        y2 = fused_mp.linear_reduce_scatter(xr, wr, mp_g)
+        torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    assert float(grad.float().min()) == 2.0 and float(grad.float().max()) == 2.0
+    xl = [torch.empty_like(xa) for _ in range(2)]
+    torch.distributed.all_gather(xl, xa, group=mp_g.pg)
+    ref1 = torch.cat(xl, 0).float() @ wc.float()
+    assert ((y1.as_subclass(torch.Tensor).float() - ref1).norm() / ref1.norm()).item() < 2e-2
+    full = xr.float() @ wr.float()
+    torch.distributed.all_reduce(full, group=mp_g.pg)
+    ref2 = full.chunk(2, 0)[hcg.get_model_parallel_rank()]
+    assert ((y2.as_subclass(torch.Tensor).float() - ref2).norm() / ref2.norm()).item() < 2e-2
     dist.barrier()
 
 

@@ -59,3 +59,35 @@ def test_group_sharded_gpu():
     """GroupSharded stage 2/3 over the windowed peer-memory reduce-scatter / all-gather."""
     _need(2)
     run_dist("sharding", 2, extra_env={"B200_TEST_GPU": "1"})
+
+
+# ---- wider worlds (4 / 8 GPUs): the peer-memory kernels and the fused paths beyond a pair of ranks -------------------------------------
+@pytest.mark.parametrize("world", [4, 8])
+def test_p2p_collectives_and_fused_linear_wide(world):
+    _need(world)
+    run_dist("p2p_kernels", world, extra_env={"B200_TEST_GPU": "1"}, timeout=400)
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_moe_fused_dispatch_combine_wide(world):
+    _need(world)
+    run_dist("moe_fused_a2a", world, extra_env={"B200_TEST_GPU": "1"}, timeout=400)
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_data_parallel_and_sharding_wide(world):
+    _need(world)
+    run_dist("dp", world, extra_env={"B200_TEST_GPU": "1"}, timeout=400)
+    run_dist("sharding", world, extra_env={"B200_TEST_GPU": "1"}, timeout=400)
+
+
+def test_hybrid_mp_pp_gpu():
+    _need(4)
+    run_dist("hybrid_mp_pp", 4, extra_env={"B200_TEST_GPU": "1"}, timeout=400)
+
+
+def test_stress_dp_allreduce_overlaps_mp_fused_gemms():
+    """1000 iterations of a dp-group spinning all-reduce on a side stream under mp-group fused GEMMs (the co-residency / deadlock
+    scenario): must neither hang (bounded spins trap after 10 s) nor corrupt results."""
+    _need(4)
+    run_dist("stress_dp_mp_overlap", 4, extra_env={"B200_TEST_GPU": "1"}, timeout=600)
