@@ -143,6 +143,8 @@ struct Params {
   uint32_t idesc_kk;     // A K-major, B K-major   (S, dP)
   uint32_t idesc_mm;     // A MN-major, B MN-major (dV, dK)
   uint32_t idesc_mk;     // A MN-major, B K-major  (dQ^T)
+  const int4* colmask;   // [b, mask_heads, sk] hidden row ranges per key column (see AttnArgs::colmask); nullptr: none
+  int mask_heads;
 };
 
 template <typename T>
@@ -257,6 +259,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       const float lse2 = row_ok ? p.lse[stat] * kLog2e : 0.f;
       const float dl = row_ok ? p.delta[stat] : 0.f;
       const int lim = p.causal ? min(p.sk - 1, row + p.causal_off) : p.sk - 1;   // last visible key of this query row
+      const int4* cm = p.colmask ? p.colmask + ((int64_t)batch * p.mask_heads + (p.mask_heads > 1 ? head : 0)) * p.sk : nullptr;
       mbar_wait(s_full, ph);
       tc_fence_after();
       // previous iteration's dV/dK/dQ MMAs have retired (we waited dq_full below), so the P / dS tiles are free
@@ -277,6 +280,10 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
               const int key = n0 + half * 64 + c * 32 + i;
               float x = ex2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse2));
               if (!row_ok || key > lim) x = 0.f;
+              if (cm != nullptr && key < p.sk) {
+                const int4 m = __ldg(cm + key);
+                if ((row >= m.x && row < m.y) || (row >= m.z && row < m.w)) x = 0.f;
+              }
               pv[t2] = x;
               ds[t2] = x * (__uint_as_float(rp[i]) - dl) * p.scale;
             }
@@ -454,6 +461,8 @@ int attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
   p.b = f.b; p.sq = f.sq; p.sk = f.sk; p.h = f.h; p.hk = f.hk;
   p.scale = f.scale; p.scale_log2 = f.scale * 1.4426950408889634f;
   p.causal = f.causal; p.causal_off = f.sk - f.sq;
+  p.colmask = reinterpret_cast<const int4*>(f.colmask);
+  p.mask_heads = f.mask_heads > 0 ? f.mask_heads : 1;
   p.lse = f.lse; p.delta = a.delta; p.dq = a.dq; p.dk = a.dk; p.dv = a.dv;
   p.dkv_sb = a.dkv_strides[0]; p.dkv_ss = a.dkv_strides[1]; p.dkv_sh = a.dkv_strides[2];
   p.dq_sb = a.dq_strides[0]; p.dq_ss = a.dq_strides[1]; p.dq_sh = a.dq_strides[2];

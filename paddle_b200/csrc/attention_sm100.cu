@@ -141,6 +141,8 @@ struct Params {
   int64_t o_sb, o_ss, o_sh;   // element strides of the output [B,S,H,D]
   int dtype;
   uint32_t idesc_qk, idesc_pv;
+  const int4* colmask;        // [b, mask_heads, sk] row ranges hidden from every key column (nullptr: none)
+  int mask_heads;
 };
 
 template <typename T>
@@ -288,6 +290,17 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 #pragma unroll
         for (int i = 0; i < 64; ++i)
           if (n0 + i > lim) s[i] = -INFINITY;
+      }
+      if (p.colmask) {     // flashmask / varlen: key column j hides the query rows [lt_start, lt_end) and [ut_start, ut_end)
+        const int4* cm = p.colmask + ((int64_t)batch * p.mask_heads + (p.mask_heads > 1 ? head : 0)) * p.sk;
+#pragma unroll 8
+        for (int i = 0; i < 64; ++i) {
+          const int key = n0 + i;
+          if (key < p.sk) {
+            const int4 m = __ldg(cm + key);         // same address in every lane: one broadcast transaction
+            if ((row >= m.x && row < m.y) || (row >= m.z && row < m.w)) s[i] = -INFINITY;
+          }
+        }
       }
       float mxp[8];
 #pragma unroll
@@ -465,6 +478,8 @@ int attention_fwd(const AttnArgs& a, cudaStream_t s) {
   p.dtype = a.dtype;
   p.idesc_qk = make_idesc(a.dtype, BN, false);
   p.idesc_pv = make_idesc(a.dtype, HD, true);
+  p.colmask = reinterpret_cast<const int4*>(a.colmask);
+  p.mask_heads = a.mask_heads > 0 ? a.mask_heads : 1;
   dim3 grid((a.sq + BM - 1) / BM, a.h, a.b);
   static bool attr_bf = false, attr_h = false;
   if (a.dtype == kBF16) {

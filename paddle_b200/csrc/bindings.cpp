@@ -651,17 +651,27 @@ bool attention_supported(const Tensor& q, const Tensor& k, const Tensor& v) {
 }
 
 // q [B,Sq,H,D], k/v [B,Sk,Hk,D] (strided views allowed) -> (out [B,Sq,H,D] contiguous, lse fp32 [B,H,Sq])
-std::vector<Tensor> attention_fwd(const Tensor& q, const Tensor& k, const Tensor& v, double scale, bool causal, bool out_seq_major) {
+static void set_colmask(b200::AttnArgs& a, const OptT& colmask) {
+  if (!(colmask.has_value() && colmask->defined())) return;
+  const Tensor& m = *colmask;
+  TORCH_CHECK(m.is_cuda() && m.scalar_type() == at::kInt && m.is_contiguous() && m.dim() == 4 && m.size(0) == a.b && m.size(2) == a.sk && m.size(3) == 4 &&
+              (m.size(1) == 1 || m.size(1) == a.h), "attention: colmask must be int32 [B, 1|H, Sk, 4] (lt_start, lt_end, ut_start, ut_end)");
+  a.colmask = m.data_ptr<int>();
+  a.mask_heads = (int)m.size(1);
+}
+
+std::vector<Tensor> attention_fwd(const Tensor& q, const Tensor& k, const Tensor& v, double scale, bool causal, bool out_seq_major, const OptT& colmask) {
   c10::cuda::CUDAGuard guard(q.device());
   b200::AttnArgs a;
   TORCH_CHECK(fill_attn(a, q, k, v, scale, causal), "paddle_b200.attention_fwd: unsupported operands");
+  set_colmask(a, colmask);
   // out_seq_major: the output is laid out [Sq,B,H,D] (sequence-parallel layers consume it without a transpose copy)
   Tensor out = out_seq_major ? torch::empty({a.sq, a.b, a.h, a.d}, q.options()) : torch::empty({a.b, a.sq, a.h, a.d}, q.options());
   if (out_seq_major) { a.o_strides[0] = (int64_t)a.h * a.d; a.o_strides[1] = (int64_t)a.b * a.h * a.d; a.o_strides[2] = a.d; }
   Tensor lse = torch::empty({a.b, a.h, a.sq}, q.options().dtype(at::kFloat));
   a.o = out.data_ptr(); a.lse = lse.data_ptr<float>();
   static const int variant = [] { const char* e = getenv("B200_ATTN_FWD"); return e ? atoi(e) : 1; }();   // 1: single query tile, key-split softmax warpgroups (default, fastest measured); 2: ping-pong (experimental)
-  int rc = (variant == 2 && a.sq >= 256) ? b200::attention_fwd2(a, cur_stream()) : b200::attention_fwd(a, cur_stream());
+  int rc = (variant == 2 && a.sq >= 256 && !a.colmask) ? b200::attention_fwd2(a, cur_stream()) : b200::attention_fwd(a, cur_stream());
   g_launches += 1;
   check_err();
   TORCH_CHECK(rc == 0, "paddle_b200.attention_fwd launch failed rc=", rc);
@@ -670,10 +680,11 @@ std::vector<Tensor> attention_fwd(const Tensor& q, const Tensor& k, const Tensor
 
 // backward of attention_fwd: returns (dq [B,Sq,H,D], dk, dv [B,Sk,Hk,D]) in the input dtype
 std::vector<Tensor> attention_bwd(const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& out, const Tensor& lse, const Tensor& d_out,
-                                  double scale, bool causal) {
+                                  double scale, bool causal, const OptT& colmask) {
   c10::cuda::CUDAGuard guard(q.device());
   b200::AttnBwdArgs a;
   TORCH_CHECK(fill_attn(a.fwd, q, k, v, scale, causal), "paddle_b200.attention_bwd: unsupported operands");
+  set_colmask(a.fwd, colmask);
   TORCH_CHECK(out.is_contiguous() && d_out.is_contiguous() && lse.is_contiguous() && lse.scalar_type() == at::kFloat, "attention_bwd: out / d_out / lse layout");
   a.fwd.o = out.data_ptr(); a.fwd.lse = lse.data_ptr<float>();
   Tensor dq32 = torch::zeros({a.fwd.b, a.fwd.sq, a.fwd.h, a.fwd.d}, q.options().dtype(at::kFloat));
@@ -779,8 +790,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("decode_attention", traced("decode_attention", &decode_attention));
   m.def("attention_supported", &attention_supported);
   m.def("attention_fwd", traced("attention_fwd", &attention_fwd), pybind11::arg("q"), pybind11::arg("k"), pybind11::arg("v"), pybind11::arg("scale"), pybind11::arg("causal"),
-        pybind11::arg("out_seq_major") = false);
-  m.def("attention_bwd", traced("attention_bwd", &attention_bwd));
+        pybind11::arg("out_seq_major") = false, pybind11::arg("colmask") = pybind11::none());
+  m.def("attention_bwd", traced("attention_bwd", &attention_bwd), pybind11::arg("q"), pybind11::arg("k"), pybind11::arg("v"), pybind11::arg("out"), pybind11::arg("lse"),
+        pybind11::arg("d_out"), pybind11::arg("scale"), pybind11::arg("causal"), pybind11::arg("colmask") = pybind11::none());
   m.def("attention_bwd_packed", traced("attention_bwd_packed", &attention_bwd_packed), pybind11::arg("qkv"), pybind11::arg("nh"), pybind11::arg("nkv"), pybind11::arg("out"),
         pybind11::arg("lse"), pybind11::arg("d_out"), pybind11::arg("scale"), pybind11::arg("causal"), pybind11::arg("seq_major") = false);
   m.def("launch_count", &launch_count);

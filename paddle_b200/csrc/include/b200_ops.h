@@ -176,6 +176,11 @@ struct AttnArgs {
   float scale;
   int causal;      // bottom-right aligned: key j visible to query i iff j <= i + (sk - sq)
   int dtype;
+  // Column-wise row-range mask (flashmask / packed variable-length sequences): per (batch, mask head, key) an int4
+  // {lt_start, lt_end, ut_start, ut_end}; query row i does NOT see key j iff lt_start <= i < lt_end or ut_start <= i < ut_end.
+  // colmask == nullptr: no mask.  mask_heads is 1 (shared by all heads) or h.
+  const int* colmask = nullptr;
+  int mask_heads = 1;
 };
 int attention_fwd_supported(const AttnArgs& a);
 int attention_fwd(const AttnArgs& a, cudaStream_t s);

@@ -67,6 +67,90 @@ class _FlashAttn(torch.autograd.Function):
         return dq, dk, dv, None, None
 
 
+class _FlashAttnColMask(torch.autograd.Function):
+    """tcgen05 flash attention with a column-wise row-range mask (flashmask / packed variable-length sequences / sliding windows):
+    colmask int32 [B, 1|H, Sk, 4] = (lt_start, lt_end, ut_start, ut_end): key j hides query rows [lt_start, lt_end) and
+    [ut_start, ut_end).  Forward and backward are the same kernels as the dense path (csrc/attention_sm100.cu,
+    attention_bwd_sm100.cu) with the mask test added to their score-tile loops."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, colmask, scale, causal):
+        out, lse = ext().attention_fwd(q, k, v, scale, causal, False, colmask)
+        ctx.save_for_backward(q, k, v, out, lse, colmask)
+        ctx.scale, ctx.causal = scale, causal
+        return out
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, out, lse, colmask = ctx.saved_tensors
+        dq, dk, dv = ext().attention_bwd(q, k, v, out, lse, do.contiguous(), ctx.scale, ctx.causal, colmask)
+        return dq, dk, dv, None, None, None
+
+
+_INT_MAX = 2 ** 31 - 1
+
+
+def colmask_from_startend(startend_row_indices, causal, sq):
+    """Paddle flashmask `startend_row_indices` [B, Hm, Sk, {1,2,4}] -> the kernels' int4 form [B, Hm, Sk, 4]."""
+    idx = raw(startend_row_indices).to(torch.int32)
+    n = idx.shape[-1]
+    zero = torch.zeros_like(idx[..., 0])
+    big = torch.full_like(zero, _INT_MAX)
+    if causal:
+        lts, lte = idx[..., 0], (idx[..., 1] if n >= 2 else big)
+        uts = ute = zero
+    elif n == 1:
+        lts, lte, uts, ute = idx[..., 0], big, zero, zero
+    elif n == 2:
+        lts, lte, uts, ute = idx[..., 0], big, zero, idx[..., 1]
+    else:
+        lts, lte, uts, ute = idx[..., 0], idx[..., 1], idx[..., 2], idx[..., 3]
+    return torch.stack([lts, lte, uts, ute], -1).contiguous()
+
+
+def colmask_from_cu_seqlens(cu_q, cu_k, total_k):
+    """Packed variable-length batch -> document mask: key j of sequence s is visible to the query rows [cu_q[s], cu_q[s+1]) only."""
+    cu_q, cu_k = raw(cu_q).to(torch.int64), raw(cu_k).to(torch.int64)
+    keys = torch.arange(total_k, device=cu_k.device)
+    seq = torch.bucketize(keys, cu_k[1:], right=True).clamp(max=cu_q.numel() - 2)
+    qs, qe = cu_q[seq].to(torch.int32), cu_q[seq + 1].to(torch.int32)
+    valid = keys < cu_k[-1]
+    zero = torch.zeros_like(qs)
+    lts = torch.where(valid, qe, zero)                          # rows >= qe hidden; keys beyond the last sequence hide every row
+    lte = torch.full_like(qs, _INT_MAX)
+    ute = torch.where(valid, qs, zero)                          # rows < qs hidden
+    return torch.stack([lts, lte, zero, ute], -1).reshape(1, 1, total_k, 4).contiguous()
+
+
+def colmask_from_window(sq, sk, left, right, causal, device):
+    """Sliding window: query i sees keys in [i - left, i + right] (right = 0 under a causal mask)."""
+    keys = torch.arange(sk, device=device, dtype=torch.int32)
+    off = sk - sq
+    lts = (keys - off + left + 1).clamp(min=0)                  # rows i with key < i + off - left  <=>  i > key - off + left
+    lte = torch.full_like(keys, _INT_MAX)
+    uts = torch.zeros_like(keys)
+    ute = (keys - off - (0 if causal else right)).clamp(min=0) if not causal else torch.zeros_like(keys)   # rows i < key - off - right
+    return torch.stack([lts, lte, uts, ute], -1).reshape(1, 1, sk, 4).contiguous()
+
+
+def attention_colmask(q, k, v, colmask, causal=False, scale=None):
+    """[B,S,H,D] attention under a column-wise row-range mask on the own tcgen05 kernels; None if the operands do not qualify."""
+    q, k, v = raw(q), raw(k), raw(v)
+    if not fused_ok(q, k, v, None, 0.0, causal):
+        return None
+    sc = float(scale) if scale is not None else 1.0 / math.sqrt(q.shape[-1])
+    return wrap(_FlashAttnColMask.apply(q, k, v, raw(colmask).to(torch.int32).contiguous(), sc, bool(causal)))
+
+
+def colmask_to_dense(colmask, sq):
+    """Boolean visibility [B, Hm, Sq, Sk] of an int4 column mask (reference path / tests)."""
+    m = raw(colmask).long()
+    rows = torch.arange(sq, device=m.device).reshape(1, 1, sq, 1)
+    lts, lte, uts, ute = (m[..., i].unsqueeze(2) for i in range(4))
+    hidden = ((rows >= lts) & (rows < lte)) | ((rows >= uts) & (rows < ute))
+    return ~hidden
+
+
 class _FlashAttnPacked(torch.autograd.Function):
     """Attention over a packed projection qkv [B,S,nh+2*nkv,D] (or [S,B,...] when seq_major): the kernels read q/k/v in place
     through strided TMA maps and the backward writes d(qkv) in place (dk/dv slices straight from the kernel epilogue), so

@@ -43,6 +43,15 @@ def flash_attn_unpadded(query, key, value, cu_seqlens_q, cu_seqlens_k, max_seqle
     from ...kernels import attention as K
 
     q, k, v = T(query), T(key), T(value)
+    if q.is_cuda and (dropout == 0.0 or not training) and q.dim() == 3:
+        # packed batch as ONE sequence under a document mask: no host read of cu_seqlens, no per-sequence launches.
+        # (causal: the diagonal of every sequence is the global diagonal when q and k are packed alike - self attention)
+        same = cu_seqlens_q is cu_seqlens_k or (raw(cu_seqlens_q).shape == raw(cu_seqlens_k).shape and q.size(0) == k.size(0))
+        if same or not causal:
+            cm = K.colmask_from_cu_seqlens(cu_seqlens_q, cu_seqlens_k, k.size(0))
+            out = K.attention_colmask(q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0), cm, causal and same, scale)
+            if out is not None:
+                return out.squeeze(0), None
     cq, ck = raw(cu_seqlens_q).tolist(), raw(cu_seqlens_k).tolist()
     outs = []
     for i in range(len(cq) - 1):
@@ -74,6 +83,17 @@ def flashmask_attention(query, key, value, startend_row_indices=None, dropout=0.
     q, k, v = T(query), T(key), T(value)
     sq, sk = q.size(1), k.size(1)
     mask = None
+    if q.is_cuda and (dropout == 0.0 or not training) and (startend_row_indices is not None or window_size is not None):
+        if startend_row_indices is not None:
+            cm = K.colmask_from_startend(startend_row_indices, causal, sq)
+        else:
+            w = (window_size, window_size) if isinstance(window_size, int) else tuple(window_size)
+            cm = K.colmask_from_window(sq, sk, int(w[0]), int(w[1]), causal, q.device)
+        if cm.shape[0] == 1 and q.size(0) > 1:
+            cm = cm.expand(q.size(0), -1, -1, -1).contiguous()
+        out = K.attention_colmask(q, k, v, cm, causal, None)
+        if out is not None:
+            return out
     if startend_row_indices is not None:
         idx = raw(startend_row_indices).long()
         rows = torch.arange(sq, device=q.device).reshape(1, 1, sq, 1)

@@ -4,8 +4,13 @@
   linear_reduce_scatter : Y = reduce_scatter_seq(X @ W_local)                (RowSequenceParallelLinear)
   allgather_linear      : Y = all_gather_seq(X_local) @ W_local              (ColumnSequenceParallelLinear)
 
-Fast path (GPU, symmetric heap initialised, bf16/fp16): ONE kernel per op from csrc/comm/ that overlaps the NVLink
-transfers with the tcgen05 tiles (see parallel/symm.py).  Fallback: GEMM kernel + torch.distributed collective.
+Fast path (GPU, symmetric heap initialised, bf16/fp16), see parallel/symm.py for the exact launch sequence of each op:
+  * all-gather -> GEMM: two staging copies of the local shard (into the symmetric shard buffer the peers read, and into the gathered
+    operand), then ONE CTA-pair GEMM launch whose copy warps pull the peers' shards over NVLink while the tensor cores run;
+  * GEMM -> reduce-scatter: ONE GEMM launch whose TMA-store epilogue writes every output row into its owner's staging slot (peer
+    HBM) + a small `reduce_slots` kernel that sums `world` local slots;
+  * row-parallel all-reduce: GEMM into the symmetric buffer, then the two-shot peer-memory all-reduce kernel, then one copy out.
+Fallback: GEMM kernel + torch.distributed collective (bracketed by distributed.comm_timer for the exposed-communication report).
 """
 from __future__ import annotations
 

@@ -569,3 +569,68 @@ def test_fused_fp8_quantize_and_transpose(e5m2):
     assert abs(float(inv) - float(amax / fmax)) < 1e-6 * float(amax / fmax) + 1e-12
     back = q.float() * inv
     assert rel_err(back, x) < (0.15 if e5m2 else 0.05)
+
+
+def _dense_masked_attention(q, k, v, vis, causal):
+    b, sq, h, d = q.shape
+    sk = k.shape[1]
+    s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) / d ** 0.5
+    m = vis.expand(b, h, sq, sk).clone()
+    if causal:
+        m &= torch.ones(sq, sk, dtype=torch.bool, device=q.device).tril(sk - sq)
+    s = s.masked_fill(~m, float("-inf"))
+    p = torch.softmax(s, -1).nan_to_num(0.0)
+    return torch.einsum("bhqk,bkhd->bqhd", p, v.float())
+
+
+@pytest.mark.parametrize("kind", ["flashmask_causal_doc", "flashmask_4", "varlen", "window"])
+def test_attention_variants_run_on_own_kernels(kind):
+    """flashmask / flash_attn_unpadded / sliding-window attention launch attn::fwd_kernel + the tcgen05 backward (launch counter) and
+    match a dense fp32 masked softmax, forward and gradients (reference python/paddle/nn/functional/flash_attention.py:593,1098)."""
+    import paddle_b200.nn.functional as F
+    from paddle_b200.kernels import attention as KAT
+
+    torch.manual_seed(3)
+    B, S, H, D = 2, 384, 4, 128
+    mk = lambda *sh: (torch.randn(*sh, device="cuda") * 0.5).to(torch.bfloat16).requires_grad_(True)  # noqa: E731
+    causal = False
+    if kind == "varlen":
+        lens = [100, 180, 104]
+        cu = torch.tensor([0, 100, 280, 384], device="cuda", dtype=torch.int32)
+        q, k, v = mk(S, H, D), mk(S, H, D), mk(S, H, D)
+        causal = True
+        kernels.reset_launch_count()
+        out, _ = F.flash_attn_unpadded(q.as_subclass(paddle.Tensor), k.as_subclass(paddle.Tensor), v.as_subclass(paddle.Tensor), cu, cu, 180, 180, D ** -0.5, causal=True)
+        vis = KAT.colmask_to_dense(KAT.colmask_from_cu_seqlens(cu, cu, S), S)
+        ref_in = [t.detach().float().unsqueeze(0) for t in (q, k, v)]
+    else:
+        q, k, v = mk(B, S, H, D), mk(B, S, H, D), mk(B, S, H, D)
+        keys = torch.arange(S, device="cuda")
+        if kind == "flashmask_causal_doc":       # causal document mask: two documents per row of the batch
+            causal = True
+            lts = torch.where(keys < 200, torch.full_like(keys, 200), torch.full_like(keys, S)).reshape(1, 1, S, 1).expand(B, 1, S, 1).int().contiguous()
+            se = lts
+        elif kind == "flashmask_4":
+            lts, lte = (keys + 64).clamp(max=S), (keys + 128).clamp(max=S)
+            uts, ute = (keys - 160).clamp(min=0), (keys - 96).clamp(min=0)
+            se = torch.stack([lts, lte, uts, ute], -1).reshape(1, 1, S, 4).expand(B, 1, S, 4).int().contiguous()
+        kernels.reset_launch_count()
+        if kind == "window":
+            out = F.flashmask_attention(q.as_subclass(paddle.Tensor), k.as_subclass(paddle.Tensor), v.as_subclass(paddle.Tensor), None, causal=False, window_size=(48, 16))
+            vis = KAT.colmask_to_dense(KAT.colmask_from_window(S, S, 48, 16, False, q.device), S)
+        else:
+            out = F.flashmask_attention(q.as_subclass(paddle.Tensor), k.as_subclass(paddle.Tensor), v.as_subclass(paddle.Tensor), se, causal=causal)
+            vis = KAT.colmask_to_dense(KAT.colmask_from_startend(se, causal, S), S)
+        ref_in = [t.detach().float() for t in (q, k, v)]
+    assert kernels.launch_count() >= 1, "the variant did not reach the native attention kernel"
+    out_t = out.as_subclass(torch.Tensor)
+    g = torch.randn_like(out_t)
+    out_t.backward(g)
+    rq, rk, rv = (t.requires_grad_(True) for t in ref_in)
+    ref = _dense_masked_attention(rq, rk, rv, vis, causal)
+    got = out_t.float().unsqueeze(0) if kind == "varlen" else out_t.float()
+    assert rel_err(got, ref) < 2e-2, rel_err(got, ref)
+    ref.backward(g.float().unsqueeze(0) if kind == "varlen" else g.float())
+    for name, a, b in (("dq", q.grad, rq.grad), ("dk", k.grad, rk.grad), ("dv", v.grad, rv.grad)):
+        bb = b.squeeze(0) if kind == "varlen" else b
+        assert rel_err(a.float(), bb) < 3e-2, (name, rel_err(a.float(), bb))
