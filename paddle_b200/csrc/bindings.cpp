@@ -561,6 +561,29 @@ Tensor moe_rows_dot(const Tensor& src, const Tensor& dest, const Tensor& g, int6
   return dw;
 }
 
+// x [M, K] bf16 / fp16, w int8 [N, K] (or int4 packed [N, K/2]), scale float [N], bias [N] or None -> [M, N]
+Tensor weight_only_gemm(const Tensor& x, const Tensor& w, const Tensor& scale, const OptT& bias, bool int4) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous() && (x.scalar_type() == at::kBFloat16 || x.scalar_type() == at::kHalf), "weight_only_gemm: x [M, K] bf16 / fp16 contiguous");
+  TORCH_CHECK(w.is_cuda() && w.dim() == 2 && w.is_contiguous() && w.scalar_type() == at::kChar && w.size(1) == (int4 ? x.size(1) / 2 : x.size(1)), "weight_only_gemm: w int8 [N, K] (int4: [N, K/2])");
+  TORCH_CHECK(scale.is_cuda() && scale.scalar_type() == at::kFloat && scale.numel() == w.size(0) && scale.is_contiguous(), "weight_only_gemm: scale float32 [N]");
+  c10::cuda::CUDAGuard guard(x.device());
+  b200::WoGemmArgs g;
+  g.m = (int)x.size(0); g.k = (int)x.size(1); g.n = (int)w.size(0);
+  Tensor out = torch::empty({g.m, g.n}, x.options());
+  Tensor ws;
+  g.ws = nullptr;
+  if (g.m <= 64) { ws = torch::empty({g.m, g.n}, x.options().dtype(at::kFloat)); g.ws = ws.data_ptr<float>(); }
+  g.x = x.data_ptr(); g.w = w.data_ptr(); g.scale = scale.data_ptr<float>(); g.out = out.data_ptr();
+  g.bias = nullptr;
+  if (bias.has_value() && bias->defined()) { TORCH_CHECK(bias->scalar_type() == x.scalar_type() && bias->numel() == g.n && bias->is_contiguous(), "weight_only_gemm: bias [N] in x dtype"); g.bias = bias->data_ptr(); }
+  g.int4 = int4 ? 1 : 0; g.bf16 = x.scalar_type() == at::kBFloat16 ? 1 : 0;
+  int rc = b200::gemm_weight_only(g, cur_stream());
+  g_launches += 1;
+  check_err();
+  TORCH_CHECK(rc == 0, "paddle_b200.weight_only_gemm: unsupported shape (K multiple of 64, N multiple of 8) rc=", rc);
+  return out;
+}
+
 // D = act(scale * A[M,K] @ B[N,K]^T + bias), A/B fp8 (e4m3 / e5m2), D half / bf16 / fp32
 // (q [M,K] fp8, qT [K,M] fp8 or undefined, inv_scale float[1]) of a 2-D bf16 / fp16 / fp32 tensor; two launches, no host sync
 std::vector<Tensor> quantize_fp8(const Tensor& x, bool e5m2, bool want_transpose) {
@@ -781,6 +804,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("moe_rows_combine", traced("moe_rows_combine", &moe_rows_combine), pybind11::arg("src"), pybind11::arg("dest"), pybind11::arg("w") = pybind11::none(),
         pybind11::arg("topk") = 1);
   m.def("moe_rows_dot", traced("moe_rows_dot", &moe_rows_dot));
+  m.def("weight_only_gemm", traced("weight_only_gemm", &weight_only_gemm), pybind11::arg("x"), pybind11::arg("w"), pybind11::arg("scale"), pybind11::arg("bias") = pybind11::none(),
+        pybind11::arg("int4") = false);
   m.def("gemm_grouped", traced("gemm_grouped", &gemm_grouped), pybind11::arg("a"), pybind11::arg("b"), pybind11::arg("tile_expert"), pybind11::arg("b_is_nk") = false,
         pybind11::arg("out") = pybind11::none());
   m.def("gemm_grouped_wgrad", traced("gemm_grouped_wgrad", &gemm_grouped_wgrad));

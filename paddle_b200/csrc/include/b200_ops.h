@@ -159,6 +159,16 @@ void fp8_amax(const void* x, int64_t n, int dtype, float* amax, cudaStream_t s);
 // q[M,K] (and qT[K,M] when non-null) = saturate_fp8(x * fmax / amax); inv_scale[0] = amax / fmax.  M, K multiples of 64.
 void fp8_cast_transpose(const void* x, int64_t m, int64_t k, int dtype, const float* amax, int e5m2, void* q, void* qT, float* inv_scale, cudaStream_t s);
 
+// ---- gemm_wo_sm100.cu: weight-only quantised GEMM (dequantisation inside the SM) ---------------------------------
+// out[m, n] = x[m, k] @ dequant(w)[n, k]^T * scale[n] (+ bias[n]).  w: int8 [n, k] or packed int4 [n, k / 2] (low nibble = even k).
+struct WoGemmArgs {
+  const void* x; const void* w; const float* scale; const void* bias; void* out;
+  float* ws;        // optional fp32 [m, n] workspace: enables split-K for narrow layers (decode)
+  int m, n, k;
+  int int4, bf16;   // weight format; activation dtype (1 bf16, 0 fp16)
+};
+int gemm_weight_only(const WoGemmArgs& g, cudaStream_t s);
+
 // ---- decode_attention.cu --------------------------------------------------------------------------------------
 // Single-token decode attention: q [B,H,128], k/v cache [B,Hkv,S_max,128], lens[b] valid positions; out [B,H,128].
 // part_acc: fp32 [B,H,splits,128] scratch, part_ml: fp32 [B,H,splits,2] scratch.

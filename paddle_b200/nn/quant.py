@@ -49,6 +49,23 @@ def weight_dequantize(x, scale, algo="weight_only_int8", out_dtype="float16", gr
 
 
 def weight_only_linear(x, weight, bias=None, weight_scale=None, weight_dtype="int8", arch=None, group_size=-1):
+    """y = x @ dequant(weight)^T + bias.  CUDA bf16 / fp16 activations with per-channel scales run csrc/gemm_wo_sm100.cu: the int8 / int4
+    weights are streamed by TMA and expanded to 16-bit INSIDE the SM (no dequantised copy of the weight is ever written to HBM), which is
+    what makes weight-only decoding faster than the 16-bit GEMM (it is bound by weight bytes).  Grouped scales / CPU: dequantise + linear."""
+    xr = x.as_subclass(torch.Tensor)
+    wr = weight.as_subclass(torch.Tensor)
+    if xr.is_cuda and xr.dtype in (torch.bfloat16, torch.float16) and weight_scale is not None and (group_size is None or group_size <= 0) \
+            and weight_dtype in ("int8", "int4") and wr.dtype == torch.int8 and xr.shape[-1] % 64 == 0 and wr.shape[0] % 8 == 0:
+        from ..framework.flags import flag
+
+        if flag("FLAGS_use_fused_kernels", True):
+            from .._build import ext
+
+            x2 = xr.reshape(-1, xr.shape[-1]).contiguous()
+            sc = weight_scale.as_subclass(torch.Tensor).float().contiguous()
+            b = None if bias is None else bias.as_subclass(torch.Tensor).to(xr.dtype).contiguous()
+            y = ext().weight_only_gemm(x2, wr.contiguous(), sc, b, weight_dtype == "int4")
+            return _w(y.reshape(*xr.shape[:-1], wr.shape[0]))
     w = weight_dequantize(weight, weight_scale, "weight_only_" + weight_dtype, x.dtype, group_size)
     from . import functional as F
 

@@ -634,3 +634,25 @@ def test_attention_variants_run_on_own_kernels(kind):
     for name, a, b in (("dq", q.grad, rq.grad), ("dk", k.grad, rk.grad), ("dv", v.grad, rv.grad)):
         bb = b.squeeze(0) if kind == "varlen" else b
         assert rel_err(a.float(), bb) < 3e-2, (name, rel_err(a.float(), bb))
+
+
+@pytest.mark.parametrize("wdt", ["int8", "int4"])
+@pytest.mark.parametrize("m", [1, 8, 48, 300])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_weight_only_linear_dequant_in_sm(wdt, m, dtype):
+    """csrc/gemm_wo_sm100.cu (raw int8 / int4 weights by TMA, dequantised inside the SM, tcgen05, split-K for decode) vs dequantise + fp32
+    matmul; the kernel must be the one that runs (launch counter)."""
+    from paddle_b200.nn import quant as Q
+
+    torch.manual_seed(4)
+    k, n = 1024, 1536
+    w = torch.randn(k, n, device="cuda") * 0.05
+    x = (torch.randn(m, k, device="cuda") * 0.5).to(dtype)
+    bias = (torch.randn(n, device="cuda") * 0.1).to(dtype)
+    wq, sc = Q.weight_quantize(w.as_subclass(paddle.Tensor), algo=f"weight_only_{wdt}")
+    kernels.reset_launch_count()
+    y = Q.weight_only_linear(x.as_subclass(paddle.Tensor), wq, bias.as_subclass(paddle.Tensor), sc, wdt)
+    assert kernels.launch_count() == 1
+    wd = Q.weight_dequantize(wq, sc, algo=f"weight_only_{wdt}", out_dtype="float32").as_subclass(torch.Tensor)
+    ref = x.float() @ wd.float() + bias.float()
+    assert rel_err(y.as_subclass(torch.Tensor), ref) < 1e-2, rel_err(y.as_subclass(torch.Tensor), ref)
