@@ -147,7 +147,7 @@ struct Params {
   int mask_heads;
 };
 
-template <typename T>
+template <typename T, bool MASKED>
 __global__ void __launch_bounds__(kThreads, 1)
 bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
            const __grid_constant__ CUtensorMap map_do, const Params p) {
@@ -259,7 +259,8 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       const float lse2 = row_ok ? p.lse[stat] * kLog2e : 0.f;
       const float dl = row_ok ? p.delta[stat] : 0.f;
       const int lim = p.causal ? min(p.sk - 1, row + p.causal_off) : p.sk - 1;   // last visible key of this query row
-      const int4* cm = p.colmask ? p.colmask + ((int64_t)batch * p.mask_heads + (p.mask_heads > 1 ? head : 0)) * p.sk : nullptr;
+      const int4* cm = MASKED ? p.colmask + ((int64_t)batch * p.mask_heads + (p.mask_heads > 1 ? head : 0)) * p.sk : nullptr;
+      (void)cm;
       mbar_wait(s_full, ph);
       tc_fence_after();
       // previous iteration's dV/dK/dQ MMAs have retired (we waited dq_full below), so the P / dS tiles are free
@@ -280,9 +281,11 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
               const int key = n0 + half * 64 + c * 32 + i;
               float x = ex2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse2));
               if (!row_ok || key > lim) x = 0.f;
-              if (cm != nullptr && key < p.sk) {
-                const int4 m = __ldg(cm + key);
-                if ((row >= m.x && row < m.y) || (row >= m.z && row < m.w)) x = 0.f;
+              if constexpr (MASKED) {
+                if (key < p.sk) {
+                  const int4 m = __ldg(cm + key);
+                  if ((row >= m.x && row < m.y) || (row >= m.z && row < m.w)) x = 0.f;
+                }
               }
               pv[t2] = x;
               ds[t2] = x * (__uint_as_float(rp[i]) - dl) * p.scale;
@@ -470,16 +473,13 @@ int attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
   p.idesc_mm = make_idesc(f.dtype, true, true);
   p.idesc_mk = make_idesc(f.dtype, true, false);
   dim3 grid((f.sk + BN - 1) / BN, f.hk, f.b);
-  static bool attr_bf = false, attr_h = false;
-  if (f.dtype == kBF16) {
-    auto kern = bwd_kernel<__nv_bfloat16>;
-    if (!attr_bf) { B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_bf = true; }
+  static bool attr_set[4] = {false, false, false, false};
+  auto go = [&](auto kern, int slot) {
+    if (!attr_set[slot]) { B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_set[slot] = true; }
     kern<<<grid, kThreads, SMEM_BYTES, s>>>(mq, mk, mv, mdo, p);
-  } else {
-    auto kern = bwd_kernel<__half>;
-    if (!attr_h) { B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_h = true; }
-    kern<<<grid, kThreads, SMEM_BYTES, s>>>(mq, mk, mv, mdo, p);
-  }
+  };
+  if (f.dtype == kBF16) { if (p.colmask) go(bwd_kernel<__nv_bfloat16, true>, 0); else go(bwd_kernel<__nv_bfloat16, false>, 1); }
+  else { if (p.colmask) go(bwd_kernel<__half, true>, 2); else go(bwd_kernel<__half, false>, 3); }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return 3; }
   return 0;

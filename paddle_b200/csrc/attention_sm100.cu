@@ -145,7 +145,8 @@ struct Params {
   int mask_heads;
 };
 
-template <typename T>
+// MASKED: column-wise row-range mask (flashmask / varlen) compiled in; the dense instantiation carries none of its code or registers
+template <typename T, bool MASKED>
 __global__ void __launch_bounds__(kThreads, 1)
 fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
            const __grid_constant__ CUtensorMap map_v, const Params p) {
@@ -291,7 +292,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         for (int i = 0; i < 64; ++i)
           if (n0 + i > lim) s[i] = -INFINITY;
       }
-      if (p.colmask) {     // flashmask / varlen: key column j hides the query rows [lt_start, lt_end) and [ut_start, ut_end)
+      if constexpr (MASKED) {     // flashmask / varlen: key column j hides the query rows [lt_start, lt_end) and [ut_start, ut_end)
         const int4* cm = p.colmask + ((int64_t)batch * p.mask_heads + (p.mask_heads > 1 ? head : 0)) * p.sk;
 #pragma unroll 8
         for (int i = 0; i < 64; ++i) {
@@ -482,13 +483,22 @@ int attention_fwd(const AttnArgs& a, cudaStream_t s) {
   p.mask_heads = a.mask_heads > 0 ? a.mask_heads : 1;
   dim3 grid((a.sq + BM - 1) / BM, a.h, a.b);
   static bool attr_bf = false, attr_h = false;
-  if (a.dtype == kBF16) {
-    auto kern = fwd_kernel<__nv_bfloat16>;
+  static bool attr_bf_m = false, attr_h_m = false;
+  if (a.dtype == kBF16 && !p.colmask) {
+    auto kern = fwd_kernel<__nv_bfloat16, false>;
     if (!attr_bf) { B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_bf = true; }
     kern<<<grid, kThreads, SMEM_BYTES, s>>>(mq, mk, mv, p);
-  } else {
-    auto kern = fwd_kernel<__half>;
+  } else if (a.dtype == kBF16) {
+    auto kern = fwd_kernel<__nv_bfloat16, true>;
+    if (!attr_bf_m) { B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_bf_m = true; }
+    kern<<<grid, kThreads, SMEM_BYTES, s>>>(mq, mk, mv, p);
+  } else if (!p.colmask) {
+    auto kern = fwd_kernel<__half, false>;
     if (!attr_h) { B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_h = true; }
+    kern<<<grid, kThreads, SMEM_BYTES, s>>>(mq, mk, mv, p);
+  } else {
+    auto kern = fwd_kernel<__half, true>;
+    if (!attr_h_m) { B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_h_m = true; }
     kern<<<grid, kThreads, SMEM_BYTES, s>>>(mq, mk, mv, p);
   }
   cudaError_t e = cudaGetLastError();

@@ -81,8 +81,7 @@ __device__ __forceinline__ bool last_cta(uint32_t* counter) {
 // ---------------------------------------------------------------------------------------------- two-shot all-reduce
 // buffer of n elements at `off` in every rank's heap. Rank r owns elements [r*chunk, (r+1)*chunk): it reads that range
 // from every peer, sums, and writes the result back into every peer's buffer.
-// U vectors per thread and iteration: U * world 16-byte peer loads are in flight per thread (8 in total for any world size), which is
-// what it takes to cover the ~2 us NVLink round trip with 64 CTAs (measured: 2 loads in flight per thread reach ~225 GB/s at world 2).
+// U vectors per thread and iteration (U * world 16-byte peer loads in flight per thread); see the launcher for the measured choice.
 template <typename T, int U>
 __global__ void __launch_bounds__(kThreads) allreduce_kernel(Peers P, int64_t off, int64_t n, int rank, int world,
                                                              uint32_t epoch, uint32_t* counter) {
@@ -415,10 +414,9 @@ void p2p_allreduce(const int64_t* bases, int64_t off, int64_t n, int dtype, int 
   Peers P = make_peers(bases, world);
   B200_DISPATCH_DTYPE(dtype, T, {
     constexpr int N = Vec16<T>::N;
-    const int grid = comm_grid(n / N / world + 1);
-    if (world <= 2) allreduce_kernel<T, 4><<<grid, kThreads, 0, s>>>(P, off, n, rank, world, epoch, counter);
-    else if (world <= 4) allreduce_kernel<T, 2><<<grid, kThreads, 0, s>>>(P, off, n, rank, world, epoch, counter);
-    else allreduce_kernel<T, 1><<<grid, kThreads, 0, s>>>(P, off, n, rank, world, epoch, counter);
+    // measured on 2 x B200 (6.5 GB slab): more peer loads in flight per thread (U = 4) was SLOWER (53.6 vs 29.3 ms) - the loop is bound by
+    // the posted remote stores, not by load latency - so every world size keeps one vector per thread and iteration
+    allreduce_kernel<T, 1><<<comm_grid(n / N / world + 1), kThreads, 0, s>>>(P, off, n, rank, world, epoch, counter);
   });
   B200_CUDA_CHECK(cudaGetLastError());
 }

@@ -26,7 +26,8 @@ namespace wo {
 constexpr int BLOCK_N = 128;     // output channels per CTA = UMMA M (TMEM lanes)
 constexpr int BLOCK_K = 64;
 constexpr int kBStages = 3;      // dequantised A-operand ring
-constexpr int kThreads = 192;    // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2-5: dequantise + epilogue
+constexpr int kDqWarps = 8;      // dequantise warps: two per SM sub-partition so that their ld.shared / convert / st.shared chains overlap
+constexpr int kThreads = 64 + kDqWarps * 32;    // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2-9: dequantise (2-5 also epilogue)
 constexpr uint32_t A_TILE_BYTES = BLOCK_N * BLOCK_K * 2;   // 16 KB dequantised weight tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -159,7 +160,7 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 1); }
-    for (int s = 0; s < kBStages; ++s) { mbar_init(a_ready(s), 4); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < kBStages; ++s) { mbar_init(a_ready(s), kDqWarps); mbar_init(a_empty(s), 1); }
     mbar_init(tfull, 1);
     fence_barrier_init();
     fence_proxy_async();
@@ -204,7 +205,8 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     }
   } else {
     // ================= dequantise warps (then epilogue): thread = (row, 16-byte piece) work items =================
-    const int tid = threadIdx.x - 64;                     // 0..127
+    const int tid = threadIdx.x - 64;                     // 0..kDqWarps*32-1
+    constexpr int DQ = kDqWarps * 32;
     const int ew = warp & 3;                              // TMEM lane quadrant this warp may read (hardware: warp id % 4)
     for (int i = 0; i < num_kb; ++i) {
       const int s = i % STAGES, t = i % kBStages;
@@ -215,8 +217,8 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       if constexpr (!INT4) {
         // raw tile: 128 rows x 64 B, SWIZZLE_64B (16-byte piece q of row r sits at piece q ^ ((r >> 1) & 3))
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int c = tid + it * 128, r = c >> 2, q = c & 3;
+        for (int it = 0; it < 512 / DQ; ++it) {
+          const int c = tid + it * DQ, r = c >> 2, q = c & 3;
           uint4 v;
           const uint32_t src = raw + r * 64 + ((q ^ ((r >> 1) & 3)) << 4);
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src));
@@ -237,8 +239,8 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       } else {
         // raw tile: 128 rows x 32 B, SWIZZLE_32B (piece q of row r at q ^ ((r >> 2) & 1)); one 16-byte piece = 32 weights = 4 output chunks
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          const int c = tid + it * 128, r = c >> 1, q = c & 1;
+        for (int it = 0; it < 256 / DQ; ++it) {
+          const int c = tid + it * DQ, r = c >> 1, q = c & 1;
           uint4 v;
           const uint32_t src = raw + r * 32 + ((q ^ ((r >> 2) & 1)) << 4);
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src));
@@ -262,8 +264,8 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready(t));
     }
-    // ---- epilogue: TMEM lane = output channel, column = token ----
-    if (num_kb > 0) {
+    // ---- epilogue (warps 2-5: one per TMEM lane quadrant): TMEM lane = output channel, column = token ----
+    if (num_kb > 0 && warp < 6) {
       mbar_wait(tfull, 0);
       tc_fence_after();
       const int ch = n0 + ew * 32 + lane;
@@ -364,9 +366,12 @@ static int launch(const WoGemmArgs& g, const CUtensorMap& mw, cudaStream_t s) {
   const int num_kb = (g.k + BLOCK_K - 1) / BLOCK_K;
   const int n_tiles = (g.n + BLOCK_N - 1) / BLOCK_N, t_tiles = (g.m + NTOK - 1) / NTOK;
   int splits = 1;
-  if (g.ws != nullptr) {      // narrow layers: spread the reduction over the idle SMs
+  if (g.ws != nullptr) {      // decode: one wave of CTAs over all SMs - split the reduction as far as the SM count and K allow
     const int ctas = n_tiles * t_tiles;
-    while (splits < 8 && ctas * splits * 2 <= sm_count() && num_kb / (splits * 2) >= 8) splits *= 2;
+    splits = sm_count() / (ctas > 0 ? ctas : 1);
+    if (splits > num_kb / 8) splits = num_kb / 8;
+    if (splits > 16) splits = 16;
+    if (splits < 1) splits = 1;
   }
   p.splits = splits;
   p.kb_per_split = (num_kb + splits - 1) / splits;

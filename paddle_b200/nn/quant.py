@@ -62,6 +62,13 @@ def weight_only_linear(x, weight, bias=None, weight_scale=None, weight_dtype="in
             from .._build import ext
 
             x2 = xr.reshape(-1, xr.shape[-1]).contiguous()
+            if x2.shape[0] > 128:
+                # prefill: compute bound, and every token tile would dequantise the weight tile again - expand the weight once instead
+                # (one pass over the int weights) and run the bf16 tcgen05 GEMM; the fused kernel is the decode / small-batch path
+                w = weight_dequantize(weight, weight_scale, "weight_only_" + weight_dtype, x.dtype, group_size)
+                from . import functional as F
+
+                return F.linear(x, w, bias)
             sc = weight_scale.as_subclass(torch.Tensor).float().contiguous()
             b = None if bias is None else bias.as_subclass(torch.Tensor).to(xr.dtype).contiguous()
             y = ext().weight_only_gemm(x2, wr.contiguous(), sc, b, weight_dtype == "int4")
