@@ -570,9 +570,6 @@ Tensor weight_only_gemm(const Tensor& x, const Tensor& w, const Tensor& scale, c
   b200::WoGemmArgs g;
   g.m = (int)x.size(0); g.k = (int)x.size(1); g.n = (int)w.size(0);
   Tensor out = torch::empty({g.m, g.n}, x.options());
-  Tensor ws;
-  g.ws = nullptr;
-  if (g.m <= 64) { ws = torch::empty({g.m, g.n}, x.options().dtype(at::kFloat)); g.ws = ws.data_ptr<float>(); }
   g.x = x.data_ptr(); g.w = w.data_ptr(); g.scale = scale.data_ptr<float>(); g.out = out.data_ptr();
   g.bias = nullptr;
   if (bias.has_value() && bias->defined()) { TORCH_CHECK(bias->scalar_type() == x.scalar_type() && bias->numel() == g.n && bias->is_contiguous(), "weight_only_gemm: bias [N] in x dtype"); g.bias = bias->data_ptr(); }

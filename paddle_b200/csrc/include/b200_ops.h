@@ -163,7 +163,6 @@ void fp8_cast_transpose(const void* x, int64_t m, int64_t k, int dtype, const fl
 // out[m, n] = x[m, k] @ dequant(w)[n, k]^T * scale[n] (+ bias[n]).  w: int8 [n, k] or packed int4 [n, k / 2] (low nibble = even k).
 struct WoGemmArgs {
   const void* x; const void* w; const float* scale; const void* bias; void* out;
-  float* ws;        // optional fp32 [m, n] workspace: enables split-K for narrow layers (decode)
   int m, n, k;
   int int4, bf16;   // weight format; activation dtype (1 bf16, 0 fp16)
 };

@@ -13,17 +13,29 @@ from paddle_b200.nn import quant as Q  # noqa: E402
 E = ext()
 
 
-def timeit(fn, n=30):
+def timeit(fn, n=20):
+    """Device time per call: `n` calls captured into one CUDA graph (no host launch overhead between them), replayed 5 times."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        fn()
+        st.synchronize()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(n):
+                fn()
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(n):
-        fn()
+    for _ in range(5):
+        g.replay()
     b.record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b) / n
+    return a.elapsed_time(b) / (5 * n)
 
 
 rows = []
@@ -40,8 +52,10 @@ for k, n in [(5120, 15360), (5120, 5120), (13824, 5120), (5120, 27648)]:
             i[0] = (i[0] + 1) % 4
             return i[0]
 
-        t8 = timeit(lambda: E.weight_only_gemm(x, qs[nxt()][0].as_subclass(torch.Tensor), qs[i[0]][1].as_subclass(torch.Tensor).float(), None, False))
-        t4 = timeit(lambda: E.weight_only_gemm(x, q4[nxt()][0].as_subclass(torch.Tensor), q4[i[0]][1].as_subclass(torch.Tensor).float(), None, True))
+        w8 = [(q[0].as_subclass(torch.Tensor), q[1].as_subclass(torch.Tensor).float()) for q in qs]
+        w4 = [(q[0].as_subclass(torch.Tensor), q[1].as_subclass(torch.Tensor).float()) for q in q4]
+        t8 = timeit(lambda: E.weight_only_gemm(x, *w8[nxt()], None, False))
+        t4 = timeit(lambda: E.weight_only_gemm(x, *w4[nxt()], None, True))
         tb = timeit(lambda: torch.matmul(x, wb[nxt()]))
         row = {"k": k, "n": n, "m": m, "int8_ms": round(t8, 4), "int4_ms": round(t4, 4), "bf16_matmul_ms": round(tb, 4), "int8_speedup_vs_bf16": round(tb / t8, 2),
                "int4_speedup_vs_bf16": round(tb / t4, 2), "int8_weight_gbs": round(k * n / t8 / 1e6, 1), "int4_weight_gbs": round(k * n / 2 / t4 / 1e6, 1)}

@@ -639,13 +639,14 @@ def test_attention_variants_run_on_own_kernels(kind):
 @pytest.mark.parametrize("wdt", ["int8", "int4"])
 @pytest.mark.parametrize("m", [1, 8, 48, 128])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-def test_weight_only_linear_dequant_in_sm(wdt, m, dtype):
+@pytest.mark.parametrize("k", [1344, 5120])      # 1344 = 21 k-blocks: ragged raw boxes and uneven cluster split-K ranks; 5120: many ring phases
+def test_weight_only_linear_dequant_in_sm(wdt, m, dtype, k):
     """csrc/gemm_wo_sm100.cu (raw int8 / int4 weights by TMA, dequantised inside the SM, tcgen05, split-K for decode) vs dequantise + fp32
     matmul; the kernel must be the one that runs (launch counter)."""
     from paddle_b200.nn import quant as Q
 
     torch.manual_seed(4)
-    k, n = 1024, 1536
+    n = 1536
     w = torch.randn(k, n, device="cuda") * 0.05
     x = (torch.randn(m, k, device="cuda") * 0.5).to(dtype)
     bias = (torch.randn(n, device="cuda") * 0.1).to(dtype)
