@@ -1,13 +1,14 @@
-// Weight-only quantised GEMM for sm_100a: out[M,N] = x[M,K] (bf16 / fp16) @ dequant(Wq[N,K] int8 | int4) * scale[N] (+ bias).
+// Weight-only quantised GEMM for sm_100a: out[M,N] = x[M,K] (bf16 / fp16) @ dequant(Wq[N,K] int8 | int4) * scale[N] (+ bias), M <= 64.
 //
-// The int8 / int4 weights never exist in HBM as 16-bit values: TMA streams the raw quantised tile (one or half a byte per weight)
-// into a deep shared-memory ring, eight dequantise warps (four groups, one k-block each) expand it IN THE SM into the 128B-swizzled K-major operand layout, and
-// tcgen05 multiplies.  The problem is computed transposed (D^T[N, M] = W[N, K] x^T) so that the weight tile is the 128-row A operand
-// at full UMMA height even when M is a handful of decode tokens, the per-channel scale is a per-thread scalar in the epilogue
-// (TMEM lane = output channel), and the token tile (UMMA N = 16 / 64 / 128) only costs what the batch needs.
-// Decode is weight-bandwidth bound: 5-7 raw boxes of 16 KB (128 channels x one full 128-byte line) in flight per SM cover the HBM
-// latency; split-K spreads narrow
-// layers over all SMs (fp32 atomics into a workspace, finalised by a tiny kernel).
+// The int8 / int4 weights never exist as 16-bit values in HBM or in shared memory: TMA streams raw [128 channels x 128 B] boxes into a
+// deep ring, sixteen dequantise warps expand them IN REGISTERS with packed 16-bit magic-number arithmetic and store them straight into
+// TMEM (tcgen05.st), and tcgen05.mma reads its A operand from there.  The problem is computed transposed (D^T[N, M] = W[N, K] x^T) so
+// that the weight tile is the 128-row A operand at full UMMA height even when M is a handful of decode tokens, the per-channel scale is
+// a per-thread scalar in the epilogue (TMEM lane = output channel), and the token tile (UMMA N = 16 / 64) only costs what the batch
+// needs.  Narrow layers are split along K over a thread-block CLUSTER whose CTAs reduce their partial tiles through DSMEM - no
+// workspace, no atomics, no second kernel.  What each design step bought (k = 5120, n = 15360, m = 1, B200, profiles/
+// bench_weight_only_r2.json and ncu_weight_only_r2.md): 64-byte boxes + one issuer + smem operand 43 us; four issuers 30 us; weight
+// producer no longer throttled by the activation ring 23 us (cuBLAS bf16 on the 2x larger weight: 25 us).
 //
 // Parity: paddle/phi/kernels/gpu/weight_only_linear_kernel.cu:27, python/paddle/nn/quant/quantized_linear.py:183.
 #include <cuda.h>
@@ -26,15 +27,8 @@ namespace wo {
 
 constexpr int BLOCK_N = 128;     // output channels per CTA = UMMA M (TMEM lanes)
 constexpr int BLOCK_K = 64;
-// Warp roles for G dequantise groups (G = 4 or 6): warp 0 TMA producer; warp 1 TMEM alloc + MMA issuer 0; warps 2 .. 2G+1 dequantise
-// (two per group; 2-5 also run the epilogue); warps 2G+2 .. 3G issuers 1 .. G-1.  Group g converts k-blocks g, g + G, ... into ring slot g
-// and issuer g multiplies them, so the wait -> ld.shared -> convert -> st.shared -> fence -> arrive -> issue -> commit chains of G
-// consecutive k-blocks overlap.  The MMAs are tiny (NTOK columns): a k-block costs what its ISSUE sequence costs, and one issuing
-// thread caps at ~800 cycles per k-block - hence one issuer per slot.
-constexpr int kDqGroupWarps = 2;
-__host__ __device__ constexpr int wo_threads(int G) { return 32 * (3 * G + 1); }
+__host__ __device__ constexpr int wo_threads(int G) { return 32 * (4 + 4 * G + (G > 3 ? G - 3 : 0)); }   // producer, 3 issuers, 4G dequantise, issuers 3 ..
 __host__ __device__ constexpr uint32_t pow2_at_least(uint32_t v) { uint32_t r = 32; while (r < v) r *= 2; return r; }
-constexpr uint32_t A_TILE_BYTES = BLOCK_N * BLOCK_K * 2;   // 16 KB dequantised weight tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -90,6 +84,23 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {   // A operand in TMEM
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
+      "%23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n\t"
+      "tcgen05.wait::st.sync.aligned;"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -122,62 +133,60 @@ struct Params {
   uint32_t idesc;
 };
 
-template <bool BF16> __device__ __forceinline__ uint32_t pack2(float a, float b) {
-  if constexpr (BF16) { __nv_bfloat162 v = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
-  else { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+// PTX prmt in its default mode: selector nibble bit 3 replicates the sign bit of the selected byte (the __byte_perm intrinsic only documents 3 bits)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
 }
-
-// Pack two SMALL INTEGER floats (|v| <= 256: 8 significant bits) into the 16-bit pair.  bf16 keeps 8 significand bits, so taking the
-// high halves is exact and costs one full-rate PRMT instead of a quarter-rate F2FP; fp16 goes through the converter.
-template <bool BF16> __device__ __forceinline__ uint32_t pack2_exact(float a, float b) {
-  if constexpr (BF16) return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632);
-  else return pack2<false>(a, b);
-}
-
-// four signed int8 in `w` -> four floats (exact): byte ^ 0x80 is 0..255; 0x4B0000xx is 8388608 + xx
-__device__ __forceinline__ void int8x4_to_f(uint32_t w, float (&f)[4]) {
-  const uint32_t u = w ^ 0x80808080u;
-  f[0] = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7650)) - 8388736.f;
-  f[1] = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7651)) - 8388736.f;
-  f[2] = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7652)) - 8388736.f;
-  f[3] = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7653)) - 8388736.f;
-}
+__device__ __forceinline__ __half2 u32_as_half2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
+__device__ __forceinline__ uint32_t half2_as_u32(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+__device__ __forceinline__ __nv_bfloat162 u32_as_bf162(uint32_t v) { return *reinterpret_cast<__nv_bfloat162*>(&v); }
+__device__ __forceinline__ uint32_t bf162_as_u32(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
 
 // NTOK: token tile (UMMA N).  INT4: two weights per byte (low nibble = even k).
-// The raw weights arrive as [128 channels x 128 bytes] boxes (one TMA load = 2 k-blocks of int8 / 4 k-blocks of int4): full 128-byte
-// lines per channel row keep the L2 / DRAM request count at a quarter (int4) / half (int8) of one-k-block boxes, which is what bounded
-// the first version of this kernel.  The activation tile and the dequantised operand stay per 64-wide k-block.
+//
+// Data path of one 64-wide k-block:  TMA raw box (128 channels x 128 B, shared by 2 int8 / 4 int4 k-blocks) -> one thread per channel
+// row reads its 64 (32) bytes, expands them to 64 bf16 / fp16 in registers and stores them with tcgen05.st into the TMEM rows the tensor
+// core reads its A operand from (tcgen05.mma with A in TMEM) -> D^T[128 channels, NTOK tokens] += A x_tile^T.  The dequantised weights
+// never touch shared memory: the first version wrote them to a swizzled smem tile and the MMA read them back, and that round trip
+// (16 KB written + 16 KB read per k-block on top of the raw bytes) saturated the 128 B/clk shared-memory pipe at ~600 cycles per k-block.
+//
+// Warp roles for G ring slots: warp 0 TMA producer; warps 1-3 and 4+4G .. issuers 0 .. G-1 (warp 1 also owns the TMEM allocation);
+// warps 4 .. 4+4G-1 dequantise, four per group = one per TMEM lane quadrant (a warp may only touch lanes 32 (warp % 4) ..).  Group g
+// converts k-blocks g, g + G, ... into TMEM slot g and issuer g multiplies them: the MMAs are tiny (NTOK columns), a k-block costs what
+// its ISSUE sequence costs (~800 cycles for one thread), so every slot has its own issuer and the chains of G k-blocks overlap.
 template <int NTOK, int G, int WST, int XPER, bool INT4, bool BF16>
 __global__ void __launch_bounds__(wo_threads(G), 1)
 wo_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const Params p) {
-  constexpr int kBStages = G, kDqWarps = kDqGroupWarps * G, kDqGroups = G, kIssuers = G;
-  // Activation tiles: XPER private stages per issuer (k-block i -> stage (i % G) * XPER + (i / G) % XPER), so every x_full barrier has ONE
-  // waiter that sees its phases in order.  (A ring shared by all issuers lets one issuer run a whole phase ahead of another and read
-  // the parity of the previous phase as "done".)
-  constexpr int XST = G * XPER;
   constexpr int KB_PER_W = INT4 ? 4 : 2;                        // k-blocks covered by one raw box
   constexpr uint32_t W_BYTES = BLOCK_N * 128;                   // 16 KB raw box
   constexpr uint32_t X_BYTES = NTOK * BLOCK_K * 2;
   constexpr int ACC_PER = NTOK <= 16 ? 2 : 1;                   // independent TMEM accumulators per issuer (summed in the epilogue)
   constexpr int NACC = G * ACC_PER;
-  constexpr uint32_t TMEM_COLS = pow2_at_least(NACC * NTOK);
+  constexpr uint32_t A_COLS = BLOCK_K / 2;                      // one slot: 128 lanes x 32 columns, two 16-bit k values per column
+  constexpr uint32_t A_COL0 = NACC * NTOK;                      // accumulators first, then the G operand slots
+  constexpr uint32_t TMEM_COLS = pow2_at_least(A_COL0 + G * A_COLS);
   static_assert(TMEM_COLS <= 512, "weight-only gemm: TMEM budget");
   static_assert(NTOK * 512 <= WST * W_BYTES, "weight-only gemm: the split-K partial tile is staged in the raw weight ring");
+  // Activation tiles: XPER private stages per issuer (k-block i -> stage (i % G) * XPER + (i / G) % XPER), so every x_full barrier has ONE
+  // waiter that sees its phases in order.  (A ring shared by all issuers lets one issuer run a whole phase ahead of another and read
+  // the parity of the previous phase as "done".)
+  constexpr int XST = G * XPER;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t wring = base;                                  // [WST] raw weight boxes
   const uint32_t xring = wring + WST * W_BYTES;                 // [XST] activation tiles
-  const uint32_t aring = xring + XST * X_BYTES;                 // [kBStages] dequantised weight tiles
-  const uint32_t bars = aring + kBStages * A_TILE_BYTES;
+  const uint32_t bars = xring + XST * X_BYTES;
   auto w_full = [&](int s) { return bars + 8u * s; };
   auto w_empty = [&](int s) { return bars + 8u * (WST + s); };
   auto x_full = [&](int s) { return bars + 8u * (2 * WST + s); };
   auto x_empty = [&](int s) { return bars + 8u * (2 * WST + XST + s); };
   auto a_ready = [&](int s) { return bars + 8u * (2 * WST + 2 * XST + s); };
-  auto a_empty = [&](int s) { return bars + 8u * (2 * WST + 2 * XST + kBStages + s); };
-  const uint32_t tfull = bars + 8u * (2 * WST + 2 * XST + 2 * kBStages);
-  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + WST * W_BYTES + XST * X_BYTES + kBStages * A_TILE_BYTES + 8 * (2 * WST + 2 * XST + 2 * kBStages + 1));
+  auto a_empty = [&](int s) { return bars + 8u * (2 * WST + 2 * XST + G + s); };
+  const uint32_t tfull = bars + 8u * (2 * WST + 2 * XST + 2 * G);
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + WST * W_BYTES + XST * X_BYTES + 8 * (2 * WST + 2 * XST + 2 * G + 1));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BLOCK_N;
@@ -189,10 +198,10 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
-    for (int s = 0; s < WST; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), KB_PER_W * kDqGroupWarps); }
+    for (int s = 0; s < WST; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), KB_PER_W * 4); }
     for (int s = 0; s < XST; ++s) { mbar_init(x_full(s), 1); mbar_init(x_empty(s), 1); }
-    for (int s = 0; s < kBStages; ++s) { mbar_init(a_ready(s), kDqGroupWarps); mbar_init(a_empty(s), 1); }
-    mbar_init(tfull, kIssuers);
+    for (int s = 0; s < G; ++s) { mbar_init(a_ready(s), 4); mbar_init(a_empty(s), 1); }
+    mbar_init(tfull, G);
     fence_barrier_init();
     fence_proxy_async();
   } else if (warp == 1) {
@@ -203,123 +212,141 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const bool is_dq = warp >= 4 && warp < 4 + 4 * G;
+  const int ew = warp & 3;                                  // TMEM lane quadrant this warp may access (hardware: warp id % 4)
 
   if (warp == 0) {
     if (lane == 0) {
-      // ================= TMA producer: raw quantised weights (one box per KB_PER_W k-blocks) + the activation tile =================
-      for (int i = 0; i < num_kb; ++i) {
-        const int kb = kb0 + i;
-        if (i % KB_PER_W == 0) {                          // kb0 is a multiple of KB_PER_W (launcher), so boxes start on 128-byte columns
-          const int j = i / KB_PER_W, ws = j % WST;
-          mbar_wait(w_empty(ws), ((j / WST) & 1) ^ 1);
-          mbar_expect_tx(w_full(ws), W_BYTES);
-          tma_load_2d(wring + ws * W_BYTES, &map_w, w_full(ws), kb * (INT4 ? BLOCK_K / 2 : BLOCK_K), n0);
-        }
-        const int s = (i % G) * XPER + (i / G) % XPER;
-        mbar_wait(x_empty(s), (((i / G) / XPER) & 1) ^ 1);
-        mbar_expect_tx(x_full(s), X_BYTES);
-        tma_load_3d(xring + s * X_BYTES, &map_x, x_full(s), kb * BLOCK_K, tok0, 0);
+      // ================= TMA producer: raw quantised weights, one box per KB_PER_W k-blocks, throttled only by the box ring.  (The
+      // activation tiles are loaded by the issuers: on this thread their small ring capped the weight bytes in flight.) =================
+      const int num_box = (num_kb + KB_PER_W - 1) / KB_PER_W;
+      for (int j = 0; j < num_box; ++j) {                   // kb0 is a multiple of KB_PER_W (launcher), so boxes start on 128-byte columns
+        const int ws = j % WST;
+        mbar_wait(w_empty(ws), ((j / WST) & 1) ^ 1);
+        mbar_expect_tx(w_full(ws), W_BYTES);
+        tma_load_2d(wring + ws * W_BYTES, &map_w, w_full(ws), (kb0 + j * KB_PER_W) * (INT4 ? BLOCK_K / 2 : BLOCK_K), n0);
       }
     }
-  } else if (warp == 1 || warp >= 2 + kDqWarps) {
+  } else if (!is_dq) {
     if (lane == 0) {
-      // ================= MMA issuers: D^T[128 channels, NTOK tokens] += W_tile[128, 64] x_tile[NTOK, 64]^T =================
-      // Issuer g takes k-blocks g, g + 4, ... (ring slot g, its own accumulators).  Descriptors are built once and advanced by adding to
-      // the 14-bit (address >> 4) field.
-      const int g = warp == 1 ? 0 : warp - (1 + kDqWarps);
-      const uint64_t ad = make_desc(aring + g * A_TILE_BYTES, 16, 1024), bdesc0 = make_desc(xring, 16, 1024);
-      const uint32_t tacc = tmem_base + (uint32_t)(g * ACC_PER * NTOK);
-      int aph = 0;
-      for (int i = g; i < num_kb; i += kIssuers) {
-        const int s = g * XPER + (i / G) % XPER;
-        mbar_wait(x_full(s), ((i / G) / XPER) & 1);        // the activation tile of this k-block has landed
-        mbar_wait(a_ready(g), aph);                        // dequantise group g has written the weight tile
-        aph ^= 1;
-        tc_fence_after();
-        const uint64_t bd = bdesc0 + (uint64_t)((s * X_BYTES) >> 4);
+      // ================= MMA issuers: D^T[128 channels, NTOK tokens] += A(TMEM slot g)[128, 64] x_tile[NTOK, 64]^T =================
+      const int g = warp < 4 ? warp - 1 : warp - (4 + 4 * G) + 3;
+      if (g < G) {
+        const uint64_t bdesc0 = make_desc(xring, 16, 1024);
+        const uint32_t tacc = tmem_base + (uint32_t)(g * ACC_PER * NTOK), ta = tmem_base + A_COL0 + (uint32_t)g * A_COLS;
+        int aph = 0;
+        // issuer g also streams its own activation tiles: the tile of local iteration jj goes to private stage jj % XPER, XPER - 1 ahead
+        auto load_x = [&](int jj) {
+          const int i2 = g + jj * G;
+          if (i2 >= num_kb) return;
+          const int st = g * XPER + jj % XPER;
+          mbar_wait(x_empty(st), ((jj / XPER) & 1) ^ 1);     // the MMAs of iteration jj - XPER (committed XPER - 1 iterations ago) are done
+          mbar_expect_tx(x_full(st), X_BYTES);
+          tma_load_3d(xring + st * X_BYTES, &map_x, x_full(st), (kb0 + i2) * BLOCK_K, tok0, 0);
+        };
+        for (int jj = 0; jj < XPER - 1; ++jj) load_x(jj);
+        for (int i = g, j = 0; i < num_kb; i += G, ++j) {
+          load_x(j + XPER - 1);
+          const int s = g * XPER + j % XPER;
+          mbar_wait(x_full(s), (j / XPER) & 1);              // the activation tile of this k-block has landed
+          mbar_wait(a_ready(g), aph);                        // dequantise group g has stored the weight rows (tcgen05.st, waited, fenced)
+          aph ^= 1;
+          tc_fence_after();
+          const uint64_t bd = bdesc0 + (uint64_t)((s * X_BYTES) >> 4);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k)
-          umma_f16(tacc + (uint32_t)((k % ACC_PER) * NTOK), ad + 2 * k, bd + 2 * k, p.idesc, (i != g || k >= ACC_PER) ? 1u : 0u);
-        umma_commit(x_empty(s));
-        umma_commit(a_empty(g));
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_f16_ts(tacc + (uint32_t)((k % ACC_PER) * NTOK), ta + 8u * k, bd + 2 * k, p.idesc, (i != g || k >= ACC_PER) ? 1u : 0u);
+          umma_commit(x_empty(s));
+          umma_commit(a_empty(g));
+        }
+        umma_commit(tfull);
       }
-      umma_commit(tfull);
     }
   } else {
-    // ================= dequantise warps (then epilogue): thread = (row, 16-byte piece) work items =================
-    constexpr int DQ = kDqGroupWarps * 32;                // threads that share one k-block
-    const int grp = (warp - 2) / kDqGroupWarps;
-    const int tid = (threadIdx.x - 64) % DQ;
-    const int ew = warp & 3;                              // TMEM lane quadrant this warp may read (hardware: warp id % 4)
-    for (int i = grp; i < num_kb; i += kDqGroups) {
-      const int t = grp, j = i / KB_PER_W, ws = j % WST, sub = i % KB_PER_W;
+    // ================= dequantise warps (warps 4-7 also run the epilogue): thread = one channel row of the box =================
+    const int grp = (warp - 4) >> 2;
+    const int r = ew * 32 + lane;                            // channel row inside the tile = TMEM lane
+    const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + A_COL0 + (uint32_t)grp * A_COLS;
+    for (int i = grp; i < num_kb; i += G) {
+      const int j = i / KB_PER_W, ws = j % WST, sub = i % KB_PER_W;
       mbar_wait(w_full(ws), (j / WST) & 1);
-      mbar_wait(a_empty(t), ((i / kBStages) & 1) ^ 1);
-      const uint32_t raw = wring + ws * W_BYTES;             // 128 rows x 128 B, SWIZZLE_128B: 16-byte piece c of row r sits at piece c ^ (r & 7)
-      const uint32_t dst = aring + t * A_TILE_BYTES;
+      const uint32_t rowp = wring + ws * W_BYTES + r * 128;  // 128 rows x 128 B, SWIZZLE_128B: 16-byte piece c of row r sits at piece c ^ (r & 7)
+      // 64 dequantised values, two per register, k ascending, in the activation dtype (tcgen05 kind::f16 rejects mixed f16 x bf16
+      // operands).  The conversion rate is what bounds this kernel once the loads are deep enough, so it is done with packed 16-bit
+      // arithmetic and magic numbers instead of int -> fp32 -> 16-bit:
+      //   fp16: 0x6400 | u = 1024 + u exactly (10-bit mantissa holds a whole byte); one HSUB2 / HFMA2 removes the offset.
+      //   bf16: only 7 mantissa bits: 0x4300 | (b & 0x7F) = 128 + low7 and 0x4300 | (b & 0x80) = 128 + 128 sign, whose difference is the
+      //         two's-complement byte; int4 nibbles (value + 8 < 128) fit directly.
+      uint32_t o[32];
       if constexpr (!INT4) {
-        // this k-block = pieces 4 sub .. 4 sub + 3 of every row.  All loads are issued before the first conversion (the asm statements are
-        // volatile, i.e. kept in program order: interleaving load / convert / store per item would expose every shared-memory latency).
-        constexpr int ITEMS = 512 / DQ;
-        uint4 v[ITEMS];
+        uint4 v[4];
 #pragma unroll
-        for (int it = 0; it < ITEMS; ++it) {
-          const int c = tid + it * DQ, r = c >> 2, q = c & 3;
-          const uint32_t src = raw + r * 128 + (((sub * 4 + q) ^ (r & 7)) << 4);
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[it].x), "=r"(v[it].y), "=r"(v[it].z), "=r"(v[it].w) : "r"(src));
-        }
+        for (int q = 0; q < 4; ++q)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[q].x), "=r"(v[q].y), "=r"(v[q].z), "=r"(v[q].w) : "r"(rowp + (((sub * 4 + q) ^ (r & 7)) << 4)));
 #pragma unroll
-        for (int it = 0; it < ITEMS; ++it) {
-          const int c = tid + it * DQ, r = c >> 2, q = c & 3;
-          const uint32_t w4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
-          uint32_t o[8];
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t w4[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float f[4];
-            int8x4_to_f(w4[j], f);
-            o[2 * j] = pack2_exact<BF16>(f[0], f[1]);
-            o[2 * j + 1] = pack2_exact<BF16>(f[2], f[3]);
+          for (int e = 0; e < 4; ++e) {
+            if constexpr (BF16) {
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const uint32_t t = __byte_perm(w4[e], 0x43434343u, hh ? 0x5342 : 0x5140);      // [0x43 b1 0x43 b0]
+                o[q * 8 + e * 2 + hh] = bf162_as_u32(__hsub2(u32_as_bf162(t & 0xFF7FFF7Fu), u32_as_bf162(t & 0xFF80FF80u)));
+              }
+            } else {
+              const uint32_t u = w4[e] ^ 0x80808080u;        // byte + 128 in 0..255
+              const __half2 bias8 = u32_as_half2(0x64806480u);   // 1024 + 128
+              o[q * 8 + e * 2] = half2_as_u32(__hsub2(u32_as_half2(__byte_perm(u, 0x64646464u, 0x5140)), bias8));
+              o[q * 8 + e * 2 + 1] = half2_as_u32(__hsub2(u32_as_half2(__byte_perm(u, 0x64646464u, 0x5342)), bias8));
+            }
           }
-          // dequantised tile: K-major SWIZZLE_128B, row r at r * 128 B, 16-byte chunk j at (j ^ (r & 7)); int8 piece q -> chunks 2q, 2q+1
-          const uint32_t row = dst + r * 128;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((2 * q) ^ (r & 7)) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((2 * q + 1) ^ (r & 7)) << 4)), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
         }
       } else {
-        // this k-block = pieces 2 sub, 2 sub + 1 of every row; one 16-byte piece = 32 weights = 4 output chunks
-        constexpr int ITEMS = 256 / DQ;
-        uint4 v[ITEMS];
+        uint4 v[2];
 #pragma unroll
-        for (int it = 0; it < ITEMS; ++it) {
-          const int c = tid + it * DQ, r = c >> 1, q = c & 1;
-          const uint32_t src = raw + r * 128 + (((sub * 2 + q) ^ (r & 7)) << 4);
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[it].x), "=r"(v[it].y), "=r"(v[it].z), "=r"(v[it].w) : "r"(src));
-        }
+        for (int q = 0; q < 2; ++q)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[q].x), "=r"(v[q].y), "=r"(v[q].z), "=r"(v[q].w) : "r"(rowp + (((sub * 2 + q) ^ (r & 7)) << 4)));
+        // byte c = (k = 2c low nibble, k = 2c + 1 high nibble), nibble ^ 8 = value + 8
 #pragma unroll
-        for (int it = 0; it < ITEMS; ++it) {
-          const int c = tid + it * DQ, r = c >> 1, q = c & 1;
-          const uint32_t w4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
-          const uint32_t row = dst + r * 128;
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t w4[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {                    // 4 bytes = 8 weights = one 16-byte output chunk
-            const uint32_t lo = (w4[j] & 0x0F0F0F0Fu) ^ 0x08080808u, hi = ((w4[j] >> 4) & 0x0F0F0F0Fu) ^ 0x08080808u;   // nibble ^ 8 = value + 8
-            float a[4], b[4];
+          for (int e = 0; e < 4; ++e) {
+            if constexpr (BF16) {
+              // low / high nibbles as separate byte vectors; PRMT picks byte c of each and zero-fills the upper bytes (selector | 8
+              // replicates the sign bit of a byte < 16): [0 hi 0 lo] | 0x43004300 = (128 + lo, 128 + hi), minus 136
+              const uint32_t lo = (w4[e] ^ 0x88888888u) & 0x0F0F0F0Fu, hi = ((w4[e] >> 4) ^ 0x88888888u) & 0x0F0F0F0Fu;
+              const __nv_bfloat162 off = u32_as_bf162(0x43084308u);   // 136
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              a[e] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7650 + e)) - 8388616.f;
-              b[e] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7650 + e)) - 8388616.f;
+              for (int b = 0; b < 4; ++b) {
+                const uint32_t t = prmt(lo, hi, 0x8080 + b * 0x0001 + (4 + b) * 0x0100) | 0x43004300u;
+                o[q * 16 + e * 4 + b] = bf162_as_u32(__hsub2(u32_as_bf162(t), off));
+              }
+            } else {
+              // [0x64 byte 0x64 byte] & 0x64F0640F = (1024 + lo, 1024 + 16 hi); HFMA2 with (1, 1/16) and (-1032, -72) leaves (lo - 8, hi - 8)
+              const __half2 mul4 = u32_as_half2(0x2C003C00u), add4 = u32_as_half2(0xD480E408u);
+              const uint32_t u = w4[e] ^ 0x88888888u;
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                const uint32_t t = __byte_perm(u, 0x64646464u, 0x4040 + b * 0x0101) & 0x64F0640Fu;
+                o[q * 16 + e * 4 + b] = half2_as_u32(__hfma2(u32_as_half2(t), mul4, add4));
+              }
             }
-            const uint32_t o0 = pack2_exact<BF16>(a[0], b[0]), o1 = pack2_exact<BF16>(a[1], b[1]), o2 = pack2_exact<BF16>(a[2], b[2]), o3 = pack2_exact<BF16>(a[3], b[3]);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((4 * q + j) ^ (r & 7)) << 4)), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
           }
         }
       }
-      fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(a_ready(t)); mbar_arrive(w_empty(ws)); }   // the raw pieces are in registers / converted: the box slot may be refilled
+      if (lane == 0) mbar_arrive(w_empty(ws));               // the raw bytes are in registers: the box slot may be refilled
+      mbar_wait(a_empty(grp), ((i / G) & 1) ^ 1);            // the MMAs that read this slot's previous contents have completed
+      tc_fence_after();
+      tmem_st32(ta, o);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready(grp));
     }
-    // ---- epilogue (warps 2-5: one per TMEM lane quadrant): TMEM lane = output channel, column = token ----
-    if (warp < 6) {
+    // ---- epilogue (warps 4-7: one per TMEM lane quadrant): TMEM lane = output channel, column = token ----
+    if (warp < 8) {
       if (num_kb > 0) {
         mbar_wait(tfull, 0);
         tc_fence_after();
@@ -329,24 +356,24 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       const float sc = ch_ok ? p.scale[ch] : 0.f;
       float bv = 0.f;
       if (ch_ok && p.bias && p.splits == 1) bv = BF16 ? __bfloat162float(((const __nv_bfloat16*)p.bias)[ch]) : __half2float(((const __half*)p.bias)[ch]);
-      const int nacc = min(kIssuers, num_kb) * ACC_PER;    // accumulators that received at least one MMA (issuer g has work iff num_kb > g)
+      const int nacc = min(G, num_kb) * ACC_PER;           // accumulators that received at least one MMA (issuer g has work iff num_kb > g)
 #pragma unroll 1
       for (int c = 0; c < NTOK / 16; ++c) {
-        uint32_t r[16];
+        uint32_t acc[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = 0u;
+        for (int j = 0; j < 16; ++j) acc[j] = 0u;
         for (int a = 0; a < nacc; ++a) {
           uint32_t r2[16];
           tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + a * NTOK + c * 16, r2);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          for (int j = 0; j < 16; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(r2[j]));
         }
         if (p.splits > 1) {
           // split-K inside a cluster: park the partial tile [token][channel] in this CTA's shared memory (the raw weight ring is idle
           // now: every box was consumed before the last MMA could be issued); the cluster reduces it below through DSMEM
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(wring + (uint32_t)(((c * 16 + j) * BLOCK_N + chl) * 4)), "r"(r[j]) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(wring + (uint32_t)(((c * 16 + j) * BLOCK_N + chl) * 4)), "r"(acc[j]) : "memory");
           continue;
         }
         if (!ch_ok) continue;
@@ -354,7 +381,7 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         for (int j = 0; j < 16; ++j) {
           const int tok = tok0 + c * 16 + j;
           if (tok >= p.m) break;
-          const float y = __uint_as_float(r[j]) * sc + bv;
+          const float y = __uint_as_float(acc[j]) * sc + bv;
           if constexpr (BF16) ((__nv_bfloat16*)p.out)[(int64_t)tok * p.n + ch] = __float2bfloat16_rn(y);
           else ((__half*)p.out)[(int64_t)tok * p.n + ch] = __float2half_rn(y);
         }
@@ -366,11 +393,11 @@ wo_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     // ---- cluster reduction: the p.splits CTAs of a cluster hold the partial tiles of ONE output tile; CTA r sums 32-channel chunks
     // r, r + splits, ... over all ranks (ld.shared::cluster) and writes the scaled result.  No workspace, no atomics, no second kernel.
     cluster_sync();
-    if (warp >= 2 && warp < 6) {
+    if (warp >= 4 && warp < 8) {
       uint32_t rank;
       asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
       const int tok_n = min(NTOK, p.m - tok0);
-      for (int c = (int)rank * 4 + (warp - 2); c < tok_n * 4; c += p.splits * 4) {
+      for (int c = (int)rank * 4 + (warp - 4); c < tok_n * 4; c += p.splits * 4) {
         const int tok = c >> 2, chl = (c & 3) * 32 + lane, ch = n0 + chl;
         float acc = 0.f;
         const uint32_t local = wring + (uint32_t)((tok * BLOCK_N + chl) * 4);
@@ -429,9 +456,8 @@ static bool make_w_map(CUtensorMap* out, const void* w, int n, int row_bytes) {
 static uint32_t make_idesc(bool bf16, int ntok) {
   uint32_t d = 0;
   d |= 1u << 4;                                  // fp32 accumulate
-  const uint32_t f = bf16 ? 1u : 0u;
-  d |= f << 7;                                   // A (weights) format
-  d |= f << 10;                                  // B (activations) format
+  d |= (bf16 ? 1u : 0u) << 7;                    // A (dequantised weights, TMEM) in the activation dtype: mixed f16 x bf16 traps
+  d |= (bf16 ? 1u : 0u) << 10;                   // B (activations)
   d |= (uint32_t)(ntok >> 3) << 17;              // UMMA N = tokens
   d |= (uint32_t)(BLOCK_N >> 4) << 24;           // UMMA M = 128 channels
   return d;
@@ -440,7 +466,7 @@ static uint32_t make_idesc(bool bf16, int ntok) {
 template <int NTOK, int G, int WST, int XPER, bool INT4, bool BF16>
 static int launch(const WoGemmArgs& g, const CUtensorMap& mw, cudaStream_t s) {
   constexpr int XST = G * XPER;
-  constexpr uint32_t SMEM = WST * BLOCK_N * 128 + XST * NTOK * BLOCK_K * 2 + G * A_TILE_BYTES + 1024 + 512;
+  constexpr uint32_t SMEM = WST * BLOCK_N * 128 + XST * NTOK * BLOCK_K * 2 + 1024 + 512;
   static_assert(SMEM <= 232448, "weight-only gemm: shared memory budget");
   static_assert(8 * (2 * WST + 2 * XST + 2 * G + 1) + 8 <= 512, "weight-only gemm: barrier area");
   constexpr int kMaxSplits = 8;                 // portable cluster size
@@ -497,16 +523,15 @@ static int launch(const WoGemmArgs& g, const CUtensorMap& mw, cudaStream_t s) {
 
 template <bool INT4, bool BF16>
 static int dispatch_tok(const WoGemmArgs& g, const CUtensorMap& mw, cudaStream_t s) {
-  if (g.m <= 16) return launch<16, 6, 5, 2, INT4, BF16>(g, mw, s);       // decode: 6 groups, 80 KB of raw weights in flight
-  if (g.m <= 64) return launch<64, 4, 5, 2, INT4, BF16>(g, mw, s);
-  return launch<128, 4, 5, 1, INT4, BF16>(g, mw, s);
+  if (g.m <= 16) return launch<16, 4, 10, 4, INT4, BF16>(g, mw, s);      // decode: 160 KB of raw weights in flight
+  return launch<64, 4, 8, 3, INT4, BF16>(g, mw, s);
 }
 
 }  // namespace wo
 
 int gemm_weight_only(const WoGemmArgs& g, cudaStream_t s) {
   using namespace wo;
-  if (g.k % 64 || g.n % 8 || g.m <= 0) return 1;
+  if (g.k % 64 || g.n % 8 || g.m <= 0 || g.m > 64) return 1;      // larger batches: dequantise once + the bf16 GEMM (nn/quant.py)
   if ((reinterpret_cast<uintptr_t>(g.x) | reinterpret_cast<uintptr_t>(g.w) | reinterpret_cast<uintptr_t>(g.out)) & 15) return 1;
   CUtensorMap mw;
   const int row_bytes = g.int4 ? g.k / 2 : g.k;

@@ -62,7 +62,7 @@ def weight_only_linear(x, weight, bias=None, weight_scale=None, weight_dtype="in
             from .._build import ext
 
             x2 = xr.reshape(-1, xr.shape[-1]).contiguous()
-            if x2.shape[0] > 128:
+            if x2.shape[0] > 64:
                 # prefill: compute bound, and every token tile would dequantise the weight tile again - expand the weight once instead
                 # (one pass over the int weights) and run the bf16 tcgen05 GEMM; the fused kernel is the decode / small-batch path
                 w = weight_dequantize(weight, weight_scale, "weight_only_" + weight_dtype, x.dtype, group_size)

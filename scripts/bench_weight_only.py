@@ -44,7 +44,7 @@ for k, n in [(5120, 15360), (5120, 5120), (13824, 5120), (5120, 27648)]:
     qs = [Q.weight_quantize(w.as_subclass(paddle.Tensor), algo="weight_only_int8") for w in ws]
     q4 = [Q.weight_quantize(w.as_subclass(paddle.Tensor), algo="weight_only_int4") for w in ws]
     wb = [w.to(torch.bfloat16) for w in ws]
-    for m in (1, 16, 64, 4096):
+    for m in (1, 16, 64):
         x = (torch.randn(m, k, device="cuda") * 0.5).to(torch.bfloat16)
         i = [0]
 
