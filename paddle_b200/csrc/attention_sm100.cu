@@ -6,10 +6,15 @@
 // Parity (behaviour): paddle.nn.functional.flash_attention / scaled_dot_product_attention
 // (python/paddle/nn/functional/flash_attention.py -> phi flash_attn kernels calling the flash-attention library).
 //
-// CTA = 128 query rows of one (batch, head).  Warps 0-7: softmax + epilogue (two warpgroups, one 64-key half of each S tile
-// each), warp 8: TMA producer, warp 9: TMEM alloc + MMA issuer.
-// TMEM columns: [0,128) S buffer 0, [128,256) S buffer 1, [256,384) O accumulator.  P is double-buffered in shared memory so
-// the softmax of tile j+1 overlaps the P V MMA of tile j (it only waits for that MMA when a row maximum really moved).
+// CTA = 128 query rows of one (batch, head).  The key tiles are dealt to TWO independent softmax streams by parity: warpgroup w
+// (warps 4w .. 4w+3, one thread = one query row = one TMEM lane, the whole 128-key row of the tile) owns tiles w, w + 2, ... with its own
+// S buffer, P buffer, running (max, sum) and its own O accumulator in TMEM; the two partial results are merged once in the epilogue
+// (flash-decoding style).  Nothing is exchanged between the warpgroups per tile, so their phases drift apart and the exp2 unit, which
+// bounds the softmax (16 / clk / SM = 1024 cycles per tile, the same as the two MMAs), is fed by one stream while the other loads,
+// reduces, stores P or waits.  Warp 8: TMA producer; warp 9: TMEM alloc + S = Q K^T issuer; warp 10: O += P V issuer - one thread
+// issuing all 16 MMAs of a tile (descriptor arithmetic included) needed ~2900 cycles per tile and was itself the bound (ncu: the issuer
+// warp busy 78 % of the time, profiles/ncu_attention_r2.md).
+// TMEM columns: [0,128) S stream 0, [128,256) S stream 1, [256,384) O stream 0, [384,512) O stream 1.
 #include <cuda.h>
 #include <cstdio>
 #include <string>
@@ -21,10 +26,10 @@ namespace b200 {
 namespace attn {
 
 constexpr int BM = 128, BN = 128, HD = 128;
-constexpr int kThreads = 320;   // warps 0-7: softmax (2 warpgroups), warp 8: TMA producer, warp 9: TMEM alloc + MMA issuer
+constexpr int kThreads = 352;   // warps 0-7: softmax (2 warpgroups = 2 streams), warp 8: TMA producer, warp 9: TMEM alloc + QK issuer, warp 10: PV issuer
 constexpr uint32_t TILE_BYTES = 128 * 128 * 2;   // 32 KB: every operand tile (Q, K, V, P)
 constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;  // one 64-wide K-block of a tile
-constexpr uint32_t SMEM_BYTES = 7 * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*row max / sum exchange*/;   // Q, 2x K, 2x V, 2x P
+constexpr uint32_t SMEM_BYTES = 7 * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;   // Q, 2x K, 2x V, 2x P (the epilogue exchange reuses the Q tile)
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t O_COL = 256;
 
@@ -158,16 +163,17 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   auto sK = [&](int s) { return base + (1 + s) * TILE_BYTES; };
   auto sV = [&](int s) { return base + (3 + s) * TILE_BYTES; };
   const uint32_t bars = base + 7 * TILE_BYTES;
-  const uint32_t q_full = bars, pv_done = bars + 8 * 13;
-  auto p_full = [&](int s) { return bars + 8u * (14 + s); };
-  auto p_free = [&](int s) { return bars + 8u * (16 + s); };
+  const uint32_t q_full = bars;
   auto k_full = [&](int s) { return bars + 8u * (1 + s); };
   auto v_full = [&](int s) { return bars + 8u * (3 + s); };
   auto k_empty = [&](int s) { return bars + 8u * (5 + s); };
   auto v_empty = [&](int s) { return bars + 8u * (7 + s); };
-  auto s_full = [&](int s) { return bars + 8u * (9 + s); };
-  auto s_empty = [&](int s) { return bars + 8u * (11 + s); };
-  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + 7 * TILE_BYTES + 8 * 18);
+  auto s_full = [&](int w) { return bars + 8u * (9 + w); };      // per stream: S tile computed
+  auto s_empty = [&](int w) { return bars + 8u * (11 + w); };    // per stream: S tile consumed (4 warp arrivals)
+  auto pv_done = [&](int w) { return bars + 8u * (13 + w); };    // per stream: O accumulator holds every P V issued so far
+  auto p_full = [&](int w) { return bars + 8u * (15 + w); };     // per stream: P tile written (4 warp arrivals)
+  auto p_free = [&](int w) { return bars + 8u * (17 + w); };     // per stream: P tile read by its P V
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + 7 * TILE_BYTES + 8 * 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = (int)gridDim.x - 1 - (int)blockIdx.x;   // long (late) rows first under the causal mask
@@ -187,10 +193,10 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(k_full(s), 1); mbar_init(v_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_empty(s), 1);
-      mbar_init(s_full(s), 1); mbar_init(s_empty(s), 8);
-      mbar_init(p_full(s), 8); mbar_init(p_free(s), 1);
+      mbar_init(s_full(s), 1); mbar_init(s_empty(s), 4);
+      mbar_init(p_full(s), 4); mbar_init(p_free(s), 1);
+      mbar_init(pv_done(s), 1);
     }
-    mbar_init(pv_done, 1);
     fence_barrier_init();
     fence_proxy_async();
   } else if (warp == 9) {
@@ -226,172 +232,196 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     }
   } else if (warp == 9) {
     if (lane == 0 && n_tiles > 0) {
-      // ================= MMA issuer =================
+      // ================= S = Q K^T issuer.  Descriptors are built once; a k-step only adds to the 14-bit (address >> 4) field =========
       mbar_wait(q_full, 0);
-      auto issue_qk = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(k_full(s), (j >> 1) & 1);
-        mbar_wait(s_empty(s), ((j >> 1) & 1) ^ 1);
+      const uint64_t qd = make_desc(sQ, 16, 1024), kd0 = make_desc(sK(0), 16, 1024);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1, ph = (j >> 1) & 1;              // K stage and stream share the parity of j
+        mbar_wait(k_full(s), ph);
+        mbar_wait(s_empty(s), ph ^ 1);
         tc_fence_after();
+        const uint64_t kd = kd0 + (uint64_t)((s * TILE_BYTES) >> 4);
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_base + s * BN, make_desc(sQ + kb * HALF_BYTES + k * 32, 16, 1024),
-                     make_desc(sK(s) + kb * HALF_BYTES + k * 32, 16, 1024), p.idesc_qk, (kb | k) != 0);
+            umma_f16(tmem_base + s * BN, qd + ((kb * HALF_BYTES + k * 32) >> 4), kd + ((kb * HALF_BYTES + k * 32) >> 4), p.idesc_qk, (kb | k) != 0);
         umma_commit(s_full(s));
         umma_commit(k_empty(s));
-      };
-      issue_qk(0);
+      }
+    }
+  } else if (warp == 10) {
+    if (lane == 0 && n_tiles > 0) {
+      // ================= O_stream += P V issuer =================
+      const uint64_t pd0 = make_desc(sP(0), 16, 1024), vd0 = make_desc(sV(0), 8192, 1024);
       for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) issue_qk(j + 1);     // S(j+1) is computed while the softmax warps work on S(j)
-        const int s = j & 1;
-        mbar_wait(p_full(s), (j >> 1) & 1);
-        mbar_wait(v_full(s), (j >> 1) & 1);
+        const int s = j & 1, ph = (j >> 1) & 1;
+        mbar_wait(p_full(s), ph);
+        mbar_wait(v_full(s), ph);
         tc_fence_after();
+        const uint64_t pd = pd0 + (uint64_t)((s * TILE_BYTES) >> 4), vd = vd0 + (uint64_t)((s * TILE_BYTES) >> 4);
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_base + O_COL, make_desc(sP(s) + kb * HALF_BYTES + k * 32, 16, 1024),
-                     make_desc(sV(s) + kb * HALF_BYTES + k * 2048, 8192, 1024), p.idesc_pv, (j | kb | k) != 0);
-        umma_commit(pv_done);
+            umma_f16(tmem_base + O_COL + s * HD, pd + ((kb * HALF_BYTES + k * 32) >> 4), vd + ((kb * HALF_BYTES + k * 2048) >> 4), p.idesc_pv, (j >= 2) || (kb | k) != 0);
+        umma_commit(pv_done(s));
         umma_commit(p_free(s));
         umma_commit(v_empty(s));
       }
     }
   } else {
-    // ================= softmax + epilogue: 2 warpgroups, each owns one 64-key half of every S tile =================
-    // thread -> (query row = TMEM lane, key half).  Two warps per scheduler hide each other's latencies; the row maximum is
-    // agreed between the two halves through shared memory once per tile, the row sums stay separate until the epilogue.
-    const int half = warp >> 2;                      // 0: keys [0,64) of the tile, 1: keys [64,128)
+    // ================= softmax + epilogue: warpgroup w is stream w (tiles w, w + 2, ...); thread -> query row = TMEM lane ==========
+    const int w = warp >> 2;
     const int rl = (warp & 3) * 32 + lane;           // row inside the tile == TMEM lane
     const int row = m0 + rl;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    float* xch = reinterpret_cast<float*>(gen + 7 * TILE_BYTES + 8 * 20);   // [2 (half)][128] floats
+    const uint32_t tS = tmem_base + lane_off + w * BN, tO = tmem_base + lane_off + O_COL + w * HD;
     float m_i = -INFINITY, l_i = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
-      const int sb = j & 1, n0 = j * BN + half * 64;
-      mbar_wait(s_full(sb), (j >> 1) & 1);
+    int it = 0;                                      // local iteration of this stream
+    for (int j = w; j < n_tiles; j += 2, ++it) {
+      const int ph = it & 1;
+      mbar_wait(s_full(w), ph);
       tc_fence_after();
-      float s[64];
+      // The whole 128-key row goes to registers at once and the S buffer is handed back immediately: this stream's next Q K^T (issue +
+      // MMA + commit is ~1500-2500 cycles of latency) then runs under this tile's softmax instead of after it.
+      float sv[128];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + lane_off + sb * BN + half * 64 + c * 32, r);
+        tmem_ld32(tS + c * 32, r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(r[i]);   // raw logits; the softmax scale is folded into the exp2 FFMA
+        for (int i = 0; i < 32; ++i) sv[c * 32 + i] = __uint_as_float(r[i]);   // raw logits; the softmax scale is folded into the exp2 FFMA
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty(sb));      // QK(j+2) may overwrite this S buffer (8 warp arrivals)
+      if (lane == 0) mbar_arrive(s_empty(w));
       const bool edge = (j * BN + BN > p.sk) || (p.causal && j * BN + BN - 1 > m0 + p.causal_off);
       if (edge) {
-        const int lim = p.causal ? min(p.sk - 1, row + p.causal_off) : p.sk - 1;   // last visible key
+        const int lim = (p.causal ? min(p.sk - 1, row + p.causal_off) : p.sk - 1) - j * BN;   // last visible key, tile-relative
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (n0 + i > lim) s[i] = -INFINITY;
+        for (int i = 0; i < 128; ++i)
+          if (i > lim) sv[i] = -INFINITY;
       }
       if constexpr (MASKED) {     // flashmask / varlen: key column j hides the query rows [lt_start, lt_end) and [ut_start, ut_end)
         const int4* cm = p.colmask + ((int64_t)batch * p.mask_heads + (p.mask_heads > 1 ? head : 0)) * p.sk;
-#pragma unroll 8
-        for (int i = 0; i < 64; ++i) {
-          const int key = n0 + i;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          const int key = j * BN + i;
           if (key < p.sk) {
             const int4 m = __ldg(cm + key);         // same address in every lane: one broadcast transaction
-            if ((row >= m.x && row < m.y) || (row >= m.z && row < m.w)) s[i] = -INFINITY;
+            if ((row >= m.x && row < m.y) || (row >= m.z && row < m.w)) sv[i] = -INFINITY;
           }
         }
       }
       float mxp[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mxp[i] = s[i];
+      for (int i = 0; i < 8; ++i) mxp[i] = sv[i];
 #pragma unroll
-      for (int i = 8; i < 64; ++i) mxp[i & 7] = fmaxf(mxp[i & 7], s[i]);
-      float mx = fmaxf(fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])), fmaxf(fmaxf(mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7])));
-      xch[half * 128 + rl] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mx = fmaxf(mx, xch[(half ^ 1) * 128 + rl]) * p.scale_log2;   // scale > 0
-      asm volatile("bar.sync 1, 256;" ::: "memory");              // exchange slots may be rewritten (shared memory is full: one slot set)
+      for (int i = 8; i < 128; ++i) mxp[i & 7] = fmaxf(mxp[i & 7], sv[i]);
+      const float mx = fmaxf(fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])), fmaxf(fmaxf(mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7]))) * p.scale_log2;   // scale > 0
       float m_new = fmaxf(m_i, mx);
       if (m_new == -INFINITY) m_new = 0.f;          // fully masked so far: keep exp2 finite
-      if (j == 0) {
+      if (it == 0) {
         m_i = m_new;
       } else {
-        const bool need = (m_new - m_i) > 8.f;      // lazy rescale: keep a stale max while exp2 stays <= 2^8 (same decision in both halves)
-        if (__any_sync(0xffffffffu, need)) {         // rare: only then must P V (j-1) have landed in TMEM before we touch O
-          mbar_wait(pv_done, (j - 1) & 1);
+        const bool need = (m_new - m_i) > 8.f;      // lazy rescale: keep a stale max while exp2 stays <= 2^8
+        if (__any_sync(0xffffffffu, need)) {         // rare: only then must this stream's previous P V have landed before we touch O
+          mbar_wait(pv_done(w), (it - 1) & 1);
           tc_fence_after();
           const float alpha = need ? ex2(m_i - m_new) : 1.f;
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {              // this half rescales its 64 columns of O
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
             uint32_t r[32];
-            tmem_ld32(tmem_base + lane_off + O_COL + half * 64 + c * 32, r);
+            tmem_ld32(tO + c * 32, r);
 #pragma unroll
             for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st32(tmem_base + lane_off + O_COL + half * 64 + c * 32, r);
+            tmem_st32(tO + c * 32, r);
           }
+          tc_fence_before();
           l_i *= alpha;
           if (need) m_i = m_new;
         }
       }
-      mbar_wait(p_free(sb), ((j >> 1) & 1) ^ 1);    // P V (j-2) has finished reading this P buffer
+      mbar_wait(p_free(w), ph ^ 1);                 // this stream's previous P V has finished reading the P buffer
+      // ---- P = exp2(S * scale - m), row sum, P tile to shared memory (K-major SWIZZLE_128B, two 64-key blocks) ----
       float sump[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) sump[e] = 0.f;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 16; ++c) {                 // 8 keys = one 16-byte piece
         uint32_t u[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float p0 = ex2(fmaf(s[c * 8 + 2 * e], p.scale_log2, -m_i));
-          const float p1 = ex2(fmaf(s[c * 8 + 2 * e + 1], p.scale_log2, -m_i));
+          const float p0 = ex2(fmaf(sv[c * 8 + 2 * e], p.scale_log2, -m_i));
+          const float p1 = ex2(fmaf(sv[c * 8 + 2 * e + 1], p.scale_log2, -m_i));
           sump[2 * e] += p0;
           sump[2 * e + 1] += p1;
           u[e] = pack2<T>(p0, p1);          // one cvt.rn.{bf16x2,f16x2}.f32 per pair
         }
-        // K-major SWIZZLE_128B: the 64-key block `half`, row r at r*128 B, 16-byte chunk index XOR (r % 8)
-        const uint32_t addr = sP(sb) + half * HALF_BYTES + rl * 128 + ((c ^ (rl & 7)) << 4);
+        const uint32_t addr = sP(w) + (c >> 3) * HALF_BYTES + rl * 128 + (((c & 7) ^ (rl & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
       }
       l_i += ((sump[0] + sump[1]) + (sump[2] + sump[3])) + ((sump[4] + sump[5]) + (sump[6] + sump[7]));
       fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full(sb));      // 8 warp arrivals
+      if (lane == 0) mbar_arrive(p_full(w));       // this stream's P V may start
     }
-    if (n_tiles > 0) {
-      mbar_wait(pv_done, (n_tiles - 1) & 1);
+    if (it > 0) {
+      mbar_wait(pv_done(w), (it - 1) & 1);
       tc_fence_after();
     }
-    // combine the two halves' row sums
-    xch[half * 128 + rl] = l_i;
+    // ---- merge the two streams: row r of both O accumulators lives in TMEM lane r, which both warpgroups' warp (r / 32) can read; only
+    // (max, sum) cross through shared memory - each stream publishes in its OWN P buffer, which is idle once its last P V completed
+    // (the Q / K / V tiles may still be read by the other stream's MMAs) ----
+    float* xch_me = reinterpret_cast<float*>(gen + (5 + w) * TILE_BYTES);        // [128][2] floats
+    const float* xch_x = reinterpret_cast<const float*>(gen + (5 + (w ^ 1)) * TILE_BYTES);
+    xch_me[rl * 2] = it > 0 ? m_i : -INFINITY;
+    xch_me[rl * 2 + 1] = it > 0 ? l_i : 0.f;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float l_tot = l_i + xch[(half ^ 1) * 128 + rl];
+    const float m_x = xch_x[rl * 2], l_x = xch_x[rl * 2 + 1];
+    const float m_me = it > 0 ? m_i : -INFINITY, l_me = it > 0 ? l_i : 0.f;
+    float m_tot = fmaxf(m_me, m_x);
+    if (m_tot == -INFINITY) m_tot = 0.f;
+    const float a_me = l_me > 0.f ? ex2(m_me - m_tot) : 0.f, a_x = l_x > 0.f ? ex2(m_x - m_tot) : 0.f;
+    const float l_tot = l_me * a_me + l_x * a_x;
     const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
-    T* orow = reinterpret_cast<T*>(p.o) + (int64_t)batch * p.o_sb + (int64_t)row * p.o_ss + (int64_t)head * p.o_sh + half * 64;
+    const float c_me = a_me * inv, c_x = a_x * inv;
+    const bool any_me = __any_sync(0xffffffffu, c_me != 0.f), any_x = __any_sync(0xffffffffu, c_x != 0.f);   // tcgen05.ld is warp-collective
+    // warpgroup w writes output columns [64 w, 64 w + 64) of its rows from BOTH accumulators
+    const uint32_t tO_me = tmem_base + lane_off + O_COL + w * HD + w * 64, tO_x = tmem_base + lane_off + O_COL + (w ^ 1) * HD + w * 64;
+    T* orow = reinterpret_cast<T*>(p.o) + (int64_t)batch * p.o_sb + (int64_t)row * p.o_ss + (int64_t)head * p.o_sh + w * 64;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      float acc[32];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {                   // this half writes its 64 output columns
-      uint32_t r[32];
-      if (n_tiles > 0) {
-        tmem_ld32(tmem_base + lane_off + O_COL + half * 64 + c * 32, r);
-      } else {
+      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+      if (any_me) {
+        uint32_t r[32];
+        tmem_ld32(tO_me + c * 32, r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = 0u;
+        for (int i = 0; i < 32; ++i) acc[i] = c_me != 0.f ? __uint_as_float(r[i]) * c_me : 0.f;
+      }
+      if (any_x) {
+        uint32_t r[32];
+        tmem_ld32(tO_x + c * 32, r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] += c_x != 0.f ? __uint_as_float(r[i]) * c_x : 0.f;
       }
       if (row < p.sq) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 o;
-          o.x = pack2<T>(__uint_as_float(r[q * 8 + 0]) * inv, __uint_as_float(r[q * 8 + 1]) * inv);
-          o.y = pack2<T>(__uint_as_float(r[q * 8 + 2]) * inv, __uint_as_float(r[q * 8 + 3]) * inv);
-          o.z = pack2<T>(__uint_as_float(r[q * 8 + 4]) * inv, __uint_as_float(r[q * 8 + 5]) * inv);
-          o.w = pack2<T>(__uint_as_float(r[q * 8 + 6]) * inv, __uint_as_float(r[q * 8 + 7]) * inv);
+          o.x = pack2<T>(acc[q * 8 + 0], acc[q * 8 + 1]);
+          o.y = pack2<T>(acc[q * 8 + 2], acc[q * 8 + 3]);
+          o.z = pack2<T>(acc[q * 8 + 4], acc[q * 8 + 5]);
+          o.w = pack2<T>(acc[q * 8 + 6], acc[q * 8 + 7]);
           *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = o;
         }
       }
     }
-    if (half == 0 && row < p.sq && p.lse) p.lse[((int64_t)batch * p.h + head) * p.sq + row] = l_tot > 0.f ? (m_i + log2f(l_tot)) * 0.69314718055994531f : -INFINITY;
+    if (w == 0 && row < p.sq && p.lse) p.lse[((int64_t)batch * p.h + head) * p.sq + row] = l_tot > 0.f ? (m_tot + log2f(l_tot)) * 0.69314718055994531f : -INFINITY;
     tc_fence_before();
   }
 

@@ -690,8 +690,7 @@ std::vector<Tensor> attention_fwd(const Tensor& q, const Tensor& k, const Tensor
   if (out_seq_major) { a.o_strides[0] = (int64_t)a.h * a.d; a.o_strides[1] = (int64_t)a.b * a.h * a.d; a.o_strides[2] = a.d; }
   Tensor lse = torch::empty({a.b, a.h, a.sq}, q.options().dtype(at::kFloat));
   a.o = out.data_ptr(); a.lse = lse.data_ptr<float>();
-  static const int variant = [] { const char* e = getenv("B200_ATTN_FWD"); return e ? atoi(e) : 1; }();   // 1: single query tile, key-split softmax warpgroups (default, fastest measured); 2: ping-pong (experimental)
-  int rc = (variant == 2 && a.sq >= 256 && !a.colmask) ? b200::attention_fwd2(a, cur_stream()) : b200::attention_fwd(a, cur_stream());
+  int rc = b200::attention_fwd(a, cur_stream());
   g_launches += 1;
   check_err();
   TORCH_CHECK(rc == 0, "paddle_b200.attention_fwd launch failed rc=", rc);

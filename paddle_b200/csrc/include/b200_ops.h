@@ -193,8 +193,6 @@ struct AttnArgs {
 };
 int attention_fwd_supported(const AttnArgs& a);
 int attention_fwd(const AttnArgs& a, cudaStream_t s);
-// ping-pong variant: two query tiles per CTA (attention_fwd2_sm100.cu); same contract
-int attention_fwd2(const AttnArgs& a, cudaStream_t s);
 // Backward (attention_bwd_sm100.cu). fwd: the forward's arguments with o (contiguous [B,Sq,H,D]) and lse filled in.
 // d_o: contiguous [B,Sq,H,D]; delta: fp32 scratch [B,H,Sq]; dq: fp32 [B,Sq,H,D] ZEROED by the caller; dk/dv: [B,Sk,Hk,D] views (dkv_strides).
 struct AttnBwdArgs {
