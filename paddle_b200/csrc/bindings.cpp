@@ -628,6 +628,61 @@ Tensor gemm_fp8(const Tensor& a, const Tensor& b, const OptT& bias, double scale
   return d;
 }
 
+// OCP MX quantisation of a contiguous [rows, K] tensor (rows, K multiples of 128) along K: (q e4m3 [rows, K], sf uint8 [rows / 128 * K / 128 * 512])
+std::vector<Tensor> quantize_mx(const Tensor& x) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous() && x.size(0) % 128 == 0 && x.size(1) % 128 == 0, "quantize_mx: contiguous [rows, K] with rows, K multiples of 128");
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor q = torch::empty({x.size(0), x.size(1)}, x.options().dtype(at::kFloat8_e4m3fn));
+  Tensor sf = torch::empty({x.size(0) / 128 * (x.size(1) / 128) * 512}, x.options().dtype(at::kByte));
+  int rc = b200::mx_quantize(x.data_ptr(), x.size(0), x.size(1), dt_code(x), q.data_ptr(), sf.data_ptr<uint8_t>(), cur_stream());
+  g_launches += 1;
+  check_err();
+  TORCH_CHECK(rc == 0, "paddle_b200.quantize_mx failed rc=", rc);
+  return {q, sf};
+}
+
+Tensor dequantize_mx(const Tensor& q, const Tensor& sf) {
+  TORCH_CHECK(q.is_cuda() && q.dim() == 2 && q.is_contiguous() && q.scalar_type() == at::kFloat8_e4m3fn && sf.scalar_type() == at::kByte && sf.is_contiguous()
+              && sf.numel() == q.size(0) / 128 * (q.size(1) / 128) * 512, "dequantize_mx: (q e4m3 [rows, K], sf) as produced by quantize_mx");
+  c10::cuda::CUDAGuard guard(q.device());
+  Tensor out = torch::empty({q.size(0), q.size(1)}, q.options().dtype(at::kFloat));
+  int rc = b200::mx_dequantize(q.data_ptr(), sf.data_ptr<uint8_t>(), q.size(0), q.size(1), out.data_ptr<float>(), cur_stream());
+  g_launches += 1;
+  check_err();
+  TORCH_CHECK(rc == 0, "paddle_b200.dequantize_mx failed rc=", rc);
+  return out;
+}
+
+// D[M,N] = (A * 2^sfa) (B * 2^sfb)^T: both operands e4m3 K-major with one E8M0 scale per 32 k (quantize_mx); M, N, K multiples of 128
+Tensor gemm_fp8_mx(const Tensor& a, const Tensor& sfa, const Tensor& b, const Tensor& sfb, const OptT& bias, at::ScalarType out_dtype) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.dim() == 2 && b.dim() == 2 && a.is_contiguous() && b.is_contiguous() && a.size(1) == b.size(1),
+              "gemm_fp8_mx: operands must be contiguous [M,K] and [N,K]");
+  TORCH_CHECK(a.scalar_type() == at::kFloat8_e4m3fn && b.scalar_type() == at::kFloat8_e4m3fn, "gemm_fp8_mx: e4m3 operands required");
+  TORCH_CHECK(a.size(0) % 128 == 0 && b.size(0) % 128 == 0 && a.size(1) % 128 == 0, "gemm_fp8_mx: M, N, K must be multiples of 128");
+  TORCH_CHECK(sfa.scalar_type() == at::kByte && sfb.scalar_type() == at::kByte && sfa.is_contiguous() && sfb.is_contiguous()
+              && sfa.numel() == a.size(0) / 128 * (a.size(1) / 128) * 512 && sfb.numel() == b.size(0) / 128 * (b.size(1) / 128) * 512, "gemm_fp8_mx: scale blocks do not match the operands");
+  c10::cuda::CUDAGuard guard(a.device());
+  b200::GemmFp8Args g;
+  g.m = (int)a.size(0); g.k = (int)a.size(1); g.n = (int)b.size(0);
+  Tensor d = torch::empty({g.m, g.n}, a.options().dtype(out_dtype));
+  g.a = a.data_ptr(); g.b = b.data_ptr(); g.d = d.data_ptr();
+  g.bias = nullptr;
+  if (bias.has_value() && bias->defined()) {
+    TORCH_CHECK(bias->scalar_type() == out_dtype && bias->numel() == g.n, "gemm_fp8_mx: bias must be [N] in the output dtype");
+    g.bias = bias->data_ptr();
+  }
+  g.lda = a.stride(0); g.ldb = b.stride(0); g.ldd = d.stride(0);
+  g.a_e5m2 = 0; g.b_e5m2 = 0;
+  g.scale = 1.f; g.act = 0; g.out_dtype = dt_code(d); g.batch = 1;
+  g.sfa = sfa.data_ptr<uint8_t>(); g.sfb = sfb.data_ptr<uint8_t>();
+  g.stride_a = g.stride_b = g.stride_d = 0;
+  int rc = b200::gemm_fp8_tcgen05(g, cur_stream());
+  g_launches += 1;
+  check_err();
+  TORCH_CHECK(rc == 0, "paddle_b200.gemm_fp8_mx launch failed rc=", rc);
+  return d;
+}
+
 // q [B,H,D], k_cache / v_cache [B,Hkv,S_max,D] contiguous, lens int32 [B] -> out [B,H,D]
 Tensor decode_attention(const Tensor& q, const Tensor& k_cache, const Tensor& v_cache, const Tensor& lens, double scale) {
   TORCH_CHECK(q.is_cuda() && q.dim() == 3 && k_cache.dim() == 4 && v_cache.dim() == 4 && q.is_contiguous() && k_cache.is_contiguous() && v_cache.is_contiguous(),
@@ -807,6 +862,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_grouped_wgrad", traced("gemm_grouped_wgrad", &gemm_grouped_wgrad));
   m.def("gemm_fp8", traced("gemm_fp8", &gemm_fp8), pybind11::arg("a"), pybind11::arg("b"), pybind11::arg("bias") = pybind11::none(), pybind11::arg("scale") = 1.0,
         pybind11::arg("act") = 0, pybind11::arg("out_dtype") = at::kBFloat16, pybind11::arg("scale_a") = pybind11::none(), pybind11::arg("scale_b") = pybind11::none());
+  m.def("quantize_mx", traced("quantize_mx", &quantize_mx));
+  m.def("dequantize_mx", traced("dequantize_mx", &dequantize_mx));
+  m.def("gemm_fp8_mx", traced("gemm_fp8_mx", &gemm_fp8_mx), pybind11::arg("a"), pybind11::arg("sfa"), pybind11::arg("b"), pybind11::arg("sfb"), pybind11::arg("bias") = pybind11::none(),
+        pybind11::arg("out_dtype") = at::kBFloat16);
   m.def("quantize_fp8", traced("quantize_fp8", &quantize_fp8), pybind11::arg("x"), pybind11::arg("e5m2") = false, pybind11::arg("want_transpose") = false);
   m.def("decode_attention", traced("decode_attention", &decode_attention));
   m.def("attention_supported", &attention_supported);

@@ -3,6 +3,12 @@
 // instruction, 2x the bf16 rate), fp32 accumulation and a per-tensor dequantisation scale (+ bias / activation) fused in the
 // epilogue.  Both operands are K-major ("TN" GEMM): A [M,K], B [N,K], 1 byte per element.
 //
+// MX variant (`MX = true`, BN = 128): OCP microscaling - one E8M0 (power-of-two) scale per 32 consecutive K elements of every A row
+// and B row.  The scale bytes travel as 512-byte blocks (128 rows x 4 k-blocks, byte = (row % 32) * 16 + (row / 32) * 4 + k-block: the
+// layout tcgen05.cp.32x128b.warpx4 scatters into 4 TMEM columns of every lane quadrant), one bulk copy per operand and stage; the issuer
+// copies them smem -> TMEM in front of the stage's four `tcgen05.mma.kind::mxf8f6f4.block_scale` (the k-block is selected by the
+// a_sf_id / b_sf_id fields of the instruction descriptor), so dequantisation costs no epilogue work and no extra pass.
+//
 // Parity (behaviour): fp8_fp8_half_gemm_fused (paddle/phi/kernels/fusion/fp8_gemm/fp8_gemm_with_cublasLt/*) which calls cuBLASLt.
 #include <cuda.h>
 #include <cstdio>
@@ -23,11 +29,24 @@ constexpr int kThreads = 256;
 constexpr int kAccStages = 2;
 constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K;      // 16 KB
 
-template <int BN> struct Cfg {
+constexpr uint32_t SF_BLOCK_BYTES = 512;   // scale bytes of 128 rows x 128 k (4 blocks of 32)
+
+template <int BN, bool MX = false> struct Cfg {
   static constexpr uint32_t B_STAGE_BYTES = BN * BLOCK_K;
-  static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr uint32_t TMEM_COLS = kAccStages * BN;  // 512 / 256 / 128: powers of two >= 32
+  static constexpr uint32_t SF_BYTES = MX ? 2048u : 0u;          // [SFA 512 | SFB 512 per 128 columns] behind the operand tiles
+  static constexpr uint32_t SF_TX = MX ? SF_BLOCK_BYTES * (1 + BN / 128) : 0u;
+  static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES + SF_BYTES;
+  static constexpr uint32_t TX_BYTES = A_STAGE_BYTES + B_STAGE_BYTES + SF_TX;
+  // MX at BN = 256 keeps ONE accumulator (256 columns) so that the scale columns fit: a 128-wide tile reads A and B from shared memory
+  // at 128 B/clk for full-rate fp8 MMAs - all the pipe has, before the TMA writes - and tops out at ~1.5 PFLOP/s; the 256-wide tile
+  // needs 96 B/clk and wins even without the epilogue overlap.
+  static constexpr int ACC = (MX && BN == 256) ? 1 : kAccStages;
+  static constexpr uint32_t SF_COL0 = ACC * BN;                  // MX: per smem stage 4 columns SFA + BN / 32 columns SFB after the accumulators
+  static constexpr uint32_t SF_STAGE_COLS = BN == 256 ? 16 : 8;
+  static constexpr uint32_t TMEM_COLS = MX ? 512u : kAccStages * BN;  // powers of two >= 32
   static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(!MX || ACC * BN + kStages * SF_STAGE_COLS <= 512, "MX: TMEM budget");
+  static_assert(SMEM_BYTES <= 232448, "fp8 gemm: shared memory budget");
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -93,6 +112,30 @@ __device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// block-scaled MMA: D += (A * 2^sfa) (B * 2^sfb)^T, one E8M0 scale per 32 k; the scale bytes sit in TMEM columns [tsfa, +4) / [tsfb, +4)
+__device__ __forceinline__ void umma_mxf8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t tsfa, uint32_t tsfb, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale.scale_vec::1X [%0], %1, %2, %3, [%4], [%5], p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(tsfa), "r"(tsfb), "r"(accumulate)
+      : "memory");
+}
+// 32 rows x 128 bits of shared memory -> 4 TMEM columns, replicated into the four 32-lane quadrants
+__device__ __forceinline__ void tmem_cp_sf(uint32_t tmem_dst, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
+}
+// un-swizzled K-major descriptor of a scale block: 8-row x 16-byte atoms, 128 bytes apart along the rows (one atom along K)
+__device__ __forceinline__ uint64_t make_sf_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(128u >> 4) << 32;          // SBO
+  d |= (uint64_t)1 << 46;
+  return d;                                   // layout type 0 = no swizzle, LBO 0
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -134,6 +177,8 @@ struct Params {
   float scale;
   const float* scale_a;   // optional device scalars (per-tensor dequantisation factors produced by quantize_fp8): no host round trip
   const float* scale_b;
+  const uint8_t* sfa;     // MX: E8M0 scale blocks [m / 128][k / 128][512] of A, same for B over n
+  const uint8_t* sfb;
   uint32_t idesc;
 };
 
@@ -163,10 +208,10 @@ __device__ __forceinline__ void store_row_chunk(TO* __restrict__ dst, const floa
   }
 }
 
-template <int BN>
+template <int BN, bool MX>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_fp8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, MX>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024B alignment
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -227,10 +272,16 @@ gemm_fp8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          mbar_expect_tx(full_bar(stage), C::TX_BYTES);
           const int k0 = kb * BLOCK_K;
           tma_load_3d(sa, &map_a, full_bar(stage), k0, m0, bz, hint);  // box {128 k bytes, 128 m}
           tma_load_3d(sb, &map_b, full_bar(stage), k0, n0, bz, hint);  // box {128 k bytes, BN n}
+          if constexpr (MX) {
+            bulk_load(sb + C::B_STAGE_BYTES, p.sfa + ((int64_t)mb * num_kb + kb) * SF_BLOCK_BYTES, SF_BLOCK_BYTES, full_bar(stage));
+#pragma unroll
+            for (int h = 0; h < BN / 128; ++h)
+              bulk_load(sb + C::B_STAGE_BYTES + (1 + h) * SF_BLOCK_BYTES, p.sfb + ((int64_t)(nb * (BN / 128) + h) * num_kb + kb) * SF_BLOCK_BYTES, SF_BLOCK_BYTES, full_bar(stage));
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -241,22 +292,33 @@ gemm_fp8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
+      const uint64_t desc_a0 = make_smem_desc(smem_base, 16, 1024), desc_b0 = make_smem_desc(smem_base + A_STAGE_BYTES, 16, 1024);
+      const uint64_t desc_sf0 = make_sf_desc(smem_base + A_STAGE_BYTES + C::B_STAGE_BYTES);
+      (void)desc_sf0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-        const int as = local & 1;
-        const uint32_t aphase = (local >> 1) & 1;
+        const int as = local % C::ACC;
+        const uint32_t aphase = (local / C::ACC) & 1;
         mbar_wait(tempty_bar(as), aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          // descriptors are built once (desc_a0 / desc_b0 / desc_sf0 below the loop head) and advanced by adding to the address field
+          const uint64_t soff = (uint64_t)((stage * C::STAGE_BYTES) >> 4);
+          uint32_t tsfa = 0, tsfb = 0;
+          if constexpr (MX) {      // scale bytes smem -> TMEM; tcgen05.cp and tcgen05.mma execute in issue order
+            tsfa = tmem_base + C::SF_COL0 + stage * C::SF_STAGE_COLS;
+            tsfb = tsfa + 4;
+            tmem_cp_sf(tsfa, desc_sf0 + soff);
+#pragma unroll
+            for (int h = 0; h < BN / 128; ++h) tmem_cp_sf(tsfb + 4 * h, desc_sf0 + soff + (uint64_t)(((1 + h) * SF_BLOCK_BYTES) >> 4));
+          }
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t adesc = make_smem_desc(sa + k * 32, 16, 1024);   // K-major: 32 fp8 elements = 32 B per step
-            const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, 1024);
-            umma_f8(tmem_d, adesc, bdesc, p.idesc, (kb | k) != 0);
+            const uint64_t adesc = desc_a0 + soff + 2 * k, bdesc = desc_b0 + soff + 2 * k;   // K-major: 32 fp8 elements = 32 B per step
+            if constexpr (MX) umma_mxf8(tmem_d, adesc, bdesc, p.idesc | ((uint32_t)k << 29) | ((uint32_t)k << 4), tsfa, tsfb, (kb | k) != 0);   // a_sf_id, b_sf_id = k-block
+            else umma_f8(tmem_d, adesc, bdesc, p.idesc, (kb | k) != 0);
           }
           umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -271,8 +333,8 @@ gemm_fp8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       int bz, mb, nb;
       tile_coords(tile, bz, mb, nb);
-      const int as = local & 1;
-      const uint32_t aphase = (local >> 1) & 1;
+      const int as = local % C::ACC;
+      const uint32_t aphase = (local / C::ACC) & 1;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const int row = mb * BLOCK_M + ew * 32 + lane;
@@ -376,9 +438,21 @@ static uint32_t make_idesc(int a_e5m2, int b_e5m2, int bn) {
   return d;
 }
 
-template <int BN>
+// block-scaled descriptor (cute::UMMA::InstrDescriptorBlockScaled): no c_format (always fp32); bits [4,6) b_sf_id, 23 scale format
+// (1 = E8M0), [29,31) a_sf_id - the two ids are OR-ed in per MMA
+static uint32_t make_idesc_mx(int a_e5m2, int b_e5m2, int bn) {
+  uint32_t d = 0;
+  d |= (a_e5m2 ? 1u : 0u) << 7;
+  d |= (b_e5m2 ? 1u : 0u) << 10;
+  d |= (uint32_t)(bn >> 3) << 17;
+  d |= 1u << 23;
+  d |= (uint32_t)(BLOCK_M >> 4) << 24;
+  return d;
+}
+
+template <int BN, bool MX>
 static int launch(const GemmFp8Args& g, cudaStream_t s) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, MX>;
   CUtensorMap ma, mb;
   const uint64_t batch = g.batch > 1 ? g.batch : 1;
   if (!make_map8(&ma, g.a, g.k, g.m, batch, g.lda, g.stride_a, BLOCK_M)) return 2;
@@ -392,9 +466,10 @@ static int launch(const GemmFp8Args& g, cudaStream_t s) {
   p.accumulate = 0;
   p.scale = g.scale;
   p.scale_a = g.scale_a_dev; p.scale_b = g.scale_b_dev;
-  p.idesc = make_idesc(g.a_e5m2, g.b_e5m2, BN);
+  p.sfa = g.sfa; p.sfb = g.sfb;
+  p.idesc = MX ? make_idesc_mx(g.a_e5m2, g.b_e5m2, BN) : make_idesc(g.a_e5m2, g.b_e5m2, BN);
   static bool attr_set = false;
-  auto kern = gemm_fp8_kernel<BN>;
+  auto kern = gemm_fp8_kernel<BN, MX>;
   if (!attr_set) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
@@ -412,8 +487,14 @@ static int launch(const GemmFp8Args& g, cudaStream_t s) {
 int gemm_fp8_tcgen05(const GemmFp8Args& g, cudaStream_t s) {
   if (g.m <= 0 || g.n <= 0 || g.k <= 0 || g.k % 16 || g.lda % 16 || g.ldb % 16) return 1;   // TMA strides: multiples of 16 bytes
   if ((reinterpret_cast<uintptr_t>(g.a) | reinterpret_cast<uintptr_t>(g.b)) & 15) return 1;
-  if (g.n <= 128) return gemm8::launch<128>(g, s);
-  return gemm8::launch<256>(g, s);
+  if (g.sfa || g.sfb) {
+    // MX: whole 128 x 128 x 128 scale blocks only
+    if (!g.sfa || !g.sfb || g.m % 128 || g.n % 128 || g.k % 128 || g.batch > 1) return 1;
+    if ((reinterpret_cast<uintptr_t>(g.sfa) | reinterpret_cast<uintptr_t>(g.sfb)) & 15) return 1;
+    return g.n % 256 == 0 ? gemm8::launch<256, true>(g, s) : gemm8::launch<128, true>(g, s);
+  }
+  if (g.n <= 128) return gemm8::launch<128, false>(g, s);
+  return gemm8::launch<256, false>(g, s);
 }
 
 }  // namespace b200

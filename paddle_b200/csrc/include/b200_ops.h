@@ -147,12 +147,18 @@ struct GemmFp8Args {
   float scale;
   const float* scale_a_dev = nullptr;   // device scalars multiplied into the dequantisation scale (quantize_fp8 outputs)
   const float* scale_b_dev = nullptr;
+  const uint8_t* sfa = nullptr;         // MX block scaling: E8M0 scale blocks of A / B (mx_quantize layout); both or neither
+  const uint8_t* sfb = nullptr;
   int act;          // 0 none, 1 gelu, 2 relu
   int out_dtype;
   int batch;
   int64_t stride_a, stride_b, stride_d;
 };
 int gemm_fp8_tcgen05(const GemmFp8Args& g, cudaStream_t s);
+// OCP MX quantisation of a contiguous [rows, k] tensor along k: q = e4m3(x / 2^e), one E8M0 byte (e + 127) per 32 elements, written in
+// the 512-byte block layout [rows / 128][k / 128][(row % 32) * 16 + ((row % 128) / 32) * 4 + (k / 32) % 4] the block-scaled MMA consumes.
+int mx_quantize(const void* x, int64_t rows, int64_t k, int dtype, void* q, uint8_t* sf, cudaStream_t s);
+int mx_dequantize(const void* q, const uint8_t* sf, int64_t rows, int64_t k, float* out, cudaStream_t s);
 // ---- quant_fp8.cu: fused per-tensor fp8 quantisation ----------------------------------------------------------
 // amax[0] = max(amax[0], max |x|)  (amax is a device float, zero it first)
 void fp8_amax(const void* x, int64_t n, int dtype, float* amax, cudaStream_t s);

@@ -87,4 +87,89 @@ void fp8_cast_transpose(const void* x, int64_t m, int64_t k, int dtype, const fl
   B200_CUDA_CHECK(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------- MX (block-scaled) quantisation
+// One thread = one block of 32 consecutive k of one row: amax, power-of-two scale (rounded UP so that nothing saturates: 2^e >=
+// amax / 448), 32 e4m3 bytes, one E8M0 byte.  Neighbouring threads take neighbouring blocks of the same row: 64-byte loads coalesce.
+__device__ __forceinline__ int64_t mx_sf_offset(int64_t row, int64_t kb32, int64_t k_tiles) {
+  const int64_t mt = row >> 7, r = row & 127;
+  return ((mt * k_tiles + (kb32 >> 2)) << 9) + (r & 31) * 16 + (r >> 5) * 4 + (kb32 & 3);
+}
+
+template <typename T>
+__global__ void mx_quantize_kernel(const T* __restrict__ x, int64_t rows, int64_t K, uint8_t* __restrict__ q, uint8_t* __restrict__ sf) {
+  const int64_t nblk = K >> 5;
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= rows * nblk) return;
+  const int64_t row = idx / nblk, kb = idx - row * nblk;
+  const T* src = x + row * K + kb * 32;
+  float v[32];
+  if constexpr (sizeof(T) == 2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const Vec16<T> t = ld16(src + i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i * 8 + j] = to_f(t.v[j]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = to_f(src[i]);
+  }
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(v[i]));
+  int e = -127;
+  if (amax > 0.f && isfinite(amax)) {
+    int ex;
+    const float m = frexpf(amax * (1.f / 448.f), &ex);      // amax / 448 = m 2^ex, m in [0.5, 1): ceil(log2) = ex, or ex - 1 when m == 0.5
+    e = (m == 0.5f) ? ex - 1 : ex;
+    e = max(-127, min(127, e));
+  }
+  const float inv = exp2f((float)-e);                          // exact power of two
+  uint8_t o[32];
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const __nv_fp8x2_storage_t pr = __nv_cvt_float2_to_fp8x2(make_float2(v[i] * inv, v[i + 1] * inv), __NV_SATFINITE, __NV_E4M3);
+    o[i] = (uint8_t)(pr & 0xFF);
+    o[i + 1] = (uint8_t)(pr >> 8);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(q + row * K + kb * 32);
+  dst[0] = *reinterpret_cast<const uint4*>(o);
+  dst[1] = *reinterpret_cast<const uint4*>(o + 16);
+  sf[mx_sf_offset(row, kb, K >> 7)] = (uint8_t)(e + 127);
+}
+
+int mx_quantize(const void* x, int64_t rows, int64_t k, int dtype, void* q, uint8_t* sf, cudaStream_t s) {
+  if (rows <= 0 || k <= 0 || rows % 128 || k % 128) return 1;
+  const int64_t total = rows * (k / 32);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  B200_DISPATCH_DTYPE(dtype, T, { mx_quantize_kernel<T><<<blocks, 256, 0, s>>>((const T*)x, rows, k, (uint8_t*)q, sf); });
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return 3; }
+  return 0;
+}
+
+__global__ void mx_dequantize_kernel(const uint8_t* __restrict__ q, const uint8_t* __restrict__ sf, int64_t rows, int64_t K, float* __restrict__ out) {
+  const int64_t nblk = K >> 5;
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= rows * nblk) return;
+  const int64_t row = idx / nblk, kb = idx - row * nblk;
+  const float sc = exp2f((float)((int)sf[mx_sf_offset(row, kb, K >> 7)] - 127));
+  const uint8_t* src = q + row * K + kb * 32;
+  float* dst = out + row * K + kb * 32;
+#pragma unroll 8
+  for (int i = 0; i < 32; ++i) {
+    const __half_raw h = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)src[i], __NV_E4M3);
+    dst[i] = __half2float(*reinterpret_cast<const __half*>(&h)) * sc;
+  }
+}
+
+int mx_dequantize(const void* q, const uint8_t* sf, int64_t rows, int64_t k, float* out, cudaStream_t s) {
+  if (rows <= 0 || k <= 0 || rows % 128 || k % 128) return 1;
+  const int64_t total = rows * (k / 32);
+  mx_dequantize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const uint8_t*)q, sf, rows, k, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return 3; }
+  return 0;
+}
+
 }  // namespace b200

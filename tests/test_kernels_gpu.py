@@ -657,3 +657,63 @@ def test_weight_only_linear_dequant_in_sm(wdt, m, dtype, k):
     wd = Q.weight_dequantize(wq, sc, algo=f"weight_only_{wdt}", out_dtype="float32").as_subclass(torch.Tensor)
     ref = x.float() @ wd.float() + bias.float()
     assert rel_err(y.as_subclass(torch.Tensor), ref) < 1e-2, rel_err(y.as_subclass(torch.Tensor), ref)
+
+
+def test_mx_quantize_matches_reference():
+    """csrc/quant_fp8.cu mx_quantize: e4m3 values and E8M0 block scales equal the PyTorch reference (ceil-rounded power-of-two scale), and
+    the 512-byte block layout round-trips through dequantize_mx."""
+    from paddle_b200.kernels import gemm_fp8 as G
+
+    torch.manual_seed(2)
+    x = (torch.randn(256, 384, device="cuda") * torch.logspace(-3, 2, 384, device="cuda")).to(torch.bfloat16)
+    x[5, 32:64] = 0
+    q, sf = G.quantize_mx(x)
+    # reference on the CPU path of the same function
+    qr, sfr = G.quantize_mx(x.cpu())
+    assert torch.equal(sf.cpu(), sfr)
+    assert torch.equal(q.cpu().view(torch.uint8), qr.view(torch.uint8))
+    d = G.dequantize_mx(q, sf)
+    dr = G.dequantize_mx(qr, sfr)
+    assert torch.equal(d.cpu(), dr)
+    assert rel_err(d, x.float()) < 4e-2
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 128), (256, 384, 512), (384, 1024, 256), (256, 512, 1024)])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_mx_block_scaled_gemm(shape, out_dtype):
+    """tcgen05.mma.kind::mxf8f6f4.block_scale (csrc/gemm_fp8_sm100.cu, MX): the result equals the fp32 matmul of the DEQUANTISED operands,
+    with scales that differ per row and per k-block (a wrong scale slot or byte shows up as an O(1) error)."""
+    from paddle_b200.kernels import gemm_fp8 as G
+
+    m, n, k = shape
+    torch.manual_seed(7)
+    a = torch.randn(m, k, device="cuda") * torch.exp2(torch.randint(-6, 7, (m, k // 32), device="cuda").float()).repeat_interleave(32, 1)
+    b = torch.randn(n, k, device="cuda") * torch.exp2(torch.randint(-6, 7, (n, k // 32), device="cuda").float()).repeat_interleave(32, 1)
+    aq, sa = G.quantize_mx(a.to(torch.bfloat16))
+    bq, sb = G.quantize_mx(b.to(torch.bfloat16))
+    bias = torch.randn(n, device="cuda").to(out_dtype)
+    kernels.reset_launch_count()
+    y = G.mx_gemm(aq, sa, bq, sb, bias, out_dtype)
+    assert kernels.launch_count() == 1
+    ref = G.dequantize_mx(aq, sa) @ G.dequantize_mx(bq, sb).t() + bias.float()
+    tol = 1e-2 if out_dtype == torch.bfloat16 else 1e-5
+    assert rel_err(y, ref) < tol, rel_err(y, ref)
+
+
+def test_mx_fp8_linear_grads():
+    """MX block-scaled Linear (three block_scale GEMMs, each quantised along its own contraction axis) vs the fp32 Linear."""
+    from paddle_b200.kernels import gemm_fp8 as G
+
+    torch.manual_seed(3)
+    x = (torch.randn(256, 512, device="cuda") * 0.5).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(512, 384, device="cuda") * 0.05).to(torch.bfloat16).requires_grad_(True)
+    b = torch.zeros(384, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    y = G.mx_fp8_linear(x, w, b).as_subclass(torch.Tensor)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    yr = xr @ wr
+    yr.backward(g.float())
+    assert rel_err(y, yr) < 5e-2
+    assert rel_err(x.grad, xr.grad) < 5e-2
+    assert rel_err(w.grad, wr.grad) < 5e-2
