@@ -20,9 +20,11 @@
 
 #include "include/b200_common.cuh"
 #include "include/b200_ops.h"
+#include "include/b200_ptx.cuh"
 
 namespace b200 {
 namespace attn_bwd {
+using namespace ptx;
 
 constexpr int BM = 128, BN = 128, HD = 128;
 constexpr int kThreads = 320;   // warps 0-7: softmax / dQ / epilogue (2 warpgroups), warp 8: TMA producer, warp 9: TMEM alloc + MMA issuer
@@ -32,92 +34,12 @@ constexpr uint32_t SMEM_BYTES = 6 * TILE_BYTES + 1024 + 256;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 384;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint64_t gtimer() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  uint64_t t0 = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) break;
-    if (++spins == 2048) t0 = gtimer();
-    if (spins > 2048 && (spins & 1023) == 0 && gtimer() - t0 > 4000000000ull) {
-      printf("b200 attention bwd: mbarrier timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 // Operand descriptors for one 128x128 bf16 tile stored as two 64-wide halves [half][row 0..127][128 B swizzled]:
 //   K-major use   (rows = M or N index, inner = K):   K step k (16 elems) inside half kb -> +kb*HALF + k*32,  LBO 16, SBO 1024
 //   MN-major use  (rows = K index, inner = M or N):   K step k (16 rows)                 -> +k*2048,         LBO HALF (next 64 M/N), SBO 1024
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kb, int k) { return make_desc(tile + kb * HALF_BYTES + k * 32, 16, 1024); }
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kk) { return make_desc(tile + kk * 2048, HALF_BYTES, 1024); }
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kb, int k) { return make_smem_desc(tile + kb * HALF_BYTES + k * 32, 16, 1024); }
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kk) { return make_smem_desc(tile + kk * 2048, HALF_BYTES, 1024); }
 
 template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
 template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
@@ -267,8 +189,8 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t rs[32], rp[32];
-        tmem_ld32(tmem_base + lane_off + S_COL + half * 64 + c * 32, rs);
-        tmem_ld32(tmem_base + lane_off + DP_COL + half * 64 + c * 32, rp);
+        tmem_ld_32x32(tmem_base + lane_off + S_COL + half * 64 + c * 32, rs);
+        tmem_ld_32x32(tmem_base + lane_off + DP_COL + half * 64 + c * 32, rp);
 #pragma unroll
         for (int q8 = 0; q8 < 4; ++q8) {
           uint32_t up[4], ud[4];
@@ -312,7 +234,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + lane_off + S_COL + half * 64 + c * 32, r);
+        tmem_ld_32x32(tmem_base + lane_off + S_COL + half * 64 + c * 32, r);
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(sDQ + (uint32_t)(half * 64 + c * 32 + i) * 512u + (uint32_t)rl * 4u), "r"(r[i]) : "memory");
@@ -342,8 +264,8 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     for (int c = 0; c < 2; ++c) {
       uint32_t rv[32], rk[32];
       if (total > 0) {
-        tmem_ld32(tmem_base + lane_off + DV_COL + half * 64 + c * 32, rv);
-        tmem_ld32(tmem_base + lane_off + DK_COL + half * 64 + c * 32, rk);
+        tmem_ld_32x32(tmem_base + lane_off + DV_COL + half * 64 + c * 32, rv);
+        tmem_ld_32x32(tmem_base + lane_off + DK_COL + half * 64 + c * 32, rk);
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) { rv[i] = 0u; rk[i] = 0u; }

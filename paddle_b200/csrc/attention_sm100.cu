@@ -21,9 +21,11 @@
 
 #include "include/b200_common.cuh"
 #include "include/b200_ops.h"
+#include "include/b200_ptx.cuh"
 
 namespace b200 {
 namespace attn {
+using namespace ptx;
 
 constexpr int BM = 128, BN = 128, HD = 128;
 constexpr int kThreads = 352;   // warps 0-7: softmax (2 warpgroups = 2 streams), warp 8: TMA producer, warp 9: TMEM alloc + QK issuer, warp 10: PV issuer
@@ -33,99 +35,7 @@ constexpr uint32_t SMEM_BYTES = 7 * TILE_BYTES + 1024 /*align*/ + 256 /*barriers
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t O_COL = 256;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint64_t gtimer() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  uint64_t t0 = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) break;
-    if (++spins == 2048) t0 = gtimer();
-    if (spins > 2048 && (spins & 1023) == 0 && gtimer() - t0 > 4000000000ull) {  // protocol bug: trap, never hang the GPU
-      printf("b200 attention: mbarrier timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {   // SWIZZLE_128B smem descriptor
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n\t"
-      "tcgen05.wait::st.sync.aligned;"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
 template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
@@ -234,7 +144,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     if (lane == 0 && n_tiles > 0) {
       // ================= S = Q K^T issuer.  Descriptors are built once; a k-step only adds to the 14-bit (address >> 4) field =========
       mbar_wait(q_full, 0);
-      const uint64_t qd = make_desc(sQ, 16, 1024), kd0 = make_desc(sK(0), 16, 1024);
+      const uint64_t qd = make_smem_desc(sQ, 16, 1024), kd0 = make_smem_desc(sK(0), 16, 1024);
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j & 1, ph = (j >> 1) & 1;              // K stage and stream share the parity of j
         mbar_wait(k_full(s), ph);
@@ -253,7 +163,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   } else if (warp == 10) {
     if (lane == 0 && n_tiles > 0) {
       // ================= O_stream += P V issuer =================
-      const uint64_t pd0 = make_desc(sP(0), 16, 1024), vd0 = make_desc(sV(0), 8192, 1024);
+      const uint64_t pd0 = make_smem_desc(sP(0), 16, 1024), vd0 = make_smem_desc(sV(0), 8192, 1024);
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j & 1, ph = (j >> 1) & 1;
         mbar_wait(p_full(s), ph);
@@ -289,7 +199,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
-        tmem_ld32(tS + c * 32, r);
+        tmem_ld_32x32(tS + c * 32, r);
 #pragma unroll
         for (int i = 0; i < 32; ++i) sv[c * 32 + i] = __uint_as_float(r[i]);   // raw logits; the softmax scale is folded into the exp2 FFMA
       }
@@ -333,7 +243,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
             uint32_t r[32];
-            tmem_ld32(tO + c * 32, r);
+            tmem_ld_32x32(tO + c * 32, r);
 #pragma unroll
             for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
             tmem_st32(tO + c * 32, r);
@@ -399,13 +309,13 @@ fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       for (int i = 0; i < 32; ++i) acc[i] = 0.f;
       if (any_me) {
         uint32_t r[32];
-        tmem_ld32(tO_me + c * 32, r);
+        tmem_ld_32x32(tO_me + c * 32, r);
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = c_me != 0.f ? __uint_as_float(r[i]) * c_me : 0.f;
       }
       if (any_x) {
         uint32_t r[32];
-        tmem_ld32(tO_x + c * 32, r);
+        tmem_ld_32x32(tO_x + c * 32, r);
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] += c_x != 0.f ? __uint_as_float(r[i]) * c_x : 0.f;
       }
