@@ -8,6 +8,7 @@ void bind(pybind11::module_& m) {
   bind_graph(m);
   bind_tracer(m);
   bind_data_feed(m);
+  bind_ir(m);
 }
 }  // namespace runtime
 }  // namespace b200

@@ -353,6 +353,10 @@ class Executor:
             program = program._program
         if not program.nodes and not fetch_list:
             return []   # startup program: parameters are initialised at creation time
+        from ..framework.flags import flag
+
+        if flag("FLAGS_enable_pir_api", False) and program.nodes and not program.__dict__.get("_pir_report"):
+            program = self._pir_optimized(program, fetch_list)
         feed = feed or {}
         env = {}
         dev = None
@@ -405,6 +409,23 @@ class Executor:
             v = env[vid]
             outs.append(v.detach().cpu().as_subclass(Tensor).numpy() if return_numpy else v)
         return outs
+
+    @staticmethod
+    def _pir_optimized(program, fetch_list):
+        """FLAGS_enable_pir_api: the program runs through the native IR pass pipeline (paddle_b200.pir: DCE / CSE / identity removal / constant
+        folding / fusion patterns) once per fetch set; the lowered program is cached on the source program."""
+        from .. import pir
+
+        if not pir.core_available() or any(n.kind != "op" for n in program.nodes):
+            return program          # programs with training / control nodes keep their recorded form
+        key = tuple(f if isinstance(f, str) else id(f) for f in (fetch_list or []))
+        cache = program.__dict__.setdefault("_pir_cache", {})
+        if key not in cache or cache[key][0] != len(program.nodes):
+            try:
+                cache[key] = (len(program.nodes), pir.optimize(program, fetch_list=fetch_list))
+            except Exception:  # noqa: BLE001  (an op the translator cannot encode: run as recorded)
+                cache[key] = (len(program.nodes), program)
+        return cache[key][1]
 
     def train_from_dataset(self, program=None, dataset=None, scope=None, thread=0, debug=False, fetch_list=None, fetch_info=None, print_period=100,
                            fetch_handler=None):
