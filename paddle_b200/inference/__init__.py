@@ -127,10 +127,38 @@ class Config:
     def summary(self):
         return f"Config(prefix={self._prefix}, gpu={self._use_gpu}, precision={self._precision.name})"
 
-    # ---- optimisation pipeline switches.  The reference drives an IR pass list + TensorRT / oneDNN sub-graph engines; here the saved
-    # model runs through the hand-written kernels and CUDA-graph replay, so these calls record the request (visible in `summary()` /
-    # `pass_builder().all_passes()`), and the ones that map to something real act on it (precision, cuda graph, memory pool, streams).
-    _PASSES = ["constant_folding", "common_subexpression_elimination", "fuse_gemm_epilogue", "dead_code_elimination"]
+    # ---- optimisation pipeline.  Parity: the analysis predictor's IR pass list (paddle/fluid/inference/api/paddle_pass_builder.cc).  For a
+    # saved PROGRAM artifact (static.save_inference_model / a traced program) the pass names map onto the native IR passes of
+    # paddle_b200.pir and are really run when the predictor is created (switch_ir_optim(False) or an empty list skips them); a pickled
+    # Layer artifact executes through the hand-written kernels directly and the list is only recorded.
+    _PASSES = ["identity_op_clean_pass", "common_subexpression_elimination_pass", "constant_folding_pass", "dead_code_elimination_pass", "fuse_gemm_epilogue_pass",
+               "fused_swiglu_pass", "add_norm_fuse_pass", "inplace_pass"]
+    _PASS_TO_PIR = {
+        "identity_op_clean_pass": ["identity_elim"], "common_subexpression_elimination_pass": ["cse"], "constant_folding_pass": ["constant_fold"],
+        "dead_code_elimination_pass": ["dce"], "fuse_gemm_epilogue_pass": ["fuse_matmul_add", "fuse_linear_act_gelu", "fuse_linear_act_relu"],
+        "matmul_add_act_fuse_pass": ["fuse_matmul_add", "fuse_linear_act_gelu", "fuse_linear_act_relu"], "fused_swiglu_pass": ["fuse_swiglu"],
+        "add_norm_fuse_pass": ["fuse_add_rms_norm"], "inplace_pass": ["inplace"],
+        # the short names the round-1 list used
+        "constant_folding": ["constant_fold"], "common_subexpression_elimination": ["cse"], "fuse_gemm_epilogue": ["fuse_matmul_add", "fuse_linear_act_gelu", "fuse_linear_act_relu"],
+        "dead_code_elimination": ["dce"],
+    }
+
+    def _pir_passes(self):
+        """The configured pass list as native pass names (dead code is swept before and after the fusions)."""
+        if not getattr(self, "_ir_optim", True):
+            return []
+        out = []
+        for name in self._opt()["passes"]:
+            for p in self._PASS_TO_PIR.get(name, [name] if name in ("dce", "cse", "identity_elim", "constant_fold", "inplace") else []):
+                if p not in out or p == "dce":
+                    out.append(p)
+        if out and "dce" in out:
+            first_fuse = next((i for i, p in enumerate(out) if p.startswith("fuse_")), None)
+            if first_fuse is not None and "dce" not in out[:first_fuse]:
+                out.insert(first_fuse, "dce")
+            if not out[-1] in ("dce", "inplace"):
+                out.append("dce")
+        return out
 
     def _opt(self):
         return self.__dict__.setdefault("_options", {"passes": list(self._PASSES)})
@@ -373,6 +401,32 @@ class Predictor:
             if config._precision in (PrecisionType.Half, PrecisionType.Bfloat16) and hasattr(self._layer, "_inner"):
                 self._layer._inner._cast_floating(torch.float16 if config._precision == PrecisionType.Half else torch.bfloat16)
         self._dev = torch.device("cuda", config._gpu_id) if (config._use_gpu and torch.cuda.is_available()) else torch.device("cpu")
+        self._ir_report = self._run_ir_passes()
+
+    def _run_ir_passes(self):
+        """Program artifacts go through the configured IR passes once, here (paddle_b200.pir); returns the per-pass report."""
+        blob = getattr(self._layer, "_blob", None)
+        passes = self._config._pir_passes()
+        if blob is None or not passes:
+            return []
+        from .. import pir
+
+        prog = blob["program"]
+        if not pir.core_available() or any(n.kind != "op" for n in prog.nodes):
+            return []
+        try:
+            opt, report = pir.optimize(prog, fetch_list=list(self._layer._fetch), passes=passes, return_report=True)
+        except Exception:  # noqa: BLE001  (an op the translator cannot encode: run the program as saved)
+            return []
+        if self._config._opt().get("ir_debug"):
+            for r in report:
+                print(f"[ir pass] {r['pass']}: {r['ops_before']} -> {r['ops_after']} ops ({r['changed']} rewrites)")
+        blob["program"] = opt
+        return report
+
+    def ir_pass_report(self):
+        """[{pass, ops_before, ops_after, changed}] of the IR passes that ran when this predictor was built."""
+        return list(self._ir_report)
 
     def get_input_names(self):
         return list(self._inputs)

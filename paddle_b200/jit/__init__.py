@@ -324,7 +324,13 @@ def load(path, **configs):
     if spec.get("pickled_layer"):
         layer = pickle.loads(spec["pickled_layer"])
     elif spec.get("program"):
-        layer = _ProgramLayer(pickle.loads(spec["program"]))
+        blob = spec["program"]
+        if isinstance(blob, (bytes, bytearray)):         # jit.save of a traced layer: the blob travels pickled inside the spec
+            blob = pickle.loads(blob)
+        else:                                            # static.save_inference_model: the .pdmodel IS the blob
+            blob = dict(spec)
+            blob.setdefault("single", len(blob.get("fetch_vids", [])) == 1)
+        layer = _ProgramLayer(blob)
         layer.eval()
         return layer
     else:

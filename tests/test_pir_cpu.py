@@ -234,3 +234,40 @@ def test_executor_runs_through_pir_when_flag_is_set():
         np.testing.assert_allclose(again, ref, rtol=1e-5, atol=1e-5)
     finally:
         paddle.disable_static()
+
+
+def test_inference_predictor_runs_ir_passes_on_program_artifacts(tmp_path):
+    """Config.pass_builder() names map onto the native IR passes and are really applied to a saved program (fewer ops, same output);
+    switch_ir_optim(False) leaves the program as saved."""
+    from paddle_b200 import inference, static
+
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            x = static.data("x", [2, 4], "float32")
+            w = paddle.to_tensor(np.random.RandomState(0).randn(4, 6).astype("float32"))
+            b = paddle.to_tensor(np.random.RandomState(1).randn(6).astype("float32"))
+            h = paddle.add(paddle.matmul(x, w), b)
+            h2 = paddle.add(paddle.matmul(x, w), b)
+            y = paddle.nn.functional.gelu(h) + paddle.reshape(h2, [2, 6])
+        exe = static.Executor()
+        static.save_inference_model(str(tmp_path / "m"), [x], [y], exe, program=main)
+    finally:
+        paddle.disable_static()
+    data = np.random.RandomState(2).randn(2, 4).astype("float32")
+    cfg0 = inference.Config(str(tmp_path / "m.pdmodel"), str(tmp_path / "m.pdiparams"))
+    cfg0.switch_ir_optim(False)
+    p0 = inference.create_predictor(cfg0)
+    assert p0.ir_pass_report() == []
+    ref = p0.run([data])[0]
+    n_saved = len(p0._layer._blob["program"].nodes)
+    cfg = inference.Config(str(tmp_path / "m.pdmodel"), str(tmp_path / "m.pdiparams"))
+    assert "fuse_gemm_epilogue_pass" in cfg.pass_builder().all_passes()
+    cfg.pass_builder().delete_pass("inplace_pass")
+    p1 = inference.create_predictor(cfg)
+    rep = p1.ir_pass_report()
+    assert rep and {r["pass"] for r in rep} >= {"cse", "dce", "fuse_matmul_add"} and "inplace" not in {r["pass"] for r in rep}
+    assert len(p1._layer._blob["program"].nodes) < n_saved
+    got = p1.run([data])[0]
+    np.testing.assert_allclose(np.asarray(got), np.asarray(ref), rtol=1e-5, atol=1e-5)
