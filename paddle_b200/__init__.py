@@ -86,4 +86,11 @@ def install_as_paddle():
 
 
 from . import _compat_paths as _compat_paths  # noqa: E402
+
+from .framework import flags as _flags_mod  # noqa: E402
+
+if _flags_mod.flag("FLAGS_b200_native_allocator", False):      # before anything touches the GPU
+    from .device.cuda import use_auto_growth_allocator as _use_native_allocator
+
+    _use_native_allocator()
 _compat_paths.install()

@@ -9,6 +9,7 @@ void bind(pybind11::module_& m) {
   bind_tracer(m);
   bind_data_feed(m);
   bind_ir(m);
+  bind_allocator(m);
 }
 }  // namespace runtime
 }  // namespace b200

@@ -23,6 +23,7 @@ _FLAGS = {
     "FLAGS_eager_delete_tensor_gb": 0.0,
     "FLAGS_fraction_of_gpu_memory_to_use": 0.92,
     "FLAGS_allocator_strategy": "auto_growth",
+    "FLAGS_b200_native_allocator": False,   # environment, at import: all CUDA memory through csrc/runtime/allocator.cpp instead of the torch caching allocator
     "FLAGS_enable_async_trace": False,
     "FLAGS_sync_nccl_allreduce": False,
     "FLAGS_max_inplace_grad_add": 0,

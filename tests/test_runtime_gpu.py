@@ -154,3 +154,43 @@ def test_to_static_captures_training_forward_backward():
             np.testing.assert_allclose(p.grad.numpy(), q.grad.numpy(), rtol=2e-4, atol=1e-6)
     graphs = [v for v in snet.forward._train_graphs.values()]
     assert graphs and graphs[0] is not None, "training call was not captured"
+
+
+@pytest.mark.gpu
+def test_native_auto_growth_allocator_serves_all_cuda_memory():
+    """FLAGS_b200_native_allocator=1: torch's allocations go through csrc/runtime/allocator.cpp (CUDAPluggableAllocator); a small training
+    loop runs, the statistics move, cross-stream frees are deferred, empty_cache returns idle chunks to cudaFree."""
+    import os
+    import subprocess
+    import sys
+
+    code = r"""
+import torch, paddle_b200 as paddle
+from paddle_b200.device import cuda as C
+assert C.auto_growth_allocator_active()
+x = torch.randn(1024, 1024, device="cuda")
+s0 = C.allocator_stats()
+assert s0["allocated"] >= x.numel() * 4 and s0["num_chunks"] >= 1 and C.memory_allocated() == s0["allocated"]
+lin = paddle.nn.Linear(1024, 1024).to("cuda")
+opt = paddle.optimizer.AdamW(learning_rate=1e-3, parameters=lin.parameters())
+for _ in range(5):
+    loss = (lin(x.as_subclass(paddle.Tensor)) ** 2).mean()
+    loss.backward(); opt.step(); opt.clear_grad()
+side = torch.cuda.Stream()
+with torch.cuda.stream(side):
+    y = torch.empty(1 << 20, device="cuda")
+    y.fill_(1.0)
+del y                                             # freed on the default stream, allocated on `side`
+torch.cuda.synchronize()
+s1 = C.allocator_stats()
+assert s1["num_allocs"] > s0["num_allocs"] and s1["allocated_peak"] >= s1["allocated"] and s1["reserved"] >= s1["allocated"]
+peak = C.max_memory_allocated()
+del x, lin, opt, loss
+C.empty_cache()
+s2 = C.allocator_stats()
+assert s2["reserved"] <= s1["reserved"] and s2["num_backend_frees"] >= 1
+print("OK", s1["num_allocs"], s1["num_chunks"], s1["deferred_frees"], peak, s2["reserved"])
+"""
+    env = dict(os.environ, FLAGS_b200_native_allocator="1", B200_ALLOCATOR_CHUNK_MB="64")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
