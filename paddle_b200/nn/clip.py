@@ -6,6 +6,15 @@ import torch
 from ..tensor import Tensor
 
 
+def _is_rows(g):
+    return type(g).__name__ == "SelectedRows"
+
+
+def _sq(g):
+    """sum of squares of a gradient; SelectedRows: of its MERGED rows (python/paddle/nn/clip.py merge_selected_rows + get_tensor_from_selected_rows)."""
+    return g.squared_l2_norm() if _is_rows(g) else g.as_subclass(torch.Tensor).float().pow(2).sum()
+
+
 class ClipGradBase:
     def __call__(self, params_grads):
         return self._dygraph_clip(params_grads)
@@ -22,7 +31,7 @@ class ClipGradByValue(ClipGradBase):
             if g is None or not getattr(p, "need_clip", True):
                 out.append((p, g))
             else:
-                out.append((p, torch.clamp(g, self.min, self.max)))
+                out.append((p, type(g)(g.rows, torch.clamp(g.merge().value, self.min, self.max), g.height) if _is_rows(g) else torch.clamp(g, self.min, self.max)))
         return out
 
 
@@ -35,6 +44,10 @@ class ClipGradByNorm(ClipGradBase):
         for p, g in params_grads:
             if g is None or not getattr(p, "need_clip", True):
                 out.append((p, g))
+                continue
+            if _is_rows(g):
+                g = g.merge()
+                out.append((p, g.scale(float(self.clip_norm / max(float(torch.sqrt(_sq(g))), self.clip_norm)))))
                 continue
             n = torch.linalg.vector_norm(g.float())
             out.append((p, (g.float() * (self.clip_norm / torch.clamp(n, min=self.clip_norm))).to(g.dtype)))
@@ -51,8 +64,8 @@ class ClipGradByGlobalNorm(ClipGradBase):
         for p, g in params_grads:
             if g is None or not getattr(p, "need_clip", True):
                 continue
-            s = g.as_subclass(torch.Tensor).float().pow(2).sum()
-            sq = s if sq is None else sq + s
+            s = _sq(g)
+            sq = s if sq is None else sq + s.to(sq.device)
         return sq
 
     def _dygraph_clip(self, params_grads):
@@ -66,7 +79,7 @@ class ClipGradByGlobalNorm(ClipGradBase):
             if g is None or not getattr(p, "need_clip", True):
                 out.append((p, g))
             else:
-                out.append((p, (g * coef.to(g.dtype))))
+                out.append((p, g.scale(coef.to(g.value.dtype).to(g.value.device)) if _is_rows(g) else (g * coef.to(g.dtype))))
         return out
 
 

@@ -40,6 +40,7 @@ class Embedding(Layer):
         self._num_embeddings, self._embedding_dim = num_embeddings, embedding_dim
         self._padding_idx = None if padding_idx is None else (padding_idx if padding_idx >= 0 else num_embeddings + padding_idx)
         self._max_norm, self._norm_type, self._scale_grad_by_freq = max_norm, norm_type, scale_grad_by_freq
+        self._sparse = bool(sparse)      # the weight gradient is row-sparse (SelectedRows): optimizers touch only the looked-up rows
         self.weight = self.create_parameter([num_embeddings, embedding_dim], attr=weight_attr, dtype=self._dtype,
                                             default_initializer=I.XavierNormal())
         if self._padding_idx is not None:
@@ -47,7 +48,7 @@ class Embedding(Layer):
                 self.weight[self._padding_idx] = 0
 
     def forward(self, x):
-        return F.embedding(x, self.weight, self._padding_idx, self._max_norm, self._norm_type, False, self._scale_grad_by_freq)
+        return F.embedding(x, self.weight, self._padding_idx, self._max_norm, self._norm_type, self._sparse, self._scale_grad_by_freq)
 
     def extra_repr(self):
         return f"{self._num_embeddings}, {self._embedding_dim}"

@@ -102,7 +102,7 @@ def embedding(x, weight, padding_idx=None, max_norm=None, norm_type=2.0, sparse=
     w = T(weight)
     if padding_idx is not None and padding_idx < 0:
         padding_idx = w.size(0) + padding_idx
-    return F.embedding(T(x).long(), w, padding_idx, max_norm, norm_type, scale_grad_by_freq, False)
+    return F.embedding(T(x).long(), w, padding_idx, max_norm, norm_type, scale_grad_by_freq, bool(sparse))      # sparse: row-sparse weight gradient (SelectedRows)
 
 
 def one_hot(x, num_classes, name=None):

@@ -187,23 +187,43 @@ class Optimizer:
                 out.append((g, p, gr))
         return out
 
+    def _has_sparse_grad(self):
+        for g in self._param_groups:
+            for p in g["params"]:
+                gr = torch.Tensor.grad.__get__(p)
+                if gr is not None and gr.layout != torch.strided:
+                    return True
+        return False
+
     @torch.no_grad()
     def step(self):
-        if self._arena is not None and hasattr(self, "_arena_step") and self._arena_ok():
+        if self._arena is not None and hasattr(self, "_arena_step") and self._arena_ok() and not self._has_sparse_grad():
             self._step_count += 1
             return self._arena_step()
         items = self._collect()
         if not items:
             return
         self._step_count += 1
+        # row-sparse gradients (nn.Embedding(sparse=True)) travel as SelectedRows with merged rows
+        from ..framework.selected_rows import SelectedRows
+
+        items = [(g, p, SelectedRows.from_sparse_coo(gr).merge() if gr.layout != torch.strided else gr) for g, p, gr in items]
         if self._grad_clip is not None:
-            pg = self._grad_clip([(p, gr.as_subclass(Tensor)) for _, p, gr in items])
-            items = [(g, p, _raw(ng)) for (g, p, _), (_, ng) in zip(items, pg)]
+            pg = self._grad_clip([(p, gr if isinstance(gr, SelectedRows) else gr.as_subclass(Tensor)) for _, p, gr in items])
+            items = [(g, p, ng if isinstance(ng, SelectedRows) else _raw(ng)) for (g, p, _), (_, ng) in zip(items, pg)]
         base_lr = self.get_lr()
         for g, p, gr in items:
             lr = base_lr * g.get("learning_rate", 1.0) * getattr(p, "optimize_attr", {}).get("learning_rate", 1.0)
             wd, kind = self._wd_value(g, p)
-            self._update_param(g, p, _raw(p), gr, lr, wd, kind)
+            if isinstance(gr, SelectedRows):
+                self._update_param_sparse(g, p, _raw(p), gr, lr, wd, kind)
+            else:
+                self._update_param(g, p, _raw(p), gr, lr, wd, kind)
+
+    def _update_param_sparse(self, group, p, pr, grad, lr, wd, kind):
+        """Row-sparse gradient.  Default: the reference's non-lazy semantics = the dense update with zeros in the rows that were not looked
+        up (moments decay everywhere).  SGD and lazy Adam / AdamW override this to touch only `grad.rows`."""
+        self._update_param(group, p, pr, grad.to_dense().to(pr.dtype), lr, wd, kind)
 
     def backward(self, loss, startup_program=None, parameters=None, no_grad_set=None, callbacks=None):
         """First half of minimize(): run autograd and return [(param, grad)]. Parity: optimizer.py:Optimizer.backward."""
@@ -363,6 +383,12 @@ class SGD(Optimizer):
     def __init__(self, learning_rate=0.001, parameters=None, weight_decay=None, grad_clip=None, multi_precision=False, name=None):
         super().__init__(learning_rate, parameters, weight_decay, grad_clip, name, multi_precision)
 
+    def _update_param_sparse(self, group, p, pr, grad, lr, wd, kind):
+        # paddle/phi/kernels/selected_rows/sgd_kernel: param[rows] -= lr * grad_rows (regularisation reaches only the touched rows too)
+        if wd != 0.0 or pr.dtype != grad.value.dtype or self._master(p) is not None:
+            return super()._update_param_sparse(group, p, pr, grad, lr, wd, kind)
+        pr.index_add_(0, grad.rows.to(pr.device), grad.value, alpha=-lr)
+
     def _update_param(self, group, p, pr, grad, lr, wd, kind):
         if pr.is_cuda and kind == "l2" and pr.dtype in (torch.float32, torch.bfloat16, torch.float16) and grad.dtype == pr.dtype:
             from .._build import ext
@@ -408,6 +434,7 @@ class Adam(Optimizer):
                  lazy_mode=False, multi_precision=False, use_multi_tensor=False, amsgrad=False, name=None, moment_dtype=None):
         super().__init__(learning_rate, parameters, weight_decay, grad_clip, name, multi_precision)
         self._beta1, self._beta2, self._epsilon, self._amsgrad = beta1, beta2, epsilon, amsgrad
+        self._lazy_mode = bool(lazy_mode)     # row-sparse gradients update only their rows (moments of the other rows stay frozen)
         self._moment_dtype = _dt.convert_dtype(moment_dtype)
         self._lr_ratio = None
         self._apply_decay_param_fun = None
@@ -421,6 +448,38 @@ class Adam(Optimizer):
         if self._moment_dtype is not None:
             return self._moment_dtype
         return torch.float32 if (self._multi_precision or p.dtype == torch.float32) else p.dtype
+
+    def _update_param_sparse(self, group, p, pr, grad, lr, wd, kind):
+        """lazy_mode=True (paddle/phi/kernels/selected_rows/adam_kernel, lazy branch): only the rows present in the gradient update their
+        moments and their parameter rows; the bias correction still follows the global step.  Otherwise: dense semantics."""
+        if not getattr(self, "_lazy_mode", False) or self._amsgrad or self._master(p) is not None:
+            return super()._update_param_sparse(group, p, pr, grad, lr, wd, kind)
+        b1, b2 = self._betas()
+        sdt = self._state_dtype(p)
+        m = self._acc("moment1", p, dtype=sdt)
+        v = self._acc("moment2", p, dtype=sdt)
+        b1p = self._acc("beta1_pow_acc", p, init=1.0, dtype=torch.float32, shape=(1,))
+        b2p = self._acc("beta2_pow_acc", p, init=1.0, dtype=torch.float32, shape=(1,))
+        step = self._aux.setdefault("steps", {}).get(p.name, 0) + 1
+        self._aux["steps"][p.name] = step
+        rows = grad.rows.to(pr.device)
+        gf = grad.value.float()
+        pf = pr[rows].float()
+        if self._decoupled:
+            if self._apply_decay_param_fun is not None and not self._apply_decay_param_fun(p.name):
+                wd = 0.0
+            pf = pf * (1.0 - lr * wd)
+        elif wd != 0.0:
+            gf = self._apply_decay_to_grad(pf, gf, wd, kind)
+        mf = m[rows].float() * b1 + gf * (1 - b1)
+        vf = v[rows].float() * b2 + gf * gf * (1 - b2)
+        b1p.mul_(b1)
+        b2p.mul_(b2)
+        c1, c2 = 1 - b1 ** step, 1 - b2 ** step
+        pf = pf - (lr / c1) * mf / ((vf / c2).sqrt() + self._epsilon)
+        m[rows] = mf.to(m.dtype)
+        v[rows] = vf.to(v.dtype)
+        pr[rows] = pf.to(pr.dtype)
 
     def _update_param(self, group, p, pr, grad, lr, wd, kind):
         b1, b2 = self._betas()
