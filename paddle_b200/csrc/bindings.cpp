@@ -122,6 +122,47 @@ std::vector<Tensor> layer_norm_bwd(const Tensor& dy, const Tensor& x, const OptT
 }
 
 // ------------------------------------------------------------------------------------------------ elementwise
+// out = dropout(x + bias) (upscale_in_train) + y; returns (out, mask uint8).  seed / offset: Philox counter of this call
+std::vector<Tensor> bias_dropout_add(const Tensor& x, const OptT& bias, const OptT& y, double p, bool upscale, int64_t seed, int64_t offset) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && x.dim() >= 1, "bias_dropout_add: contiguous CUDA tensor required");
+  const int64_t cols = x.size(-1);
+  if (bias.has_value() && bias->defined()) TORCH_CHECK(bias->is_contiguous() && bias->numel() == cols && bias->scalar_type() == x.scalar_type(), "bias_dropout_add: bias [cols] in x dtype");
+  if (y.has_value() && y->defined()) TORCH_CHECK(y->is_contiguous() && y->numel() == x.numel() && y->scalar_type() == x.scalar_type(), "bias_dropout_add: y must match x");
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor out = torch::empty_like(x);
+  Tensor mask = torch::empty(x.sizes(), x.options().dtype(at::kByte));
+  b200::bias_dropout_add_fwd(x.data_ptr(), optp(bias), optp(y), out.data_ptr(), mask.data_ptr<uint8_t>(), x.numel(), (int)cols, (float)p, upscale ? 1 : 0, (uint64_t)seed,
+                             (uint64_t)offset, dt_code(x), cur_stream());
+  g_launches += 1;
+  check_err();
+  return {out, mask};
+}
+
+Tensor dropout_bwd(const Tensor& dout, const Tensor& mask, double p, bool upscale) {
+  TORCH_CHECK(dout.is_cuda() && dout.is_contiguous() && mask.is_contiguous() && mask.scalar_type() == at::kByte && mask.numel() == dout.numel(), "dropout_bwd: dout + uint8 mask of the same size");
+  c10::cuda::CUDAGuard guard(dout.device());
+  Tensor dx = torch::empty_like(dout);
+  b200::dropout_bwd(dout.data_ptr(), mask.data_ptr<uint8_t>(), dx.data_ptr(), dout.numel(), (float)p, upscale ? 1 : 0, dt_code(dout), cur_stream());
+  g_launches += 1;
+  check_err();
+  return dx;
+}
+
+// act(x + bias): act 0 gelu / 1 relu / 2 silu; gated (swiglu / geglu): the second half of the row multiplies the activated first half
+Tensor bias_act(const Tensor& x, const OptT& bias, int64_t act, bool gated) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && x.dim() >= 1, "bias_act: contiguous CUDA tensor required");
+  const int64_t cols = x.size(-1), rows = x.numel() / cols;
+  if (bias.has_value() && bias->defined()) TORCH_CHECK(bias->is_contiguous() && bias->numel() == cols && bias->scalar_type() == x.scalar_type(), "bias_act: bias [cols] in x dtype");
+  c10::cuda::CUDAGuard guard(x.device());
+  auto shape = x.sizes().vec();
+  if (gated) shape.back() = cols / 2;
+  Tensor out = torch::empty(shape, x.options());
+  b200::bias_act_fwd(x.data_ptr(), optp(bias), out.data_ptr(), rows, (int)cols, (int)act, gated ? 1 : 0, dt_code(x), cur_stream());
+  g_launches += 1;
+  check_err();
+  return out;
+}
+
 Tensor swiglu_fwd(const Tensor& gate, const OptT& up) {
   check_cuda_contig(gate, "gate");
   c10::cuda::CUDAGuard guard(gate.device());
@@ -824,6 +865,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rms_norm_bwd", traced("rms_norm_bwd", &rms_norm_bwd));
   m.def("layer_norm_fwd", traced("layer_norm_fwd", &layer_norm_fwd));
   m.def("layer_norm_bwd", traced("layer_norm_bwd", &layer_norm_bwd));
+  m.def("bias_dropout_add", traced("bias_dropout_add", &bias_dropout_add));
+  m.def("dropout_bwd", traced("dropout_bwd", &dropout_bwd));
+  m.def("bias_act", traced("bias_act", &bias_act));
   m.def("swiglu_fwd", traced("swiglu_fwd", &swiglu_fwd));
   m.def("swiglu_bwd", traced("swiglu_bwd", &swiglu_bwd));
   m.def("rope", traced("rope", &rope));

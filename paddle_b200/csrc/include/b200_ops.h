@@ -34,6 +34,14 @@ void rope_apply(const void* x, void* y, const float* cos_t, const float* sin_t, 
 // y = a + b (residual add), vectorised
 void add_fwd(const void* a, const void* b, void* y, int64_t n, int dtype, cudaStream_t s);
 
+// ---- fused_dropout.cu -----------------------------------------------------------------------------------------
+// out = dropout(x + bias[col]) * scale + y (bias / y optional), mask: 1 byte per element; Philox(seed, vector index, offset)
+void bias_dropout_add_fwd(const void* x, const void* bias, const void* y, void* out, uint8_t* mask, int64_t n, int cols, float p, int upscale, uint64_t seed,
+                          uint64_t offset, int dtype, cudaStream_t s);
+void dropout_bwd(const void* dout, const uint8_t* mask, void* dx, int64_t n, float p, int upscale, int dtype, cudaStream_t s);
+// act: 0 gelu, 1 relu, 2 silu; gated: out[r, c] = act(x[r, c] + b[c]) * (x[r, cols/2 + c] + b[cols/2 + c])
+void bias_act_fwd(const void* x, const void* bias, void* out, int64_t rows, int cols, int act, int gated, int dtype, cudaStream_t s);
+
 // ---- loss.cu --------------------------------------------------------------------------------------------------
 // per-row softmax cross-entropy with integer labels. loss/lse fp32 [rows].
 void softmax_ce_fwd(const void* logits, const int64_t* labels, float* loss, float* lse, int64_t rows, int vocab,

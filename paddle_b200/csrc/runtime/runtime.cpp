@@ -10,6 +10,7 @@ void bind(pybind11::module_& m) {
   bind_data_feed(m);
   bind_ir(m);
   bind_allocator(m);
+  bind_custom_device(m);
 }
 }  // namespace runtime
 }  // namespace b200

@@ -12,5 +12,6 @@ void bind_tracer(pybind11::module_& m);
 void bind_data_feed(pybind11::module_& m);
 void bind_ir(pybind11::module_& m);
 void bind_allocator(pybind11::module_& m);
+void bind_custom_device(pybind11::module_& m);
 }  // namespace runtime
 }  // namespace b200

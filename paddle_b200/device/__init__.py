@@ -31,7 +31,9 @@ def get_all_device_type():
 
 
 def get_all_custom_device_type():
-    return []
+    from . import custom
+
+    return custom.get_all_custom_device_type()      # plug-ins loaded through device.custom.load_custom_device / CUSTOM_DEVICE_ROOT
 
 
 def get_available_device():
@@ -39,7 +41,9 @@ def get_available_device():
 
 
 def get_available_custom_device():
-    return []
+    from . import custom
+
+    return custom.get_available_custom_device()
 
 
 def device_count():

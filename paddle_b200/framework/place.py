@@ -124,7 +124,9 @@ def is_compiled_with_xpu() -> bool:
 
 
 def is_compiled_with_custom_device(device_type="") -> bool:
-    return False
+    from ..device import custom
+
+    return custom.is_compiled_with_custom_device(device_type)
 
 
 def is_compiled_with_cinn() -> bool:

@@ -101,9 +101,29 @@ def fused_linear_activation(x, y, bias, trans_x=False, trans_y=False, activation
     return {"gelu": TF.gelu, "relu": torch.relu}[activation](out)
 
 
+def _fused_ew_ok(x, *others):
+    """CUDA tensors of one 16-bit / fp32 dtype whose last dimension fills whole 16-byte vectors: csrc/fused_dropout.cu applies."""
+    from ....framework.flags import flag
+
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and flag("FLAGS_use_fused_kernels", True)) or x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        return False
+    vec = 16 // x.element_size()
+    if x.dim() < 1 or x.shape[-1] % vec or x.numel() == 0:
+        return False
+    return all(o is None or (o.is_cuda and o.dtype == x.dtype) for o in others)
+
+
 def fused_bias_act(x, bias=None, dequant_scales=None, shift=None, smooth=None, act_method="gelu", compute_dtype="default", quant_scale=-1,
                    quant_round_type=0, quant_max_bound=0, quant_min_bound=0):
     x = _raw(x)
+    b = None if bias is None else _raw(bias)
+    act_id = {"gelu": 0, "relu": 1, "silu": 2, "swish": 2, "geglu": 0, "swiglu": 2}.get(act_method)
+    gated = act_method in ("swiglu", "geglu")
+    if dequant_scales is None and shift is None and smooth is None and quant_scale <= 0 and act_id is not None and _fused_ew_ok(x, b) and not (x.requires_grad and torch.is_grad_enabled()) \
+            and (not gated or (x.shape[-1] // 2) % (16 // x.element_size()) == 0) and (b is None or b.numel() == x.shape[-1]):
+        from ...._build import ext
+
+        return _w(ext().bias_act(x.contiguous(), None if b is None else b.contiguous(), act_id, gated))     # one pass: csrc/fused_dropout.cu
     if dequant_scales is not None:
         x = x.float() * _raw(dequant_scales)
     if bias is not None:
@@ -124,9 +144,41 @@ def fused_bias_act(x, bias=None, dequant_scales=None, shift=None, smooth=None, a
     return _w(out)
 
 
+class _BiasDropoutAdd(torch.autograd.Function):
+    """out = dropout(x + bias) + y in one kernel; the byte mask is the only thing saved.  Philox counter: (seed, offset) from the framework
+    generator, advanced per call so that successive calls never reuse a stream position."""
+
+    @staticmethod
+    def forward(ctx, x, bias, y, p, upscale):
+        from ...._build import ext
+
+        # the device generator owns the Philox position: take (seed, offset) from it and advance it by what one vector stream may draw
+        # (two uniform4 = 8 values), exactly like a native dropout would - re-seeding replays the same masks
+        gen = torch.cuda.default_generators[x.device.index if x.device.index is not None else torch.cuda.current_device()]
+        seed = int(gen.initial_seed()) & 0x7FFFFFFFFFFFFFFF
+        offset = int(gen.get_offset())
+        gen.set_offset(offset + 8)
+        out, mask = ext().bias_dropout_add(x.contiguous(), None if bias is None else bias.contiguous(), None if y is None else y.contiguous(), float(p), bool(upscale), seed, offset)
+        ctx.save_for_backward(mask)
+        ctx.p, ctx.upscale, ctx.has_bias, ctx.has_y = float(p), bool(upscale), bias is not None, y is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from ...._build import ext
+
+        (mask,) = ctx.saved_tensors
+        dx = ext().dropout_bwd(dout.contiguous(), mask, ctx.p, ctx.upscale)
+        dbias = dx.reshape(-1, dx.shape[-1]).sum(0) if ctx.has_bias else None
+        return dx, dbias, (dout if ctx.has_y else None), None, None
+
+
 def fused_dropout_add(x, y, p=0.5, training=True, mode="upscale_in_train", name=None):
     from ....nn import functional as F
 
+    xr, yr = _raw(x), _raw(y)
+    if training and 0.0 < p < 1.0 and _fused_ew_ok(xr, yr) and xr.shape == yr.shape:
+        return _w(_BiasDropoutAdd.apply(xr, None, yr, p, mode == "upscale_in_train"))
     return F.dropout(x, p, training=training, mode=mode) + y
 
 
@@ -134,6 +186,10 @@ def fused_bias_dropout_residual_layer_norm(x, residual, bias=None, ln_scale=None
                                            mode="upscale_in_train", name=None):
     from ....nn import functional as F
 
+    xr, rr, br = _raw(x), _raw(residual), (None if bias is None else _raw(bias))
+    if training and 0.0 < dropout_rate < 1.0 and _fused_ew_ok(xr, rr, br) and xr.shape == rr.shape and (br is None or br.numel() == xr.shape[-1]):
+        h = _w(_BiasDropoutAdd.apply(xr, br, rr, dropout_rate, mode == "upscale_in_train"))      # bias + dropout + residual: one pass
+        return F.layer_norm(h, [h.shape[-1]], ln_scale, ln_bias, ln_epsilon)                      # fused LayerNorm kernel (csrc/norm.cu)
     h = x if bias is None else x + bias
     h = F.dropout(h, dropout_rate, training=training, mode=mode) + residual
     return F.layer_norm(h, [h.shape[-1]], ln_scale, ln_bias, ln_epsilon)

@@ -717,3 +717,66 @@ def test_mx_fp8_linear_grads():
     assert rel_err(y, yr) < 5e-2
     assert rel_err(x.grad, xr.grad) < 5e-2
     assert rel_err(w.grad, wr.grad) < 5e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_fused_dropout_add_and_bias_dropout_residual_ln(dtype):
+    """csrc/fused_dropout.cu: out = dropout(x + bias) + y in one kernel with a byte mask; statistics of the mask, exact reconstruction of the
+    forward from it, exact backward, reproducibility under the framework seed, and the fused LayerNorm composition."""
+    from paddle_b200.incubate.nn import functional as IF
+
+    paddle.seed(11)
+    x = torch.randn(256, 1024, device="cuda", dtype=dtype, requires_grad=True)
+    y = torch.randn(256, 1024, device="cuda", dtype=dtype, requires_grad=True)
+    kernels.reset_launch_count()
+    out = IF.fused_dropout_add(x.as_subclass(paddle.Tensor), y.as_subclass(paddle.Tensor), p=0.25, training=True).as_subclass(torch.Tensor)
+    assert kernels.launch_count() == 1
+    kept = ((out - y).abs() > 0).float().mean().item()              # x is never exactly 0
+    assert abs(kept - 0.75) < 0.01, kept
+    ref = torch.where((out - y).abs() > 0, x.float() / 0.75 + y.float(), y.float())
+    assert rel_err(out, ref) < (1e-2 if dtype == torch.bfloat16 else 1e-6)
+    g = torch.randn_like(out)
+    out.backward(g)
+    assert torch.equal(y.grad, g)
+    gx_ref = torch.where((out.detach() - y.detach()).abs() > 0, g.float() / 0.75, torch.zeros_like(g, dtype=torch.float32))
+    assert rel_err(x.grad, gx_ref) < (1e-2 if dtype == torch.bfloat16 else 1e-6)
+    paddle.seed(11)
+    out2 = IF.fused_dropout_add(x.detach().as_subclass(paddle.Tensor), y.detach().as_subclass(paddle.Tensor), p=0.25, training=True).as_subclass(torch.Tensor)
+    assert torch.equal(out2, out.detach())                          # same seed, same masks
+    out3 = IF.fused_dropout_add(x.detach().as_subclass(paddle.Tensor), y.detach().as_subclass(paddle.Tensor), p=0.25, training=True).as_subclass(torch.Tensor)
+    assert not torch.equal(out3, out2)                              # the generator moved on
+    # bias + dropout + residual + LayerNorm
+    b = torch.randn(1024, device="cuda", dtype=dtype, requires_grad=True)
+    gam = torch.rand(1024, device="cuda", dtype=dtype) + 0.5
+    bet = torch.randn(1024, device="cuda", dtype=dtype)
+    paddle.seed(5)
+    o = IF.fused_bias_dropout_residual_layer_norm(x.detach().as_subclass(paddle.Tensor), y.detach().as_subclass(paddle.Tensor), b.as_subclass(paddle.Tensor),
+                                                  gam.as_subclass(paddle.Tensor), bet.as_subclass(paddle.Tensor), dropout_rate=0.1, training=True).as_subclass(torch.Tensor)
+    assert abs(o.float().mean().item() - bet.float().mean().item()) < 0.1 and torch.isfinite(o).all()
+    o.sum().backward()
+    assert b.grad is not None and torch.isfinite(b.grad).all()
+    # eval mode is the identity path
+    oe = IF.fused_dropout_add(x.detach().as_subclass(paddle.Tensor), y.detach().as_subclass(paddle.Tensor), p=0.25, training=False).as_subclass(torch.Tensor)
+    assert rel_err(oe, x.detach().float() + y.detach().float()) < 1e-2
+
+
+@pytest.mark.parametrize("act", ["gelu", "relu", "silu", "swiglu", "geglu"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_fused_bias_act_kernel(act, dtype):
+    from paddle_b200.incubate.nn import functional as IF
+
+    torch.manual_seed(0)
+    x = torch.randn(96, 512, device="cuda", dtype=dtype)
+    b = torch.randn(512, device="cuda", dtype=dtype)
+    kernels.reset_launch_count()
+    out = IF.fused_bias_act(x.as_subclass(paddle.Tensor), b.as_subclass(paddle.Tensor), act_method=act).as_subclass(torch.Tensor)
+    assert kernels.launch_count() == 1
+    h = x.float() + b.float()
+    F = torch.nn.functional
+    if act == "swiglu":
+        ref = F.silu(h[:, :256]) * h[:, 256:]
+    elif act == "geglu":
+        ref = F.gelu(h[:, :256]) * h[:, 256:]
+    else:
+        ref = {"gelu": F.gelu, "relu": torch.relu, "silu": F.silu}[act](h)
+    assert out.shape == ref.shape and rel_err(out, ref) < 1e-2
