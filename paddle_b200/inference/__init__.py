@@ -189,8 +189,10 @@ class Config:
 
     def delete_pass(self, name):
         p = self._opt()["passes"]
-        if name in p:
-            p.remove(name)
+        for cand in (name, name + "_pass", name[:-5] if name.endswith("_pass") else name):     # "constant_folding" == "constant_folding_pass"
+            if cand in p:
+                p.remove(cand)
+                return
 
     def enable_custom_passes(self, passes, custom_pass_only=False):
         self._opt()["passes"] = (list(passes) if custom_pass_only else self._opt()["passes"] + list(passes))
