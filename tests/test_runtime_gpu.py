@@ -185,10 +185,13 @@ torch.cuda.synchronize()
 s1 = C.allocator_stats()
 assert s1["num_allocs"] > s0["num_allocs"] and s1["allocated_peak"] >= s1["allocated"] and s1["reserved"] >= s1["allocated"]
 peak = C.max_memory_allocated()
-del x, lin, opt, loss
-C.empty_cache()
+big = torch.empty(96 << 20, dtype=torch.uint8, device="cuda")      # larger than a chunk: gets a chunk of its own
+s_big = C.allocator_stats()
+assert s_big["reserved"] >= s1["reserved"] + (96 << 20)
+del big
+C.empty_cache()                                                    # ... which goes back to cudaFree once it is idle
 s2 = C.allocator_stats()
-assert s2["reserved"] <= s1["reserved"] and s2["num_backend_frees"] >= 1
+assert s2["reserved"] <= s_big["reserved"] - (96 << 20) and s2["num_backend_frees"] >= 1, (s_big, s2)
 print("OK", s1["num_allocs"], s1["num_chunks"], s1["deferred_frees"], peak, s2["reserved"])
 """
     env = dict(os.environ, FLAGS_b200_native_allocator="1", B200_ALLOCATOR_CHUNK_MB="64")
