@@ -743,6 +743,27 @@ Tensor decode_attention(const Tensor& q, const Tensor& k_cache, const Tensor& v_
   return out;
 }
 
+// paged KV cache: q [B,H,D], caches [num_blocks,Hkv,block_size,D], lens int32 [B] (positions valid per sequence), block_tables int32 [B,max_blocks]
+Tensor decode_attention_paged(const Tensor& q, const Tensor& k_cache, const Tensor& v_cache, const Tensor& lens, const Tensor& block_tables, double scale) {
+  TORCH_CHECK(q.is_cuda() && q.dim() == 3 && k_cache.dim() == 4 && v_cache.dim() == 4 && q.is_contiguous() && k_cache.is_contiguous() && v_cache.is_contiguous(),
+              "decode_attention_paged: q [B,H,D], caches [num_blocks,Hkv,block_size,D] contiguous");
+  TORCH_CHECK(lens.scalar_type() == at::kInt && lens.is_contiguous() && lens.numel() == q.size(0), "decode_attention_paged: lens must be int32 [B]");
+  TORCH_CHECK(block_tables.is_cuda() && block_tables.scalar_type() == at::kInt && block_tables.is_contiguous() && block_tables.dim() == 2 && block_tables.size(0) == q.size(0),
+              "decode_attention_paged: block_tables must be int32 [B, max_blocks] on the device");
+  c10::cuda::CUDAGuard guard(q.device());
+  const int b = (int)q.size(0), h = (int)q.size(1), d = (int)q.size(2), hkv = (int)k_cache.size(1), bs = (int)k_cache.size(2), mb = (int)block_tables.size(1);
+  const int splits = b200::decode_attention_splits(b, h, mb * bs);
+  Tensor out = torch::empty_like(q);
+  Tensor pacc = torch::empty({b, h, splits, d}, q.options().dtype(at::kFloat));
+  Tensor pml = torch::empty({b, h, splits, 2}, q.options().dtype(at::kFloat));
+  int rc = b200::decode_attention(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), lens.data_ptr<int>(), out.data_ptr(), pacc.data_ptr<float>(),
+                                  pml.data_ptr<float>(), b, h, hkv, mb * bs, d, splits, (float)scale, dt_code(q), cur_stream(), block_tables.data_ptr<int>(), mb, bs);
+  g_launches += 2;
+  check_err();
+  TORCH_CHECK(rc == 0, "paddle_b200.decode_attention_paged: unsupported shape (head_dim 128, fp16/bf16 only) rc=", rc);
+  return out;
+}
+
 static bool fill_attn(b200::AttnArgs& a, const Tensor& q, const Tensor& k, const Tensor& v, double scale, bool causal) {
   if (q.dim() != 4 || k.dim() != 4 || v.dim() != 4) return false;
   if (q.stride(3) != 1 || k.stride(3) != 1 || v.stride(3) != 1) return false;
@@ -912,6 +933,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         pybind11::arg("out_dtype") = at::kBFloat16);
   m.def("quantize_fp8", traced("quantize_fp8", &quantize_fp8), pybind11::arg("x"), pybind11::arg("e5m2") = false, pybind11::arg("want_transpose") = false);
   m.def("decode_attention", traced("decode_attention", &decode_attention));
+  m.def("decode_attention_paged", traced("decode_attention_paged", &decode_attention_paged));
   m.def("attention_supported", &attention_supported);
   m.def("attention_fwd", traced("attention_fwd", &attention_fwd), pybind11::arg("q"), pybind11::arg("k"), pybind11::arg("v"), pybind11::arg("scale"), pybind11::arg("causal"),
         pybind11::arg("out_seq_major") = false, pybind11::arg("colmask") = pybind11::none());

@@ -8,6 +8,10 @@
 // contiguous range of positions; thread t handles positions t, t+128, ... with a private online softmax (m, l, acc[D]);
 // the CTA combines its threads through shared memory and writes one partial (m, l, acc) per split; a second tiny kernel
 // merges the splits.  D = 128, fp16 / bf16.
+//
+// Paged caches (block_multihead_attention, paddle/phi/kernels/fusion/gpu/block_multi_head_attention_kernel.cu): with `block_tables`
+// [B, max_blocks] the caches are [num_blocks, Hkv, block_size, D] and position p of sequence b lives in block block_tables[b, p / block_size]
+// at row p % block_size - one table lookup per cached row, the rest of the kernel is unchanged.
 #include <cuda.h>
 #include <cstdio>
 
@@ -22,10 +26,11 @@ constexpr int D = 128, kThreads = 128;
 template <typename T>
 __global__ void __launch_bounds__(kThreads) decode_split_kernel(const T* __restrict__ q, const T* __restrict__ kc, const T* __restrict__ vc,
                                                                 const int* __restrict__ lens, float* __restrict__ part_acc,
-                                                                float* __restrict__ part_ml, int h, int hkv, int smax, int splits, float scale_log2) {
+                                                                float* __restrict__ part_ml, int h, int hkv, int smax, int splits, float scale_log2,
+                                                                const int* __restrict__ block_tables, int max_blocks, int block_size) {
   const int split = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int kvh = head / (h / hkv);
-  const int len = min(lens[b], smax);
+  const int len = block_tables ? min(lens[b], max_blocks * block_size) : min(lens[b], smax);
   const int per = (len + splits - 1) / splits;
   const int p0 = split * per, p1 = min(len, p0 + per);
   __shared__ float sq[D];
@@ -36,12 +41,21 @@ __global__ void __launch_bounds__(kThreads) decode_split_kernel(const T* __restr
   __syncthreads();
   const T* kbase = kc + ((int64_t)b * hkv + kvh) * (int64_t)smax * D;
   const T* vbase = vc + ((int64_t)b * hkv + kvh) * (int64_t)smax * D;
+  const int* bt = block_tables ? block_tables + (int64_t)b * max_blocks : nullptr;
+  // element offset of cached position `pos` of this (sequence, kv head)
+  auto row_off = [&](int pos) -> int64_t {
+    if (!bt) return (int64_t)pos * D;
+    const int blk = bt[pos / block_size];
+    return (((int64_t)blk * hkv + kvh) * block_size + pos % block_size) * D;
+  };
+  if (bt) { kbase = kc; vbase = vc; }
   float m = -INFINITY, l = 0.f;
   float acc[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) acc[i] = 0.f;
   for (int pos = p0 + tid; pos < p1; pos += kThreads) {
-    const Vec16<T>* kr = reinterpret_cast<const Vec16<T>*>(kbase + (int64_t)pos * D);
+    const int64_t roff = row_off(pos);
+    const Vec16<T>* kr = reinterpret_cast<const Vec16<T>*>(kbase + roff);
     float s = 0.f;
 #pragma unroll
     for (int c = 0; c < D / 8; ++c) {
@@ -52,7 +66,7 @@ __global__ void __launch_bounds__(kThreads) decode_split_kernel(const T* __restr
     const float m_new = fmaxf(m, s);
     const float alpha = exp2f(m - m_new), pv = exp2f(s - m_new);
     l = l * alpha + pv;
-    const Vec16<T>* vr = reinterpret_cast<const Vec16<T>*>(vbase + (int64_t)pos * D);
+    const Vec16<T>* vr = reinterpret_cast<const Vec16<T>*>(vbase + roff);
 #pragma unroll
     for (int c = 0; c < D / 8; ++c) {
       const Vec16<T> vv = ld16(reinterpret_cast<const T*>(vr + c));
@@ -124,18 +138,20 @@ int decode_attention_splits(int b, int h, int smax) {
 }
 
 int decode_attention(const void* q, const void* k_cache, const void* v_cache, const int* lens, void* out, float* part_acc, float* part_ml, int b,
-                     int h, int hkv, int smax, int d, int splits, float scale, int dtype, cudaStream_t s) {
+                     int h, int hkv, int smax, int d, int splits, float scale, int dtype, cudaStream_t s, const int* block_tables, int max_blocks,
+                     int block_size) {
   using namespace decode;
   if (d != D || h % hkv || (dtype != kBF16 && dtype != kF16)) return 1;
+  if (block_tables && (max_blocks <= 0 || block_size <= 0)) return 1;
   dim3 grid(splits, h, b);
   const float sl2 = scale * 1.4426950408889634f;
   if (dtype == kBF16) {
     decode_split_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k_cache, (const __nv_bfloat16*)v_cache, lens,
-                                                                   part_acc, part_ml, h, hkv, smax, splits, sl2);
+                                                                   part_acc, part_ml, h, hkv, smax, splits, sl2, block_tables, max_blocks, block_size);
     decode_merge_kernel<__nv_bfloat16><<<b * h, D, 0, s>>>(part_acc, part_ml, (__nv_bfloat16*)out, splits);
   } else {
     decode_split_kernel<__half><<<grid, kThreads, 0, s>>>((const __half*)q, (const __half*)k_cache, (const __half*)v_cache, lens, part_acc, part_ml, h, hkv,
-                                                           smax, splits, sl2);
+                                                           smax, splits, sl2, block_tables, max_blocks, block_size);
     decode_merge_kernel<__half><<<b * h, D, 0, s>>>(part_acc, part_ml, (__half*)out, splits);
   }
   cudaError_t e = cudaGetLastError();

@@ -187,7 +187,8 @@ int gemm_weight_only(const WoGemmArgs& g, cudaStream_t s);
 // part_acc: fp32 [B,H,splits,128] scratch, part_ml: fp32 [B,H,splits,2] scratch.
 int decode_attention_splits(int b, int h, int smax);
 int decode_attention(const void* q, const void* k_cache, const void* v_cache, const int* lens, void* out, float* part_acc, float* part_ml, int b,
-                     int h, int hkv, int smax, int d, int splits, float scale, int dtype, cudaStream_t s);
+                     int h, int hkv, int smax, int d, int splits, float scale, int dtype, cudaStream_t s, const int* block_tables = nullptr,
+                     int max_blocks = 0, int block_size = 0);   // block_tables: paged caches [num_blocks, Hkv, block_size, D]
 
 // ---- attention_sm100.cu ---------------------------------------------------------------------------------------
 // Flash-attention forward (head_dim 128, fp16/bf16). q [B,Sq,H,D], k/v [B,Sk,Hk,D], o [B,Sq,H,D] as strided views (element

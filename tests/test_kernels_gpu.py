@@ -781,3 +781,40 @@ def test_fused_bias_act_kernel(act, dtype):
     else:
         ref = {"gelu": F.gelu, "relu": torch.relu, "silu": F.silu}[act](h)
     assert out.shape == ref.shape and rel_err(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_paged_block_attention_decode_and_prefill(dtype):
+    """incubate/nn/paged_attention.block_attention on CUDA: vectorised cache scatter, decode rows through decode_attention_paged (block-table
+    lookups in csrc/decode_attention.cu), prefill rows through the packed varlen tcgen05 attention - against the per-token reference."""
+    from paddle_b200.incubate.nn import paged_attention as PA
+
+    torch.manual_seed(0)
+    nh, nkv, d, bs, nblocks = 8, 2, 128, 16, 64
+    # a mixed batch: two prefill sequences (37 and 130 tokens), three decoding sequences with 5 / 63 / 200 cached positions
+    enc = torch.tensor([37, 130, 0, 0, 0], dtype=torch.int32)
+    dec = torch.tensor([0, 0, 5, 63, 200], dtype=torch.int32)
+    now = torch.tensor([37, 130, 1, 1, 1], dtype=torch.int32)
+    cu = torch.zeros(6, dtype=torch.int32)
+    cu[1:] = torch.cumsum(now, 0)
+    total = int(cu[-1])
+    perm = torch.randperm(nblocks)
+    bt = torch.full((5, 16), -1, dtype=torch.int32)
+    nxt = 0
+    for b, need in enumerate([37, 130, 6, 64, 201]):
+        n = (need + bs - 1) // bs
+        bt[b, :n] = perm[nxt:nxt + n].to(torch.int32)
+        nxt += n
+    bt = bt.clamp(min=0)
+    qkv = (torch.randn(total, (nh + 2 * nkv) * d, device="cuda") * 0.5).to(dtype)
+    kc0 = (torch.randn(nblocks, nkv, bs, d, device="cuda") * 0.5).to(dtype)
+    vc0 = (torch.randn(nblocks, nkv, bs, d, device="cuda") * 0.5).to(dtype)
+    args = (enc.cuda(), dec.cuda(), now.cuda(), cu.cuda(), bt.cuda(), bs)
+    kernels.reset_launch_count()
+    out, _, kc1, vc1 = PA.block_attention(qkv, kc0.clone(), vc0.clone(), *args)
+    assert kernels.launch_count() >= 3                                  # paged decode (2 launches) + varlen attention
+    ref, _, kc2, vc2 = PA._block_attention_ref(qkv, kc0.clone(), vc0.clone(), *args)
+    assert torch.equal(kc1.as_subclass(torch.Tensor), kc2.as_subclass(torch.Tensor)) and torch.equal(vc1.as_subclass(torch.Tensor), vc2.as_subclass(torch.Tensor))
+    o, r = out.as_subclass(torch.Tensor).float(), ref.as_subclass(torch.Tensor).float()
+    assert rel_err(o[:167], r[:167]) < 2e-2                             # prefill rows
+    assert rel_err(o[167:], r[167:]) < 2e-2                             # decode rows
