@@ -633,7 +633,11 @@ static int launch(const GemmArgs& g, cudaStream_t s) {
     attr_set = true;
   }
   const int num_tiles = ((g.m + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((g.n + BLOCK_N - 1) / BLOCK_N) * (int)batch;
-  const int max_clusters = sm_count() / 2;
+  // B200_GEMM_RESERVE_SMS=<n>: keep n SMs out of every persistent GEMM grid so that concurrently launched collective kernels are resident
+  // unconditionally (docs/race_detection.md, "cross-rank progress"); default 0
+  static const int reserve = [] { const char* e = getenv("B200_GEMM_RESERVE_SMS"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : v; }();
+  const int usable = sm_count() - reserve;
+  const int max_clusters = usable >= 2 ? usable / 2 : 1;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
   kern<<<clusters * 2, kThreads, SMEM_BYTES, s>>>(ma, mb, dm, p);
   cudaError_t e = cudaGetLastError();
