@@ -67,6 +67,7 @@ struct Params {
   uint32_t idesc_mk;     // A MN-major, B K-major  (dQ^T)
   const int4* colmask;   // [b, mask_heads, sk] hidden row ranges per key column (see AttnArgs::colmask); nullptr: none
   int mask_heads;
+  int* dq_sem;           // deterministic dQ: turn counter per (batch, head, query tile); nullptr = reduce in arrival order
 };
 
 template <typename T, bool MASKED>
@@ -241,13 +242,41 @@ bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       }
       tc_fence_before();
       fence_proxy_async();
-      asm volatile("bar.sync 1, 256;" ::: "memory");      // both softmax warpgroups: the whole [128][128] fp32 tile is in smem
+      // Deterministic mode (FLAGS_cudnn_deterministic): the fp32 adds of the bulk reduce are order dependent, so the key tiles take turns on
+      // a query tile in ascending order (tile n waits for the counter to reach n; every key tile from 0 on contributes to every query tile
+      // it visits, masked or not).  CTAs with a lower blockIdx.x are dispatched first, so the tile waited for is resident or done.
+      int* sem = nullptr;
+      if (p.dq_sem) {
+        sem = p.dq_sem + ((int64_t)batch * p.h + head) * num_m + (m0 / BM);
+        if (threadIdx.x == 0) {
+          uint64_t t0 = 0;
+          uint32_t spins = 0;
+          while (true) {
+            int v;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(sem) : "memory");
+            if (v >= n_tile) break;
+            if (++spins == 4096) t0 = globaltimer_ns();
+            if (spins > 4096 && (spins & 1023) == 0 && globaltimer_ns() - t0 > 10000000000ull) {
+              printf("b200 attention bwd: deterministic dQ turn timeout (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
+              __trap();
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // both softmax warpgroups: the whole [128][128] fp32 tile is in smem (and it is our turn)
       if (half == 0 && m0 + rl < p.sq) {
         float* dst = p.dq + (int64_t)batch * p.dq_sb + (int64_t)(m0 + rl) * p.dq_ss + (int64_t)head * p.dq_sh;
         asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 512;" ::"l"(dst), "r"(sDQ + (uint32_t)rl * 512u) : "memory");
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tile in shared memory may be overwritten
+      if (sem) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the adds have been performed, not just read from smem
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(sem), "r"(n_tile + 1) : "memory");
+      } else {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tile in shared memory may be overwritten
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);            // 8 warp arrivals
     }
@@ -388,6 +417,7 @@ int attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
   p.causal = f.causal; p.causal_off = f.sk - f.sq;
   p.colmask = reinterpret_cast<const int4*>(f.colmask);
   p.mask_heads = f.mask_heads > 0 ? f.mask_heads : 1;
+  p.dq_sem = a.dq_sem;
   p.lse = f.lse; p.delta = a.delta; p.dq = a.dq; p.dk = a.dk; p.dv = a.dv;
   p.dkv_sb = a.dkv_strides[0]; p.dkv_ss = a.dkv_strides[1]; p.dkv_sh = a.dkv_strides[2];
   p.dq_sb = a.dq_strides[0]; p.dq_ss = a.dq_strides[1]; p.dq_sh = a.dq_strides[2];

@@ -814,6 +814,8 @@ std::vector<Tensor> attention_fwd(const Tensor& q, const Tensor& k, const Tensor
   return {out, lse};
 }
 
+static bool g_deterministic = false;     // FLAGS_cudnn_deterministic: order-dependent reductions take a fixed order
+
 // backward of attention_fwd: returns (dq [B,Sq,H,D], dk, dv [B,Sk,Hk,D]) in the input dtype
 std::vector<Tensor> attention_bwd(const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& out, const Tensor& lse, const Tensor& d_out,
                                   double scale, bool causal, const OptT& colmask) {
@@ -829,6 +831,8 @@ std::vector<Tensor> attention_bwd(const Tensor& q, const Tensor& k, const Tensor
   Tensor delta = torch::empty({a.fwd.b, a.fwd.h, a.fwd.sq}, q.options().dtype(at::kFloat));
   a.d_o = d_out.data_ptr(); a.delta = delta.data_ptr<float>(); a.dq = dq32.data_ptr<float>(); a.dk = dk.data_ptr(); a.dv = dv.data_ptr();
   for (int i = 0; i < 3; ++i) { a.dkv_strides[i] = dk.stride(i); a.o_strides[i] = out.stride(i); a.dq_strides[i] = dq32.stride(i); }
+  Tensor sem;
+  if (g_deterministic) { sem = torch::zeros({a.fwd.b, a.fwd.h, (a.fwd.sq + 127) / 128}, q.options().dtype(at::kInt)); a.dq_sem = sem.data_ptr<int>(); }
   int rc = b200::attention_bwd(a, cur_stream());
   g_launches += 2;
   check_err();
@@ -857,6 +861,8 @@ Tensor attention_bwd_packed(const Tensor& qkv, int64_t nh, int64_t nkv, const Te
   Tensor delta = torch::empty({a.fwd.b, a.fwd.h, a.fwd.sq}, qkv.options().dtype(at::kFloat));
   a.d_o = d_out.data_ptr(); a.delta = delta.data_ptr<float>(); a.dq = dq32_mem.data_ptr<float>(); a.dk = dk.data_ptr(); a.dv = dv.data_ptr();
   for (int i = 0; i < 3; ++i) { a.dkv_strides[i] = dk.stride(i); a.o_strides[i] = ov.stride(i); a.dq_strides[i] = dq32.stride(i); }
+  Tensor sem;
+  if (g_deterministic) { sem = torch::zeros({a.fwd.b, a.fwd.h, (a.fwd.sq + 127) / 128}, qkv.options().dtype(at::kInt)); a.dq_sem = sem.data_ptr<int>(); }
   int rc = b200::attention_bwd(a, cur_stream());
   g_launches += 2;
   check_err();
@@ -932,6 +938,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_fp8_mx", traced("gemm_fp8_mx", &gemm_fp8_mx), pybind11::arg("a"), pybind11::arg("sfa"), pybind11::arg("b"), pybind11::arg("sfb"), pybind11::arg("bias") = pybind11::none(),
         pybind11::arg("out_dtype") = at::kBFloat16);
   m.def("quantize_fp8", traced("quantize_fp8", &quantize_fp8), pybind11::arg("x"), pybind11::arg("e5m2") = false, pybind11::arg("want_transpose") = false);
+  m.def("set_deterministic", [](bool on) { g_deterministic = on; });
+  m.def("deterministic", []() { return g_deterministic; });
   m.def("decode_attention", traced("decode_attention", &decode_attention));
   m.def("decode_attention_paged", traced("decode_attention_paged", &decode_attention_paged));
   m.def("attention_supported", &attention_supported);

@@ -220,6 +220,7 @@ struct AttnBwdArgs {
   int64_t dkv_strides[3];   // element strides (batch, seq, head) of dk and dv (16-byte aligned rows)
   int64_t o_strides[3];     // element strides (batch, seq, head) shared by the forward output `fwd.o` and d_o
   int64_t dq_strides[3];    // element strides (batch, seq, head) of the fp32 dq accumulator
+  int* dq_sem = nullptr;    // deterministic mode: zeroed int32 [B, H, ceil(Sq / 128)] turn counters - key tiles add into a dQ tile in ascending order
 };
 int attention_bwd(const AttnBwdArgs& a, cudaStream_t s);
 

@@ -48,6 +48,27 @@ for _k in list(_FLAGS):
 def set_flags(flags: dict):
     for k, v in flags.items():
         _FLAGS[k] = _coerce(_FLAGS[k], v) if k in _FLAGS else v
+        if k == "FLAGS_cudnn_deterministic":
+            _apply_deterministic(bool(_FLAGS[k]))
+
+
+def _apply_deterministic(on):
+    """FLAGS_cudnn_deterministic reaches the hand-written kernels too: order-dependent reductions (the dQ bulk-reduce of the attention
+    backward) take a fixed order; PyTorch's own switch covers the library kernels."""
+    import torch
+
+    try:
+        torch.backends.cudnn.deterministic = bool(on)
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        from .._build import load
+
+        m = load()
+        if m is not None and hasattr(m, "set_deterministic"):
+            m.set_deterministic(bool(on))
+    except Exception:  # noqa: BLE001
+        pass
 
 
 def get_flags(names):
@@ -58,3 +79,7 @@ def get_flags(names):
 
 def flag(name, default=None):
     return _FLAGS.get(name, default)
+
+
+if _FLAGS.get("FLAGS_cudnn_deterministic"):
+    _apply_deterministic(True)

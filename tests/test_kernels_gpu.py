@@ -818,3 +818,27 @@ def test_paged_block_attention_decode_and_prefill(dtype):
     o, r = out.as_subclass(torch.Tensor).float(), ref.as_subclass(torch.Tensor).float()
     assert rel_err(o[:167], r[:167]) < 2e-2                             # prefill rows
     assert rel_err(o[167:], r[167:]) < 2e-2                             # decode rows
+
+
+def test_attention_backward_is_bitwise_reproducible_in_deterministic_mode():
+    """FLAGS_cudnn_deterministic: the key tiles reduce into a dQ tile in ascending order (turn counters in csrc/attention_bwd_sm100.cu), so
+    repeated backward passes are bit-identical; the default mode (arrival-order bulk reduce) only has to match numerically."""
+    E = _ext()
+    torch.manual_seed(0)
+    b, s, h, d = 2, 1024, 8, 128
+    q, k, v = (torch.randn(b, s, h, d, device="cuda", dtype=torch.bfloat16) for _ in range(3))
+    out, lse = E.attention_fwd(q, k, v, d ** -0.5, True)
+    g = torch.randn_like(out)
+    base = E.attention_bwd(q, k, v, out, lse, g, d ** -0.5, True)
+    paddle.set_flags({"FLAGS_cudnn_deterministic": True})
+    try:
+        assert E.deterministic()
+        runs = [E.attention_bwd(q, k, v, out, lse, g, d ** -0.5, True) for _ in range(4)]
+    finally:
+        paddle.set_flags({"FLAGS_cudnn_deterministic": False})
+    assert not E.deterministic()
+    for r in runs[1:]:
+        for a, c in zip(runs[0], r):
+            assert torch.equal(a, c)
+    for a, c in zip(runs[0], base):
+        assert rel_err(a, c.float()) < 2e-2
