@@ -119,8 +119,8 @@ class StaticFunction:
         sample = tuple((a.as_subclass(torch.Tensor) if type(a) is not torch.Tensor else a).detach().clone().requires_grad_(a.requires_grad) for a in args)
         try:
             graphed = torch.cuda.make_graphed_callables(pure, sample + tuple(params), num_warmup_iters=2, allow_unused_input=True)
-        except Exception:  # noqa: BLE001  capture-unsafe body: stay eager for this signature
-            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001  capture-unsafe body: stay eager for this signature
+            _capture_failed(e)
             return None
         return graphed, params
 
@@ -184,9 +184,34 @@ class StaticFunction:
             with torch.cuda.graph(g):
                 out = self._fn(*static_args, **static_kwargs)
             return g, static_in, out
-        except Exception:  # capture-unsafe function (host sync, dynamic shapes...): stay eager for this signature
-            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001  capture-unsafe function (host sync, dynamic shapes...): stay eager for this signature
+            _capture_failed(e)
             return None
+
+
+def _capture_failed(exc):
+    """A capture that died half way leaves the device RNG registered as "capturing" (every later random op then raises "Offset increment
+    outside graph capture"): drain the device and run one trivial capture to completion, which resets the generator.  B200_JIT_DEBUG=1 prints
+    why the capture failed."""
+    import os
+
+    if os.environ.get("B200_JIT_DEBUG"):
+        import traceback
+
+        traceback.print_exception(type(exc), exc, exc.__traceback__)
+    try:
+        torch.cuda.synchronize()
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                torch.zeros(1, device="cuda")
+        torch.cuda.synchronize()
+    except Exception:  # noqa: BLE001
+        pass
 
 
 def _clone_tree(o):
