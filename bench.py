@@ -49,7 +49,20 @@ def parse():
     ap.add_argument("--no-comm-calibration", action="store_true")
     ap.add_argument("--recompute-skip", type=int, default=-1,
                     help="N=1 only: number of trailing decoder layers that keep their activations (default: as many as fit in HBM)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    # auto-tuner trials (paddle_b200.distributed.launch --auto_tuner_json / distributed.auto_tuner.AutoTuner.tune): the candidate arrives in the
+    # environment and overrides the layout flags; sharding candidates are not a bench.py layout and leave the flags untouched
+    tune = os.environ.get("B200_TUNE_CFG")
+    if tune:
+        c = json.loads(tune)
+        if c.get("sharding", 1) == 1:
+            args.layout = f"{c['dp']},{c['mp']},{c['pp']}"
+            args.micro_batch = int(c.get("micro_batch", args.micro_batch))
+            args.pp_schedule = c.get("pp_schedule", args.pp_schedule) if c.get("pp", 1) > 1 else args.pp_schedule
+            args.vpp = int(c.get("vpp", args.vpp))
+            if c.get("recompute") == "none":
+                args.recompute_skip = -1
+    return args
 
 
 class ClockSampler:

@@ -32,6 +32,8 @@ def parse(argv=None):
     ap.add_argument("--server_num", type=int, default=None, help="parameter-server mode: servers started on this node")
     ap.add_argument("--trainer_num", type=int, default=None, help="parameter-server mode: trainers started on this node")
     ap.add_argument("--servers", default="", help="parameter-server mode: explicit ip:port list of the servers")
+    ap.add_argument("--auto_tuner_json", default=None, help="auto-tuner mode: JSON with the model / search space (distributed/auto_tuner.py); every trial is one "
+                    "launch of the training script with the candidate in B200_TUNE_* variables; the script prints a JSON line with the metric")
     ap.add_argument("training_script")
     ap.add_argument("training_script_args", nargs=argparse.REMAINDER)
     return ap.parse_args(argv)
@@ -144,5 +146,31 @@ def launch(args):
         port = str(_free_port()) if not args.master else port
 
 
+def launch_auto_tuner(args):
+    """`--auto_tuner_json cfg.json`: trial loop of distributed.auto_tuner.  Parity: the auto-tuner mode of paddle.distributed.launch
+    (python/paddle/distributed/launch/controllers/collective.py + auto_tuner/tuner.py)."""
+    import json
+
+    from ..auto_tuner import AutoTuner
+
+    with open(args.auto_tuner_json) as f:
+        cfg = json.load(f)
+    nproc = args.nproc_per_node or cfg.get("num_gpus", 1)
+    cfg.setdefault("num_gpus", nproc * int(str(args.nnodes).split(":")[0]))
+    os.makedirs(args.log_dir, exist_ok=True)
+    cfg.setdefault("history_path", os.path.join(args.log_dir, "auto_tuner_history.jsonl"))
+    tuner = AutoTuner(cfg)
+    cmd = [sys.executable, "-m", "paddle_b200.distributed.launch", "--nproc_per_node", str(nproc), "--log_dir", os.path.join(args.log_dir, "trial")]
+    if args.master:
+        cmd += ["--master", args.master]
+    cmd += [args.training_script] + list(args.training_script_args)
+    best = tuner.tune(command=cmd, max_trials=int(cfg.get("max_trials", 8)), max_time_s=cfg.get("max_time_s"), timeout_s=int(cfg.get("trial_timeout_s", 1800)),
+                      metric_key=cfg.get("metric_key", "value"))
+    tuner.recorder.to_csv(os.path.join(args.log_dir, "auto_tuner_history.csv"))
+    print(json.dumps({"auto_tuner_best": best, "trials": len(tuner.history)}))
+    return 0 if best is not None else 1
+
+
 def main(argv=None):
-    sys.exit(launch(parse(argv)))
+    args = parse(argv)
+    sys.exit(launch_auto_tuner(args) if args.auto_tuner_json else launch(args))
