@@ -1,0 +1,207 @@
+"""Autoregressive generation with a KV cache for the decoder-only models of this package (`LlamaForCausalLM`).
+
+Role parity: the serving path the reference builds out of `masked_multihead_attention` / `block_multihead_attention` +
+`FusedMultiTransformer` (python/paddle/incubate/nn/layer/fused_transformer.py) and PaddleNLP's `generate()`: prefill once, then one
+token per step against cached keys / values, greedy or sampled (temperature, top-k, top-p), ragged prompts, early stop on EOS.
+
+The cache layout is the decode kernel's: `k`, `v` of every layer are [B, H_kv, S_max, D] with `lens[b]` valid positions
+(csrc/decode_attention.cu).  Prefill runs the model's own sublayers (fused RMSNorm / packed rotary / flash attention on CUDA) and writes
+the rotated keys and the values into the cache; a decode step projects ONE token, rotates it at position `lens[b]`, appends it and attends
+to the cache - through `decode_attention` (split-K over the cached positions) when `FLAGS_b200_decode_kernel` is set and the shapes qualify
+(CUDA, head_dim 128, fp16 / bf16), otherwise through a masked softmax over the cache (any device / dtype; the default until the kernel
+path has been exercised end to end on hardware)."""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from ..tensor import Tensor
+
+
+def _raw(t):
+    return t.as_subclass(torch.Tensor) if isinstance(t, torch.Tensor) and type(t) is not torch.Tensor else t
+
+
+def _w(t):
+    return t.as_subclass(Tensor) if isinstance(t, torch.Tensor) and not isinstance(t, Tensor) else t
+
+
+class KVCache:
+    """Per-layer key / value cache [B, H_kv, S_max, D] + the number of valid positions per sequence."""
+
+    def __init__(self, num_layers, batch, kv_heads, max_len, head_dim, dtype, device):
+        self.k = [torch.zeros(batch, kv_heads, max_len, head_dim, dtype=dtype, device=device) for _ in range(num_layers)]
+        self.v = [torch.zeros(batch, kv_heads, max_len, head_dim, dtype=dtype, device=device) for _ in range(num_layers)]
+        self.lens = torch.zeros(batch, dtype=torch.int32, device=device)
+        self.max_len = max_len
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.k + self.v)
+
+    def write_prefix(self, layer, k, v):
+        """k, v: [B, S, H_kv, D] of the prompt (positions 0 .. S-1)."""
+        s = k.shape[1]
+        self.k[layer][:, :, :s] = k.transpose(1, 2)
+        self.v[layer][:, :, :s] = v.transpose(1, 2)
+
+    def append(self, layer, k, v):
+        """k, v: [B, H_kv, D] of the new token; lands at position lens[b] of every sequence."""
+        idx = self.lens.long()
+        b = torch.arange(k.shape[0], device=k.device)
+        self.k[layer][b, :, idx] = k
+        self.v[layer][b, :, idx] = v
+
+
+def _attend_cache(q, kc, vc, lens, scale):
+    """q [B, H, D] against the cache [B, H_kv, S_max, D] with `lens` valid positions (the new token already appended)."""
+    from ..framework.flags import flag
+
+    if flag("FLAGS_b200_decode_kernel", False) and q.is_cuda and q.shape[-1] == 128 and q.dtype in (torch.float16, torch.bfloat16):
+        from .._build import ext
+
+        return ext().decode_attention(q.contiguous(), kc, vc, lens.to(torch.int32).contiguous(), float(scale))
+    b, h, d = q.shape
+    hkv = kc.shape[1]
+    smax = int(lens.max().item())
+    k = kc[:, :, :smax].float()
+    v = vc[:, :, :smax].float()
+    if hkv != h:
+        k = k.repeat_interleave(h // hkv, 1)
+        v = v.repeat_interleave(h // hkv, 1)
+    s = torch.einsum("bhd,bhsd->bhs", q.float(), k) * scale
+    mask = torch.arange(smax, device=q.device)[None, None, :] >= lens.long()[:, None, None]
+    s = s.masked_fill(mask, float("-inf"))
+    return torch.einsum("bhs,bhsd->bhd", torch.softmax(s, -1), v).to(q.dtype)
+
+
+class LlamaGenerator:
+    """Prefill + decode over the sublayers of a `LlamaForCausalLM` (no tensor / pipeline parallelism: serve one replica per GPU)."""
+
+    def __init__(self, model):
+        from . import llama as L
+
+        self.model, self.cfg = model, model.config
+        self.layers = list(model.llama.layers)
+        at = self.layers[0].self_attn
+        if at.mp != 1:
+            raise NotImplementedError("LlamaGenerator serves a single-rank replica (mp_degree 1)")
+        self.nh, self.nkv, self.hd = at.num_heads, at.num_kv_heads, at.head_dim
+        self._rope = L.rope_cache
+        self._KR = L.KR
+        self._KA = L.KA
+
+    # -- one decoder layer on [B, S, hidden] with explicit positions; returns (h, k, v) with k, v [B, S, H_kv, D] (k rotated)
+    def _layer(self, layer, h, cos, sin, position_ids, attend):
+        at, mlp = layer.self_attn, layer.mlp
+        nh, nkv, hd = self.nh, self.nkv, self.hd
+        x = layer.input_layernorm(h)
+        qkv = _raw(self._KR.apply_rope_packed(at.qkv_proj(x), cos, sin, nh + nkv, nh + 2 * nkv, hd, position_ids, neox=True))
+        b, s = qkv.shape[0], qkv.shape[1]
+        qkv = qkv.reshape(b, s, nh + 2 * nkv, hd)
+        q, k, v = qkv[:, :, :nh], qkv[:, :, nh:nh + nkv], qkv[:, :, nh + nkv:]
+        a = attend(q, k, v)                                               # [B, S, H, D]
+        a = at.o_proj(_w(a.reshape(b, s, nh * hd)))
+        x, h = layer.post_attention_layernorm(a, residual=h)
+        return h + mlp.down_proj(self._KA.swiglu(mlp.gate_up_proj(x))), k, v
+
+    @torch.no_grad()
+    def prefill(self, input_ids, prompt_lens, cache):
+        """Whole prompts (right padded to a common length) through the stack; fills the cache; returns the logits of every sequence's
+        LAST real token [B, vocab]."""
+        ids = _raw(input_ids)
+        b, s = ids.shape
+        scale = 1.0 / math.sqrt(self.hd)
+        h = self.model.llama.embedding(_w(ids))
+        cos, sin = self._rope(self.cfg, _raw(h).device)
+        pos = torch.arange(s, device=ids.device, dtype=torch.int64).unsqueeze(0).expand(b, s).contiguous()
+
+        def attend(q, k, v):
+            rep = self.nh // self.nkv
+            kk, vv = (k.repeat_interleave(rep, 2), v.repeat_interleave(rep, 2)) if rep > 1 else (k, v)
+            o = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), kk.transpose(1, 2), vv.transpose(1, 2), is_causal=True, scale=scale)
+            return o.transpose(1, 2)
+
+        for i, layer in enumerate(self.layers):
+            h, k, v = self._layer(layer, h, cos, sin, pos, attend)
+            cache.write_prefix(i, k, v)
+        cache.lens.copy_(prompt_lens.to(torch.int32))
+        last = (prompt_lens.long() - 1).clamp(min=0)
+        hl = _raw(h)[torch.arange(b, device=ids.device), last].unsqueeze(1)   # [B, 1, hidden]
+        return _raw(self.model.lm_head(_w(hl)))[:, 0]
+
+    @torch.no_grad()
+    def decode_step(self, tokens, cache):
+        """One new token per sequence ([B] ids) at position cache.lens[b]; returns logits [B, vocab] and advances the cache."""
+        ids = _raw(tokens).reshape(-1, 1)
+        b = ids.shape[0]
+        scale = 1.0 / math.sqrt(self.hd)
+        h = self.model.llama.embedding(_w(ids))
+        cos, sin = self._rope(self.cfg, _raw(h).device)
+        pos = cache.lens.long().reshape(b, 1)
+        for i, layer in enumerate(self.layers):
+            def attend(q, k, v, i=i):
+                cache.append(i, k[:, 0], v[:, 0])
+                return _attend_cache(q[:, 0], cache.k[i], cache.v[i], cache.lens + 1, scale).unsqueeze(1)
+
+            h, _, _ = self._layer(layer, h, cos, sin, pos, attend)
+        cache.lens += 1
+        return _raw(self.model.lm_head(h))[:, 0]
+
+
+def _sample(logits, do_sample, temperature, top_k, top_p, generator=None):
+    if not do_sample or temperature == 0.0:
+        return logits.argmax(-1)
+    logits = logits.float() / max(float(temperature), 1e-6)
+    if top_k and top_k > 0:
+        kth = torch.topk(logits, min(int(top_k), logits.shape[-1]), dim=-1).values[..., -1:]
+        logits = logits.masked_fill(logits < kth, float("-inf"))
+    if top_p is not None and top_p < 1.0:
+        sorted_logits, order = torch.sort(logits, descending=True, dim=-1)
+        probs = torch.softmax(sorted_logits, -1)
+        drop = probs.cumsum(-1) - probs > top_p                       # keep the smallest prefix whose mass reaches top_p
+        sorted_logits = sorted_logits.masked_fill(drop, float("-inf"))
+        logits = torch.full_like(logits, float("-inf")).scatter(-1, order, sorted_logits)
+    return torch.multinomial(torch.softmax(logits, -1), 1, generator=generator).squeeze(-1)
+
+
+@torch.no_grad()
+def generate(model, input_ids, max_new_tokens=32, prompt_lens=None, do_sample=False, temperature=1.0, top_k=0, top_p=1.0, eos_token_id=None, pad_token_id=0,
+             max_length=None, return_cache=False):
+    """Generate up to `max_new_tokens` tokens per sequence.  `input_ids` [B, S] (right padded when `prompt_lens` [B] is given).
+    Returns ids [B, S_max_prompt + new] where position `prompt_lens[b] + t` holds the t-th generated token of sequence b (the padding
+    of shorter prompts is overwritten), padded with `pad_token_id` after an EOS."""
+    was_training = model.training
+    model.eval()
+    try:
+        ids = _raw(input_ids).long()
+        b, s = ids.shape
+        dev = ids.device
+        lens = torch.full((b,), s, dtype=torch.int64, device=dev) if prompt_lens is None else _raw(prompt_lens).to(dev).long()
+        total = int(max_length) if max_length is not None else s + int(max_new_tokens)
+        gen = LlamaGenerator(model)
+        p0 = next(iter(model.parameters()))
+        cache = KVCache(len(gen.layers), b, gen.nkv, total, gen.hd, _raw(p0).dtype, dev)
+        out = torch.full((b, total), int(pad_token_id), dtype=torch.int64, device=dev)
+        for i in range(b):
+            out[i, : int(lens[i])] = ids[i, : int(lens[i])]
+        logits = gen.prefill(ids, lens, cache)
+        done = torch.zeros(b, dtype=torch.bool, device=dev)
+        rows = torch.arange(b, device=dev)
+        steps = min(int(max_new_tokens), total - int(lens.min()))
+        for t in range(steps):
+            nxt = _sample(logits, do_sample, temperature, top_k, top_p)
+            nxt = torch.where(done, torch.full_like(nxt, int(pad_token_id)), nxt)
+            pos = (lens + t).clamp(max=total - 1)
+            out[rows, pos] = torch.where(lens + t < total, nxt, out[rows, pos])
+            if eos_token_id is not None:
+                done = done | (nxt == int(eos_token_id))
+                if bool(done.all()):
+                    break
+            if t + 1 < steps and int(cache.lens.max()) < total:
+                logits = gen.decode_step(nxt, cache)
+        res = _w(out)
+        return (res, cache) if return_cache else res
+    finally:
+        if was_training:
+            model.train()
