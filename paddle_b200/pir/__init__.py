@@ -199,7 +199,7 @@ def translate_to_pir(program, fetch_vids=None):
                             [_ty(program._keep[v]) for v in node.outs])
             for v, r in zip(node.outs, res):
                 vid_of[r], ir_of[v] = v, r
-            templates[_last_op_id(ir)] = ("node", node)
+            templates[_last_op_id(ir)] = ("node", node, [ir_of[v] for v in refs if v in ir_of])
             continue
         t_args, t_kwargs = enc(node.args), enc(node.kwargs)
         attrs = {}
@@ -309,6 +309,10 @@ def _perm_of(name, node, program):
     return None
 
 
+def _identity(x):
+    return x
+
+
 # implementations of the ops only rewrite patterns create
 def _fused_linear(x, w, b, activation=None):
     from ..nn import functional as F
@@ -389,7 +393,13 @@ def lower(tr, pm=None):
         tpl = tr.templates.get(op["id"])
         operands = op["operands"]
         if tpl is not None and tpl[0] == "node":
-            out.nodes.append(tpl[1])
+            # an opaque node (run-time control flow) reads the value table by the ORIGINAL slots: when a rewrite moved one of its inputs to
+            # another slot (CSE / a fusion), bind the old slot to the survivor first
+            node = tpl[1]
+            for old_ir, cur_ir in zip(tpl[2], operands):
+                if old_ir != cur_ir and old_ir in tr.vid_of:
+                    out.nodes.append(_Node(_identity, (_Ref(vid(cur_ir)),), {}, [tr.vid_of[old_ir]]))
+            out.nodes.append(node)
             continue
         if tpl is not None:
             _, fn, t_args, t_kwargs, kind = tpl

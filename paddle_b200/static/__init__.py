@@ -416,8 +416,8 @@ class Executor:
         folding / fusion patterns) once per fetch set; the lowered program is cached on the source program."""
         from .. import pir
 
-        if not pir.core_available() or any(n.kind != "op" for n in program.nodes):
-            return program          # programs with training / control nodes keep their recorded form
+        if not pir.core_available() or any(n.kind not in ("op", "control") for n in program.nodes):
+            return program          # programs with a training node keep their recorded form (its closure re-walks the recorded tape)
         key = tuple(f if isinstance(f, str) else id(f) for f in (fetch_list or []))
         cache = program.__dict__.setdefault("_pir_cache", {})
         if key not in cache or cache[key][0] != len(program.nodes):

@@ -271,3 +271,42 @@ def test_inference_predictor_runs_ir_passes_on_program_artifacts(tmp_path):
     assert len(p1._layer._blob["program"].nodes) < n_saved
     got = p1.run([data])[0]
     np.testing.assert_allclose(np.asarray(got), np.asarray(ref), rtol=1e-5, atol=1e-5)
+
+
+def test_programs_with_run_time_control_flow_go_through_the_passes():
+    """A while_loop node is opaque to the IR (side-effect op that keeps its inputs alive); the ops around it are still optimised, and when CSE
+    moves one of the loop's inputs to another slot the lowering binds the old slot to the survivor."""
+    paddle.enable_static()
+    try:
+        main = paddle.static.Program()
+        with paddle.static.program_guard(main):
+            x = paddle.static.data("x", [4], "float32")
+            n = paddle.static.data("n", [1], "int64")
+            a = paddle.exp(x)
+            b = paddle.exp(x)                                   # same value as `a`: CSE merges it, the loop below reads `b`
+            i0 = paddle.zeros([1], "int64")
+
+            def cond(i, acc):
+                return i < n
+
+            def body(i, acc):
+                return i + 1, acc + b
+
+            _, acc = paddle.static.nn.while_loop(cond, body, [i0, paddle.zeros([4], "float32")])
+            dead = paddle.tanh(a)
+            y = acc * a
+        exe = paddle.static.Executor()
+        feed = {"x": np.array([0.1, 0.2, 0.3, 0.4], "float32"), "n": np.array([3], "int64")}
+        (ref,) = exe.run(main, feed=feed, fetch_list=[y])
+        np.testing.assert_allclose(ref, 3 * np.exp(feed["x"]) ** 2, rtol=1e-5)
+        opt, report = pir.optimize(main, fetch_list=[y], return_report=True)
+        assert any(r["pass"] == "cse" and r["changed"] >= 1 for r in report) and any(r["pass"] == "dce" and r["changed"] >= 1 for r in report)
+        assert sum(1 for nd in opt.nodes if getattr(nd.fn, "__name__", "") == "exp") == 1
+        assert any(nd.kind == "control" for nd in opt.nodes)
+        (got,) = exe.run(opt, feed=feed, fetch_list=[y])
+        np.testing.assert_allclose(got, ref, rtol=1e-6)
+        feed2 = {"x": feed["x"], "n": np.array([5], "int64")}      # the trip count is still a run-time value
+        (got2,) = exe.run(opt, feed=feed2, fetch_list=[y])
+        np.testing.assert_allclose(got2, 5 * np.exp(feed["x"]) ** 2, rtol=1e-5)
+    finally:
+        paddle.disable_static()
