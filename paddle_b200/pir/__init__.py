@@ -15,7 +15,8 @@ import torch
 
 from .._build import load as _load
 
-__all__ = ["Program", "PassManager", "translate_to_pir", "optimize", "default_passes", "DEFAULT_PATTERNS", "core_available"]
+__all__ = ["Program", "PassManager", "translate_to_pir", "optimize", "default_passes", "DEFAULT_PATTERNS", "core_available", "Value", "Operation", "Block", "global_block", "parse",
+           "register_op_impl", "lower"]
 
 
 def _native():
@@ -37,6 +38,140 @@ def Program():
 
 def parse(text):
     return _native().IrProgram.parse(text)
+
+
+# ------------------------------------------------------------------------------------------------ object views (paddle.pir Python API)
+class Value:
+    """View of one SSA value of a program (`paddle.pir.Value`): shape / dtype / defining op / users, replace_all_uses_with."""
+
+    __slots__ = ("_p", "id")
+
+    def __init__(self, program, vid):
+        self._p, self.id = program, int(vid)
+
+    def _info(self):
+        return self._p.value_info(self.id)
+
+    @property
+    def shape(self):
+        return list(self._info()["type"][1])
+
+    @property
+    def dtype(self):
+        return self._info()["type"][0]
+
+    @property
+    def name(self):
+        return self._info()["name"] or f"%{self.id}"
+
+    def is_block_argument(self):
+        return self._info()["def_op"] < 0
+
+    def get_defining_op(self):
+        d = self._info()["def_op"]
+        return None if d < 0 else Operation(self._p, d)
+
+    def all_used_ops(self):
+        return [Operation(self._p, o["id"]) for o in self._p.ops() if self.id in o["operands"]]
+
+    def use_count(self):
+        return self._p.use_counts()[self.id]
+
+    def use_empty(self):
+        return self.use_count() == 0
+
+    def replace_all_uses_with(self, other):
+        self._p.replace_all_uses(self.id, other.id if isinstance(other, Value) else int(other))
+
+    def __eq__(self, o):
+        return isinstance(o, Value) and o._p is self._p and o.id == self.id
+
+    def __hash__(self):
+        return hash((id(self._p), self.id))
+
+    def __repr__(self):
+        t = self._info()["type"]
+        return f"Value(%{self.id}: tensor<{'x'.join(str(d) for d in t[1])}{'x' if t[1] else ''}{t[0]}>)"
+
+
+class Operation:
+    """View of one operation (`paddle.pir.Operation`)."""
+
+    __slots__ = ("_p", "id")
+
+    def __init__(self, program, op_id):
+        self._p, self.id = program, int(op_id)
+
+    def _rec(self):
+        for o in self._p.ops():
+            if o["id"] == self.id:
+                return o
+        raise RuntimeError(f"operation {self.id} was erased")
+
+    def name(self):
+        return self._rec()["name"]
+
+    def attrs(self):
+        return dict(self._rec()["attrs"])
+
+    def num_operands(self):
+        return len(self._rec()["operands"])
+
+    def num_results(self):
+        return len(self._rec()["results"])
+
+    def operands_source(self):
+        return [Value(self._p, v) for v in self._rec()["operands"]]
+
+    def operand_source(self, i):
+        return Value(self._p, self._rec()["operands"][i])
+
+    def results(self):
+        return [Value(self._p, v) for v in self._rec()["results"]]
+
+    def result(self, i):
+        return Value(self._p, self._rec()["results"][i])
+
+    def num_regions(self):
+        return self._rec()["num_regions"]
+
+    def blocks(self):
+        return [Block(self._p.region(self.id, k)) for k in range(self.num_regions())]
+
+    def erase(self):
+        self._p.erase_op(self.id)
+
+    def __repr__(self):
+        r = self._rec()
+        return f"Operation({r['name']}, operands={r['operands']}, results={r['results']})"
+
+
+class Block:
+    """`program.global_block()`: the ordered operations and the block arguments (inputs / parameters)."""
+
+    def __init__(self, program):
+        self.program = program
+
+    @property
+    def ops(self):
+        return [Operation(self.program, o["id"]) for o in self.program.ops()]
+
+    def args(self):
+        return [Value(self.program, a[0]) for a in self.program.args()]
+
+    def kwargs(self):
+        return {a[2]: Value(self.program, a[0]) for a in self.program.args()}
+
+    def __len__(self):
+        return self.program.num_ops()
+
+    def __iter__(self):
+        return iter(self.ops)
+
+
+def global_block(program):
+    """Block view of an IR program (the native object has no Python subclass: `pir.global_block(p)` plays `p.global_block()`)."""
+    return Block(program)
 
 
 # (name, source ops, result ops): op = (op name, [input symbols], [output symbols], {attribute constraints / "$sym.attr" copies})

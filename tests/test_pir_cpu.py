@@ -310,3 +310,24 @@ def test_programs_with_run_time_control_flow_go_through_the_passes():
         np.testing.assert_allclose(got2, 5 * np.exp(feed["x"]) ** 2, rtol=1e-5)
     finally:
         paddle.disable_static()
+
+
+def test_object_views_walk_and_edit_a_program():
+    p, (x, w, b, t, y, z) = _mlp_ir()
+    blk = pir.global_block(p)
+    assert len(blk) == 5 and [o.name() for o in blk][:3] == ["pd_op.matmul", "pd_op.add", "pd_op.gelu"]
+    assert [v.name for v in blk.args()] == ["x", "w", "b"] and set(blk.kwargs()) == {"x", "w", "b"}
+    mm = blk.ops[0]
+    assert mm.num_operands() == 2 and mm.num_results() == 1 and mm.operand_source(0) == pir.Value(p, x)
+    out = mm.result(0)
+    assert out.shape == [4, 16] and out.dtype == "float32" and not out.is_block_argument() and pir.Value(p, x).is_block_argument()
+    assert out.get_defining_op().name() == "pd_op.matmul" and [o.name() for o in out.all_used_ops()] == ["pd_op.add"]
+    yv = pir.Value(p, y)
+    assert yv.use_count() == 2 and {o.name() for o in yv.all_used_ops()} == {"pd_op.gelu", "pd_op.exp"}
+    # manual rewrite through the views: gelu reads the matmul result directly, the add becomes dead
+    yv.replace_all_uses_with(out)
+    assert yv.use_empty()
+    blk.ops[1].erase()
+    pir.PassManager(["dce", "compact"], patterns=[]).run(p)
+    assert [o.name() for o in pir.global_block(p)] == ["pd_op.matmul", "pd_op.gelu"]
+    assert "Value(%" in repr(out) and "Operation(pd_op.matmul" in repr(pir.global_block(p).ops[0])
