@@ -1,4 +1,4 @@
-"""Autoregressive generation with a KV cache for the decoder-only models of this package (`LlamaForCausalLM`).
+"""Autoregressive generation with a KV cache for the decoder-only models of this package (`LlamaForCausalLM`, `MixtralForCausalLM`).
 
 Role parity: the serving path the reference builds out of `masked_multihead_attention` / `block_multihead_attention` +
 `FusedMultiTransformer` (python/paddle/incubate/nn/layer/fused_transformer.py) and PaddleNLP's `generate()`: prefill once, then one
@@ -75,25 +75,49 @@ def _attend_cache(q, kc, vc, lens, scale):
     return torch.einsum("bhs,bhsd->bhd", torch.softmax(s, -1), v).to(q.dtype)
 
 
-class LlamaGenerator:
-    """Prefill + decode over the sublayers of a `LlamaForCausalLM` (no tensor / pipeline parallelism: serve one replica per GPU)."""
+class DecoderAdapter:
+    """What generation needs from a decoder-only model of this package: embedding, decoder layers (each with `input_layernorm`, `self_attn`
+    = LlamaAttention, `post_attention_layernorm` and a feed-forward), the output head.  Llama (dense SwiGLU MLP) and Mixtral (MoE
+    feed-forward: routing is per token, so cached decoding equals recomputation) are supported."""
 
     def __init__(self, model):
         from . import llama as L
 
-        self.model, self.cfg = model, model.config
-        self.layers = list(model.llama.layers)
+        self.model, self.L = model, L
+        if hasattr(model, "llama"):
+            self.cfg = model.config
+            self.layers = list(model.llama.layers)
+            self.embed = model.llama.embedding
+            self.head = model.lm_head
+            self.ffn = lambda layer, x: layer.mlp.down_proj(L.KA.swiglu(layer.mlp.gate_up_proj(x)))
+        elif hasattr(model, "embed_tokens") and hasattr(model, "layers") and hasattr(list(model.layers)[0], "moe"):
+            self.cfg = model.cfg
+            self.layers = list(model.layers)
+            self.embed = model.embed_tokens
+            self.head = lambda h: model.lm_head(model.norm(h))
+            self.ffn = lambda layer, x: layer.moe(x)
+        else:
+            raise NotImplementedError(f"generation does not know the layout of {type(model).__name__}")
         at = self.layers[0].self_attn
         if at.mp != 1:
-            raise NotImplementedError("LlamaGenerator serves a single-rank replica (mp_degree 1)")
+            raise NotImplementedError("generation serves a single-rank replica (mp_degree 1)")
         self.nh, self.nkv, self.hd = at.num_heads, at.num_kv_heads, at.head_dim
-        self._rope = L.rope_cache
-        self._KR = L.KR
-        self._KA = L.KA
+
+
+class LlamaGenerator:
+    """Prefill + decode over the sublayers of a decoder-only model (`LlamaForCausalLM`, `MixtralForCausalLM`); no tensor / pipeline
+    parallelism: serve one replica per GPU."""
+
+    def __init__(self, model):
+        ad = DecoderAdapter(model)
+        self.ad, self.model, self.cfg, self.layers = ad, model, ad.cfg, ad.layers
+        self.nh, self.nkv, self.hd = ad.nh, ad.nkv, ad.hd
+        self._rope = ad.L.rope_cache
+        self._KR = ad.L.KR
 
     # -- one decoder layer on [B, S, hidden] with explicit positions; returns (h, k, v) with k, v [B, S, H_kv, D] (k rotated)
     def _layer(self, layer, h, cos, sin, position_ids, attend):
-        at, mlp = layer.self_attn, layer.mlp
+        at = layer.self_attn
         nh, nkv, hd = self.nh, self.nkv, self.hd
         x = layer.input_layernorm(h)
         qkv = _raw(self._KR.apply_rope_packed(at.qkv_proj(x), cos, sin, nh + nkv, nh + 2 * nkv, hd, position_ids, neox=True))
@@ -103,7 +127,7 @@ class LlamaGenerator:
         a = attend(q, k, v)                                               # [B, S, H, D]
         a = at.o_proj(_w(a.reshape(b, s, nh * hd)))
         x, h = layer.post_attention_layernorm(a, residual=h)
-        return h + mlp.down_proj(self._KA.swiglu(mlp.gate_up_proj(x))), k, v
+        return h + self.ad.ffn(layer, x), k, v
 
     @torch.no_grad()
     def prefill(self, input_ids, prompt_lens, cache):
@@ -112,7 +136,7 @@ class LlamaGenerator:
         ids = _raw(input_ids)
         b, s = ids.shape
         scale = 1.0 / math.sqrt(self.hd)
-        h = self.model.llama.embedding(_w(ids))
+        h = self.ad.embed(_w(ids))
         cos, sin = self._rope(self.cfg, _raw(h).device)
         pos = torch.arange(s, device=ids.device, dtype=torch.int64).unsqueeze(0).expand(b, s).contiguous()
 
@@ -128,7 +152,7 @@ class LlamaGenerator:
         cache.lens.copy_(prompt_lens.to(torch.int32))
         last = (prompt_lens.long() - 1).clamp(min=0)
         hl = _raw(h)[torch.arange(b, device=ids.device), last].unsqueeze(1)   # [B, 1, hidden]
-        return _raw(self.model.lm_head(_w(hl)))[:, 0]
+        return _raw(self.ad.head(_w(hl)))[:, 0]
 
     @torch.no_grad()
     def decode_step(self, tokens, cache):
@@ -136,7 +160,7 @@ class LlamaGenerator:
         ids = _raw(tokens).reshape(-1, 1)
         b = ids.shape[0]
         scale = 1.0 / math.sqrt(self.hd)
-        h = self.model.llama.embedding(_w(ids))
+        h = self.ad.embed(_w(ids))
         cos, sin = self._rope(self.cfg, _raw(h).device)
         pos = cache.lens.long().reshape(b, 1)
         for i, layer in enumerate(self.layers):
@@ -146,7 +170,7 @@ class LlamaGenerator:
 
             h, _, _ = self._layer(layer, h, cos, sin, pos, attend)
         cache.lens += 1
-        return _raw(self.model.lm_head(h))[:, 0]
+        return _raw(self.ad.head(h))[:, 0]
 
 
 def _sample(logits, do_sample, temperature, top_k, top_p, generator=None):

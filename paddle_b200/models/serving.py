@@ -57,15 +57,13 @@ class LLMEngine:
     """add_request() any time; step() runs one scheduler iteration (admit / preempt, one packed forward, one token per running sequence)."""
 
     def __init__(self, model, num_blocks=256, block_size=16, max_running=64, max_batch_tokens=8192):
-        from . import llama as L
+        from .generation import DecoderAdapter
 
-        self.model, self.cfg = model, model.config
         model.eval()
-        self.layers = list(model.llama.layers)
-        at = self.layers[0].self_attn
-        if at.mp != 1:
-            raise NotImplementedError("LLMEngine serves a single-rank replica (mp_degree 1)")
-        self.nh, self.nkv, self.hd = at.num_heads, at.num_kv_heads, at.head_dim
+        ad = DecoderAdapter(model)                 # Llama (dense) and Mixtral (MoE) layouts
+        self.ad, self.model, self.cfg, self.layers = ad, model, ad.cfg, ad.layers
+        self.nh, self.nkv, self.hd = ad.nh, ad.nkv, ad.hd
+        L = ad.L
         self.block_size, self.max_running, self.max_batch_tokens = int(block_size), int(max_running), int(max_batch_tokens)
         p0 = _raw(next(iter(model.parameters())))
         self.device, self.dtype = p0.device, p0.dtype
@@ -159,19 +157,19 @@ class LLMEngine:
         dec_t = torch.tensor(dec, dtype=torch.int32, device=dev)
         now_t = torch.tensor(n_new, dtype=torch.int32, device=dev)
         nh, nkv, hd = self.nh, self.nkv, self.hd
-        h = self.model.llama.embedding(_w(ids))
+        h = self.ad.embed(_w(ids))
         cos, sin = self._L.rope_cache(self.cfg, dev)
         for li, layer in enumerate(self.layers):
-            at, mlp = layer.self_attn, layer.mlp
+            at = layer.self_attn
             x = layer.input_layernorm(h)
             qkv = _raw(self._L.KR.apply_rope_packed(at.qkv_proj(x), cos, sin, nh + nkv, nh + 2 * nkv, hd, position_ids, neox=True))
             t = qkv.shape[1]
             out, _, _, _ = block_attention(qkv.reshape(t, (nh + 2 * nkv) * hd), self.key_cache[li], self.value_cache[li], enc_t, dec_t, now_t, cu, bt, self.block_size)
             a = at.o_proj(_w(_raw(out).reshape(1, t, nh * hd)))
             x, h = layer.post_attention_layernorm(a, residual=h)
-            h = h + mlp.down_proj(self._L.KA.swiglu(mlp.gate_up_proj(x)))
+            h = h + self.ad.ffn(layer, x)
         last = (cu[1:].long() - 1)
-        return _raw(self.model.lm_head(_w(_raw(h)[:, last])))[0]                             # [num_seqs, vocab]
+        return _raw(self.ad.head(_w(_raw(h)[:, last])))[0]                             # [num_seqs, vocab]
 
     def step(self):
         """One iteration.  Returns [(request id, new token, finished)] for every sequence that produced a token."""

@@ -76,3 +76,23 @@ def test_sampling_controls_and_eos():
     m.train()
     models.generate(m, ids, max_new_tokens=1)
     assert m.training is True                                  # the caller's mode is restored
+
+
+def test_mixtral_moe_generation_and_serving():
+    """The MoE feed-forward routes per token, so cached decoding (and continuous batching) reproduces full recomputation."""
+    paddle.seed(4)
+    cfg = models.mixtral_tiny()
+    m = models.MixtralForCausalLM(cfg)
+    m.eval()
+    ids = torch.randint(1, cfg.vocab_size, (2, 6))
+    ref = ids.clone()
+    for _ in range(5):
+        with torch.no_grad():
+            lg = m(ref.as_subclass(paddle.Tensor)).as_subclass(torch.Tensor)
+        ref = torch.cat([ref, lg[:, -1].argmax(-1, keepdim=True)], 1)
+    out = models.generate(m, ids, max_new_tokens=5).as_subclass(torch.Tensor)
+    assert torch.equal(out, ref)
+    eng = models.LLMEngine(m, num_blocks=32, block_size=4)
+    a, b = eng.add_request(ids[0].tolist(), 5), eng.add_request(ids[1].tolist(), 5)
+    res = eng.run_until_done()
+    assert res[a] == ref[0, 6:].tolist() and res[b] == ref[1, 6:].tolist()
