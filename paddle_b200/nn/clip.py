@@ -31,7 +31,11 @@ class ClipGradByValue(ClipGradBase):
             if g is None or not getattr(p, "need_clip", True):
                 out.append((p, g))
             else:
-                out.append((p, type(g)(g.rows, torch.clamp(g.merge().value, self.min, self.max), g.height) if _is_rows(g) else torch.clamp(g, self.min, self.max)))
+                if _is_rows(g):
+                    m = g.merge()                      # clip the summed rows, as the dense gradient would be
+                    out.append((p, type(g)(m.rows, torch.clamp(m.value, self.min, self.max), m.height)))
+                else:
+                    out.append((p, torch.clamp(g, self.min, self.max)))
         return out
 
 

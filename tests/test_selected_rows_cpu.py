@@ -105,3 +105,13 @@ def test_global_norm_clip_counts_merged_rows():
     moved = e.weight.numpy() - w0
     expect = -(sr.to_dense() * (0.5 / gn)).numpy()
     np.testing.assert_allclose(moved, expect, rtol=1e-4, atol=1e-6)
+
+
+def test_value_and_norm_clip_on_duplicate_rows():
+    sr = SelectedRows([2, 2, 5], torch.tensor([[3.0, -4.0], [3.0, -4.0], [0.5, 0.5]]), height=8)
+    p = paddle.to_tensor(np.zeros((8, 2), "float32"))
+    (_, c), = paddle.nn.ClipGradByValue(5.0)([(p, sr)])
+    assert c.rows.tolist() == [2, 5] and torch.equal(c.value, torch.tensor([[5.0, -5.0], [0.5, 0.5]]))     # rows are summed first (6, -8), then clipped
+    (_, n), = paddle.nn.ClipGradByNorm(1.0)([(p, sr)])
+    dense = sr.to_dense()
+    assert torch.allclose(n.to_dense(), dense / dense.norm(), atol=1e-6)
