@@ -1,4 +1,5 @@
-"""Autoregressive generation with a KV cache for the decoder-only models of this package (`LlamaForCausalLM`, `MixtralForCausalLM`).
+"""Autoregressive generation with a KV cache for the decoder-only models of this package (`LlamaForCausalLM`, `MixtralForCausalLM`,
+`GPTForCausalLM`).
 
 Role parity: the serving path the reference builds out of `masked_multihead_attention` / `block_multihead_attention` +
 `FusedMultiTransformer` (python/paddle/incubate/nn/layer/fused_transformer.py) and PaddleNLP's `generate()`: prefill once, then one
@@ -173,6 +174,77 @@ class LlamaGenerator:
         return _raw(self.ad.head(h))[:, 0]
 
 
+class GPTGenerator:
+    """Prefill + decode for `GPTForCausalLM` (models/gpt.py): learned absolute positions, LayerNorm, packed [3, H, D] qkv projection with
+    bias, GELU MLP, LM head tied to the token embedding.  Same interface as LlamaGenerator."""
+
+    def __init__(self, model):
+        self.model, self.cfg = model, model.cfg
+        self.layers = list(model.gpt.blocks)
+        self.nh = self.nkv = self.cfg.num_attention_heads
+        self.hd = self.cfg.head_dim
+
+    def _layer(self, blk, h, attend):
+        from ..nn import functional as F
+
+        b, s, hid = h.shape
+        qkv = _raw(blk.qkv(blk.ln1(h))).reshape(b, s, 3, self.nh, self.hd)
+        a = attend(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2])
+        h = h + blk.proj(_w(a.reshape(b, s, hid)))
+        return h + blk.fc2(F.gelu(blk.fc1(blk.ln2(h)))), qkv[:, :, 1], qkv[:, :, 2]
+
+    def _embed(self, ids, pos):
+        g = self.model.gpt
+        if int(pos.max()) >= self.cfg.max_position_embeddings:
+            raise ValueError(f"position {int(pos.max())} is outside the model's {self.cfg.max_position_embeddings} learned positions")
+        return g.wte(_w(ids)) + g.wpe(_w(pos))
+
+    def _head(self, h):
+        g = self.model.gpt
+        return _raw(g.wte(g.ln_f(h), project=True))
+
+    @torch.no_grad()
+    def prefill(self, input_ids, prompt_lens, cache):
+        ids = _raw(input_ids)
+        b, s = ids.shape
+        scale = 1.0 / math.sqrt(self.hd)
+        h = self._embed(ids, torch.arange(s, device=ids.device, dtype=torch.int64).unsqueeze(0).expand(b, s))
+
+        def attend(q, k, v):
+            o = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True, scale=scale)
+            return o.transpose(1, 2)
+
+        for i, blk in enumerate(self.layers):
+            h, k, v = self._layer(blk, h, attend)
+            cache.write_prefix(i, k, v)
+        cache.lens.copy_(prompt_lens.to(torch.int32))
+        last = (prompt_lens.long() - 1).clamp(min=0)
+        hl = _raw(h)[torch.arange(b, device=ids.device), last].unsqueeze(1)
+        return self._head(_w(hl))[:, 0]
+
+    @torch.no_grad()
+    def decode_step(self, tokens, cache):
+        ids = _raw(tokens).reshape(-1, 1)
+        b = ids.shape[0]
+        scale = 1.0 / math.sqrt(self.hd)
+        h = self._embed(ids, cache.lens.long().reshape(b, 1))
+        for i, blk in enumerate(self.layers):
+            def attend(q, k, v, i=i):
+                cache.append(i, k[:, 0], v[:, 0])
+                return _attend_cache(q[:, 0], cache.k[i], cache.v[i], cache.lens + 1, scale).unsqueeze(1)
+
+            h, _, _ = self._layer(blk, h, attend)
+        cache.lens += 1
+        return self._head(h)[:, 0]
+
+
+def make_generator(model):
+    """The generator for a decoder-only model of this package."""
+    if hasattr(model, "gpt") and hasattr(model.gpt, "blocks"):
+        return GPTGenerator(model)
+    return LlamaGenerator(model)
+
+
 def _sample(logits, do_sample, temperature, top_k, top_p, generator=None):
     if not do_sample or temperature == 0.0:
         return logits.argmax(-1)
@@ -203,7 +275,7 @@ def generate(model, input_ids, max_new_tokens=32, prompt_lens=None, do_sample=Fa
         dev = ids.device
         lens = torch.full((b,), s, dtype=torch.int64, device=dev) if prompt_lens is None else _raw(prompt_lens).to(dev).long()
         total = int(max_length) if max_length is not None else s + int(max_new_tokens)
-        gen = LlamaGenerator(model)
+        gen = make_generator(model)
         p0 = next(iter(model.parameters()))
         cache = KVCache(len(gen.layers), b, gen.nkv, total, gen.hd, _raw(p0).dtype, dev)
         out = torch.full((b, total), int(pad_token_id), dtype=torch.int64, device=dev)

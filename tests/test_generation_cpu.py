@@ -96,3 +96,25 @@ def test_mixtral_moe_generation_and_serving():
     a, b = eng.add_request(ids[0].tolist(), 5), eng.add_request(ids[1].tolist(), 5)
     res = eng.run_until_done()
     assert res[a] == ref[0, 6:].tolist() and res[b] == ref[1, 6:].tolist()
+
+
+def test_gpt_generation_matches_full_recompute():
+    """GPT layout: learned positions, LayerNorm, tied head.  Greedy KV-cache decoding equals recomputing the sequence; ragged prompts."""
+    paddle.seed(5)
+    cfg = models.gpt_tiny()
+    m = models.GPTForCausalLM(cfg)
+    m.eval()
+    ids = torch.randint(1, cfg.vocab_size, (2, 7))
+    ref = ids.clone()
+    for _ in range(6):
+        with torch.no_grad():
+            lg = m(ref.as_subclass(paddle.Tensor)).as_subclass(torch.Tensor)
+        ref = torch.cat([ref, lg[:, -1].argmax(-1, keepdim=True)], 1)
+    assert torch.equal(models.generate(m, ids, max_new_tokens=6).as_subclass(torch.Tensor), ref)
+    batch = ids.clone()
+    batch[1, 4:] = 0
+    out = models.generate(m, batch, max_new_tokens=4, prompt_lens=torch.tensor([7, 4])).as_subclass(torch.Tensor)
+    solo = models.generate(m, ids[1:2, :4], max_new_tokens=4).as_subclass(torch.Tensor)
+    assert torch.equal(out[1, :8], solo[0])
+    with pytest.raises(ValueError):
+        models.generate(m, ids, max_new_tokens=cfg.max_position_embeddings)
