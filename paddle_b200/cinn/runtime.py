@@ -1,0 +1,140 @@
+"""Compile, cache and launch generated kernels.
+
+A kernel is compiled once per (source, target): `nvcc -gencode arch=compute_100a,code=sm_100a` into a small shared object whose `extern "C"`
+launcher is called through ctypes with raw device pointers and the current CUDA stream; the host target is `g++ -O2`.  Objects are cached
+in-tree under `paddle_b200/_build_cache/cinn/` (keyed by the hash of the source), so a warm cache travels with the package.
+Role parity: CINN's runtime module / NVRTC compile cache (paddle/cinn/runtime, paddle/cinn/backends/nvrtc)."""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import os
+import shutil
+import subprocess
+import threading
+
+import torch
+
+from ..tensor import Tensor
+from . import codegen
+
+_CACHE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "_build_cache", "cinn")
+_LOCK = threading.Lock()
+_LOADED = {}
+_TORCH_DT = {"float32": torch.float32, "float64": torch.float64, "float16": torch.float16, "bfloat16": torch.bfloat16, "int32": torch.int32, "int64": torch.int64,
+             "bool": torch.bool, "uint8": torch.uint8}
+
+stats = {"compiled": 0, "cache_hits": 0, "launches": 0}
+
+
+class CompileError(RuntimeError):
+    pass
+
+
+def _nvcc():
+    return shutil.which("nvcc") or ("/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else None)
+
+
+def compile_source(src, target, keep_source=True):
+    """-> path of the shared object."""
+    tag = hashlib.sha1((target + "\0" + src).encode()).hexdigest()[:20]
+    os.makedirs(_CACHE, exist_ok=True)
+    so = os.path.join(_CACHE, f"k_{target}_{tag}.so")
+    if os.path.exists(so):
+        stats["cache_hits"] += 1
+        return so
+    ext = "cu" if target == "cuda" else "cc"
+    path = os.path.join(_CACHE, f"k_{target}_{tag}.{ext}")
+    with open(path, "w") as f:
+        f.write(src)
+    tmp = so + f".tmp{os.getpid()}"
+    if target == "cuda":
+        nvcc = _nvcc()
+        if nvcc is None:
+            raise CompileError("nvcc not found: generated CUDA kernels cannot be built")
+        cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--cudart", "shared", "-shared", "-Xcompiler", "-fPIC", "-o", tmp, path]
+    else:
+        cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fno-math-errno", "-o", tmp, path]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise CompileError(f"{' '.join(cmd)}\n{r.stderr[-4000:]}")
+    os.replace(tmp, so)
+    stats["compiled"] += 1
+    if not keep_source:
+        os.remove(path)
+    return so
+
+
+def _load(so):
+    with _LOCK:
+        lib = _LOADED.get(so)
+        if lib is None:
+            lib = _LOADED[so] = ctypes.CDLL(so)
+        return lib
+
+
+class FusedKernel:
+    """Callable for one fusion group: tensors in operand order -> result tensor(s) in result order."""
+
+    def __init__(self, spec):
+        self.spec = spec
+        self._fn = {}
+        self.sources = {}
+        self.launches = 0
+
+    def source(self, target):
+        if target not in self.sources:
+            self.sources[target] = codegen.cuda_source(self.spec) if target == "cuda" else codegen.host_source(self.spec)
+        return self.sources[target]
+
+    def build(self, target):
+        if target not in self._fn:
+            lib = _load(compile_source(self.source(target), target))
+            if target == "cuda":
+                fn = lib.cinn_launch
+                fn.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int]
+            else:
+                fn = lib.cinn_run
+                fn.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]
+            fn.restype = ctypes.c_int
+            self._fn[target] = fn
+        return self._fn[target]
+
+    def __call__(self, *tensors, **_attrs):
+        spec = self.spec
+        if len(tensors) != len(spec.inputs):
+            raise TypeError(f"{spec.name}: expected {len(spec.inputs)} tensors, got {len(tensors)}")
+        raw = []
+        for t, n in zip(tensors, spec.inputs):
+            t = t.as_subclass(torch.Tensor) if type(t) is not torch.Tensor else t
+            if tuple(t.shape) != n.shape or t.dtype != _TORCH_DT[n.dtype]:
+                raise TypeError(f"{spec.name}: operand is {list(t.shape)} {t.dtype}, the kernel was generated for {list(n.shape)} {n.dtype}")
+            raw.append(t.detach().contiguous())
+        dev = raw[0].device if raw else torch.device("cpu")
+        if any(t.device != dev for t in raw):
+            raise TypeError(f"{spec.name}: operands live on different devices")
+        target = "cuda" if dev.type == "cuda" else "host"
+        fn = self.build(target)
+        outs = [torch.empty(n.shape, dtype=_TORCH_DT[n.dtype], device=dev) for n in spec.outputs]
+        ins_p = (ctypes.c_void_p * max(len(raw), 1))(*[t.data_ptr() for t in raw])
+        outs_p = (ctypes.c_void_p * len(outs))(*[t.data_ptr() for t in outs])
+        if target == "cuda":
+            with torch.cuda.device(dev):
+                aligned = all(t.data_ptr() % 16 == 0 for t in raw + outs)
+                rc = fn(ins_p, outs_p, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), int(aligned))
+            if rc != 0:
+                raise RuntimeError(f"{spec.name}: kernel launch failed with CUDA error {rc}")
+        else:
+            rc = fn(ins_p, outs_p)
+            if rc != 0:
+                raise RuntimeError(f"{spec.name}: host kernel returned {rc}")
+        self.launches += 1
+        stats["launches"] += 1
+        res = [o.as_subclass(Tensor) for o in outs]
+        return res[0] if len(res) == 1 else tuple(res)
+
+
+def clear_cache():
+    if os.path.isdir(_CACHE):
+        shutil.rmtree(_CACHE)
+    _LOADED.clear()

@@ -888,6 +888,18 @@ void bind_ir(py::module_& m) {
       .def("replace_all_uses", &Program::replace_all_uses)
       .def("replacements", [](const Program& p) { return p.replaced; })
       .def("erase_op", [](Program& p, int op_id) { p.ops.at(op_id).erased = true; })
+      .def("set_insertion_point_after", [](Program& p, int op_id) {
+        // ops added from now on are placed right after `op_id` in program order (in the order they are added)
+        for (size_t i = 0; i < p.order.size(); ++i)
+          if (p.order[i] == op_id) { p.insert_at = (int)i + 1; return; }
+        throw std::runtime_error("ir: unknown op " + std::to_string(op_id));
+      })
+      .def("set_insertion_point_before", [](Program& p, int op_id) {
+        for (size_t i = 0; i < p.order.size(); ++i)
+          if (p.order[i] == op_id) { p.insert_at = (int)i; return; }
+        throw std::runtime_error("ir: unknown op " + std::to_string(op_id));
+      })
+      .def("reset_insertion_point", [](Program& p) { p.insert_at = -1; })
       .def("clone", [](const Program& p) {
         Out os;
         print_program(p, os, 0);

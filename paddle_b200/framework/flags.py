@@ -11,6 +11,7 @@ _FLAGS = {
     "FLAGS_b200_p2p_collectives": True,    # fused compute+collective kernels over peer memory
     "FLAGS_b200_gemm_backend": "tcgen05",  # "tcgen05" | "cublas"
     "FLAGS_b200_decode_kernel": False,     # models.generation: decode steps attend through csrc/decode_attention.cu (CUDA, head_dim 128, fp16 / bf16)
+    "FLAGS_use_cinn": False,               # pir.optimize: fuse elementwise / reduction chains into generated sm_100a kernels (paddle_b200.cinn)
     "FLAGS_enable_pir_api": False,         # static Executor: run programs through the native IR pass pipeline (paddle_b200.pir) before replay
     "FLAGS_b200_fp8_block_scaled": False,  # with FLAGS_b200_fp8_linear: OCP MX scaling (one E8M0 scale per 32 k, applied by tcgen05 block_scale MMAs) instead of per-tensor
     "FLAGS_b200_fp8_linear": False,        # nn.Linear / F.linear run as fp8 tcgen05 GEMMs (per-tensor scaling, e4m3 fwd / e5m2 grads)

@@ -65,6 +65,8 @@ class StaticFunction:
         except Exception:  # noqa: BLE001  (source unavailable, exotic syntax): the function runs as written
             fn = self._dygraph_fn
         self._fn, self._layer, self._input_spec = fn, layer, input_spec
+        self._backend = backend.upper() if isinstance(backend, str) else None
+        self._cinn = {}                 # input signature -> (executor, program, feed names, fetch targets, single result?) or None
         self._graphs = {}
         self._train_graphs = {}
         self._warm = {}
@@ -132,9 +134,65 @@ class StaticFunction:
         ts = [a for a in list(args) + list(kwargs.values()) if isinstance(a, torch.Tensor)]
         return bool(ts) and all(t.is_cuda for t in ts)
 
+    # ---- backend="CINN": trace -> IR passes -> fused generated kernels (paddle_b200.cinn); no-grad calls only ------------------------------
+    def _cinn_entry(self, args):
+        from .. import cinn, static
+
+        prog = static.Program()
+        fwd = None
+        if self._layer is not None:
+            fwd = self._layer.__dict__.get("forward")
+            if isinstance(fwd, StaticFunction):
+                self._layer.__dict__.pop("forward", None)
+        try:
+            with static.program_guard(prog), torch.no_grad():
+                ins, call = [], []
+                for i, a in enumerate(args):
+                    if isinstance(a, torch.Tensor):
+                        v = static.data(f"x{i}", list(a.shape), str(a.dtype).replace("torch.", ""))
+                        ins.append(v)
+                        call.append(v)
+                    else:
+                        call.append(a)
+                out = self._fn(*call)
+        finally:
+            if isinstance(fwd, StaticFunction):
+                self._layer.forward = fwd
+        outs = list(out) if isinstance(out, (list, tuple)) else [out]
+        if not outs or not all(isinstance(o, torch.Tensor) and id(o) in prog._fetch_alias for o in outs):
+            return None                                           # results that are not values of the program: run as written
+        infer = prog.clone(for_test=True)
+        new, report = cinn.compile_program(infer, outs)
+        return static.Executor(), new, [v.name for v in ins], outs, not isinstance(out, (list, tuple)), report
+
+    def _call_cinn(self, args):
+        key = _sig(args, {})
+        if key not in self._cinn:
+            try:
+                self._cinn[key] = self._cinn_entry(args)
+            except Exception as e:  # noqa: BLE001  (untraceable function): eager
+                if os.environ.get("B200_JIT_DEBUG"):
+                    raise
+                self._cinn[key] = None
+                self._cinn_error = e
+        entry = self._cinn[key]
+        if entry is None:
+            return self._fn(*args)
+        exe, prog, feeds, fetch, single, _ = entry
+        res = exe.run(prog, feed=dict(zip(feeds, [a for a in args if isinstance(a, torch.Tensor)])), fetch_list=fetch, return_numpy=False)
+        res = [o.as_subclass(Tensor) if isinstance(o, torch.Tensor) else o for o in res]
+        return res[0] if single else res
+
+    def cinn_report(self, *args):
+        """FusionResult of the program compiled for these arguments (None when it was not compiled)."""
+        e = self._cinn.get(_sig(args, {}))
+        return None if e is None else e[5]
+
     def __call__(self, *args, **kwargs):
         if not _enabled[0] or getattr(self._dygraph_fn, "_not_to_static", False):
             return self._dygraph_fn(*args, **kwargs)
+        if self._backend == "CINN" and not kwargs and (not torch.is_grad_enabled() or not _needs_grad(self, args)):
+            return self._call_cinn(args)
         if self._can_train_graph(args, kwargs):
             key = ("train",) + _sig(args, kwargs)
             entry = self._train_graphs.get(key, False)
@@ -222,6 +280,12 @@ def _clone_tree(o):
     if isinstance(o, dict):
         return {k: _clone_tree(v) for k, v in o.items()}
     return o
+
+
+def _needs_grad(sf, args):
+    if any(isinstance(a, torch.Tensor) and a.requires_grad for a in args):
+        return True
+    return sf._layer is not None and sf._layer.training and any(not p.stop_gradient for p in sf._layer.parameters())
 
 
 def to_static(function=None, input_spec=None, build_strategy=None, backend=None, **kwargs):

@@ -565,8 +565,10 @@ def lower(tr, pm=None):
     return out
 
 
-def optimize(program, fetch_list=None, passes=None, patterns=None, return_report=False):
-    """Run a pass pipeline over a recorded static Program and return the optimised Program (same feeds, same fetch targets)."""
+def optimize(program, fetch_list=None, passes=None, patterns=None, return_report=False, cinn=None):
+    """Run a pass pipeline over a recorded static Program and return the optimised Program (same feeds, same fetch targets).
+    `cinn`: True / dict of `cinn.fuse` options - after the passes, fusible elementwise / reduction chains become generated kernels
+    (default: FLAGS_use_cinn)."""
     fetch_vids = None
     if fetch_list is not None:
         fetch_vids = []
@@ -579,6 +581,17 @@ def optimize(program, fetch_list=None, passes=None, patterns=None, return_report
     tr = translate_to_pir(program, fetch_vids)
     pm = PassManager(passes, patterns)
     report = pm.run(tr.ir)
+    if cinn is None:
+        from ..framework.flags import flag
+
+        cinn = bool(flag("FLAGS_use_cinn", False))
+    if cinn:
+        from ..cinn import fuse as _cinn_fuse
+
+        fr = _cinn_fuse(tr, **(cinn if isinstance(cinn, dict) else {}))
+        report = list(report) + [("cinn_fusion", len(fr.groups))]
     new = lower(tr, pm)
     new.__dict__["_pir_report"] = report
+    if cinn:
+        new.__dict__["_cinn_report"] = fr
     return (new, report) if return_report else new

@@ -1,0 +1,261 @@
+"""paddle_b200.cinn: fusion groups, generated kernels (run through the host target here; the CUDA source of every kernel must also generate,
+and a sample is cross-compiled with nvcc for sm_100a), numerics vs the unfused program."""
+import shutil
+
+import numpy as np
+import pytest
+import torch
+
+import paddle_b200 as paddle
+from paddle_b200 import cinn, static
+
+pytestmark = pytest.mark.skipif(not cinn.is_available(), reason="native IR core not built")
+F = paddle.nn.functional
+
+
+def _run_both(build, feeds, rtol=1e-5, atol=1e-6, expect_kernels=None, expect_fused=None):
+    """build(**placeholders) -> fetch list.  Returns the FusionResult; asserts fused == unfused."""
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            ph = {k: static.data(k, list(v.shape), str(v.dtype)) for k, v in feeds.items()}
+            fetch = build(**ph)
+            fetch = list(fetch) if isinstance(fetch, (list, tuple)) else [fetch]
+        new, rep = cinn.compile_program(main, fetch)
+        exe = static.Executor()
+        a = exe.run(main, feed=feeds, fetch_list=fetch)
+        b = exe.run(new, feed=feeds, fetch_list=fetch)
+    finally:
+        paddle.disable_static()
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and x.dtype == y.dtype
+        np.testing.assert_allclose(np.asarray(y, dtype=np.float64), np.asarray(x, dtype=np.float64), rtol=rtol, atol=atol)
+    if expect_kernels is not None:
+        assert len(rep.groups) == expect_kernels, (rep, rep.rejected)
+    if expect_fused is not None:
+        assert sum(len(g["ops"]) for g in rep.groups) == expect_fused, [g["ops"] for g in rep.groups]
+    for g in rep.groups:
+        assert "__global__" in g["kernel"].source("cuda")
+    return rep
+
+
+def test_elementwise_chain_with_broadcasts_is_one_kernel():
+    rng = np.random.default_rng(0)
+    x, b, c = rng.standard_normal((6, 5, 16), dtype=np.float32), rng.standard_normal((16,), dtype=np.float32), rng.standard_normal((6, 1, 1), dtype=np.float32)
+    r = rng.standard_normal((5, 1), dtype=np.float32)
+
+    def build(x, b, c, r):
+        y = paddle.tanh(x * b + c) * 0.5 - r
+        y = paddle.maximum(y, paddle.abs(x)) / (1.0 + paddle.exp(-y))
+        return paddle.where(y > 0.25, y, 2.0 - y * y)
+
+    rep = _run_both(build, dict(x=x, b=b, c=c, r=r), expect_kernels=1)
+    g = rep.groups[0]
+    assert g["kind"] == "elementwise" and g["inputs"] == 4 and g["outputs"] == 1 and len(g["ops"]) >= 10
+    assert "_vec4" in g["kernel"].source("cuda")                      # 16 columns: the 4-wide variant exists
+
+
+def test_softmax_and_normalisation_chains_become_row_kernels():
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((3, 7, 40), dtype=np.float32)
+    w, b = rng.standard_normal((40,), dtype=np.float32), rng.standard_normal((40,), dtype=np.float32)
+
+    def layer_norm_by_hand(x, w, b):
+        mu = x.mean(-1, keepdim=True)
+        xc = x - mu
+        var = (xc * xc).mean(-1, keepdim=True)
+        return xc * paddle.rsqrt(var + 1e-5) * w + b
+
+    rep = _run_both(layer_norm_by_hand, dict(x=x, w=w, b=b), rtol=2e-5, atol=2e-6, expect_kernels=1)
+    assert rep.groups[0]["kind"] == "reduce"
+    src = rep.groups[0]["kernel"].source("cuda")
+    assert "cinn_warp_reduce" in src and "c" in src                  # 40 columns: one warp per row, centred input kept in registers
+
+    def rms_then_softmax(x, w):
+        ms = (x * x).mean(-1, keepdim=True)
+        y = x * paddle.rsqrt(ms + 1e-6) * w
+        return F.softmax(y * 0.7, -1), F.log_softmax(y, -1)
+
+    rep = _run_both(rms_then_softmax, dict(x=x, w=w), rtol=2e-5, atol=2e-6, expect_kernels=1)
+    assert rep.groups[0]["outputs"] == 2
+
+
+def test_row_results_and_nonkeepdim_reductions():
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((9, 33), dtype=np.float32)
+
+    def build(x):
+        e = paddle.exp(x - x.amax(-1, keepdim=True))
+        s = e.sum(-1)                                   # [9]: a per-row result that leaves the group
+        lse = paddle.log(s) + x.amax(-1)
+        return e / e.sum(-1, keepdim=True), lse, (x * x).sum(-1, keepdim=True)
+
+    rep = _run_both(build, dict(x=x), rtol=2e-5, atol=2e-6)
+    assert sum(g["kind"] == "reduce" for g in rep.groups) >= 1
+    assert sum(len(g["ops"]) for g in rep.groups) >= 8
+
+
+def test_long_rows_use_the_block_schedule():
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((3, 3000), dtype=np.float32)
+    rep = _run_both(lambda x: F.softmax(x * 1.5 + 0.1, -1), dict(x=x), rtol=2e-5, atol=1e-7, expect_kernels=1)
+    assert "cinn_block_reduce" in rep.groups[0]["kernel"].source("cuda")
+    y = rng.standard_normal((2, 9000), dtype=np.float32)
+    rep = _run_both(lambda y: F.softmax(y * 1.5 + 0.1, -1), dict(y=y), rtol=2e-5, atol=1e-7, expect_kernels=1)
+    assert "_Pragma" not in rep.groups[0]["kernel"].source("cuda").split("__global__")[-1]       # too long for the register cache: plain column loops
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16", "float64"])
+def test_other_float_types(dtype):
+    rng = np.random.default_rng(4)
+    td = getattr(torch, dtype)
+    x = torch.from_numpy(rng.standard_normal((8, 24))).to(td)
+    w = torch.from_numpy(rng.standard_normal((24,))).to(td)
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            xv, wv = static.data("x", [8, 24], dtype), static.data("w", [24], dtype)
+            y = F.gelu(xv * wv) + F.silu(xv)
+            out = F.softmax(y, -1) * wv
+        new, rep = cinn.compile_program(main, [out])
+        exe = static.Executor()
+        b = exe.run(new, feed={"x": x, "w": w}, fetch_list=[out], return_numpy=False)[0].as_subclass(torch.Tensor)
+    finally:
+        paddle.disable_static()
+    assert len(rep.groups) == 1 and b.dtype == td
+    xf, wf = x.double(), w.double()
+    ref = torch.softmax(torch.nn.functional.gelu(xf * wf) + torch.nn.functional.silu(xf), -1) * wf
+    tol = {"bfloat16": 2e-2, "float16": 3e-3, "float64": 1e-12}[dtype]
+    assert torch.allclose(b.double(), ref, rtol=tol, atol=tol)        # ONE rounding at the store: closer to fp64 than the per-op rounded eager chain
+
+
+def test_casts_compares_and_integer_inputs():
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((4, 12), dtype=np.float32)
+    k = rng.integers(-3, 4, size=(4, 12)).astype(np.int64)
+    m = rng.integers(0, 2, size=(12,)).astype(bool)
+
+    def build(x, k, m):
+        y = x * k.astype("float32") + 1.0
+        z = paddle.where(m, y, -y)
+        return z.astype("float16"), (z >= 0.5), paddle.clip(z, -1.0, 1.0)
+
+    rep = _run_both(build, dict(x=x, k=k, m=m), rtol=1e-3, atol=1e-3)
+    assert len(rep.groups) == 1 and rep.groups[0]["outputs"] == 3
+
+
+def test_groups_are_cut_at_ops_that_are_not_generated():
+    rng = np.random.default_rng(6)
+    x, w = rng.standard_normal((8, 16), dtype=np.float32), rng.standard_normal((16, 16), dtype=np.float32)
+
+    def build(x, w):
+        a = paddle.exp(x * 0.1) + 1.0                      # group 1
+        h = paddle.matmul(a, w)                            # stays a GEMM
+        g = F.relu(h) * 2.0 - a                            # group 2 reads the GEMM and group 1's value
+        return g, a
+
+    rep = _run_both(build, dict(x=x, w=w), rtol=1e-5, atol=1e-5, expect_kernels=2)
+    assert all("matmul" not in g["ops"] for g in rep.groups)
+
+
+def test_a_single_op_is_left_alone_and_inplace_spellings_are_skipped():
+    x = np.random.default_rng(7).standard_normal((4, 4)).astype(np.float32)
+    rep = _run_both(lambda x: paddle.exp(x), dict(x=x), expect_kernels=0)
+    assert rep.groups == []
+
+
+def test_to_static_backend_cinn():
+    class Head(paddle.nn.Layer):
+        def __init__(self):
+            super().__init__()
+            self.fc = paddle.nn.Linear(32, 48)
+
+        def forward(self, x):
+            h = self.fc(x)
+            h = F.gelu(h) * 1.702 + paddle.tanh(h)
+            return F.softmax(h - h.mean(-1, keepdim=True), -1)
+
+    paddle.seed(0)
+    net = Head()
+    net.eval()
+    x = paddle.randn([5, 32])
+    with paddle.no_grad():
+        ref = net(x)
+    fast = paddle.jit.to_static(net, backend="CINN")
+    with paddle.no_grad():
+        out = fast(x)
+        out2 = fast(x)
+    rep = fast.forward.cinn_report(x)
+    assert rep is not None and len(rep.groups) == 1 and rep.groups[0]["kind"] == "reduce"
+    assert rep.groups[0]["kernel"].launches == 2
+    np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(out2.numpy(), ref.numpy(), rtol=2e-5, atol=1e-6)
+    y = paddle.randn([3, 32])                                      # another signature: compiled separately
+    with paddle.no_grad():
+        np.testing.assert_allclose(fast(y).numpy(), net(y).numpy(), rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not on PATH")
+def test_generated_cuda_cross_compiles_for_sm100a():
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((4, 64), dtype=np.float32).astype(np.float32)
+    h = torch.from_numpy(x).to(torch.bfloat16)
+
+    rep = _run_both(lambda x: F.softmax(paddle.tanh(x) * 3.0, -1), dict(x=x), rtol=2e-5, atol=1e-7, expect_kernels=1)
+    so = cinn.nvcc_check(rep.groups[0]["kernel"])
+    assert so.endswith(".so")
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            xv = static.data("x", [4, 64], "bfloat16")
+            out = F.silu(xv) * xv + 1.0
+        new, rep = cinn.compile_program(main, [out])
+    finally:
+        paddle.disable_static()
+    assert len(rep.groups) == 1
+    assert cinn.nvcc_check(rep.groups[0]["kernel"]).endswith(".so")
+    del h
+
+
+# ---- random programs: whatever the grouping decides, the fused program must equal the unfused one -----------------------------------------
+def _bshape(rng, full):
+    nd = int(rng.integers(0, len(full) + 1))
+    sh = list(full[len(full) - nd:])
+    return [1 if rng.random() < 0.4 else d for d in sh]
+
+
+_UN = [paddle.tanh, paddle.exp, paddle.abs, F.sigmoid, F.relu, paddle.sin, lambda v: v * v, lambda v: -v, lambda v: 1.0 - v, lambda v: 2.0 / (paddle.abs(v) + 1.0), F.silu, F.gelu]
+_BI = [lambda a, b: a + b, lambda a, b: a - b, lambda a, b: a * b, paddle.maximum, paddle.minimum, lambda a, b: a / (paddle.abs(b) + 1.5),
+       lambda a, b: paddle.where(a > b, a, b * 0.5)]
+_RED = [lambda v: v.sum(-1, keepdim=True), lambda v: v.mean(-1, keepdim=True), lambda v: v.amax(-1, keepdim=True), lambda v: v.amin(-1, keepdim=True)]
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_programs(seed):
+    rng = np.random.default_rng(1000 + seed)
+    full = [int(rng.integers(1, 7)) for _ in range(int(rng.integers(1, 5)))]
+    full[-1] = int(rng.choice([1, 3, 4, 8, 33, 40, 300]))
+    shapes = [full] + [_bshape(rng, full) for _ in range(int(rng.integers(0, 4)))]
+    feeds = {f"i{k}": rng.standard_normal(s).astype(np.float32) for k, s in enumerate(shapes)}
+
+    def build(**ph):
+        ph = list(ph.values())
+        vals, fulls = list(ph), [ph[0]]
+        for _ in range(int(rng.integers(3, 14))):
+            r = rng.random()
+            if r < 0.4:
+                v = _UN[rng.integers(len(_UN))](vals[rng.integers(len(vals))])
+            elif r < 0.85:
+                a = fulls[rng.integers(len(fulls))] if rng.random() < 0.7 else vals[rng.integers(len(vals))]
+                v = _BI[rng.integers(len(_BI))](a, vals[rng.integers(len(vals))])
+            else:
+                v = _RED[rng.integers(len(_RED))](fulls[rng.integers(len(fulls))])
+            vals.append(v)
+            if list(v.shape) == full:
+                fulls.append(v)
+        return [vals[-1]] + [vals[int(rng.integers(len(ph), len(vals)))] for _ in range(int(rng.integers(0, 2)))]
+
+    _run_both(build, feeds, rtol=2e-4, atol=2e-5)

@@ -1,0 +1,94 @@
+"""Generated (paddle_b200.cinn) kernels on the device vs an fp32 PyTorch reference.
+
+This file sorts last on purpose and its tests are non-strict xfail: the generated CUDA was cross-compiled for sm_100a and its bodies were
+checked through the host target (tests/test_cinn_cpu.py), but the launch path (ctypes launcher on the current stream, vector variants,
+shuffle / shared-memory reductions, register row cache) had no hardware run when it was written.  A pass shows up as XPASS."""
+import pytest
+import torch
+
+import paddle_b200 as paddle
+from paddle_b200 import cinn, static
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run of the generated-kernel launch path")]
+F = paddle.nn.functional
+
+
+def _fused(build, feeds):
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            ph = {k: static.data(k, list(v.shape), str(v.dtype).replace("torch.", "")) for k, v in feeds.items()}
+            fetch = build(**ph)
+            fetch = list(fetch) if isinstance(fetch, (list, tuple)) else [fetch]
+        new, rep = cinn.compile_program(main, fetch)
+        out = static.Executor().run(new, feed=feeds, fetch_list=fetch, return_numpy=False)
+    finally:
+        paddle.disable_static()
+    torch.cuda.synchronize()
+    return [o.as_subclass(torch.Tensor) for o in out], rep
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2), (torch.float16, 3e-3)])
+def test_elementwise_vec4_and_scalar_variants(dtype, tol):
+    torch.manual_seed(0)
+    x = torch.randn(64, 12, 256, device="cuda").to(dtype)
+    b = torch.randn(256, device="cuda").to(dtype)
+    g = torch.randn(64, 1, 1, device="cuda").to(dtype)
+
+    def build(x, b, g):
+        return F.gelu(x * b + g) * paddle.tanh(x) - 0.5
+
+    (out,), rep = _fused(build, dict(x=x, b=b, g=g))
+    assert len(rep.groups) == 1 and rep.groups[0]["kernel"].launches == 1
+    xf, bf, gf = x.float(), b.float(), g.float()
+    ref = torch.nn.functional.gelu(xf * bf + gf) * torch.tanh(xf) - 0.5
+    assert out.dtype == dtype and torch.allclose(out.float(), ref, rtol=tol, atol=tol)
+    # an unaligned view takes the scalar variant
+    x2 = torch.randn(64 * 12 * 256 + 1, device="cuda").to(dtype)[1:].view(64, 12, 256)
+    (out2,), _ = _fused(build, dict(x=x2, b=b, g=g))
+    ref2 = torch.nn.functional.gelu(x2.float() * bf + gf) * torch.tanh(x2.float()) - 0.5
+    assert torch.allclose(out2.float(), ref2, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("cols", [40, 256, 1000, 4096, 12000])
+def test_row_kernels_every_schedule(cols):
+    torch.manual_seed(1)
+    x = torch.randn(37, cols, device="cuda")
+    w = torch.randn(cols, device="cuda")
+
+    def build(x, w):
+        mu = x.mean(-1, keepdim=True)
+        xc = x - mu
+        y = xc * paddle.rsqrt((xc * xc).mean(-1, keepdim=True) + 1e-5) * w
+        return F.softmax(y, -1), y.amax(-1)
+
+    (p, m), rep = _fused(build, dict(x=x, w=w))
+    assert len(rep.groups) == 1 and rep.groups[0]["kind"] == "reduce"
+    xc = x - x.mean(-1, keepdim=True)
+    y = xc * torch.rsqrt((xc * xc).mean(-1, keepdim=True) + 1e-5) * w
+    assert torch.allclose(p, torch.softmax(y, -1), rtol=1e-4, atol=1e-6)
+    assert torch.allclose(m, y.amax(-1), rtol=1e-4, atol=1e-5)
+
+
+def test_to_static_backend_cinn_on_device():
+    class Head(paddle.nn.Layer):
+        def __init__(self):
+            super().__init__()
+            self.fc = paddle.nn.Linear(256, 512)
+
+        def forward(self, x):
+            h = self.fc(x)
+            return F.softmax(F.silu(h) * 1.3 - h.mean(-1, keepdim=True), -1)
+
+    paddle.seed(0)
+    net = Head().to("gpu")
+    net.eval()
+    x = paddle.randn([64, 256]).cuda()
+    fast = paddle.jit.to_static(net, backend="CINN")
+    with paddle.no_grad():
+        ref = net(x)
+        out = fast(x)
+    rep = fast.forward.cinn_report(x)
+    assert rep is not None and len(rep.groups) >= 1
+    assert torch.allclose(out.as_subclass(torch.Tensor), ref.as_subclass(torch.Tensor), rtol=1e-4, atol=1e-6)
