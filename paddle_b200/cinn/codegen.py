@@ -57,6 +57,8 @@ class Spec:
 
     def __init__(self, name, full, nodes, inputs, outputs):
         self.name, self.full, self.nodes, self.inputs, self.outputs = name, tuple(full), nodes, inputs, outputs
+        if len({id(n) for n in outputs}) != len(outputs):
+            raise ValueError("a group result is listed twice")
         self.cols = int(full[-1]) if full else 1
         self.rows = _prod(full[:-1]) if full else 1
         self.has_reduce = any(n.kind == "reduce" for n in nodes)
@@ -89,9 +91,12 @@ class _Body:
         if ctx == "full":
             target = self.spec.full
         else:
-            target = lead          # row context: the flat index IS `row`; a keepdim trailing 1 carries no stride
-            if len(shape) == len(lead) + 1 and shape and shape[-1] == 1:
-                shape = shape[:-1]
+            target = lead          # row contexts: the flat index IS `row`
+            if ctx == "keep":      # consumer is S[:-1] + (1,): the input's last axis lines up with that 1 and carries no stride
+                if shape:
+                    if shape[-1] != 1:
+                        raise Unsupported(f"cannot broadcast {list(n.shape)} per row")
+                    shape = shape[:-1]
         if len(shape) > len(target):
             if all(d == 1 for d in shape[: len(shape) - len(target)]):
                 shape = shape[len(shape) - len(target):]
@@ -439,10 +444,17 @@ class _RowEmitter:
             return self.row_named[a.id], compute_type(a.dtype)
         return f"v{a.id}", compute_type(a.dtype)
 
-    def _ref_row(self, a):
-        if a.kind == "in":
-            return f"r{a.id}_r", compute_type(a.dtype)
-        return self.row_named[a.id], compute_type(a.dtype)
+    def _row_ctx(self, n):
+        """Row context of a per-row node: 'keep' for S[:-1] + (1,), 'row' for S[:-1]."""
+        return "keep" if len(n.shape) == len(self.spec.full) and self.spec.full else "row"
+
+    def _ref_row_for(self, ctx):
+        def ref(a):
+            if a.kind == "in":
+                return f"r{a.id}_{ctx[0]}", compute_type(a.dtype)
+            return self.row_named[a.id], compute_type(a.dtype)
+
+        return ref
 
     def column_loop(self, k, per_element):
         """for j: evaluate loop k's nodes, then the `per_element()` statements."""
@@ -468,11 +480,12 @@ class _RowEmitter:
 
     def row_values(self, level):
         for n in self.plan.row_ews[level]:
+            ctx = self._row_ctx(n)
             for a in n.args:
                 if isinstance(a, Node) and a.kind == "in":
-                    self._hoist_input(a, "row")
+                    self._hoist_input(a, ctx)
             self.row_named[n.id] = f"r{n.id}"
-            self.w(f"const {compute_type(n.dtype)} r{n.id} = {self.body.ew_expr(n, self._ref_row)};")
+            self.w(f"const {compute_type(n.dtype)} r{n.id} = {self.body.ew_expr(n, self._ref_row_for(ctx))};")
 
     def emit(self, store_guard=None):
         spec, plan = self.spec, self.plan

@@ -101,6 +101,73 @@ class FusedKernel:
         return self._fn[target]
 
     def __call__(self, *tensors, **_attrs):
+        if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+            outs = _FusedFn.apply(self, *[t.as_subclass(torch.Tensor) if type(t) is not torch.Tensor else t for t in tensors])
+            res = [o.as_subclass(Tensor) for o in outs]
+            return res[0] if len(res) == 1 else tuple(res)
+        return self._run(tensors)
+
+    # ---- backward: one more generated kernel (cinn/autodiff.py); the torch interpreter when a derivative rule is missing --------------------
+    def _backward_kernel(self, need):
+        key = tuple(bool(v) for v in need)
+        if not hasattr(self, "_bwd"):
+            self._bwd = {}
+        if key not in self._bwd:
+            from .autodiff import backward_spec
+            from .expr import Unsupported
+
+            try:
+                bspec, plan = backward_spec(self.spec, key)
+                bk = FusedKernel(bspec) if bspec is not None else None
+                if bk is not None:
+                    bk.source("cuda")
+                self._bwd[key] = (bk, plan)
+            except Unsupported as e:
+                self._bwd[key] = (None, None)
+                self.backward_fallback = str(e)
+        return self._bwd[key]
+
+    def backward(self, inputs, grad_outputs, need):
+        """Gradients of the inputs (None where not needed)."""
+        spec = self.spec
+        gouts = []
+        for g, n in zip(grad_outputs, spec.outputs):
+            if g is None:
+                g = torch.zeros(n.shape, dtype=_TORCH_DT[n.dtype], device=inputs[0].device)
+            gouts.append(g.contiguous())
+        bk, plan = self._backward_kernel(need)
+        if plan is None:                                           # no generated backward: differentiate the reference evaluation
+            from .interp import evaluate
+
+            with torch.enable_grad():
+                xs = [t.detach().requires_grad_(bool(nd) and t.is_floating_point()) for t, nd in zip(inputs, need)]
+                outs = evaluate(spec, xs)
+                pairs = [(o, g) for o, g in zip(outs, gouts) if o.requires_grad]
+                wrt = [x for x in xs if x.requires_grad]
+                gs = torch.autograd.grad([o for o, _ in pairs], wrt, [g for _, g in pairs], allow_unused=True) if pairs and wrt else []
+            it = iter(gs)
+            return [next(it) if x.requires_grad else None for x in xs]
+        res = []
+        if bk is not None:
+            operands = [inputs[i] if kind == "in" else gouts[i] for kind, i in plan.inputs]
+            res = bk._run(operands)
+            res = list(res) if isinstance(res, tuple) else [res]
+            res = [r.as_subclass(torch.Tensor) for r in res]
+        grads = []
+        for k, (t, nd) in enumerate(zip(inputs, need)):
+            if not nd or k not in plan.parts:
+                grads.append(None)
+                continue
+            acc = None
+            for kind, i in plan.parts[k]:
+                p = res[i] if kind == "out" else gouts[i]
+                if tuple(p.shape) != tuple(t.shape):
+                    p = p.sum_to_size(t.shape) if p.dim() >= t.dim() else p.reshape(t.shape)
+                acc = p if acc is None else acc + p
+            grads.append(None if acc is None else acc.to(t.dtype))
+        return grads
+
+    def _run(self, tensors):
         spec = self.spec
         if len(tensors) != len(spec.inputs):
             raise TypeError(f"{spec.name}: expected {len(spec.inputs)} tensors, got {len(tensors)}")
@@ -132,6 +199,23 @@ class FusedKernel:
         stats["launches"] += 1
         res = [o.as_subclass(Tensor) for o in outs]
         return res[0] if len(res) == 1 else tuple(res)
+
+
+class _FusedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kernel, *tensors):
+        with torch.no_grad():
+            outs = kernel._run(tensors)
+        outs = tuple(o.as_subclass(torch.Tensor) for o in (outs if isinstance(outs, tuple) else (outs,)))
+        ctx.kernel = kernel
+        ctx.save_for_backward(*tensors)
+        ctx.mark_non_differentiable(*[o for o in outs if not o.is_floating_point()])
+        return outs
+
+    @staticmethod
+    def backward(ctx, *grad_outputs):
+        grads = ctx.kernel.backward(list(ctx.saved_tensors), list(grad_outputs), ctx.needs_input_grad[1:])
+        return (None, *grads)
 
 
 def clear_cache():

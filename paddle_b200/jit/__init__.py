@@ -161,12 +161,13 @@ class StaticFunction:
         outs = list(out) if isinstance(out, (list, tuple)) else [out]
         if not outs or not all(isinstance(o, torch.Tensor) and id(o) in prog._fetch_alias for o in outs):
             return None                                           # results that are not values of the program: run as written
-        infer = prog.clone(for_test=True)
+        training = torch.is_grad_enabled() and self._layer is not None and self._layer.training
+        infer = prog if training else prog.clone(for_test=True)        # a training trace keeps dropout etc. live; fused kernels are differentiable
         new, report = cinn.compile_program(infer, outs)
         return static.Executor(), new, [v.name for v in ins], outs, not isinstance(out, (list, tuple)), report
 
     def _call_cinn(self, args):
-        key = _sig(args, {})
+        key = _sig(args, {}) + (bool(torch.is_grad_enabled() and self._layer is not None and self._layer.training),)
         if key not in self._cinn:
             try:
                 self._cinn[key] = self._cinn_entry(args)
@@ -185,13 +186,16 @@ class StaticFunction:
 
     def cinn_report(self, *args):
         """FusionResult of the program compiled for these arguments (None when it was not compiled)."""
-        e = self._cinn.get(_sig(args, {}))
-        return None if e is None else e[5]
+        for training in (False, True):
+            e = self._cinn.get(_sig(args, {}) + (training,))
+            if e is not None:
+                return e[5]
+        return None
 
     def __call__(self, *args, **kwargs):
         if not _enabled[0] or getattr(self._dygraph_fn, "_not_to_static", False):
             return self._dygraph_fn(*args, **kwargs)
-        if self._backend == "CINN" and not kwargs and (not torch.is_grad_enabled() or not _needs_grad(self, args)):
+        if self._backend == "CINN" and not kwargs:
             return self._call_cinn(args)
         if self._can_train_graph(args, kwargs):
             key = ("train",) + _sig(args, kwargs)

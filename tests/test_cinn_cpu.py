@@ -218,6 +218,13 @@ def test_generated_cuda_cross_compiles_for_sm100a():
     assert len(rep.groups) == 1
     assert cinn.nvcc_check(rep.groups[0]["kernel"]).endswith(".so")
     del h
+    # a generated backward (reductions at three levels) builds too
+    xs, ws = torch.randn(6, 300), torch.randn(300)
+    k = _kernel_of(lambda x, w: F.softmax(x * w, -1) * paddle.rsqrt((x * x).mean(-1, keepdim=True) + 1e-6), dict(x=xs, w=ws))
+    a = [xs.clone().requires_grad_(True), ws.clone().requires_grad_(True)]
+    k(*a).as_subclass(torch.Tensor).sum().backward()
+    (bk, plan), = k._bwd.values()
+    assert plan is not None and cinn.nvcc_check(bk).endswith(".so")
 
 
 # ---- random programs: whatever the grouping decides, the fused program must equal the unfused one -----------------------------------------
@@ -259,3 +266,187 @@ def test_random_programs(seed):
         return [vals[-1]] + [vals[int(rng.integers(len(ph), len(vals)))] for _ in range(int(rng.integers(0, 2)))]
 
     _run_both(build, feeds, rtol=2e-4, atol=2e-5)
+
+
+# ---- backward: generated from the forward group (cinn/autodiff.py) ---------------------------------------------------------------------------
+def _kernel_of(build, feeds):
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            ph = {k: static.data(k, list(v.shape), str(v.dtype).replace("torch.", "")) for k, v in feeds.items()}
+            fetch = build(**ph)
+            fetch = list(fetch) if isinstance(fetch, (list, tuple)) else [fetch]
+        _, rep = cinn.compile_program(main, fetch)
+    finally:
+        paddle.disable_static()
+    assert len(rep.groups) == 1, (rep, rep.rejected)
+    return rep.groups[0]["kernel"]
+
+
+def _check_grads(kernel, torch_fn, inputs, rtol=1e-4, atol=1e-5):
+    a = [t.clone().requires_grad_(True) for t in inputs]
+    b = [t.clone().requires_grad_(True) for t in inputs]
+    oa = kernel(*a)
+    oa = [o.as_subclass(torch.Tensor) for o in (oa if isinstance(oa, tuple) else (oa,))]
+    ob = torch_fn(*b)
+    ob = list(ob) if isinstance(ob, (tuple, list)) else [ob]
+    torch.manual_seed(0)
+    gos = [torch.randn_like(o) for o in ob]
+    ga = torch.autograd.grad(oa, a, gos, allow_unused=True)
+    gb = torch.autograd.grad(ob, b, gos, allow_unused=True)
+    for x, y, t in zip(ga, gb, inputs):
+        assert x is not None and x.shape == t.shape and x.dtype == t.dtype
+        assert torch.allclose(x, y, rtol=rtol, atol=atol), (x - y).abs().max()
+    (bk, plan), = kernel._bwd.values()
+    assert plan is not None, getattr(kernel, "backward_fallback", None)          # generated, not the interpreter fall-back
+    return bk, plan
+
+
+def test_backward_of_a_normalisation_is_one_generated_kernel():
+    torch.manual_seed(0)
+    x, w, b = torch.randn(5, 6, 48), torch.randn(48), torch.randn(48)
+
+    def build(x, w, b):
+        mu = x.mean(-1, keepdim=True)
+        xc = x - mu
+        return xc * paddle.rsqrt((xc * xc).mean(-1, keepdim=True) + 1e-5) * w + b
+
+    k = _kernel_of(build, dict(x=x, w=w, b=b))
+    bk, plan = _check_grads(k, lambda x, w, b: torch.nn.functional.layer_norm(x, (48,), w, b, 1e-5), [x, w, b])
+    assert bk.spec.has_reduce and bk.spec.max_level >= 2                # the row sums of the backward are inside the kernel
+    assert set(plan.parts) == {0, 1, 2}
+    assert "__global__" in bk.source("cuda")
+
+
+def test_backward_softmax_ties_and_broadcast_inputs():
+    torch.manual_seed(1)
+    x, s = torch.randn(7, 33), torch.randn(7, 1)
+    k = _kernel_of(lambda x, s: F.softmax(x * s, -1) * F.log_softmax(x, -1), dict(x=x, s=s))
+    _check_grads(k, lambda x, s: torch.softmax(x * s, -1) * torch.log_softmax(x, -1), [x, s])
+    # amax with tied maxima: the gradient is shared, like the eager op
+    t = torch.tensor([[1.0, 3.0, 3.0, 0.0], [2.0, 2.0, 2.0, 2.0]])
+    k = _kernel_of(lambda t: t.amax(-1, keepdim=True) * 2.0 + paddle.maximum(t, 2.0 - t).sum(-1, keepdim=True), dict(t=t))
+    _check_grads(k, lambda t: t.amax(-1, keepdim=True) * 2.0 + torch.maximum(t, 2.0 - t).sum(-1, keepdim=True), [t])
+    # an input broadcast over leading axes gets its gradient summed back to its shape
+    a, c = torch.randn(3, 4, 8), torch.randn(4, 1)
+    k = _kernel_of(lambda a, c: paddle.tanh(a * c) / (1.0 + paddle.exp(-a)) - c, dict(a=a, c=c))
+    _check_grads(k, lambda a, c: torch.tanh(a * c) / (1.0 + torch.exp(-a)) - c, [a, c])
+
+
+def test_backward_half_precision_and_missing_rule_fallback():
+    torch.manual_seed(2)
+    x = torch.randn(16, 64).to(torch.bfloat16)
+    k = _kernel_of(lambda x: F.gelu(x) * paddle.tanh(x) + x, dict(x=x))
+    xa = x.clone().requires_grad_(True)
+    out = k(xa).as_subclass(torch.Tensor)
+    out.float().sum().backward()
+    xr = x.float().requires_grad_(True)
+    (torch.nn.functional.gelu(xr) * torch.tanh(xr) + xr).sum().backward()
+    assert xa.grad.dtype == torch.bfloat16 and torch.allclose(xa.grad.float(), xr.grad, rtol=2e-2, atol=2e-2)
+    # fmod by a tensor has no rule: the gradient comes from differentiating the reference evaluation
+    y, d = torch.rand(4, 8) * 5, torch.rand(4, 8) + 1.0
+    k = _kernel_of(lambda y, d: paddle.exp(torch.fmod(y, d) * 0.1), dict(y=y, d=d))
+    ya, da = y.clone().requires_grad_(True), d.clone().requires_grad_(True)
+    k(ya, da).as_subclass(torch.Tensor).sum().backward()
+    yr, dr = y.clone().requires_grad_(True), d.clone().requires_grad_(True)
+    torch.exp(torch.fmod(yr, dr) * 0.1).sum().backward()
+    assert torch.allclose(ya.grad, yr.grad, rtol=1e-4, atol=1e-6) and torch.allclose(da.grad, dr.grad, rtol=1e-4, atol=1e-5)
+    assert "fmod" in k.backward_fallback
+
+
+def test_to_static_cinn_trains():
+    class Net(paddle.nn.Layer):
+        def __init__(self):
+            super().__init__()
+            self.fc1, self.fc2 = paddle.nn.Linear(16, 32), paddle.nn.Linear(32, 4)
+            self.g = self.create_parameter([32], default_initializer=paddle.nn.initializer.Constant(1.0))
+
+        def forward(self, x):
+            h = self.fc1(x)
+            h = h * paddle.rsqrt((h * h).mean(-1, keepdim=True) + 1e-6) * self.g          # RMSNorm written out: one generated kernel
+            h = F.silu(h) + 0.1 * paddle.tanh(h)
+            return F.log_softmax(self.fc2(h), -1)
+
+    def run(compiled):
+        paddle.seed(3)
+        net = Net()
+        opt = paddle.optimizer.SGD(learning_rate=0.1, parameters=net.parameters())
+        fwd = paddle.jit.to_static(net, backend="CINN") if compiled else net
+        x = paddle.to_tensor(np.random.default_rng(0).standard_normal((8, 16)).astype("float32"))
+        y = paddle.to_tensor(np.arange(8) % 4)
+        losses = []
+        for _ in range(5):
+            lp = fwd(x)
+            loss = -(lp * F.one_hot(y, 4)).sum(-1).mean()
+            loss.backward()
+            opt.step()
+            opt.clear_grad()
+            losses.append(float(loss))
+        return losses, (fwd.forward.cinn_report(x) if compiled else None)
+
+    ref, _ = run(False)
+    got, rep = run(True)
+    assert rep is not None and len(rep.groups) >= 1 and sum(g["kernel"].launches for g in rep.groups) >= 5
+    assert any(getattr(g["kernel"], "_bwd", None) for g in rep.groups)              # the backward went through generated kernels
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-5)
+    assert got[-1] < got[0]
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_program_gradients(seed):
+    """Generated backward == autograd through the reference evaluation of the same group."""
+    from paddle_b200.cinn import interp
+
+    rng = np.random.default_rng(500 + seed)
+    full = [int(rng.integers(1, 6)) for _ in range(int(rng.integers(1, 4)))]
+    full[-1] = int(rng.choice([1, 4, 8, 33]))
+    shapes = [full] + [_bshape(rng, full) for _ in range(int(rng.integers(0, 3)))]
+    feeds = {f"i{k}": torch.from_numpy(rng.standard_normal(s).astype(np.float32)) for k, s in enumerate(shapes)}
+
+    def build(**ph):
+        ph = list(ph.values())
+        vals, fulls = list(ph), [ph[0]]
+        for _ in range(int(rng.integers(3, 10))):
+            r = rng.random()
+            if r < 0.4:
+                v = _UN[rng.integers(len(_UN))](vals[rng.integers(len(vals))])
+            elif r < 0.85:
+                v = _BI[rng.integers(len(_BI))](fulls[rng.integers(len(fulls))], vals[rng.integers(len(vals))])
+            else:
+                v = _RED[rng.integers(len(_RED))](fulls[rng.integers(len(fulls))])
+            vals.append(v)
+            if list(v.shape) == full:
+                fulls.append(v)
+        return vals[-1]
+
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            ph = {k: static.data(k, list(v.shape), "float32") for k, v in feeds.items()}
+            out = build(**ph)
+        _, rep = cinn.compile_program(main, [out])
+    finally:
+        paddle.disable_static()
+    for g in rep.groups:
+        k = g["kernel"]
+        torch.manual_seed(seed)
+        ins = [torch.randn(n.shape) for n in k.spec.inputs]
+        a = [t.clone().requires_grad_(True) for t in ins]
+        b = [t.clone().requires_grad_(True) for t in ins]
+        oa = k(*a)
+        oa = [o.as_subclass(torch.Tensor) for o in (oa if isinstance(oa, tuple) else (oa,))]
+        ob = interp.evaluate(k.spec, b)
+        gos = [torch.randn_like(o) for o in ob]
+        pa = [(o, g_) for o, g_ in zip(oa, gos) if o.requires_grad]
+        pb = [(o, g_) for o, g_ in zip(ob, gos) if o.requires_grad]
+        if not pa:
+            continue
+        ga = torch.autograd.grad([o for o, _ in pa], a, [g_ for _, g_ in pa], allow_unused=True)
+        gb = torch.autograd.grad([o for o, _ in pb], b, [g_ for _, g_ in pb], allow_unused=True)
+        for x, y in zip(ga, gb):
+            if x is None or y is None:
+                assert (x is None or float(x.abs().max()) == 0.0) and (y is None or float(y.abs().max()) == 0.0)
+                continue
+            assert torch.allclose(x, y, rtol=2e-3, atol=2e-4, equal_nan=True)

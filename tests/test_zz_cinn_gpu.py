@@ -92,3 +92,33 @@ def test_to_static_backend_cinn_on_device():
     rep = fast.forward.cinn_report(x)
     assert rep is not None and len(rep.groups) >= 1
     assert torch.allclose(out.as_subclass(torch.Tensor), ref.as_subclass(torch.Tensor), rtol=1e-4, atol=1e-6)
+
+
+def test_generated_backward_on_device():
+    torch.manual_seed(2)
+    x = torch.randn(64, 512, device="cuda", requires_grad=True)
+    w = torch.randn(512, device="cuda", requires_grad=True)
+    b = torch.randn(512, device="cuda", requires_grad=True)
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            xv, wv, bv = static.data("x", [64, 512], "float32"), static.data("w", [512], "float32"), static.data("b", [512], "float32")
+            mu = xv.mean(-1, keepdim=True)
+            xc = xv - mu
+            out = F.gelu(xc * paddle.rsqrt((xc * xc).mean(-1, keepdim=True) + 1e-5) * wv + bv)
+        _, rep = cinn.compile_program(main, [out])
+    finally:
+        paddle.disable_static()
+    k = rep.groups[0]["kernel"]
+    o = k(x, w, b).as_subclass(torch.Tensor)
+    go = torch.randn_like(o)
+    got = torch.autograd.grad(o, [x, w, b], go)
+    xr, wr, br = (t.detach().clone().requires_grad_(True) for t in (x, w, b))
+    ref_o = torch.nn.functional.gelu(torch.nn.functional.layer_norm(xr, (512,), wr, br, 1e-5))
+    ref = torch.autograd.grad(ref_o, [xr, wr, br], go)
+    assert torch.allclose(o, ref_o, rtol=1e-4, atol=1e-5)
+    for a, r in zip(got, ref):
+        assert torch.allclose(a, r, rtol=1e-3, atol=1e-4)
+    (bk, plan), = k._bwd.values()
+    assert plan is not None and bk.launches == 1
