@@ -45,7 +45,7 @@ def __getattr__(name):
 
     lazy = {"vision", "metric", "hapi", "distribution", "sparse", "incubate", "jit", "static", "inference", "profiler", "quantization",
             "device", "text", "audio", "geometric", "models", "parallel", "utils", "fft", "signal", "linalg", "hub", "onnx", "callbacks",
-            "sysconfig", "version", "base", "tensor_ns", "decomposition", "cost_model", "reader", "dataset", "tensorrt", "pir"}
+            "sysconfig", "version", "base", "tensor_ns", "decomposition", "cost_model", "reader", "dataset", "tensorrt", "pir", "cinn", "_C_ops"}
     if name in lazy:
         return importlib.import_module("." + name, __name__)
     if name == "DataParallel":

@@ -26,3 +26,16 @@ def is_bfloat16_supported(place=None):
 
 def is_float16_supported(place=None):
     return True
+
+
+def _get_all_register_op_kernels(lib="phi"):
+    """{op: [kernel keys]} of the KernelFactory (kernels/registry.py).  Parity: core._get_all_register_op_kernels."""
+    from ..kernels.registry import all_registered_kernels
+
+    return all_registered_kernels()
+
+
+def get_all_op_names():
+    from ..ops import schema
+
+    return sorted(schema.build_registry())

@@ -450,3 +450,25 @@ def test_random_program_gradients(seed):
                 assert (x is None or float(x.abs().max()) == 0.0) and (y is None or float(y.abs().max()) == 0.0)
                 continue
             assert torch.allclose(x, y, rtol=2e-3, atol=2e-4, equal_nan=True)
+
+
+def test_static_executor_uses_generated_kernels_under_the_flags():
+    """FLAGS_enable_pir_api + FLAGS_use_cinn: Executor.run compiles inference programs on first use (programs with a training node keep their
+    recorded form)."""
+    paddle.enable_static()
+    old = paddle.get_flags(["FLAGS_enable_pir_api", "FLAGS_use_cinn"])
+    try:
+        paddle.set_flags({"FLAGS_enable_pir_api": True, "FLAGS_use_cinn": True})
+        main = static.Program()
+        with static.program_guard(main):
+            x = static.data("x", [6, 20], "float32")
+            out = F.softmax(paddle.tanh(x) * 2.0 - x.mean(-1, keepdim=True), -1)
+        xv = np.random.default_rng(0).standard_normal((6, 20)).astype("float32")
+        before = cinn.stats["launches"]
+        got = static.Executor().run(main, feed={"x": xv}, fetch_list=[out])[0]
+        assert cinn.stats["launches"] == before + 1
+    finally:
+        paddle.set_flags(old)
+        paddle.disable_static()
+    t = torch.from_numpy(xv)
+    np.testing.assert_allclose(got, torch.softmax(torch.tanh(t) * 2.0 - t.mean(-1, keepdim=True), -1).numpy(), rtol=2e-5, atol=1e-7)
