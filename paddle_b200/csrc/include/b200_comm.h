@@ -28,5 +28,13 @@ void p2p_gather_pull(const int64_t* bases, int64_t src_off, void* dst, int64_t c
 // stats (optional, device uint64[2]) accumulates the spun nanoseconds and the number of waits.
 void p2p_signal_flag(void* remote_flag, uint32_t value, cudaStream_t s);
 void p2p_wait_flag(const void* flag, uint32_t value, void* stats, double timeout_s, cudaStream_t s);
+// NVLS (multicast) collectives, csrc/comm/nvls_collectives.cu.  pads[r] = rank r's signal pad as mapped here, pad_off = byte offset of our
+// barrier words inside it; mc / local = multicast and local address of the symmetric buffer; dtype 0 fp32, 1 bf16, 2 fp16.
+void nvls_allreduce(const int64_t* pads, int64_t pad_off, int64_t mc, int64_t local, int64_t off, int64_t n, int dtype, int rank, int world, uint32_t epoch,
+                    uint32_t* counter, cudaStream_t s);
+void nvls_reduce_scatter(const int64_t* pads, int64_t pad_off, int64_t mc, int64_t local, int64_t off, void* out, int64_t n, int dtype, int rank, int world,
+                         uint32_t epoch, uint32_t* counter, cudaStream_t s);
+void nvls_allgather(const int64_t* pads, int64_t pad_off, int64_t mc, int64_t local, int64_t off, const void* src, int64_t chunk_bytes, int rank, int world,
+                    uint32_t epoch, uint32_t* counter, cudaStream_t s);
 }  // namespace comm
 }  // namespace b200

@@ -230,7 +230,38 @@ class SymmHeap {
   void* wait_stats_ = nullptr;
 };
 
+namespace {
+int nvls_dcode(at::ScalarType st) {
+  switch (st) {
+    case at::kFloat: return 0;
+    case at::kBFloat16: return 1;
+    case at::kHalf: return 2;
+    default: throw std::runtime_error("nvls: unsupported dtype (float32 / bfloat16 / float16)");
+  }
+}
+uint32_t* counter_of(const at::Tensor& c) {
+  if (!c.is_cuda() || c.scalar_type() != at::kInt || c.numel() < 1) throw std::runtime_error("nvls: counter must be a CUDA int32 tensor");
+  return reinterpret_cast<uint32_t*>(c.data_ptr());
+}
+}  // namespace
+
 void bind_symm(pybind11::module_& m) {
+  // NVLS collectives over a torch.distributed._symmetric_memory buffer (parallel/nvls.py owns the handles)
+  m.def("nvls_allreduce", [](const std::vector<int64_t>& pads, int64_t pad_off, int64_t mc, int64_t local, int64_t off, int64_t n, at::ScalarType dt, int rank,
+                             int64_t epoch, const at::Tensor& counter) {
+    comm::nvls_allreduce(pads.data(), pad_off, mc, local, off, n, nvls_dcode(dt), rank, (int)pads.size(), (uint32_t)epoch, counter_of(counter),
+                         at::cuda::getCurrentCUDAStream().stream());
+  });
+  m.def("nvls_reduce_scatter", [](const std::vector<int64_t>& pads, int64_t pad_off, int64_t mc, int64_t local, int64_t off, at::Tensor out, int64_t n, int rank,
+                                  int64_t epoch, const at::Tensor& counter) {
+    comm::nvls_reduce_scatter(pads.data(), pad_off, mc, local, off, out.data_ptr(), n, nvls_dcode(out.scalar_type()), rank, (int)pads.size(), (uint32_t)epoch,
+                              counter_of(counter), at::cuda::getCurrentCUDAStream().stream());
+  });
+  m.def("nvls_allgather", [](const std::vector<int64_t>& pads, int64_t pad_off, int64_t mc, int64_t local, int64_t off, const at::Tensor& src, int rank, int64_t epoch,
+                             const at::Tensor& counter) {
+    comm::nvls_allgather(pads.data(), pad_off, mc, local, off, src.data_ptr(), (int64_t)src.numel() * src.element_size(), rank, (int)pads.size(), (uint32_t)epoch,
+                         counter_of(counter), at::cuda::getCurrentCUDAStream().stream());
+  });
   pybind11::class_<BestFitAllocator>(m, "BestFitAllocator")
       .def(pybind11::init<int64_t, int64_t, int64_t>(), pybind11::arg("begin"), pybind11::arg("end"), pybind11::arg("min_align") = 256)
       .def("alloc", &BestFitAllocator::alloc, pybind11::arg("nbytes"), pybind11::arg("align") = 256)

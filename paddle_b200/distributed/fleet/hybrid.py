@@ -105,6 +105,13 @@ def _allreduce_flat_impl(flat, group):
     if flat.is_cuda and flat.dtype in (torch.bfloat16, torch.float16, torch.float32):
         from ...framework.flags import flag
 
+        if flag("FLAGS_b200_nvls", False):                   # opt-in: the switch reduces (parallel/nvls.py)
+            from ...parallel import nvls
+
+            nc = nvls.context_for(group)
+            if nc is not None and nc.supports(flat):
+                nc.all_reduce_(flat)
+                return
         if flag("FLAGS_b200_p2p_collectives", True):
             from ...parallel import symm
 

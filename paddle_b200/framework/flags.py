@@ -10,6 +10,7 @@ _FLAGS = {
     "FLAGS_b200_sync_debug": False,        # serialise side streams (race triage)
     "FLAGS_b200_p2p_collectives": True,    # fused compute+collective kernels over peer memory
     "FLAGS_b200_gemm_backend": "tcgen05",  # "tcgen05" | "cublas"
+    "FLAGS_b200_nvls": False,              # all-reduce through NVSwitch multicast (parallel/nvls.py, multimem.ld_reduce / st); not yet run on hardware
     "FLAGS_b200_decode_kernel": False,     # models.generation: decode steps attend through csrc/decode_attention.cu (CUDA, head_dim 128, fp16 / bf16)
     "FLAGS_use_cinn": False,               # pir.optimize: fuse elementwise / reduction chains into generated sm_100a kernels (paddle_b200.cinn)
     "FLAGS_enable_pir_api": False,         # static Executor: run programs through the native IR pass pipeline (paddle_b200.pir) before replay

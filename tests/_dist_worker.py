@@ -1405,6 +1405,60 @@ def case_hapi_fit():
     assert os.path.exists(os.path.join(tmp, "hapi", "ck.pdparams"))
 
 
+def case_nvls_kernels():
+    """NVSwitch multicast collectives (parallel/nvls.py, csrc/comm/nvls_collectives.cu) vs NCCL.  Exits 77 when the box has no NVLS."""
+    assert GPU
+    dist.init_parallel_env()
+    r, w = dist.get_rank(), dist.get_world_size()
+    paddle.set_flags({"FLAGS_b200_nvls": True})
+    from paddle_b200.parallel import nvls
+
+    nc = nvls.context_for(None, nbytes=64 << 20)
+    if nc is None:
+        print("NVLS unavailable on this system")
+        sys.exit(77)
+    torch.manual_seed(r)
+    for n in (1 << 10, 1 << 20, (3 << 20) + 64):
+        for dt in (torch.bfloat16, torch.float32, torch.float16):
+            t = (torch.randn(n, device="cuda") * 0.5).to(dt)
+            ref = t.clone()
+            torch.distributed.all_reduce(ref)
+            nc.all_reduce_(t)
+            torch.cuda.synchronize()
+            assert (t.float() - ref.float()).abs().max().item() <= 2e-2 * max(1.0, ref.float().abs().max().item()), (n, dt)
+    # a tensor that lives in the buffer is reduced in place (no staging copies)
+    v = nc.tensor(1 << 20, (4096, 64), torch.bfloat16)
+    v.copy_((torch.randn(4096, 64, device="cuda") * 0.5).to(torch.bfloat16))
+    ref = v.clone()
+    torch.distributed.all_reduce(ref)
+    nc.all_reduce_(v)
+    torch.cuda.synchronize()
+    assert (v.float() - ref.float()).abs().max().item() <= 2e-2 * max(1.0, ref.float().abs().max().item())
+    # reduce-scatter / all-gather
+    x = (torch.randn(w * 8192, device="cuda") * 0.5).to(torch.bfloat16)
+    full = x.clone()
+    torch.distributed.all_reduce(full)
+    out = torch.empty(8192, device="cuda", dtype=torch.bfloat16)
+    nc.reduce_scatter(out, x)
+    torch.cuda.synchronize()
+    assert (out.float() - full.chunk(w)[r].float()).abs().max().item() <= 2e-2 * max(1.0, full.float().abs().max().item())
+    mine = torch.full((4096,), float(r + 1), device="cuda")
+    gathered = torch.empty(w * 4096, device="cuda")
+    nc.all_gather(gathered, mine)
+    torch.cuda.synchronize()
+    assert torch.equal(gathered.view(w, 4096)[:, 0].cpu(), torch.arange(1, w + 1, dtype=torch.float32))
+    # the hybrid data-parallel gradient all-reduce takes this path under the flag
+    from paddle_b200.distributed.fleet.hybrid import _allreduce_flat
+
+    g = (torch.randn(1 << 18, device="cuda") * 0.1).to(torch.bfloat16)
+    ref = g.clone()
+    torch.distributed.all_reduce(ref)
+    before = nc.epoch
+    _allreduce_flat(g, None)
+    torch.cuda.synchronize()
+    assert nc.epoch == before + 1 and (g.float() - ref.float()).abs().max().item() <= 2e-2
+
+
 if __name__ == "__main__":
     case = sys.argv[1]
     if GPU:

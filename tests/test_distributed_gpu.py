@@ -91,3 +91,10 @@ def test_stress_dp_allreduce_overlaps_mp_fused_gemms():
     scenario): must neither hang (bounded spins trap after 10 s) nor corrupt results."""
     _need(4)
     run_dist("stress_dp_mp_overlap", 4, extra_env={"B200_TEST_GPU": "1"}, timeout=600)
+
+
+@pytest.mark.xfail(strict=False, reason="first hardware run of the NVLS (multimem) kernels")
+def test_nvls_collectives():
+    """NVSwitch multicast all-reduce / reduce-scatter / all-gather (csrc/comm/nvls_collectives.cu) vs NCCL; skipped without NVLS support."""
+    _need(2)
+    run_dist("nvls_kernels", 2, extra_env={"B200_TEST_GPU": "1"})
