@@ -409,7 +409,8 @@ class Predictor:
         """Program artifacts go through the configured IR passes once, here (paddle_b200.pir); returns the per-pass report."""
         blob = getattr(self._layer, "_blob", None)
         passes = self._config._pir_passes()
-        if blob is None or not passes:
+        use_cinn = bool(self._config._opt().get("cinn"))           # Config.enable_cinn(): generated kernels for the elementwise / reduction chains
+        if blob is None or not (passes or use_cinn):
             return []
         from .. import pir
 
@@ -417,7 +418,7 @@ class Predictor:
         if not pir.core_available() or any(n.kind != "op" for n in prog.nodes):
             return []
         try:
-            opt, report = pir.optimize(prog, fetch_list=list(self._layer._fetch), passes=passes, return_report=True)
+            opt, report = pir.optimize(prog, fetch_list=list(self._layer._fetch), passes=passes, return_report=True, cinn=use_cinn)
         except Exception:  # noqa: BLE001  (an op the translator cannot encode: run the program as saved)
             return []
         if self._config._opt().get("ir_debug"):

@@ -588,8 +588,9 @@ def optimize(program, fetch_list=None, passes=None, patterns=None, return_report
     if cinn:
         from ..cinn import fuse as _cinn_fuse
 
+        before = tr.ir.num_ops()
         fr = _cinn_fuse(tr, **(cinn if isinstance(cinn, dict) else {}))
-        report = list(report) + [("cinn_fusion", len(fr.groups))]
+        report = list(report) + [{"pass": "cinn_fusion", "ops_before": before, "ops_after": tr.ir.num_ops(), "changed": len(fr.groups)}]
     new = lower(tr, pm)
     new.__dict__["_pir_report"] = report
     if cinn:

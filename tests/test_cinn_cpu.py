@@ -472,3 +472,32 @@ def test_static_executor_uses_generated_kernels_under_the_flags():
         paddle.disable_static()
     t = torch.from_numpy(xv)
     np.testing.assert_allclose(got, torch.softmax(torch.tanh(t) * 2.0 - t.mean(-1, keepdim=True), -1).numpy(), rtol=2e-5, atol=1e-7)
+
+
+def test_inference_config_enable_cinn(tmp_path):
+    """Config.enable_cinn(): the predictor's program runs its pointwise / softmax tail as one generated kernel (reference: AnalysisConfig::EnableCINN)."""
+    from paddle_b200 import inference
+
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            x = static.data("x", [4, 16], "float32")
+            w = paddle.to_tensor(np.random.RandomState(0).randn(16, 24).astype("float32"))
+            h = paddle.matmul(x, w)
+            y = F.softmax(paddle.tanh(h) * 1.5 + F.sigmoid(h), -1)
+        static.save_inference_model(str(tmp_path / "m"), [x], [y], static.Executor(), program=main)
+    finally:
+        paddle.disable_static()
+    data = np.random.RandomState(2).randn(4, 16).astype("float32")
+    cfg0 = inference.Config(str(tmp_path / "m.pdmodel"), str(tmp_path / "m.pdiparams"))
+    ref = inference.create_predictor(cfg0).run([data])[0]
+    cfg = inference.Config(str(tmp_path / "m.pdmodel"), str(tmp_path / "m.pdiparams"))
+    cfg.enable_cinn()
+    before = cinn.stats["launches"]
+    p = inference.create_predictor(cfg)
+    rep = {r["pass"]: r for r in p.ir_pass_report()}
+    assert rep["cinn_fusion"]["changed"] == 1 and rep["cinn_fusion"]["ops_after"] < rep["cinn_fusion"]["ops_before"]
+    got = p.run([data])[0]
+    assert cinn.stats["launches"] == before + 1
+    np.testing.assert_allclose(np.asarray(got), np.asarray(ref), rtol=2e-5, atol=1e-7)
