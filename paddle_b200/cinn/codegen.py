@@ -350,13 +350,13 @@ class _Plan:
 def _params(spec):
     ps = [f"const {_STORE[n.dtype]}* __restrict__ in{k}" for k, n in enumerate(spec.inputs)]
     ps += [f"{_STORE[n.dtype]}* __restrict__ out{k}" for k, n in enumerate(spec.outputs)]
-    return ", ".join(ps)
+    return ", ".join(ps + ["long long rows"])
 
 
 def _call_args(spec):
     a = [f"(const {_STORE[n.dtype]}*)in[{k}]" for k, n in enumerate(spec.inputs)]
     a += [f"({_STORE[n.dtype]}*)out[{k}]" for k, n in enumerate(spec.outputs)]
-    return ", ".join(a)
+    return ", ".join(a + ["rows"])
 
 
 class _RowEmitter:
@@ -528,10 +528,10 @@ class _RowEmitter:
 def host_source(spec):
     em = _RowEmitter(spec, f"for (int j = 0; j < {spec.cols}; ++j) {{", lambda r, T: f"const {T} r{r.id} = acc{r.id};")
     body = em.emit()
-    return (_HOST_PRELUDE + f"\nextern \"C\" int cinn_run(void** in, void** out) {{\n"
+    return (_HOST_PRELUDE + f"\nextern \"C\" int cinn_run(void** in, void** out, long long rows) {{\n"
             + "".join(f"  const {_STORE[n.dtype]}* in{k} = (const {_STORE[n.dtype]}*)in[{k}];\n" for k, n in enumerate(spec.inputs))
             + "".join(f"  {_STORE[n.dtype]}* out{k} = ({_STORE[n.dtype]}*)out[{k}];\n" for k, n in enumerate(spec.outputs))
-            + f"  for (long long row = 0; row < {spec.rows}LL; ++row) {{\n{body}\n  }}\n  return 0;\n}}\n")
+            + f"  for (long long row = 0; row < rows; ++row) {{\n{body}\n  }}\n  return 0;\n}}\n")
 
 
 # ---- CUDA ------------------------------------------------------------------------------------------------------------------------------
@@ -572,8 +572,8 @@ def _flat_kernels(spec):
         return " + ".join(parts) if parts else "0"
 
     L = []
-    L.append(f"extern \"C\" __global__ void __launch_bounds__(256) {spec.name}_flat({_params(spec)}) {{")
-    L.append(f"  const long long n = {spec.rows * spec.cols}LL;")
+    L.append(f"extern \"C\" __global__ void __launch_bounds__(256) cinn_k_flat({_params(spec)}) {{")
+    L.append(f"  const long long n = rows * {spec.cols}LL;")
     L.append("  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n; e += gridDim.x * 256LL) {")
     if need_row or any(uj and not same[i] for i, (rp, uj) in idx.items()):
         L.append(f"    const long long row = e / {spec.cols}LL; const long long j = e - row * {spec.cols}LL; (void)row; (void)j;")
@@ -587,8 +587,8 @@ def _flat_kernels(spec):
         L.append(f"    st(out{k}, e, v{n.id});")
     L.append("  }\n}")
     if _vec_ok(spec):
-        L.append(f"extern \"C\" __global__ void __launch_bounds__(256) {spec.name}_vec4({_params(spec)}) {{")
-        L.append(f"  const long long ng = {spec.rows * spec.cols // 4}LL;")
+        L.append(f"extern \"C\" __global__ void __launch_bounds__(256) cinn_k_vec4({_params(spec)}) {{")
+        L.append(f"  const long long ng = rows * {spec.cols // 4}LL;")
         L.append("  for (long long g = blockIdx.x * 256LL + threadIdx.x; g < ng; g += gridDim.x * 256LL) {")
         L.append(f"    const long long e = g * 4; const long long row = e / {spec.cols}LL; const long long j = e - row * {spec.cols}LL; (void)row; (void)j;")
         for n in closure:
@@ -641,35 +641,35 @@ def _row_kernel(spec):
     if per is None or em.cache_per is None:
         em = _RowEmitter(spec, f"for (int j = lane; j < {spec.cols}; j += {lanes}) {{", red)
     body = em.emit(store_guard="lane == 0")
-    L = [f"extern \"C\" __global__ void __launch_bounds__({threads}) {spec.name}_row({_params(spec)}) {{"]
+    L = [f"extern \"C\" __global__ void __launch_bounds__({threads}) cinn_k_row({_params(spec)}) {{"]
     if warp:
         L.append("  const int lane = threadIdx.x & 31;")
-        L.append(f"  for (long long row = blockIdx.x * {rpb}LL + (threadIdx.x >> 5); row < {spec.rows}LL; row += gridDim.x * {rpb}LL) {{")
+        L.append(f"  for (long long row = blockIdx.x * {rpb}LL + (threadIdx.x >> 5); row < rows; row += gridDim.x * {rpb}LL) {{")
     else:
         L.append("  __shared__ double cinn_smem[32];")
         L.append("  const int lane = threadIdx.x;")
-        L.append(f"  for (long long row = blockIdx.x; row < {spec.rows}LL; row += gridDim.x) {{")
+        L.append("  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {")
     L.append(body)
     L.append("  }\n}")
     return "\n".join(L), threads, rpb
 
 
 def cuda_source(spec):
-    """Kernels + an `extern "C"` launcher: cinn_launch(in, out, stream, allow_vec) -> cudaError_t of the launch."""
+    """Kernels + an `extern "C"` launcher: cinn_launch(in, out, stream, allow_vec, rows) -> cudaError_t of the launch.  The number of rows
+    (product of the leading extents) is a run-time argument and the kernel names are fixed, so groups that differ only in batch / sequence
+    extents generate the same source and share one compiled object."""
     cap = SM_COUNT * 8
+    clamp = "static inline int cinn_grid(long long want, long long cap) { return (int)(want < 1 ? 1 : (want > cap ? cap : want)); }\n"
     if spec.has_reduce:
         k, threads, rpb = _row_kernel(spec)
-        blocks = (spec.rows + rpb - 1) // rpb
-        launch = (f"  int grid = {min(blocks, cap * (1 if rpb > 1 else 2))};\n"
-                  f"  {spec.name}_row<<<grid, {threads}, 0, (cudaStream_t)stream>>>({_call_args(spec)});\n")
+        launch = (f"  const int grid = cinn_grid((rows + {rpb - 1}) / {rpb}, {cap * (1 if rpb > 1 else 2)});\n"
+                  f"  cinn_k_row<<<grid, {threads}, 0, (cudaStream_t)stream>>>({_call_args(spec)});\n")
     else:
         k = _flat_kernels(spec)
-        n = spec.rows * spec.cols
-        g1 = min((n + 255) // 256, cap)
-        launch = ""
+        launch = f"  const long long n = rows * {spec.cols}LL;\n"
         if _vec_ok(spec):
-            g4 = min((n // 4 + 255) // 256, cap)
-            launch += (f"  if (allow_vec) {{ {spec.name}_vec4<<<{max(g4, 1)}, 256, 0, (cudaStream_t)stream>>>({_call_args(spec)}); return (int)cudaGetLastError(); }}\n")
-        launch += f"  {spec.name}_flat<<<{max(g1, 1)}, 256, 0, (cudaStream_t)stream>>>({_call_args(spec)});\n"
-    return (_CUDA_PRELUDE + "\n" + k + "\n\nextern \"C\" int cinn_launch(void** in, void** out, void* stream, int allow_vec) {\n  (void)allow_vec;\n"
+            launch += (f"  if (allow_vec) {{ cinn_k_vec4<<<cinn_grid((n / 4 + 255) / 256, {cap}), 256, 0, (cudaStream_t)stream>>>({_call_args(spec)}); "
+                       "return (int)cudaGetLastError(); }\n")
+        launch += f"  cinn_k_flat<<<cinn_grid((n + 255) / 256, {cap}), 256, 0, (cudaStream_t)stream>>>({_call_args(spec)});\n"
+    return (_CUDA_PRELUDE + "\n" + k + "\n\n" + clamp + "extern \"C\" int cinn_launch(void** in, void** out, void* stream, int allow_vec, long long rows) {\n  (void)allow_vec;\n"
             + launch + "  return (int)cudaGetLastError();\n}\n")

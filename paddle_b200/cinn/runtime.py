@@ -92,10 +92,10 @@ class FusedKernel:
             lib = _load(compile_source(self.source(target), target))
             if target == "cuda":
                 fn = lib.cinn_launch
-                fn.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int]
+                fn.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong]
             else:
                 fn = lib.cinn_run
-                fn.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]
+                fn.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.c_longlong]
             fn.restype = ctypes.c_int
             self._fn[target] = fn
         return self._fn[target]
@@ -188,11 +188,11 @@ class FusedKernel:
         if target == "cuda":
             with torch.cuda.device(dev):
                 aligned = all(t.data_ptr() % 16 == 0 for t in raw + outs)
-                rc = fn(ins_p, outs_p, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), int(aligned))
+                rc = fn(ins_p, outs_p, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), int(aligned), spec.rows)
             if rc != 0:
                 raise RuntimeError(f"{spec.name}: kernel launch failed with CUDA error {rc}")
         else:
-            rc = fn(ins_p, outs_p)
+            rc = fn(ins_p, outs_p, spec.rows)
             if rc != 0:
                 raise RuntimeError(f"{spec.name}: host kernel returned {rc}")
         self.launches += 1

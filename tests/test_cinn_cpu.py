@@ -501,3 +501,23 @@ def test_inference_config_enable_cinn(tmp_path):
     got = p.run([data])[0]
     assert cinn.stats["launches"] == before + 1
     np.testing.assert_allclose(np.asarray(got), np.asarray(ref), rtol=2e-5, atol=1e-7)
+
+
+def test_groups_that_differ_only_in_leading_extents_share_one_object():
+    """The row count is a launch argument: softmax(x * w) over [B, S, 64] compiles once for every (B, S)."""
+    w = np.random.default_rng(0).standard_normal((64,)).astype(np.float32)
+    paths, srcs = set(), set()
+    for shape in ((2, 3, 64), (5, 64), (7, 1, 4, 64)):
+        x = np.random.default_rng(1).standard_normal(shape).astype(np.float32)
+        rep = _run_both(lambda x, w: F.softmax(x * w, -1), dict(x=x, w=w), rtol=2e-5, atol=1e-7, expect_kernels=1)
+        k = rep.groups[0]["kernel"]
+        srcs.add(k.source("cuda"))
+        from paddle_b200.cinn import runtime
+
+        paths.add(runtime.compile_source(k.source("host"), "host"))
+    assert len(srcs) == 1 and len(paths) == 1
+    # an input that is broadcast over SOME leading axes bakes those extents into the index math: a different kernel, still correct
+    x = np.random.default_rng(2).standard_normal((2, 3, 64)).astype(np.float32)
+    g = np.random.default_rng(3).standard_normal((2, 1, 1)).astype(np.float32)
+    rep = _run_both(lambda x, g: F.softmax(x * g, -1), dict(x=x, g=g), rtol=2e-5, atol=1e-7, expect_kernels=1)
+    assert rep.groups[0]["kernel"].source("cuda") not in srcs
