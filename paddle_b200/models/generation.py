@@ -104,6 +104,63 @@ class DecoderAdapter:
             raise NotImplementedError("generation serves a single-rank replica (mp_degree 1)")
         self.nh, self.nkv, self.hd = at.num_heads, at.num_kv_heads, at.head_dim
 
+    # -- the three pieces a packed-batch engine (models/serving.py) needs; tokens are [1, T], positions [1, T]
+    def embed_tokens(self, ids, position_ids):
+        return self.embed(_w(ids))
+
+    def attn_in(self, layer, h, position_ids):
+        """-> packed q | k | v of every token [1, T, (H + 2 H_kv) * D] (normed, projected, rotated)."""
+        L = self.L
+        if not hasattr(self, "_rope"):
+            self._rope = L.rope_cache(self.cfg, _raw(h).device)
+        cos, sin = self._rope
+        nh, nkv, hd = self.nh, self.nkv, self.hd
+        return _raw(L.KR.apply_rope_packed(layer.self_attn.qkv_proj(layer.input_layernorm(h)), cos, sin, nh + nkv, nh + 2 * nkv, hd, position_ids, neox=True))
+
+    def attn_out(self, layer, h, a):
+        """Attention output [1, T, H * D] -> the layer's output."""
+        a = layer.self_attn.o_proj(_w(a))
+        x, h = layer.post_attention_layernorm(a, residual=h)
+        return h + self.ffn(layer, x)
+
+    def logits(self, h):
+        return _raw(self.head(_w(h)))
+
+
+class GPTAdapter:
+    """The same interface for `GPTForCausalLM` (learned positions, LayerNorm, biased packed qkv, GELU MLP, tied head)."""
+
+    def __init__(self, model):
+        self.model, self.cfg = model, model.cfg
+        self.layers = list(model.gpt.blocks)
+        self.nh = self.nkv = self.cfg.num_attention_heads
+        self.hd = self.cfg.head_dim
+
+    def embed_tokens(self, ids, position_ids):
+        g = self.model.gpt
+        if int(position_ids.max()) >= self.cfg.max_position_embeddings:
+            raise ValueError(f"position {int(position_ids.max())} is outside the model's {self.cfg.max_position_embeddings} learned positions")
+        return g.wte(_w(ids)) + g.wpe(_w(position_ids))
+
+    def attn_in(self, blk, h, position_ids):
+        return _raw(blk.qkv(blk.ln1(h)))                   # [.., 3, H, D] flattened: q | k | v per token
+
+    def attn_out(self, blk, h, a):
+        from ..nn import functional as F
+
+        h = h + blk.proj(_w(a))
+        return h + blk.fc2(F.gelu(blk.fc1(blk.ln2(h))))
+
+    def logits(self, h):
+        g = self.model.gpt
+        return _raw(g.wte(g.ln_f(_w(h)), project=True))
+
+
+def make_adapter(model):
+    if hasattr(model, "gpt") and hasattr(model.gpt, "blocks"):
+        return GPTAdapter(model)
+    return DecoderAdapter(model)
+
 
 class LlamaGenerator:
     """Prefill + decode over the sublayers of a decoder-only model (`LlamaForCausalLM`, `MixtralForCausalLM`); no tensor / pipeline

@@ -57,13 +57,12 @@ class LLMEngine:
     """add_request() any time; step() runs one scheduler iteration (admit / preempt, one packed forward, one token per running sequence)."""
 
     def __init__(self, model, num_blocks=256, block_size=16, max_running=64, max_batch_tokens=8192):
-        from .generation import DecoderAdapter
+        from .generation import make_adapter
 
         model.eval()
-        ad = DecoderAdapter(model)                 # Llama (dense) and Mixtral (MoE) layouts
+        ad = make_adapter(model)                   # Llama (dense), Mixtral (MoE) and GPT layouts
         self.ad, self.model, self.cfg, self.layers = ad, model, ad.cfg, ad.layers
         self.nh, self.nkv, self.hd = ad.nh, ad.nkv, ad.hd
-        L = ad.L
         self.block_size, self.max_running, self.max_batch_tokens = int(block_size), int(max_running), int(max_batch_tokens)
         p0 = _raw(next(iter(model.parameters())))
         self.device, self.dtype = p0.device, p0.dtype
@@ -73,7 +72,6 @@ class LLMEngine:
         self.value_cache = [torch.zeros(shape, dtype=self.dtype, device=self.device) for _ in self.layers]
         self.waiting, self.running, self.done = [], [], {}
         self._next_id = 0
-        self._L = L
         self.stats = {"steps": 0, "prefill_tokens": 0, "decode_tokens": 0, "preemptions": 0, "max_running": 0}
 
     # ---- requests ---------------------------------------------------------------------------------------------------------------
@@ -157,19 +155,14 @@ class LLMEngine:
         dec_t = torch.tensor(dec, dtype=torch.int32, device=dev)
         now_t = torch.tensor(n_new, dtype=torch.int32, device=dev)
         nh, nkv, hd = self.nh, self.nkv, self.hd
-        h = self.ad.embed(_w(ids))
-        cos, sin = self._L.rope_cache(self.cfg, dev)
+        h = self.ad.embed_tokens(ids, position_ids)
         for li, layer in enumerate(self.layers):
-            at = layer.self_attn
-            x = layer.input_layernorm(h)
-            qkv = _raw(self._L.KR.apply_rope_packed(at.qkv_proj(x), cos, sin, nh + nkv, nh + 2 * nkv, hd, position_ids, neox=True))
+            qkv = self.ad.attn_in(layer, h, position_ids)
             t = qkv.shape[1]
             out, _, _, _ = block_attention(qkv.reshape(t, (nh + 2 * nkv) * hd), self.key_cache[li], self.value_cache[li], enc_t, dec_t, now_t, cu, bt, self.block_size)
-            a = at.o_proj(_w(_raw(out).reshape(1, t, nh * hd)))
-            x, h = layer.post_attention_layernorm(a, residual=h)
-            h = h + self.ad.ffn(layer, x)
+            h = self.ad.attn_out(layer, h, _raw(out).reshape(1, t, nh * hd))
         last = (cu[1:].long() - 1)
-        return _raw(self.ad.head(_w(_raw(h)[:, last])))[0]                             # [num_seqs, vocab]
+        return self.ad.logits(_raw(h)[:, last])[0]                                     # [num_seqs, vocab]
 
     def step(self):
         """One iteration.  Returns [(request id, new token, finished)] for every sequence that produced a token."""

@@ -81,3 +81,19 @@ def test_eos_and_gqa_and_sampling_reproducibility():
     e2 = models.LLMEngine(m, num_blocks=32, block_size=8)
     b = e2.add_request(p, 6, do_sample=True, temperature=0.9, top_k=20)
     assert e2.run_until_done()[b] == r1
+
+
+def test_gpt_layout_through_the_engine():
+    """Learned positions / LayerNorm / tied head: continuous batching reproduces per-request greedy decoding."""
+    paddle.seed(6)
+    cfg = models.gpt_tiny()
+    m = models.GPTForCausalLM(cfg)
+    m.eval()
+    prompts = [torch.randint(1, cfg.vocab_size, (n,)).tolist() for n in (5, 9, 3)]
+    eng = models.LLMEngine(m, num_blocks=24, block_size=4, max_running=2)
+    ids = [eng.add_request(p, 6) for p in prompts]
+    res = eng.run_until_done()
+    for i, p in zip(ids, prompts):
+        ref = models.generate(m, torch.tensor([p]), max_new_tokens=6).as_subclass(torch.Tensor)[0, len(p):].tolist()
+        assert res[i] == ref
+    assert eng.stats["max_running"] <= 2
