@@ -2,8 +2,8 @@
 machine without a GPU; same expression bodies).
 
 Schedules
-  * elementwise group  -> one grid-stride kernel over the flat domain; a second variant moves 4 elements per thread with 8 / 16-byte vector
-    accesses (picked at launch when every pointer is 16-byte aligned); the grid is capped at 148 SMs x 8 CTAs.
+  * elementwise group  -> one grid-stride kernel over the flat domain; a second variant moves 4 elements per thread (8 when a 16-bit tensor is
+    streamed, so that its accesses are 16 bytes wide; picked at launch when every pointer is 16-byte aligned); the grid is capped at 148 SMs x 8 CTAs.
   * group with reductions over the last axis -> a row kernel: one warp per row for rows of <= 256 columns (shuffle reductions, 8 rows per
     CTA), one 256-thread CTA per row up to 2048 columns, one 1024-thread CTA per row beyond (shuffle + one shared-memory exchange).
     Reductions that feed later elementwise work become successive passes over the row (pass s computes every reduction whose input depends
@@ -238,35 +238,43 @@ __device__ inline void st(int* p, long long i, int v) { p[i] = v; }
 __device__ inline void st(long long* p, long long i, long long v) { p[i] = v; }
 __device__ inline void st(bool* p, long long i, bool v) { p[i] = v; }
 __device__ inline void st(unsigned char* p, long long i, int v) { p[i] = (unsigned char)v; }
-// 4 consecutive elements per access
-__device__ inline void ld4(const float* p, long long i, float (&o)[4]) { const float4 v = *reinterpret_cast<const float4*>(p + i); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
-__device__ inline void ld4(const int* p, long long i, int (&o)[4]) { const int4 v = *reinterpret_cast<const int4*>(p + i); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
-__device__ inline void ld4(const __half* p, long long i, float (&o)[4]) {
-  const uint2 v = *reinterpret_cast<const uint2*>(p + i);
-  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+// V consecutive elements per access: raw 16 / 8 / 4-byte chunks, converted element by element in registers
+template <int V, class S> struct __align__((V * sizeof(S)) >= 16 ? 16 : (V * sizeof(S))) CinnRaw { S e[V]; };
+template <int V, class S> __device__ inline void cinn_ld_raw(CinnRaw<V, S>& r, const S* p) {
+  constexpr int B = V * sizeof(S);
+  if constexpr (B % 16 == 0) {
+#pragma unroll
+    for (int k = 0; k < B / 16; ++k) reinterpret_cast<uint4*>(&r)[k] = reinterpret_cast<const uint4*>(p)[k];
+  } else if constexpr (B == 8) {
+    *reinterpret_cast<uint2*>(&r) = *reinterpret_cast<const uint2*>(p);
+  } else {
+    static_assert(B == 4, "vector access of 4, 8 or a multiple of 16 bytes");
+    *reinterpret_cast<unsigned*>(&r) = *reinterpret_cast<const unsigned*>(p);
+  }
 }
-__device__ inline void ld4(const __nv_bfloat16* p, long long i, float (&o)[4]) {
-  const uint2 v = *reinterpret_cast<const uint2*>(p + i);
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
-  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+template <int V, class S> __device__ inline void cinn_st_raw(const CinnRaw<V, S>& r, S* p) {
+  constexpr int B = V * sizeof(S);
+  if constexpr (B % 16 == 0) {
+#pragma unroll
+    for (int k = 0; k < B / 16; ++k) reinterpret_cast<uint4*>(p)[k] = reinterpret_cast<const uint4*>(&r)[k];
+  } else if constexpr (B == 8) {
+    *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(&r);
+  } else {
+    *reinterpret_cast<unsigned*>(p) = *reinterpret_cast<const unsigned*>(&r);
+  }
 }
-__device__ inline void ld4(const bool* p, long long i, bool (&o)[4]) { const uchar4 v = *reinterpret_cast<const uchar4*>(p + i); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
-__device__ inline void ld4(const unsigned char* p, long long i, int (&o)[4]) { const uchar4 v = *reinterpret_cast<const uchar4*>(p + i); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
-__device__ inline void st4(float* p, long long i, const float (&o)[4]) { *reinterpret_cast<float4*>(p + i) = make_float4(o[0], o[1], o[2], o[3]); }
-__device__ inline void st4(int* p, long long i, const int (&o)[4]) { *reinterpret_cast<int4*>(p + i) = make_int4(o[0], o[1], o[2], o[3]); }
-__device__ inline void st4(__half* p, long long i, const float (&o)[4]) {
-  const __half2 a = __floats2half2_rn(o[0], o[1]), b = __floats2half2_rn(o[2], o[3]);
-  uint2 v; v.x = *reinterpret_cast<const unsigned*>(&a); v.y = *reinterpret_cast<const unsigned*>(&b);
-  *reinterpret_cast<uint2*>(p + i) = v;
+template <int V, class S, class T> __device__ inline void ldv(const S* p, long long i, T (&o)[V]) {
+  CinnRaw<V, S> r;
+  cinn_ld_raw<V, S>(r, p + i);
+#pragma unroll
+  for (int u = 0; u < V; ++u) o[u] = ld(&r.e[u], 0);
 }
-__device__ inline void st4(__nv_bfloat16* p, long long i, const float (&o)[4]) {
-  const __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b = __floats2bfloat162_rn(o[2], o[3]);
-  uint2 v; v.x = *reinterpret_cast<const unsigned*>(&a); v.y = *reinterpret_cast<const unsigned*>(&b);
-  *reinterpret_cast<uint2*>(p + i) = v;
+template <int V, class S, class T> __device__ inline void stv(S* p, long long i, const T (&o)[V]) {
+  CinnRaw<V, S> r;
+#pragma unroll
+  for (int u = 0; u < V; ++u) st(&r.e[u], 0, o[u]);
+  cinn_st_raw<V, S>(r, p + i);
 }
-__device__ inline void st4(bool* p, long long i, const bool (&o)[4]) { *reinterpret_cast<uchar4*>(p + i) = make_uchar4(o[0], o[1], o[2], o[3]); }
-__device__ inline void st4(unsigned char* p, long long i, const int (&o)[4]) { *reinterpret_cast<uchar4*>(p + i) = make_uchar4(o[0], o[1], o[2], o[3]); }
 template <class T> __device__ inline T cinn_warp_reduce(int op, T v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = cinn_comb(op, v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -538,28 +546,29 @@ def host_source(spec):
 SM_COUNT = 148
 
 
-def _vec_ok(spec):
-    if spec.cols % 4 != 0:
-        return False
+def _vec_width(spec):
+    """Elements per thread of the vector variant: 8 when a 16-bit (or narrower) tensor is streamed (16-byte accesses for it), else 4; 0 = none."""
     body = _Body(spec)
+    sizes = []
     for n in list(spec.inputs) + list(spec.outputs):
-        if n.kind == "in":
-            _, uses_j = body.in_index(n, "full")
-            if not uses_j:
-                continue
-        if _ESIZE[n.dtype] == 8:
-            return False
-    return True
+        if n.kind == "in" and not body.in_index(n, "full")[1]:
+            continue                                       # read once per row, not streamed
+        sizes.append(_ESIZE[n.dtype])
+    if not sizes:
+        return 0
+    if min(sizes) <= 2 and spec.cols % 8 == 0:
+        return 8
+    return 4 if spec.cols % 4 == 0 else 0
 
 
 def _flat_kernels(spec):
-    """Elementwise group: scalar and 4-wide kernels."""
+    """Elementwise group: scalar kernel + a V-wide vector kernel."""
     body = _Body(spec)
     in_pos = {n.id: k for k, n in enumerate(spec.inputs)}
     closure = _Plan(spec).full_closure(spec.outputs)
     idx = {n.id: body.in_index(n, "full") for n in closure if n.kind == "in"}
-    need_row = any(rp is not None for rp, _ in idx.values())
-    same = {nid: (tuple(n.shape) == spec.full) for nid, n in ((n.id, n) for n in closure if n.kind == "in")}
+    same = {n.id: (tuple(n.shape) == spec.full) for n in closure if n.kind == "in"}
+    need_rj = any(not same[i] for i in idx)
 
     def ref(a):
         return f"v{a.id}", compute_type(a.dtype)
@@ -575,7 +584,7 @@ def _flat_kernels(spec):
     L.append(f"extern \"C\" __global__ void __launch_bounds__(256) cinn_k_flat({_params(spec)}) {{")
     L.append(f"  const long long n = rows * {spec.cols}LL;")
     L.append("  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n; e += gridDim.x * 256LL) {")
-    if need_row or any(uj and not same[i] for i, (rp, uj) in idx.items()):
+    if need_rj:
         L.append(f"    const long long row = e / {spec.cols}LL; const long long j = e - row * {spec.cols}LL; (void)row; (void)j;")
     for n in closure:
         T = compute_type(n.dtype)
@@ -586,22 +595,23 @@ def _flat_kernels(spec):
     for k, n in enumerate(spec.outputs):
         L.append(f"    st(out{k}, e, v{n.id});")
     L.append("  }\n}")
-    if _vec_ok(spec):
-        L.append(f"extern \"C\" __global__ void __launch_bounds__(256) cinn_k_vec4({_params(spec)}) {{")
-        L.append(f"  const long long ng = rows * {spec.cols // 4}LL;")
+    V = _vec_width(spec)
+    if V:
+        L.append(f"extern \"C\" __global__ void __launch_bounds__(256) cinn_k_vec{V}({_params(spec)}) {{")
+        L.append(f"  const long long ng = rows * {spec.cols // V}LL;")
         L.append("  for (long long g = blockIdx.x * 256LL + threadIdx.x; g < ng; g += gridDim.x * 256LL) {")
-        L.append(f"    const long long e = g * 4; const long long row = e / {spec.cols}LL; const long long j = e - row * {spec.cols}LL; (void)row; (void)j;")
+        L.append(f"    const long long e = g * {V}; const long long row = e / {spec.cols}LL; const long long j = e - row * {spec.cols}LL; (void)row; (void)j;")
         for n in closure:
             if n.kind == "in":
                 T = compute_type(n.dtype)
                 if idx[n.id][1]:
-                    L.append(f"    {T} a{n.id}[4]; ld4(in{in_pos[n.id]}, {offset(n, 'j')}, a{n.id});")
+                    L.append(f"    {T} a{n.id}[{V}]; ldv<{V}>(in{in_pos[n.id]}, {offset(n, 'j')}, a{n.id});")
                 else:
                     L.append(f"    const {T} s{n.id} = ld(in{in_pos[n.id]}, {offset(n, 'j')});")
         for k, n in enumerate(spec.outputs):
-            L.append(f"    {compute_type(n.dtype)} o{k}[4];")
+            L.append(f"    {compute_type(n.dtype)} o{k}[{V}];")
         L.append("#pragma unroll")
-        L.append("    for (int u = 0; u < 4; ++u) {")
+        L.append(f"    for (int u = 0; u < {V}; ++u) {{")
         for n in closure:
             T = compute_type(n.dtype)
             if n.kind == "in":
@@ -612,7 +622,7 @@ def _flat_kernels(spec):
             L.append(f"      o{k}[u] = v{n.id};")
         L.append("    }")
         for k, n in enumerate(spec.outputs):
-            L.append(f"    st4(out{k}, e, o{k});")
+            L.append(f"    stv<{V}>(out{k}, e, o{k});")
         L.append("  }\n}")
     return "\n".join(L)
 
@@ -667,8 +677,9 @@ def cuda_source(spec):
     else:
         k = _flat_kernels(spec)
         launch = f"  const long long n = rows * {spec.cols}LL;\n"
-        if _vec_ok(spec):
-            launch += (f"  if (allow_vec) {{ cinn_k_vec4<<<cinn_grid((n / 4 + 255) / 256, {cap}), 256, 0, (cudaStream_t)stream>>>({_call_args(spec)}); "
+        V = _vec_width(spec)
+        if V:
+            launch += (f"  if (allow_vec) {{ cinn_k_vec{V}<<<cinn_grid((n / {V} + 255) / 256, {cap}), 256, 0, (cudaStream_t)stream>>>({_call_args(spec)}); "
                        "return (int)cudaGetLastError(); }\n")
         launch += f"  cinn_k_flat<<<cinn_grid((n + 255) / 256, {cap}), 256, 0, (cudaStream_t)stream>>>({_call_args(spec)});\n"
     return (_CUDA_PRELUDE + "\n" + k + "\n\n" + clamp + "extern \"C\" int cinn_launch(void** in, void** out, void* stream, int allow_vec, long long rows) {\n  (void)allow_vec;\n"

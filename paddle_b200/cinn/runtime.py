@@ -44,7 +44,8 @@ def compile_source(src, target, keep_source=True):
         stats["cache_hits"] += 1
         return so
     ext = "cu" if target == "cuda" else "cc"
-    path = os.path.join(_CACHE, f"k_{target}_{tag}.{ext}")
+    final_src = os.path.join(_CACHE, f"k_{target}_{tag}.{ext}")
+    path = os.path.join(_CACHE, f"k_{target}_{tag}.{os.getpid()}.{ext}")       # per-process names: the ranks of a job compile the same kernel at once
     with open(path, "w") as f:
         f.write(src)
     tmp = so + f".tmp{os.getpid()}"
@@ -60,7 +61,9 @@ def compile_source(src, target, keep_source=True):
         raise CompileError(f"{' '.join(cmd)}\n{r.stderr[-4000:]}")
     os.replace(tmp, so)
     stats["compiled"] += 1
-    if not keep_source:
+    if keep_source:
+        os.replace(path, final_src)
+    else:
         os.remove(path)
     return so
 
