@@ -46,7 +46,7 @@ def backward_spec(spec, need_grad):
     in_index = {n.id: k for k, n in enumerate(spec.inputs)}
     for n in spec.nodes:
         if n.kind == "in":
-            fwd[n.id] = b.node("in", "load", [], n.shape, n.dtype, "in", {"src": ("in", in_index[n.id])})
+            fwd[n.id] = b.node("in", "load", [], n.shape, n.dtype, "in", {"src": ("in", in_index[n.id]), "view": n.attrs.get("view", False)})
         else:
             fwd[n.id] = b.node(n.kind, n.op, [fwd[a.id] if isinstance(a, Node) else a for a in n.args], n.shape, n.dtype, n.space)
     adj = {}                                        # forward node id -> [contribution nodes] (in that node's space)

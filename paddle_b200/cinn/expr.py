@@ -57,7 +57,7 @@ class GroupBuilder:
     def __init__(self, full):
         self.full = tuple(int(d) for d in full)
         self.nodes = []
-        self.inputs = {}          # (ir value id) -> input node
+        self.inputs = {}          # (ir value id, shape it is read as) -> input node
         self.by_value = {}        # ir value id -> node that computes it inside the group
 
     # -- shape classes
@@ -78,15 +78,33 @@ class GroupBuilder:
         self.nodes.append(n)
         return n
 
-    def input(self, value_id, shape, dtype):
-        if value_id in self.by_value:
+    def input(self, value_id, shape, dtype, view=None):
+        """Input node of an outside value.  `view`: read the (contiguous) tensor under another shape with the same number of elements -
+        how per-channel statistics [C] line up with [N, C, H, W]."""
+        if value_id in self.by_value and view is None:
             return self.by_value[value_id]
-        if value_id not in self.inputs:
+        shape = tuple(int(d) for d in (view if view is not None else shape))
+        key = (value_id, shape)
+        if key not in self.inputs:
             if dtype not in SUPPORTED_DTYPES:
                 raise Unsupported(f"input dtype {dtype}")
-            n = self._add(Node("in", "load", [], shape, dtype, {"value": value_id}, space="in"))
-            self.inputs[value_id] = n
-        return self.inputs[value_id]
+            n = self._add(Node("in", "load", [], shape, dtype, {"value": value_id, "view": view is not None}, space="in"))
+            self.inputs[key] = n
+        return self.inputs[key]
+
+    def view(self, node, shape):
+        """The same outside tensor read under another shape."""
+        if not isinstance(node, Node) or node.kind != "in":
+            raise Unsupported("only values from outside the group can be re-viewed")
+        n = 1
+        for d in shape:
+            n *= int(d)
+        m = 1
+        for d in node.shape:
+            m *= d
+        if n != m:
+            raise Unsupported("view changes the number of elements")
+        return self.input(node.attrs["value"], None, node.dtype, view=shape)
 
     def ew(self, op, args, shape, dtype):
         space = self.space_of(shape)
@@ -280,6 +298,126 @@ class Frontend:
             inner = self.g.ew("mul", [self.g.ew("add", [x, self.g.ew("mul", [x3, 0.044715], s, d)], s, d), math.sqrt(2.0 / math.pi)], s, d)
             return self.g.ew("mul", [self.g.ew("mul", [x, 0.5], s, d), self.g.ew("add", [self.g.ew("tanh", [inner], s, d), 1.0], s, d)], s, d)
         raise Unsupported("gelu mode")
+
+    def op_relu6(self, a, k, s, d):
+        if k.get("inplace"):
+            raise Unsupported("in-place activation")
+        return self.g.ew("minimum", [self.g.ew("maximum", [a[0], 0.0], s, d), 6.0], s, d)
+
+    def op_hardtanh(self, a, k, s, d):
+        lo, hi = k.get("min_val", a[1] if len(a) > 1 else -1.0), k.get("max_val", a[2] if len(a) > 2 else 1.0)
+        if k.get("inplace") or not (_is_num(lo) and _is_num(hi)):
+            raise Unsupported("hardtanh signature")
+        return self.g.ew("minimum", [self.g.ew("maximum", [a[0], float(lo)], s, d), float(hi)], s, d)
+
+    def op_elu(self, a, k, s, d):
+        alpha = k.get("alpha", a[1] if len(a) > 1 else 1.0)
+        if k.get("inplace") or not _is_num(alpha):
+            raise Unsupported("elu signature")
+        x = a[0]
+        neg = self.g.ew("mul", [self.g.ew("expm1", [x], s, d), float(alpha)], s, d)
+        return self.g.ew("where", [self.g.ew("gt", [x, 0.0], s, "bool"), x, neg], s, d)
+
+    def op_selu(self, a, k, s, d):
+        if k.get("inplace") or len(a) != 1:
+            raise Unsupported("selu signature")
+        alpha, scale = 1.6732632423543772, 1.0507009873554805
+        x = a[0]
+        neg = self.g.ew("mul", [self.g.ew("expm1", [x], s, d), alpha], s, d)
+        return self.g.ew("mul", [self.g.ew("where", [self.g.ew("gt", [x, 0.0], s, "bool"), x, neg], s, d), scale], s, d)
+
+    def _softplus1(self, x, s, d):
+        sp = self.g.ew("log1p", [self.g.ew("exp", [x], s, d)], s, d)
+        return self.g.ew("where", [self.g.ew("gt", [x, 20.0], s, "bool"), x, sp], s, d)
+
+    def op_mish(self, a, k, s, d):
+        if k.get("inplace") or len(a) != 1:
+            raise Unsupported("mish signature")
+        return self.g.ew("mul", [a[0], self.g.ew("tanh", [self._softplus1(a[0], s, d)], s, d)], s, d)
+
+    def op_log_sigmoid(self, a, k, s, d):
+        if len(a) != 1 or k:
+            raise Unsupported("log_sigmoid signature")
+        x = a[0]
+        t = self.g.ew("log1p", [self.g.ew("exp", [self.g.ew("neg", [self.g.ew("abs", [x], s, d)], s, d)], s, d)], s, d)
+        return self.g.ew("sub", [self.g.ew("minimum", [x, 0.0], s, d), t], s, d)
+
+    op_logsigmoid = op_log_sigmoid
+
+    def op_tanhshrink(self, a, k, s, d):
+        if len(a) != 1 or k:
+            raise Unsupported("tanhshrink signature")
+        return self.g.ew("sub", [a[0], self.g.ew("tanh", [a[0]], s, d)], s, d)
+
+    def op_softsign(self, a, k, s, d):
+        if len(a) != 1 or k:
+            raise Unsupported("softsign signature")
+        return self.g.ew("div", [a[0], self.g.ew("add", [self.g.ew("abs", [a[0]], s, d), 1.0], s, d)], s, d)
+
+    # -- normalisations over the last axis (a lone norm stays on its hand-written kernel: groups need two recorded ops)
+    def _affine(self, y, w, b, s, d):
+        if w is not None:
+            if not isinstance(w, Node):
+                raise Unsupported("norm weight")
+            y = self.g.ew("mul", [y, w], s, d)
+        if b is not None:
+            if not isinstance(b, Node):
+                raise Unsupported("norm bias")
+            y = self.g.ew("add", [y, b], s, d)
+        return y
+
+    def op_layer_norm(self, a, k, s, d):
+        x = a[0]
+        shape = k.get("normalized_shape", a[1] if len(a) > 1 else None)
+        w, b = k.get("weight", a[2] if len(a) > 2 else None), k.get("bias", a[3] if len(a) > 3 else None)
+        eps = k.get("eps", k.get("epsilon", a[4] if len(a) > 4 else 1e-5))
+        if isinstance(shape, int):
+            shape = [shape]
+        if not isinstance(x, Node) or x.shape != self.g.full or d not in FLOATS or list(shape or []) != [self.g.full[-1]] or not _is_num(eps):
+            raise Unsupported("layer_norm over more than the last axis")
+        rs, n = self.g.full[:-1] + (1,), self.g.full[-1]
+        mu = self.g.ew("mul", [self.g.reduce("sum", x, True, d), 1.0 / n], rs, d)
+        xc = self.g.ew("sub", [x, mu], s, d)
+        var = self.g.ew("mul", [self.g.reduce("sum", self.g.ew("mul", [xc, xc], s, d), True, d), 1.0 / n], rs, d)
+        inv = self.g.ew("rsqrt", [self.g.ew("add", [var, float(eps)], rs, d)], rs, d)
+        return self._affine(self.g.ew("mul", [xc, inv], s, d), w, b, s, d)
+
+    def op_rms_norm(self, a, k, s, d):
+        x = a[0]
+        w = k.get("weight", a[1] if len(a) > 1 else None)
+        eps = k.get("eps", k.get("epsilon", a[2] if len(a) > 2 else 1e-6))
+        b = k.get("bias", a[3] if len(a) > 3 else None)
+        res = k.get("residual", a[4] if len(a) > 4 else None)
+        if not isinstance(x, Node) or x.shape != self.g.full or d not in FLOATS or res is not None or not _is_num(eps) or len(a) > 5:
+            raise Unsupported("rms_norm signature")
+        rs, n = self.g.full[:-1] + (1,), self.g.full[-1]
+        ms = self.g.ew("mul", [self.g.reduce("sum", self.g.ew("mul", [x, x], s, d), True, d), 1.0 / n], rs, d)
+        inv = self.g.ew("rsqrt", [self.g.ew("add", [ms, float(eps)], rs, d)], rs, d)
+        return self._affine(self.g.ew("mul", [x, inv], s, d), w, b, s, d)
+
+    def op_batch_norm(self, a, k, s, d):
+        """Inference form only: y = (x - mean_c) * rsqrt(var_c + eps) * w_c + b_c with the channel on axis 1 (axis -1 for 2-D inputs)."""
+        x = a[0]
+        mean, var = k.get("running_mean", a[1] if len(a) > 1 else None), k.get("running_var", a[2] if len(a) > 2 else None)
+        w, b = k.get("weight", a[3] if len(a) > 3 else None), k.get("bias", a[4] if len(a) > 4 else None)
+        training = k.get("training", a[5] if len(a) > 5 else False)
+        eps = k.get("eps", k.get("epsilon", a[7] if len(a) > 7 else 1e-5))
+        if training or not isinstance(x, Node) or not isinstance(mean, Node) or not isinstance(var, Node) or len(s) < 2 or d not in FLOATS or not _is_num(eps):
+            raise Unsupported("batch_norm in training mode / without running statistics")
+        if k.get("data_format", "NCHW") not in ("NCHW", "NCL", "NCDHW", "NC"):
+            raise Unsupported("batch_norm layout")
+        cshape = (s[1],) + (1,) * (len(s) - 2)
+
+        def per_channel(t):
+            if t is None:
+                return None
+            if not isinstance(t, Node) or t.shape != (s[1],):
+                raise Unsupported("batch_norm statistics shape")
+            return self.g.view(t, cshape) if len(s) > 2 else t
+
+        mean, var, w, b = (per_channel(t) for t in (mean, var, w, b))
+        inv = self.g.ew("rsqrt", [self.g.ew("add", [var, float(eps)], s, d)], s, d)        # broadcast inputs: evaluated per element, read once per row
+        return self._affine(self.g.ew("mul", [self.g.ew("sub", [x, mean], s, d), inv], s, d), w, b, s, d)
 
     def op_softplus(self, a, k, s, d):
         beta, thr = k.get("beta", a[1] if len(a) > 1 else 1.0), k.get("threshold", a[2] if len(a) > 2 else 20.0)

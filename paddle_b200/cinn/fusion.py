@@ -16,7 +16,7 @@ from .expr import Frontend, GroupBuilder, Node, Unsupported, dtype_name
 from .runtime import CompileError, FusedKernel
 
 _PATTERN_OPS = {"swiglu"}                                                   # ops DRR patterns introduce that lower to primitives
-_ROW_OPS = {"sum", "mean", "amax", "amin", "softmax", "log_softmax"}       # their domain is the INPUT's shape
+_ROW_OPS = {"sum", "mean", "amax", "amin", "softmax", "log_softmax", "layer_norm", "rms_norm"}       # their domain is the INPUT's shape
 
 
 class Group:
@@ -39,7 +39,7 @@ class Group:
         remap = {}
         for n in other.gb.nodes:
             if n.kind == "in":
-                v = n.attrs["value"]
+                v = (n.attrs["value"], n.shape)
                 if v in self.gb.inputs:
                     remap[id(n)] = self.gb.inputs[v]
                     continue

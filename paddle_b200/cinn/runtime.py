@@ -76,6 +76,13 @@ def _load(so):
         return lib
 
 
+def _numel(shape):
+    n = 1
+    for d in shape:
+        n *= int(d)
+    return n
+
+
 class FusedKernel:
     """Callable for one fusion group: tensors in operand order -> result tensor(s) in result order."""
 
@@ -162,12 +169,13 @@ class FusedKernel:
                 grads.append(None)
                 continue
             acc = None
+            seen = spec.inputs[k].shape                       # the shape the group read this tensor under (differs from t.shape for a view)
             for kind, i in plan.parts[k]:
                 p = res[i] if kind == "out" else gouts[i]
-                if tuple(p.shape) != tuple(t.shape):
-                    p = p.sum_to_size(t.shape) if p.dim() >= t.dim() else p.reshape(t.shape)
+                if tuple(p.shape) != tuple(seen):
+                    p = p.sum_to_size(seen) if p.dim() >= len(seen) else p.reshape(seen)
                 acc = p if acc is None else acc + p
-            grads.append(None if acc is None else acc.to(t.dtype))
+            grads.append(None if acc is None else acc.reshape(t.shape).to(t.dtype))
         return grads
 
     def _run(self, tensors):
@@ -177,6 +185,8 @@ class FusedKernel:
         raw = []
         for t, n in zip(tensors, spec.inputs):
             t = t.as_subclass(torch.Tensor) if type(t) is not torch.Tensor else t
+            if n.attrs.get("view") and tuple(t.shape) != n.shape and t.numel() == _numel(n.shape):
+                t = t.contiguous().reshape(n.shape)                 # the group reads this tensor under another shape (per-channel statistics)
             if tuple(t.shape) != n.shape or t.dtype != _TORCH_DT[n.dtype]:
                 raise TypeError(f"{spec.name}: operand is {list(t.shape)} {t.dtype}, the kernel was generated for {list(n.shape)} {n.dtype}")
             raw.append(t.detach().contiguous())

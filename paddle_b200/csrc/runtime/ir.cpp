@@ -447,6 +447,14 @@ static int pass_identity_elim(Program& p) {
       const Attr* bi = find_attr(op, "bias");
       identity = sc && std::holds_alternative<double>(*sc) && std::get<double>(*sc) == 1.0 && (!bi || (std::holds_alternative<double>(*bi) && std::get<double>(*bi) == 0.0));
     }
+    else if ((n == "dropout" || n == "dropout2d" || n == "dropout3d" || n == "alpha_dropout" || n == "feature_alpha_dropout") && op.operands.size() == 1 && in == out) {
+      // inference clone / eval mode: dropout(training=False) in the default upscale_in_train mode, or p = 0, passes its input through
+      auto is_false = [&](const char* k) { const Attr* a = find_attr(op, k); return a && std::holds_alternative<bool>(*a) && !std::get<bool>(*a); };
+      auto is_zero = [&](const char* k) { const Attr* a = find_attr(op, k); return a && ((std::holds_alternative<double>(*a) && std::get<double>(*a) == 0.0) || (std::holds_alternative<int64_t>(*a) && std::get<int64_t>(*a) == 0)); };
+      auto downscale = [&](const char* k) { const Attr* a = find_attr(op, k); return a && std::holds_alternative<std::string>(*a) && std::get<std::string>(*a) == "downscale_in_infer"; };
+      const bool eval = is_false("ktraining") || is_false("a3");
+      identity = (is_zero("a1") || is_zero("kp")) || (eval && !downscale("a4") && !downscale("kmode"));
+    }
     if (identity) {
       p.replace_all_uses(op.results[0], op.operands[0]);
       op.erased = true;

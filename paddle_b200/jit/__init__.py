@@ -166,23 +166,52 @@ class StaticFunction:
         new, report = cinn.compile_program(infer, outs)
         return static.Executor(), new, [v.name for v in ins], outs, not isinstance(out, (list, tuple)), report
 
-    def _call_cinn(self, args):
-        key = _sig(args, {}) + (bool(torch.is_grad_enabled() and self._layer is not None and self._layer.training),)
-        if key not in self._cinn:
-            try:
-                self._cinn[key] = self._cinn_entry(args)
-            except Exception as e:  # noqa: BLE001  (untraceable function): eager
-                if os.environ.get("B200_JIT_DEBUG"):
-                    raise
-                self._cinn[key] = None
-                self._cinn_error = e
-        entry = self._cinn[key]
-        if entry is None:
-            return self._fn(*args)
+    def _run_cinn_entry(self, entry, args):
         exe, prog, feeds, fetch, single, _ = entry
         res = exe.run(prog, feed=dict(zip(feeds, [a for a in args if isinstance(a, torch.Tensor)])), fetch_list=fetch, return_numpy=False)
         res = [o.as_subclass(Tensor) if isinstance(o, torch.Tensor) else o for o in res]
         return res[0] if single else res
+
+    def _call_cinn(self, args):
+        key = _sig(args, {}) + (bool(torch.is_grad_enabled() and self._layer is not None and self._layer.training),)
+        if key not in self._cinn:
+            # First call with this signature: trace + compile, then CHECK the compiled program against the function itself on the real
+            # arguments (same RNG state).  A forward that leaves the recorded tensor type (`as_subclass(torch.Tensor)` fast paths, .numpy(),
+            # python branching on values) bakes trace-time constants into the program; such a function keeps running as written.
+            try:
+                entry = self._cinn_entry(args)
+            except Exception as e:  # noqa: BLE001  (untraceable function): eager
+                if os.environ.get("B200_JIT_DEBUG"):
+                    raise
+                entry, self._cinn_error = None, e
+            cpu_rng = torch.get_rng_state()
+            cuda_rng = torch.cuda.get_rng_state_all() if torch.cuda.is_available() else None
+            ref = self._fn(*args)
+            if entry is not None:
+                now_cpu = torch.get_rng_state()
+                torch.set_rng_state(cpu_rng)
+                if cuda_rng is not None:
+                    now_cuda = torch.cuda.get_rng_state_all()
+                    torch.cuda.set_rng_state_all(cuda_rng)
+                try:
+                    with torch.no_grad():
+                        got = self._run_cinn_entry(entry, args)
+                    if not _same_tree(ref, got):
+                        entry, self._cinn_error = None, RuntimeError("the traced program does not reproduce the function (it leaves the recorded tensor type); running eagerly")
+                except Exception as e:  # noqa: BLE001
+                    if os.environ.get("B200_JIT_DEBUG"):
+                        raise
+                    entry, self._cinn_error = None, e
+                finally:
+                    torch.set_rng_state(now_cpu)
+                    if cuda_rng is not None:
+                        torch.cuda.set_rng_state_all(now_cuda)
+            self._cinn[key] = entry
+            return ref
+        entry = self._cinn[key]
+        if entry is None:
+            return self._fn(*args)
+        return self._run_cinn_entry(entry, args)
 
     def cinn_report(self, *args):
         """FusionResult of the program compiled for these arguments (None when it was not compiled)."""
@@ -284,6 +313,21 @@ def _clone_tree(o):
     if isinstance(o, dict):
         return {k: _clone_tree(v) for k, v in o.items()}
     return o
+
+
+def _same_tree(a, b):
+    """Same structure, and tensors equal within the tolerance of a re-associated / once-rounded computation."""
+    if isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor):
+        if a.shape != b.shape or a.dtype != b.dtype:
+            return False
+        if not a.is_floating_point():
+            return bool(torch.equal(a, b))
+        tol = {torch.float16: 2e-2, torch.bfloat16: 5e-2}.get(a.dtype, 1e-3)
+        x, y = a.detach().float(), b.detach().float()
+        return bool(torch.allclose(x, y, rtol=tol, atol=tol * max(1.0, float(x.abs().max()) if x.numel() else 1.0), equal_nan=True))
+    if isinstance(a, (list, tuple)) and isinstance(b, (list, tuple)):
+        return len(a) == len(b) and all(_same_tree(x, y) for x, y in zip(a, b))
+    return isinstance(a, torch.Tensor) == isinstance(b, torch.Tensor)
 
 
 def _needs_grad(sf, args):

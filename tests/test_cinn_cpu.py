@@ -521,3 +521,70 @@ def test_groups_that_differ_only_in_leading_extents_share_one_object():
     g = np.random.default_rng(3).standard_normal((2, 1, 1)).astype(np.float32)
     rep = _run_both(lambda x, g: F.softmax(x * g, -1), dict(x=x, g=g), rtol=2e-5, atol=1e-7, expect_kernels=1)
     assert rep.groups[0]["kernel"].source("cuda") not in srcs
+
+
+def test_to_static_cinn_refuses_a_trace_that_bakes_constants():
+    """A forward that leaves the recorded tensor type computes on trace-time placeholders; the first-call check catches it and the function keeps
+    running as written."""
+    class Leaky(paddle.nn.Layer):
+        def forward(self, x):
+            raw = x.as_subclass(torch.Tensor)                       # invisible to the tracer
+            return (paddle.tanh(x) * 2.0 + raw.cos().as_subclass(paddle.Tensor)) * 0.5
+
+    net = Leaky()
+    net.eval()
+    f = paddle.jit.to_static(net, backend="CINN")
+    for seed in (0, 1):
+        x = paddle.to_tensor(np.random.default_rng(seed).standard_normal((4, 8)).astype("float32"))
+        with paddle.no_grad():
+            got = f(x)
+        t = x.as_subclass(torch.Tensor)
+        assert torch.allclose(got.as_subclass(torch.Tensor), (torch.tanh(t) * 2.0 + torch.cos(t)) * 0.5, atol=1e-6)
+    assert f.forward.cinn_report(x) is None and "does not reproduce" in str(f.forward._cinn_error)
+
+
+def test_activation_zoo_and_recorded_norms():
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((6, 24)).astype(np.float32) * 3
+    w, b = rng.standard_normal((24,)).astype(np.float32), rng.standard_normal((24,)).astype(np.float32)
+
+    def acts(x):
+        s = F.relu6(x) + F.elu(x, 0.7) + F.selu(x) + F.mish(x) + F.leaky_relu(x, 0.2) + F.softplus(x) + F.hardswish(x) + F.log_sigmoid(x) + F.tanhshrink(x)
+        return s + F.softsign(x) + F.hardtanh(x, -2.0, 1.5) + F.hardsigmoid(x) + F.gelu(x, approximate=True)
+
+    rep = _run_both(acts, dict(x=x), rtol=2e-5, atol=2e-5, expect_kernels=1)
+    assert rep.rejected == []
+
+    def norms(x, w, b):
+        h = F.layer_norm(x, [24], w, b, 1e-5)                 # recorded as ONE op, decomposed inside the group
+        h = F.gelu(h) + x
+        return F.rms_norm(h, w, 1e-6) * 0.5, F.layer_norm(h, 24)
+
+    rep = _run_both(norms, dict(x=x, w=w, b=b), rtol=3e-5, atol=3e-5, expect_kernels=1)
+    assert rep.groups[0]["kind"] == "reduce" and {"layer_norm", "rms_norm", "gelu"} <= set(rep.groups[0]["ops"])
+    # a lone norm is not a group: it keeps its hand-written kernel
+    rep = _run_both(lambda x, w, b: F.layer_norm(x, [24], w, b), dict(x=x, w=w, b=b), expect_kernels=0)
+
+
+def test_batch_norm_inference_folds_into_the_pointwise_tail():
+    """conv -> BN(eval) -> relu -> + skip -> relu: everything after the convolution is one kernel; the per-channel statistics [C] are read as [C, 1, 1]."""
+    paddle.seed(0)
+    conv, bn = paddle.nn.Conv2D(4, 8, 3, padding=1), paddle.nn.BatchNorm2D(8)
+    bn._mean.set_value(paddle.randn([8]) * 0.3)
+    bn._variance.set_value(paddle.rand([8]) + 0.5)
+    bn.weight.set_value(paddle.randn([8]))
+    bn.bias.set_value(paddle.randn([8]))
+    conv.eval()
+    bn.eval()
+    x = np.random.default_rng(1).standard_normal((2, 4, 6, 6)).astype(np.float32)
+    skip = np.random.default_rng(2).standard_normal((2, 8, 6, 6)).astype(np.float32)
+    rep = _run_both(lambda x, skip: F.relu(F.relu(bn(conv(x))) + skip), dict(x=x, skip=skip), rtol=1e-5, atol=1e-5, expect_kernels=1)
+    g = rep.groups[0]
+    assert g["ops"] == ["batch_norm", "relu", "add", "relu"] and g["kind"] == "elementwise"
+    # the view survives differentiation: gradients of the statistics come back in their own shape
+    k = g["kernel"]
+    ins = [torch.randn(n.shape if not n.attrs.get("view") else (8,)) for n in k.spec.inputs]
+    ins = [t.abs() + 0.5 if i == 2 else t for i, t in enumerate(ins)]
+    a = [t.clone().requires_grad_(True) for t in ins]
+    k(*a).as_subclass(torch.Tensor).sum().backward()
+    assert all(t.grad is not None and t.grad.shape == t.shape for t in a)
