@@ -383,7 +383,9 @@ def save(layer, path, input_spec=None, **configs):
         was_training = bool(getattr(layer, "training", False))
         layer.eval()
         try:
-            spec["program"] = pickle.dumps(_trace_program(layer, spec["input_spec"]))
+            traced = _trace_program(layer, spec["input_spec"])
+            _check_trace(layer, traced, spec["input_spec"])
+            spec["program"] = pickle.dumps(traced)
         except Exception as e:  # noqa: BLE001
             spec["program"] = None
             trace_error = e
@@ -398,6 +400,30 @@ def save(layer, path, input_spec=None, **configs):
                                + (f" ({type(trace_error).__name__}: {trace_error})" if "trace_error" in locals() else " (pass input_spec so that the forward can be traced)"))
     with open(path + ".pdmodel", "wb") as f:
         pickle.dump(spec, f)
+
+
+def _check_trace(layer, traced, input_spec):
+    """Run the traced program and the layer on random inputs of the traced sizes: a forward that leaves the recorded tensor type (raw-tensor
+    fast paths, .numpy(), python branches on values) bakes trace-time constants into the program, and a saved model must not be silently wrong."""
+    from .. import static
+
+    g = torch.Generator().manual_seed(0)
+    ins = []
+    for shape, dtype, _ in input_spec:
+        dt = getattr(torch, dtype.replace("paddle.", "").replace("torch.", ""), torch.float32)
+        dims = [1 if (d is None or d < 0) else int(d) for d in shape]
+        t = torch.randn(dims, generator=g) if dt.is_floating_point else torch.randint(0, 2, dims, generator=g)
+        ins.append(t.to(dt).as_subclass(Tensor))
+    dev = next((p.device for p in layer.parameters()), torch.device("cpu"))
+    ins = [t.to(dev) for t in ins]
+    with torch.no_grad():
+        ref = layer(*ins)
+        prog = traced["program"]
+        prog._fetch_alias = {id(t): vid for vid, t in enumerate(prog._keep)}
+        got = static.Executor().run(prog, feed=dict(zip(traced["feeds"], ins)), fetch_list=[prog._keep[v] for v in traced["fetch_vids"]], return_numpy=False)
+    ref = list(ref) if isinstance(ref, (list, tuple)) else [ref]
+    if not _same_tree(ref, list(got)):
+        raise RuntimeError("the traced program does not reproduce the layer's forward (it computes on raw tensors / python values the tracer cannot see)")
 
 
 def _trace_program(layer, input_spec):
@@ -415,6 +441,8 @@ def _trace_program(layer, input_spec):
         if isinstance(fwd, StaticFunction):
             layer.forward = fwd
     outs = list(out) if isinstance(out, (list, tuple)) else [out]
+    if not all(isinstance(o, torch.Tensor) and id(o) in prog._fetch_alias for o in outs):
+        raise RuntimeError("the forward's results are not values of the traced program (it computes them on raw tensors / python values the tracer cannot see)")
     infer = prog.clone(for_test=True)
     return {"program": infer, "feeds": [v.name for v in ins], "fetch_vids": [prog._fetch_alias[id(o)] for o in outs], "single": not isinstance(out, (list, tuple))}
 

@@ -348,3 +348,41 @@ def test_sparse_conv_pool_rulebook_matches_dense():
     r2 = torch.nn.functional.conv2d(x2.permute(0,3,1,2), w2.permute(3,2,0,1), None, 1, 1).permute(0,2,3,1)
     act2 = torch.nn.functional.conv2d((x2.abs().sum(-1,keepdim=True)>0).float().permute(0,3,1,2), torch.ones(1,1,3,3), None, 1, 1)[:,0]>0
     assert torch.allclose(o2[act2], r2[act2], atol=1e-4)
+
+
+def test_jit_save_refuses_a_trace_that_bakes_constants(tmp_path):
+    """A locally-defined layer is saved as a traced program; when its forward computes on raw tensors the trace is wrong and save says so."""
+    import torch
+
+    import paddle_b200 as paddle
+    from paddle_b200.static import InputSpec
+
+    class Fine(paddle.nn.Layer):
+        def __init__(self):
+            super().__init__()
+            self.fc = paddle.nn.Linear(4, 3)
+
+        def forward(self, x):
+            return paddle.tanh(self.fc(x))
+
+    class Leaky(Fine):
+        def forward(self, x):
+            return paddle.tanh(self.fc(x)) + x.as_subclass(torch.Tensor).sum(-1, keepdim=True).cos().as_subclass(paddle.Tensor)
+
+    class Blind(Fine):
+        def forward(self, x):
+            return (self.fc(x).as_subclass(torch.Tensor) * 2.0).as_subclass(paddle.Tensor)
+
+    spec = [InputSpec([2, 4], "float32", "x")]
+    paddle.jit.save(Fine(), str(tmp_path / "fine"), input_spec=spec)
+    x = paddle.randn([2, 4])
+    m = Fine()
+    paddle.jit.save(m, str(tmp_path / "fine2"), input_spec=spec)
+    loaded = paddle.jit.load(str(tmp_path / "fine2"))
+    assert torch.allclose(loaded(x).as_subclass(torch.Tensor), m(x).as_subclass(torch.Tensor), atol=1e-6)
+    import pytest
+
+    with pytest.raises(RuntimeError, match="does not reproduce"):
+        paddle.jit.save(Leaky(), str(tmp_path / "leaky"), input_spec=spec)
+    with pytest.raises(RuntimeError, match="not values of the traced program"):
+        paddle.jit.save(Blind(), str(tmp_path / "blind"), input_spec=spec)
