@@ -61,7 +61,8 @@ class Spec:
             raise ValueError("a group result is listed twice")
         self.cols = int(full[-1]) if full else 1
         self.rows = _prod(full[:-1]) if full else 1
-        self.has_reduce = any(n.kind == "reduce" for n in nodes)
+        # row schedule: reductions, or per-row values (e.g. the gradient of a non-keepdim row result on its way back to the columns)
+        self.has_reduce = any(n.kind == "reduce" or (n.kind == "ew" and n.space == "row") for n in nodes)
         for n in nodes:                                   # levels: how many reductions deep a value is
             if n.kind == "in":
                 n.level = 0

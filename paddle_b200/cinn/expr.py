@@ -111,6 +111,8 @@ class GroupBuilder:
         if space is None:
             raise Unsupported(f"shape {list(shape)} is neither the domain {list(self.full)} nor its per-row shape")
         for a in args:
+            if isinstance(a, Node) and a.attrs.get("post"):
+                raise Unsupported("a value that is finished outside the kernel cannot be read inside the group")
             if isinstance(a, Node) and a.kind != "in":
                 if space == "full" and not (a.space == "full" or (a.space == "row" and a.shape == self.full[:-1] + (1,))):
                     raise Unsupported("a non-keepdim row value does not broadcast per row")
@@ -512,9 +514,22 @@ class Frontend:
             raise Unsupported("reduction dtype")
         if not isinstance(x, Node):
             raise Unsupported("reduction input")
-        self._last_axis(x, dim)
         if x.dtype not in FLOATS:
             raise Unsupported("integer reduction")
+        nd = len(x.shape)
+        everything = dim is None or (isinstance(dim, (list, tuple)) and sorted(i % nd for i in dim) == list(range(nd)) and nd > 1)
+        if everything and nd >= 1:
+            # reduction to a scalar (the tail of a loss): the kernel reduces every row, the handful of per-row partials is finished by one
+            # small library reduction on the way out (`post`); nothing inside the group may read the value
+            if keep or tuple(s) != () or x.shape != self.g.full:
+                raise Unsupported("full reduction with keepdim / outside the domain")
+            n = self.g.reduce(op, x, False, d)
+            count = 1
+            for e in x.shape:
+                count *= e
+            n.attrs = {"post": op}
+            return n, count
+        self._last_axis(x, dim)
         return self.g.reduce(op, x, bool(keep), d), x.shape[-1]
 
     def op_sum(self, a, k, s, d):
@@ -528,6 +543,9 @@ class Frontend:
 
     def op_mean(self, a, k, s, d):
         r, n = self._reduce("sum", a, k, s, d)
+        if r.attrs.get("post"):
+            r.attrs = {"post": "sum", "scale": 1.0 / n}
+            return r
         return self.g.ew("mul", [r, 1.0 / n], r.shape, d)
 
     # -- composites over the last axis

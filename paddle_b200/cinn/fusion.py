@@ -162,7 +162,9 @@ def fuse(tr, min_ops=2, targets=("cuda",), precompile=False):
             node = chosen.fe.lower(name, args, kwargs, rshape, rdt)
             if not isinstance(node, Node) or node.kind == "in":
                 raise Unsupported("op lowered to no computation")
-            if node.shape != rshape or node.dtype != rdt:
+            if node.attrs.get("post") and rshape == () and node.dtype == rdt:
+                pass                                  # per-row partials, finished to the recorded scalar on the way out
+            elif node.shape != rshape or node.dtype != rdt:
                 raise Unsupported(f"lowered type {node.dtype}{list(node.shape)} differs from the recorded {rdt}{list(rshape)}")
         except Unsupported as e:
             chosen.restore(snap)

@@ -18,7 +18,7 @@ _BI = {"add": torch.add, "sub": torch.sub, "mul": torch.mul, "div": torch.div, "
 _WIDE = {"float16": torch.float32, "bfloat16": torch.float32}
 
 
-def evaluate(spec, tensors, widen=True):
+def evaluate(spec, tensors, widen=True, finished=True):
     """Outputs of the group for the given input tensors.  `widen`: compute half types in fp32 and round once at the end (what the generated
     kernels do); False rounds after every op like the unfused program."""
     vals = {}
@@ -67,6 +67,10 @@ def evaluate(spec, tensors, widen=True):
     for n in spec.outputs:
         v = vals[n.id]
         outs.append(v.to(_TORCH_DT[n.dtype]) if v.dtype != _TORCH_DT[n.dtype] else v)
+    if finished:
+        from .runtime import finish
+
+        outs = finish(spec, outs)
     return outs
 
 

@@ -112,10 +112,12 @@ class FusedKernel:
 
     def __call__(self, *tensors, **_attrs):
         if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
-            outs = _FusedFn.apply(self, *[t.as_subclass(torch.Tensor) if type(t) is not torch.Tensor else t for t in tensors])
-            res = [o.as_subclass(Tensor) for o in outs]
-            return res[0] if len(res) == 1 else tuple(res)
-        return self._run(tensors)
+            outs = list(_FusedFn.apply(self, *[t.as_subclass(torch.Tensor) if type(t) is not torch.Tensor else t for t in tensors]))
+        else:
+            outs = self._run(tensors)
+            outs = list(outs) if isinstance(outs, tuple) else [outs]
+        res = [o.as_subclass(Tensor) for o in finish(self.spec, outs)]
+        return res[0] if len(res) == 1 else tuple(res)
 
     # ---- backward: one more generated kernel (cinn/autodiff.py); the torch interpreter when a derivative rule is missing --------------------
     def _backward_kernel(self, need):
@@ -151,7 +153,7 @@ class FusedKernel:
 
             with torch.enable_grad():
                 xs = [t.detach().requires_grad_(bool(nd) and t.is_floating_point()) for t, nd in zip(inputs, need)]
-                outs = evaluate(spec, xs)
+                outs = evaluate(spec, xs, finished=False)
                 pairs = [(o, g) for o, g in zip(outs, gouts) if o.requires_grad]
                 wrt = [x for x in xs if x.requires_grad]
                 gs = torch.autograd.grad([o for o, _ in pairs], wrt, [g for _, g in pairs], allow_unused=True) if pairs and wrt else []
@@ -212,6 +214,20 @@ class FusedKernel:
         stats["launches"] += 1
         res = [o.as_subclass(Tensor) for o in outs]
         return res[0] if len(res) == 1 else tuple(res)
+
+
+def finish(spec, outs):
+    """Results that are reductions to a scalar leave the kernel as per-row partials; the last step is one small library reduction."""
+    res = []
+    for o, n in zip(outs, spec.outputs):
+        post = n.attrs.get("post")
+        if post:
+            o = o.as_subclass(torch.Tensor)
+            o = {"sum": o.sum, "max": o.amax, "min": o.amin}[post]()
+            if n.attrs.get("scale") is not None:
+                o = o * n.attrs["scale"]
+        res.append(o)
+    return res
 
 
 class _FusedFn(torch.autograd.Function):
