@@ -170,7 +170,7 @@ class _Body:
         if op == "floordiv":
             return f"floor{sfx}({a} / {b})" if f else f"cinn_floordiv({a}, {b})"
         if op == "fmod":
-            return f"fmod{sfx}({a}, {b})" if f else f"({a} % {b})"
+            return f"fmod{sfx}({a}, {b})" if f else f"cinn_mod({a}, {b})"
         if op == "maximum":
             return f"cinn_max({a}, {b})"
         if op == "minimum":
@@ -212,7 +212,12 @@ _RED_ID = {"sum": 0, "max": 1, "min": 2}
 _COMMON = r"""
 template <class T> CINN_HD inline T cinn_max(T a, T b) { return (a != a || a > b) ? a : b; }     // NaN propagates, as in the eager ops
 template <class T> CINN_HD inline T cinn_min(T a, T b) { return (a != a || a < b) ? a : b; }
-template <class T> CINN_HD inline T cinn_floordiv(T a, T b) { T q = a / b; return ((a % b != 0) && ((a < 0) != (b < 0))) ? q - 1 : q; }
+template <class T> CINN_HD inline T cinn_floordiv(T a, T b) {        // integers; a zero divisor yields -1 (what the device does) instead of trapping the host
+  if (b == 0) return (T)-1;
+  T q = a / b;
+  return ((a % b != 0) && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+template <class T> CINN_HD inline T cinn_mod(T a, T b) { return b == 0 ? (T)-1 : a % b; }
 template <class T> CINN_HD inline T cinn_comb(int op, T a, T b) { return op == 0 ? a + b : (op == 1 ? cinn_max(a, b) : cinn_min(a, b)); }
 """
 

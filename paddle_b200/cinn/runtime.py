@@ -45,10 +45,11 @@ def compile_source(src, target, keep_source=True):
         return so
     ext = "cu" if target == "cuda" else "cc"
     final_src = os.path.join(_CACHE, f"k_{target}_{tag}.{ext}")
-    path = os.path.join(_CACHE, f"k_{target}_{tag}.{os.getpid()}.{ext}")       # per-process names: the ranks of a job compile the same kernel at once
+    uniq = f"{os.getpid()}_{threading.get_ident()}"
+    path = os.path.join(_CACHE, f"k_{target}_{tag}.{uniq}.{ext}")       # per-process names: the ranks of a job compile the same kernel at once
     with open(path, "w") as f:
         f.write(src)
-    tmp = so + f".tmp{os.getpid()}"
+    tmp = so + f".tmp{uniq}"
     if target == "cuda":
         nvcc = _nvcc()
         if nvcc is None:
