@@ -342,6 +342,62 @@ def gradients(targets, inputs, target_gradients=None, no_grad_set=None):
     return grad(targets, inputs, target_gradients, allow_unused=True)
 
 
+class _ValueGC:
+    """Garbage collection of the executor's value table (the interpreter GC of the reference, new_executor/garbage_collector): every value
+    carries the number of nodes that still have to read it; when the last reader has run the entry is dropped, so the tensor's memory goes back to
+    the allocator while the program is still running.  Counting (rather than last-use positions) stays correct under any dependency-respecting
+    execution order.  Programs with training / control nodes read the table through closures: no collection there.  FLAGS_eager_delete_tensor_gb
+    < 0 turns it off."""
+
+    def __init__(self, readers, keep, reads):
+        self.readers, self.keep, self.reads = readers, keep, reads
+        self.stats = {"freed": 0, "peak_live": 0}
+
+    @staticmethod
+    def _refs(x, out):
+        if isinstance(x, _Ref):
+            out.add(x.vid)
+        elif isinstance(x, (list, tuple)):
+            for i in x:
+                _ValueGC._refs(i, out)
+        elif isinstance(x, dict):
+            for i in x.values():
+                _ValueGC._refs(i, out)
+
+    @staticmethod
+    def plan(program, fetch_list, fed):
+        if any(n.kind != "op" for n in program.nodes):
+            return None
+        keep = set(fed)
+        for f in fetch_list or []:
+            vid = program._name2vid.get(f) if isinstance(f, str) else program._fetch_alias.get(id(f))
+            if vid is not None:
+                keep.add(vid)
+        keep.update(program.__dict__.get("_pir_alias", {}).values())
+        readers, reads = {}, {}
+        for n in program.nodes:
+            r = set()
+            _ValueGC._refs(n.args, r)
+            _ValueGC._refs(n.kwargs, r)
+            reads[id(n)] = r
+            for v in r:
+                readers[v] = readers.get(v, 0) + 1
+        return _ValueGC(readers, keep, reads)
+
+    def after(self, node, env):
+        self.stats["peak_live"] = max(self.stats["peak_live"], len(env))
+        for v in self.reads.get(id(node), ()):
+            c = self.readers.get(v, 0) - 1
+            self.readers[v] = c
+            if c == 0 and v not in self.keep and v in env:
+                del env[v]
+                self.stats["freed"] += 1
+        for v in node.outs:                              # produced but never read and not fetched
+            if self.readers.get(v, 0) == 0 and v not in self.keep and v in env:
+                del env[v]
+                self.stats["freed"] += 1
+
+
 class Executor:
     def __init__(self, place=None):
         self.place = place
@@ -395,8 +451,12 @@ class Executor:
             fl(out)
             for vid, t in zip(n.outs, flat):
                 env[vid] = t
+            if gc is not None:                          # values nobody will read any more leave the table right away
+                gc.after(n, env)
 
+        gc = _ValueGC.plan(program, fetch_list, set(env)) if flag("FLAGS_eager_delete_tensor_gb", 0.0) >= 0 else None
         self._schedule(program, run_node)
+        self.last_gc_stats = gc.stats if gc is not None else None
         outs = []
         for f in fetch_list or []:
             if isinstance(f, str):

@@ -274,3 +274,40 @@ def test_decomposition_rewrites_composites_into_primitives():
     D.decompose(m2, blacklist={"gelu"})
     assert "gelu" in names(m2) and "softmax" not in names(m2)
     assert D.has_decomp("rms_norm") and D.get_decomp_rule("softmax") is not None
+
+
+def test_executor_frees_values_after_their_last_reader():
+    """Interpreter GC: the value table holds only what is still needed; results are unchanged; training programs are left alone."""
+    import numpy as np
+
+    import paddle_b200 as paddle
+    from paddle_b200 import static
+
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            x = static.data("x", [4, 8], "float32")
+            h = x
+            for i in range(12):
+                h = paddle.tanh(h * 1.1 + 0.1)
+            side = paddle.exp(x)                      # never read, not fetched
+            out = h + x
+        exe = static.Executor()
+        xv = np.random.RandomState(0).randn(4, 8).astype("float32")
+        got = exe.run(main, feed={"x": xv}, fetch_list=[out])[0]
+        st = exe.last_gc_stats
+        assert st is not None and st["freed"] >= 36 and st["peak_live"] <= 6      # 38 values in the program, a handful alive at any time
+        ref = xv.copy()
+        for i in range(12):
+            ref = np.tanh(ref * 1.1 + 0.1)
+        np.testing.assert_allclose(got, ref + xv, rtol=1e-5, atol=1e-6)
+        mid = exe.run(main, feed={"x": xv}, fetch_list=[h, out])                  # a fetched intermediate survives
+        np.testing.assert_allclose(mid[0], ref, rtol=1e-5, atol=1e-6)
+        paddle.set_flags({"FLAGS_eager_delete_tensor_gb": -1.0})
+        exe.run(main, feed={"x": xv}, fetch_list=[out])
+        assert exe.last_gc_stats is None
+    finally:
+        paddle.set_flags({"FLAGS_eager_delete_tensor_gb": 0.0})
+        paddle.disable_static()
+    del side
