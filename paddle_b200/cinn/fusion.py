@@ -209,11 +209,16 @@ def fuse(tr, min_ops=2, targets=("cuda",), precompile=False):
             continue
         for k, n in enumerate(nodes):
             n.id = k
-        sig = hashlib.sha1(repr([(n.kind, n.op, [a.id if isinstance(a, Node) else a for a in n.args], n.shape, n.dtype) for n in nodes]
+        sig = hashlib.sha1(repr([(n.kind, n.op, [a.id if isinstance(a, Node) else a for a in n.args], n.shape, n.dtype,
+                                  sorted((k, v) for k, v in n.attrs.items() if k != "value")) for n in nodes]
                                 + [o.id for o in out_nodes]).encode()).hexdigest()[:12]
         kname = f"cinn_fused_{sig}"
-        spec = codegen.Spec(kname, g.gb.full, nodes, in_nodes, out_nodes)
-        kernel = FusedKernel(spec)
+        known = pir._IMPL.get(kname)
+        if isinstance(known, FusedKernel):                 # the same computation on the same types was compiled before (another layer, another program)
+            kernel, spec = known, known.spec
+        else:
+            spec = codegen.Spec(kname, g.gb.full, nodes, in_nodes, out_nodes)
+            kernel = FusedKernel(spec)
         try:
             for t in targets:
                 kernel.source(t)

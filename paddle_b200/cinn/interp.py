@@ -37,6 +37,8 @@ def evaluate(spec, tensors, widen=True, finished=True):
         if n.kind == "in":
             t = next(it)
             t = t.as_subclass(torch.Tensor) if type(t) is not torch.Tensor else t
+            if n.attrs.get("view") and tuple(t.shape) != n.shape:
+                t = t.reshape(n.shape)
             vals[n.id] = t.to(cdt(n)) if t.dtype != cdt(n) else t
             continue
         if n.kind == "reduce":
