@@ -47,11 +47,25 @@ def backward_spec(spec, need_grad):
     for n in spec.nodes:
         if n.kind == "in":
             fwd[n.id] = b.node("in", "load", [], n.shape, n.dtype, "in", {"src": ("in", in_index[n.id]), "view": n.attrs.get("view", False)})
+        elif n.kind == "creduce":
+            continue                                   # results of column reductions are never read inside a group
         else:
             fwd[n.id] = b.node(n.kind, n.op, [fwd[a.id] if isinstance(a, Node) else a for a in n.args], n.shape, n.dtype, n.space)
     adj = {}                                        # forward node id -> [contribution nodes] (in that node's space)
     parts = {}                                      # forward input node id -> {(space, shape): [contribution nodes]}
     for k, o in enumerate(spec.outputs):
+        if o.kind == "creduce" and o.dtype in FLOATS:
+            # d sum_K(x) / dx: the gradient, read under the keepdim shape so that it broadcasts over the reduced axes
+            keep = tuple(1 if i in o.attrs["axes"] else e for i, e in enumerate(spec.full))
+            g = b.node("in", "load", [], keep, o.dtype, "in", {"src": ("grad", k), "view": True})
+            x = o.args[0]
+            c = b.node("ew", "mul", [g, float(o.attrs.get("scale") or 1.0)], spec.full, x.dtype, "full")
+            if x.kind == "in":
+                if need_grad[in_index[x.id]] and x.dtype in FLOATS:
+                    parts.setdefault(x.id, {}).setdefault(("full", x.shape), []).append(c)
+            elif x.dtype in FLOATS:
+                adj.setdefault(x.id, []).append(c)
+            continue
         if o.dtype in FLOATS:
             g = b.node("in", "load", [], o.shape, o.dtype, "in", {"src": ("grad", k)})
             if o.space == "row":                     # bring a per-row gradient into the row space before column work reads it
@@ -83,7 +97,7 @@ def backward_spec(spec, need_grad):
         adj.setdefault(x.id, []).append(c)
 
     for n in reversed(spec.nodes):
-        if n.kind == "in" or n.id not in adj or n.dtype not in FLOATS:
+        if n.kind in ("in", "creduce") or n.id not in adj or n.dtype not in FLOATS:
             continue
         a = total(adj[n.id], n)
         me = fwd[n.id]

@@ -10,6 +10,8 @@ Schedules
     on s earlier reductions).  Up to 8192 columns every thread owns <= 8 columns, the column loops are unrolled over them and a value a
     later pass reads again stays in a register array (softmax numerator, centred input of a normalisation); longer rows recompute from the
     inputs through L1 / L2.  Per-row values live in registers; the per-row part of every broadcast index is hoisted out of the column loops.
+  * group with sums over LEADING axes (bias gradients, batch statistics) -> the domain is read as [A, K, B]; CTAs of 32 columns x 8 k-lanes, the K
+    range split over `split` CTAs that leave fp32 partials, a second kernel adds them (deterministic, no atomics).
 Role parity: CINN's group schedule + CodeGenCUDA_Dev (paddle/cinn/ir/group_schedule, paddle/cinn/backends/codegen_cuda_dev.cc)."""
 from __future__ import annotations
 
@@ -63,6 +65,8 @@ class Spec:
         self.rows = _prod(full[:-1]) if full else 1
         # row schedule: reductions, or per-row values (e.g. the gradient of a non-keepdim row result on its way back to the columns)
         self.has_reduce = any(n.kind == "reduce" or (n.kind == "ew" and n.space == "row") for n in nodes)
+        self.col = [n for n in nodes if n.kind == "creduce"]            # column reductions: the group runs on the [A, K, B] schedule
+        self.akb = self.col[0].attrs["akb"] if self.col else None
         for n in nodes:                                   # levels: how many reductions deep a value is
             if n.kind == "in":
                 n.level = 0
@@ -349,7 +353,7 @@ class _Plan:
 
     def full_closure(self, targets):
         """Full-space nodes (and inputs read per element) a column loop has to evaluate for `targets`, in topological order."""
-        need, stack = set(), [t for t in targets]
+        need, stack = set(), [t.args[0] if t.kind == "creduce" else t for t in targets]
         while stack:
             n = stack.pop()
             if n.id in need:
@@ -539,10 +543,62 @@ class _RowEmitter:
         return "\n".join(self.lines)
 
 
+def _col_body(spec, ld_indent):
+    """Per-element statements of a column-reduction group, for `e` (flat index), `row`, `j` in scope: loads, the closure of every result, stores
+    of the full results; returns (lines, names of the values the reductions add up)."""
+    body = _Body(spec)
+    in_pos = {n.id: k for k, n in enumerate(spec.inputs)}
+    out_pos = {n.id: k for k, n in enumerate(spec.outputs)}
+    closure = _Plan(spec).full_closure(spec.outputs)
+    idx = {n.id: body.in_index(n, "full") for n in closure if n.kind == "in"}
+
+    def ref(a):
+        return f"v{a.id}", compute_type(a.dtype)
+
+    L = []
+    for n in closure:
+        T = compute_type(n.dtype)
+        if n.kind == "in":
+            rp, uj = idx[n.id]
+            off = "e" if tuple(n.shape) == spec.full else (" + ".join(([f"({rp})"] if rp else []) + (["j"] if uj else [])) or "0")
+            L.append(f"{ld_indent}const {T} v{n.id} = ld(in{in_pos[n.id]}, {off});")
+        else:
+            L.append(f"{ld_indent}const {T} v{n.id} = {body.ew_expr(n, ref)};")
+    for n in spec.outputs:
+        if n.kind == "ew":
+            L.append(f"{ld_indent}st(out{out_pos[n.id]}, e, v{n.id});")
+    return L, out_pos
+
+
+def _host_col_source(spec):
+    A, K, B = spec.akb
+    lines, out_pos = _col_body(spec, "        ")
+    L = [_HOST_PRELUDE, "extern \"C\" int cinn_run(void** in, void** out, long long rows, int aux) {", "  (void)rows; (void)aux;"]
+    L += [f"  const {_STORE[n.dtype]}* in{k} = (const {_STORE[n.dtype]}*)in[{k}];" for k, n in enumerate(spec.inputs)]
+    L += [f"  {_STORE[n.dtype]}* out{k} = ({_STORE[n.dtype]}*)out[{k}];" for k, n in enumerate(spec.outputs)]
+    L.append(f"  for (long long a = 0; a < {A}LL; ++a) for (long long b = 0; b < {B}LL; ++b) {{")
+    for r in spec.col:
+        L.append(f"    {compute_type(r.dtype)} acc{r.id} = 0;")
+    L.append(f"    for (long long k = 0; k < {K}LL; ++k) {{")
+    L.append(f"      const long long e = (a * {K}LL + k) * {B}LL + b; const long long row = e / {spec.cols}LL; const long long j = e - row * {spec.cols}LL; (void)row; (void)j;")
+    L += lines
+    for r in spec.col:
+        L.append(f"        acc{r.id} += ({compute_type(r.dtype)})v{r.args[0].id};")
+    L.append("    }")
+    for r in spec.col:
+        sc = r.attrs.get("scale")
+        T = compute_type(r.dtype)
+        L.append(f"    st(out{out_pos[r.id]}, a * {B}LL + b, acc{r.id}{'' if sc is None else ' * ' + _lit(sc, T)});")
+    L.append("  }\n  return 0;\n}")
+    return "\n".join(L) + "\n"
+
+
 def host_source(spec):
+    if spec.col:
+        return _host_col_source(spec)
     em = _RowEmitter(spec, f"for (int j = 0; j < {spec.cols}; ++j) {{", lambda r, T: f"const {T} r{r.id} = acc{r.id};")
     body = em.emit()
-    return (_HOST_PRELUDE + f"\nextern \"C\" int cinn_run(void** in, void** out, long long rows) {{\n"
+    return (_HOST_PRELUDE + f"\nextern \"C\" int cinn_run(void** in, void** out, long long rows, int aux) {{\n  (void)aux;\n"
             + "".join(f"  const {_STORE[n.dtype]}* in{k} = (const {_STORE[n.dtype]}*)in[{k}];\n" for k, n in enumerate(spec.inputs))
             + "".join(f"  {_STORE[n.dtype]}* out{k} = ({_STORE[n.dtype]}*)out[{k}];\n" for k, n in enumerate(spec.outputs))
             + f"  for (long long row = 0; row < rows; ++row) {{\n{body}\n  }}\n  return 0;\n}}\n")
@@ -670,13 +726,72 @@ def _row_kernel(spec):
     return "\n".join(L), threads, rpb
 
 
+def _cuda_col_kernels(spec):
+    """Column reduction on [A, K, B]: CTAs of 32 columns x 8 k-lanes; `split` CTAs share the K range of one (a, column tile) and leave fp32
+    partials that a second, tiny kernel adds up (no atomics: the result is deterministic).  grid = (ceil(B / 32), split, min(A, 65535))."""
+    A, K, B = spec.akb
+    lines, out_pos = _col_body(spec, "        ")
+    parts = ", ".join(f"{compute_type(r.dtype)}* __restrict__ part{r.id}" for r in spec.col)
+    L = [f"extern \"C\" __global__ void __launch_bounds__(256) cinn_k_col({_params(spec)}, {parts}, int split) {{", "  (void)rows;"]
+    for r in spec.col:
+        L.append(f"  __shared__ {compute_type(r.dtype)} sm{r.id}[8][33];")
+    L.append("  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;")
+    L.append("  const long long b = blockIdx.x * 32LL + tx;")
+    L.append(f"  for (long long a = blockIdx.z; a < {A}LL; a += gridDim.z) {{")
+    for r in spec.col:
+        L.append(f"    {compute_type(r.dtype)} acc{r.id} = 0;")
+    L.append(f"    if (b < {B}LL) {{")
+    L.append(f"      for (long long k = blockIdx.y * 8LL + ty; k < {K}LL; k += 8LL * split) {{")
+    L.append(f"        const long long e = (a * {K}LL + k) * {B}LL + b; const long long row = e / {spec.cols}LL; const long long j = e - row * {spec.cols}LL; (void)row; (void)j;")
+    L += lines
+    for r in spec.col:
+        L.append(f"        acc{r.id} += ({compute_type(r.dtype)})v{r.args[0].id};")
+    L.append("      }\n    }")
+    for r in spec.col:
+        L.append(f"    sm{r.id}[ty][tx] = acc{r.id};")
+    L.append("    __syncthreads();")
+    L.append(f"    if (ty == 0 && b < {B}LL) {{")
+    for r in spec.col:
+        T = compute_type(r.dtype)
+        L.append(f"      {T} s{r.id} = 0;\n#pragma unroll\n      for (int t = 0; t < 8; ++t) s{r.id} += sm{r.id}[t][tx];")
+        L.append(f"      part{r.id}[((long long)blockIdx.y * {A}LL + a) * {B}LL + b] = s{r.id};")
+    L.append("    }\n    __syncthreads();\n  }\n}")
+    outs = ", ".join(f"{_STORE[r.dtype]}* __restrict__ out{out_pos[r.id]}, const {compute_type(r.dtype)}* __restrict__ part{r.id}" for r in spec.col)
+    L.append(f"extern \"C\" __global__ void __launch_bounds__(256) cinn_k_colfin({outs}, int split) {{")
+    L.append(f"  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < {A * B}LL; i += gridDim.x * 256LL) {{")
+    for r in spec.col:
+        T = compute_type(r.dtype)
+        sc = r.attrs.get("scale")
+        L.append(f"    {T} s{r.id} = 0; for (int p = 0; p < split; ++p) s{r.id} += part{r.id}[(long long)p * {A * B}LL + i];")
+        L.append(f"    st(out{out_pos[r.id]}, i, s{r.id}{'' if sc is None else ' * ' + _lit(sc, T)});")
+    L.append("  }\n}")
+    n_out = len(spec.outputs)
+    part_args = ", ".join(f"({compute_type(r.dtype)}*)out[{n_out + i}]" for i, r in enumerate(spec.col))
+    fin_args = ", ".join(f"({_STORE[r.dtype]}*)out[{out_pos[r.id]}], (const {compute_type(r.dtype)}*)out[{n_out + i}]" for i, r in enumerate(spec.col))
+    launch = (f"  const int split = aux < 1 ? 1 : aux;\n"
+              f"  dim3 grid((unsigned)(({B}LL + 31) / 32), (unsigned)split, (unsigned)({min(A, 65535)}));\n"
+              f"  cinn_k_col<<<grid, 256, 0, (cudaStream_t)stream>>>({_call_args(spec)}, {part_args}, split);\n"
+              f"  cinn_k_colfin<<<cinn_grid(({A * B}LL + 255) / 256, {SM_COUNT * 8}), 256, 0, (cudaStream_t)stream>>>({fin_args}, split);\n")
+    return "\n".join(L), launch
+
+
+def col_split(spec, sm_count=SM_COUNT):
+    """How many CTAs share the K range of one column tile (launch argument `aux`): enough CTAs to cover the machine twice, at least 16 k per CTA."""
+    A, K, B = spec.akb
+    tiles = ((B + 31) // 32) * min(A, 65535)
+    want = -(-2 * sm_count // max(tiles, 1))
+    return int(max(1, min(want, max(1, K // 16), 64)))
+
+
 def cuda_source(spec):
     """Kernels + an `extern "C"` launcher: cinn_launch(in, out, stream, allow_vec, rows) -> cudaError_t of the launch.  The number of rows
     (product of the leading extents) is a run-time argument and the kernel names are fixed, so groups that differ only in batch / sequence
     extents generate the same source and share one compiled object."""
     cap = SM_COUNT * 8
     clamp = "static inline int cinn_grid(long long want, long long cap) { return (int)(want < 1 ? 1 : (want > cap ? cap : want)); }\n"
-    if spec.has_reduce:
+    if spec.col:
+        k, launch = _cuda_col_kernels(spec)
+    elif spec.has_reduce:
         k, threads, rpb = _row_kernel(spec)
         launch = (f"  const int grid = cinn_grid((rows + {rpb - 1}) / {rpb}, {cap * (1 if rpb > 1 else 2)});\n"
                   f"  cinn_k_row<<<grid, {threads}, 0, (cudaStream_t)stream>>>({_call_args(spec)});\n")
@@ -688,5 +803,5 @@ def cuda_source(spec):
             launch += (f"  if (allow_vec) {{ cinn_k_vec{V}<<<cinn_grid((n / {V} + 255) / 256, {cap}), 256, 0, (cudaStream_t)stream>>>({_call_args(spec)}); "
                        "return (int)cudaGetLastError(); }\n")
         launch += f"  cinn_k_flat<<<cinn_grid((n + 255) / 256, {cap}), 256, 0, (cudaStream_t)stream>>>({_call_args(spec)});\n"
-    return (_CUDA_PRELUDE + "\n" + k + "\n\n" + clamp + "extern \"C\" int cinn_launch(void** in, void** out, void* stream, int allow_vec, long long rows) {\n  (void)allow_vec;\n"
+    return (_CUDA_PRELUDE + "\n" + k + "\n\n" + clamp + "extern \"C\" int cinn_launch(void** in, void** out, void* stream, int allow_vec, long long rows, int aux) {\n  (void)allow_vec; (void)aux;\n"
             + launch + "  return (int)cudaGetLastError();\n}\n")

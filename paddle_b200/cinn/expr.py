@@ -110,8 +110,10 @@ class GroupBuilder:
         space = self.space_of(shape)
         if space is None:
             raise Unsupported(f"shape {list(shape)} is neither the domain {list(self.full)} nor its per-row shape")
+        if space == "row" and any(n.kind == "creduce" for n in self.nodes):
+            raise Unsupported("row values in a column-reduction group")
         for a in args:
-            if isinstance(a, Node) and a.attrs.get("post"):
+            if isinstance(a, Node) and (a.attrs.get("post") or a.attrs.get("sealed")):
                 raise Unsupported("a value that is finished outside the kernel cannot be read inside the group")
             if isinstance(a, Node) and a.kind != "in":
                 if space == "full" and not (a.space == "full" or (a.space == "row" and a.shape == self.full[:-1] + (1,))):
@@ -127,8 +129,36 @@ class GroupBuilder:
     def reduce(self, op, x, keepdim, dtype):
         if not isinstance(x, Node) or x.shape != self.full or (x.kind != "in" and x.space != "full"):
             raise Unsupported("reduction input is not a full-domain value")
+        if any(n.kind == "creduce" for n in self.nodes):
+            raise Unsupported("row and column reductions in one group")
         shape = self.full[:-1] + ((1,) if keepdim else ())
         return self._add(Node("reduce", op, [x], shape, dtype, space="row"))
+
+    def creduce(self, x, axes, keepdim, dtype, scale=None):
+        """Sum over a contiguous run of axes that does NOT include the last one ("column" reduction: bias gradients, batch statistics):
+        the domain is read as [A, K, B] with the run collapsed to K.  The result leaves the group (nothing inside may read it)."""
+        if not isinstance(x, Node) or x.shape != self.full or (x.kind != "in" and x.space != "full"):
+            raise Unsupported("reduction input is not a full-domain value")
+        if any(n.kind == "reduce" or (n.kind == "ew" and n.space == "row") for n in self.nodes):
+            raise Unsupported("row and column reductions in one group")
+        nd = len(self.full)
+        axes = sorted(set(int(a) % nd for a in axes))
+        if not axes or axes != list(range(axes[0], axes[-1] + 1)) or axes[-1] >= nd - 1:
+            raise Unsupported("reduction axes are not a contiguous run before the last axis")
+        A = K = B = 1
+        for i, e in enumerate(self.full):
+            if i < axes[0]:
+                A *= e
+            elif i <= axes[-1]:
+                K *= e
+            else:
+                B *= e
+        akb = (A, K, B)
+        for n in self.nodes:
+            if n.kind == "creduce" and n.attrs["akb"] != akb:
+                raise Unsupported("column reductions over different axes in one group")
+        shape = tuple(1 if i in axes else e for i, e in enumerate(self.full)) if keepdim else tuple(e for i, e in enumerate(self.full) if i not in axes)
+        return self._add(Node("creduce", "sum", [x], shape, dtype, {"akb": akb, "sealed": True, "scale": scale, "axes": tuple(axes), "keepdim": bool(keepdim)}, space="col"))
 
 
 def _check_broadcast(src, dst):
@@ -529,6 +559,16 @@ class Frontend:
                 count *= e
             n.attrs = {"post": op}
             return n, count
+        dims = [dim] if isinstance(dim, int) and not isinstance(dim, bool) else list(dim) if isinstance(dim, (list, tuple)) else None
+        if dims and all(isinstance(i, int) for i in dims) and (nd - 1) not in [i % nd for i in dims]:
+            if op != "sum":
+                raise Unsupported("only sums reduce over leading axes")
+            if x.shape != self.g.full:
+                raise Unsupported("reduction outside the domain")
+            count = 1
+            for i in set(i % nd for i in dims):
+                count *= x.shape[i]
+            return self.g.creduce(x, dims, bool(keep), d), count
         self._last_axis(x, dim)
         return self.g.reduce(op, x, bool(keep), d), x.shape[-1]
 
@@ -545,6 +585,9 @@ class Frontend:
         r, n = self._reduce("sum", a, k, s, d)
         if r.attrs.get("post"):
             r.attrs = {"post": "sum", "scale": 1.0 / n}
+            return r
+        if r.kind == "creduce":
+            r.attrs["scale"] = 1.0 / n
             return r
         return self.g.ew("mul", [r, 1.0 / n], r.shape, d)
 

@@ -137,7 +137,7 @@ def fuse(tr, min_ops=2, targets=("cuda",), precompile=False):
             if g is not None and g.open and (g.gb.full == domain if name in _ROW_OPS else g.gb.space_of(rshape) is not None):
                 if chosen is None:
                     chosen = g
-                elif g is not chosen and g.gb.full == chosen.gb.full:       # two open groups feed this op: one kernel
+                elif g is not chosen and g.gb.full == chosen.gb.full and _compatible(g, chosen):       # two open groups feed this op: one kernel
                     chosen.absorb(g)
                     for val, owner in list(group_of.items()):
                         if owner is g:
@@ -238,9 +238,23 @@ def fuse(tr, min_ops=2, targets=("cuda",), precompile=False):
             ir.erase_op(oid)
         pir.register_op_impl(kname, kernel)
         res.groups.append({"name": kname, "ops": [op_name[o] for o in g.op_ids], "inputs": len(in_nodes), "outputs": len(out_nodes),
-                           "kind": "reduce" if spec.has_reduce else "elementwise", "kernel": kernel, "domain": list(g.gb.full)})
+                           "kind": "column" if spec.col else "reduce" if spec.has_reduce else "elementwise", "kernel": kernel, "domain": list(g.gb.full)})
     ir.verify()
     return res
+
+
+def _compatible(a, b):
+    """May two groups on the same domain share a kernel?  Not when one reduces along rows and the other along columns (different schedules), nor
+    when their column reductions collapse different axes."""
+    def kinds(g):
+        row = any(n.kind == "reduce" or (n.kind == "ew" and n.space == "row") for n in g.gb.nodes)
+        col = {n.attrs["akb"] for n in g.gb.nodes if n.kind == "creduce"}
+        return row, col
+
+    (ra, ca), (rb, cb) = kinds(a), kinds(b)
+    if (ra and cb) or (rb and ca):
+        return False
+    return len(ca | cb) <= 1
 
 
 def _prune(nodes, outputs):

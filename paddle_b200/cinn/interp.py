@@ -41,6 +41,12 @@ def evaluate(spec, tensors, widen=True, finished=True):
                 t = t.reshape(n.shape)
             vals[n.id] = t.to(cdt(n)) if t.dtype != cdt(n) else t
             continue
+        if n.kind == "creduce":
+            r = vals[n.args[0].id].sum(dim=n.attrs["axes"], keepdim=n.attrs["keepdim"])
+            if n.attrs.get("scale") is not None:
+                r = r * n.attrs["scale"]
+            vals[n.id] = r.to(cdt(n))
+            continue
         if n.kind == "reduce":
             x = vals[n.args[0].id]
             keep = len(n.shape) == len(n.args[0].shape)

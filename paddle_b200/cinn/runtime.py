@@ -103,10 +103,10 @@ class FusedKernel:
             lib = _load(compile_source(self.source(target), target))
             if target == "cuda":
                 fn = lib.cinn_launch
-                fn.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong]
+                fn.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_int]
             else:
                 fn = lib.cinn_run
-                fn.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.c_longlong]
+                fn.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.c_longlong, ctypes.c_int]
             fn.restype = ctypes.c_int
             self._fn[target] = fn
         return self._fn[target]
@@ -199,16 +199,21 @@ class FusedKernel:
         target = "cuda" if dev.type == "cuda" else "host"
         fn = self.build(target)
         outs = [torch.empty(n.shape, dtype=_TORCH_DT[n.dtype], device=dev) for n in spec.outputs]
+        aux, scratch = 0, []
+        if spec.col and target == "cuda":                       # partial sums of the column reductions: [split, A, B] per reduction
+            aux = codegen.col_split(spec, torch.cuda.get_device_properties(dev).multi_processor_count)
+            A, _, B = spec.akb
+            scratch = [torch.empty(aux * A * B, dtype=torch.float64 if r.dtype == "float64" else torch.float32, device=dev) for r in spec.col]
         ins_p = (ctypes.c_void_p * max(len(raw), 1))(*[t.data_ptr() for t in raw])
-        outs_p = (ctypes.c_void_p * len(outs))(*[t.data_ptr() for t in outs])
+        outs_p = (ctypes.c_void_p * (len(outs) + len(scratch)))(*[t.data_ptr() for t in outs + scratch])
         if target == "cuda":
             with torch.cuda.device(dev):
                 aligned = all(t.data_ptr() % 16 == 0 for t in raw + outs)
-                rc = fn(ins_p, outs_p, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), int(aligned), spec.rows)
+                rc = fn(ins_p, outs_p, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), int(aligned), spec.rows, aux)
             if rc != 0:
                 raise RuntimeError(f"{spec.name}: kernel launch failed with CUDA error {rc}")
         else:
-            rc = fn(ins_p, outs_p, spec.rows)
+            rc = fn(ins_p, outs_p, spec.rows, 0)
             if rc != 0:
                 raise RuntimeError(f"{spec.name}: host kernel returned {rc}")
         self.launches += 1

@@ -238,7 +238,8 @@ _UN = [paddle.tanh, paddle.exp, paddle.abs, F.sigmoid, F.relu, paddle.sin, lambd
 _BI = [lambda a, b: a + b, lambda a, b: a - b, lambda a, b: a * b, paddle.maximum, paddle.minimum, lambda a, b: a / (paddle.abs(b) + 1.5),
        lambda a, b: paddle.where(a > b, a, b * 0.5)]
 _RED = [lambda v: v.sum(-1, keepdim=True), lambda v: v.mean(-1, keepdim=True), lambda v: v.amax(-1, keepdim=True), lambda v: v.amin(-1, keepdim=True),
-        lambda v: v.sum(-1), lambda v: v.mean(), lambda v: v.amax()]
+        lambda v: v.sum(-1), lambda v: v.mean(), lambda v: v.amax(), lambda v: v.sum(0), lambda v: v.mean(0, keepdim=True),
+        lambda v: v.sum(tuple(range(v.dim() - 1))) if v.dim() > 1 else v.sum(), lambda v: v.sum(1) if v.dim() > 2 else v.sum(0)]
 
 
 @pytest.mark.parametrize("seed", range(24))
@@ -619,3 +620,33 @@ def test_loss_tail_reduces_to_a_scalar():
     ref = ((torch.log_softmax(zr, -1) * torch.from_numpy(oh)) * (zr * 0.1 + 1.0)).mean()
     ref.backward()
     assert torch.allclose(out, ref, rtol=1e-5, atol=1e-7) and torch.allclose(zt.grad, zr.grad, rtol=1e-4, atol=1e-7)
+
+
+
+def test_column_reductions_bias_gradient_pattern():
+    """Sums over leading axes ([A, K, B] schedule): `(dy * f(x)).sum((0, 1))` and its sibling share one kernel with their elementwise producers;
+    means, keepdim, a middle axis; the backward is a plain elementwise kernel that reads the gradient under the keepdim shape."""
+    rng = np.random.default_rng(21)
+    dy, x = rng.standard_normal((6, 5, 16)).astype(np.float32), rng.standard_normal((6, 5, 16)).astype(np.float32)
+    g = rng.standard_normal((16,)).astype(np.float32)
+
+    def grads(dy, x, g):
+        xh = paddle.tanh(x) * g
+        return (dy * xh).sum(axis=[0, 1]), (xh * xh).mean(axis=[0, 1])
+
+    rep = _run_both(grads, dict(dy=dy, x=x, g=g), rtol=2e-5, atol=2e-5, expect_kernels=1)
+    k = rep.groups[0]["kernel"]
+    assert rep.groups[0]["kind"] == "column" and k.spec.akb == (1, 30, 16) and len(k.spec.col) == 2
+    src = k.source("cuda")
+    assert "cinn_k_col(" in src and "cinn_k_colfin(" in src and "atomic" not in src
+    rep = _run_both(lambda dy, x: (dy * x).mean(axis=1, keepdim=True), dict(dy=dy, x=x), rtol=2e-5, atol=2e-6, expect_kernels=1)
+    assert rep.groups[0]["kernel"].spec.akb == (6, 5, 16)
+    rep = _run_both(lambda dy, x: ((dy * x).sum(axis=0), dy * x + 1.0), dict(dy=dy, x=x), rtol=2e-5, atol=2e-5)
+    assert any(g_["kind"] == "column" for g_ in rep.groups)
+    # gradient through the column reduction
+    k = _kernel_of(lambda x, dy: (paddle.tanh(x) * dy).sum(axis=[0, 1]), dict(x=torch.from_numpy(x), dy=torch.from_numpy(dy)))      # operands in recording order
+    bk, plan = _check_grads(k, lambda x, dy: (torch.tanh(x) * dy).sum((0, 1)), [torch.from_numpy(x), torch.from_numpy(dy)])
+    assert not bk.spec.col and not bk.spec.has_reduce
+    # a row reduction and a column reduction of the same chain do not share a kernel
+    rep = _run_both(lambda dy, x: ((dy * x).sum(axis=0), (dy * x).sum(axis=-1)), dict(dy=dy, x=x), rtol=2e-5, atol=2e-5)
+    assert all(not (g_["kernel"].spec.col and any(n.kind == "reduce" for n in g_["kernel"].spec.nodes)) for g_ in rep.groups)

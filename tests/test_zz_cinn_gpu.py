@@ -122,3 +122,20 @@ def test_generated_backward_on_device():
         assert torch.allclose(a, r, rtol=1e-3, atol=1e-4)
     (bk, plan), = k._bwd.values()
     assert plan is not None and bk.launches == 1
+
+
+@pytest.mark.parametrize("shape", [(64, 128, 256), (4096, 48), (3, 2000, 40)])
+def test_column_reduction_schedule(shape):
+    torch.manual_seed(3)
+    dy = torch.randn(*shape, device="cuda")
+    x = torch.randn(*shape, device="cuda")
+    lead = list(range(len(shape) - 1))
+
+    def build(dy, x):
+        t = dy * paddle.tanh(x)
+        return t.sum(axis=lead), (dy * x).mean(axis=lead[-1:])
+
+    (s, m), rep = _fused(build, dict(dy=dy, x=x))
+    assert any(g["kind"] == "column" for g in rep.groups)
+    assert torch.allclose(s, (dy * torch.tanh(x)).sum(lead), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(m, (dy * x).mean(lead[-1]), rtol=1e-4, atol=1e-5)
