@@ -131,10 +131,10 @@ class Config:
     # saved PROGRAM artifact (static.save_inference_model / a traced program) the pass names map onto the native IR passes of
     # paddle_b200.pir and are really run when the predictor is created (switch_ir_optim(False) or an empty list skips them); a pickled
     # Layer artifact executes through the hand-written kernels directly and the list is only recorded.
-    _PASSES = ["identity_op_clean_pass", "common_subexpression_elimination_pass", "constant_folding_pass", "dead_code_elimination_pass", "fuse_gemm_epilogue_pass",
+    _PASSES = ["conv_bn_fuse_pass", "identity_op_clean_pass", "common_subexpression_elimination_pass", "constant_folding_pass", "dead_code_elimination_pass", "fuse_gemm_epilogue_pass",
                "fused_swiglu_pass", "add_norm_fuse_pass", "inplace_pass"]
     _PASS_TO_PIR = {
-        "identity_op_clean_pass": ["identity_elim"], "common_subexpression_elimination_pass": ["cse"], "constant_folding_pass": ["constant_fold"],
+        "conv_bn_fuse_pass": ["conv_bn_fuse"], "conv_eltwiseadd_bn_fuse_pass": ["conv_bn_fuse"], "identity_op_clean_pass": ["identity_elim"], "common_subexpression_elimination_pass": ["cse"], "constant_folding_pass": ["constant_fold"],
         "dead_code_elimination_pass": ["dce"], "fuse_gemm_epilogue_pass": ["fuse_matmul_add", "fuse_linear_act_gelu", "fuse_linear_act_relu"],
         "matmul_add_act_fuse_pass": ["fuse_matmul_add", "fuse_linear_act_gelu", "fuse_linear_act_relu"], "fused_swiglu_pass": ["fuse_swiglu"],
         "add_norm_fuse_pass": ["fuse_add_rms_norm"], "inplace_pass": ["inplace"],
@@ -149,7 +149,7 @@ class Config:
             return []
         out = []
         for name in self._opt()["passes"]:
-            for p in self._PASS_TO_PIR.get(name, [name] if name in ("dce", "cse", "identity_elim", "constant_fold", "inplace") else []):
+            for p in self._PASS_TO_PIR.get(name, [name] if name in ("dce", "cse", "identity_elim", "constant_fold", "inplace", "conv_bn_fuse") else []):
                 if p not in out or p == "dce":
                     out.append(p)
         if out and "dce" in out:
@@ -420,6 +420,10 @@ class Predictor:
         try:
             opt, report = pir.optimize(prog, fetch_list=list(self._layer._fetch), passes=passes, return_report=True, cinn=use_cinn)
         except Exception:  # noqa: BLE001  (an op the translator cannot encode: run the program as saved)
+            import os
+
+            if os.environ.get("B200_JIT_DEBUG"):
+                raise
             return []
         if self._config._opt().get("ir_debug"):
             for r in report:

@@ -565,6 +565,81 @@ def lower(tr, pm=None):
     return out
 
 
+def conv_bn_fuse(tr):
+    """Inference: `batch_norm(conv(x, W, b), mean, var, gamma, beta)` with constant statistics becomes `conv(x, W', b')`,
+    W' = W * gamma / sqrt(var + eps) per output channel, b' = (b - mean) * gamma / sqrt(var + eps) + beta.  Works on the Translation (it creates
+    new parameter values).  Parity: conv_bn_fuse_pass of the reference's inference pipeline (paddle/fluid/framework/ir/conv_bn_fuse_pass.cc).
+    Returns the number of fused pairs."""
+    ir = tr.ir
+    fused = 0
+    uses = ir.use_counts()
+    by_result = {}
+    for op in ir.ops():
+        for r in op["results"]:
+            by_result[r] = op
+    for bn in ir.ops():
+        if bn["name"] != "pd_op.batch_norm":
+            continue
+        tb = tr.templates.get(bn["id"])
+        if tb is None or tb[0] != "call":
+            continue
+        args, kw = list(tb[2]), dict(tb[3])
+
+        def arg(i, key, default=None):
+            return kw[key] if key in kw else (args[i] if len(args) > i else default)
+
+        xs, mean_s, var_s, w_s, b_s = arg(0, "input"), arg(1, "running_mean"), arg(2, "running_var"), arg(3, "weight"), arg(4, "bias")
+        training, eps = arg(5, "training", False), arg(7, "eps", 1e-5)
+        if training or not all(isinstance(v, _Slot) for v in (xs, mean_s, var_s)) or not isinstance(eps, float):
+            continue
+        val = lambda slot: bn["operands"][slot.k]      # noqa: E731
+        conv = by_result.get(val(xs))
+        if conv is None or conv["name"] not in ("pd_op.conv2d", "pd_op.conv1d", "pd_op.conv3d") or uses[val(xs)] != 1 or val(xs) in ir.outputs():
+            continue
+        tc = tr.templates.get(conv["id"])
+        if tc is None or tc[0] != "call" or tc[3] or len(tc[2]) < 2 or not isinstance(tc[2][0], _Slot) or not isinstance(tc[2][1], _Slot):
+            continue
+        cargs = list(tc[2])
+        wv = conv["operands"][cargs[1].k]
+        bias_slot = cargs[2] if len(cargs) > 2 else None
+        if wv not in tr.params or (isinstance(bias_slot, _Slot) and conv["operands"][bias_slot.k] not in tr.params) or (bias_slot is not None and not isinstance(bias_slot, _Slot)):
+            continue
+        stats = [tr.params.get(val(s_)) if isinstance(s_, _Slot) else None for s_ in (mean_s, var_s, w_s, b_s)]
+        if stats[0] is None or stats[1] is None or (isinstance(w_s, _Slot) and stats[2] is None) or (isinstance(b_s, _Slot) and stats[3] is None):
+            continue
+        W = _t(tr.params[wv]).detach()
+        mean, var = _t(stats[0]).detach().to(W.dtype), _t(stats[1]).detach().to(W.dtype)
+        gamma = _t(stats[2]).detach().to(W.dtype) if stats[2] is not None else torch.ones_like(mean)
+        beta = _t(stats[3]).detach().to(W.dtype) if stats[3] is not None else torch.zeros_like(mean)
+        b0 = _t(tr.params[conv["operands"][bias_slot.k]]).detach() if isinstance(bias_slot, _Slot) else torch.zeros_like(mean)
+        scale = gamma * torch.rsqrt(var + eps)
+        W2 = (W * scale.reshape(-1, *([1] * (W.dim() - 1)))).contiguous()
+        b2 = ((b0 - mean) * scale + beta).contiguous()
+        wn = ir.add_param(f"conv_bn_w{fused}", *_ty(W2))
+        bnew = ir.add_param(f"conv_bn_b{fused}", *_ty(b2))
+        tr.params[wn], tr.params[bnew] = W2, b2
+        ir.set_insertion_point_after(bn["id"])
+        new = ir.add_op(conv["name"], [conv["operands"][cargs[0].k], wn, bnew], dict(conv["attrs"]), [ir.value_type(bn["results"][0])])
+        ir.reset_insertion_point()
+        rest = tuple(cargs[3:])
+        tr.templates[_op_of(ir, new[0])] = ("call", tc[1], (_Slot(0), _Slot(1), _Slot(2)) + rest, {}, "op")
+        ir.replace_all_uses(bn["results"][0], new[0])
+        ir.erase_op(bn["id"])
+        ir.erase_op(conv["id"])
+        uses = ir.use_counts()
+        fused += 1
+    if fused:
+        ir.verify()
+    return fused
+
+
+def _op_of(ir, value):
+    return ir.value_info(value)["def_op"]
+
+
+TRANSLATION_PASSES = {"conv_bn_fuse": conv_bn_fuse}
+
+
 def optimize(program, fetch_list=None, passes=None, patterns=None, return_report=False, cinn=None):
     """Run a pass pipeline over a recorded static Program and return the optimised Program (same feeds, same fetch targets).
     `cinn`: True / dict of `cinn.fuse` options - after the passes, fusible elementwise / reduction chains become generated kernels
@@ -579,8 +654,14 @@ def optimize(program, fetch_list=None, passes=None, patterns=None, return_report
         for n in program.nodes:          # side-effect nodes keep their inputs alive through is_pure(); nothing else to add
             pass
     tr = translate_to_pir(program, fetch_vids)
+    early = []
+    if passes is not None:                       # passes that need the Translation (they create parameters) run first; the rest is native
+        for name in [p for p in passes if p in TRANSLATION_PASSES]:
+            before = tr.ir.num_ops()
+            early.append({"pass": name, "ops_before": before, "changed": TRANSLATION_PASSES[name](tr), "ops_after": tr.ir.num_ops()})
+        passes = [p for p in passes if p not in TRANSLATION_PASSES]
     pm = PassManager(passes, patterns)
-    report = pm.run(tr.ir)
+    report = early + list(pm.run(tr.ir))
     if cinn is None:
         from ..framework.flags import flag
 

@@ -331,3 +331,40 @@ def test_object_views_walk_and_edit_a_program():
     pir.PassManager(["dce", "compact"], patterns=[]).run(p)
     assert [o.name() for o in pir.global_block(p)] == ["pd_op.matmul", "pd_op.gelu"]
     assert "Value(%" in repr(out) and "Operation(pd_op.matmul" in repr(pir.global_block(p).ops[0])
+
+
+def test_conv_bn_fuse_in_the_predictor(tmp_path):
+    """The predictor's default passes fold inference batch norms into the preceding convolution (fewer ops, same numbers)."""
+    from paddle_b200 import inference, static
+
+    paddle.seed(3)
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            x = static.data("x", [2, 3, 10, 10], "float32")
+            c1, b1 = paddle.nn.Conv2D(3, 8, 3, padding=1), paddle.nn.BatchNorm2D(8)
+            c2, b2 = paddle.nn.Conv2D(8, 8, 3, padding=1, bias_attr=False), paddle.nn.BatchNorm2D(8)
+            for bn in (b1, b2):
+                bn._mean.set_value(paddle.randn([8]) * 0.2)
+                bn._variance.set_value(paddle.rand([8]) + 0.5)
+                bn.weight.set_value(paddle.randn([8]))
+                bn.bias.set_value(paddle.randn([8]))
+                bn.eval()
+            h = paddle.nn.functional.relu(b1(c1(x)))
+            y = paddle.nn.functional.relu(b2(c2(h)) + h)
+        static.save_inference_model(str(tmp_path / "m"), [x], [y], static.Executor(), program=main)
+    finally:
+        paddle.disable_static()
+    data = np.random.RandomState(0).randn(2, 3, 10, 10).astype("float32")
+    cfg0 = inference.Config(str(tmp_path / "m.pdmodel"), str(tmp_path / "m.pdiparams"))
+    cfg0.switch_ir_optim(False)
+    ref = inference.create_predictor(cfg0).run([data])[0]
+    cfg = inference.Config(str(tmp_path / "m.pdmodel"), str(tmp_path / "m.pdiparams"))
+    assert cfg.pass_builder().all_passes()[0] == "conv_bn_fuse_pass"
+    p = inference.create_predictor(cfg)
+    rep = {r["pass"]: r for r in p.ir_pass_report()}
+    assert rep["conv_bn_fuse"]["changed"] == 2
+    names = [getattr(n.fn, "__name__", "") for n in p._layer._blob["program"].nodes]
+    assert "batch_norm" not in names and names.count("conv2d") == 2
+    np.testing.assert_allclose(np.asarray(p.run([data])[0]), np.asarray(ref), rtol=1e-4, atol=1e-5)
