@@ -82,14 +82,20 @@ def test_to_static_backend_cinn_on_device():
             return F.softmax(F.silu(h) * 1.3 - h.mean(-1, keepdim=True), -1)
 
     paddle.seed(0)
-    net = Head().to("gpu")
-    net.eval()
-    x = paddle.randn([64, 256]).cuda()
-    fast = paddle.jit.to_static(net, backend="CINN")
-    with paddle.no_grad():
-        ref = net(x)
-        out = fast(x)
-    rep = fast.forward.cinn_report(x)
+    paddle.set_device("gpu:0")                         # parameters and randn land on the device
+    try:
+        net = Head()
+        net.eval()
+        x = paddle.randn([64, 256])
+        fast = paddle.jit.to_static(net, backend="CINN")
+        with paddle.no_grad():
+            ref = net(x)
+            fast(x)                                    # first call: trace, compile, verify against the eager forward
+            out = fast(x)                              # second call: the compiled program
+        rep = fast.forward.cinn_report(x)
+    finally:
+        paddle.set_device("cpu")
+    assert x.is_cuda
     assert rep is not None and len(rep.groups) >= 1
     assert torch.allclose(out.as_subclass(torch.Tensor), ref.as_subclass(torch.Tensor), rtol=1e-4, atol=1e-6)
 
