@@ -142,33 +142,50 @@ def fuse(tr, min_ops=2, targets=("cuda",), precompile=False):
                     for val, owner in list(group_of.items()):
                         if owner is g:
                             group_of[val] = chosen
-        fresh = chosen is None
-        if fresh:
-            chosen = Group(len(groups), domain)
-            chosen.pos = pos
-        snap = chosen.snapshot()
+        sideways = None
+        if chosen is None:
+            # horizontal fusion: no producer is in a group, but an open group on this domain already reads one of this op's operands - joining
+            # it saves a pass over that tensor (dbeta = dy.sum(0) next to dgamma = (dy * xhat).sum(0))
+            wanted = set(tensor_operands)
+            for g in reversed(groups):
+                if g.open and not g.dead and (g.gb.full == domain if name in _ROW_OPS else g.gb.full == rshape) \
+                        and any(v in wanted for (v, _shape) in g.gb.inputs):
+                    sideways = g
+                    break
+        node = fresh = None
+        for cand_group in ([chosen, None] if chosen is not None else [sideways, None] if sideways is not None else [None]):
+            fresh = cand_group is None
+            grp = Group(len(groups), domain) if fresh else cand_group
+            if fresh:
+                grp.pos = pos
+            snap = grp.snapshot()
 
-        def operand_node(k, g=chosen, op=op):
-            v = op["operands"][k]
-            if v in g.gb.by_value:
-                return g.gb.by_value[v]
-            dt, shape = vtype(v)
-            return g.gb.input(v, shape, dt)
+            def operand_node(k, g=grp, op=op):
+                v = op["operands"][k]
+                if v in g.gb.by_value:
+                    return g.gb.by_value[v]
+                dt, shape = vtype(v)
+                return g.gb.input(v, shape, dt)
 
-        try:
-            args = [_decode(a, operand_node, Slot) for a in tpl[2]]
-            kwargs = {k: _decode(a, operand_node, Slot) for k, a in tpl[3].items()}
-            kwargs = {k: v for k, v in kwargs.items() if not (k == "name" and (v is None or isinstance(v, str)))}
-            node = chosen.fe.lower(name, args, kwargs, rshape, rdt)
-            if not isinstance(node, Node) or node.kind == "in":
-                raise Unsupported("op lowered to no computation")
-            if node.attrs.get("post") and rshape == () and node.dtype == rdt:
-                pass                                  # per-row partials, finished to the recorded scalar on the way out
-            elif node.shape != rshape or node.dtype != rdt:
-                raise Unsupported(f"lowered type {node.dtype}{list(node.shape)} differs from the recorded {rdt}{list(rshape)}")
-        except Unsupported as e:
-            chosen.restore(snap)
-            res.rejected.append((name, str(e)))
+            try:
+                args = [_decode(a, operand_node, Slot) for a in tpl[2]]
+                kwargs = {k: _decode(a, operand_node, Slot) for k, a in tpl[3].items()}
+                kwargs = {k: v for k, v in kwargs.items() if not (k == "name" and (v is None or isinstance(v, str)))}
+                node = grp.fe.lower(name, args, kwargs, rshape, rdt)
+                if not isinstance(node, Node) or node.kind == "in":
+                    raise Unsupported("op lowered to no computation")
+                if node.attrs.get("post") and rshape == () and node.dtype == rdt:
+                    pass                                  # per-row partials, finished to the recorded scalar on the way out
+                elif node.shape != rshape or node.dtype != rdt:
+                    raise Unsupported(f"lowered type {node.dtype}{list(node.shape)} differs from the recorded {rdt}{list(rshape)}")
+                chosen = grp
+                break
+            except Unsupported as e:
+                grp.restore(snap)
+                node = None
+                if cand_group is None:                   # a join that does not fit falls back to a group of its own; only that failure is final
+                    res.rejected.append((name, str(e)))
+        if node is None:
             close_producers(op)
             continue
         node.value_id = r

@@ -650,3 +650,16 @@ def test_column_reductions_bias_gradient_pattern():
     # a row reduction and a column reduction of the same chain do not share a kernel
     rep = _run_both(lambda dy, x: ((dy * x).sum(axis=0), (dy * x).sum(axis=-1)), dict(dy=dy, x=x), rtol=2e-5, atol=2e-5)
     assert all(not (g_["kernel"].spec.col and any(n.kind == "reduce" for n in g_["kernel"].spec.nodes)) for g_ in rep.groups)
+
+
+def test_sibling_reductions_sharing_an_input_join_one_kernel():
+    """LayerNorm-backward shape: dgamma = (dy * xhat).sum(0) and dbeta = dy.sum(0) read dy once."""
+    rng = np.random.default_rng(31)
+    dy, xhat = rng.standard_normal((40, 24)).astype(np.float32), rng.standard_normal((40, 24)).astype(np.float32)
+    rep = _run_both(lambda dy, xhat: ((dy * xhat).sum(axis=0), dy.sum(axis=0)), dict(dy=dy, xhat=xhat), rtol=2e-5, atol=2e-5, expect_kernels=1)
+    g = rep.groups[0]
+    assert g["kind"] == "column" and g["inputs"] == 2 and g["outputs"] == 2 and g["ops"] == ["mul", "sum", "sum"]
+    # a sideways candidate that does not fit (row reduction next to a column group) opens its own group instead of being dropped
+    rep = _run_both(lambda dy, xhat: ((dy * xhat).sum(axis=0), F.softmax(paddle.tanh(dy * 2.0), -1) * 3.0), dict(dy=dy, xhat=xhat), rtol=2e-5, atol=2e-5)
+    assert rep.rejected == [] and "column" in [g_["kind"] for g_ in rep.groups]
+    assert all(not (g_["kernel"].spec.col and any(n.kind == "reduce" for n in g_["kernel"].spec.nodes)) for g_ in rep.groups)
