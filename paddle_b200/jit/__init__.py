@@ -1,10 +1,11 @@
 """paddle.jit. Parity: python/paddle/jit/api.py (to_static, save, load, not_to_static, enable_to_static, ignore_module),
 translated_layer.py (TranslatedLayer).
 
-B200 design ("CUDA streams and graphs instead of a tracing compiler"): ``to_static`` does not trace into an IR.  A
+B200 design ("CUDA streams and graphs instead of a tracing compiler"): by default ``to_static`` does not trace into an IR.  A
 static function keeps running the eager kernels, but once its inputs have a stable signature (shapes/dtypes) the whole
 call is captured into a CUDA graph and replayed with one launch; a guard cache keyed by the signature holds one graph
-per shape.  ``jit.save`` writes the parameters (.pdiparams, same pickle format as paddle.save) plus a .pdmodel file that
+per shape.  ``backend="CINN"`` selects the other mode: trace -> IR passes -> generated kernels (paddle_b200.cinn), verified
+against the eager function on the first call of every signature.  ``jit.save`` writes the parameters (.pdiparams, same pickle format as paddle.save) plus a .pdmodel file that
 pickles the Layer's class path + constructor spec + InputSpec, so ``jit.load`` rebuilds a ``TranslatedLayer``.
 """
 from __future__ import annotations
@@ -134,7 +135,7 @@ class StaticFunction:
         ts = [a for a in list(args) + list(kwargs.values()) if isinstance(a, torch.Tensor)]
         return bool(ts) and all(t.is_cuda for t in ts)
 
-    # ---- backend="CINN": trace -> IR passes -> fused generated kernels (paddle_b200.cinn); no-grad calls only ------------------------------
+    # ---- backend="CINN": trace -> IR passes -> fused generated kernels (paddle_b200.cinn); inference and training ---------------------------
     def _cinn_entry(self, args):
         from .. import cinn, static
 
