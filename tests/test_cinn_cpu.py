@@ -663,3 +663,19 @@ def test_sibling_reductions_sharing_an_input_join_one_kernel():
     rep = _run_both(lambda dy, xhat: ((dy * xhat).sum(axis=0), F.softmax(paddle.tanh(dy * 2.0), -1) * 3.0), dict(dy=dy, xhat=xhat), rtol=2e-5, atol=2e-5)
     assert rep.rejected == [] and "column" in [g_["kind"] for g_ in rep.groups]
     assert all(not (g_["kernel"].spec.col and any(n.kind == "reduce" for n in g_["kernel"].spec.nodes)) for g_ in rep.groups)
+
+
+def test_missing_compiler_degrades_to_the_reference_evaluation(monkeypatch):
+    from paddle_b200.cinn import runtime
+
+    x = torch.randn(4, 8)
+    k = _kernel_of(lambda x: F.softmax(paddle.tanh(x) * 2.0, -1), dict(x=x))
+
+    def boom(src, target, keep_source=True):
+        raise runtime.CompileError("g++: not found")
+
+    monkeypatch.setattr(runtime, "compile_source", boom)
+    k._fn.clear()
+    with pytest.warns(UserWarning, match="could not be built"):
+        out = k(x).as_subclass(torch.Tensor)
+    assert torch.allclose(out, torch.softmax(torch.tanh(x) * 2.0, -1), atol=1e-6)
