@@ -318,6 +318,8 @@ def _minimize_node(optimizer, loss, program):
 
     n = _Node(train_step, (), {}, [], kind="train")
     n.args = (optimizer,)
+    if vid is not None:
+        n.kwargs = {"loss": _Ref(vid)}          # declared read: keeps the loss alive (and re-bound to this slot) when the program goes through IR passes
     program.nodes.append(n)
 
 
@@ -332,6 +334,8 @@ def append_backward(loss, parameter_list=None, no_grad_set=None, callbacks=None)
         env[vid].backward(retain_graph=True)
 
     n = _Node(bwd, (), {}, [], kind="train")
+    if vid is not None:
+        n.kwargs = {"loss": _Ref(vid)}
     prog.nodes.append(n)
     return [(p, p) for p in params]
 
@@ -476,8 +480,10 @@ class Executor:
         folding / fusion patterns) once per fetch set; the lowered program is cached on the source program."""
         from .. import pir
 
-        if not pir.core_available() or any(n.kind not in ("op", "control") for n in program.nodes):
-            return program          # programs with a training node keep their recorded form (its closure re-walks the recorded tape)
+        if not pir.core_available() or any(n.kind not in ("op", "control", "train") for n in program.nodes):
+            return program
+        if any(n.kind == "train" and not n.kwargs for n in program.nodes):
+            return program          # a training node that does not declare what it reads (older pickles): keep the recorded form
         key = tuple(f if isinstance(f, str) else id(f) for f in (fetch_list or []))
         cache = program.__dict__.setdefault("_pir_cache", {})
         if key not in cache or cache[key][0] != len(program.nodes):

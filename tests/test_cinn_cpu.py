@@ -679,3 +679,38 @@ def test_missing_compiler_degrades_to_the_reference_evaluation(monkeypatch):
     with pytest.warns(UserWarning, match="could not be built"):
         out = k(x).as_subclass(torch.Tensor)
     assert torch.allclose(out, torch.softmax(torch.tanh(x) * 2.0, -1), atol=1e-6)
+
+
+def test_static_training_program_through_passes_and_generated_kernels():
+    """FLAGS_enable_pir_api + FLAGS_use_cinn on a program with optimizer.minimize: the training node declares the loss it reads, the forward is
+    rewritten (fusions, generated kernels with generated backward) and the loss curve is the unoptimised one."""
+    def run(flags):
+        old = paddle.get_flags(list(flags))
+        paddle.set_flags(flags)
+        paddle.enable_static()
+        try:
+            paddle.seed(0)
+            main, start = static.Program(), static.Program()
+            with static.program_guard(main, start):
+                x, y = static.data("x", [8, 16], "float32"), static.data("y", [8, 1], "float32")
+                h = static.nn.fc(x, 32)
+                h = h * paddle.rsqrt((h * h).mean(-1, keepdim=True) + 1e-6)
+                h = F.silu(h) + paddle.tanh(h) * 0.1
+                p = static.nn.fc(h, 1)
+                loss = ((p - y) * (p - y)).mean()
+                paddle.optimizer.SGD(learning_rate=0.05).minimize(loss)
+            exe = static.Executor()
+            exe.run(start)
+            rng = np.random.default_rng(0)
+            xv, yv = rng.standard_normal((8, 16)).astype("float32"), rng.standard_normal((8, 1)).astype("float32")
+            return [float(exe.run(main, feed={"x": xv, "y": yv}, fetch_list=[loss])[0]) for _ in range(5)]
+        finally:
+            paddle.disable_static()
+            paddle.set_flags(old)
+
+    ref = run({"FLAGS_enable_pir_api": False, "FLAGS_use_cinn": False})
+    before = cinn.stats["launches"]
+    got = run({"FLAGS_enable_pir_api": True, "FLAGS_use_cinn": True})
+    assert cinn.stats["launches"] - before >= 10                 # forward and backward kernels, every step
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)
+    assert got[-1] < 0.5 * got[0]
