@@ -42,3 +42,14 @@ def recordable(fn):
         return out
 
     return wrapper
+
+
+def make_recordable(namespace, names):
+    """Wrap the named module-level functions of `namespace` (a module's globals()) as recordable ops.  For modules whose public functions compute on
+    raw tensors (fast paths into kernels / index arithmetic) - without this a static program would silently bake its placeholder values in."""
+    for name in names:
+        fn = namespace.get(name)
+        if callable(fn) and not isinstance(fn, type) and not getattr(fn, "_b200_recordable", False):
+            w = recordable(fn)
+            w._b200_recordable = True
+            namespace[name] = w

@@ -132,3 +132,9 @@ def weighted_sample_neighbors(row, colptr, edge_weight, input_nodes, sample_size
         outs.append(row[idx])
         cnts.append(idx.numel())
     return _w(torch.cat(outs) if outs else row[:0]), _w(torch.tensor(cnts, dtype=torch.int32))
+
+
+# static programs record these as single ops (their bodies compute on raw tensors; framework/recording.py)
+from ..framework.recording import make_recordable as _make_recordable  # noqa: E402
+
+_make_recordable(globals(), ['send_u_recv', 'send_ue_recv', 'send_uv', 'segment_sum', 'segment_mean', 'segment_max', 'segment_min'])

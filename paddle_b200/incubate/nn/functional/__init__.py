@@ -426,3 +426,10 @@ def fused_multi_transformer(x, ln_scales, ln_biases, qkv_weights, qkv_biases, li
         if not pre_layer_norm:
             h = F.layer_norm(h, [h.shape[-1]], ffn_ln_scales[i], ffn_ln_biases[i], epsilon)
     return (h, new_caches) if cache_kvs is not None else h
+
+
+from ....framework.recording import make_recordable as _make_recordable  # noqa: E402
+
+# Static-graph recording: these functions work on raw tensors (fast paths straight into the kernels), which the op tape cannot see; each public entry
+# point is therefore recorded as ONE node.  Outside a program_guard the wrapper is a single `is None` test.
+_make_recordable(globals(), __all__)

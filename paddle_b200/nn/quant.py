@@ -108,3 +108,9 @@ class Stub:
         return x
 
     forward = __call__
+
+
+# static programs record these as single ops (their bodies compute on raw tensors; framework/recording.py)
+from ..framework.recording import make_recordable as _make_recordable  # noqa: E402
+
+_make_recordable(globals(), ['weight_quantize', 'weight_dequantize', 'llm_int8_linear', 'apply_per_channel_scale'])

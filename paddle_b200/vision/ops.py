@@ -502,3 +502,9 @@ def decode_jpeg(x, mode="unchanged", name=None):
     a = np.asarray(img)
     a = a[None] if a.ndim == 2 else a.transpose(2, 0, 1)
     return _w(torch.from_numpy(np.ascontiguousarray(a)))
+
+
+# static programs record these as single ops (their bodies compute on raw tensors; framework/recording.py)
+from ..framework.recording import make_recordable as _make_recordable  # noqa: E402
+
+_make_recordable(globals(), ['roi_align', 'roi_pool', 'psroi_pool', 'deform_conv2d', 'box_coder', 'yolo_box', 'prior_box'])

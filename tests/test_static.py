@@ -311,3 +311,78 @@ def test_executor_frees_values_after_their_last_reader():
         paddle.set_flags({"FLAGS_eager_delete_tensor_gb": 0.0})
         paddle.disable_static()
     del side
+
+
+def test_incubate_fused_functionals_are_recorded_in_static_programs():
+    """The fused functionals compute on raw tensors; in a program they are recorded as single nodes, so the program follows its feeds instead
+    of baking the placeholder values in."""
+    import numpy as np
+    import torch
+
+    import paddle_b200 as paddle
+    import paddle_b200.incubate.nn.functional as IF
+    from paddle_b200 import static
+
+    paddle.seed(0)
+    w, b = paddle.rand([8]) + 0.5, paddle.randn([8])
+    lw, lb = paddle.randn([8, 4]), paddle.randn([4])
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            x = static.data("x", [4, 8], "float32")
+            h = IF.fused_rms_norm(x, w, None, 1e-6, 1)
+            h = h[0] if isinstance(h, (tuple, list)) else h
+            h = IF.fused_layer_norm(h, w, b, 1e-5, begin_norm_axis=1)
+            h = h[0] if isinstance(h, (tuple, list)) else h
+            h = IF.fused_bias_act(h, b, act_method="gelu")
+            y = IF.fused_linear_activation(h, lw, lb, activation="relu") + IF.fused_linear(h, lw, lb) + IF.fused_matmul_bias(h, lw, lb)
+        assert len(main.nodes) >= 6
+        exe = static.Executor()
+        outs = []
+        for seed in (1, 2):
+            xv = np.random.RandomState(seed).randn(4, 8).astype("float32")
+            got = exe.run(main, feed={"x": xv}, fetch_list=[y])[0]
+            t = torch.from_numpy(xv)
+            wt, bt, lwt, lbt = (v.as_subclass(torch.Tensor) for v in (w, b, lw, lb))
+            r = t * torch.rsqrt((t * t).mean(-1, keepdim=True) + 1e-6) * wt
+            r = torch.nn.functional.layer_norm(r, (8,), wt, bt, 1e-5)
+            r = torch.nn.functional.gelu(r + bt)
+            lin = r @ lwt + lbt
+            np.testing.assert_allclose(got, (torch.relu(lin) + 2 * lin).numpy(), rtol=2e-4, atol=2e-4)
+            outs.append(got)
+        assert not np.allclose(outs[0], outs[1])
+    finally:
+        paddle.disable_static()
+
+
+def test_raw_tensor_namespaces_are_recorded():
+    """geometric / vision.ops / nn.quant functions index raw tensors; in a program each is one recorded node."""
+    import numpy as np
+
+    import paddle_b200 as paddle
+    from paddle_b200 import static
+
+    idx = paddle.to_tensor([0, 1, 2, 0])
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            x = static.data("x", [4, 8], "float32")
+            a = paddle.geometric.send_u_recv(x, idx, idx, "sum")
+            b = paddle.geometric.segment_sum(x, paddle.to_tensor([0, 0, 1, 1]))
+            r = paddle.vision.ops.roi_align(x.reshape([1, 2, 4, 4]), paddle.to_tensor([[0.0, 0.0, 2.0, 2.0]]), paddle.to_tensor([1], dtype="int32"), 2)
+        exe = static.Executor()
+        res = []
+        for seed in (0, 1):
+            xv = np.random.RandomState(seed).randn(4, 8).astype("float32")
+            ga, gb, gr = exe.run(main, feed={"x": xv}, fetch_list=[a, b, r])
+            ref = np.zeros_like(xv)
+            for s, d in zip([0, 1, 2, 0], [0, 1, 2, 0]):
+                ref[d] += xv[s]
+            np.testing.assert_allclose(ga, ref, rtol=1e-6)
+            np.testing.assert_allclose(gb, np.stack([xv[:2].sum(0), xv[2:].sum(0)]), rtol=1e-6)
+            res.append(gr)
+        assert res[0].shape == (1, 2, 2, 2) and not np.allclose(res[0], res[1])
+    finally:
+        paddle.disable_static()
