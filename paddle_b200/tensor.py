@@ -16,6 +16,7 @@ import torch
 
 from .framework import dtype as _dt
 from .framework import place as _place
+from .framework import recording as _rec
 
 _NOWRAP = None
 
@@ -175,7 +176,17 @@ class Tensor(torch.Tensor):
         return True
 
     # ---- conversion --------------------------------------------------------
+    def _no_static_value(self, what):
+        """A value of a program that is being built has no data yet: a host read would hand the PLACEHOLDER's zeros to python code (an `if`, a loop
+        bound, a shape) and freeze them into the program.  The reference raises here too."""
+        prog = _rec.current[0]
+        if prog is not None and _rec._inside[0] == 0 and id(self) in prog._vids:
+            raise RuntimeError(f"{what} of a program variable while the program is being built: it has no value yet (fetch it through Executor.run, "
+                               "or use static.nn.cond / while_loop for value-dependent control flow)")
+
     def numpy(self):
+        if _rec.current[0] is not None:
+            self._no_static_value(".numpy()")
         t = self.detach().as_subclass(torch.Tensor)
         if t.device.type != "cpu":
             t = t.cpu()
@@ -287,6 +298,8 @@ class Tensor(torch.Tensor):
     cast = astype
 
     def item(self, *idx):
+        if _rec.current[0] is not None:
+            self._no_static_value(".item()")
         if idx:
             return torch.Tensor.item(self.reshape(-1)[idx[0]] if len(idx) == 1 else self[idx])
         return torch.Tensor.item(self)
@@ -409,7 +422,29 @@ class Tensor(torch.Tensor):
         return self.size(0)
 
     def __bool__(self):
+        if _rec.current[0] is not None:
+            self._no_static_value("bool()")
         return bool(torch.Tensor.item(self)) if self.numel() == 1 else torch.Tensor.__bool__(self)
+
+    def __float__(self):
+        if _rec.current[0] is not None:
+            self._no_static_value("float()")
+        return torch.Tensor.__float__(self)
+
+    def __int__(self):
+        if _rec.current[0] is not None:
+            self._no_static_value("int()")
+        return torch.Tensor.__int__(self)
+
+    def __index__(self):
+        if _rec.current[0] is not None:
+            self._no_static_value("an integer index")
+        return torch.Tensor.__index__(self)
+
+    def tolist(self):
+        if _rec.current[0] is not None:
+            self._no_static_value(".tolist()")
+        return torch.Tensor.tolist(self)
 
     def dim(self):
         return torch.Tensor.dim(self)

@@ -386,3 +386,30 @@ def test_raw_tensor_namespaces_are_recorded():
         assert res[0].shape == (1, 2, 2, 2) and not np.allclose(res[0], res[1])
     finally:
         paddle.disable_static()
+
+
+def test_host_reads_of_program_variables_raise_while_building():
+    """.numpy() / .item() / bool() / int() on a value of the program under construction would hand placeholder zeros to python code; they raise,
+    like in the reference.  Constants and fetched results are ordinary tensors."""
+    import pytest
+
+    import paddle_b200 as paddle
+    from paddle_b200 import static
+
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            x = static.data("x", [4, 8], "float32")
+            y = (x * 2).sum()
+            for read in (lambda: y.numpy(), lambda: y.item(), lambda: bool(y > 0), lambda: float(y), lambda: int(y), lambda: x.tolist()):
+                with pytest.raises(RuntimeError, match="no value yet"):
+                    read()
+            with pytest.raises(RuntimeError, match="no value yet"):
+                if y > 0:                                  # value-dependent python branch
+                    pass
+            assert paddle.to_tensor([3.0]).item() == 3.0   # not a program value
+        out = static.Executor().run(main, feed={"x": __import__("numpy").ones((4, 8), "float32")}, fetch_list=[y], return_numpy=False)[0]
+        assert float(out) == 64.0 and out.item() == 64.0
+    finally:
+        paddle.disable_static()
