@@ -42,7 +42,6 @@ def _patch():
             if callable(fn):
                 setattr(Tensor, name, fn)
     Tensor.where = lambda self, x=None, y=None, name=None: search.where(self, x, y)
-    Tensor.tolist = lambda self: torch.Tensor.tolist(self)
     Tensor.einsum = None
     del Tensor.einsum
     # operators with paddle scalar/ndarray tolerance are inherited from torch.Tensor; only the few that differ:
