@@ -468,6 +468,12 @@ class Executor:
             else:
                 vid = program._fetch_alias.get(id(f))
                 if vid is None:
+                    if isinstance(f, torch.Tensor) and program.placeholders and not getattr(f, "persistable", False) and not isinstance(f, torch.nn.Parameter) \
+                            and not getattr(f, "is_parameter", False):
+                        import warnings
+
+                        warnings.warn("Executor.run: a fetch target is not a value of this program (it was computed outside the recorded ops, e.g. on raw tensors); "
+                                      "its trace-time value is returned and does not depend on the feeds", stacklevel=2)
                     outs.append(f.numpy() if return_numpy and isinstance(f, torch.Tensor) else f)
                     continue
             v = env[vid]
