@@ -418,7 +418,7 @@ class Predictor:
         if not pir.core_available() or any(n.kind != "op" for n in prog.nodes):
             return []
         try:
-            opt, report = pir.optimize(prog, fetch_list=list(self._layer._fetch), passes=passes, return_report=True, cinn=use_cinn)
+            opt, report = pir.optimize(prog, fetch_list=list(self._layer._fetch), passes=passes, return_report=True, cinn=False)
         except Exception:  # noqa: BLE001  (an op the translator cannot encode: run the program as saved)
             import os
 
@@ -429,7 +429,21 @@ class Predictor:
             for r in report:
                 print(f"[ir pass] {r['pass']}: {r['ops_before']} -> {r['ops_after']} ops ({r['changed']} rewrites)")
         blob["program"] = opt
+        if use_cinn:
+            # generated kernels are compiled for concrete shapes and the saved program may declare dynamic ones: the Executor specialises it per
+            # feed signature (first run generic, later runs compiled; static/__init__.py:Executor._specialised)
+            opt.__dict__["_cinn_on_run"] = True
         return report
+
+    def cinn_report(self):
+        """{feed signature: FusionResult} of the specialisations built so far (Config.enable_cinn())."""
+        prog = getattr(self._layer, "_blob", {}).get("program") if hasattr(self._layer, "_blob") else None
+        out = {}
+        for (_, sig, _n), p in (getattr(prog, "__dict__", {}).get("_cinn_cache", {}) or {}).items():
+            rep = getattr(p, "__dict__", {}).get("_cinn_report")
+            if rep is not None:
+                out[sig] = rep
+        return out
 
     def ir_pass_report(self):
         """[{pass, ops_before, ops_after, changed}] of the IR passes that ran when this predictor was built."""

@@ -415,9 +415,22 @@ class Executor:
             return []   # startup program: parameters are initialised at creation time
         from ..framework.flags import flag
 
-        if flag("FLAGS_enable_pir_api", False) and program.nodes and not program.__dict__.get("_pir_report"):
-            program = self._pir_optimized(program, fetch_list)
         feed = feed or {}
+        on_run = program.__dict__.get("_cinn_on_run")                 # set by inference.Config.enable_cinn(): specialise per feed signature
+        if program.nodes and (on_run or (flag("FLAGS_enable_pir_api", False) and not program.__dict__.get("_pir_report"))):
+            if on_run or flag("FLAGS_use_cinn", False):
+                hit = self._specialised(program, fetch_list, feed, return_numpy, passes=[] if on_run else None)
+                if isinstance(hit, tuple):                              # first run with this signature: the generic program's results
+                    return hit[1]
+                program = hit
+            else:
+                program = self._pir_optimized(program, fetch_list)
+        return self._execute(program, feed, fetch_list, return_numpy)[0]
+
+    def _execute(self, program, feed, fetch_list, return_numpy, keep_env=False):
+        """One pass over the program's nodes.  Returns (fetched values, value table when keep_env)."""
+        from ..framework.flags import flag
+
         env = {}
         dev = None
         for name, vid in program.placeholders.items():
@@ -458,7 +471,7 @@ class Executor:
             if gc is not None:                          # values nobody will read any more leave the table right away
                 gc.after(n, env)
 
-        gc = _ValueGC.plan(program, fetch_list, set(env)) if flag("FLAGS_eager_delete_tensor_gb", 0.0) >= 0 else None
+        gc = _ValueGC.plan(program, fetch_list, set(env)) if (flag("FLAGS_eager_delete_tensor_gb", 0.0) >= 0 and not keep_env) else None
         self._schedule(program, run_node)
         self.last_gc_stats = gc.stats if gc is not None else None
         outs = []
@@ -473,12 +486,45 @@ class Executor:
                         import warnings
 
                         warnings.warn("Executor.run: a fetch target is not a value of this program (it was computed outside the recorded ops, e.g. on raw tensors); "
-                                      "its trace-time value is returned and does not depend on the feeds", stacklevel=2)
+                                      "its trace-time value is returned and does not depend on the feeds", stacklevel=3)
                     outs.append(f.numpy() if return_numpy and isinstance(f, torch.Tensor) else f)
                     continue
             v = env[vid]
             outs.append(v.detach().cpu().as_subclass(Tensor).numpy() if return_numpy else v)
-        return outs
+        return outs, (env if keep_env else None)
+
+    def _specialised(self, program, fetch_list, feed, return_numpy, passes=None):
+        """Generated kernels are compiled for concrete shapes, a program may declare dynamic ones (-1: its recorded example uses extent 1).  So the
+        program is specialised per FEED SIGNATURE: the first run with a signature executes the generic program (its results are returned) and keeps
+        every value; their actual types go into the IR, the passes + kernel fusion run on that, and later runs with the same signature use the
+        result.  Kernels whose source does not depend on the leading extents share one compiled object across signatures (cinn/codegen.py).
+        Returns the specialised program, or (None, outputs) on the first run."""
+        import copy
+
+        from .. import pir
+
+        if not pir.core_available() or any(n.kind not in ("op", "control", "train") for n in program.nodes) \
+                or any(n.kind == "train" and not n.kwargs for n in program.nodes):
+            return program
+        sig = tuple(sorted((name, tuple(v.shape), str(getattr(v, "dtype", ""))) for name, v in feed.items() if name in program.placeholders))
+        key = (tuple(f if isinstance(f, str) else id(f) for f in (fetch_list or [])), sig, len(program.nodes))
+        cache = program.__dict__.setdefault("_cinn_cache", {})
+        if key in cache:
+            return cache[key]
+        outs, env = self._execute(program, feed, fetch_list, return_numpy, keep_env=True)
+        try:
+            shaped = copy.copy(program)
+            shaped.__dict__ = dict(program.__dict__)
+            shaped.__dict__.pop("_pir_report", None)
+            shaped._keep = [env.get(vid, t) for vid, t in enumerate(program._keep)]
+            cache[key] = pir.optimize(shaped, fetch_list=fetch_list, passes=passes, cinn=True)
+        except Exception:  # noqa: BLE001  (an op the translator cannot encode, a kernel that cannot be generated: run as recorded)
+            import os
+
+            if os.environ.get("B200_JIT_DEBUG"):
+                raise
+            cache[key] = program
+        return None, outs
 
     @staticmethod
     def _pir_optimized(program, fetch_list):
@@ -494,7 +540,7 @@ class Executor:
         cache = program.__dict__.setdefault("_pir_cache", {})
         if key not in cache or cache[key][0] != len(program.nodes):
             try:
-                cache[key] = (len(program.nodes), pir.optimize(program, fetch_list=fetch_list))
+                cache[key] = (len(program.nodes), pir.optimize(program, fetch_list=fetch_list, cinn=False))      # shape-independent passes only
             except Exception:  # noqa: BLE001  (an op the translator cannot encode: run as recorded)
                 cache[key] = (len(program.nodes), program)
         return cache[key][1]

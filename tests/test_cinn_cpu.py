@@ -462,8 +462,7 @@ def test_random_program_gradients(seed):
 
 
 def test_static_executor_uses_generated_kernels_under_the_flags():
-    """FLAGS_enable_pir_api + FLAGS_use_cinn: Executor.run compiles inference programs on first use (programs with a training node keep their
-    recorded form)."""
+    """FLAGS_enable_pir_api + FLAGS_use_cinn: Executor.run specialises a program per feed signature (first run generic, later runs compiled)."""
     paddle.enable_static()
     old = paddle.get_flags(["FLAGS_enable_pir_api", "FLAGS_use_cinn"])
     try:
@@ -474,8 +473,12 @@ def test_static_executor_uses_generated_kernels_under_the_flags():
             out = F.softmax(paddle.tanh(x) * 2.0 - x.mean(-1, keepdim=True), -1)
         xv = np.random.default_rng(0).standard_normal((6, 20)).astype("float32")
         before = cinn.stats["launches"]
-        got = static.Executor().run(main, feed={"x": xv}, fetch_list=[out])[0]
+        exe = static.Executor()
+        first = exe.run(main, feed={"x": xv}, fetch_list=[out])[0]         # first run with this feed signature: generic program, then specialise
+        assert cinn.stats["launches"] == before
+        got = exe.run(main, feed={"x": xv}, fetch_list=[out])[0]
         assert cinn.stats["launches"] == before + 1
+        np.testing.assert_allclose(got, first, rtol=2e-5, atol=1e-7)
     finally:
         paddle.set_flags(old)
         paddle.disable_static()
@@ -484,32 +487,40 @@ def test_static_executor_uses_generated_kernels_under_the_flags():
 
 
 def test_inference_config_enable_cinn(tmp_path):
-    """Config.enable_cinn(): the predictor's program runs its pointwise / softmax tail as one generated kernel (reference: AnalysisConfig::EnableCINN)."""
+    """Config.enable_cinn(): the predictor's program runs its pointwise / softmax tail as one generated kernel (reference: AnalysisConfig::EnableCINN).
+    The saved program declares a dynamic batch; the executor specialises per input signature (first run generic, later runs compiled)."""
     from paddle_b200 import inference
 
     paddle.enable_static()
     try:
         main = static.Program()
         with static.program_guard(main):
-            x = static.data("x", [4, 16], "float32")
+            x = static.data("x", [-1, 16], "float32")
             w = paddle.to_tensor(np.random.RandomState(0).randn(16, 24).astype("float32"))
             h = paddle.matmul(x, w)
             y = F.softmax(paddle.tanh(h) * 1.5 + F.sigmoid(h), -1)
         static.save_inference_model(str(tmp_path / "m"), [x], [y], static.Executor(), program=main)
     finally:
         paddle.disable_static()
-    data = np.random.RandomState(2).randn(4, 16).astype("float32")
     cfg0 = inference.Config(str(tmp_path / "m.pdmodel"), str(tmp_path / "m.pdiparams"))
-    ref = inference.create_predictor(cfg0).run([data])[0]
+    plain = inference.create_predictor(cfg0)
     cfg = inference.Config(str(tmp_path / "m.pdmodel"), str(tmp_path / "m.pdiparams"))
     cfg.enable_cinn()
-    before = cinn.stats["launches"]
     p = inference.create_predictor(cfg)
-    rep = {r["pass"]: r for r in p.ir_pass_report()}
-    assert rep["cinn_fusion"]["changed"] == 1 and rep["cinn_fusion"]["ops_after"] < rep["cinn_fusion"]["ops_before"]
-    got = p.run([data])[0]
-    assert cinn.stats["launches"] == before + 1
-    np.testing.assert_allclose(np.asarray(got), np.asarray(ref), rtol=2e-5, atol=1e-7)
+    before = cinn.stats["launches"]
+    for n_spec, batch in enumerate((4, 3), 1):
+        data = np.random.RandomState(batch).randn(batch, 16).astype("float32")
+        ref = plain.run([data])[0]
+        first = p.run([data])[0]                              # first run with this signature: generic program, then specialise
+        launches = cinn.stats["launches"]
+        got = p.run([data])[0]
+        assert cinn.stats["launches"] == launches + 1 and len(p.cinn_report()) == n_spec
+        np.testing.assert_allclose(np.asarray(first), np.asarray(ref), rtol=2e-5, atol=1e-7)
+        np.testing.assert_allclose(np.asarray(got), np.asarray(ref), rtol=2e-5, atol=1e-7)
+    assert cinn.stats["launches"] == before + 2
+    reps = list(p.cinn_report().values())
+    assert all(len(r.groups) == 1 and "softmax" in r.groups[0]["ops"] for r in reps)
+    assert reps[0].groups[0]["kernel"].source("cuda") == reps[1].groups[0]["kernel"].source("cuda")      # one compiled object for both batch sizes
 
 
 def test_groups_that_differ_only_in_leading_extents_share_one_object():
