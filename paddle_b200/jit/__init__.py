@@ -67,6 +67,8 @@ class StaticFunction:
             fn = self._dygraph_fn
         self._fn, self._layer, self._input_spec = fn, layer, input_spec
         self._backend = backend.upper() if isinstance(backend, str) else None
+        if self._backend is None and getattr(build_strategy, "build_cinn_pass", False):       # BuildStrategy().build_cinn_pass = True (older spelling)
+            self._backend = "CINN"
         self._cinn = {}                 # input signature -> (executor, program, feed names, fetch targets, single result?) or None
         self._graphs = {}
         self._train_graphs = {}

@@ -637,6 +637,10 @@ class Executor:
 class CompiledProgram:
     def __init__(self, program_or_graph, build_strategy=None):
         self._program = program_or_graph
+        self._build_strategy = build_strategy
+        if getattr(build_strategy, "build_cinn_pass", False) and hasattr(program_or_graph, "nodes"):
+            # BuildStrategy.build_cinn_pass: pointwise / reduction chains run as generated kernels, specialised per feed signature by the Executor
+            program_or_graph.__dict__["_cinn_on_run"] = True
 
     def with_data_parallel(self, *a, **k):
         return self

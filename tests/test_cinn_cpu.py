@@ -725,3 +725,32 @@ def test_static_training_program_through_passes_and_generated_kernels():
     assert cinn.stats["launches"] - before >= 10                 # forward and backward kernels, every step
     np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)
     assert got[-1] < 0.5 * got[0]
+
+
+def test_build_strategy_build_cinn_pass():
+    """CompiledProgram(program, BuildStrategy(build_cinn_pass=True)) and to_static(build_strategy=...) select the generated-kernel path."""
+    bs = static.BuildStrategy()
+    bs.build_cinn_pass = True
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            x = static.data("x", [-1, 12], "float32")
+            out = F.softmax(paddle.tanh(x) * 2.0, -1) * 3.0
+        cp = static.CompiledProgram(main, build_strategy=bs)
+        exe = static.Executor()
+        xv = np.random.default_rng(0).standard_normal((5, 12)).astype("float32")
+        a = exe.run(cp, feed={"x": xv}, fetch_list=[out])[0]
+        before = cinn.stats["launches"]
+        b = exe.run(cp, feed={"x": xv}, fetch_list=[out])[0]
+        assert cinn.stats["launches"] == before + 1
+        np.testing.assert_allclose(b, a, rtol=2e-5, atol=1e-7)
+    finally:
+        paddle.disable_static()
+    f = paddle.jit.to_static(lambda t: F.softmax(paddle.tanh(t) * 2.0, -1) * 3.0, build_strategy=bs)
+    t = paddle.to_tensor(xv)
+    with paddle.no_grad():
+        f(t)
+        got = f(t)
+    assert f.cinn_report(t) is not None
+    np.testing.assert_allclose(got.numpy(), a, rtol=2e-5, atol=1e-7)
