@@ -522,9 +522,5 @@ def block_diag(inputs, name=None):
     return torch.block_diag(*[T(i) for i in inputs])
 
 
-def pad_sequences_placeholder():  # pragma: no cover
-    raise NotImplementedError
-
-
 __all__ = [n for n in list(globals()) if not n.startswith("_") and n not in (
     "np", "torch", "builtins", "T", "ax", "dt", "raw", "shp", "to_int", "to_tensor", "wrap", "annotations", "pad_sequences_placeholder")]
