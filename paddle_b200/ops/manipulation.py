@@ -523,4 +523,4 @@ def block_diag(inputs, name=None):
 
 
 __all__ = [n for n in list(globals()) if not n.startswith("_") and n not in (
-    "np", "torch", "builtins", "T", "ax", "dt", "raw", "shp", "to_int", "to_tensor", "wrap", "annotations", "pad_sequences_placeholder")]
+    "np", "torch", "builtins", "T", "ax", "dt", "raw", "shp", "to_int", "to_tensor", "wrap", "annotations")]
