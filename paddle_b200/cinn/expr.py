@@ -175,10 +175,6 @@ def _is_num(v):
     return isinstance(v, (int, float)) and not isinstance(v, bool) or isinstance(v, bool)
 
 
-def _tensor_args(args):
-    return [a for a in args if isinstance(a, Node)]
-
-
 class Frontend:
     """`lower(name, args, kwargs, out_shape, out_dtype)` where tensor arguments are already Nodes (or python numbers).  Returns the node that
     holds the op's result.  Raises Unsupported for anything that is not a fusible primitive / composite."""

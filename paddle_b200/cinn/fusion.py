@@ -12,7 +12,7 @@ import hashlib
 import torch
 
 from . import codegen
-from .expr import Frontend, GroupBuilder, Node, Unsupported, dtype_name
+from .expr import Frontend, GroupBuilder, Node, Unsupported
 from .runtime import CompileError, FusedKernel
 
 _PATTERN_OPS = {"swiglu"}                                                   # ops DRR patterns introduce that lower to primitives

@@ -2,8 +2,6 @@
 generators.  Used as the autograd fall-back of a fused kernel whose backward cannot be generated, and by the tests as an oracle."""
 from __future__ import annotations
 
-import math
-
 import torch
 
 from .expr import Node
@@ -83,4 +81,3 @@ def evaluate(spec, tensors, widen=True, finished=True):
 
 
 __all__ = ["evaluate"]
-_ = math

@@ -15,7 +15,6 @@ from __future__ import annotations
 import torch
 
 from ..incubate.nn.paged_attention import block_attention
-from ..tensor import Tensor
 from .generation import _raw, _sample, _w
 
 
