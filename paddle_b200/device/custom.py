@@ -31,7 +31,22 @@ def load_custom_device(path):
     if dev.device_type in _REGISTRY:
         raise RuntimeError(f"custom device type '{dev.device_type}' is already registered (from {_REGISTRY[dev.device_type].path})")
     _REGISTRY[dev.device_type] = dev
+    _register_kernels(dev.device_type)
     return dev
+
+
+def _register_kernels(device_type):
+    """The device type becomes a backend of the KernelFactory: every op with a host implementation gets a kernel that launches the plug-in's device
+    kernel when it has one and falls back to the host otherwise; `register_kernel(op, backend=device_type)` adds more (custom kernels, reference:
+    paddle/phi/core/custom_kernel.cc)."""
+    from ..kernels.registry import KernelFactory
+
+    f = KernelFactory.instance()
+    dtypes = tuple(_NP2NAME.values())
+    for op in _HOST_IMPL:
+        if _HOST_IMPL[op] is None or any(k.backend == device_type for k in f.kernels(op)):
+            continue
+        f.register(op, device_type, dtypes, (lambda *ins, _op=op: run_op(_op, list(ins))), native=f"plug-in '{device_type}' kernel or host fallback")
 
 
 def load_custom_device_dir(root):

@@ -55,16 +55,20 @@ class Kernel:
         return self.fn(*args, **kwargs)
 
 
+def _is_keyed(a):
+    """Arguments that carry a kernel key: torch tensors and plug-in device tensors (device.custom.CustomTensor: `.place`, numpy `.dtype`)."""
+    return isinstance(a, torch.Tensor) or (hasattr(a, "place") and hasattr(a, "dtype") and hasattr(a.place, "get_device_type"))
+
+
 def _dtype_name(t):
     return str(t.dtype).replace("torch.", "")
 
 
 def _backend_of(t):
+    if not isinstance(t, torch.Tensor):
+        return t.place.get_device_type()                 # a custom device: its plug-in's device type is the backend
     if t.is_cuda:
         return "GPU"
-    place = getattr(t, "_custom_place", None)
-    if place is not None:
-        return place.get_device_type()
     return "CPU"
 
 
@@ -118,9 +122,9 @@ class KernelFactory:
         ks = self._table.get(op)
         if not ks:
             raise KeyError(f"no kernel is registered for op '{op}'")
-        t = next((a for a in args if isinstance(a, torch.Tensor)), None)
+        t = next((a for a in args if _is_keyed(a)), None)
         if t is None:
-            t = next((a for a in kwargs.values() if isinstance(a, torch.Tensor)), None)
+            t = next((a for a in kwargs.values() if _is_keyed(a)), None)
         if t is None:
             raise TypeError(f"op '{op}': kernel selection needs a tensor argument")
         backend, dt = _backend_of(t), _dtype_name(t)

@@ -117,3 +117,27 @@ def test_rejects_bad_plugins(tmp_path):
             C.load_custom_device(dev.path)
     finally:
         C.unload_custom_device("custom_cpu")
+
+
+def test_plugin_device_type_is_a_kernel_factory_backend(plugin):
+    """Loading a plug-in registers its device type as a backend: `dispatch(op, custom tensors)` selects its kernels, and a user kernel registered
+    for that backend (reference: custom kernels for custom devices) takes part in the same selection."""
+    from paddle_b200.kernels.registry import KernelFactory, KernelKey, dispatch, register_kernel
+
+    f = KernelFactory.instance()
+    assert f.has_kernel("add", KernelKey("custom_cpu", "float32")) and f.has_kernel("relu", KernelKey("custom_cpu", "float32"))
+    place = C.CustomPlace("custom_cpu", 0)
+    a = C.to_device(np.arange(6, dtype=np.float32).reshape(2, 3) - 2, place)
+    b = C.to_device(np.ones((2, 3), np.float32), place)
+    k = f.select("add", a, b)
+    assert k.backend == "custom_cpu"
+    np.testing.assert_allclose(dispatch("add", a, b).numpy(), a.numpy() + 1)
+    np.testing.assert_allclose(dispatch("relu", a).numpy(), np.maximum(a.numpy(), 0))
+
+    @register_kernel("negate", backend="custom_cpu", dtypes=("float32",))
+    def negate(t):
+        return C.to_device(-t.numpy(), t.place)
+
+    np.testing.assert_allclose(dispatch("negate", a).numpy(), -a.numpy())
+    with pytest.raises(NotImplementedError):
+        dispatch("negate", paddle.ones([2]))                      # no kernel of this op for the CPU backend
