@@ -114,6 +114,10 @@ class Program:
         self.random_seed = 0
         self._fetch_alias = {}       # id(example tensor) -> vid (for fetch_list lookups after recording)
         self._name2vid = {}
+        try:
+            _live_programs.add(self)     # global_scope().find_var(name) looks parameters up through the live programs
+        except NameError:                # module still initialising
+            pass
 
     # ---- recording -----------------------------------------------------------------------------------------
     def _new_vid(self, t, name=None):
@@ -303,6 +307,8 @@ def create_global_var(shape, value, dtype, persistable=False, force_cpu=False, n
     t.persistable = persistable
     if name:
         t.name = name
+    if persistable and name:
+        _global_vars.append(t)
     return t
 
 
@@ -657,18 +663,137 @@ class ExecutionStrategy:
         self.num_threads, self.num_iteration_per_drop_scope = 1, 10
 
 
+class _TensorView:
+    """What `scope.find_var(name).get_tensor()` hands out (the LoDTensor handle of the reference): reads and writes go to the live tensor, so
+    `np.array(t)` sees the current parameter value and `t.set(array, place)` changes what the next Executor.run computes with."""
+
+    def __init__(self, holder):
+        self._h = holder
+
+    def _t(self):
+        t = self._h._tensor
+        if t is None:
+            raise RuntimeError(f"variable '{self._h.name}' holds no tensor yet")
+        return t
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._t().detach().cpu().as_subclass(torch.Tensor)
+        a = a.float().numpy() if a.dtype == torch.bfloat16 else a.numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+    def set(self, value, place=None):
+        src = value if isinstance(value, torch.Tensor) else torch.as_tensor(np.asarray(value))
+        t = self._h._tensor
+        if t is None:
+            self._h._tensor = src.clone().as_subclass(Tensor)
+            return
+        if tuple(src.shape) != tuple(t.shape):
+            raise ValueError(f"set: shape {list(src.shape)} does not match variable '{self._h.name}' {list(t.shape)}")
+        with torch.no_grad():
+            t.as_subclass(torch.Tensor).copy_(src.to(t.dtype))
+
+    def shape(self):
+        return list(self._t().shape)
+
+    def _dtype(self):
+        return self._t().dtype
+
+    def _place(self):
+        return self._t().place if hasattr(self._t(), "place") else CPUPlace()
+
+    def lod(self):
+        return []
+
+    def recursive_sequence_lengths(self):
+        return []
+
+    def set_lod(self, lod):
+        pass
+
+    def set_recursive_sequence_lengths(self, lens):
+        pass
+
+    def _is_initialized(self):
+        return self._h._tensor is not None
+
+
+class _ScopeVar:
+    def __init__(self, name, tensor=None):
+        self.name, self._tensor = name, tensor
+
+    def get_tensor(self):
+        return _TensorView(self)
+
+    def get_value(self):
+        return self._tensor
+
+    def set_value(self, value):
+        _TensorView(self).set(value)
+
+
 class _Scope:
-    def __init__(self):
+    """Name -> variable table (reference: paddle/fluid/framework/scope.h, `paddle.static.global_scope()`).  Persistable variables - the parameters
+    and global vars of every live Program - are visible in the global scope by name; `var(name)` creates a local one; child scopes chain up."""
+
+    def __init__(self, parent=None):
         self.vars = {}
+        self._parent = parent
+        self._kids = []
+
+    def var(self, name=None):
+        name = name or f"_generated_var_{len(self.vars)}"
+        if name not in self.vars:
+            self.vars[name] = _ScopeVar(name)
+        return self.vars[name]
 
     def find_var(self, name):
-        return self.vars.get(name)
+        v = self.vars.get(name)
+        if v is not None:
+            return v
+        if self._parent is not None:
+            return self._parent.find_var(name)
+        if self is _root_scope:
+            t = _find_persistable(name)
+            if t is not None:
+                v = self.vars[name] = _ScopeVar(name, t)
+                return v
+        return None
 
-    def var(self, name):
-        return self.vars.setdefault(name, None)
+    def erase(self, names):
+        for n in names:
+            self.vars.pop(n, None)
+
+    def local_var_names(self):
+        return list(self.vars)
+
+    def new_scope(self):
+        s = _Scope(parent=self)
+        self._kids.append(s)
+        return s
+
+    def drop_kids(self):
+        self._kids.clear()
 
 
-_scope = _Scope()
+def _find_persistable(name):
+    """A parameter / persistable global var of any live Program (or of the default programs), by name."""
+    for prog in list(_live_programs):
+        for p in prog.all_parameters():
+            if getattr(p, "name", None) == name:
+                return p
+    for t in list(_global_vars):
+        if getattr(t, "name", None) == name:
+            return t
+    return None
+
+
+import weakref as _weakref  # noqa: E402
+
+_live_programs = _weakref.WeakSet()
+_global_vars = []
+_root_scope = _Scope()
+_scope = _root_scope
+Scope = _Scope
 
 
 def global_scope():

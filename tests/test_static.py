@@ -413,3 +413,43 @@ def test_host_reads_of_program_variables_raise_while_building():
         assert float(out) == 64.0 and out.item() == 64.0
     finally:
         paddle.disable_static()
+
+
+def test_global_scope_reads_and_writes_parameters():
+    """`global_scope().find_var(name).get_tensor()`: np.array() reads the live parameter, .set() changes what the next run computes with; a fresh
+    Scope is empty; scopes chain through new_scope()."""
+    import numpy as np
+
+    import paddle_b200 as paddle
+    from paddle_b200 import static
+
+    paddle.enable_static()
+    try:
+        main, start = static.Program(), static.Program()
+        with static.program_guard(main, start):
+            x = static.data("x", [2, 4], "float32")
+            y = static.nn.fc(x, 3)
+        exe = static.Executor()
+        exe.run(start)
+        wname, bname = [p.name for p in main.all_parameters()]
+        sc = static.global_scope()
+        w = sc.find_var(wname).get_tensor()
+        assert np.array(w).shape == (4, 3) and w.shape() == [4, 3] and w._is_initialized()
+        w.set(np.full((4, 3), 0.5, "float32"), paddle.CPUPlace())
+        sc.find_var(bname).get_tensor().set(np.array([1.0, 2.0, 3.0], "float32"), paddle.CPUPlace())
+        out = exe.run(main, feed={"x": np.ones((2, 4), "float32")}, fetch_list=[y])[0]
+        np.testing.assert_allclose(out, [[3.0, 4.0, 5.0]] * 2)
+        import pytest
+
+        with pytest.raises(ValueError):
+            w.set(np.zeros((2, 2), "float32"), paddle.CPUPlace())
+        assert sc.find_var("no_such_var") is None
+        with static.scope_guard(static.Scope()):
+            assert static.global_scope().find_var(wname) is None
+            v = static.global_scope().var("tmp")
+            v.get_tensor().set(np.arange(3, dtype="float32"), paddle.CPUPlace())
+            assert np.array(static.global_scope().find_var("tmp").get_tensor()).tolist() == [0.0, 1.0, 2.0]
+        kid = sc.new_scope()
+        assert kid.find_var(wname) is not None and kid.find_var("tmp") is None
+    finally:
+        paddle.disable_static()
