@@ -39,3 +39,11 @@ def get_all_op_names():
     from ..ops import schema
 
     return sorted(schema.build_registry())
+
+
+def __getattr__(name):
+    if name in ("Scope", "_Scope"):          # legacy spelling: paddle.base.core.Scope()
+        from ..static import Scope
+
+        return Scope
+    raise AttributeError(name)
