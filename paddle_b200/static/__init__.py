@@ -235,6 +235,70 @@ class Program:
     def num_blocks(self):
         return 1
 
+    # ---- introspection (reference: Program.global_block().ops, op.type / input_arg_names / output_arg_names, Program.to_string) ------------
+    @property
+    def idx(self):
+        return 0
+
+    @property
+    def blocks(self):
+        return [self]
+
+    def block(self, index=0):
+        return self
+
+    def _value_name(self, vid):
+        t = self._keep[vid] if 0 <= vid < len(self._keep) else None
+        return getattr(t, "name", None) or f"tmp_{vid}"
+
+    @property
+    def ops(self):
+        prog = self
+
+        class _OpView:
+            def __init__(self, idx, node):
+                self.idx, self._n = idx, node
+                fn = node.fn
+                self.type = {"train": "backward_and_update", "control": "control_flow"}.get(node.kind) or (getattr(fn, "__name__", None) or str(fn)).strip("_")
+
+            def _refs(self):
+                out = set()
+                _ValueGC._refs(self._n.args, out)
+                _ValueGC._refs(self._n.kwargs, out)
+                return sorted(out)
+
+            @property
+            def input_arg_names(self):
+                return [prog._value_name(v) for v in self._refs()]
+
+            @property
+            def output_arg_names(self):
+                return [prog._value_name(v) for v in self._n.outs]
+
+            def attr(self, name):
+                return self._n.kwargs.get(name)
+
+            def all_attrs(self):
+                return {k: v for k, v in self._n.kwargs.items() if not isinstance(v, (_Ref, torch.Tensor))}
+
+            def __repr__(self):
+                return f"{{Out={self.output_arg_names}}} = {self.type}(inputs={self.input_arg_names})"
+
+        return [_OpView(i, n) for i, n in enumerate(self.nodes)]
+
+    def to_string(self, throw_on_error=False, with_details=False):
+        lines = [f"{{ // block 0  ({len(self.nodes)} ops, feeds: {list(self.placeholders)})"]
+        for name, vid in self.placeholders.items():
+            t = self._keep[vid]
+            lines.append(f"    var {name} : shape{getattr(t, 'desc_shape', list(t.shape))} dtype({str(t.dtype).replace('torch.', '')})")
+        for p in self.all_parameters():
+            lines.append(f"    persist trainable param {p.name} : shape{list(p.shape)} dtype({str(p.dtype).replace('torch.', '')})")
+        lines += [f"    {op!r}" for op in self.ops]
+        return "\n".join(lines + ["}"])
+
+    def __str__(self):
+        return self.to_string()
+
     def __repr__(self):
         return f"Program(nodes={len(self.nodes)}, feeds={list(self.placeholders)})"
 
@@ -928,13 +992,44 @@ def load_from_file(path):
 
 def Print(input, first_n=-1, message=None, summarize=20, print_tensor_name=True, print_tensor_type=True, print_tensor_shape=True,
           print_tensor_layout=True, print_tensor_lod=True, print_phase="both"):
-    print(message or "", input)
-    return input
+    """Prints the tensor when the op RUNS (in a program: at every Executor.run, up to `first_n` times), not while the program is being built."""
+    from ..framework import recording
+
+    state = {"n": 0}
+
+    def _print_op(t):
+        if recording._inside[0] == 0 and (first_n < 0 or state["n"] < first_n):          # _inside > 0: the recorder is only taking the example output
+            state["n"] += 1
+            r = t.as_subclass(torch.Tensor) if isinstance(t, torch.Tensor) else t
+            head = [message or ""]
+            if print_tensor_shape and isinstance(r, torch.Tensor):
+                head.append(f"shape={list(r.shape)}")
+            if print_tensor_type and isinstance(r, torch.Tensor):
+                head.append(f"dtype={str(r.dtype).replace('torch.', '')}")
+            flat = r.detach().reshape(-1)[: max(int(summarize), 0) if summarize and summarize > 0 else None] if isinstance(r, torch.Tensor) else r
+            print(" ".join(h for h in head if h), "data:", flat.tolist() if isinstance(flat, torch.Tensor) else flat)
+        return t * 1 if isinstance(t, torch.Tensor) else t
+
+    _print_op.__name__ = "print"
+    return recording.recordable(_print_op)(input)
 
 
 def py_func(func, x, out, backward_func=None, skip_vars_in_backward_input=None):
-    res = func(*x) if isinstance(x, (list, tuple)) else func(x)
-    return res
+    """Runs `func` on the values of `x` when the op runs.  In a program the call is ONE recorded node (its example outputs come from calling `func`
+    once on the placeholders while building); the returned variables are the op's results (`out` only declares their types in the reference)."""
+    from ..framework import recording
+
+    xs = list(x) if isinstance(x, (list, tuple)) else [x]
+
+    def _py_func_op(*vals):
+        res = func(*[v.as_subclass(Tensor) if isinstance(v, torch.Tensor) and not isinstance(v, Tensor) else v for v in vals])
+        conv = lambda r: r if isinstance(r, torch.Tensor) else to_tensor(np.asarray(r))      # noqa: E731
+        if isinstance(res, (list, tuple)):
+            return type(res)(conv(r) for r in res)
+        return None if res is None else conv(res)
+
+    _py_func_op.__name__ = "py_func"
+    return recording.recordable(_py_func_op)(*xs)
 
 
 def accuracy(input, label, k=1, correct=None, total=None):
@@ -944,11 +1039,25 @@ def accuracy(input, label, k=1, correct=None, total=None):
 
 
 def auc(input, label, curve="ROC", num_thresholds=4095, topk=1, slide_steps=1, ins_tag_weight=None):
+    """Area under the curve, accumulated over the runs of the op (the statistics live with the op, like the reference's stat variables).
+    Returns (global auc, batch auc, [statistics])."""
+    from ..framework import recording
     from ..metric import Auc
 
-    m = Auc(curve, num_thresholds)
-    m.update(input, label)
-    return to_tensor(np.asarray(m.accumulate(), dtype=np.float32))
+    total = Auc(curve, num_thresholds)
+
+    def _auc_op(pred, lbl):
+        if recording._inside[0] > 0:                      # building: types only, the placeholders carry no data
+            z = to_tensor(np.asarray(0.0, dtype=np.float32))
+            return z, z * 1
+        batch = Auc(curve, num_thresholds)
+        batch.update(pred, lbl)
+        total.update(pred, lbl)
+        return to_tensor(np.asarray(total.accumulate(), dtype=np.float32)), to_tensor(np.asarray(batch.accumulate(), dtype=np.float32))
+
+    _auc_op.__name__ = "auc"
+    g, b = recording.recordable(_auc_op)(input, label)
+    return g, b, [total]
 
 
 def ctr_metric_bundle(input, label, ins_tag_weight=None):

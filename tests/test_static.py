@@ -453,3 +453,40 @@ def test_global_scope_reads_and_writes_parameters():
         assert kid.find_var(wname) is not None and kid.find_var("tmp") is None
     finally:
         paddle.disable_static()
+
+
+def test_print_py_func_auc_run_with_the_program_and_programs_can_be_inspected(capsys):
+    import numpy as np
+
+    import paddle_b200 as paddle
+    from paddle_b200 import static
+
+    paddle.enable_static()
+    try:
+        main, start = static.Program(), static.Program()
+        with static.program_guard(main, start):
+            x = static.data("x", [2, 4], "float32")
+            lbl = static.data("lbl", [2, 1], "int64")
+            h = static.nn.fc(x, 2)
+            p = static.Print(h, message="h at run", first_n=1)
+            q = static.py_func(lambda t: t.numpy().sum() * np.ones((2,), "float32"), [p], None)
+            a, ba, _ = static.auc(paddle.nn.functional.softmax(p), lbl)
+        assert "h at run" not in capsys.readouterr().out                       # nothing is printed while the program is built
+        assert [op.type for op in main.global_block().ops] == ["matmul", "add", "print", "py_func", "softmax", "auc"]
+        ops = main.global_block().ops
+        assert ops[0].input_arg_names == ["x"] and ops[1].output_arg_names == ops[2].input_arg_names
+        text = main.to_string()
+        assert "var x : shape[2, 4]" in text and "param fc_w_" in text and "py_func(" in text and str(main) == text
+        exe = static.Executor()
+        exe.run(start)
+        outs = []
+        for k in (1.0, 3.0):
+            outs.append(exe.run(main, feed={"x": np.ones((2, 4), "float32") * k, "lbl": np.array([[0], [1]])}, fetch_list=[q, h, a]))
+        printed = capsys.readouterr().out
+        assert printed.count("h at run") == 1 and "shape=[2, 2]" in printed   # first_n = 1
+        for q_, h_, a_ in outs:
+            np.testing.assert_allclose(q_, np.full((2,), h_.sum()), rtol=1e-6)  # py_func saw the run-time values
+            assert 0.0 <= float(a_) <= 1.0
+        assert not np.allclose(outs[0][0], outs[1][0])
+    finally:
+        paddle.disable_static()
