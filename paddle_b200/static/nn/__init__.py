@@ -174,9 +174,9 @@ def row_conv(input, future_context_size, param_attr=None, act=None):
     T_ = input.shape[1]
     out = 0
     for i in range(future_context_size + 1):
-        shifted = torch.nn.functional.pad(input.as_subclass(torch.Tensor)[:, i:], (0, 0, 0, i))
+        shifted = torch.nn.functional.pad(input[:, i:], (0, 0, 0, i))        # stays on the recorded tensor type: every step is an op of the program
         out = out + shifted * w[i]
-    return _act(out.as_subclass(Tensor), act)
+    return _act(out if isinstance(out, Tensor) else out.as_subclass(Tensor), act)
 
 
 # control flow (python-side at record time, matching dygraph semantics)
@@ -184,11 +184,42 @@ from .control_flow import case, cond, switch_case, while_loop  # noqa: F401,E402
 
 
 def static_pylayer(forward_fn, inputs, backward_fn=None, name=None):
-    return forward_fn(*inputs)
+    """`forward_fn(*inputs)` with a user-defined backward.  Without `backward_fn` the forward's ops are recorded as they are; with it the call is ONE
+    recorded node around an autograd function whose backward is `backward_fn(*output_grads) -> input_grads` (reference: static_pylayer.py)."""
+    if backward_fn is None:
+        return forward_fn(*inputs)
+    from ...framework import recording
+
+    class _Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, *xs):
+            with torch.no_grad():
+                out = forward_fn(*[x.as_subclass(Tensor) if isinstance(x, torch.Tensor) and not isinstance(x, Tensor) else x for x in xs])
+            outs = out if isinstance(out, (list, tuple)) else (out,)
+            ctx.single = not isinstance(out, (list, tuple))
+            res = tuple(o.as_subclass(torch.Tensor) * 1 for o in outs)
+            return res[0] if ctx.single else res
+
+        @staticmethod
+        def backward(ctx, *grads):
+            g = backward_fn(*[t.as_subclass(Tensor) for t in grads])
+            g = g if isinstance(g, (list, tuple)) else (g,)
+            return tuple(None if t is None else t.as_subclass(torch.Tensor) for t in g)
+
+    def _static_pylayer_op(*xs):
+        out = _Fn.apply(*[x.as_subclass(torch.Tensor) if isinstance(x, torch.Tensor) else x for x in xs])
+        if isinstance(out, tuple):
+            return tuple(o.as_subclass(Tensor) for o in out)
+        return out.as_subclass(Tensor)
+
+    _static_pylayer_op.__name__ = "static_pylayer"
+    return recording.recordable(_static_pylayer_op)(*inputs)
 
 
 def py_func(func, x, out, backward_func=None, skip_vars_in_backward_input=None):
-    return func(*x) if isinstance(x, (list, tuple)) else func(x)
+    from .. import py_func as _py_func            # one recorded node that calls `func` when the program runs
+
+    return _py_func(func, x, out, backward_func, skip_vars_in_backward_input)
 
 
 from .sequence import (sequence_concat, sequence_conv, sequence_enumerate, sequence_expand, sequence_expand_as, sequence_first_step,  # noqa: F401,E402

@@ -490,3 +490,31 @@ def test_print_py_func_auc_run_with_the_program_and_programs_can_be_inspected(ca
         assert not np.allclose(outs[0][0], outs[1][0])
     finally:
         paddle.disable_static()
+
+
+def test_static_pylayer_custom_backward_and_row_conv_are_recorded():
+    import numpy as np
+
+    import paddle_b200 as paddle
+    from paddle_b200 import static
+
+    paddle.enable_static()
+    try:
+        main, start = static.Program(), static.Program()
+        with static.program_guard(main, start):
+            x = static.data("x", [3, 4], "float32")
+            x.stop_gradient = False
+            y = static.nn.static_pylayer(lambda t: paddle.tanh(t), [x], backward_fn=lambda dy: dy * 5.0)       # deliberately "wrong" gradient
+            loss = y.sum()
+            (gx,) = static.gradients([loss], [x])
+            r = static.nn.row_conv(x.reshape([1, 3, 4]), 1)
+        exe = static.Executor()
+        exe.run(start)
+        for seed in (0, 1):
+            xv = np.random.RandomState(seed).randn(3, 4).astype("float32")
+            yv, gv, rv = exe.run(main, feed={"x": xv}, fetch_list=[y, gx, r])
+            np.testing.assert_allclose(yv, np.tanh(xv), rtol=1e-6)
+            np.testing.assert_allclose(gv, np.full((3, 4), 5.0), rtol=1e-6)      # the user's backward, not autograd's
+            assert rv.shape == (1, 3, 4) and np.abs(rv).sum() > 0
+    finally:
+        paddle.disable_static()
