@@ -1079,28 +1079,47 @@ class WeightNormParamAttr(ParamAttr):
 
 
 class ExponentialMovingAverage:
-    def __init__(self, decay=0.999, thres_steps=None, name=None):
-        self._decay, self._shadow, self._backup, self._params = decay, {}, {}, None
+    """EMA_t = decay * EMA_{t-1} + (1 - decay) * theta_t, EMA_0 = 0; `apply()` swaps in the bias-corrected EMA_t / (1 - decay^t).
+    In a program `update()` appends an op, so the averages move with EVERY Executor.run of the training program (call it after
+    `optimizer.minimize`); in dynamic mode every call is one update.  `thres_steps` (a step-count variable / number) caps the decay at
+    (1 + steps) / (10 + steps).  Parity: python/paddle/static/nn/... ExponentialMovingAverage."""
 
-    def update(self, parameters=None):
-        params = parameters or self._params or _main[0].all_parameters()
-        self._params = params
+    def __init__(self, decay=0.999, thres_steps=None, name=None):
+        self._decay, self._thres, self._shadow, self._backup, self._params = float(decay), thres_steps, {}, {}, None
+        self._step, self._decay_pow = 0, 1.0
+
+    def _one_update(self, env=None):
+        d = self._decay
+        if self._thres is not None:
+            t = self._thres
+            steps = float(t.as_subclass(torch.Tensor).reshape(-1)[0]) if isinstance(t, torch.Tensor) else float(t)
+            d = min(d, (1.0 + steps) / (10.0 + steps))
+        self._step += 1
+        self._decay_pow *= d
         with torch.no_grad():
-            for p in params:
+            for p in self._params:
                 s = self._shadow.get(p.name)
                 if s is None:
-                    self._shadow[p.name] = p.detach().clone()
-                else:
-                    s.mul_(self._decay).add_(p.detach(), alpha=1 - self._decay)
+                    s = self._shadow[p.name] = torch.zeros_like(p.detach().as_subclass(torch.Tensor), dtype=torch.float32)
+                s.mul_(d).add_(p.detach().as_subclass(torch.Tensor).float(), alpha=1.0 - d)
+
+    def update(self, parameters=None):
+        prog = _recording[0]
+        params = list(parameters) if parameters is not None else (self._params or (prog or _main[0]).all_parameters())
+        self._params = [p for p in params if not getattr(p, "stop_gradient", False)] or list(params)
+        if prog is not None:                               # building a program: the update is an op of it
+            prog.nodes.append(_Node(self._one_update, (), {}, [], kind="control"))
+        else:
+            self._one_update()
 
     @contextlib.contextmanager
     def apply(self, executor=None, need_restore=True):
-        params = self._params or []
+        corr = 1.0 - self._decay_pow
         with torch.no_grad():
-            for p in params:
+            for p in self._params or []:
                 self._backup[p.name] = p.detach().clone()
-                if p.name in self._shadow:
-                    p.copy_(self._shadow[p.name])
+                if p.name in self._shadow and corr > 0:
+                    p.as_subclass(torch.Tensor).copy_((self._shadow[p.name] / corr).to(p.dtype))
         try:
             yield
         finally:
@@ -1111,7 +1130,7 @@ class ExponentialMovingAverage:
         with torch.no_grad():
             for p in self._params or []:
                 if p.name in self._backup:
-                    p.copy_(self._backup[p.name])
+                    p.as_subclass(torch.Tensor).copy_(self._backup[p.name])
 
 
 class IpuStrategy:

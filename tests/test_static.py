@@ -518,3 +518,41 @@ def test_static_pylayer_custom_backward_and_row_conv_are_recorded():
             assert rv.shape == (1, 3, 4) and np.abs(rv).sum() > 0
     finally:
         paddle.disable_static()
+
+
+def test_exponential_moving_average_moves_with_every_run():
+    """ema.update() inside a program is an op: EMA_t = d * EMA_{t-1} + (1 - d) * theta_t per Executor.run; apply() swaps in EMA_t / (1 - d^t)."""
+    import numpy as np
+
+    import paddle_b200 as paddle
+    from paddle_b200 import static
+
+    paddle.enable_static()
+    try:
+        paddle.seed(0)
+        main, start = static.Program(), static.Program()
+        with static.program_guard(main, start):
+            x = static.data("x", [4, 3], "float32")
+            y = static.data("y", [4, 1], "float32")
+            loss = ((static.nn.fc(x, 1) - y) ** 2).mean()
+            paddle.optimizer.SGD(learning_rate=0.1).minimize(loss)
+            ema = static.ExponentialMovingAverage(0.5)
+            ema.update()
+        exe = static.Executor()
+        exe.run(start)
+        w = main.all_parameters()[0]
+        rng = np.random.RandomState(0)
+        feed = {"x": rng.randn(4, 3).astype("float32"), "y": rng.randn(4, 1).astype("float32")}
+        ref, hist = np.zeros(tuple(w.shape), np.float32), []
+        for t in range(1, 4):
+            exe.run(main, feed=feed, fetch_list=[loss])
+            cur = np.array(static.global_scope().find_var(w.name).get_tensor())
+            hist.append(cur.copy())
+            ref = 0.5 * ref + 0.5 * cur                       # the update runs after the optimizer step of the same run
+        assert not np.allclose(hist[0], hist[-1])
+        with ema.apply(exe):
+            inside = np.array(static.global_scope().find_var(w.name).get_tensor())
+            np.testing.assert_allclose(inside, ref / (1 - 0.5 ** 3), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(np.array(static.global_scope().find_var(w.name).get_tensor()), hist[-1])      # restored
+    finally:
+        paddle.disable_static()
