@@ -11,6 +11,7 @@ void bind(pybind11::module_& m) {
   bind_ir(m);
   bind_allocator(m);
   bind_custom_device(m);
+  bind_vision(m);
 }
 }  // namespace runtime
 }  // namespace b200

@@ -11,6 +11,7 @@ void bind_graph(pybind11::module_& m);
 void bind_tracer(pybind11::module_& m);
 void bind_data_feed(pybind11::module_& m);
 void bind_ir(pybind11::module_& m);
+void bind_vision(pybind11::module_& m);
 void bind_allocator(pybind11::module_& m);
 void bind_custom_device(pybind11::module_& m);
 }  // namespace runtime

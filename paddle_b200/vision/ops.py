@@ -31,9 +31,23 @@ def _iou(a, b):
 
 
 def _nms_single(boxes, scores, thr):
-    order = torch.argsort(scores, descending=True)
-    iou = _iou(boxes[order], boxes[order])
+    """Greedy NMS.  The serial part (does box i survive the survivors before it) runs in the native runtime (csrc/runtime/vision_ops.cpp): CUDA boxes
+    send ONE [n, n] suppression matrix to the host instead of synchronising per box; CPU boxes are scanned directly.  Python loop as the fall-back."""
+    order = torch.argsort(scores, descending=True, stable=True)
     n = order.numel()
+    if n == 0:
+        return order
+    from .._build import load
+
+    m = load()
+    sb = boxes[order].float()
+    if m is not None and hasattr(m, "nms_scan"):
+        if sb.is_cuda:
+            keep = m.nms_scan((_iou(sb, sb) > thr).triu_(1).to(torch.uint8).cpu())
+        else:
+            keep = m.nms_sorted_cpu(sb.contiguous(), float(thr))
+        return order[keep.to(order.device)]
+    iou = _iou(sb, sb)
     keep = torch.ones(n, dtype=torch.bool, device=boxes.device)
     for i in range(n):
         if keep[i]:
@@ -90,28 +104,58 @@ def _bilinear_zero(feat, y, x):
 
 
 def roi_align(x, boxes, boxes_num, output_size, spatial_scale=1.0, sampling_ratio=-1, aligned=True, name=None):
+    """RoIAlign without a python loop over the boxes: the boxes are grouped by their sampling grid (identical (sh, sw) -> one batched gather), the
+    four bilinear neighbours of every sample come from ONE index_select over the NHWC-flattened feature map per group (chunked to bound memory).
+    One host read (the box sizes decide the adaptive sampling grid), no per-box synchronisation."""
     x, boxes = _raw(x), _raw(boxes).float()
-    nums = _raw(boxes_num).tolist()
+    n_img, c, h, w = x.shape
     oh, ow = (output_size, output_size) if isinstance(output_size, int) else output_size
-    outs = []
-    bi = 0
+    k = boxes.shape[0]
+    if k == 0:
+        return _w(x.new_zeros((0, c, oh, ow)))
+    img_of = torch.repeat_interleave(torch.arange(n_img, device=x.device), _raw(boxes_num).to(x.device).long())
     off = 0.5 if aligned else 0.0
-    for img, n in enumerate(nums):
-        for k in range(n):
-            x1, y1, x2, y2 = (boxes[bi] * spatial_scale - off).tolist()
-            bi += 1
-            rw, rh = x2 - x1, y2 - y1
-            if not aligned:
-                rw, rh = max(rw, 1.0), max(rh, 1.0)
-            bh, bw = rh / oh, rw / ow
-            sh = sampling_ratio if sampling_ratio > 0 else max(1, int(math.ceil(rh / oh)))
-            sw = sampling_ratio if sampling_ratio > 0 else max(1, int(math.ceil(rw / ow)))
-            iy = (torch.arange(oh, device=x.device).float()[:, None] * bh + y1 + (torch.arange(sh, device=x.device).float()[None] + 0.5) * bh / sh).reshape(-1)
-            ix = (torch.arange(ow, device=x.device).float()[:, None] * bw + x1 + (torch.arange(sw, device=x.device).float()[None] + 0.5) * bw / sw).reshape(-1)
-            yy, xx = torch.meshgrid(iy, ix, indexing="ij")
-            v = _bilinear(x[img].float(), yy, xx).reshape(x.shape[1], oh, sh, ow, sw).mean((2, 4))
-            outs.append(v)
-    out = torch.stack(outs) if outs else x.new_zeros((0, x.shape[1], oh, ow))
+    b = boxes * spatial_scale - off
+    x1, y1 = b[:, 0], b[:, 1]
+    rw, rh = b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]
+    if not aligned:
+        rw, rh = rw.clamp(min=1.0), rh.clamp(min=1.0)
+    bw, bh = rw / ow, rh / oh
+    if sampling_ratio > 0:
+        sh_all = torch.full((k,), int(sampling_ratio), dtype=torch.int64)
+        sw_all = sh_all.clone()
+    else:
+        sh_all = torch.ceil(rh / oh).clamp(min=1).long().cpu()          # the one host read
+        sw_all = torch.ceil(rw / ow).clamp(min=1).long().cpu()
+    feat = x.float().permute(0, 2, 3, 1).reshape(n_img * h * w, c)       # NHWC rows
+    out = x.new_zeros((k, c, oh, ow), dtype=torch.float32)
+    key = sh_all * 100003 + sw_all
+    for kv in torch.unique(key).tolist():
+        idx = torch.nonzero(key == kv).reshape(-1).to(x.device)
+        sh, sw = int(kv // 100003), int(kv % 100003)
+        per_roi = oh * sh * ow * sw * c
+        step = max(1, (1 << 24) // max(per_roi, 1))                       # <= 16 M gathered elements per corner and chunk
+        for lo in range(0, idx.numel(), step):
+            g = idx[lo: lo + step]
+            gy = (torch.arange(oh, device=x.device).float()[None, :, None] * bh[g, None, None] + y1[g, None, None]
+                  + (torch.arange(sh, device=x.device).float()[None, None, :] + 0.5) * bh[g, None, None] / sh).reshape(g.numel(), oh * sh)
+            gx = (torch.arange(ow, device=x.device).float()[None, :, None] * bw[g, None, None] + x1[g, None, None]
+                  + (torch.arange(sw, device=x.device).float()[None, None, :] + 0.5) * bw[g, None, None] / sw).reshape(g.numel(), ow * sw)
+            yy = gy[:, :, None].expand(-1, -1, ow * sw)
+            xx = gx[:, None, :].expand(-1, oh * sh, -1)
+            valid = (yy >= -1.0) & (yy <= h) & (xx >= -1.0) & (xx <= w)     # samples outside the map contribute zero
+            yc, xc = yy.clamp(min=0), xx.clamp(min=0)
+            y0, x0 = yc.floor().clamp(max=h - 1), xc.floor().clamp(max=w - 1)
+            y1i, x1i = (y0 + 1).clamp(max=h - 1), (x0 + 1).clamp(max=w - 1)
+            yc = torch.where(y0 >= h - 1, y0, yc)
+            xc = torch.where(x0 >= w - 1, x0, xc)
+            ly, lx = yc - y0, xc - x0
+            base = (img_of[g] * (h * w))[:, None, None]
+            acc = 0
+            for yi, xi, wt in ((y0, x0, (1 - ly) * (1 - lx)), (y0, x1i, (1 - ly) * lx), (y1i, x0, ly * (1 - lx)), (y1i, x1i, ly * lx)):
+                rows = (base + yi.long() * w + xi.long()).reshape(-1)
+                acc = acc + feat.index_select(0, rows).reshape(g.numel(), oh * sh, ow * sw, c) * (wt * valid)[..., None]
+            out[g] = acc.reshape(g.numel(), oh, sh, ow, sw, c).mean((2, 4)).permute(0, 3, 1, 2)
     return _w(out.to(x.dtype))
 
 

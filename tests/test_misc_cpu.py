@@ -187,3 +187,88 @@ def test_inference_config_switches_hooks_and_memory_model(tmp_path):
     np.testing.assert_allclose(outs[0].numpy(), net(paddle.to_tensor(x)).numpy(), rtol=1e-5, atol=1e-6)
     pool = I.PredictorPool(cfg, 2)
     assert pool.retrieve(1) is not pool.retrieve(0)
+
+
+def test_detection_ops_vectorised_roi_align_and_native_nms():
+    """roi_align batches the boxes (no python loop per box) and nms runs its serial scan in the native runtime: both against plain references."""
+    import math
+
+    import numpy as np
+    import torch
+
+    import paddle_b200 as paddle
+    from paddle_b200.vision import ops
+
+    rng = np.random.RandomState(0)
+    feat = rng.randn(2, 5, 18, 22).astype("float32")
+    k = 30
+    xy = rng.rand(k, 2) * np.array([70, 60]) - 6
+    wh = rng.rand(k, 2) * np.array([40, 30]) + 1
+    boxes = np.concatenate([xy, xy + wh], 1).astype("float32")
+    nums = [18, 12]
+
+    def bilinear(f, y, x):
+        c, h, w = f.shape
+        if y < -1 or y > h or x < -1 or x > w:
+            return np.zeros(c, "float32")
+        y, x = min(max(y, 0), h - 1), min(max(x, 0), w - 1)
+        y0, x0 = int(math.floor(y)), int(math.floor(x))
+        y1, x1 = min(y0 + 1, h - 1), min(x0 + 1, w - 1)
+        ly, lx = y - y0, x - x0
+        return f[:, y0, x0] * (1 - ly) * (1 - lx) + f[:, y0, x1] * (1 - ly) * lx + f[:, y1, x0] * ly * (1 - lx) + f[:, y1, x1] * ly * lx
+
+    def reference(out_hw, scale, ratio, aligned):
+        oh, ow = out_hw
+        res, bi = [], 0
+        for img, n in enumerate(nums):
+            for _ in range(n):
+                x1, y1, x2, y2 = boxes[bi] * scale - (0.5 if aligned else 0.0)
+                bi += 1
+                rw, rh = x2 - x1, y2 - y1
+                if not aligned:
+                    rw, rh = max(rw, 1.0), max(rh, 1.0)
+                sh = ratio if ratio > 0 else max(1, math.ceil(rh / oh))
+                sw = ratio if ratio > 0 else max(1, math.ceil(rw / ow))
+                o = np.zeros((feat.shape[1], oh, ow), "float32")
+                for i in range(oh):
+                    for j in range(ow):
+                        acc = 0
+                        for a in range(sh):
+                            for b in range(sw):
+                                acc = acc + bilinear(feat[img], y1 + i * rh / oh + (a + 0.5) * rh / oh / sh, x1 + j * rw / ow + (b + 0.5) * rw / ow / sw)
+                        o[:, i, j] = acc / (sh * sw)
+                res.append(o)
+        return np.stack(res)
+
+    for out_hw, scale, ratio, aligned in (((3, 3), 0.25, -1, True), ((2, 4), 0.2, 2, False)):
+        got = ops.roi_align(paddle.to_tensor(feat), paddle.to_tensor(boxes), paddle.to_tensor(nums, dtype="int32"), out_hw, scale, ratio, aligned).numpy()
+        np.testing.assert_allclose(got, reference(out_hw, scale, ratio, aligned), rtol=1e-4, atol=1e-5)
+    assert ops.roi_align(paddle.to_tensor(feat), paddle.to_tensor(np.zeros((0, 4), "float32")), paddle.to_tensor([0, 0], dtype="int32"), 2).shape == [0, 5, 2, 2]
+
+    # greedy NMS against the textbook loop
+    n = 300
+    xy = rng.rand(n, 2) * 60
+    bx = np.concatenate([xy, xy + rng.rand(n, 2) * 25 + 2], 1).astype("float32")
+    sc = rng.rand(n).astype("float32")
+
+    def iou(a, b):
+        iw = max(min(a[2], b[2]) - max(a[0], b[0]), 0)
+        ih = max(min(a[3], b[3]) - max(a[1], b[1]), 0)
+        inter = iw * ih
+        return inter / max((a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter, 1e-10)
+
+    order, keep = np.argsort(-sc, kind="stable"), []
+    for i in order:
+        if all(iou(bx[i], bx[j]) <= 0.45 for j in keep):
+            keep.append(i)
+    got = ops.nms(paddle.to_tensor(bx), 0.45, paddle.to_tensor(sc)).numpy()
+    assert got.tolist() == keep
+    from paddle_b200._build import load
+
+    m = load()
+    if m is not None and hasattr(m, "nms_scan"):                       # the device path's scan over a suppression matrix
+        sb = torch.from_numpy(bx[order])
+        from paddle_b200.vision.ops import _iou
+
+        kept = m.nms_scan((_iou(sb, sb) > 0.45).triu_(1).to(torch.uint8))
+        assert order[kept.numpy()].tolist() == keep
