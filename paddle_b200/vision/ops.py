@@ -159,50 +159,74 @@ def roi_align(x, boxes, boxes_num, output_size, spatial_scale=1.0, sampling_rati
     return _w(out.to(x.dtype))
 
 
+def _roi_bins(lo, size, parts, limit, integer):
+    """Start / end (exclusive) of the `parts` bins that split [lo, lo + size) along one axis, clipped to [0, limit].  -> two [K, parts] int64 tensors."""
+    i = torch.arange(parts, device=lo.device, dtype=torch.float32)[None]
+    if integer:                                            # roi_pool: integer box, bins floor / ceil of i * size / parts
+        s = lo[:, None] + torch.floor(i * size[:, None] / parts)
+        e = lo[:, None] + torch.ceil((i + 1) * size[:, None] / parts)
+    else:                                                  # psroi_pool: real-valued box
+        s = torch.floor(lo[:, None] + i * size[:, None] / parts)
+        e = torch.ceil(lo[:, None] + (i + 1) * size[:, None] / parts)
+    return s.clamp(0, limit).long(), e.clamp(0, limit).long()
+
+
 def roi_pool(x, boxes, boxes_num, output_size, spatial_scale=1.0, name=None):
+    """Max over every bin of every box, batched: bins become row / column masks and the maximum is taken in two masked reductions (columns, then
+    rows) over chunks of boxes - no python loop over boxes or bins, no host read of the box coordinates."""
     x, boxes = _raw(x), _raw(boxes).float()
-    nums = _raw(boxes_num).tolist()
     oh, ow = (output_size, output_size) if isinstance(output_size, int) else output_size
-    H, W = x.shape[-2:]
-    outs, bi = [], 0
-    for img, n in enumerate(nums):
-        for k in range(n):
-            x1, y1, x2, y2 = [int(round(v * spatial_scale)) for v in boxes[bi].tolist()]
-            bi += 1
-            rh, rw = max(y2 - y1 + 1, 1), max(x2 - x1 + 1, 1)
-            o = x.new_zeros((x.shape[1], oh, ow))
-            for i in range(oh):
-                hs, he = min(max(y1 + int(math.floor(i * rh / oh)), 0), H), min(max(y1 + int(math.ceil((i + 1) * rh / oh)), 0), H)
-                for j in range(ow):
-                    ws, we = min(max(x1 + int(math.floor(j * rw / ow)), 0), W), min(max(x1 + int(math.ceil((j + 1) * rw / ow)), 0), W)
-                    if he > hs and we > ws:
-                        o[:, i, j] = x[img, :, hs:he, ws:we].amax((-2, -1))
-            outs.append(o)
-    return _w(torch.stack(outs) if outs else x.new_zeros((0, x.shape[1], oh, ow)))
+    n_img, c, H, W = x.shape
+    k = boxes.shape[0]
+    if k == 0:
+        return _w(x.new_zeros((0, c, oh, ow)))
+    img_of = torch.repeat_interleave(torch.arange(n_img, device=x.device), _raw(boxes_num).to(x.device).long())
+    r = torch.round(boxes * spatial_scale)
+    x1, y1, x2, y2 = r[:, 0], r[:, 1], r[:, 2], r[:, 3]
+    rh, rw = (y2 - y1 + 1).clamp(min=1), (x2 - x1 + 1).clamp(min=1)
+    hs, he = _roi_bins(y1, rh, oh, H, True)
+    ws, we = _roi_bins(x1, rw, ow, W, True)
+    ys, xs = torch.arange(H, device=x.device)[None, None], torch.arange(W, device=x.device)[None, None]
+    out = x.new_zeros((k, c, oh, ow))
+    neg = torch.finfo(x.dtype).min if x.dtype.is_floating_point else torch.iinfo(x.dtype).min
+    step = max(1, (1 << 25) // max(c * H * W * max(ow, 1), 1))
+    for lo in range(0, k, step):
+        sl = slice(lo, min(k, lo + step))
+        f = x[img_of[sl]]                                                        # [g, C, H, W]
+        mw = (xs >= ws[sl, :, None]) & (xs < we[sl, :, None])                    # [g, ow, W]
+        t = f[:, :, :, None, :].masked_fill(~mw[:, None, None], neg).amax(-1)    # [g, C, H, ow]
+        mh = (ys >= hs[sl, :, None]) & (ys < he[sl, :, None])                    # [g, oh, H]
+        v = t[:, :, None].masked_fill(~mh[:, None, :, :, None], neg).amax(3)     # [g, C, oh, ow]
+        empty = ((he[sl] <= hs[sl])[:, :, None] | (we[sl] <= ws[sl])[:, None, :])[:, None]
+        out[sl] = v.masked_fill(empty, 0)
+    return _w(out)
 
 
 def psroi_pool(x, boxes, boxes_num, output_size, spatial_scale=1.0, name=None):
+    """Position-sensitive average pooling through a summed-area table: every bin is four gathers, whatever its size."""
     x, boxes = _raw(x), _raw(boxes).float()
-    nums = _raw(boxes_num).tolist()
     oh, ow = (output_size, output_size) if isinstance(output_size, int) else output_size
-    C = x.shape[1] // (oh * ow)
-    H, W = x.shape[-2:]
-    outs, bi = [], 0
-    for img, n in enumerate(nums):
-        for k in range(n):
-            x1, y1, x2, y2 = (boxes[bi] * spatial_scale).tolist()
-            bi += 1
-            rh, rw = max(y2 - y1, 0.1), max(x2 - x1, 0.1)
-            o = x.new_zeros((C, oh, ow))
-            for i in range(oh):
-                hs, he = min(max(int(math.floor(y1 + i * rh / oh)), 0), H), min(max(int(math.ceil(y1 + (i + 1) * rh / oh)), 0), H)
-                for j in range(ow):
-                    ws, we = min(max(int(math.floor(x1 + j * rw / ow)), 0), W), min(max(int(math.ceil(x1 + (j + 1) * rw / ow)), 0), W)
-                    if he > hs and we > ws:
-                        ch = torch.arange(C, device=x.device) * oh * ow + i * ow + j
-                        o[:, i, j] = x[img, ch, hs:he, ws:we].mean((-2, -1))
-            outs.append(o)
-    return _w(torch.stack(outs) if outs else x.new_zeros((0, C, oh, ow)))
+    n_img, ctot, H, W = x.shape
+    C = ctot // (oh * ow)
+    k = boxes.shape[0]
+    if k == 0:
+        return _w(x.new_zeros((0, C, oh, ow)))
+    img_of = torch.repeat_interleave(torch.arange(n_img, device=x.device), _raw(boxes_num).to(x.device).long())
+    b = boxes * spatial_scale
+    rh, rw = (b[:, 3] - b[:, 1]).clamp(min=0.1), (b[:, 2] - b[:, 0]).clamp(min=0.1)
+    hs, he = _roi_bins(b[:, 1], rh, oh, H, False)
+    ws, we = _roi_bins(b[:, 0], rw, ow, W, False)
+    sat = torch.nn.functional.pad(x.double().cumsum(-1).cumsum(-2), (1, 0, 1, 0))           # [N, Ctot, H+1, W+1]
+    ch = (torch.arange(C, device=x.device)[:, None, None] * (oh * ow) + torch.arange(oh, device=x.device)[None, :, None] * ow
+          + torch.arange(ow, device=x.device)[None, None, :])                                   # [C, oh, ow] -> input channel of every output bin
+    n_i = img_of[:, None, None, None].expand(k, C, oh, ow)
+    c_i = ch[None].expand(k, C, oh, ow)
+    h0, h1 = hs[:, None, :, None].expand(k, C, oh, ow), he[:, None, :, None].expand(k, C, oh, ow)
+    w0, w1 = ws[:, None, None, :].expand(k, C, oh, ow), we[:, None, None, :].expand(k, C, oh, ow)
+    total = sat[n_i, c_i, h1, w1] - sat[n_i, c_i, h0, w1] - sat[n_i, c_i, h1, w0] + sat[n_i, c_i, h0, w0]
+    area = ((h1 - h0) * (w1 - w0)).clamp(min=0)
+    out = torch.where(area > 0, total / area.clamp(min=1), torch.zeros_like(total))
+    return _w(out.to(x.dtype))
 
 
 def deform_conv2d(x, offset, weight, bias=None, stride=1, padding=0, dilation=1, deformable_groups=1, groups=1, mask=None, name=None):
@@ -318,31 +342,27 @@ def prior_box(input, image, min_sizes, max_sizes=None, aspect_ratios=(1.0,), var
             ars.append(a)
             if flip:
                 ars.append(1.0 / a)
-    boxes = []
-    for i in range(fh):
-        for j in range(fw):
-            cx, cy = (j + offset) * sw, (i + offset) * sh
-            cell = []
-            for k, ms in enumerate(min_sizes):
-                def add(w, h):
-                    cell.append([(cx - w / 2) / iw, (cy - h / 2) / ih, (cx + w / 2) / iw, (cy + h / 2) / ih])
-
-                if min_max_aspect_ratios_order:
-                    add(ms, ms)
-                    if max_sizes:
-                        s = math.sqrt(ms * max_sizes[k])
-                        add(s, s)
-                    for a in ars:
-                        if abs(a - 1.0) > 1e-6:
-                            add(ms * math.sqrt(a), ms / math.sqrt(a))
-                else:
-                    for a in ars:
-                        add(ms * math.sqrt(a), ms / math.sqrt(a))
-                    if max_sizes:
-                        s = math.sqrt(ms * max_sizes[k])
-                        add(s, s)
-            boxes.append(cell)
-    b = torch.tensor(boxes, dtype=torch.float32).reshape(fh, fw, -1, 4)
+    # the (w, h) of the priors of ONE cell, in the reference's order; the grid of centres is added by broadcasting (no loop over cells)
+    whs = []
+    for k, ms in enumerate(min_sizes):
+        if min_max_aspect_ratios_order:
+            whs.append((ms, ms))
+            if max_sizes:
+                s_ = math.sqrt(ms * max_sizes[k])
+                whs.append((s_, s_))
+            whs += [(ms * math.sqrt(a), ms / math.sqrt(a)) for a in ars if abs(a - 1.0) > 1e-6]
+        else:
+            whs += [(ms * math.sqrt(a), ms / math.sqrt(a)) for a in ars]
+            if max_sizes:
+                s_ = math.sqrt(ms * max_sizes[k])
+                whs.append((s_, s_))
+    wh = torch.tensor(whs, dtype=torch.float64)                                        # [P, 2]
+    cx = ((torch.arange(fw, dtype=torch.float64) + offset) * sw)[None, :, None]        # [1, fw, 1]
+    cy = ((torch.arange(fh, dtype=torch.float64) + offset) * sh)[:, None, None]        # [fh, 1, 1]
+    half_w, half_h = wh[:, 0] / 2, wh[:, 1] / 2
+    boxes = torch.stack([((cx - half_w) / iw).expand(fh, fw, -1), ((cy - half_h) / ih).expand(fh, fw, -1),
+                         ((cx + half_w) / iw).expand(fh, fw, -1), ((cy + half_h) / ih).expand(fh, fw, -1)], -1)
+    b = boxes.to(torch.float32).reshape(fh, fw, -1, 4)
     if clip:
         b = b.clamp(0, 1)
     v = torch.tensor(variance, dtype=torch.float32).expand_as(b).clone()

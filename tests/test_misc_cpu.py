@@ -272,3 +272,49 @@ def test_detection_ops_vectorised_roi_align_and_native_nms():
 
         kept = m.nms_scan((_iou(sb, sb) > 0.45).triu_(1).to(torch.uint8))
         assert order[kept.numpy()].tolist() == keep
+
+
+def test_roi_pool_and_psroi_pool_batched_match_the_bin_loops():
+    import math
+
+    import numpy as np
+
+    import paddle_b200 as paddle
+    from paddle_b200.vision import ops
+
+    rng = np.random.RandomState(1)
+    k = 24
+    xy = rng.rand(k, 2) * np.array([60, 50]) - 4
+    boxes = np.concatenate([xy, xy + rng.rand(k, 2) * np.array([50, 40]) + 0.5], 1).astype("float32")
+    nums = [14, 10]
+    img_of = [0] * 14 + [1] * 10
+    x = rng.randn(2, 4, 20, 24).astype("float32")
+    H, W = 20, 24
+    for scale, (oh, ow) in ((0.25, (3, 3)), (1.0, (2, 4))):
+        ref = np.zeros((k, 4, oh, ow), "float32")
+        for b in range(k):
+            x1, y1, x2, y2 = [int(round(float(v) * scale)) for v in boxes[b]]
+            rh, rw = max(y2 - y1 + 1, 1), max(x2 - x1 + 1, 1)
+            for i in range(oh):
+                hs, he = min(max(y1 + math.floor(i * rh / oh), 0), H), min(max(y1 + math.ceil((i + 1) * rh / oh), 0), H)
+                for j in range(ow):
+                    ws, we = min(max(x1 + math.floor(j * rw / ow), 0), W), min(max(x1 + math.ceil((j + 1) * rw / ow), 0), W)
+                    if he > hs and we > ws:
+                        ref[b, :, i, j] = x[img_of[b], :, hs:he, ws:we].max((-2, -1))
+        got = ops.roi_pool(paddle.to_tensor(x), paddle.to_tensor(boxes), paddle.to_tensor(nums, dtype="int32"), (oh, ow), scale).numpy()
+        np.testing.assert_allclose(got, ref, rtol=0, atol=0)
+    oh = ow = 3
+    xp = rng.randn(2, 2 * oh * ow, H, W).astype("float32")
+    ref = np.zeros((k, 2, oh, ow), "float32")
+    for b in range(k):
+        x1, y1, x2, y2 = [float(v) * 0.5 for v in boxes[b]]
+        rh, rw = max(y2 - y1, 0.1), max(x2 - x1, 0.1)
+        for i in range(oh):
+            hs, he = min(max(math.floor(y1 + i * rh / oh), 0), H), min(max(math.ceil(y1 + (i + 1) * rh / oh), 0), H)
+            for j in range(ow):
+                ws, we = min(max(math.floor(x1 + j * rw / ow), 0), W), min(max(math.ceil(x1 + (j + 1) * rw / ow), 0), W)
+                if he > hs and we > ws:
+                    for c in range(2):
+                        ref[b, c, i, j] = xp[img_of[b], c * oh * ow + i * ow + j, hs:he, ws:we].mean()
+    got = ops.psroi_pool(paddle.to_tensor(xp), paddle.to_tensor(boxes), paddle.to_tensor(nums, dtype="int32"), 3, 0.5).numpy()
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)
