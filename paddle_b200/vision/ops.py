@@ -241,21 +241,28 @@ def deform_conv2d(x, offset, weight, bias=None, stride=1, padding=0, dilation=1,
     Wo = (W + 2 * p[1] - d[1] * (kw - 1) - 1) // s[1] + 1
     base_y = (torch.arange(Ho, device=x.device) * s[0] - p[0]).float()[:, None]
     base_x = (torch.arange(Wo, device=x.device) * s[1] - p[1]).float()[None, :]
-    cols = x.new_zeros((N, C, kh * kw, Ho, Wo), dtype=torch.float32)
     cpg = C // deformable_groups
-    off = offset.float().reshape(N, deformable_groups, kh * kw, 2, Ho, Wo)
-    m = None if mask is None else _raw(mask).float().reshape(N, deformable_groups, kh * kw, Ho, Wo)
-    for n in range(N):
-        for g in range(deformable_groups):
-            feat = x[n, g * cpg:(g + 1) * cpg].float()
-            for k in range(kh * kw):
-                ky, kx = divmod(k, kw)
-                yy = base_y + ky * d[0] + off[n, g, k, 0]
-                xx = base_x + kx * d[1] + off[n, g, k, 1]
-                v = _bilinear_zero(feat, yy, xx)
-                if m is not None:
-                    v = v * m[n, g, k]
-                cols[n, g * cpg:(g + 1) * cpg, k] = v
+    K = kh * kw
+    off = offset.float().reshape(N, deformable_groups, K, 2, Ho, Wo)
+    ky = (torch.arange(K, device=x.device) // kw).float()[:, None, None] * d[0]
+    kx = (torch.arange(K, device=x.device) % kw).float()[:, None, None] * d[1]
+    yy = base_y[None] + ky + off[:, :, :, 0]                                  # [N, G, K, Ho, Wo]: every sampling position at once
+    xx = base_x[None] + kx + off[:, :, :, 1]
+    y0, x0 = yy.floor(), xx.floor()
+    ly, lx = yy - y0, xx - x0
+    feat = x.float().reshape(N * deformable_groups, cpg, H * W)
+    cols = 0
+    for dy, wy in ((0, 1 - ly), (1, ly)):                                        # four bilinear corners, each ONE gather; out-of-range corners add 0
+        for dx, wx in ((0, 1 - lx), (1, lx)):
+            yi, xi = (y0 + dy).long(), (x0 + dx).long()
+            ok = (yi >= 0) & (yi < H) & (xi >= 0) & (xi < W)
+            idx = (yi.clamp(0, H - 1) * W + xi.clamp(0, W - 1)).reshape(N * deformable_groups, 1, K * Ho * Wo).expand(-1, cpg, -1)
+            wgt = (wy * wx * ok).reshape(N * deformable_groups, 1, K * Ho * Wo)
+            cols = cols + feat.gather(2, idx) * wgt
+    cols = cols.reshape(N, deformable_groups, cpg, K, Ho, Wo)
+    if mask is not None:
+        cols = cols * _raw(mask).float().reshape(N, deformable_groups, 1, K, Ho, Wo)
+    cols = cols.reshape(N, C, K, Ho, Wo)
     cols = cols.reshape(N, groups, (C // groups) * kh * kw, Ho * Wo)
     wg = weight.float().reshape(groups, Co // groups, Cg * kh * kw)
     out = torch.einsum("gok,ngkl->ngol", wg, cols).reshape(N, Co, Ho, Wo)

@@ -318,3 +318,48 @@ def test_roi_pool_and_psroi_pool_batched_match_the_bin_loops():
                         ref[b, c, i, j] = xp[img_of[b], c * oh * ow + i * ow + j, hs:he, ws:we].mean()
     got = ops.psroi_pool(paddle.to_tensor(xp), paddle.to_tensor(boxes), paddle.to_tensor(nums, dtype="int32"), 3, 0.5).numpy()
     np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_deform_conv2d_batched_sampling_matches_a_plain_loop():
+    """All sampling positions of all images / groups / taps are gathered at once; checked against a per-output-pixel loop (v2: with mask)."""
+    import math
+
+    import numpy as np
+
+    import paddle_b200 as paddle
+    from paddle_b200.vision import ops
+
+    rng = np.random.RandomState(0)
+    N, C, H, W, Co, k, st, pd, dl, dg = 1, 4, 6, 7, 3, 3, 2, 1, 1, 2
+    x = rng.randn(N, C, H, W).astype("float32")
+    w = rng.randn(Co, C, k, k).astype("float32")
+    Ho, Wo = (H + 2 * pd - dl * (k - 1) - 1) // st + 1, (W + 2 * pd - dl * (k - 1) - 1) // st + 1
+    off = (rng.randn(N, 2 * dg * k * k, Ho, Wo) * 1.2).astype("float32")
+    m = rng.rand(N, dg * k * k, Ho, Wo).astype("float32")
+
+    def sample(f, y, xq):
+        y0, x0 = math.floor(y), math.floor(xq)
+        v = 0.0
+        for dy in (0, 1):
+            for dx in (0, 1):
+                yi, xi = y0 + dy, x0 + dx
+                if 0 <= yi < H and 0 <= xi < W:
+                    v += f[yi, xi] * (1 - abs(y - yi)) * (1 - abs(xq - xi))
+        return v
+
+    ref = np.zeros((N, Co, Ho, Wo), "float32")
+    cpg = C // dg
+    for o in range(Co):
+        for i in range(Ho):
+            for j in range(Wo):
+                acc = 0.0
+                for c in range(C):
+                    g = c // cpg
+                    for t in range(k * k):
+                        ky, kx = divmod(t, k)
+                        y = i * st - pd + ky * dl + off[0, (g * k * k + t) * 2, i, j]
+                        xq = j * st - pd + kx * dl + off[0, (g * k * k + t) * 2 + 1, i, j]
+                        acc += w[o, c, ky, kx] * sample(x[0, c], y, xq) * m[0, g * k * k + t, i, j]
+                ref[0, o, i, j] = acc
+    got = ops.deform_conv2d(paddle.to_tensor(x), paddle.to_tensor(off), paddle.to_tensor(w), None, st, pd, dl, dg, 1, paddle.to_tensor(m)).numpy()
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4)
