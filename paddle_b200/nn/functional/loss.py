@@ -250,18 +250,20 @@ def hsigmoid_loss(input, label, num_classes, weight, bias=None, path_table=None,
             logits = logits + T(bias).reshape(-1)[table.clamp(min=0)]
         loss = F.binary_cross_entropy_with_logits(logits, code, reduction="none") * valid
         return loss.sum(1, keepdim=True)
-    depth = max(1, (num_classes - 1).bit_length())
-    losses = []
-    for b in range(x.size(0)):
-        c = int(label[b]) + num_classes
-        total = x.new_zeros(())
-        while c > 1:
-            node, bit = c // 2 - 1, c % 2
-            logit = (x[b] * w[node]).sum() + (T(bias).reshape(-1)[node] if bias is not None else 0)
-            total = total + F.binary_cross_entropy_with_logits(logit, logit.new_tensor(float(bit)))
-            c //= 2
-        losses.append(total)
-    return torch.stack(losses).reshape(-1, 1)
+    # default tree: class c is leaf (c + num_classes) of the complete binary tree; its path is c >> 1, c >> 2, ... down to the root, the code bits
+    # are the low bits on the way - built for the whole batch at once
+    depth = max(1, (2 * num_classes - 1).bit_length())
+    c = (label.reshape(-1).long() + num_classes)[:, None]
+    d = torch.arange(depth, device=x.device)[None]
+    cur = c >> d                                           # node code at every level, leaf first
+    valid = (cur > 1).to(x.dtype)
+    table = ((cur >> 1) - 1).clamp(min=0)
+    code = (cur & 1).to(x.dtype)
+    logits = torch.einsum("bd,bld->bl", x, w[table])
+    if bias is not None:
+        logits = logits + T(bias).reshape(-1)[table]
+    loss = F.binary_cross_entropy_with_logits(logits, code, reduction="none") * valid
+    return loss.sum(1, keepdim=True)
 
 
 def adaptive_log_softmax_with_loss(input, label, head_weight, tail_weights, cutoffs, head_bias=None, name=None):
