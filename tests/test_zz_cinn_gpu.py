@@ -145,3 +145,34 @@ def test_column_reduction_schedule(shape):
     assert any(g["kind"] == "column" for g in rep.groups)
     assert torch.allclose(s, (dy * torch.tanh(x)).sum(lead), rtol=1e-4, atol=1e-3)
     assert torch.allclose(m, (dy * x).mean(lead[-1]), rtol=1e-4, atol=1e-5)
+
+
+def test_batched_detection_ops_on_device():
+    """vision.ops after their rewrite as batched tensor programs: device results equal the CPU results (no per-box host synchronisation inside)."""
+    import numpy as np
+
+    from paddle_b200.vision import ops
+
+    rng = np.random.RandomState(0)
+    feat = rng.randn(2, 8, 24, 30).astype("float32")
+    k = 64
+    xy = rng.rand(k, 2) * np.array([100, 80]) - 5
+    boxes = np.concatenate([xy, xy + rng.rand(k, 2) * np.array([60, 50]) + 1], 1).astype("float32")
+    nums = np.array([40, 24], "int32")
+    sc = rng.rand(k).astype("float32")
+
+    def run(dev):
+        t = lambda a: paddle.to_tensor(a).to(dev)       # noqa: E731
+        ra = ops.roi_align(t(feat), t(boxes), t(nums), 7, 0.25)
+        rp = ops.roi_pool(t(feat), t(boxes), t(nums), 3, 0.25)
+        keep = ops.nms(t(boxes), 0.4, t(sc))
+        off = (rng.randn(2, 18, 24, 30) * 0.7).astype("float32")
+        dc = ops.deform_conv2d(t(feat), t(off), t(rng.randn(4, 8, 3, 3).astype("float32")), None, 1, 1)
+        return [v.cpu().numpy() for v in (ra, rp, keep, dc)]
+
+    rng_state = rng.get_state()
+    cpu = run("cpu")
+    rng.set_state(rng_state)
+    gpu = run("gpu:0")
+    for a, b in zip(cpu, gpu):
+        np.testing.assert_allclose(b, a, rtol=1e-4, atol=1e-4)
