@@ -93,6 +93,8 @@ class DataLoader:
                  drop_last=False, collate_fn=None, num_workers=0, use_buffer_reader=True, prefetch_factor=2, use_shared_memory=True,
                  timeout=0, worker_init_fn=None, persistent_workers=False, pin_memory=None, device_prefetch=None):
         self.dataset, self.return_list = dataset, return_list
+        # static-graph feeding: with return_list=False every batch is a {variable name: tensor} dict for Executor.run(feed=...)
+        self._feed_names = [getattr(v, "name", None) or f"feed_{i}" for i, v in enumerate(feed_list)] if feed_list else None
         self.collate_fn, self.num_workers = collate_fn, int(num_workers)
         self.prefetch_factor, self.timeout, self.worker_init_fn = max(1, prefetch_factor), timeout, worker_init_fn
         self.use_buffer_reader = use_buffer_reader
@@ -242,6 +244,16 @@ class DataLoader:
         return mv(batch)
 
     def __iter__(self):
+        if not self.return_list and self._feed_names:
+            for batch in self._iter_batches():
+                items = list(batch) if isinstance(batch, (list, tuple)) else [batch]
+                if len(items) != len(self._feed_names):
+                    raise ValueError(f"DataLoader(feed_list=...): the dataset yields {len(items)} fields, feed_list names {len(self._feed_names)}")
+                yield dict(zip(self._feed_names, items))
+            return
+        yield from self._iter_batches()
+
+    def _iter_batches(self):
         nslots = self.prefetch_factor + 2
         if self._device is None or not self.use_buffer_reader:
             for i, samples in enumerate(self._sample_batches()):

@@ -39,7 +39,7 @@ def cross_entropy(input, label, weight=None, ignore_index=-100, reduction="mean"
     if use_softmax and x.is_cuda and weight is None and label_smoothing == 0.0:
         from ...kernels import loss as K
 
-        per = K.softmax_cross_entropy(x.reshape(-1, x.size(-1)), label.reshape(-1), ignore_index).reshape(label.size())
+        per = K.softmax_cross_entropy(x.reshape(-1, x.size(-1)), label.reshape(-1), ignore_index).reshape_as(label)     # reshape_as: no extents baked into a recorded program
         if reduction == "none":
             return per
         if reduction == "sum":
@@ -53,7 +53,7 @@ def cross_entropy(input, label, weight=None, ignore_index=-100, reduction="mean"
                                reduction="none", label_smoothing=label_smoothing)
     else:
         loss = F.nll_loss(torch.log(lead.float()), lab, None if weight is None else T(weight).float(), ignore_index=ignore_index, reduction="none")
-    loss = loss.reshape(label.size())
+    loss = loss.reshape_as(label)          # by reference to the label: a recorded program keeps working when the batch extent is dynamic
     if reduction == "none":
         return loss.to(x.dtype)
     if reduction == "sum":

@@ -486,6 +486,8 @@ class Executor:
         from ..framework.flags import flag
 
         feed = feed or {}
+        if isinstance(feed, (list, tuple)):                          # one dict per place (DataLoader(return_list=False) on several places): this process runs the first
+            feed = feed[0] if feed else {}
         on_run = program.__dict__.get("_cinn_on_run")                 # set by inference.Config.enable_cinn(): specialise per feed signature
         if program.nodes and (on_run or (flag("FLAGS_enable_pir_api", False) and not program.__dict__.get("_pir_report"))):
             if on_run or flag("FLAGS_use_cinn", False):
@@ -525,7 +527,15 @@ class Executor:
             if n.kind in ("train", "control"):      # backward + update / run-time control flow: the node works on the value table
                 n.fn(env)
                 return
-            out = n.fn(*decode(n.args), **decode(n.kwargs))
+            try:
+                out = n.fn(*decode(n.args), **decode(n.kwargs))
+            except RuntimeError as e:
+                if "shape" in str(e) and any(-1 in getattr(program._keep[v], "desc_shape", []) for v in program.placeholders.values()):
+                    name = (getattr(n.fn, "__name__", None) or str(n.fn)).strip("_")
+                    raise RuntimeError(f"op '{name}' of the program failed on this feed: {e}.  The program declares dynamic dims (-1); it was recorded with extent 1 "
+                                       "for them, and python code that read a tensor's size while the program was built froze that 1 into an argument.  Use "
+                                       "reshape([-1, ...]) / reshape_as / paddle.shape(x) for run-time extents, or declare the dims with their real sizes.") from e
+                raise
             flat = []
 
             def fl(o):

@@ -556,3 +556,50 @@ def test_exponential_moving_average_moves_with_every_run():
         np.testing.assert_allclose(np.array(static.global_scope().find_var(w.name).get_tensor()), hist[-1])      # restored
     finally:
         paddle.disable_static()
+
+
+def test_dataloader_feed_dicts_dynamic_batch_training_and_the_baked_extent_hint():
+    """DataLoader(feed_list=..., return_list=False) yields {name: tensor} feeds; cross_entropy with [-1, 1] labels trains at any batch size (its
+    reshape goes by reference to the label); an extent frozen by python code fails with an explanation."""
+    import numpy as np
+    import pytest
+
+    import paddle_b200 as paddle
+    from paddle_b200 import static
+
+    class DS(paddle.io.Dataset):
+        def __len__(self):
+            return 18
+
+        def __getitem__(self, i):
+            return np.random.RandomState(i).randn(4).astype("float32"), np.array([i % 3], "int64")
+
+    paddle.enable_static()
+    try:
+        paddle.seed(0)
+        main, start = static.Program(), static.Program()
+        with static.program_guard(main, start):
+            x = static.data("x", [-1, 4], "float32")
+            y = static.data("y", [-1, 1], "int64")
+            loss = paddle.nn.functional.cross_entropy(static.nn.fc(x, 3), y)
+            paddle.optimizer.SGD(0.2).minimize(loss)
+        loader = paddle.io.DataLoader(DS(), feed_list=[x, y], places=paddle.CPUPlace(), batch_size=4, return_list=False)     # last batch has 2 samples
+        exe = static.Executor()
+        exe.run(start)
+        ls = []
+        for _ in range(4):
+            for feed in loader:
+                assert sorted(feed) == ["x", "y"]
+                ls.append(float(exe.run(main, feed=feed, fetch_list=[loss])[0]))
+        assert np.mean(ls[-5:]) < np.mean(ls[:5])
+        assert np.isfinite(float(exe.run(main, feed=[feed], fetch_list=[loss])[0]))      # a list of per-place dicts is accepted too
+
+        frozen = static.Program()
+        with static.program_guard(frozen):
+            z = static.data("z", [-1, 4], "float32")
+            flat = paddle.reshape(z, [z.size(0) * 4])            # reads the placeholder's extent (1) while building
+        assert exe.run(frozen, feed={"z": np.zeros((1, 4), "float32")}, fetch_list=[flat])[0].shape == (4,)
+        with pytest.raises(RuntimeError, match="dynamic dims"):
+            exe.run(frozen, feed={"z": np.zeros((3, 4), "float32")}, fetch_list=[flat])
+    finally:
+        paddle.disable_static()
