@@ -11,6 +11,7 @@ from ...ops._helpers import T, raw, shp, to_int, wrap
 
 
 from ...framework.recording import recordable as _recordable  # noqa: E402
+from ...framework.recording import recordable as _recordable  # noqa: E402  (bodies that compute on raw tensors are recorded as ONE op in static programs)
 
 def linear(x, weight, bias=None, name=None):
     """y = x @ W + b with W laid out [in, out]. Parity: nn/functional/common.py:linear.
@@ -147,6 +148,7 @@ def _size_arg(v):
     return int(v)
 
 
+@_recordable
 def interpolate(x, size=None, scale_factor=None, mode="nearest", align_corners=False, align_mode=0,
                 data_format="NCHW", recompute_scale_factor=None, name=None):
     x = T(x)

@@ -258,3 +258,9 @@ def fp8_fp8_half_gemm_fused(x, y, transpose_x=False, transpose_y=False, bias=Non
 
 
 __all__ = [n for n in list(globals()) if not n.startswith("_") and n not in ("torch", "T", "ax", "dt", "raw", "to_int", "wrap", "annotations")]
+
+
+# static programs record these as single ops (their bodies compute on raw tensors / read values; framework/recording.py)
+from ..framework.recording import make_recordable as _make_recordable  # noqa: E402
+
+_make_recordable(globals(), ['histogramdd', 'lstsq', 'pca_lowrank', 'svd_lowrank'])

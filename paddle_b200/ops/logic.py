@@ -99,3 +99,9 @@ for _n in ["equal", "not_equal", "greater_than", "greater_equal", "less_than", "
     globals()[_n + "_"] = _mk_inplace(globals()[_n])
 
 __all__ = [n for n in list(globals()) if not n.startswith("_") and n not in ("torch", "T", "raw", "scalar_or_tensor", "wrap", "annotations")]
+
+
+# static programs record these as single ops (their bodies compute on raw tensors / read values; framework/recording.py)
+from ..framework.recording import make_recordable as _make_recordable  # noqa: E402
+
+_make_recordable(globals(), ['equal_all'])

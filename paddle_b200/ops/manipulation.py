@@ -524,3 +524,9 @@ def block_diag(inputs, name=None):
 
 __all__ = [n for n in list(globals()) if not n.startswith("_") and n not in (
     "np", "torch", "builtins", "T", "ax", "dt", "raw", "shp", "to_int", "to_tensor", "wrap", "annotations")]
+
+
+# static programs record these as single ops (their bodies compute on raw tensors / read values; framework/recording.py)
+from ..framework.recording import make_recordable as _make_recordable  # noqa: E402
+
+_make_recordable(globals(), ['unique', 'unique_consecutive'])

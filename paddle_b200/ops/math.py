@@ -516,3 +516,9 @@ for _n in _INPLACE:
 
 __all__ = [n for n in list(globals()) if not n.startswith("_") and n not in (
     "np", "torch", "T", "ax", "binary_args", "dt", "raw", "scalar_or_tensor", "shp", "to_int", "to_tensor", "wrap", "annotations")]
+
+
+# static programs record these as single ops (their bodies compute on raw tensors / read values; framework/recording.py)
+from ..framework.recording import make_recordable as _make_recordable  # noqa: E402
+
+_make_recordable(globals(), ['allclose', 'histogramdd'])

@@ -129,3 +129,9 @@ def randn_like(x, dtype=None, name=None):
 
 
 __all__ = [n for n in list(globals()) if not n.startswith("_") and n not in ("torch", "T", "dev", "dt", "raw", "shp", "to_int", "wrap", "annotations")]
+
+
+# static programs record these as single ops (their bodies compute on raw tensors / read values; framework/recording.py)
+from ..framework.recording import make_recordable as _make_recordable  # noqa: E402
+
+_make_recordable(globals(), ['binomial', 'standard_gamma'])

@@ -603,3 +603,50 @@ def test_dataloader_feed_dicts_dynamic_batch_training_and_the_baked_extent_hint(
             exe.run(frozen, feed={"z": np.zeros((3, 4), "float32")}, fetch_list=[flat])
     finally:
         paddle.disable_static()
+
+
+def test_no_public_op_leaks_out_of_a_recorded_program():
+    """Sweep: call every public function of paddle.nn.functional / paddle.* that accepts a simple argument pattern on a program variable; its
+    tensor results must be values of the program (a body that computes on raw tensors would bake the placeholder's zeros in)."""
+    import inspect
+    import warnings
+
+    import torch
+
+    import paddle_b200 as paddle
+    from paddle_b200 import static
+
+    legit = {"to_tensor", "from_numpy", "get_rng_state", "rank", "get_cuda_rng_state"}          # constants by definition
+    skip = {"enable_static", "disable_static", "seed", "set_device", "save", "load", "summary", "flops", "set_flags", "set_default_dtype", "set_grad_enabled",
+            "set_printoptions", "manual_seed", "batch", "no_grad", "enable_grad", "set_cuda_rng_state", "set_rng_state", "disable_signal_handler", "check_shape",
+            "install_as_paddle"}
+    patterns = (((4, 8), lambda x: (x,)), ((1, 2, 4, 4), lambda x: (x,)), ((4, 8), lambda x: (x, x * 0.5 + 0.1)), ((1, 2, 4, 4), lambda x: (x, 2)), ((4, 8), lambda x: (x, 1)))
+    leaks, probed = [], 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for label, mod in (("F", paddle.nn.functional), ("paddle", paddle)):
+            names = [n for n in getattr(mod, "__all__", dir(mod)) if not n.startswith("_") and hasattr(mod, n)]
+            for n in names:
+                fn = getattr(mod, n)
+                if n in skip or not callable(fn) or inspect.isclass(fn) or inspect.ismodule(fn):
+                    continue
+                for shape, args in patterns:
+                    paddle.enable_static()
+                    try:
+                        main = static.Program()
+                        with static.program_guard(main):
+                            x = static.data("x", list(shape), "float32")
+                            try:
+                                out = fn(*args(x))
+                            except BaseException:  # noqa: BLE001  (this argument pattern does not fit the function)
+                                continue
+                            outs = [o for o in (out if isinstance(out, (list, tuple)) else [out]) if isinstance(o, torch.Tensor)]
+                            if not outs:
+                                continue
+                            probed += 1
+                            if n not in legit and not all(id(o) in main._fetch_alias for o in outs):
+                                leaks.append(f"{label}.{n}")
+                            break
+                    finally:
+                        paddle.disable_static()
+    assert probed > 350 and leaks == [], leaks
