@@ -159,3 +159,9 @@ def __getattr__(name):
     if name == "inference":   # paddle.incubate.inference: the predictor API lives in paddle_b200.inference
         return importlib.import_module("paddle_b200.inference")
     raise AttributeError(name)
+
+
+# static programs record these as single ops (their bodies compute on raw tensors; framework/recording.py)
+from ..framework.recording import make_recordable as _make_recordable  # noqa: E402
+
+_make_recordable(globals(), ["softmax_mask_fuse", "softmax_mask_fuse_upper_triangle", "identity_loss"])
