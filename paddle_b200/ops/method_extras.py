@@ -77,7 +77,7 @@ def _retain_grads(self):
 
 
 def _matrix_transpose(self, name=None):
-    return _raw(self).mT.as_subclass(Tensor)
+    return torch.transpose(self, -2, -1)               # on the tensor itself: recorded as an op in static programs
 
 
 def _is_same_shape(self, other):
