@@ -29,10 +29,97 @@ def _w(t):
     return t.as_subclass(Tensor) if isinstance(t, torch.Tensor) and not isinstance(t, Tensor) else t
 
 
+# ---- static programs ---------------------------------------------------------------------------------------------------------------------------
+# The classes below compute through torch.distributions objects built from RAW parameter tensors, which the op tape of a static program cannot
+# see.  While a program is being built, a method call on a distribution is therefore recorded as ONE node that rebuilds the distribution from its
+# constructor arguments (program values among them are references, resolved at run time) and calls the method: log_prob / entropy / kl follow the feeds,
+# and sample / rsample draw anew at every run.
+def _enc(x):
+    if isinstance(x, Distribution) and hasattr(x, "_ctor"):
+        return ("__dist__", type(x), _enc(x._ctor[0]), _enc(x._ctor[1]))
+    if isinstance(x, (list, tuple)):
+        return type(x)(_enc(i) for i in x)
+    if isinstance(x, dict):
+        return {k: _enc(v) for k, v in x.items()}
+    return x
+
+
+def _dec(x):
+    if isinstance(x, tuple) and len(x) == 4 and x[0] == "__dist__":
+        return x[1](*_dec(x[2]), **_dec(x[3]))
+    if isinstance(x, (list, tuple)):
+        return type(x)(_dec(i) for i in x)
+    if isinstance(x, dict):
+        return {k: _dec(v) for k, v in x.items()}
+    return x
+
+
+def _replay(spec, name, margs, mkw):
+    d = _dec(spec)
+    attr = getattr(d, name)
+    return attr(*_dec(margs), **_dec(mkw)) if callable(attr) else attr
+
+
+def _replay_kl(spec_p, spec_q):
+    return kl_divergence(_dec(spec_p), _dec(spec_q))
+
+
+def _recording_program():
+    from ..framework import recording
+
+    return recording.current[0] if recording._inside[0] == 0 else None
+
+
+def _in_program(self, name, a, k, fn):
+    prog = _recording_program()
+    if prog is not None and hasattr(self, "_ctor"):
+        from ..framework import recording
+
+        spec, ea, ek = _enc(self), _enc(a), _enc(k)
+        sampler = name in ("sample", "rsample")
+        if sampler or prog._touches_program((spec, ea, ek)):
+            rec = recording.recordable(_replay, always=sampler)
+            return rec(spec, name, ea, ek)
+    return fn(self, *a, **k)
+
+
+def _guard_method(name, fn):
+    import functools
+
+    @functools.wraps(fn)
+    def method(self, *a, **k):
+        return _in_program(self, name, a, k, fn)
+
+    method._b200_guarded = True
+    return method
+
+
+_GUARDED = ("sample", "rsample", "log_prob", "prob", "probs", "entropy", "cdf", "icdf")
+
+
 class Distribution:
     """Base class. Parity: distribution/distribution.py."""
 
     _d = None
+
+    def __init_subclass__(cls, **kw):
+        super().__init_subclass__(**kw)
+        init = cls.__dict__.get("__init__")
+        if init is not None and not getattr(init, "_b200_captures", False):
+            import functools
+
+            @functools.wraps(init)
+            def __init__(self, *a, **k):
+                if not hasattr(self, "_ctor"):                     # the outermost constructor's arguments describe the object
+                    self._ctor = (a, k)
+                init(self, *a, **k)
+
+            __init__._b200_captures = True
+            cls.__init__ = __init__
+        for name in _GUARDED:
+            fn = cls.__dict__.get(name)
+            if callable(fn) and not getattr(fn, "_b200_guarded", False):
+                setattr(cls, name, _guard_method(name, fn))
 
     def __init__(self, batch_shape=(), event_shape=()):
         self._batch_shape, self._event_shape = tuple(batch_shape), tuple(event_shape)
@@ -47,15 +134,15 @@ class Distribution:
 
     @property
     def mean(self):
-        return _w(self._d.mean)
+        return _in_program(self, "mean", (), {}, lambda s: _w(s._d.mean))
 
     @property
     def variance(self):
-        return _w(self._d.variance)
+        return _in_program(self, "variance", (), {}, lambda s: _w(s._d.variance))
 
     @property
     def stddev(self):
-        return _w(self._d.stddev)
+        return _in_program(self, "stddev", (), {}, lambda s: _w(s._d.stddev))
 
     def sample(self, shape=()):
         with torch.no_grad():
@@ -83,6 +170,12 @@ class Distribution:
 
     def kl_divergence(self, other):
         return kl_divergence(self, other)
+
+
+for _n in _GUARDED:
+    if callable(Distribution.__dict__.get(_n)) and not getattr(Distribution.__dict__[_n], "_b200_guarded", False):
+        setattr(Distribution, _n, _guard_method(_n, Distribution.__dict__[_n]))
+Distribution.probs = Distribution.prob
 
 
 class ExponentialFamily(Distribution):
@@ -390,6 +483,13 @@ def register_kl(cls_p, cls_q):
 
 
 def kl_divergence(p, q):
+    prog = _recording_program()
+    if prog is not None and hasattr(p, "_ctor") and hasattr(q, "_ctor"):
+        sp, sq = _enc(p), _enc(q)
+        if prog._touches_program((sp, sq)):
+            from ..framework import recording
+
+            return recording.recordable(_replay_kl)(sp, sq)
     for (cp, cq), fn in _KL_REGISTRY.items():
         if isinstance(p, cp) and isinstance(q, cq):
             return fn(p, q)

@@ -25,11 +25,16 @@ def _rewrap(o):
     return o
 
 
-def recordable(fn):
+def recordable(fn=None, *, always=False):
+    """Decorator.  `always`: record the call even when no argument is a value of the program - for ops whose result must be produced anew at every
+    run although nothing feeds them (random sampling: a program would otherwise bake ONE sample in)."""
+    if fn is None:
+        return lambda f: recordable(f, always=always)
+
     @functools.wraps(fn)
     def wrapper(*args, **kwargs):
         prog = current[0]
-        if prog is None or _inside[0] or not (prog._touches_program(args) or prog._touches_program(kwargs)):
+        if prog is None or _inside[0] or not (always or prog._touches_program(args) or prog._touches_program(kwargs)):
             return fn(*args, **kwargs)
         _inside[0] += 1
         try:
@@ -44,12 +49,12 @@ def recordable(fn):
     return wrapper
 
 
-def make_recordable(namespace, names):
+def make_recordable(namespace, names, always=False):
     """Wrap the named module-level functions of `namespace` (a module's globals()) as recordable ops.  For modules whose public functions compute on
     raw tensors (fast paths into kernels / index arithmetic) - without this a static program would silently bake its placeholder values in."""
     for name in names:
         fn = namespace.get(name)
         if callable(fn) and not isinstance(fn, type) and not getattr(fn, "_b200_recordable", False):
-            w = recordable(fn)
+            w = recordable(fn, always=always)
             w._b200_recordable = True
             namespace[name] = w

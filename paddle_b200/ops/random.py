@@ -134,4 +134,6 @@ __all__ = [n for n in list(globals()) if not n.startswith("_") and n not in ("to
 # static programs record these as single ops (their bodies compute on raw tensors / read values; framework/recording.py)
 from ..framework.recording import make_recordable as _make_recordable  # noqa: E402
 
-_make_recordable(globals(), ['binomial', 'standard_gamma'])
+# samplers: every run of a program draws anew, also when nothing of the program feeds them (constant probabilities, shapes only) - recorded unconditionally
+_make_recordable(globals(), ['rand', 'randn', 'standard_normal', 'normal', 'uniform', 'randint', 'randperm', 'log_normal', 'binomial', 'standard_gamma', 'bernoulli',
+                             'poisson', 'multinomial', 'randint_like', 'rand_like', 'randn_like'], always=True)

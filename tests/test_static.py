@@ -650,3 +650,68 @@ def test_no_public_op_leaks_out_of_a_recorded_program():
                     finally:
                         paddle.disable_static()
     assert probed > 350 and leaks == [], leaks
+
+
+def test_samplers_draw_anew_at_every_run_of_a_program():
+    """rand / randn / randint / uniform / normal / randperm / bernoulli / multinomial inside a program are ops, not constants: two runs differ, a
+    re-seeded run repeats."""
+    import numpy as np
+
+    import paddle_b200 as paddle
+    from paddle_b200 import static
+
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            x = static.data("x", [4, 8], "float32")
+            outs = [x + paddle.rand([4, 8]), x + paddle.randn([4, 8]), x + paddle.randint(0, 1000, [4, 8]).astype("float32"), x + paddle.uniform([4, 8]),
+                    x + paddle.normal(0.0, 1.0, [4, 8]), x[0] + paddle.randperm(8).astype("float32"), x + paddle.bernoulli(paddle.full([4, 8], 0.5)),
+                    x[0, :5] + paddle.multinomial(paddle.ones([50]), 5).astype("float32")]
+        exe = static.Executor()
+        xv = np.zeros((4, 8), "float32")
+        a = exe.run(main, feed={"x": xv}, fetch_list=outs)
+        b = exe.run(main, feed={"x": xv}, fetch_list=outs)
+        assert all(not np.allclose(p, q) for p, q in zip(a, b))
+        paddle.seed(11)
+        c = exe.run(main, feed={"x": xv}, fetch_list=outs)
+        paddle.seed(11)
+        d = exe.run(main, feed={"x": xv}, fetch_list=outs)
+        assert all(np.allclose(p, q) for p, q in zip(c, d))
+    finally:
+        paddle.disable_static()
+
+
+def test_distributions_in_a_program_follow_the_feeds_and_resample():
+    """Distribution objects wrap torch.distributions built from raw tensors; in a program a method call is one recorded node that rebuilds the
+    distribution from its constructor arguments at run time (nested distributions included)."""
+    import numpy as np
+
+    import paddle_b200 as paddle
+    from paddle_b200 import static
+
+    D = paddle.distribution
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            x = static.data("x", [4], "float32")
+            free = D.Normal(0.0, 1.0).sample([4]) + x                       # nothing of the program feeds it: still one draw per run
+            d = D.Normal(x, 1.0)
+            outs = [free, d.sample([2]), D.Categorical(paddle.ones([50])).sample([4]).astype("float32") + x, d.log_prob(paddle.zeros([4])), d.mean,
+                    D.kl_divergence(d, D.Normal(0.0, 1.0)), D.Independent(D.Normal(x, 1.0), 1).log_prob(paddle.zeros([4])), d.entropy()]
+        exe = static.Executor()
+        xv = np.arange(4, dtype="float32")
+        a = exe.run(main, feed={"x": xv}, fetch_list=outs)
+        b = exe.run(main, feed={"x": xv}, fetch_list=outs)
+        assert all(not np.allclose(p, q) for p, q in zip(a[:3], b[:3]))       # samples
+        lp = -0.5 * xv ** 2 - 0.5 * np.log(2 * np.pi)
+        np.testing.assert_allclose(a[3], lp, atol=1e-5)
+        np.testing.assert_allclose(a[4], xv)
+        np.testing.assert_allclose(a[5], 0.5 * xv ** 2, atol=1e-5)
+        np.testing.assert_allclose(a[6], lp.sum(), atol=1e-4)
+        np.testing.assert_allclose(a[7], np.full(4, 0.5 * np.log(2 * np.pi * np.e)), atol=1e-5)
+    finally:
+        paddle.disable_static()
+    n = D.Normal(0.0, 2.0)                                                    # dynamic mode: unchanged
+    assert n.sample([3]).shape == [3] and abs(float(n.entropy()) - 0.5 * np.log(2 * np.pi * np.e * 4)) < 1e-5
