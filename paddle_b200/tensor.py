@@ -379,7 +379,11 @@ class Tensor(torch.Tensor):
         return torch.Tensor.register_hook(self, hook)
 
     def set_value(self, value):
-        with torch.no_grad():
+        """Immediate assignment (not an op of a program being built): the value has to be concrete."""
+        if _rec.current[0] is not None and isinstance(value, torch.Tensor) and _rec._inside[0] == 0 and id(value) in _rec.current[0]._vids:
+            raise RuntimeError("set_value needs a concrete value, got a value of the program under construction (it has no data yet): pass a numpy array / a tensor "
+                               "built outside program_guard, or assign through the scope after the program ran")
+        with torch.no_grad(), torch._C.DisableTorchFunction():          # an action on this tensor now, never a recorded op
             if not isinstance(value, torch.Tensor):
                 value = torch.as_tensor(np.asarray(value))
             torch.Tensor.copy_(self, value.to(device=self.device).reshape(self.size()))

@@ -590,10 +590,11 @@ def test_batch_norm_inference_folds_into_the_pointwise_tail():
     """conv -> BN(eval) -> relu -> + skip -> relu: everything after the convolution is one kernel; the per-channel statistics [C] are read as [C, 1, 1]."""
     paddle.seed(0)
     conv, bn = paddle.nn.Conv2D(4, 8, 3, padding=1), paddle.nn.BatchNorm2D(8)
-    bn._mean.set_value(paddle.randn([8]) * 0.3)
-    bn._variance.set_value(paddle.rand([8]) + 0.5)
-    bn.weight.set_value(paddle.randn([8]))
-    bn.bias.set_value(paddle.randn([8]))
+    rs = np.random.RandomState(3)
+    bn._mean.set_value(rs.randn(8).astype("float32") * 0.3)
+    bn._variance.set_value(rs.rand(8).astype("float32") + 0.5)
+    bn.weight.set_value(rs.randn(8).astype("float32"))
+    bn.bias.set_value(rs.randn(8).astype("float32"))
     conv.eval()
     bn.eval()
     x = np.random.default_rng(1).standard_normal((2, 4, 6, 6)).astype(np.float32)

@@ -345,11 +345,12 @@ def test_conv_bn_fuse_in_the_predictor(tmp_path):
             x = static.data("x", [2, 3, 10, 10], "float32")
             c1, b1 = paddle.nn.Conv2D(3, 8, 3, padding=1), paddle.nn.BatchNorm2D(8)
             c2, b2 = paddle.nn.Conv2D(8, 8, 3, padding=1, bias_attr=False), paddle.nn.BatchNorm2D(8)
+            rs = np.random.RandomState(5)
             for bn in (b1, b2):
-                bn._mean.set_value(paddle.randn([8]) * 0.2)
-                bn._variance.set_value(paddle.rand([8]) + 0.5)
-                bn.weight.set_value(paddle.randn([8]))
-                bn.bias.set_value(paddle.randn([8]))
+                bn._mean.set_value(rs.randn(8).astype("float32") * 0.2)          # concrete values: set_value is an assignment, not an op of the program
+                bn._variance.set_value(rs.rand(8).astype("float32") + 0.5)
+                bn.weight.set_value(rs.randn(8).astype("float32"))
+                bn.bias.set_value(rs.randn(8).astype("float32"))
                 bn.eval()
             h = paddle.nn.functional.relu(b1(c1(x)))
             y = paddle.nn.functional.relu(b2(c2(h)) + h)
