@@ -56,7 +56,9 @@ def _select(pred, a, b, name):
             ta, tb = ta.to(dt), tb.to(dt)
         p = pred.reshape([1] * max(ta.dim(), tb.dim())) if pred.numel() == 1 else pred
         out = torch.where(p.to(torch.bool), ta, tb)
-        return out.as_subclass(type(a)) if _is_tensor(a) and type(a) is not torch.Tensor else out
+        if _is_tensor(a) and type(a) is not torch.Tensor and not isinstance(out, type(a)):
+            return out.as_subclass(type(a))
+        return out                       # unchanged object: a program being recorded tracks its values by identity
     if isinstance(a, (list, tuple)) and isinstance(b, (list, tuple)) and len(a) == len(b):
         return type(a)(_select(pred, x, y, name) for x, y in zip(a, b))
     if isinstance(a, dict) and isinstance(b, dict) and a.keys() == b.keys():

@@ -755,3 +755,24 @@ def test_build_strategy_build_cinn_pass():
         got = f(t)
     assert f.cinn_report(t) is not None
     np.testing.assert_allclose(got.numpy(), a, rtol=2e-5, atol=1e-7)
+
+
+def _branchy(x):
+    if x.sum() > 0:
+        y = paddle.exp(x) * 2.0 + 1.0
+    else:
+        y = paddle.tanh(x) - 1.0
+    return y * 0.5 + F.sigmoid(y)
+
+
+def test_tensor_dependent_branch_compiles_to_one_kernel():
+    """dy2static turns the `if` into run-both-and-select; under backend="CINN" both branches, the select and the tail are one generated kernel."""
+    f = paddle.jit.to_static(_branchy, backend="CINN")
+    for sign in (1.0, -1.0):
+        t = paddle.to_tensor(np.abs(np.random.default_rng(0).standard_normal((3, 4))).astype("float32") * sign)
+        with paddle.no_grad():
+            f(t)
+            got = f(t)
+        rep = f.cinn_report(t)
+        assert rep is not None and len(rep.groups) == 1 and "where" in rep.groups[0]["ops"] and len(rep.groups[0]["ops"]) >= 8
+        np.testing.assert_allclose(got.numpy(), _branchy(t).numpy(), rtol=1e-6, atol=1e-6)
