@@ -31,11 +31,24 @@ __all__ = ["convert_to_static", "get_code", "ProgramTranslator", "convert_ifelse
 
 
 class _Undefined:
+    """Value of a name that a branch did not assign.  After a tensor-dependent `if` a name assigned in ONE branch only stays undefined - which is
+    fine as long as the code does not use it (a branch-local temporary); any use fails with the name in the message."""
+
+    def __init__(self, name=None):
+        self._name = name
+
     def __repr__(self):
         return "UNDEFINED"
 
     def __bool__(self):
         return False
+
+    def _fail(self, *a, **k):
+        raise NameError(f"dy2static: variable '{self._name}' is assigned in only one branch of a tensor-dependent `if` and used after it; give it a value "
+                        "before the `if`")
+
+    __getattr__ = __call__ = __add__ = __radd__ = __sub__ = __rsub__ = __mul__ = __rmul__ = __truediv__ = __rtruediv__ = __getitem__ = __iter__ = __neg__ = \
+        __matmul__ = __rmatmul__ = __lt__ = __gt__ = __le__ = __ge__ = __float__ = __int__ = __len__ = _fail
 
 
 UNDEFINED = _Undefined()
@@ -46,8 +59,8 @@ def _is_tensor(x):
 
 
 def _select(pred, a, b, name):
-    if a is UNDEFINED or b is UNDEFINED:
-        raise ValueError(f"dy2static: variable '{name}' is only assigned in one branch of a tensor-dependent `if`; give it a value before the `if`")
+    if isinstance(a, _Undefined) or isinstance(b, _Undefined):
+        return _Undefined(name)              # a branch-local temporary: legal unless the code uses it after the `if`
     if _is_tensor(a) or _is_tensor(b):
         ta = a if _is_tensor(a) else torch.as_tensor(a, device=b.device, dtype=b.dtype)
         tb = b if _is_tensor(b) else torch.as_tensor(b, device=a.device, dtype=a.dtype)
@@ -326,11 +339,60 @@ class _Transformer(ast.NodeTransformer):
         return node
 
 
+def _contains_return(stmts):
+    class V(ast.NodeVisitor):
+        found = False
+
+        def visit_Return(self, node):
+            self.found = True
+
+        def visit_FunctionDef(self, node):          # a nested function's returns are its own
+            pass
+
+        visit_AsyncFunctionDef = visit_Lambda = visit_FunctionDef
+
+    v = V()
+    for s in stmts:
+        v.visit(s)
+    return v.found
+
+
+def _normalize_early_returns(stmts, counter):
+    """`if c: ...; return A` followed by `...; return B`  ->  `if c: ...; r = A  else: ...; r = B` + `return r`.
+    Only the top-level shape: the `if` body ends with its single `return`, there is no `else` (or one that ends with its single `return`), and the
+    statements after it end the function.  The rewritten `if` has no `return` inside, so the converter can treat a tensor condition
+    (run both branches, select)."""
+    for i, st in enumerate(stmts):
+        if not isinstance(st, ast.If) or not st.body or not isinstance(st.body[-1], ast.Return) or _contains_return(st.body[:-1]):
+            continue
+        if _contains_return(stmts[:i]):
+            return stmts
+        rest = stmts[i + 1:]
+        if st.orelse:
+            if rest or not isinstance(st.orelse[-1], ast.Return) or _contains_return(st.orelse[:-1]):
+                return stmts
+            other = list(st.orelse)
+        else:
+            other = _normalize_early_returns(list(rest), counter)
+            if not other or not isinstance(other[-1], ast.Return) or _contains_return(other[:-1]):
+                return stmts
+        counter[0] += 1
+        name = f"_jst_ret_{counter[0]}"
+
+        def assign(ret):
+            return ast.Assign(targets=[ast.Name(id=name, ctx=ast.Store())], value=ret.value if ret.value is not None else ast.Constant(value=None))
+
+        new_if = ast.If(test=st.test, body=st.body[:-1] + [assign(st.body[-1])], orelse=other[:-1] + [assign(other[-1])])
+        return stmts[:i] + [new_if, ast.Return(value=ast.Name(id=name, ctx=ast.Load()))]
+    return stmts
+
+
 def _transform_source(fn):
     src = textwrap.dedent(inspect.getsource(fn))
     tree = ast.parse(src)
     fdef = next(n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.AsyncFunctionDef)))
     fdef.decorator_list = []          # the decorator (to_static itself) must not run again
+    fdef.body = _normalize_early_returns(list(fdef.body), [0])
     tr = _Transformer()
     tree = tr.visit(tree)
     ast.fix_missing_locations(tree)

@@ -776,3 +776,32 @@ def test_tensor_dependent_branch_compiles_to_one_kernel():
         rep = f.cinn_report(t)
         assert rep is not None and len(rep.groups) == 1 and "where" in rep.groups[0]["ops"] and len(rep.groups[0]["ops"]) >= 8
         np.testing.assert_allclose(got.numpy(), _branchy(t).numpy(), rtol=1e-6, atol=1e-6)
+
+
+def _early(x, k=2):
+    z = x * 1.5
+    if z.sum() > 0:                # tensor condition with an early return and a branch-local temporary
+        w = paddle.exp(z)
+        return w + 1.0
+    if k > 1:                      # python condition: ordinary semantics
+        return paddle.tanh(z) - k
+    return z
+
+
+def test_early_returns_are_normalised_and_compile():
+    """`if c: ...; return A` + `...; return B` becomes an if / else that assigns the result, so a tensor condition converts (run both, select);
+    a name assigned in one branch only stays undefined unless it is used."""
+    from paddle_b200.jit.dy2static import get_code
+
+    code = get_code(_early)
+    assert "convert_ifelse" in code and "_jst_ret_" in code
+    f = paddle.jit.to_static(_early, backend="CINN")
+    plain = paddle.jit.to_static(_early)
+    for sign in (1.0, -1.0):
+        t = paddle.to_tensor(np.abs(np.random.default_rng(1).standard_normal((3, 4))).astype("float32") * sign)
+        with paddle.no_grad():
+            f(t)
+            got = f(t)
+        assert f.cinn_report(t) is not None and len(f.cinn_report(t).groups) >= 1
+        np.testing.assert_allclose(got.numpy(), _early(t).numpy(), rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(plain(t).numpy(), _early(t).numpy(), rtol=1e-6, atol=1e-6)
