@@ -18,7 +18,8 @@ import torch
 from ..tensor import Tensor
 from . import codegen
 
-_CACHE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "_build_cache", "cinn")
+# in-tree by default (a warm cache travels with the package); B200_CINN_CACHE points it elsewhere (the test-suite uses a temporary directory)
+_CACHE = os.environ.get("B200_CINN_CACHE") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "_build_cache", "cinn")
 _LOCK = threading.Lock()
 _LOADED = {}
 _TORCH_DT = {"float32": torch.float32, "float64": torch.float64, "float16": torch.float16, "bfloat16": torch.bfloat16, "int32": torch.int32, "int64": torch.int64,
