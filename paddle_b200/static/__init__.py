@@ -72,6 +72,13 @@ class _Node:
             pickle.dumps(fn)
             enc = ("obj", fn)
         except Exception:  # noqa: BLE001
+            inner = getattr(fn, "__wrapped__", None)         # a recordable wrapper made at call time: at run time its body is all that matters
+            if inner is not None:
+                try:
+                    pickle.dumps(inner)
+                    return (("obj", inner), self.args, self.kwargs, self.outs, self.kind)
+                except Exception:  # noqa: BLE001
+                    pass
             name = getattr(fn, "__name__", None)
             objclass = getattr(fn, "__objclass__", None)
             owner = None

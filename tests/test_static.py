@@ -715,3 +715,26 @@ def test_distributions_in_a_program_follow_the_feeds_and_resample():
         paddle.disable_static()
     n = D.Normal(0.0, 2.0)                                                    # dynamic mode: unchanged
     assert n.sample([3]).shape == [3] and abs(float(n.entropy()) - 0.5 * np.log(2 * np.pi * np.e * 4)) < 1e-5
+
+
+def test_programs_with_samplers_and_distribution_nodes_save_and_load(tmp_path):
+    import numpy as np
+
+    import paddle_b200 as paddle
+    from paddle_b200 import static
+
+    paddle.enable_static()
+    try:
+        main = static.Program()
+        with static.program_guard(main):
+            x = static.data("x", [-1, 4], "float32")
+            y = x + paddle.randn([4]) + paddle.distribution.Normal(0.0, 1.0).sample([4])
+            y = paddle.nn.functional.interpolate(y.reshape([1, 1, -1, 4]), scale_factor=2).reshape([-1, 8])
+        exe = static.Executor()
+        static.save_inference_model(str(tmp_path / "m"), [x], [y], exe, program=main)
+        prog, feeds, fetch = static.load_inference_model(str(tmp_path / "m"), exe)
+        feed = {feeds[0]: np.ones((3, 4), "float32")}
+        a, b = exe.run(prog, feed=feed, fetch_list=fetch)[0], exe.run(prog, feed=feed, fetch_list=fetch)[0]
+        assert a.shape == (6, 8) and not np.allclose(a, b)          # dynamic batch, per-run sampling survive the round trip
+    finally:
+        paddle.disable_static()
