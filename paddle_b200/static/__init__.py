@@ -1007,28 +1007,36 @@ def load_from_file(path):
         return f.read()
 
 
+class _PrintOp:
+    """The body of a `Print` node (a picklable object, so programs with prints can be saved)."""
+
+    __name__ = "print"
+
+    def __init__(self, first_n, message, summarize, show_type, show_shape):
+        self.first_n, self.message, self.summarize, self.show_type, self.show_shape, self.n = first_n, message, summarize, show_type, show_shape, 0
+
+    def __call__(self, t):
+        from ..framework import recording
+
+        if recording._inside[0] == 0 and (self.first_n < 0 or self.n < self.first_n):      # _inside > 0: the recorder is only taking the example output
+            self.n += 1
+            r = t.as_subclass(torch.Tensor) if isinstance(t, torch.Tensor) else t
+            head = [self.message or ""]
+            if self.show_shape and isinstance(r, torch.Tensor):
+                head.append(f"shape={list(r.shape)}")
+            if self.show_type and isinstance(r, torch.Tensor):
+                head.append(f"dtype={str(r.dtype).replace('torch.', '')}")
+            flat = r.detach().reshape(-1)[: max(int(self.summarize), 0) if self.summarize and self.summarize > 0 else None] if isinstance(r, torch.Tensor) else r
+            print(" ".join(h for h in head if h), "data:", flat.tolist() if isinstance(flat, torch.Tensor) else flat)
+        return t * 1 if isinstance(t, torch.Tensor) else t
+
+
 def Print(input, first_n=-1, message=None, summarize=20, print_tensor_name=True, print_tensor_type=True, print_tensor_shape=True,
           print_tensor_layout=True, print_tensor_lod=True, print_phase="both"):
     """Prints the tensor when the op RUNS (in a program: at every Executor.run, up to `first_n` times), not while the program is being built."""
     from ..framework import recording
 
-    state = {"n": 0}
-
-    def _print_op(t):
-        if recording._inside[0] == 0 and (first_n < 0 or state["n"] < first_n):          # _inside > 0: the recorder is only taking the example output
-            state["n"] += 1
-            r = t.as_subclass(torch.Tensor) if isinstance(t, torch.Tensor) else t
-            head = [message or ""]
-            if print_tensor_shape and isinstance(r, torch.Tensor):
-                head.append(f"shape={list(r.shape)}")
-            if print_tensor_type and isinstance(r, torch.Tensor):
-                head.append(f"dtype={str(r.dtype).replace('torch.', '')}")
-            flat = r.detach().reshape(-1)[: max(int(summarize), 0) if summarize and summarize > 0 else None] if isinstance(r, torch.Tensor) else r
-            print(" ".join(h for h in head if h), "data:", flat.tolist() if isinstance(flat, torch.Tensor) else flat)
-        return t * 1 if isinstance(t, torch.Tensor) else t
-
-    _print_op.__name__ = "print"
-    return recording.recordable(_print_op)(input)
+    return recording.recordable(_PrintOp(first_n, message, summarize, print_tensor_type, print_tensor_shape))(input)
 
 
 def py_func(func, x, out, backward_func=None, skip_vars_in_backward_input=None):
